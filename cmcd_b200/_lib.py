@@ -1,0 +1,105 @@
+"""ctypes binding of libcmcd_b200.so (include/cmcd_b200.h).  Fails loudly when the library is absent."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcmcd_b200.so")
+
+MODE = {"MCD_ULA": 0, "MCD_ULA_sn": 1, "MCD_CAIS_sn": 2, "MCD_CAIS_var_sn": 3}
+TARGET = {"gmm": 0, "many_gmm": 1, "funnel": 2, "lgcp": 3}
+ARCH = {None: 0, "none": 0, "geffner": 1, "dds": 2}
+MIX_STRIDE = 6
+
+_fp = C.c_void_p  # device pointers travel as integers
+
+
+class CmcdNet(C.Structure):
+    _fields_ = [("arch", C.c_int32), ("hidden", C.c_int32), ("hidden_pad", C.c_int32), ("n_rows", C.c_int32),
+                ("U1", _fp), ("U2", _fp), ("U3", _fp), ("W2", _fp), ("W3", _fp), ("c1", _fp), ("c2", _fp), ("c3", _fp),
+                ("out_scale", C.c_float), ("out_clip", C.c_float)]
+
+
+class CmcdNetGrad(C.Structure):
+    _fields_ = [(n, _fp) for n in ("U1", "U2", "U3", "W2", "W3", "c1", "c2", "c3", "out_scale")]
+
+
+class CmcdTarget(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("ncomp", C.c_int32), ("scale", C.c_float), ("invalid_below", C.c_float),
+                ("mix", _fp), ("lgcp_kinv", _fp), ("lgcp_linv", _fp), ("lgcp_counts", _fp),
+                ("lgcp_mu0", C.c_float), ("lgcp_log_norm", C.c_float), ("lgcp_bin_area", C.c_float)]
+
+
+class CmcdBridgeDesc(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("dim", C.c_int32), ("nbridges", C.c_int32), ("n_particles", C.c_int32),
+                ("clip_target", C.c_float), ("clip_q", C.c_float)]
+
+
+EXPORTS = {
+    "cmcd_last_error": (C.c_char_p, []),
+    "cmcd_version": (C.c_int, []),
+    "cmcd_num_sms": (C.c_int, []),
+    "cmcd_bridge_fwd": (C.c_int, [C.POINTER(CmcdBridgeDesc), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNet),
+                                  C.POINTER(CmcdTarget), _fp, _fp, _fp]),
+    "cmcd_bridge_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(CmcdBridgeDesc), C.POINTER(CmcdNet)]),
+    "cmcd_bridge_bwd": (C.c_int, [C.POINTER(CmcdBridgeDesc), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNet),
+                                  C.POINTER(CmcdTarget), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNetGrad),
+                                  _fp, C.c_size_t]),
+    "cmcd_loss_stats": (C.c_int, [_fp, _fp, C.c_int64, _fp]),
+    "cmcd_batched_elbo_lnz": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
+    "cmcd_bridge_fwd_host": (C.c_int, [C.POINTER(CmcdBridgeDesc), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNet),
+                                       C.POINTER(CmcdTarget), _fp, _fp, _fp, _fp, _fp]),
+    "cmcd_target_eval": (C.c_int, [C.POINTER(CmcdTarget), C.c_int32, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp]),
+    "cmcd_threefry2x32": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp, _fp]),
+    "cmcd_particle_noise": (C.c_int, [_fp, _fp, C.c_int64, C.c_int32, C.c_int32, _fp, _fp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the CDLL.  No fallback: a missing library is an error."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing -- build it with `python -m cmcd_b200.build` (nvcc, sm_100a). "
+                "cmcd_b200 has no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(l, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().cmcd_last_error().decode()
+        if "not implemented" in msg.lower() or "not in the registry" in msg or "no small-d" in msg:
+            raise NotImplementedError(msg)
+        raise RuntimeError(f"cmcd_b200 error {rc}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "cmcd_b200 needs contiguous tensors"
+    return t.data_ptr()
+
+
+def require_cuda(*tensors):
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("cmcd_b200: no CUDA device -- the bridge hot path has no CPU fallback")
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cmcd_b200: tensors must live on a CUDA device (no CPU fallback)")
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,172 @@
+// C ABI of libcmcd_b200.so (declared in include/cmcd_b200.h): argument validation and
+// marshalling into the kernel launchers.  No torch types, no allocation, enqueue-only.
+#include <cstdarg>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace cmcd {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int launch_bridge_fwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sms);
+int launch_bridge_bwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, const float* cot_negw,
+                      float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
+                      const cmcd_net_grad* g_net, void* ws, size_t ws_bytes);
+size_t bridge_bwd_workspace_bytes(int D, int K, int HP, int arch, int num_sms);
+int launch_loss_stats(cudaStream_t st, const float* negw, long long n, float* out4);
+int launch_batched_elbo_lnz(cudaStream_t st, const float* losses, int batches, int n, float* elbo, float* lnz);
+int launch_threefry(cudaStream_t st, const uint32_t* key2, const uint32_t* x0, const uint32_t* x1, long long n, uint32_t* y0, uint32_t* y1);
+int launch_particle_noise(cudaStream_t st, const int32_t* seeds, long long n, int d, int K, float* xi0, float* xi);
+int launch_target_eval(cudaStream_t st, const TargetDesc& t, int D, const float* x, long long n, const float* v,
+                       float* lp, float* score, float* hvp);
+int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStream_t st, int num_sms);
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return g_num_sms;
+}
+
+static int build_args(const cmcd_bridge_desc* d, const int32_t* seeds, const float* vd_mean, const float* vd_logdiag,
+                      const float* betas, const float* eps, const cmcd_net* net, const cmcd_target* tg, BridgeArgs& a) {
+    if (!d || !tg) { set_error("null descriptor"); return 2; }
+    if (d->mode < CMCD_MODE_ULA || d->mode > CMCD_MODE_CAIS_VAR_SN) { set_error("Mode not implemented."); return 2; }
+    if (d->nbridges < 0 || d->n_particles < 0 || d->dim < 1) { set_error("bad sizes N=%d K=%d d=%d", d->n_particles, d->nbridges, d->dim); return 2; }
+    std::memset(&a, 0, sizeof(a));
+    a.mode = d->mode; a.K = d->nbridges; a.N = d->n_particles;
+    a.clip_t = d->clip_target; a.clip_q = d->clip_q;
+    a.seeds = seeds; a.vd_mean = vd_mean; a.vd_logdiag = vd_logdiag; a.betas = betas; a.eps = eps;
+    const bool needs_net = d->mode != CMCD_MODE_ULA && d->nbridges >= 1;
+    if (needs_net && (!net || net->arch == CMCD_ARCH_NONE)) { set_error("mode %d needs a drift network", d->mode); return 2; }
+    if (net && net->arch != CMCD_ARCH_NONE && needs_net) {
+        if (net->arch != CMCD_ARCH_GEFFNER && net->arch != CMCD_ARCH_DDS) { set_error("nn_arch %d not implemented", net->arch); return 2; }
+        if (net->hidden_pad % 8 || net->hidden_pad < net->hidden || net->hidden < 1) { set_error("hidden_pad must be a multiple of 8 and >= hidden"); return 2; }
+        if (net->n_rows < d->nbridges + 1) { set_error("net tables need nbridges+1 rows"); return 2; }
+        a.net.arch = net->arch; a.net.H = net->hidden; a.net.HP = net->hidden_pad; a.net.T = net->n_rows;
+        a.net.U1 = net->U1; a.net.U2 = net->U2; a.net.U3 = net->U3; a.net.W2 = net->W2; a.net.W3 = net->W3;
+        a.net.c1 = net->c1; a.net.c2 = net->c2; a.net.c3 = net->c3;
+        a.net.out_scale = net->out_scale; a.net.out_clip = net->out_clip;
+    } else {
+        a.net.arch = CMCD_ARCH_NONE;
+    }
+    a.tgt.kind = tg->kind; a.tgt.ncomp = tg->ncomp; a.tgt.mix = tg->mix;
+    switch (tg->kind) {
+        case CMCD_TARGET_GMM:
+        case CMCD_TARGET_MANY_GMM:
+            if (d->dim != 2) { set_error("mixture targets are 2-D (model_handler.py:245-249), got dim=%d", d->dim); return 2; }
+            if (tg->ncomp < 1 || tg->ncomp > MIX_MAX || !tg->mix) { set_error("mixture needs 1..%d components", MIX_MAX); return 2; }
+            a.tgt.scale = tg->scale; a.tgt.inv_var = 1.0f / (tg->scale * tg->scale);
+            a.tgt.comp_norm = 0.9189385332046727f + logf(tg->scale);
+            a.tgt.log_mix = -logf((float)tg->ncomp);
+            a.tgt.invalid_below = tg->invalid_below;
+            break;
+        case CMCD_TARGET_FUNNEL:
+            if (d->dim < 2) { set_error("funnel needs dim >= 2"); return 2; }
+            break;
+        case CMCD_TARGET_LGCP:
+            if (!tg->lgcp_kinv || !tg->lgcp_linv || !tg->lgcp_counts) { set_error("lgcp needs kinv/linv/counts"); return 2; }
+            break;
+        default: set_error("target kind %d not in the registry", tg->kind); return 2;
+    }
+    return 0;
+}
+
+}  // namespace cmcd
+
+using namespace cmcd;
+
+extern "C" {
+
+const char* cmcd_last_error(void) { return g_err; }
+int cmcd_version(void) { return 100; }
+int cmcd_num_sms(void) { return num_sms(); }
+
+int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* seeds, const float* vd_mean,
+                    const float* vd_logdiag, const float* betas, const float* eps, const cmcd_net* net,
+                    const cmcd_target* target, float* out_negw, float* out_z, float* traj) {
+    BridgeArgs a;
+    if (int rc = build_args(desc, seeds, vd_mean, vd_logdiag, betas, eps, net, target, a)) return rc;
+    a.out_negw = out_negw; a.out_z = out_z; a.traj = traj;
+    if (a.N == 0) return 0;
+    const int sms = num_sms();
+    if (sms <= 0) { set_error("no CUDA device"); return 1; }
+    if (target->kind == CMCD_TARGET_LGCP) return launch_wide_fwd(a, target, desc->dim, (cudaStream_t)stream, sms);
+    return launch_bridge_fwd(a, desc->dim, (cudaStream_t)stream, sms);
+}
+
+size_t cmcd_bridge_bwd_workspace_bytes(const cmcd_bridge_desc* desc, const cmcd_net* net) {
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    const int arch = (net && desc->mode != CMCD_MODE_ULA) ? net->arch : CMCD_ARCH_NONE;
+    return bridge_bwd_workspace_bytes(desc->dim, desc->nbridges, net ? net->hidden_pad : 0, arch, sms);
+}
+
+int cmcd_bridge_bwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* seeds, const float* vd_mean,
+                    const float* vd_logdiag, const float* betas, const float* eps, const cmcd_net* net,
+                    const cmcd_target* target, const float* traj, const float* cot_negw, float* g_vd_mean,
+                    float* g_vd_logdiag, float* g_betas, float* g_eps, const cmcd_net_grad* g_net,
+                    void* workspace, size_t workspace_bytes) {
+    BridgeArgs a;
+    if (int rc = build_args(desc, seeds, vd_mean, vd_logdiag, betas, eps, net, target, a)) return rc;
+    a.traj = const_cast<float*>(traj);
+    const int sms = num_sms();
+    if (sms <= 0) { set_error("no CUDA device"); return 1; }
+    if (target->kind == CMCD_TARGET_LGCP) { set_error("lgcp reverse pass not implemented in this build"); return 2; }
+    if (!traj || !cot_negw) { set_error("bridge_bwd needs traj and cot_negw"); return 2; }
+    return launch_bridge_bwd(a, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
+                             g_eps, g_net, workspace, workspace_bytes);
+}
+
+int cmcd_loss_stats(void* stream, const float* negw, int64_t n, float* out4) {
+    return launch_loss_stats((cudaStream_t)stream, negw, n, out4);
+}
+int cmcd_batched_elbo_lnz(void* stream, const float* losses, int32_t batches, int32_t n, float* elbo, float* lnz) {
+    if (batches < 1 || n < 1) { set_error("empty batch"); return 2; }
+    return launch_batched_elbo_lnz((cudaStream_t)stream, losses, batches, n, elbo, lnz);
+}
+
+int cmcd_bridge_fwd_host(const cmcd_bridge_desc* desc, void* stream, const int32_t* seeds_host, const float* vd_mean,
+                         const float* vd_logdiag, const float* betas, const float* eps, const cmcd_net* net,
+                         const cmcd_target* target, int32_t* seeds_dev, float* negw_dev, float* z_dev,
+                         float* out_negw_host, float* out_z_host) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = desc->n_particles;
+    CMCD_CUDA_OK(cudaMemcpyAsync(seeds_dev, seeds_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (int rc = cmcd_bridge_fwd(desc, stream, seeds_dev, vd_mean, vd_logdiag, betas, eps, net, target, negw_dev, z_dev, nullptr)) return rc;
+    CMCD_CUDA_OK(cudaMemcpyAsync(out_negw_host, negw_dev, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out_z_host) CMCD_CUDA_OK(cudaMemcpyAsync(out_z_host, z_dev, n * desc->dim * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CMCD_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int cmcd_target_eval(const cmcd_target* target, int32_t dim, void* stream, const float* x, int64_t n, const float* v,
+                     float* out_logp, float* out_score, float* out_hvp) {
+    cmcd_bridge_desc d;
+    d.mode = CMCD_MODE_ULA; d.dim = dim; d.nbridges = 0; d.n_particles = (int32_t)n;
+    d.clip_target = d.clip_q = INFINITY;
+    BridgeArgs a;
+    if (int rc = build_args(&d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, target, a)) return rc;
+    if (target->kind == CMCD_TARGET_LGCP) { set_error("target_eval: lgcp is served by the wide path"); return 2; }
+    if (n == 0) return 0;
+    return launch_target_eval((cudaStream_t)stream, a.tgt, dim, x, n, v, out_logp, out_score, out_hvp);
+}
+
+int cmcd_threefry2x32(void* stream, const uint32_t* key2, const uint32_t* x0, const uint32_t* x1, int64_t n, uint32_t* y0, uint32_t* y1) {
+    return launch_threefry((cudaStream_t)stream, key2, x0, x1, n, y0, y1);
+}
+int cmcd_particle_noise(void* stream, const int32_t* seeds, int64_t n, int32_t dim, int32_t nbridges, float* xi0, float* xi) {
+    return launch_particle_noise((cudaStream_t)stream, seeds, n, dim, nbridges, xi0, xi);
+}
+
+}  // extern "C"

@@ -1,0 +1,139 @@
+// Analytic log-density / score / Hessian-vector products of the closed-form targets.
+//
+// Replaces jax.grad(log_prob_model) (and its reverse-mode transpose) for the targets of
+// /root/reference/src/model_handler.py: many_gmm :245-284 (40 diagonal components, the
+// "-inf below -1e4" override with zero gradient :279-280), gmm :157-242 (3 full-covariance
+// components symmetrised by a coordinate flip = 6 components), funnel :124-154.
+// (lgcp :287-409 is d=1600 and lives in the wide path, wide.cu.)
+//
+// Layout of the packed parameter block `tp` (floats, staged in shared memory by the kernels):
+//   mixture targets: ncomp rows of MIX_STRIDE floats
+//     many_gmm row: mu0, mu1, -, -, -, -            (shared scale / constants in TargetDesc)
+//     gmm row:      m0, m1, p00, p01, p11, logc      (precision matrix P, logc incl. log-weight - log 2)
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace cmcd {
+
+enum TargetKind : int { TGT_GMM = 0, TGT_MANY_GMM = 1, TGT_FUNNEL = 2, TGT_LGCP = 3 };
+constexpr int MIX_STRIDE = 6;
+constexpr int MIX_MAX = 64;
+
+struct TargetDesc {
+    int kind;
+    int ncomp;
+    float scale;      // many_gmm: component scale (softplus(0.1))
+    float inv_var;    // many_gmm: 1/scale^2
+    float comp_norm;  // many_gmm: 0.5*log(2 pi) + log(scale)   (per dimension)
+    float log_mix;    // many_gmm: -log(ncomp)
+    float invalid_below;  // many_gmm: -1e4
+    const float* mix;     // device [ncomp][MIX_STRIDE]
+};
+
+// ---- 2-D mixtures ---------------------------------------------------------------------------
+// Returns log p(z).  g = grad log p (zero where the reference's override kills the gradient).
+// If WANT_HVP, also hv = (Hessian of log p) * v.
+template <bool WANT_HVP>
+__device__ __forceinline__ float mixture2_eval(const TargetDesc& t, const float* __restrict__ tp,
+                                               const float (&z)[2], float (&g)[2],
+                                               const float (&v)[2], float (&hv)[2]) {
+    const int nc = t.ncomp;
+    float m = -CUDART_INF_F;
+    if (t.kind == TGT_MANY_GMM) {
+        for (int k = 0; k < nc; ++k) {
+            const float s0 = (z[0] - tp[k * MIX_STRIDE + 0]) / t.scale;
+            const float s1 = (z[1] - tp[k * MIX_STRIDE + 1]) / t.scale;
+            const float l = ((-0.5f * s0 * s0 - t.comp_norm) + (-0.5f * s1 * s1 - t.comp_norm)) + t.log_mix;
+            m = fmaxf(m, l);
+        }
+        float S = 0.f, G0 = 0.f, G1 = 0.f, Q0 = 0.f, Q1 = 0.f;
+        for (int k = 0; k < nc; ++k) {
+            const float d0 = z[0] - tp[k * MIX_STRIDE + 0], d1 = z[1] - tp[k * MIX_STRIDE + 1];
+            const float s0 = d0 / t.scale, s1 = d1 / t.scale;
+            const float l = ((-0.5f * s0 * s0 - t.comp_norm) + (-0.5f * s1 * s1 - t.comp_norm)) + t.log_mix;
+            const float e = expf(l - m);
+            const float a0 = -d0 * t.inv_var, a1 = -d1 * t.inv_var;
+            S += e; G0 += e * a0; G1 += e * a1;
+            if (WANT_HVP) { const float av = a0 * v[0] + a1 * v[1]; Q0 += e * a0 * av; Q1 += e * a1 * av; }
+        }
+        const float lp = logf(S) + m;
+        const bool valid = lp > t.invalid_below;
+        const float inv = 1.0f / S;
+        g[0] = valid ? G0 * inv : 0.f;
+        g[1] = valid ? G1 * inv : 0.f;
+        if (WANT_HVP) {
+            const float gv = g[0] * v[0] + g[1] * v[1];
+            hv[0] = valid ? (Q0 * inv - v[0] * t.inv_var - g[0] * gv) : 0.f;
+            hv[1] = valid ? (Q1 * inv - v[1] * t.inv_var - g[1] * gv) : 0.f;
+        }
+        return valid ? lp : -CUDART_INF_F;
+    }
+    // full-covariance 2-D mixture (gmm)
+    for (int k = 0; k < nc; ++k) {
+        const float* r = tp + k * MIX_STRIDE;
+        const float d0 = z[0] - r[0], d1 = z[1] - r[1];
+        const float b0 = r[2] * d0 + r[3] * d1, b1 = r[3] * d0 + r[4] * d1;
+        m = fmaxf(m, -0.5f * (d0 * b0 + d1 * b1) + r[5]);
+    }
+    float S = 0.f, G0 = 0.f, G1 = 0.f, Q0 = 0.f, Q1 = 0.f;
+    for (int k = 0; k < nc; ++k) {
+        const float* r = tp + k * MIX_STRIDE;
+        const float d0 = z[0] - r[0], d1 = z[1] - r[1];
+        const float b0 = r[2] * d0 + r[3] * d1, b1 = r[3] * d0 + r[4] * d1;
+        const float e = expf((-0.5f * (d0 * b0 + d1 * b1) + r[5]) - m);
+        S += e; G0 -= e * b0; G1 -= e * b1;
+        if (WANT_HVP) {
+            const float bv = b0 * v[0] + b1 * v[1];
+            Q0 += e * (b0 * bv - (r[2] * v[0] + r[3] * v[1]));
+            Q1 += e * (b1 * bv - (r[3] * v[0] + r[4] * v[1]));
+        }
+    }
+    const float inv = 1.0f / S;
+    g[0] = G0 * inv; g[1] = G1 * inv;
+    if (WANT_HVP) {
+        const float gv = g[0] * v[0] + g[1] * v[1];
+        hv[0] = Q0 * inv - g[0] * gv;
+        hv[1] = Q1 * inv - g[1] * gv;
+    }
+    return logf(S) + m;
+}
+
+// ---- funnel (any D >= 2) --------------------------------------------------------------------
+template <int D, bool WANT_HVP>
+__device__ __forceinline__ float funnel_eval(const float (&z)[D], float (&g)[D], const float (&v)[D], float (&hv)[D]) {
+    const float vv = z[0];
+    const float var = expf(vv);
+    const float ldiag = sqrtf(var);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 1; j < D; ++j) { const float y = z[j] / ldiag; ss += y * y; }
+    const float n = (float)(D - 1);
+    const float lp_v = -0.5f * (vv / 3.0f) * (vv / 3.0f) - 1.0986122886681098f - 0.9189385332046727f;
+    const float lp_o = -0.5f * ss - 0.5f * n * 1.8378770664093453f - n * logf(ldiag);
+    const float iv = 1.0f / var;
+    g[0] = -vv / 9.0f + 0.5f * ss - 0.5f * n;
+    float xv = 0.f;
+#pragma unroll
+    for (int j = 1; j < D; ++j) { g[j] = -iv * z[j]; if (WANT_HVP) xv += z[j] * v[j]; }
+    if (WANT_HVP) {
+        hv[0] = (-1.0f / 9.0f - 0.5f * ss) * v[0] + iv * xv;
+#pragma unroll
+        for (int j = 1; j < D; ++j) hv[j] = iv * (z[j] * v[0] - v[j]);
+    }
+    return lp_v + lp_o;
+}
+
+template <int D, bool WANT_HVP>
+__device__ __forceinline__ float target_eval(const TargetDesc& t, const float* __restrict__ tp,
+                                             const float (&z)[D], float (&g)[D],
+                                             const float (&v)[D], float (&hv)[D]) {
+    if constexpr (D == 2) {
+        if (t.kind == TGT_FUNNEL) return funnel_eval<D, WANT_HVP>(z, g, v, hv);
+        return mixture2_eval<WANT_HVP>(t, tp, z, g, v, hv);
+    } else {
+        return funnel_eval<D, WANT_HVP>(z, g, v, hv);
+    }
+}
+
+}  // namespace cmcd

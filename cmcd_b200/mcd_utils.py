@@ -1,0 +1,162 @@
+"""Bridge operator dispatch -- host side of the fused CUDA bridge kernels.
+
+Mirrors /root/reference/src/mcd_utils.py:24-190 (``evolve``: dispatch on ``params_fixed[2]``)
+for the overdamped modes on the hot path: MCD_ULA / MCD_ULA_sn (src/mcd_over_orig.py),
+MCD_CAIS_sn (src/mcd_cais.py), MCD_CAIS_var_sn (src/mcd_cais_var.py).  Unknown modes raise
+``NotImplementedError("Mode not implemented.")`` like mcd_utils.py:190.
+
+The reference's per-particle ``evolve(z, betas, params, rng_key_gen, ...)`` runs under
+``jax.vmap``; the CUDA kernel fuses the whole per-particle program (key chain from the integer
+seed, z0 ~ q, K bridge steps, log p(z_K)) -- ``bridge`` below is that fused call as a
+``torch.autograd.Function`` (forward = ``cmcd_bridge_fwd``, backward = ``cmcd_bridge_bwd``).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+from ._lib import ARCH, MODE, CmcdBridgeDesc, CmcdNet, CmcdNetGrad
+from .nn import build_tables
+
+SUPPORTED_MODES = tuple(MODE)
+_NET_KEYS = ("U1", "U2", "U3", "W2", "W3", "c1", "c2", "c3", "out_scale")
+
+
+def eps_table(eps0, nbridges, eps_schedule=None):
+    """Per-step step sizes (mcd_cais.py:34-44,54-59), differentiable in eps0.  Returns [K]."""
+    i = torch.arange(nbridges, device=eps0.device, dtype=torch.float32)
+    if eps_schedule == "cos_sq":
+        phase = i / nbridges
+        decay = torch.cos((phase + 0.008) / 1.008 * 0.5 * math.pi) ** 2
+        return eps0 * decay
+    if eps_schedule == "linear":
+        return (0.0001 - eps0) / (nbridges - 1) * i + eps0
+    return eps0 * torch.ones_like(i)
+
+
+def _clips(mode, grad_clipping):
+    """grad_clipping -> (clip_target, clip_q).  mcd_cais.py:24-30 (1e3, target only);
+    mcd_cais_var.py:33-40 (1e2, both); mcd_over_orig.py never clips."""
+    inf = float("inf")
+    if not grad_clipping or mode in ("MCD_ULA", "MCD_ULA_sn"):
+        return inf, inf
+    return (1e2, 1e2) if mode == "MCD_CAIS_var_sn" else (1e3, inf)
+
+
+def _make_desc(mode, dim, nbridges, n, clip_t, clip_q):
+    d = CmcdBridgeDesc()
+    d.mode, d.dim, d.nbridges, d.n_particles = MODE[mode], dim, nbridges, n
+    d.clip_target, d.clip_q = clip_t, clip_q
+    return d
+
+
+def _make_net(apply_fun, tabs, nbridges):
+    net = CmcdNet()
+    if apply_fun is None or tabs is None:
+        net.arch = 0
+        return net
+    net.arch, net.hidden, net.hidden_pad, net.n_rows = ARCH[apply_fun.arch], apply_fun.hidden, apply_fun.hidden_pad, nbridges + 1
+    for k in _NET_KEYS[:-1]:
+        setattr(net, k, _lib.ptr(tabs[k]))
+    net.out_scale = float(tabs["out_scale_host"])
+    net.out_clip = 1.0e4 if apply_fun.arch == "dds" else float("inf")
+    return net
+
+
+class _Bridge(torch.autograd.Function):
+    """(-w[N], z_K[N,d]) = bridge(seeds; vd, betas, eps, net tables)."""
+
+    @staticmethod
+    def forward(ctx, cfg, seeds, vd_mean, vd_logdiag, betas, eps, *net_t):
+        mode, dim, K, apply_fun, target, clip_t, clip_q, need_grad = cfg
+        _lib.require_cuda(seeds, vd_mean)
+        dev = vd_mean.device
+        n = seeds.numel()
+        f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
+        vd_mean, vd_logdiag, betas, eps = f32(vd_mean), f32(vd_logdiag), f32(betas), f32(eps)
+        tabs = None
+        if apply_fun is not None:
+            tabs = {k: f32(t) for k, t in zip(_NET_KEYS, net_t)}
+            tabs["out_scale_host"] = float(tabs["out_scale"].item()) if apply_fun.arch == "geffner" else 1.0
+        negw = torch.empty(n, device=dev, dtype=torch.float32)
+        z = torch.empty(n, dim, device=dev, dtype=torch.float32)
+        traj = torch.empty((K + 1, dim, n), device=dev, dtype=torch.float32) if need_grad else None
+        desc, net, tg = _make_desc(mode, dim, K, n, clip_t, clip_q), _make_net(apply_fun, tabs, K), target.desc()
+        _lib.check(_lib.lib().cmcd_bridge_fwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean),
+                                              _lib.ptr(vd_logdiag), _lib.ptr(betas), _lib.ptr(eps), net, tg,
+                                              _lib.ptr(negw), _lib.ptr(z), _lib.ptr(traj)))
+        ctx.cfg, ctx.saved = cfg, (seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj)
+        ctx.mark_non_differentiable(z)
+        return negw, z
+
+    @staticmethod
+    def backward(ctx, cot_negw, _cot_z):
+        mode, dim, K, apply_fun, target, clip_t, clip_q, need_grad = ctx.cfg
+        seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj = ctx.saved
+        if traj is None:
+            raise RuntimeError("bridge was run without a trajectory; cannot differentiate")
+        dev = vd_mean.device
+        n = seeds.numel()
+        cot = cot_negw.detach().to(torch.float32).contiguous()
+        g_mean, g_logdiag = torch.zeros_like(vd_mean), torch.zeros_like(vd_logdiag)
+        g_betas = torch.zeros(max(K, 1), device=dev)
+        g_eps = torch.zeros(max(K, 1), device=dev)
+        desc, net, tg = _make_desc(mode, dim, K, n, clip_t, clip_q), _make_net(apply_fun, tabs, K), target.desc()
+        gnet, gt = CmcdNetGrad(), {}
+        if apply_fun is not None:
+            for k in _NET_KEYS:
+                if tabs[k] is not None:
+                    gt[k] = torch.zeros_like(tabs[k])
+                    setattr(gnet, k, _lib.ptr(gt[k]))
+        L = _lib.lib()
+        ws_bytes = L.cmcd_bridge_bwd_workspace_bytes(desc, net)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        _lib.check(L.cmcd_bridge_bwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean), _lib.ptr(vd_logdiag),
+                                     _lib.ptr(betas), _lib.ptr(eps), net, tg, _lib.ptr(traj), _lib.ptr(cot),
+                                     _lib.ptr(g_mean), _lib.ptr(g_logdiag), _lib.ptr(g_betas), _lib.ptr(g_eps),
+                                     gnet, _lib.ptr(ws), ws_bytes))
+        net_grads = tuple(gt.get(k) for k in _NET_KEYS) if apply_fun is not None else ()
+        return (None, None, g_mean, g_logdiag, g_betas[:K] if K else None, g_eps[:K] if K else None, *net_grads)
+
+
+def bridge(seeds, params, betas, params_fixed, log_prob_model, eps_schedule=None, grad_clipping=False):
+    """Fused per-particle program of compute_log_elbo (mcdboundingmachine.py:126-179).
+
+    Returns (-w[N], z_K[N,d]); differentiable w.r.t. everything in ``params`` / ``betas``."""
+    dim, nbridges, mode, apply_fun = params_fixed
+    if mode not in MODE:
+        raise NotImplementedError("Mode not implemented.")
+    vd = params["vd"]
+    dev = vd["mean"].device
+    uses_net = mode != "MCD_ULA" and nbridges >= 1
+    if uses_net and apply_fun is None:
+        raise RuntimeError(f"mode {mode} needs a score network")
+    clip_t, clip_q = _clips(mode, grad_clipping)
+    if nbridges >= 1:
+        sched = eps_schedule if mode in ("MCD_CAIS_sn", "MCD_CAIS_var_sn") else None  # orig ignores the schedule
+        eps = eps_table(params["eps"], nbridges, sched)
+    else:
+        betas = torch.zeros(1, device=dev)
+        eps = torch.zeros(1, device=dev)
+    net_t = ()
+    if uses_net:
+        tabs = build_tables(apply_fun, params["sn"])
+        net_t = tuple(tabs[k] for k in _NET_KEYS)
+    need_grad = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in (vd["mean"], vd["logdiag"], betas, eps, *net_t))
+    cfg = (mode, dim, nbridges, apply_fun if uses_net else None, log_prob_model, clip_t, clip_q, need_grad)
+    seeds = torch.as_tensor(seeds, dtype=torch.int32, device=dev).contiguous()
+    return _Bridge.apply(cfg, seeds, vd["mean"], vd["logdiag"], betas, eps, *net_t)
+
+
+def evolve(z, betas, params, rng_key_gen, params_fixed, log_prob_model, eps_schedule=None, grad_clipping=False):
+    """mcd_utils.py:24-33 signature.  The reference's per-particle (z, key) entry is fused away: the
+    CUDA path always starts from the integer seed (see ``bridge``).  Kept so unknown modes fail as in the
+    reference (mcd_utils.py:190) and callers get a pointer to the fused entry."""
+    mode = params_fixed[2]
+    if mode not in MODE:
+        raise NotImplementedError("Mode not implemented.")
+    raise RuntimeError("cmcd_b200 fuses evolve() into the per-particle bridge kernel; "
+                       "call mcd_utils.bridge(seeds, ...) or mcdboundingmachine.compute_log_elbo")

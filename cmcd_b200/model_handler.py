@@ -1,0 +1,152 @@
+"""Target registry -- host side.  Mirrors /root/reference/src/model_handler.py:30-43 ``load_model``.
+
+The reference returns an opaque JAX callable; a fused kernel needs a closed registry, so
+``load_model`` returns a ``Target``: still callable on a batch ``x[N,d]`` (log density, via the
+CUDA ``cmcd_target_eval`` entry -- used for plotting, utils.py:54) and tagged with the device
+buffers the bridge kernels read.  Targets outside the registry raise (no generic fallback).
+Constants follow model_handler.py: funnel :124-154, gmm :157-242, many_gmm :245-284,
+lgcp :287-409 + cp_utils.py.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CmcdTarget, MIX_STRIDE, TARGET
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+# ---- host-side threefry for the many_gmm means (jax.random.uniform(PRNGKey(0), (40,2), -1, 1)) ----
+def _threefry2x32(k0, k1, x0, x1):
+    u = np.uint32
+    rot = ((13, 15, 26, 6), (17, 29, 16, 24))
+    with np.errstate(over="ignore"):
+        ks = (u(k0), u(k1), u(k0) ^ u(k1) ^ u(0x1BD11BDA))
+        x0 = x0.astype(u) + ks[0]
+        x1 = x1.astype(u) + ks[1]
+        for g in range(5):
+            for r in rot[g % 2]:
+                x0 = x0 + x1
+                x1 = (x1 << u(r)) | (x1 >> u(32 - r))
+                x1 = x1 ^ x0
+            x0 = x0 + ks[(g + 1) % 3]
+            x1 = x1 + ks[(g + 2) % 3] + u(g + 1)
+    return x0, x1
+
+
+def many_gmm_means(n_mixes=40, dim=2, loc_scaling=40.0, seed=0):
+    n = n_mixes * dim
+    m = (n + 1) // 2
+    c = np.arange(2 * m, dtype=np.uint32)
+    c[n:] = 0
+    y0, y1 = _threefry2x32(0, seed, c[:m], c[m:])
+    bits = np.concatenate([y0, y1])[:n]
+    f = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
+    u = np.maximum(np.float32(-1.0), f * np.float32(2.0) + np.float32(-1.0))
+    return (u.reshape(n_mixes, dim) * np.float32(loc_scaling)).astype(np.float32)
+
+
+class Target:
+    """A registry target: callable log density + kernel descriptor."""
+
+    def __init__(self, kind, dim, device, ncomp=0, scale=1.0, invalid_below=-math.inf, mix=None, lgcp=None):
+        self.kind, self.dim, self.device = kind, dim, torch.device(device)
+        self.ncomp, self.scale, self.invalid_below = ncomp, scale, invalid_below
+        self.mix = None if mix is None else torch.as_tensor(mix, dtype=torch.float32).contiguous().to(self.device)
+        self.lgcp = lgcp  # dict of device tensors + scalars
+
+    def desc(self):
+        t = CmcdTarget()
+        t.kind, t.ncomp, t.scale, t.invalid_below = TARGET[self.kind], self.ncomp, self.scale, self.invalid_below
+        t.mix = _lib.ptr(self.mix)
+        if self.lgcp is not None:
+            t.lgcp_kinv, t.lgcp_linv = _lib.ptr(self.lgcp["kinv"]), _lib.ptr(self.lgcp["linv"])
+            t.lgcp_counts = _lib.ptr(self.lgcp["counts"])
+            t.lgcp_mu0, t.lgcp_log_norm = self.lgcp["mu0"], self.lgcp["log_norm"]
+            t.lgcp_bin_area = self.lgcp["bin_area"]
+        return t
+
+    def evaluate(self, x, v=None):
+        """(log p, score[, hvp]) at x[N,d] on the GPU."""
+        _lib.require_cuda(x)
+        x = x.to(torch.float32).contiguous()
+        n = x.shape[0]
+        lp = torch.empty(n, device=x.device)
+        sc = torch.empty_like(x)
+        hv = torch.empty_like(x) if v is not None else None
+        vv = None if v is None else v.to(torch.float32).contiguous()
+        d = self.desc()
+        _lib.check(_lib.lib().cmcd_target_eval(d, self.dim, _lib.current_stream(), _lib.ptr(x), n, _lib.ptr(vv),
+                                               _lib.ptr(lp), _lib.ptr(sc), _lib.ptr(hv)))
+        return (lp, sc) if v is None else (lp, sc, hv)
+
+    def __call__(self, x):
+        single = x.dim() == 1
+        lp = self.evaluate(x[None] if single else x)[0]
+        return lp[0] if single else lp
+
+
+def _gmm2_components():
+    """model_handler.py:164-195: 3 full-covariance components, symmetrised by the coordinate flip."""
+    means = np.array([[3.0, 0.0], [-2.5, 0.0], [2.0, 3.0]])
+    covs = np.array([[[0.7, 0.0], [0.0, 0.05]], [[0.7, 0.0], [0.0, 0.05]], [[1.0, 0.95], [0.95, 1.0]]])
+    rows = []
+    for flip in (False, True):
+        for m, c in zip(means, covs):
+            if flip:  # raw(flip x): mean and covariance with swapped coordinates
+                m = m[::-1]
+                c = c[::-1, ::-1]
+            p = np.linalg.inv(c)
+            logc = -math.log(2 * math.pi) - 0.5 * math.log(np.linalg.det(c)) + math.log(1.0 / 3) - math.log(2.0)
+            rows.append([m[0], m[1], p[0, 0], p[0, 1], p[1, 1], logc])
+    return np.array(rows, dtype=np.float32)
+
+
+def lgcp_constants(file_path, num_dim=1600):
+    """cp_utils.py:16-84 + model_handler.py:305-346 in float64 numpy (one-off setup, not the hot path)."""
+    m = int(round(math.sqrt(num_dim)))
+    pts = np.genfromtxt(file_path, delimiter=",")
+    counts = np.zeros((m, m))
+    for elem in pts * m:
+        r, c = int(np.floor(elem[0])), int(np.floor(elem[1]))
+        r -= r == m
+        c -= c == m
+        counts[r, c] += 1
+    gi = np.arange(m)
+    bv = np.array([[a, b] for a in gi for b in gi], dtype=np.float64)
+    gram = 1.91 * np.exp(-np.linalg.norm(bv[:, None] - bv[None], axis=-1) / (m * (1.0 / 33)))
+    chol = np.linalg.cholesky(gram)
+    linv = np.linalg.inv(chol)
+    return dict(counts=counts.reshape(-1), kinv=linv.T @ linv, linv=np.tril(linv),
+                mu0=math.log(126.0) - 0.5 * 1.91,
+                log_norm=-0.5 * num_dim * math.log(2 * math.pi) - float(np.sum(np.log(np.abs(np.diag(chol))))),
+                bin_area=1.0 / num_dim)
+
+
+def load_model(model="many_gmm", config=None, device="cuda"):
+    """model_handler.py:30-43.  Returns (log_prob, dim) (+ None sample_fn for the tractable targets)."""
+    g = lambda k, dflt: getattr(config, k, dflt) if config is not None else dflt
+    if "funnel" in model:
+        return Target("funnel", int(g("funnel_d", 10)), device), int(g("funnel_d", 10)), None
+    if "lgcp" in model:
+        if g("use_whitened", False):
+            raise NotImplementedError("use_whitened=True is outside the hot-path scope")
+        c = lgcp_constants(g("file_path", os.path.join(_DATA, "pines.csv")))
+        dev = torch.device(device)
+        lg = {k: torch.tensor(c[k], dtype=torch.float32).contiguous().to(dev) for k in ("kinv", "linv", "counts")}
+        lg.update(mu0=c["mu0"], log_norm=c["log_norm"], bin_area=c["bin_area"])
+        return Target("lgcp", 1600, device, lgcp=lg), 1600
+    if "many_gmm" in model:
+        n_mixes, loc = int(g("n_mixes", 40)), float(g("loc_scaling", 40))
+        mix = np.zeros((n_mixes, MIX_STRIDE), np.float32)
+        mix[:, :2] = many_gmm_means(n_mixes, 2, loc)
+        scale = float(np.float32(np.log1p(np.exp(np.float32(0.1)))))  # softplus(0.1) passed as *scale* (:262-267)
+        return Target("many_gmm", 2, device, ncomp=n_mixes, scale=scale, invalid_below=-1e4, mix=mix), 2, None
+    if "gmm" in model:
+        return Target("gmm", 2, device, ncomp=6, mix=_gmm2_components()), 2, None
+    raise NotImplementedError(f"target {model!r} is not in the fused-kernel registry (gmm, many_gmm, funnel, lgcp)")

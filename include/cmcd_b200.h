@@ -1,0 +1,164 @@
+/*
+ * cmcd_b200 -- C ABI of the B200-native CMCD bridge hot path (libcmcd_b200.so).
+ *
+ * Drop-in boundary for the data-parallel hot path of shreyaspadhy/CMCD: the per-particle
+ * annealed-Langevin bridge loop behind the boundmodes MCD_ULA, MCD_ULA_sn, MCD_CAIS_sn,
+ * MCD_CAIS_var_sn.  Every entry point cites the reference interface it replaces
+ * (paths relative to the reference's src/).  All pointers are DEVICE pointers unless the
+ * name ends in _host; arrays are dense row-major float32 / int32; the callee only enqueues
+ * work on `stream` (no allocation, no synchronisation) so the calls are CUDA-graph safe and
+ * usable from an XLA-FFI handler.  Return value: 0 = OK, non-zero =
+ * error, message via cmcd_last_error().  Unsupported (mode, target, arch, dim) combinations
+ * fail loudly -- there is no CPU fallback.
+ */
+#ifndef CMCD_B200_H_
+#define CMCD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* boundmode -- the `mode` string of mcd_utils.evolve (mcd_utils.py:34-190) */
+enum { CMCD_MODE_ULA = 0, CMCD_MODE_ULA_SN = 1, CMCD_MODE_CAIS_SN = 2, CMCD_MODE_CAIS_VAR_SN = 3 };
+/* target registry -- model_handler.load_model (model_handler.py:30-43) */
+enum { CMCD_TARGET_GMM = 0, CMCD_TARGET_MANY_GMM = 1, CMCD_TARGET_FUNNEL = 2, CMCD_TARGET_LGCP = 3 };
+/* drift network -- nn.initialize_network (nn.py:21-39) */
+enum { CMCD_ARCH_NONE = 0, CMCD_ARCH_GEFFNER = 1, CMCD_ARCH_DDS = 2 };
+
+#define CMCD_MIX_STRIDE 6
+
+/*
+ * Drift network in "per-step table" form.  Both reference networks evaluate, per particle x
+ * and step index t (apply_fun_sn(params["sn"], x, t); nn.py:66-70, nn_dds.py:145-164):
+ *     a1  = act(U1^T x + c1[t])                       act = softplus (geffner) | exact-erf gelu (dds)
+ *     a2  = act(W2^T a1 + U2^T x + c2[t])
+ *     o   = W3^T (a2 + skip*a1) + U3^T x + c3[t]       skip = 1 (geffner) | 0 (dds)
+ *     out = out_scale * clamp(o, -out_clip, out_clip)
+ * where everything that depends only on the step (embedding row / time-coder output pushed
+ * through the first-layer weights, biases) is folded into the tables c1,c2,c3 by the host
+ * wrapper (O(K) work, cmcd_b200/nn.py).  Leading dimension of every [.,hidden] array is
+ * hidden_pad (multiple of 8, zero padded).
+ */
+typedef struct cmcd_net {
+    int32_t arch;        /* CMCD_ARCH_* */
+    int32_t hidden;      /* H */
+    int32_t hidden_pad;  /* HP >= H, multiple of 8 */
+    int32_t n_rows;      /* rows of c1/c2/c3 (nbridges + 1) */
+    const float* U1;     /* [dim][HP] */
+    const float* U2;     /* [dim][HP] or NULL (treated as zero) */
+    const float* U3;     /* [dim][dim] or NULL */
+    const float* W2;     /* [HP][HP]  (input-major: W2[i][j] multiplies a1[i] into unit j) */
+    const float* W3;     /* [HP][dim] */
+    const float* c1;     /* [n_rows][HP] */
+    const float* c2;     /* [n_rows][HP] */
+    const float* c3;     /* [n_rows][dim] */
+    float out_scale;     /* factor_sn (geffner) | 1 (dds) */
+    float out_clip;      /* +inf (geffner) | 1e4 (dds) */
+} cmcd_net;
+
+/* Cotangents of every differentiable cmcd_net field (same shapes); NULL members are skipped. */
+typedef struct cmcd_net_grad {
+    float* U1; float* U2; float* U3; float* W2; float* W3; float* c1; float* c2; float* c3;
+    float* out_scale;    /* [1] */
+} cmcd_net_grad;
+
+/* Target density descriptor (closed registry; model_handler.py:124-409). */
+typedef struct cmcd_target {
+    int32_t kind;        /* CMCD_TARGET_* */
+    int32_t ncomp;       /* mixtures: number of components (<= 64) */
+    float scale;         /* many_gmm: shared component scale (softplus(0.1), model_handler.py:262-267) */
+    float invalid_below; /* many_gmm: log p <= this -> -inf with zero gradient (-1e4, :279-280) */
+    const float* mix;    /* [ncomp][CMCD_MIX_STRIDE]: many_gmm (mu0,mu1,-,-,-,-); gmm (m0,m1,p00,p01,p11,logc) */
+    const float* lgcp_kinv;   /* lgcp: [dim][dim] dense K^-1 (symmetric) */
+    const float* lgcp_linv;   /* lgcp: [dim][dim] dense L^-1 (lower triangular, row-major) */
+    const float* lgcp_counts; /* lgcp: [dim] */
+    float lgcp_mu0;           /* lgcp: constant prior mean */
+    float lgcp_log_norm;      /* lgcp: -d/2 log(2 pi) - sum log diag L */
+    float lgcp_bin_area;      /* lgcp: 1/dim */
+} cmcd_target;
+
+/* Static description of one bridge problem (params_fixed + the flags of main.py:162-172). */
+typedef struct cmcd_bridge_desc {
+    int32_t mode;        /* CMCD_MODE_* */
+    int32_t dim;         /* d */
+    int32_t nbridges;    /* K >= 0 (K = 0: MFVI bound, boundingmachine.py:73-111) */
+    int32_t n_particles; /* N (this rank's shard) */
+    float clip_target;   /* grad_clipping: clip on the target score (1e3 KL, 1e2 log-var; +inf = off) */
+    float clip_q;        /* clip on the q score (log-var mode only, mcd_cais_var.py:33-40; +inf = off) */
+} cmcd_bridge_desc;
+
+const char* cmcd_last_error(void);
+int cmcd_version(void);
+int cmcd_num_sms(void);
+
+/*
+ * Forward bridge: replaces the jitted vmap(compute_log_elbo) of
+ * mcdboundingmachine.compute_bound (mcdboundingmachine.py:126-205) = mcd_utils.evolve
+ * (mcd_utils.py:24-33) over mcd_cais.py:46-96 / mcd_cais_var.py:56-107 / mcd_over_orig.py:18-60.
+ *   seeds[N] int32; vd_mean[d], vd_logdiag[d]; betas[K]; eps[K] (per-step step size after
+ *   the eps schedule, mcd_cais.py:34-44,54-59); out_negw[N] = -w (the per-particle loss);
+ *   out_z[N][d] = z_K; traj = NULL or [K+1][d][N] (z_k for the reverse pass).
+ */
+int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* seeds,
+                    const float* vd_mean, const float* vd_logdiag, const float* betas, const float* eps,
+                    const cmcd_net* net, const cmcd_target* target,
+                    float* out_negw, float* out_z, float* traj);
+
+/*
+ * Reverse bridge: replaces jax.grad(compute_bound, argnum=1) (main.py:174-176) for the part
+ * of the graph that is O(N*K): given traj from cmcd_bridge_fwd and cot_negw[N] = dL/d(-w_n)
+ * (1/N for the KL mean loss, 2(l_n - mean l)/N for the log-variance loss,
+ * mcdboundingmachine.py:205,231), accumulates cotangents of vd_mean[d], vd_logdiag[d],
+ * betas[K], eps[K] and the network tables.  `workspace` of cmcd_bridge_bwd_workspace_bytes()
+ * bytes is scratch.  Outputs are overwritten (not accumulated into).
+ */
+size_t cmcd_bridge_bwd_workspace_bytes(const cmcd_bridge_desc* desc, const cmcd_net* net);
+int cmcd_bridge_bwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* seeds,
+                    const float* vd_mean, const float* vd_logdiag, const float* betas, const float* eps,
+                    const cmcd_net* net, const cmcd_target* target,
+                    const float* traj, const float* cot_negw,
+                    float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
+                    const cmcd_net_grad* g_net, void* workspace, size_t workspace_bytes);
+
+/*
+ * Reductions over the per-particle losses (mcdboundingmachine.py:205,231; utils.py:227-237).
+ * out[0]=sum l, out[1]=sum l^2, out[2]=max(-l), out[3]=sum exp(-l - max(-l)); callers combine
+ * across ranks (sum / max+sum allreduce) and finish: mean, var(ddof=0), ln Z = log(out3)+out2-log n.
+ */
+int cmcd_loss_stats(void* stream, const float* negw, int64_t n, float* out4);
+/* per-batch estimators for the eval driver: losses[batches][n] -> elbo[batches], lnz[batches] */
+int cmcd_batched_elbo_lnz(void* stream, const float* losses, int32_t batches, int32_t n, float* elbo, float* lnz);
+
+/*
+ * Host-buffer convenience entry (what the reference's host loop hands over per call,
+ * opt.py:93-97): seeds on the host, loss and z back on the host; parameters/tables resident
+ * on the device.  Copies run on `stream`; the call returns after the D2H copy completed.
+ */
+int cmcd_bridge_fwd_host(const cmcd_bridge_desc* desc, void* stream, const int32_t* seeds_host,
+                         const float* vd_mean, const float* vd_logdiag, const float* betas, const float* eps,
+                         const cmcd_net* net, const cmcd_target* target,
+                         int32_t* seeds_dev_scratch, float* negw_dev_scratch, float* z_dev_scratch,
+                         float* out_negw_host, float* out_z_host);
+
+/*
+ * log p(x), grad log p(x) and (if v != NULL) Hessian(log p)(x) v for x[n][dim] -- replaces calling
+ * log_prob_model / jax.grad(log_prob_model) on a batch (model_handler.py:124-284; used by
+ * utils.py:54 for plotting and by the tests).  Any output pointer may be NULL.
+ */
+int cmcd_target_eval(const cmcd_target* target, int32_t dim, void* stream, const float* x, int64_t n,
+                     const float* v, float* out_logp, float* out_score, float* out_hvp);
+
+/* Test hooks for the bit-exact PRNG (jax.random.* call sites listed in csrc/prng.cuh). */
+int cmcd_threefry2x32(void* stream, const uint32_t* key2, const uint32_t* x0, const uint32_t* x1, int64_t n,
+                      uint32_t* y0, uint32_t* y1);
+/* xi0[N][d], xi[K][N][d]: every Gaussian particle n consumes, in order. */
+int cmcd_particle_noise(void* stream, const int32_t* seeds, int64_t n, int32_t dim, int32_t nbridges,
+                        float* xi0, float* xi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMCD_B200_H_ */

@@ -1,0 +1,253 @@
+"""The CMCD bound ("machine") and bridge operators restated in torch-CPU.
+
+ORACLE / TEST INFRASTRUCTURE ONLY.  Follows, under /root/reference/src:
+  mcdboundingmachine.py:11-123 (initialize), :126-179 (compute_log_elbo), :183-231 (compute_bound[_var])
+  mcd_utils.py:14-33 (sample_kernel / log_prob_kernel / evolve dispatch)
+  mcd_cais.py:6-99, mcd_cais_var.py:7-112, mcd_over_orig.py:6-65 (the three step bodies)
+  vardist/diag_gauss.py:20-62, boundingmachine.py:73-111 (nbridges=0 MFVI bound)
+  utils.py:219-248 (ELBO / ln Z estimators)
+Particles are a leading batch axis (the reference vmaps a per-particle function).  Gaussians
+come from the bit-exact threefry restatement (oracle/prng.py) and enter as constants, which is
+what jax.grad sees too (noise does not depend on parameters).  Gradients: torch.autograd over
+this graph, with target/q scores taken by autograd (create_graph) exactly like jax.grad inside
+the step body.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import prng
+from .nn import initialize_network
+from .pytree import ravel_pytree
+
+_LOG_SQRT_2PI_ARG = math.sqrt(2.0 * math.pi)
+
+
+# ---------------------------------------------------------------- diag gaussian q (vardist/diag_gauss.py)
+def vd_initialize(dim, init_sigma=1.0, dtype=torch.float32):
+    return {"mean": torch.zeros(dim, dtype=dtype), "logdiag": torch.ones(dim, dtype=dtype) * math.log(init_sigma)}
+
+
+def normal_log_prob(x, loc, scale):
+    """numpyro 0.10.1 Normal.log_prob summed by Independent(.,1) (mcd_utils.py:19-21)."""
+    v = (x - loc) / scale
+    return (-0.5 * v * v - torch.log(_LOG_SQRT_2PI_ARG * scale)).sum(-1)
+
+
+def vd_log_prob(vd, z):
+    return normal_log_prob(z, vd["mean"], torch.exp(vd["logdiag"]))
+
+
+def vd_sample_rep(vd, xi0):
+    return torch.exp(vd["logdiag"]) * xi0 + vd["mean"]
+
+
+# ---------------------------------------------------------------- initialize (mcdboundingmachine.py:11-123)
+def initialize(dim, vdparams=None, nbridges=0, eps=0.01, gamma=10.0, eta=0.5, ngridb=32, mgridref_y=None,
+               trainable=("eps",), emb_dim=48, seed=1, mode="MCD_CAIS_sn", nn_arch="geffner",
+               live=False, dtype=torch.float32):
+    pt, pn = {}, {}
+    (pt if "vd" in trainable else pn)["vd"] = vdparams if vdparams is not None else vd_initialize(dim, dtype=dtype)
+    for name, val in (("eps", eps), ("gamma", gamma), ("eta", eta)):
+        (pt if name in trainable else pn)[name] = torch.tensor(float(val), dtype=dtype)
+    if mode in ("MCD_ULA_sn", "MCD_CAIS_sn", "MCD_CAIS_var_sn"):
+        sn, apply_fun_sn = initialize_network(dim, emb_dim, nbridges, nn_arch,
+                                              torch.Generator().manual_seed(seed), live, dtype)
+        pt["sn"] = sn
+    elif mode == "MCD_ULA":
+        apply_fun_sn = None
+    else:
+        raise NotImplementedError("Mode not implemented.")
+    if mgridref_y is not None:
+        ngridb = mgridref_y.shape[0] - 1
+    else:
+        ngridb = min(ngridb, nbridges)
+        mgridref_y = torch.ones(ngridb + 1, dtype=dtype)
+    pn["gridref_x"] = torch.linspace(0, 1, ngridb + 2, dtype=dtype)
+    pn["target_x"] = torch.linspace(0, 1, nbridges + 2, dtype=dtype)[1:-1]
+    (pt if "mgridref_y" in trainable else pn)["mgridref_y"] = mgridref_y
+    params_fixed = (dim, nbridges, mode, apply_fun_sn)
+    params_flat, unflatten = ravel_pytree((pt, pn), dtype)
+    return params_flat, unflatten, params_fixed
+
+
+def interp(x, xp, fp):
+    """jnp.interp restated (differentiable in fp)."""
+    i = torch.clamp(torch.searchsorted(xp, x, right=True), 1, xp.numel() - 1)
+    df = fp[i] - fp[i - 1]
+    dx = xp[i] - xp[i - 1]
+    delta = x - xp[i - 1]
+    return torch.where(dx == 0, fp[i], fp[i - 1] + (delta / dx) * df)
+
+
+def make_betas(params):
+    m = params["mgridref_y"]
+    gridref_y = torch.cumsum(m, 0) / torch.sum(m)
+    gridref_y = torch.cat([torch.zeros(1, dtype=m.dtype), gridref_y])
+    return interp(params["target_x"], params["gridref_x"], gridref_y)
+
+
+def eps_at(eps0, i, nbridges, eps_schedule):
+    """mcd_cais.py:34-44,54-59."""
+    if eps_schedule == "cos_sq":
+        phase = torch.tensor(float(i), dtype=eps0.dtype) / nbridges
+        decay = torch.cos((phase + 0.008) / 1.008 * 0.5 * math.pi) ** 2
+        return eps0 * decay
+    if eps_schedule == "linear":
+        return (0.0001 - eps0) / (nbridges - 1) * i + eps0
+    return eps0
+
+
+def _score(fn, z):
+    """jax.grad(fn)(z) per particle; differentiable again (second order) when z carries a graph."""
+    zz = z if z.requires_grad else z.detach().requires_grad_(True)
+    with torch.enable_grad():
+        (g,) = torch.autograd.grad(fn(zz).sum(), zz, create_graph=True)
+    return g
+
+
+# ---------------------------------------------------------------- the step bodies
+def evolve(z, betas, params, xi, params_fixed, log_prob_model, eps_schedule=None, grad_clipping=False, traj=None):
+    """mcd_utils.py:24-190 dispatch + the three scan bodies.  xi [K,N,d] are the per-step Gaussians."""
+    dim, nbridges, mode, apply_fun_sn = params_fixed
+    vd = params["vd"]
+    q_lp = lambda x: vd_log_prob(vd, x)
+    w = torch.zeros(z.shape[0], dtype=z.dtype)
+    if mode in ("MCD_ULA", "MCD_ULA_sn"):
+        use_sn = mode == "MCD_ULA_sn"
+        for i in range(nbridges):  # mcd_over_orig.py:18-55
+            beta, eps = betas[i], params["eps"]
+            gU = lambda x: -(beta * _score(log_prob_model, x) + (1.0 - beta) * _score(q_lp, x))
+            fk_mean = z - eps * gU(z)
+            scale = torch.sqrt(2 * eps)
+            z_new = fk_mean + scale * xi[i]
+            bk_mean = z_new - eps * gU(z_new)
+            if use_sn:
+                bk_mean = bk_mean + eps * apply_fun_sn(params["sn"], z_new, i)
+            w = w + normal_log_prob(z, bk_mean, scale) - normal_log_prob(z_new, fk_mean, scale)
+            z = z_new
+            if traj is not None:
+                traj.append(z.detach().clone())
+        return z, w
+    if mode not in ("MCD_CAIS_sn", "MCD_CAIS_var_sn"):
+        raise NotImplementedError("Mode not implemented.")
+    var = mode == "MCD_CAIS_var_sn"
+    clip = 1e2 if var else 1e3
+
+    def gradU(x, beta):
+        gp = _score(q_lp, x)
+        gu = _score(log_prob_model, x)
+        if grad_clipping:
+            gu = torch.clamp(gu, -clip, clip)
+            if var:  # mcd_cais_var.py:33-40 clips both
+                gp = torch.clamp(gp, -clip, clip)
+        return -(beta * gu + (1.0 - beta) * gp)
+
+    for i in range(nbridges):  # mcd_cais.py:46-89 / mcd_cais_var.py:56-101
+        beta = betas[i]
+        if var:
+            z = z.detach()
+        uf = gradU(z, beta)
+        eps = eps_at(params["eps"], i, nbridges, eps_schedule)
+        fk_mean = z - eps * uf - eps * apply_fun_sn(params["sn"], z, i)
+        scale = torch.sqrt(2 * eps)
+        z_new = fk_mean + scale * xi[i]
+        if var:
+            z_new = z_new.detach()
+        ub = gradU(z_new, beta)
+        bk_mean = z_new - eps * ub + eps * apply_fun_sn(params["sn"], z_new, i + 1)
+        w = w + normal_log_prob(z, bk_mean, scale) - normal_log_prob(z_new, fk_mean, scale)
+        z = z_new
+        if traj is not None:
+            traj.append(z.detach().clone())
+    return z, w
+
+
+def compute_log_elbo(seeds, params_flat, unflatten, params_fixed, log_prob, eps_schedule=None,
+                     grad_clipping=False, traj=None):
+    """mcdboundingmachine.py:126-179, batched over ``seeds``.  Returns (-w [N], z_K [N,d])."""
+    pt, pn = unflatten(params_flat)
+    pn = _detach_tree(pn)
+    params = {**pt, **pn}
+    dim, nbridges = params_fixed[0], params_fixed[1]
+    dtype = params_flat.dtype
+    xi0_np, xi_np = prng.particle_noise(np.asarray(seeds), dim, nbridges)
+    xi0, xi = torch.tensor(xi0_np, dtype=dtype), torch.tensor(xi_np, dtype=dtype)
+    z = vd_sample_rep(params["vd"], xi0)
+    w = -vd_log_prob(params["vd"], z)
+    if traj is not None:
+        traj.append(z.detach().clone())
+    if nbridges >= 1:
+        betas = make_betas(params)
+        z, w_mom = evolve(z, betas, params, xi, params_fixed, log_prob, eps_schedule, grad_clipping, traj)
+        w = w + w_mom
+    w = w + log_prob(z)
+    return -1.0 * w, z
+
+
+def _detach_tree(t):
+    if isinstance(t, dict):
+        return {k: _detach_tree(v) for k, v in t.items()}
+    if isinstance(t, (list, tuple)):
+        return type(t)(_detach_tree(v) for v in t)
+    return t.detach() if isinstance(t, torch.Tensor) else t
+
+
+def compute_bound(seeds, params_flat, unflatten, params_fixed, log_prob, eps_schedule=None, grad_clipping=False):
+    """mcdboundingmachine.py:183-205."""
+    l, z = compute_log_elbo(seeds, params_flat, unflatten, params_fixed, log_prob, eps_schedule, grad_clipping)
+    return l.mean(), (l, z)
+
+
+def compute_bound_var(seeds, params_flat, unflatten, params_fixed, log_prob, eps_schedule=None, grad_clipping=False):
+    """mcdboundingmachine.py:208-231."""
+    l, z = compute_log_elbo(seeds, params_flat, unflatten, params_fixed, log_prob, eps_schedule, grad_clipping)
+    return torch.clamp(l.var(unbiased=False), -1e7, 1e7), (l, z)
+
+
+def grad_and_loss(bound_fn, seeds, params_flat, unflatten, params_fixed, log_prob, **kw):
+    """jax.jit(jax.grad(bound_fn, 1, has_aux=True)) of main.py:174-176 -> (grad_flat, (loss[N], z[N,d]))."""
+    p = params_flat.detach().clone().requires_grad_(True)
+    loss, (l, z) = bound_fn(seeds, p, unflatten, params_fixed, log_prob, **kw)
+    (g,) = torch.autograd.grad(loss, p, allow_unused=True)
+    if g is None:
+        g = torch.zeros_like(p)
+    return g, (l.detach(), z.detach())
+
+
+# ---------------------------------------------------------------- boundingmachine.py (nbridges = 0)
+def bm_initialize(dim, vdparams=None, trainable=("vd",), init_sigma=1.0, dtype=torch.float32):
+    """boundingmachine.py:9-70 restricted to nbridges=0 (main.py:83-85); eps=0.0, eta=0.5, md absent from the path."""
+    pt, pn = {}, {}
+    (pt if "vd" in trainable else pn)["vd"] = vdparams if vdparams is not None else vd_initialize(dim, init_sigma, dtype)
+    pn["eps"] = torch.tensor(0.0, dtype=dtype)
+    pn["eta"] = torch.tensor(0.5, dtype=dtype)
+    flat, unflatten = ravel_pytree((pt, pn), dtype)
+    return flat, unflatten, (dim, 0, 1)
+
+
+def bm_compute_bound(seeds, params_flat, unflatten, params_fixed, log_prob):
+    """boundingmachine.py:73-111 with nbridges=0: loss_n = log q(z) - log p(z), z ~ q."""
+    pt, pn = unflatten(params_flat)
+    params = {**pt, **_detach_tree(pn)}
+    dim = params_fixed[0]
+    xi0_np, _ = prng.particle_noise(np.asarray(seeds), dim, 0)
+    xi0 = torch.tensor(xi0_np, dtype=params_flat.dtype)
+    z = vd_sample_rep(params["vd"], xi0)
+    w = -vd_log_prob(params["vd"], z) + log_prob(z)
+    l = -1.0 * w
+    return l.mean(), (l, z)
+
+
+# ---------------------------------------------------------------- estimators (utils.py:219-248)
+def log_final_losses(eval_losses):
+    """eval_losses [n_input_dist_seeds, n_samples] -> dict(elbo, elbo_std, ln_Z, ln_Z_std)."""
+    e = torch.as_tensor(eval_losses)
+    n = e.shape[1]
+    elbos = -e.mean(1)
+    lnz = torch.logsumexp(-e, dim=1) - math.log(n)
+    return {"elbo": elbos.mean().item(), "elbo_std": elbos.std(unbiased=False).item(),
+            "ln_Z": lnz.mean().item(), "ln_Z_std": lnz.std(unbiased=False).item()}

@@ -1,0 +1,81 @@
+"""Shared test plumbing: matched (oracle, product) problem instances on identical parameters."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from oracle import mcdboundingmachine as OM
+from oracle import model_handler as OH
+
+# name -> settings.  README configs A-E of SURVEY.md appendix A (sizes reduced where noted).
+CONFIGS = {
+    "A_gmm": dict(model="gmm", mode="MCD_CAIS_sn", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.01, sigma=1.0,
+                  eps_schedule=None, clip=False, trainable=("eta", "gamma", "vd", "mgridref_y")),
+    "B_funnel": dict(model="funnel", mode="MCD_CAIS_sn", N=300, K=8, nn_arch="geffner", emb_dim=48, eps=0.1, sigma=1.0,
+                     eps_schedule="cos_sq", clip=False, trainable=("eta", "gamma", "vd", "mgridref_y")),
+    "C_manygmm_dds": dict(model="many_gmm", mode="MCD_CAIS_sn", N=2000, K=256, nn_arch="dds", emb_dim=20, eps=1.0,
+                          sigma=60.0, eps_schedule="cos_sq", clip=True, trainable=("eta", "gamma", "mgridref_y")),
+    "C_manygmm_dds_small": dict(model="many_gmm", mode="MCD_CAIS_sn", N=500, K=16, nn_arch="dds", emb_dim=20, eps=0.3,
+                                sigma=20.0, eps_schedule="cos_sq", clip=True, trainable=("eta", "gamma", "mgridref_y")),
+    "Cvar_manygmm": dict(model="many_gmm", mode="MCD_CAIS_var_sn", N=500, K=16, nn_arch="geffner", emb_dim=130, eps=0.65,
+                         sigma=15.0, eps_schedule=None, clip=True, trainable=("eta", "gamma", "mgridref_y")),
+    "Ckl_manygmm_geffner": dict(model="many_gmm", mode="MCD_CAIS_sn", N=300, K=16, nn_arch="geffner", emb_dim=130, eps=0.1,
+                                sigma=15.0, eps_schedule=None, clip=True, trainable=("eta", "gamma", "mgridref_y")),
+    "ULA_gmm": dict(model="gmm", mode="MCD_ULA", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.01, sigma=1.0,
+                    eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    "ULAsn_funnel": dict(model="funnel", mode="MCD_ULA_sn", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.05, sigma=1.0,
+                         eps_schedule="cos_sq", clip=True, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    "ULAsn_gmm_dds": dict(model="gmm", mode="MCD_ULA_sn", N=300, K=8, nn_arch="dds", emb_dim=20, eps=0.02, sigma=1.5,
+                          eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    "lin_funnel": dict(model="funnel", mode="MCD_CAIS_sn", N=200, K=12, nn_arch="dds", emb_dim=20, eps=0.05, sigma=1.0,
+                       eps_schedule="linear", clip=True, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+}
+
+
+def seeds_for(n, seed=0):
+    """seeds = default_rng(0).integers(1, 10**6, N, int32) (mirrors opt.py:94)."""
+    return np.random.default_rng(seed).integers(1, 10**6, n).astype(np.int32)
+
+
+def oracle_problem(name, dtype=torch.float32, N=None, K=None):
+    c = dict(CONFIGS[name])
+    if N:
+        c["N"] = N
+    if K:
+        c["K"] = K
+    log_prob, dim = OH.load_model(c["model"], dtype=dtype)
+    # parameters are always drawn in float32 (identical values for every dtype), then cast
+    vdp = OM.vd_initialize(dim, c["sigma"])
+    g = torch.Generator().manual_seed(7)
+    vdp["mean"] = vdp["mean"] + 0.1 * torch.randn(dim, generator=g)  # non-trivial mean
+    mgrid = 1.0 + 0.3 * torch.rand(min(32, c["K"]) + 1, generator=g)
+    pf, unf, fixed = OM.initialize(dim, vdparams=vdp, nbridges=c["K"], eps=c["eps"], trainable=c["trainable"],
+                                   emb_dim=c["emb_dim"], mode=c["mode"], nn_arch=c["nn_arch"], mgridref_y=mgrid,
+                                   live=True)
+    return c, log_prob, dim, pf.to(dtype), unf, fixed
+
+
+def product_problem(name, pf_oracle, device="cuda", N=None, K=None):
+    """Same pytree layout as the oracle (identical initialize arguments) -> the flat vectors are interchangeable."""
+    from cmcd_b200 import mcdboundingmachine as PM
+    from cmcd_b200 import model_handler as PH
+    from cmcd_b200 import variationaldist as PV
+    c = dict(CONFIGS[name])
+    if N:
+        c["N"] = N
+    if K:
+        c["K"] = K
+    out = PH.load_model(c["model"], device=device)
+    target, dim = out[0], out[1]
+    mgrid = torch.ones(min(32, c["K"]) + 1)
+    pf, unf, fixed = PM.initialize(dim, vdparams=PV.initialize(dim, device=device), nbridges=c["K"], eps=c["eps"],
+                                   trainable=c["trainable"], emb_dim=c["emb_dim"], mode=c["mode"],
+                                   nn_arch=c["nn_arch"], mgridref_y=mgrid, device=device)
+    assert pf.numel() == pf_oracle.numel(), (pf.numel(), pf_oracle.numel())
+    return c, target, dim, pf_oracle.to(torch.float32).to(device), unf, fixed
+
+
+def rel_err(a, b, floor=1.0):
+    """|a-b| / max(|b|, floor) elementwise (numpy)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)

@@ -1,0 +1,56 @@
+"""The C-ABI library loads and exports every symbol include/cmcd_b200.h declares (no compute without a GPU)."""
+import os
+import re
+
+import pytest
+import torch
+
+from cmcd_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "cmcd_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cmcd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    names = _declared()
+    assert len(names) >= 12
+    l = _lib.lib()
+    for n in names:
+        assert hasattr(l, n), f"{n} declared in cmcd_b200.h but not exported"
+        assert n in _lib.EXPORTS, f"{n} has no ctypes binding"
+    assert set(_lib.EXPORTS) == set(names)
+    assert l.cmcd_version() >= 100
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    from cmcd_b200 import mcdboundingmachine as M, model_handler as H
+    t, dim, _ = H.load_model("gmm", device="cpu")
+    pf, unf, fixed = M.initialize(dim, nbridges=4, trainable=("vd",), mode="MCD_ULA", device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        M.compute_bound(torch.arange(1, 5), pf, unf, fixed, t)
+
+
+def test_unknown_mode_and_target_raise():
+    from cmcd_b200 import mcdboundingmachine as M, model_handler as H, mcd_utils
+    with pytest.raises(NotImplementedError):
+        M.initialize(2, nbridges=4, mode="MCD_U_a-lp", device="cpu")
+    with pytest.raises(NotImplementedError):
+        H.load_model("lorenz", device="cpu")
+    with pytest.raises(NotImplementedError, match="Mode not implemented"):
+        mcd_utils.evolve(None, None, None, None, (2, 4, "bogus", None), None)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "cmcd_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh")):
+                s = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in s and "from oracle" not in s, f

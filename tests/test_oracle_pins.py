@@ -1,0 +1,95 @@
+"""Analytic pins for the oracle restatement: normalised targets, CAIS == ULA at
+zero drift, K=0 == MFVI bound, autograd scores == closed forms, estimators."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mcdboundingmachine as OM
+from oracle import model_handler as OH
+from helpers import oracle_problem, seeds_for
+
+
+def test_targets_are_normalised_2d():
+    # ln Z = 0: integrate exp(log p) on a grid (fp64)
+    for model, lim, n in (("gmm", 12.0, 1201), ("many_gmm", 48.0, 2401)):
+        lp, dim = OH.load_model(model, dtype=torch.float64)
+        g = torch.linspace(-lim, lim, n, dtype=torch.float64)
+        xx, yy = torch.meshgrid(g, g, indexing="ij")
+        p = torch.exp(lp(torch.stack([xx.reshape(-1), yy.reshape(-1)], -1)))
+        z = p.sum().item() * (2 * lim / (n - 1)) ** 2
+        assert abs(z - 1.0) < 2e-3, (model, z)
+
+
+def test_funnel_closed_form():
+    lp, dim = OH.load_model("funnel", dtype=torch.float64)
+    x = torch.randn(64, dim, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    v = x[:, 0]
+    ref = (-v ** 2 / 18 - math.log(3 * math.sqrt(2 * math.pi)) - 0.5 * torch.exp(-v) * (x[:, 1:] ** 2).sum(-1)
+           - (dim - 1) * (v + math.log(2 * math.pi)) / 2)
+    torch.testing.assert_close(lp(x), ref, rtol=1e-12, atol=1e-12)
+
+
+def test_lgcp_constants_golden():
+    c = OH.lgcp_constants(OH.default_config().file_path)
+    assert c["counts"].sum() == 127 and c["counts"].max() == 4 and (c["counts"] > 0).sum() == 106
+    assert abs(c["half_log_det"] - 225.70548) < 1e-3
+    assert abs(c["mu_zero"] - 3.8812819) < 1e-6
+    ev = np.linalg.eigvalsh(c["gram"])
+    assert abs(ev.max() / ev.min() - 27.6) < 0.2
+
+
+def test_cais_equals_ula_at_zero_drift():
+    # reference init: factor_sn = 0 -> network output exactly 0 -> CAIS step == ULA step
+    lp, dim = OH.load_model("gmm")
+    seeds = seeds_for(64)
+    out = {}
+    for mode in ("MCD_CAIS_sn", "MCD_ULA"):
+        pf, unf, fixed = OM.initialize(dim, nbridges=6, eps=0.02, trainable=("vd",), emb_dim=8, mode=mode,
+                                       nn_arch="geffner", live=False)
+        out[mode] = OM.compute_bound(seeds, pf, unf, fixed, lp)[1][0]
+    torch.testing.assert_close(out["MCD_CAIS_sn"], out["MCD_ULA"], rtol=0, atol=0)
+
+
+def test_k0_ula_equals_mfvi():
+    lp, dim = OH.load_model("funnel")
+    seeds = seeds_for(50)
+    pf, unf, fixed = OM.initialize(dim, nbridges=0, trainable=("vd",), mode="MCD_ULA")
+    a = OM.compute_bound(seeds, pf, unf, fixed, lp)[1][0]
+    pf2, unf2, fixed2 = OM.bm_initialize(dim)
+    b = OM.bm_compute_bound(seeds, pf2, unf2, fixed2, lp)[1][0]
+    torch.testing.assert_close(a, b, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("name", ["A_gmm", "Cvar_manygmm", "ULAsn_funnel"])
+def test_fp32_vs_fp64_oracle(name):
+    c, lp, dim, pf, unf, fixed = oracle_problem(name, torch.float32, N=100)
+    c64, lp64, _, pf64, unf64, fixed64 = oracle_problem(name, torch.float64, N=100)
+    seeds = seeds_for(100)
+    kw = dict(eps_schedule=c["eps_schedule"], grad_clipping=c["clip"])
+    l32 = OM.compute_bound(seeds, pf, unf, fixed, lp, **kw)[1][0]
+    l64 = OM.compute_bound(seeds, pf64, unf64, fixed64, lp64, **kw)[1][0]
+    fin = torch.isfinite(l64)
+    assert (torch.isfinite(l32) == fin).all()
+    assert ((l32[fin].double() - l64[fin]).abs() / l64[fin].abs().clamp(min=1)).median() < 1e-5
+
+
+def test_grad_matches_finite_difference_fp64():
+    c, lp, dim, pf, unf, fixed = oracle_problem("A_gmm", torch.float64, N=20)
+    seeds = seeds_for(20)
+    g, _ = OM.grad_and_loss(OM.compute_bound, seeds, pf, unf, fixed, lp)
+    rng = np.random.default_rng(0)
+    for idx in rng.choice(np.nonzero(g.numpy())[0], 6, replace=False):
+        e = torch.zeros_like(pf)
+        e[idx] = 1e-6
+        fd = (OM.compute_bound(seeds, pf + e, unf, fixed, lp)[0] - OM.compute_bound(seeds, pf - e, unf, fixed, lp)[0]) / 2e-6
+        assert abs(fd.item() - g[idx].item()) < 1e-6 * max(1, abs(g[idx].item())), (idx, fd.item(), g[idx].item())
+
+
+def test_log_final_losses():
+    e = torch.randn(30, 500, dtype=torch.float64)
+    r = OM.log_final_losses(e)
+    assert abs(r["elbo"] + e.mean().item()) < 1e-12
+    lnz = np.log(np.exp(-e.numpy()).mean(1))
+    assert abs(r["ln_Z"] - lnz.mean()) < 1e-10 and abs(r["ln_Z_std"] - lnz.std()) < 1e-10
