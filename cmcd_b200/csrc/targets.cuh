@@ -38,15 +38,20 @@ template <bool WANT_HVP>
 __device__ __forceinline__ float mixture2_eval(const TargetDesc& t, const float* __restrict__ tp,
                                                const float (&z)[2], float (&g)[2],
                                                const float (&v)[2], float (&hv)[2]) {
+    // Hessian of a log-mixture: H = sum_k r_k (a_k a_k^T + A_k) - g g^T with a_k = grad log N_k, A_k = hess log N_k.
+    // Evaluated in the shift-invariant form sum_k r_k (a_k-p)(a_k-p)^T - (g-p)(g-p)^T with the pivot p = a of the
+    // dominant component, which avoids the fp32 cancellation of the naive form far away from the modes.
     const int nc = t.ncomp;
     float m = -CUDART_INF_F;
+    int kb = 0;
     if (t.kind == TGT_MANY_GMM) {
         for (int k = 0; k < nc; ++k) {
             const float s0 = (z[0] - tp[k * MIX_STRIDE + 0]) / t.scale;
             const float s1 = (z[1] - tp[k * MIX_STRIDE + 1]) / t.scale;
             const float l = ((-0.5f * s0 * s0 - t.comp_norm) + (-0.5f * s1 * s1 - t.comp_norm)) + t.log_mix;
-            m = fmaxf(m, l);
+            if (l > m) { m = l; kb = k; }
         }
+        const float p0 = -(z[0] - tp[kb * MIX_STRIDE + 0]) * t.inv_var, p1 = -(z[1] - tp[kb * MIX_STRIDE + 1]) * t.inv_var;
         float S = 0.f, G0 = 0.f, G1 = 0.f, Q0 = 0.f, Q1 = 0.f;
         for (int k = 0; k < nc; ++k) {
             const float d0 = z[0] - tp[k * MIX_STRIDE + 0], d1 = z[1] - tp[k * MIX_STRIDE + 1];
@@ -55,7 +60,11 @@ __device__ __forceinline__ float mixture2_eval(const TargetDesc& t, const float*
             const float e = expf(l - m);
             const float a0 = -d0 * t.inv_var, a1 = -d1 * t.inv_var;
             S += e; G0 += e * a0; G1 += e * a1;
-            if (WANT_HVP) { const float av = a0 * v[0] + a1 * v[1]; Q0 += e * a0 * av; Q1 += e * a1 * av; }
+            if (WANT_HVP) {
+                const float c0 = a0 - p0, c1 = a1 - p1;
+                const float cv = c0 * v[0] + c1 * v[1];
+                Q0 += e * c0 * cv; Q1 += e * c1 * cv;
+            }
         }
         const float lp = logf(S) + m;
         const bool valid = lp > t.invalid_below;
@@ -63,9 +72,10 @@ __device__ __forceinline__ float mixture2_eval(const TargetDesc& t, const float*
         g[0] = valid ? G0 * inv : 0.f;
         g[1] = valid ? G1 * inv : 0.f;
         if (WANT_HVP) {
-            const float gv = g[0] * v[0] + g[1] * v[1];
-            hv[0] = valid ? (Q0 * inv - v[0] * t.inv_var - g[0] * gv) : 0.f;
-            hv[1] = valid ? (Q1 * inv - v[1] * t.inv_var - g[1] * gv) : 0.f;
+            const float e0 = G0 * inv - p0, e1 = G1 * inv - p1;
+            const float ev = e0 * v[0] + e1 * v[1];
+            hv[0] = valid ? (Q0 * inv - v[0] * t.inv_var - e0 * ev) : 0.f;
+            hv[1] = valid ? (Q1 * inv - v[1] * t.inv_var - e1 * ev) : 0.f;
         }
         return valid ? lp : -CUDART_INF_F;
     }
@@ -74,7 +84,14 @@ __device__ __forceinline__ float mixture2_eval(const TargetDesc& t, const float*
         const float* r = tp + k * MIX_STRIDE;
         const float d0 = z[0] - r[0], d1 = z[1] - r[1];
         const float b0 = r[2] * d0 + r[3] * d1, b1 = r[3] * d0 + r[4] * d1;
-        m = fmaxf(m, -0.5f * (d0 * b0 + d1 * b1) + r[5]);
+        const float l = -0.5f * (d0 * b0 + d1 * b1) + r[5];
+        if (l > m) { m = l; kb = k; }
+    }
+    float p0, p1;
+    {
+        const float* r = tp + kb * MIX_STRIDE;
+        const float d0 = z[0] - r[0], d1 = z[1] - r[1];
+        p0 = -(r[2] * d0 + r[3] * d1); p1 = -(r[3] * d0 + r[4] * d1);
     }
     float S = 0.f, G0 = 0.f, G1 = 0.f, Q0 = 0.f, Q1 = 0.f;
     for (int k = 0; k < nc; ++k) {
@@ -84,17 +101,19 @@ __device__ __forceinline__ float mixture2_eval(const TargetDesc& t, const float*
         const float e = expf((-0.5f * (d0 * b0 + d1 * b1) + r[5]) - m);
         S += e; G0 -= e * b0; G1 -= e * b1;
         if (WANT_HVP) {
-            const float bv = b0 * v[0] + b1 * v[1];
-            Q0 += e * (b0 * bv - (r[2] * v[0] + r[3] * v[1]));
-            Q1 += e * (b1 * bv - (r[3] * v[0] + r[4] * v[1]));
+            const float c0 = -b0 - p0, c1 = -b1 - p1;
+            const float cv = c0 * v[0] + c1 * v[1];
+            Q0 += e * (c0 * cv - (r[2] * v[0] + r[3] * v[1]));
+            Q1 += e * (c1 * cv - (r[3] * v[0] + r[4] * v[1]));
         }
     }
     const float inv = 1.0f / S;
     g[0] = G0 * inv; g[1] = G1 * inv;
     if (WANT_HVP) {
-        const float gv = g[0] * v[0] + g[1] * v[1];
-        hv[0] = Q0 * inv - g[0] * gv;
-        hv[1] = Q1 * inv - g[1] * gv;
+        const float e0 = g[0] - p0, e1 = g[1] - p1;
+        const float ev = e0 * v[0] + e1 * v[1];
+        hv[0] = Q0 * inv - e0 * ev;
+        hv[1] = Q1 * inv - e1 * ev;
     }
     return logf(S) + m;
 }

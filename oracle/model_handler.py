@@ -69,7 +69,9 @@ def load_model_gmm(config=None, dtype=torch.float32):
     def log_prob(x):
         a = raw(x)
         b = raw(torch.flip(x, dims=(-1,)))
-        return torch.logaddexp(a, b) - math.log(2.0)
+        # np.logaddexp(a, b) (:194); torch.logaddexp's *second* derivative is NaN when one branch underflows
+        # (jnp.logaddexp has a custom JVP that is not), so the mathematically identical 2-way logsumexp is used
+        return torch.logsumexp(torch.stack([a, b], -1), -1) - math.log(2.0)
 
     return log_prob, 2
 

@@ -1,0 +1,90 @@
+"""Gradient parity: CUDA adjoint (cmcd_bridge_bwd through the C ABI + host chain) vs torch.autograd over the oracle.
+
+Reference: jax.grad(compute_bound_fn, 1, has_aux=True) (main.py:174-176).  Tolerance (north_star): gradients within
+1e-4 relative in fp32.  "Relative" is per parameter leaf against that leaf's max-norm.  The fp64 oracle is the ground
+truth; the fp32 oracle's own distance to it is reported and bounds what any fp32 implementation can achieve.
+"""
+import numpy as np
+import pytest
+import torch
+
+from cmcd_b200 import boundingmachine as PB
+from cmcd_b200 import mcdboundingmachine as PM
+from cmcd_b200 import model_handler as PH
+from cmcd_b200.pytree import tree_leaves
+from oracle import mcdboundingmachine as OM
+from oracle import model_handler as OH
+from helpers import oracle_problem, product_problem, seeds_for
+
+pytestmark = pytest.mark.gpu
+GRAD_TOL = 1e-4
+
+
+def _leaf_errs(g, ref, unflatten):
+    """max-norm relative error per pytree leaf (leaves with an all-zero reference must be ~0 too)."""
+    out = []
+    for a, b in zip(tree_leaves(unflatten(g)), tree_leaves(unflatten(ref))):
+        a, b = a.double().reshape(-1), b.double().reshape(-1)
+        if b.numel() == 0:
+            continue
+        scale = b.abs().max().item()
+        out.append((a - b).abs().max().item() / scale if scale > 0 else (a - b).abs().max().item())
+    return np.array(out)
+
+
+def _grads(name, N=None, K=None):
+    c, lp, dim, pf, unf, fixed = oracle_problem(name, torch.float32, N=N, K=K)
+    _, lp64, _, pf64, unf64, fixed64 = oracle_problem(name, torch.float64, N=N, K=K)
+    seeds = seeds_for(c["N"])
+    kw = dict(eps_schedule=c["eps_schedule"], grad_clipping=c["clip"])
+    var = "var" in c["mode"]
+    g32, (l32, _) = OM.grad_and_loss(OM.compute_bound_var if var else OM.compute_bound, seeds, pf, unf, fixed, lp, **kw)
+    g64, (l64, _) = OM.grad_and_loss(OM.compute_bound_var if var else OM.compute_bound, seeds, pf64, unf64, fixed64, lp64, **kw)
+    _, target, _, pf_p, unf_p, fixed_p = product_problem(name, pf, N=N, K=K)
+    fn = PM.compute_bound_var if var else PM.compute_bound
+    gl = PM.grad_and_loss(lambda *a: fn(*a, **kw))
+    gp, (lp_, zp_) = gl(torch.from_numpy(seeds), pf_p, unf_p, fixed_p, target)
+    return c, unf, g32, g64, gp.cpu(), l64, lp_.cpu()
+
+
+@pytest.mark.parametrize("name", ["A_gmm", "B_funnel", "C_manygmm_dds_small", "Cvar_manygmm", "Ckl_manygmm_geffner",
+                                  "ULA_gmm", "ULAsn_funnel", "ULAsn_gmm_dds", "lin_funnel"])
+def test_gradient_parity(name):
+    c, unf, g32, g64, gp, l64, lp_ = _grads(name)
+    assert torch.isfinite(gp).all()
+    e_kernel = _leaf_errs(gp, g64, unf)
+    e_oracle32 = _leaf_errs(g32, g64, unf)
+    print(f"{name}: kernel-vs-fp64 max {e_kernel.max():.2e}; fp32-oracle-vs-fp64 max {e_oracle32.max():.2e}")
+    assert (e_kernel <= np.maximum(GRAD_TOL, 2 * e_oracle32)).all(), (name, e_kernel, e_oracle32)
+    # frozen (params_notrain) entries get exactly zero gradient, like stop_gradient (mcdboundingmachine.py:142)
+    pt, pn = unf(gp)
+    assert all((l == 0).all() for l in tree_leaves(pn))
+
+
+def test_gradient_parity_mfvi():
+    """jax.grad(bm.compute_bound) with nbridges=0 (main.py:87-89)."""
+    for model in ("gmm", "many_gmm", "funnel"):
+        lp64, dim = OH.load_model(model, dtype=torch.float64)
+        seeds = seeds_for(300)
+        pf, unf, fixed = OM.bm_initialize(dim, init_sigma=1.3)
+        pf = pf.clone()
+        pf[:dim] += 0.2
+        g64, _ = OM.grad_and_loss(OM.bm_compute_bound, seeds, pf.double(), unf, fixed, lp64)
+        target = PH.load_model(model)[0]
+        pfp, unfp, fixedp = PB.initialize(dim, trainable=("vd",), init_sigma=1.3)
+        gp, _ = PM.grad_and_loss(PB.compute_bound)(torch.from_numpy(seeds), pf.cuda(), unfp, fixedp, target)
+        e = _leaf_errs(gp.cpu(), g64, unf)
+        assert (e < GRAD_TOL).all(), (model, e)
+
+
+def test_gradient_partition_sum():
+    """Sharding particles and summing shard gradients (what the NCCL allreduce does) equals the full-batch gradient."""
+    c, lp, dim, pf, unf, fixed = oracle_problem("C_manygmm_dds_small")
+    seeds = torch.from_numpy(seeds_for(1000))
+    _, target, _, pf_p, unf_p, fixed_p = product_problem("C_manygmm_dds_small", pf)
+    kw = dict(eps_schedule=c["eps_schedule"], grad_clipping=c["clip"])
+    gl = PM.grad_and_loss(lambda *a: PM.compute_bound(*a, **kw))
+    g_full, _ = gl(seeds, pf_p, unf_p, fixed_p, target)
+    parts = [gl(seeds[a:b], pf_p, unf_p, fixed_p, target)[0] * ((b - a) / 1000.0) for a, b in ((0, 400), (400, 1000))]
+    e = _leaf_errs((parts[0] + parts[1]).cpu(), g_full.cpu(), unf)
+    assert (e < 1e-5).all(), e
