@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/sec of one CMCD train iteration on the 40-GMM scaling config.
+
+Metric (BASELINE.json): particle-steps/sec = N x nbridges / time of one full train iteration (forward bridge +
+reverse/adjoint + gradient all-reduce; optimizer excluded -- it is host code in the reference, opt.py:126-128) for
+    many_gmm (40-GMM, d=2), MCD_CAIS_sn, nn_arch=dds, nbridges=256, eps=1 cos_sq, init_sigma=60, grad_clipping
+with N = 2^20 particles *per GPU* (weak scaling over ranks: particles shard with no data-path collective; the only
+collectives are the tiny loss-statistics and gradient all-reduces).
+
+One process per GPU (torchrun); rank 0 prints ONE JSON line.  `--impl reference` times the CPU oracle restatement
+(the reference's JAX path cannot run: no jax in this image) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NBRIDGES = 256
+N_PER_GPU = 1 << 20
+# algorithmic flops per particle-step: forward 35.0 kflop, KL train 105 kflop
+FLOP_FWD = 35.0e3
+FLOP_TRAIN = 105.0e3
+
+
+def _synthetic_params(unflatten, pf, dim, device):
+    """SURVEY 8d convention: reference init distributions, but a live drift head so the network path is exercised."""
+    pt, pn = unflatten(pf)
+    g = torch.Generator().manual_seed(0)
+    pt["sn"]["out"]["w"].copy_((torch.randn(64, dim, generator=g) * 0.01).to(device))
+    pt["sn"]["out"]["b"].copy_((torch.randn(dim, generator=g) * 0.01).to(device))
+    pt["sn"]["timestep_phase"].copy_((torch.randn(1, 64, generator=g) * 0.1).to(device))
+    return pf
+
+
+def _clock_sampler(path):
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    try:
+        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                stdout=open(path, "w"), stderr=subprocess.DEVNULL)
+    except OSError:
+        return None
+
+
+def _parse_clocks(path, dev_index):
+    sm, mx, reasons = [], [], set()
+    try:
+        for line in open(path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or f[0] != str(dev_index):
+                continue
+            sm.append(float(f[1])); mx.append(float(f[2]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+    except OSError:
+        pass
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    busy = sorted(sm)[len(sm) // 2:]  # upper half = samples under load
+    return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons)}
+
+
+def run_reference(args):
+    """CPU restatement oracle (torch, all host threads) on a bounded sample: N=2000 particles x K=256, train iteration."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import mcdboundingmachine as OM
+    from oracle import model_handler as OH
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = 2000
+    lp, dim = OH.load_model("many_gmm")
+    pf, unf, fixed = OM.initialize(dim, vdparams=OM.vd_initialize(dim, 60.0), nbridges=NBRIDGES, eps=1.0,
+                                   trainable=("eta", "gamma", "mgridref_y"), mode="MCD_CAIS_sn", nn_arch="dds", live=True)
+    seeds = np.random.default_rng(0).integers(1, 10**6, n).astype(np.int32)
+    kw = dict(eps_schedule="cos_sq", grad_clipping=True)
+    step = lambda: OM.grad_and_loss(OM.compute_bound, seeds, pf, unf, fixed, lp, **kw)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = n * NBRIDGES / dt
+    sample = f"N={n} particles x K={NBRIDGES} bridges per step (README.md:26 config), fp32 torch-CPU autograd"
+    print(json.dumps({
+        "impl": "reference", "metric": "particle_steps_per_sec_train_iter", "value": v, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "many_gmm MCD_CAIS_sn dds K=256 cos_sq clip, train iteration (fwd+reverse)",
+                   "particles_per_step": n, "nbridges": NBRIDGES},
+        "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference JAX path cannot run here (no jax/jaxlib in the image); this is the oracle restatement",
+    }))
+
+
+def cpu_baseline_sample(budget_s=20.0):
+    """Oracle ("port") timed on the host cores on a bounded sample of the workload."""
+    from oracle import mcdboundingmachine as OM
+    from oracle import model_handler as OH
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = 2000
+    lp, dim = OH.load_model("many_gmm")
+    pf, unf, fixed = OM.initialize(dim, vdparams=OM.vd_initialize(dim, 60.0), nbridges=NBRIDGES, eps=1.0,
+                                   trainable=("eta", "gamma", "mgridref_y"), mode="MCD_CAIS_sn", nn_arch="dds", live=True)
+    seeds = np.random.default_rng(0).integers(1, 10**6, n).astype(np.int32)
+    kw = dict(eps_schedule="cos_sq", grad_clipping=True)
+    OM.grad_and_loss(OM.compute_bound, seeds, pf, unf, fixed, lp, **kw)  # warm-up
+    t0, reps = time.perf_counter(), 0
+    while True:
+        OM.grad_and_loss(OM.compute_bound, seeds, pf, unf, fixed, lp, **kw)
+        reps += 1
+        if time.perf_counter() - t0 > budget_s or reps >= 8:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": n * NBRIDGES / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} train iterations of N={n} x K={NBRIDGES} (README.md:26 config), torch-CPU fp32 oracle"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cmcd_b200", choices=["cmcd_b200", "reference"])
+    ap.add_argument("--particles-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from cmcd_b200 import _lib, mcdboundingmachine as M, model_handler as H, variationaldist as V
+    from cmcd_b200.distributed import global_ln_z, sharded_grad_and_loss
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (cmcd_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
+
+    n_local = args.particles_per_gpu
+    n_global = n_local * world
+    target, dim, _ = H.load_model("many_gmm", device=dev)
+    pf, unf, fixed = M.initialize(dim, vdparams=V.initialize(dim, 60.0), nbridges=NBRIDGES, eps=1.0,
+                                  trainable=("eta", "gamma", "mgridref_y"), mode="MCD_CAIS_sn", nn_arch="dds", device=dev)
+    pf = _synthetic_params(unf, pf, dim, dev)
+    kw = dict(eps_schedule="cos_sq", grad_clipping=True)
+    rng = np.random.default_rng(rank)  # mirrors opt.py:94 randint(1, 1e6), a fresh batch of seeds every iteration
+    nbatch = args.warmup + args.steps
+    seeds_host = [torch.from_numpy(rng.integers(1, 10**6, n_local).astype(np.int32)).pin_memory() for _ in range(nbatch)]
+    seeds_dev = [s.to(dev) for s in seeds_host]
+
+    def local_forward(seeds, p):
+        l, (z, _) = M.compute_log_elbo(seeds, p, unf, fixed, target, **kw)
+        return l, z
+
+    def step(seeds):
+        return sharded_grad_and_loss(local_forward, seeds, pf, loss="kl")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # FP32 FMA-pipe probe (roofline denominator, "of measured")
+    sms = _lib.lib().cmcd_num_sms()
+    scratch = torch.empty(sms * 8 * 256, device=dev)
+    probe = lambda: _lib.check(_lib.lib().cmcd_ffma_probe(_lib.current_stream(), _lib.ptr(scratch), sms * 8, 4096))
+    for _ in range(3):
+        probe()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); probe(); b.record(); torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    fp32_peak_tflops = 2.0 * 16 * 4096 * sms * 8 * 256 / (best * 1e-3) / 1e12
+
+    # ---- device-resident timing (value) ----
+    for i in range(args.warmup):
+        step(seeds_dev[i])
+    clock_file = os.path.join(tempfile.gettempdir(), f"cmcd_clocks_{os.getpid()}.csv")
+    sampler = _clock_sampler(clock_file) if rank == 0 else None
+    _lib.LAUNCHES["count"] = 0
+    _lib.TIMING.update(enabled=True, fwd=[], bwd=[])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        g, loss_value, (l, z) = step(seeds_dev[args.warmup + i])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = _lib.LAUNCHES["count"]
+    _lib.TIMING["enabled"] = False
+    fwd_ms = float(np.mean([a.elapsed_time(b) for a, b in _lib.TIMING["fwd"]]))
+    bwd_ms = float(np.mean([a.elapsed_time(b) for a, b in _lib.TIMING["bwd"]]))
+    if sampler is not None:
+        sampler.terminate()
+    lnz_est = global_ln_z(l)
+
+    # ---- end-to-end timing: host seeds in (pinned), gradient + loss back on the host ----
+    g_host = torch.empty(pf.numel(), dtype=torch.float32).pin_memory()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        sd = seeds_host[args.warmup + i].to(dev, non_blocking=True)
+        g, loss_value, (l, z) = step(sd)
+        g_host.copy_(g, non_blocking=True)
+        loss_host = float(loss_value)  # already a host scalar (the reference's isnan(mean(loss)) sync, opt.py:122)
+        torch.cuda.current_stream().synchronize()
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1) / args.steps
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t[0].item(), t[1].item()
+    if rank == 0:
+        value = n_global * NBRIDGES / (ms * 1e-3)
+        e2e = n_global * NBRIDGES / (ms_e2e * 1e-3)
+        ach_bwd = (FLOP_TRAIN - FLOP_FWD) * n_local * NBRIDGES / (bwd_ms * 1e-3) / 1e12
+        ach_fwd = FLOP_FWD * n_local * NBRIDGES / (fwd_ms * 1e-3) / 1e12
+        out = {
+            "metric": "particle_steps_per_sec_train_iter", "value": value, "unit": "particle-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "many_gmm (40-GMM d=2) MCD_CAIS_sn nn_arch=dds nbridges=256 eps=1 cos_sq sigma0=60 "
+                                   "grad_clipping: one train iteration (forward bridge + adjoint + grad all-reduce)",
+                       "particles_per_gpu": n_local, "particles_global": n_global, "nbridges": NBRIDGES,
+                       "l2_policy": "inputs larger than L2: a fresh 4 MiB seed vector per step and a 2.2 GB "
+                                    "trajectory written then re-read per step (> 126 MB L2)"},
+            "e2e": {"value": e2e, "unit": "particle-steps/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": 4 * n_local, "d2h_bytes_per_step": 4 * pf.numel() + 8},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp32", "kernel": "bridge_bwd_kernel", "achieved": ach_bwd, "peak": fp32_peak_tflops,
+                         "unit": "TFLOP/s", "frac": ach_bwd / fp32_peak_tflops, "traffic": None,
+                         "peak_source": "measured live: cmcd_ffma_probe (FFMA dependent chains, CUDA events); "
+                                        "MEASURED_PEAKS.json has no FP32-pipe entry",
+                         "algorithmic_flops_per_particle_step": FLOP_TRAIN - FLOP_FWD, "avg_launch_ms": bwd_ms,
+                         "fwd_kernel": {"kernel": "bridge_fwd_kernel", "achieved": ach_fwd, "frac": ach_fwd / fp32_peak_tflops,
+                                        "algorithmic_flops_per_particle_step": FLOP_FWD, "avg_launch_ms": fwd_ms}},
+            "clocks": _parse_clocks(clock_file, local_rank),
+            "quality": {"loss_mean_finite": float(l[torch.isfinite(l)].mean().item()),
+                        "finite_frac": float(torch.isfinite(l).float().mean().item()), "ln_Z_estimate": lnz_est,
+                        "grad_norm": float(g.norm().item())},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -51,11 +51,39 @@ EXPORTS = {
     "cmcd_bridge_fwd_host": (C.c_int, [C.POINTER(CmcdBridgeDesc), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNet),
                                        C.POINTER(CmcdTarget), _fp, _fp, _fp, _fp, _fp]),
     "cmcd_target_eval": (C.c_int, [C.POINTER(CmcdTarget), C.c_int32, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp]),
+    "cmcd_ffma_probe": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32]),
     "cmcd_threefry2x32": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp, _fp]),
     "cmcd_particle_noise": (C.c_int, [_fp, _fp, C.c_int64, C.c_int32, C.c_int32, _fp, _fp]),
 }
 
 _lib = None
+
+# bookkeeping for bench.py: kernels launched by this library and optional CUDA-event timing of the two bridge launches
+LAUNCHES = {"count": 0}
+TIMING = {"enabled": False, "fwd": [], "bwd": []}
+
+
+def count_launches(n):
+    LAUNCHES["count"] += n
+
+
+def timed(kind):
+    """Context manager recording CUDA events around one bridge launch on the current stream (no sync)."""
+    import contextlib
+
+    import torch
+
+    @contextlib.contextmanager
+    def cm():
+        if not TIMING["enabled"]:
+            yield
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        TIMING[kind].append((a, b))
+    return cm()
 
 
 def lib():

@@ -27,6 +27,7 @@ int launch_threefry(cudaStream_t st, const uint32_t* key2, const uint32_t* x0, c
 int launch_particle_noise(cudaStream_t st, const int32_t* seeds, long long n, int d, int K, float* xi0, float* xi);
 int launch_target_eval(cudaStream_t st, const TargetDesc& t, int D, const float* x, long long n, const float* v,
                        float* lp, float* score, float* hvp);
+int launch_ffma_peak(cudaStream_t st, float* scratch, int blocks, int iters);
 int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStream_t st, int num_sms);
 
 static int g_num_sms = 0;
@@ -160,6 +161,11 @@ int cmcd_target_eval(const cmcd_target* target, int32_t dim, void* stream, const
     if (target->kind == CMCD_TARGET_LGCP) { set_error("target_eval: lgcp is served by the wide path"); return 2; }
     if (n == 0) return 0;
     return launch_target_eval((cudaStream_t)stream, a.tgt, dim, x, n, v, out_logp, out_score, out_hvp);
+}
+
+int cmcd_ffma_probe(void* stream, float* scratch, int32_t blocks, int32_t iters) {
+    if (blocks < 1 || iters < 1 || !scratch) { set_error("ffma_probe: bad arguments"); return 2; }
+    return launch_ffma_peak((cudaStream_t)stream, scratch, blocks, iters);
 }
 
 int cmcd_threefry2x32(void* stream, const uint32_t* key2, const uint32_t* x0, const uint32_t* x1, int64_t n, uint32_t* y0, uint32_t* y1) {

@@ -163,3 +163,26 @@ int launch_target_eval(cudaStream_t st, const TargetDesc& t, int D, const float*
     return 0;
 }
 }  // namespace cmcd
+
+namespace cmcd {
+// FP32 FMA-pipe peak probe (roofline denominator for the compute-bound bridge kernels; SURVEY 8d asks for a
+// measured FFMA number because MEASURED_PEAKS.json only carries HBM and bf16-tensor peaks).
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, float a, float b, int iters) {
+    float c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-9f + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fmaf(c[i], a, b);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+int launch_ffma_peak(cudaStream_t st, float* scratch, int blocks, int iters) {
+    ffma_peak_kernel<<<blocks, 256, 0, st>>>(scratch, 1.0001f, 1e-7f, iters);
+    CMCD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+}  // namespace cmcd

@@ -84,9 +84,11 @@ class _Bridge(torch.autograd.Function):
         z = torch.empty(n, dim, device=dev, dtype=torch.float32)
         traj = torch.empty((K + 1, dim, n), device=dev, dtype=torch.float32) if need_grad else None
         desc, net, tg = _make_desc(mode, dim, K, n, clip_t, clip_q), _make_net(apply_fun, tabs, K), target.desc()
-        _lib.check(_lib.lib().cmcd_bridge_fwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean),
-                                              _lib.ptr(vd_logdiag), _lib.ptr(betas), _lib.ptr(eps), net, tg,
-                                              _lib.ptr(negw), _lib.ptr(z), _lib.ptr(traj)))
+        with _lib.timed("fwd"):
+            _lib.check(_lib.lib().cmcd_bridge_fwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean),
+                                                  _lib.ptr(vd_logdiag), _lib.ptr(betas), _lib.ptr(eps), net, tg,
+                                                  _lib.ptr(negw), _lib.ptr(z), _lib.ptr(traj)))
+        _lib.count_launches(1)
         ctx.cfg, ctx.saved = cfg, (seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj)
         ctx.mark_non_differentiable(z)
         return negw, z
@@ -113,10 +115,12 @@ class _Bridge(torch.autograd.Function):
         L = _lib.lib()
         ws_bytes = L.cmcd_bridge_bwd_workspace_bytes(desc, net)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-        _lib.check(L.cmcd_bridge_bwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean), _lib.ptr(vd_logdiag),
-                                     _lib.ptr(betas), _lib.ptr(eps), net, tg, _lib.ptr(traj), _lib.ptr(cot),
-                                     _lib.ptr(g_mean), _lib.ptr(g_logdiag), _lib.ptr(g_betas), _lib.ptr(g_eps),
-                                     gnet, _lib.ptr(ws), ws_bytes))
+        with _lib.timed("bwd"):
+            _lib.check(L.cmcd_bridge_bwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean),
+                                         _lib.ptr(vd_logdiag), _lib.ptr(betas), _lib.ptr(eps), net, tg, _lib.ptr(traj),
+                                         _lib.ptr(cot), _lib.ptr(g_mean), _lib.ptr(g_logdiag), _lib.ptr(g_betas),
+                                         _lib.ptr(g_eps), gnet, _lib.ptr(ws), ws_bytes))
+        _lib.count_launches(2)  # adjoint kernel + partial-gradient reduce kernel
         net_grads = tuple(gt.get(k) for k in _NET_KEYS) if apply_fun is not None else ()
         return (None, None, g_mean, g_logdiag, g_betas[:K] if K else None, g_eps[:K] if K else None, *net_grads)
 

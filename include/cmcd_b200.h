@@ -151,6 +151,13 @@ int cmcd_bridge_fwd_host(const cmcd_bridge_desc* desc, void* stream, const int32
 int cmcd_target_eval(const cmcd_target* target, int32_t dim, void* stream, const float* x, int64_t n,
                      const float* v, float* out_logp, float* out_score, float* out_hvp);
 
+/*
+ * FP32 FMA-pipe probe: `blocks` x 256 threads each run iters*16 dependent-chain FFMAs (2*16*iters*256*blocks
+ * flops); scratch needs blocks*256 floats.  bench.py times it with CUDA events to get the measured FP32 roofline
+ * denominator (no reference counterpart).
+ */
+int cmcd_ffma_probe(void* stream, float* scratch, int32_t blocks, int32_t iters);
+
 /* Test hooks for the bit-exact PRNG (jax.random.* call sites listed in csrc/prng.cuh). */
 int cmcd_threefry2x32(void* stream, const uint32_t* key2, const uint32_t* x0, const uint32_t* x1, int64_t n,
                       uint32_t* y0, uint32_t* y1);

@@ -115,8 +115,10 @@ def test_target_eval_matches_autograd():
         fin = torch.isfinite(l)
         assert (torch.isfinite(l_p.cpu()) == fin).all()
         assert rel_err(l_p.cpu()[fin], l.detach()[fin]).max() < 1e-5
-        assert rel_err(s_p.cpu()[fin], s.detach()[fin]).max() < 1e-4
-        assert rel_err(h_p.cpu()[fin], h.detach()[fin]).max() < 1e-4
+        # vectors: error relative to the vector's max-norm (component-wise ratios are meaningless under cancellation)
+        vec_err = lambda a, b: ((a.double() - b).abs().amax(-1) / b.abs().amax(-1).clamp(min=1.0)).max().item()
+        assert vec_err(s_p.cpu()[fin], s.detach()[fin]) < 1e-4
+        assert vec_err(h_p.cpu()[fin], h.detach()[fin]) < 1e-4
 
 
 def test_estimators_and_stats():

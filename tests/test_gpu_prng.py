@@ -21,7 +21,8 @@ def test_threefry_block_bit_exact():
     t = lambda a: torch.from_numpy(a.view(np.int32)).cuda()
     y0, y1 = torch.empty(n, dtype=torch.int32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")
     for k in (key, np.array([0x13198A2E, 0x03707344], np.uint32)):
-        _lib.check(_lib.lib().cmcd_threefry2x32(_lib.current_stream(), _lib.ptr(t(k)), _lib.ptr(t(x0)), _lib.ptr(t(x1)),
+        kd, x0d, x1d = t(k), t(x0), t(x1)  # keep the device buffers alive across the launch
+        _lib.check(_lib.lib().cmcd_threefry2x32(_lib.current_stream(), _lib.ptr(kd), _lib.ptr(x0d), _lib.ptr(x1d),
                                                 n, _lib.ptr(y0), _lib.ptr(y1)))
         r0, r1 = P.threefry2x32(k[0], k[1], x0, x1)
         np.testing.assert_array_equal(y0.cpu().numpy().view(np.uint32), r0)
@@ -47,7 +48,7 @@ def test_jax_documented_normals_on_gpu():
     seeds = np.array([0, 42], np.int32)
     xi0 = torch.empty(2, 3, device="cuda")
     xi = torch.empty(1, 2, 3, device="cuda")
-    _lib.check(_lib.lib().cmcd_particle_noise(_lib.current_stream(), _lib.ptr(torch.from_numpy(seeds).cuda()), 2, 3, 1,
-                                              _lib.ptr(xi0), _lib.ptr(xi)))
+    sd = torch.from_numpy(seeds).cuda()
+    _lib.check(_lib.lib().cmcd_particle_noise(_lib.current_stream(), _lib.ptr(sd), 2, 3, 1, _lib.ptr(xi0), _lib.ptr(xi)))
     a, _ = P.split(P.prng_key(seeds))
     np.testing.assert_array_equal(xi0.cpu().numpy(), P.normal(a, 3))
