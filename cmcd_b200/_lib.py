@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcmcd_b200.so")
+LIB_PATH = os.environ.get("CMCD_B200_LIB") or os.path.join(_HERE, "libcmcd_b200.so")  # env override: A/B builds
 
 MODE = {"MCD_ULA": 0, "MCD_ULA_sn": 1, "MCD_CAIS_sn": 2, "MCD_CAIS_var_sn": 3}
 TARGET = {"gmm": 0, "many_gmm": 1, "funnel": 2, "lgcp": 3}
@@ -40,8 +40,9 @@ EXPORTS = {
     "cmcd_last_error": (C.c_char_p, []),
     "cmcd_version": (C.c_int, []),
     "cmcd_num_sms": (C.c_int, []),
+    "cmcd_bridge_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(CmcdBridgeDesc), C.POINTER(CmcdNet), C.POINTER(CmcdTarget)]),
     "cmcd_bridge_fwd": (C.c_int, [C.POINTER(CmcdBridgeDesc), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNet),
-                                  C.POINTER(CmcdTarget), _fp, _fp, _fp]),
+                                  C.POINTER(CmcdTarget), _fp, _fp, _fp, _fp, C.c_size_t]),
     "cmcd_bridge_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(CmcdBridgeDesc), C.POINTER(CmcdNet)]),
     "cmcd_bridge_bwd": (C.c_int, [C.POINTER(CmcdBridgeDesc), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNet),
                                   C.POINTER(CmcdTarget), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNetGrad),

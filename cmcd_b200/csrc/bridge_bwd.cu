@@ -16,6 +16,14 @@
 // (no inter-block atomics) and summed by bwd_reduce_kernel.
 #include "net.cuh"
 
+// A/B on B200 (tools/ab.sh): inlining the two network functions into the adjoint kernel is 21% faster than
+// calling them (the 255-register kernel pays for the ABI spills); the forward kernel prefers the call.
+#ifdef CMCD_NOINLINE_NET_BWD
+#define CMCD_NETB_INL __noinline__
+#else
+#define CMCD_NETB_INL __forceinline__
+#endif
+
 namespace cmcd {
 
 struct BwdLayout {  // offsets (floats) into one block's partial-gradient slice
@@ -53,15 +61,18 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 // ---- network forward with stored activations ------------------------------------------------
 // S1 <- a1, S2 <- a2, S3 <- act'(pre2).  Returns raw o (before clamp / out_scale).
 template <int D, int ACT, int HPT, int JC, int RS>
-__device__ __forceinline__ void net_fwd_store(const NetView& nv, const NetSmem& s, int t, const float (&x)[D],
-                                              float (&o)[D], float* __restrict__ S1c, float* __restrict__ S2c,
-                                              float* __restrict__ S3c) {
+__device__ CMCD_NETB_INL void net_fwd_store(const NetView& nv, const NetSmem& s, int t, const float* __restrict__ xin,
+                                           float* __restrict__ oout, float* __restrict__ S1c, float* __restrict__ S2c,
+                                           float* __restrict__ S3c) {
     const int HP = HPT ? HPT : nv.HP;
+    float x[D], o[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) x[a] = xin[a];
     const float* __restrict__ c1 = nv.c1 + (size_t)t * HP;
     const float* __restrict__ c2 = nv.c2 + (size_t)t * HP;
     const float* __restrict__ c3 = nv.c3 + (size_t)t * D;
-    const bool has_u2 = nv.U2 != nullptr, has_u3 = nv.U3 != nullptr;
-    const float skip = (nv.arch == CMCD_ARCH_GEFFNER) ? 1.f : 0.f;
+    constexpr bool has_u2 = (ACT == ACT_SOFTPLUS), has_u3 = (ACT == ACT_SOFTPLUS);
+    constexpr float skip = (ACT == ACT_SOFTPLUS) ? 1.f : 0.f;
 #pragma unroll 4
     for (int j = 0; j < HP; ++j) {
         float p = __ldg(c1 + j);
@@ -78,6 +89,7 @@ __device__ __forceinline__ void net_fwd_store(const NetView& nv, const NetSmem& 
         }
         o[m] = p;
     }
+#pragma unroll 1
     for (int j0 = 0; j0 < HP; j0 += JC) {
         float acc[JC];
 #pragma unroll
@@ -102,10 +114,13 @@ __device__ __forceinline__ void net_fwd_store(const NetView& nv, const NetSmem& 
                 acc[4 * q + 3] = fmaf(h, ww.w, acc[4 * q + 3]);
             }
         }
+        // park the pre-activations, then a rolled activation / layer-3 loop (compact code)
 #pragma unroll
+        for (int jj = 0; jj < JC; ++jj) S2c[(j0 + jj) * RS] = acc[jj];
+#pragma unroll 4
         for (int jj = 0; jj < JC; ++jj) {
             float a2, da2;
-            act_fwd_grad<ACT>(acc[jj], a2, da2);
+            act_fwd_grad<ACT>(S2c[(j0 + jj) * RS], a2, da2);
             S2c[(j0 + jj) * RS] = a2;
             S3c[(j0 + jj) * RS] = da2;
             const float hs = a2 + skip * S1c[(j0 + jj) * RS];
@@ -113,6 +128,8 @@ __device__ __forceinline__ void net_fwd_store(const NetView& nv, const NetSmem& 
             for (int m = 0; m < D; ++m) o[m] = fmaf(hs, s.W3[(j0 + jj) * D + m], o[m]);
         }
     }
+#pragma unroll
+    for (int m = 0; m < D; ++m) oout[m] = o[m];
 }
 
 // ---- network backward (block-cooperative) ----------------------------------------------------
@@ -120,16 +137,19 @@ __device__ __forceinline__ void net_fwd_store(const NetView& nv, const NetSmem& 
 // parameter cotangents into this block's partial slice.  Contains __syncthreads(): every thread of
 // the block must call it (inactive particles pass v = 0).
 template <int D, int ACT, int HPT, int JC, int BPB>
-__device__ __forceinline__ void net_bwd(const NetView& nv, const NetSmem& s, int t, const float (&x)[D],
-                                        const float (&o)[D], const float (&v)[D], float (&dx)[D],
-                                        float* __restrict__ S1, float* __restrict__ S2, float* __restrict__ S3,
-                                        float* __restrict__ sX, float* __restrict__ sVo,
-                                        float* __restrict__ part, const BwdLayout& L) {
+__device__ CMCD_NETB_INL void net_bwd(const NetView& nv, const NetSmem& s, int t, const float* __restrict__ xin,
+                                     const float* __restrict__ oin, const float* __restrict__ vin, float* __restrict__ dxout,
+                                     float* __restrict__ S1, float* __restrict__ S2, float* __restrict__ S3,
+                                     float* __restrict__ sX, float* __restrict__ sVo,
+                                     float* __restrict__ part, const BwdLayout& L) {
     constexpr int RS = BPB + 4;
+    float x[D], o[D], v[D], dx[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) { x[a] = xin[a]; o[a] = oin[a]; v[a] = vin[a]; }
     const int HP = HPT ? HPT : nv.HP;
     const int tid = threadIdx.x;
-    const float skip = (nv.arch == CMCD_ARCH_GEFFNER) ? 1.f : 0.f;
-    const bool has_u2 = nv.U2 != nullptr, has_u3 = nv.U3 != nullptr;
+    constexpr float skip = (ACT == ACT_SOFTPLUS) ? 1.f : 0.f;
+    constexpr bool has_u2 = (ACT == ACT_SOFTPLUS), has_u3 = (ACT == ACT_SOFTPLUS);
     float* S2c = S2 + tid; float* S3c = S3 + tid;
 
     // (1) private: output layer cotangent, dp2 = W3 vo * act'(pre2) -> S3
@@ -315,6 +335,8 @@ __device__ __forceinline__ void net_bwd(const NetView& nv, const NetSmem& s, int
             }
         }
     }
+#pragma unroll
+    for (int a = 0; a < D; ++a) dxout[a] = dx[a];
     __syncthreads();
 }
 

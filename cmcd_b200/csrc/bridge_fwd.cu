@@ -24,7 +24,7 @@ __device__ __forceinline__ float gauss_logprob(const float (&x)[D], const float 
 }
 
 template <int D, int ACT, int HPT, int JC>
-__global__ void __launch_bounds__(FWD_PB) bridge_fwd_kernel(const BridgeArgs a) {
+__global__ void __launch_bounds__(FWD_PB, (D <= 4 ? 4 : 2)) bridge_fwd_kernel(const BridgeArgs a) {
     extern __shared__ float4 smem4[];
     float* sm = reinterpret_cast<float*>(smem4);
     const int tid = threadIdx.x;

@@ -28,7 +28,8 @@ int launch_particle_noise(cudaStream_t st, const int32_t* seeds, long long n, in
 int launch_target_eval(cudaStream_t st, const TargetDesc& t, int D, const float* x, long long n, const float* v,
                        float* lp, float* score, float* hvp);
 int launch_ffma_peak(cudaStream_t st, float* scratch, int blocks, int iters);
-int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStream_t st, int num_sms);
+int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStream_t st, int num_sms, void* ws, size_t ws_bytes);
+size_t wide_fwd_workspace_bytes(long long N, int d, int HP);
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -77,7 +78,7 @@ static int build_args(const cmcd_bridge_desc* d, const int32_t* seeds, const flo
             if (d->dim < 2) { set_error("funnel needs dim >= 2"); return 2; }
             break;
         case CMCD_TARGET_LGCP:
-            if (!tg->lgcp_kinv || !tg->lgcp_linv || !tg->lgcp_counts) { set_error("lgcp needs kinv/linv/counts"); return 2; }
+            if (!tg->lgcp_kinv || !tg->lgcp_counts) { set_error("lgcp needs kinv and counts"); return 2; }
             break;
         default: set_error("target kind %d not in the registry", tg->kind); return 2;
     }
@@ -94,16 +95,24 @@ const char* cmcd_last_error(void) { return g_err; }
 int cmcd_version(void) { return 100; }
 int cmcd_num_sms(void) { return num_sms(); }
 
+size_t cmcd_bridge_fwd_workspace_bytes(const cmcd_bridge_desc* desc, const cmcd_net* net, const cmcd_target* target) {
+    if (!desc || !target || target->kind != CMCD_TARGET_LGCP) return 0;
+    const bool uses_net = net && net->arch != CMCD_ARCH_NONE && desc->mode != CMCD_MODE_ULA && desc->nbridges >= 1;
+    return wide_fwd_workspace_bytes(desc->n_particles, desc->dim, uses_net ? net->hidden_pad : 0);
+}
+
 int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* seeds, const float* vd_mean,
                     const float* vd_logdiag, const float* betas, const float* eps, const cmcd_net* net,
-                    const cmcd_target* target, float* out_negw, float* out_z, float* traj) {
+                    const cmcd_target* target, float* out_negw, float* out_z, float* traj,
+                    void* workspace, size_t workspace_bytes) {
     BridgeArgs a;
     if (int rc = build_args(desc, seeds, vd_mean, vd_logdiag, betas, eps, net, target, a)) return rc;
     a.out_negw = out_negw; a.out_z = out_z; a.traj = traj;
     if (a.N == 0) return 0;
     const int sms = num_sms();
     if (sms <= 0) { set_error("no CUDA device"); return 1; }
-    if (target->kind == CMCD_TARGET_LGCP) return launch_wide_fwd(a, target, desc->dim, (cudaStream_t)stream, sms);
+    if (target->kind == CMCD_TARGET_LGCP)
+        return launch_wide_fwd(a, target, desc->dim, (cudaStream_t)stream, sms, workspace, workspace_bytes);
     return launch_bridge_fwd(a, desc->dim, (cudaStream_t)stream, sms);
 }
 
@@ -144,7 +153,8 @@ int cmcd_bridge_fwd_host(const cmcd_bridge_desc* desc, void* stream, const int32
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = desc->n_particles;
     CMCD_CUDA_OK(cudaMemcpyAsync(seeds_dev, seeds_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (int rc = cmcd_bridge_fwd(desc, stream, seeds_dev, vd_mean, vd_logdiag, betas, eps, net, target, negw_dev, z_dev, nullptr)) return rc;
+    if (target->kind == CMCD_TARGET_LGCP) { set_error("bridge_fwd_host: lgcp needs the workspace entry point"); return 2; }
+    if (int rc = cmcd_bridge_fwd(desc, stream, seeds_dev, vd_mean, vd_logdiag, betas, eps, net, target, negw_dev, z_dev, nullptr, nullptr, 0)) return rc;
     CMCD_CUDA_OK(cudaMemcpyAsync(out_negw_host, negw_dev, n * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (out_z_host) CMCD_CUDA_OK(cudaMemcpyAsync(out_z_host, z_dev, n * desc->dim * sizeof(float), cudaMemcpyDeviceToHost, st));
     CMCD_CUDA_OK(cudaStreamSynchronize(st));

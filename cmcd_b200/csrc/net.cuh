@@ -42,21 +42,27 @@ __device__ inline NetSmem net_stage_smem(const NetView& nv, int D, float* sm) {
 }
 
 // out = NN(x, t).  a1col: this thread's private activation column (element j at a1col[j*PBS]).
+// __noinline__: the two evaluations per bridge step share one copy of the code (the fully inlined kernel was
+// 146 KB of SASS and stalled on instruction fetch, profiles/r1_ncu_summary.md).
 template <int D, int ACT, int HPT, int JC, int PBS>
-__device__ __forceinline__ void net_fwd(const NetView& nv, const NetSmem& s, int t, const float (&x)[D],
-                                        float (&out)[D], float* __restrict__ a1col) {
+__device__ __noinline__ void net_fwd(const NetView& nv, const NetSmem& s, int t, const float* __restrict__ x,
+                                     float* __restrict__ out, float* __restrict__ a1col) {
     const int HP = HPT ? HPT : nv.HP;
     const float* __restrict__ c1 = nv.c1 + (size_t)t * HP;
     const float* __restrict__ c2 = nv.c2 + (size_t)t * HP;
     const float* __restrict__ c3 = nv.c3 + (size_t)t * D;
-    const bool has_u2 = nv.U2 != nullptr, has_u3 = nv.U3 != nullptr;
-    const float skip = (nv.arch == CMCD_ARCH_GEFFNER) ? 1.f : 0.f;
+    // geffner <=> softplus, residual skip, U2/U3 present; dds <=> gelu, no skip, U2 = U3 = 0 (compile-time)
+    constexpr bool has_u2 = (ACT == ACT_SOFTPLUS), has_u3 = (ACT == ACT_SOFTPLUS);
+    constexpr float skip = (ACT == ACT_SOFTPLUS) ? 1.f : 0.f;
+    float xr[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) xr[a] = x[a];
     // layer 1
 #pragma unroll 4
     for (int j = 0; j < HP; ++j) {
         float p = __ldg(c1 + j);
 #pragma unroll
-        for (int a = 0; a < D; ++a) p = fmaf(x[a], s.U1[a * HP + j], p);
+        for (int a = 0; a < D; ++a) p = fmaf(xr[a], s.U1[a * HP + j], p);
         a1col[j * PBS] = act_fwd<ACT>(p);
     }
     float o[D];
@@ -65,11 +71,12 @@ __device__ __forceinline__ void net_fwd(const NetView& nv, const NetSmem& s, int
         float p = __ldg(c3 + m);
         if (has_u3) {
 #pragma unroll
-            for (int a = 0; a < D; ++a) p = fmaf(x[a], s.U3[a * D + m], p);
+            for (int a = 0; a < D; ++a) p = fmaf(xr[a], s.U3[a * D + m], p);
         }
         o[m] = p;
     }
     // layer 2 in chunks of JC output units, layer 3 folded in
+#pragma unroll 1
     for (int j0 = 0; j0 < HP; j0 += JC) {
         float acc[JC];
 #pragma unroll
@@ -77,7 +84,7 @@ __device__ __forceinline__ void net_fwd(const NetView& nv, const NetSmem& s, int
             float p = __ldg(c2 + j0 + jj);
             if (has_u2) {
 #pragma unroll
-                for (int a = 0; a < D; ++a) p = fmaf(x[a], s.U2[a * HP + j0 + jj], p);
+                for (int a = 0; a < D; ++a) p = fmaf(xr[a], s.U2[a * HP + j0 + jj], p);
             }
             acc[jj] = p;
         }
@@ -94,12 +101,33 @@ __device__ __forceinline__ void net_fwd(const NetView& nv, const NetSmem& s, int
                 acc[4 * q + 3] = fmaf(h, ww.w, acc[4 * q + 3]);
             }
         }
+        if constexpr (HPT != 0 && JC == HPT) {
+            // whole layer in registers: park the pre-activations in the (now dead) a1 column and run the
+            // activation + layer 3 as a rolled loop (compact code instead of 64 inlined GELUs)
+            if (skip != 0.f) {
 #pragma unroll
-        for (int jj = 0; jj < JC; ++jj) {
-            const float a2 = act_fwd<ACT>(acc[jj]);
-            const float hs = a2 + skip * a1col[(j0 + jj) * PBS];
+                for (int jj = 0; jj < JC; ++jj) {
+                    const float a1 = a1col[jj * PBS];
 #pragma unroll
-            for (int m = 0; m < D; ++m) o[m] = fmaf(hs, s.W3[(j0 + jj) * D + m], o[m]);
+                    for (int m = 0; m < D; ++m) o[m] = fmaf(a1, s.W3[jj * D + m], o[m]);
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < JC; ++jj) a1col[jj * PBS] = acc[jj];
+#pragma unroll 4
+            for (int j = 0; j < HP; ++j) {
+                const float a2 = act_fwd<ACT>(a1col[j * PBS]);
+#pragma unroll
+                for (int m = 0; m < D; ++m) o[m] = fmaf(a2, s.W3[j * D + m], o[m]);
+            }
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < JC; ++jj) {
+                const float a2 = act_fwd<ACT>(acc[jj]);
+                const float hs = a2 + skip * a1col[(j0 + jj) * PBS];
+#pragma unroll
+                for (int m = 0; m < D; ++m) o[m] = fmaf(hs, s.W3[(j0 + jj) * D + m], o[m]);
+            }
         }
     }
 #pragma unroll

@@ -18,8 +18,10 @@ struct Key { uint32_t k0, k1; };
 __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
 
 // 20-round Threefry-2x32 (Random123).  Rotation schedule 13,15,26,6 / 17,29,16,24.
-__device__ __forceinline__ void threefry2x32(Key key, uint32_t& x0, uint32_t& x1) {
-    const uint32_t ks0 = key.k0, ks1 = key.k1, ks2 = key.k0 ^ key.k1 ^ 0x1BD11BDAu;
+// (__noinline__, value in / value out: one shared copy of the 20 rounds keeps the bridge kernels' hot loop
+// inside the instruction cache; arguments and results travel in registers.)
+static __device__ __noinline__ uint2 threefry2x32_core(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1) {
+    const uint32_t ks0 = k0, ks1 = k1, ks2 = k0 ^ k1 ^ 0x1BD11BDAu;
     x0 += ks0; x1 += ks1;
 #define CMCD_TF_R(r) { x0 += x1; x1 = rotl32(x1, r); x1 ^= x0; }
     CMCD_TF_R(13) CMCD_TF_R(15) CMCD_TF_R(26) CMCD_TF_R(6)
@@ -33,6 +35,11 @@ __device__ __forceinline__ void threefry2x32(Key key, uint32_t& x0, uint32_t& x1
     CMCD_TF_R(13) CMCD_TF_R(15) CMCD_TF_R(26) CMCD_TF_R(6)
     x0 += ks2; x1 += ks0 + 5u;
 #undef CMCD_TF_R
+    return make_uint2(x0, x1);
+}
+__device__ __forceinline__ void threefry2x32(Key key, uint32_t& x0, uint32_t& x1) {
+    const uint2 r = threefry2x32_core(key.k0, key.k1, x0, x1);
+    x0 = r.x; x1 = r.y;
 }
 
 // jax.random.split(key) with num=2: threefry over counts iota(4) = blocks (0,2),(1,3).

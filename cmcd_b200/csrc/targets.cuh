@@ -45,19 +45,20 @@ __device__ __forceinline__ float mixture2_eval(const TargetDesc& t, const float*
     float m = -CUDART_INF_F;
     int kb = 0;
     if (t.kind == TGT_MANY_GMM) {
+        float qmin = CUDART_INF_F;
         for (int k = 0; k < nc; ++k) {
-            const float s0 = (z[0] - tp[k * MIX_STRIDE + 0]) / t.scale;
-            const float s1 = (z[1] - tp[k * MIX_STRIDE + 1]) / t.scale;
-            const float l = ((-0.5f * s0 * s0 - t.comp_norm) + (-0.5f * s1 * s1 - t.comp_norm)) + t.log_mix;
-            if (l > m) { m = l; kb = k; }
+            const float d0 = z[0] - tp[k * MIX_STRIDE + 0], d1 = z[1] - tp[k * MIX_STRIDE + 1];
+            const float q = fmaf(d0, d0, d1 * d1);       // l_k = -0.5 q / s^2 + const: argmax l = argmin q
+            if (q < qmin) { qmin = q; kb = k; }
         }
         const float p0 = -(z[0] - tp[kb * MIX_STRIDE + 0]) * t.inv_var, p1 = -(z[1] - tp[kb * MIX_STRIDE + 1]) * t.inv_var;
+        // log N_k - max = -0.5 (q_k - q_min)/s^2 ; the constants (2 comp_norm, log_mix) re-enter in lp below
+        const float hl2 = -0.5f * t.inv_var * 1.4426950408889634f;
+        m = (-0.5f * qmin * t.inv_var - 2.0f * t.comp_norm) + t.log_mix;
         float S = 0.f, G0 = 0.f, G1 = 0.f, Q0 = 0.f, Q1 = 0.f;
         for (int k = 0; k < nc; ++k) {
             const float d0 = z[0] - tp[k * MIX_STRIDE + 0], d1 = z[1] - tp[k * MIX_STRIDE + 1];
-            const float s0 = d0 / t.scale, s1 = d1 / t.scale;
-            const float l = ((-0.5f * s0 * s0 - t.comp_norm) + (-0.5f * s1 * s1 - t.comp_norm)) + t.log_mix;
-            const float e = expf(l - m);
+            const float e = exp2f(hl2 * (fmaf(d0, d0, d1 * d1) - qmin));
             const float a0 = -d0 * t.inv_var, a1 = -d1 * t.inv_var;
             S += e; G0 += e * a0; G1 += e * a1;
             if (WANT_HVP) {
@@ -143,8 +144,13 @@ __device__ __forceinline__ float funnel_eval(const float (&z)[D], float (&g)[D],
     return lp_v + lp_o;
 }
 
+#ifdef CMCD_INLINE_TARGET
+#define CMCD_TARGET_INL __forceinline__
+#else
+#define CMCD_TARGET_INL __noinline__
+#endif
 template <int D, bool WANT_HVP>
-__device__ __forceinline__ float target_eval(const TargetDesc& t, const float* __restrict__ tp,
+__device__ CMCD_TARGET_INL float target_eval(const TargetDesc& t, const float* __restrict__ tp,
                                              const float (&z)[D], float (&g)[D],
                                              const float (&v)[D], float (&hv)[D]) {
     if constexpr (D == 2) {

@@ -1,4 +1,348 @@
+// Wide path: d = 1600 (lgcp), few particles.  Each half-step is a dense [N x 1620] x [1620 x 1620] product whose
+// operand (10.5 MB of fp32 weights, or the 10.2 MB dense K^-1 of the LGCP prior) is streamed from L2 by a split-K
+// skinny GEMM spread over all SMs; small fused "finalize" kernels reduce the split-K partials and apply bias /
+// softplus / residual / score / kernel-mean arithmetic.  One launch sequence per bridge step, enqueue-only.
+//
+// Replaces, for the lgcp target: vmap(compute_log_elbo) (src/mcdboundingmachine.py:126-205) over
+// src/mcd_cais.py:46-89 / src/mcd_over_orig.py:18-55 with log_prob_model = LogGaussianCoxPines
+// (src/model_handler.py:287-409, src/cp_utils.py:87-155) and apply_fun_sn = the geffner net (src/nn.py:42-72).
+//
+// LGCP density in K^-1 form: with dv = x - mu0,  -0.5|L^-1 dv|^2 = -0.5 dv^T K^-1 dv, so
+//   log p(x) = -0.5 dv.(K^-1 dv) + log_norm + sum_j (x_j counts_j - a exp(x_j)),
+//   score(x) = -K^-1 dv + counts - a exp(x),   H v = -K^-1 v - a exp(x) o v
+// (the reference does two triangular solves per score; K is well conditioned, cond = 27.6).
 #include "common.cuh"
+
 namespace cmcd {
-int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStream_t st, int num_sms) { set_error("lgcp wide path: not built yet"); return 2; }
+
+constexpr int WG_THREADS = 128;   // skinny GEMM: 128 threads x 4 columns
+constexpr int WG_COLS = WG_THREADS * 4;
+constexpr int WG_ROWS = 8;        // particle rows per block
+
+// Y_part[s][n][m] = sum_{k in slice s} (X[n][k] - shift) * W[k][m]
+__global__ void __launch_bounds__(WG_THREADS) skinny_gemm_kernel(const float* __restrict__ X, int ldx, float shift,
+                                                                 const float* __restrict__ W, int ldw, int N, int Kd,
+                                                                 int M, int kslice, float* __restrict__ part) {
+    extern __shared__ float sx[];  // [WG_ROWS][kslice]
+    const int m0 = blockIdx.x * WG_COLS + threadIdx.x * 4;
+    const int s = blockIdx.y;
+    const int n0 = blockIdx.z * WG_ROWS;
+    const int k0 = s * kslice, k1 = min(Kd, k0 + kslice);
+    const int kl = k1 - k0;
+    for (int i = threadIdx.x; i < WG_ROWS * kl; i += WG_THREADS) {
+        const int r = i / kl, k = i % kl;
+        sx[r * kslice + k] = (n0 + r < N) ? X[(size_t)(n0 + r) * ldx + k0 + k] - shift : 0.f;
+    }
+    __syncthreads();
+    float acc[WG_ROWS][4];
+#pragma unroll
+    for (int r = 0; r < WG_ROWS; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+    if (m0 < M) {
+        const bool full = (m0 + 3 < M) && ((ldw & 3) == 0);
+#pragma unroll 4
+        for (int k = 0; k < kl; ++k) {
+            float4 w;
+            const float* wp = W + (size_t)(k0 + k) * ldw + m0;
+            if (full) w = __ldg(reinterpret_cast<const float4*>(wp));
+            else {
+                w.x = __ldg(wp);
+                w.y = (m0 + 1 < M) ? __ldg(wp + 1) : 0.f;
+                w.z = (m0 + 2 < M) ? __ldg(wp + 2) : 0.f;
+                w.w = (m0 + 3 < M) ? __ldg(wp + 3) : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < WG_ROWS; ++r) {
+                const float x = sx[r * kslice + k];
+                acc[r][0] = fmaf(x, w.x, acc[r][0]);
+                acc[r][1] = fmaf(x, w.y, acc[r][1]);
+                acc[r][2] = fmaf(x, w.z, acc[r][2]);
+                acc[r][3] = fmaf(x, w.w, acc[r][3]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < WG_ROWS; ++r) {
+            if (n0 + r < N) {
+                float* dst = part + ((size_t)s * N + n0 + r) * M + m0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (m0 + q < M) dst[q] = acc[r][q];
+            }
+        }
+    }
 }
+
+struct WideGemm {
+    int S, kslice;
+};
+static WideGemm plan_gemm(int N, int Kd, int M, int num_sms) {
+    const int cg = (M + WG_COLS - 1) / WG_COLS, rt = (N + WG_ROWS - 1) / WG_ROWS;
+    int S = (2 * num_sms + cg * rt - 1) / (cg * rt);
+    if (S < 1) S = 1;
+    if (S > 64) S = 64;
+    int ks = (Kd + S - 1) / S;
+    ks = (ks + 3) & ~3;
+    S = (Kd + ks - 1) / ks;
+    return {S, ks};
+}
+static int run_gemm(cudaStream_t st, const float* X, int ldx, float shift, const float* W, int ldw, int N, int Kd, int M,
+                    int num_sms, float* part, int* S_out) {
+    const WideGemm g = plan_gemm(N, Kd, M, num_sms);
+    dim3 grid((M + WG_COLS - 1) / WG_COLS, g.S, (N + WG_ROWS - 1) / WG_ROWS);
+    skinny_gemm_kernel<<<grid, WG_THREADS, (size_t)WG_ROWS * g.kslice * sizeof(float), st>>>(X, ldx, shift, W, ldw, N, Kd, M, g.kslice, part);
+    CMCD_CUDA_OK(cudaGetLastError());
+    *S_out = g.S;
+    return 0;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+    if (w == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (l == 0) sh[0] = t;
+    }
+    __syncthreads();
+    return sh[0];
+}
+
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+
+// ---- init: keys, z0 = mu + sigma xi0, w0 = -log q(z0).  One block per particle. ---------------------------
+__global__ void __launch_bounds__(256) wide_init_kernel(const int32_t* seeds, int d, const float* mu, const float* logdiag,
+                                                        float* z, float* w, uint32_t* keys, float* traj, long long N) {
+    __shared__ float sh[32];
+    const int n = blockIdx.x;
+    Key k = prng_key(seeds[n]), ka;
+    split(k, ka, k);
+    float lq = 0.f;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        const float xi = bits_to_normal(random_bits_at(ka, j, d));
+        const float sg = expf(logdiag[j]);
+        const float zz = sg * xi + mu[j];
+        z[(size_t)n * d + j] = zz;
+        if (traj) traj[(size_t)j * N + n] = zz;
+        const float v = (zz - mu[j]) / sg;
+        lq += -0.5f * v * v - logf(2.5066282746310002f * sg);
+    }
+    lq = block_sum(lq, sh);
+    if (threadIdx.x == 0) {
+        w[n] = -lq;
+        ka = split_first(k);    // mcdboundingmachine.py:162
+        k = split_second(ka);   // mcd_cais.py:94
+        keys[2 * n] = k.k0; keys[2 * n + 1] = k.k1;
+    }
+}
+
+// ---- target finalize: sp = -(K^-1 dv) + counts - a exp(x); lp = -0.5 dv.(K^-1 dv) + log_norm + sum(x c - a e^x) ----
+__global__ void __launch_bounds__(256) wide_target_fin_kernel(const float* __restrict__ part, int S, int N, int d,
+                                                              const float* __restrict__ x, const float* __restrict__ counts,
+                                                              float mu0, float log_norm, float area, float* sp, float* lp) {
+    __shared__ float sh[32];
+    const int n = blockIdx.x;
+    float acc = 0.f;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        float kd = 0.f;
+        for (int s = 0; s < S; ++s) kd += part[((size_t)s * N + n) * d + j];
+        const float xx = x[(size_t)n * d + j], ex = expf(xx);
+        sp[(size_t)n * d + j] = -kd + counts[j] - area * ex;
+        acc += -0.5f * (xx - mu0) * kd + (xx * counts[j] - area * ex);
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) lp[n] = acc + log_norm;
+}
+
+// ---- network finalize kernels (geffner table form with x folded into the first d hidden units) ----
+// stage 1: a1 = softplus(sum part + c1[t]); A1 = a1 + pad(x)
+__global__ void wide_l1_fin_kernel(const float* __restrict__ part, int S, int N, int HP, int d, const float* __restrict__ c1t,
+                                   const float* __restrict__ x, int fold_x, float* a1, float* A1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * HP) return;
+    const int n = i / HP, j = i % HP;
+    float p = c1t[j];
+    for (int s = 0; s < S; ++s) p += part[((size_t)s * N + n) * HP + j];
+    const float a = softplus_f(p);
+    if (a1) a1[i] = a;
+    A1[i] = a + ((fold_x && j < d) ? x[(size_t)n * d + j] : 0.f);
+}
+// stage 2: a2 = softplus(sum part + c2[t]); A2 = a2 + skip*A1   (A1 already holds a1 + pad(x))
+__global__ void wide_l2_fin_kernel(const float* __restrict__ part, int S, int N, int HP, const float* __restrict__ c2t,
+                                   const float* __restrict__ A1, float skip, float* a2, float* A2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * HP) return;
+    const int n = i / HP, j = i % HP;
+    float p = c2t[j];
+    for (int s = 0; s < S; ++s) p += part[((size_t)s * N + n) * HP + j];
+    const float a = softplus_f(p);
+    if (a2) a2[i] = a;
+    A2[i] = a + skip * A1[i];
+}
+
+// ---- forward-kernel mean + sample:  mf = z - eps uf - eps NN ; zn = mf + s xi ; fkterm kept per element ----
+// One block per particle.  NN output = out_scale * clamp(sum part3 + c3[t]).  Advances the key chain.
+__global__ void __launch_bounds__(256) wide_fwd_mean_kernel(const float* __restrict__ part3, int S, int N, int d,
+                                                            const float* __restrict__ c3t, float out_scale, float out_clip,
+                                                            int use_nn, const float* __restrict__ z, const float* __restrict__ sp,
+                                                            const float* __restrict__ mu, const float* __restrict__ logdiag,
+                                                            const float* __restrict__ betas, const float* __restrict__ epss, int step,
+                                                            float clip_t, float clip_q,
+                                                            uint32_t* keys, float* zn, float* mf_out, float* traj_row) {
+    const int n = blockIdx.x;
+    const float beta = betas[step], eps = epss[step];
+    Key k; k.k0 = keys[2 * n]; k.k1 = keys[2 * n + 1];
+    Key ka, kn;
+    split(k, ka, kn);                     // mcd_cais.py:66
+    const float scale = sqrtf(2.0f * eps);
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        const size_t e = (size_t)n * d + j;
+        float nn = 0.f;
+        if (use_nn) {
+            float o = c3t[j];
+            for (int s = 0; s < S; ++s) o += part3[((size_t)s * N + n) * d + j];
+            nn = out_scale * fminf(fmaxf(o, -out_clip), out_clip);
+        }
+        const float sg = expf(logdiag[j]);
+        const float sq = -((z[e] - mu[j]) / sg) / sg;
+        const float gu = fminf(fmaxf(sp[e], -clip_t), clip_t), gq = fminf(fmaxf(sq, -clip_q), clip_q);
+        const float uf = -(beta * gu + (1.0f - beta) * gq);
+        const float mf = (z[e] - eps * uf) - eps * nn;
+        const float xi = bits_to_normal(random_bits_at(ka, j, d));
+        const float znew = mf + scale * xi;
+        zn[e] = znew;
+        mf_out[e] = mf;
+        if (traj_row) traj_row[(size_t)j * N + n] = znew;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const Key k2 = split_second(kn);  // mcd_cais.py:87
+        keys[2 * n] = k2.k0; keys[2 * n + 1] = k2.k1;
+    }
+}
+
+// ---- backward-kernel mean + weight update:  mb = zn - eps ub + eps NN ; w += logN(z; mb, s) - logN(zn; mf, s) ----
+__global__ void __launch_bounds__(256) wide_bwd_mean_kernel(const float* __restrict__ part3, int S, int N, int d,
+                                                            const float* __restrict__ c3t, float out_scale, float out_clip,
+                                                            int use_nn, const float* __restrict__ z, const float* __restrict__ zn,
+                                                            const float* __restrict__ mf, const float* __restrict__ spn,
+                                                            const float* __restrict__ mu, const float* __restrict__ logdiag,
+                                                            const float* __restrict__ betas, const float* __restrict__ epss, int step,
+                                                            float clip_t, float clip_q, float* w) {
+    __shared__ float sh[32];
+    const int n = blockIdx.x;
+    const float beta = betas[step], eps = epss[step];
+    const float scale = sqrtf(2.0f * eps);
+    float acc = 0.f;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        const size_t e = (size_t)n * d + j;
+        float nn = 0.f;
+        if (use_nn) {
+            float o = c3t[j];
+            for (int s = 0; s < S; ++s) o += part3[((size_t)s * N + n) * d + j];
+            nn = out_scale * fminf(fmaxf(o, -out_clip), out_clip);
+        }
+        const float sg = expf(logdiag[j]);
+        const float sq = -((zn[e] - mu[j]) / sg) / sg;
+        const float gu = fminf(fmaxf(spn[e], -clip_t), clip_t), gq = fminf(fmaxf(sq, -clip_q), clip_q);
+        const float ub = -(beta * gu + (1.0f - beta) * gq);
+        const float mb = (zn[e] - eps * ub) + eps * nn;
+        const float vb = (z[e] - mb) / scale, vf = (zn[e] - mf[e]) / scale;
+        // the two log-normalisers -log(sqrt(2 pi) s) cancel exactly per element
+        acc += -0.5f * vb * vb + 0.5f * vf * vf;
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) w[n] += acc;
+}
+
+__global__ void wide_final_kernel(const float* w, const float* lp, int N, float* out_negw) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) out_negw[n] = -(w[n] + lp[n]);
+}
+
+// workspace layout (floats)
+struct WideWs {
+    size_t z, zn, mf, sp, lp, w, keys, A1, A2, part, total;
+};
+static WideWs wide_layout(long long N, int d, int HP) {
+    WideWs L;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
+    L.z = take(N * d); L.zn = take(N * d); L.mf = take(N * d); L.sp = take(N * d);
+    L.lp = take(N); L.w = take(N); L.keys = take(2 * N);
+    L.A1 = take(N * (size_t)HP); L.A2 = take(N * (size_t)HP);
+    const int mx = HP > d ? HP : d;
+    L.part = take((size_t)64 * N * mx);
+    L.total = o;
+    return L;
+}
+
+size_t wide_fwd_workspace_bytes(long long N, int d, int HP) { return wide_layout(N, d, HP > 0 ? HP : 8).total * sizeof(float); }
+
+int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStream_t st, int num_sms, void* ws, size_t ws_bytes) {
+    const long long N = a.N;
+    const int d = D, K = a.K;
+    const NetView& nv = a.net;
+    const bool has_net = nv.arch != CMCD_ARCH_NONE;
+    const int HP = has_net ? nv.HP : 8;
+    if (has_net && nv.arch != CMCD_ARCH_GEFFNER) { set_error("lgcp wide path: only nn_arch=geffner is implemented (README.md:63 config)"); return 2; }
+    const WideWs L = wide_layout(N, d, HP);
+    if (!ws || ws_bytes < L.total * sizeof(float)) { set_error("wide_fwd: workspace too small (%zu < %zu)", ws_bytes, L.total * sizeof(float)); return 2; }
+    float* f = (float*)ws;
+    float *z = f + L.z, *zn = f + L.zn, *mf = f + L.mf, *sp = f + L.sp, *lp = f + L.lp, *w = f + L.w;
+    float *A1 = f + L.A1, *A2 = f + L.A2, *part = f + L.part;
+    uint32_t* keys = (uint32_t*)(f + L.keys);
+    const bool cais = (a.mode == CMCD_MODE_CAIS_SN || a.mode == CMCD_MODE_CAIS_VAR_SN);
+    const bool nn_b = (a.mode != CMCD_MODE_ULA) && has_net, nn_f = cais && has_net;
+    const float skip = 1.f;
+    int S = 1;
+
+    wide_init_kernel<<<(unsigned)N, 256, 0, st>>>(a.seeds, d, a.vd_mean, a.vd_logdiag, z, w, keys, a.traj, N);
+    CMCD_CUDA_OK(cudaGetLastError());
+    auto target_at = [&](const float* x) -> int {
+        if (int rc = run_gemm(st, x, d, tg->lgcp_mu0, tg->lgcp_kinv, d, (int)N, d, d, num_sms, part, &S)) return rc;
+        wide_target_fin_kernel<<<(unsigned)N, 256, 0, st>>>(part, S, (int)N, d, x, tg->lgcp_counts, tg->lgcp_mu0,
+                                                            tg->lgcp_log_norm, tg->lgcp_bin_area, sp, lp);
+        CMCD_CUDA_OK(cudaGetLastError());
+        return 0;
+    };
+    // NN(x, t) up to the layer-3 split-K partials (left in `part`, S3 slices)
+    auto net_at = [&](const float* x, int t, int* S3) -> int {
+        const int nel = (int)N * HP, blk = (nel + 255) / 256;
+        if (int rc = run_gemm(st, x, d, 0.f, nv.U1, HP, (int)N, d, HP, num_sms, part, &S)) return rc;
+        wide_l1_fin_kernel<<<blk, 256, 0, st>>>(part, S, (int)N, HP, d, nv.c1 + (size_t)t * HP, x, 1, nullptr, A1);
+        CMCD_CUDA_OK(cudaGetLastError());
+        if (int rc = run_gemm(st, A1, HP, 0.f, nv.W2, HP, (int)N, HP, HP, num_sms, part, &S)) return rc;
+        wide_l2_fin_kernel<<<blk, 256, 0, st>>>(part, S, (int)N, HP, nv.c2 + (size_t)t * HP, A1, skip, nullptr, A2);
+        CMCD_CUDA_OK(cudaGetLastError());
+        if (int rc = run_gemm(st, A2, HP, 0.f, nv.W3, d, (int)N, HP, d, num_sms, part, S3)) return rc;
+        return 0;
+    };
+    if (int rc = target_at(z)) return rc;
+    for (int i = 0; i < K; ++i) {
+        int S3 = 1;
+        if (nn_f) { if (int rc = net_at(z, i, &S3)) return rc; }
+        wide_fwd_mean_kernel<<<(unsigned)N, 256, 0, st>>>(part, S3, (int)N, d, has_net ? nv.c3 + (size_t)i * d : nullptr,
+                                                          nv.out_scale, nv.out_clip, nn_f ? 1 : 0, z, sp, a.vd_mean, a.vd_logdiag,
+                                                          a.betas, a.eps, i, a.clip_t, a.clip_q, keys, zn, mf,
+                                                          a.traj ? a.traj + (size_t)(i + 1) * d * N : nullptr);
+        CMCD_CUDA_OK(cudaGetLastError());
+        if (int rc = target_at(zn)) return rc;   // sp <- score at z' (reused as the next step's forward score)
+        const int tb = cais ? i + 1 : i;
+        if (nn_b) { if (int rc = net_at(zn, tb, &S3)) return rc; }
+        wide_bwd_mean_kernel<<<(unsigned)N, 256, 0, st>>>(part, S3, (int)N, d, has_net ? nv.c3 + (size_t)tb * d : nullptr,
+                                                          nv.out_scale, nv.out_clip, nn_b ? 1 : 0, z, zn, mf, sp, a.vd_mean,
+                                                          a.vd_logdiag, a.betas, a.eps, i, a.clip_t, a.clip_q, w);
+        CMCD_CUDA_OK(cudaGetLastError());
+        float* t = z; z = zn; zn = t;
+    }
+    wide_final_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(w, lp, (int)N, a.out_negw);
+    CMCD_CUDA_OK(cudaGetLastError());
+    CMCD_CUDA_OK(cudaMemcpyAsync(a.out_z, z, (size_t)N * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+}  // namespace cmcd

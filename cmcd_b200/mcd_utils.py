@@ -84,11 +84,14 @@ class _Bridge(torch.autograd.Function):
         z = torch.empty(n, dim, device=dev, dtype=torch.float32)
         traj = torch.empty((K + 1, dim, n), device=dev, dtype=torch.float32) if need_grad else None
         desc, net, tg = _make_desc(mode, dim, K, n, clip_t, clip_q), _make_net(apply_fun, tabs, K), target.desc()
+        L = _lib.lib()
+        ws_bytes = L.cmcd_bridge_fwd_workspace_bytes(desc, net, tg)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
         with _lib.timed("fwd"):
-            _lib.check(_lib.lib().cmcd_bridge_fwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean),
-                                                  _lib.ptr(vd_logdiag), _lib.ptr(betas), _lib.ptr(eps), net, tg,
-                                                  _lib.ptr(negw), _lib.ptr(z), _lib.ptr(traj)))
-        _lib.count_launches(1)
+            _lib.check(L.cmcd_bridge_fwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean),
+                                         _lib.ptr(vd_logdiag), _lib.ptr(betas), _lib.ptr(eps), net, tg,
+                                         _lib.ptr(negw), _lib.ptr(z), _lib.ptr(traj), _lib.ptr(ws), ws_bytes))
+        _lib.count_launches(1 if ws is None else 3 + 16 * K)
         ctx.cfg, ctx.saved = cfg, (seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj)
         ctx.mark_non_differentiable(z)
         return negw, z

@@ -73,7 +73,7 @@ typedef struct cmcd_target {
     float invalid_below; /* many_gmm: log p <= this -> -inf with zero gradient (-1e4, :279-280) */
     const float* mix;    /* [ncomp][CMCD_MIX_STRIDE]: many_gmm (mu0,mu1,-,-,-,-); gmm (m0,m1,p00,p01,p11,logc) */
     const float* lgcp_kinv;   /* lgcp: [dim][dim] dense K^-1 (symmetric) */
-    const float* lgcp_linv;   /* lgcp: [dim][dim] dense L^-1 (lower triangular, row-major) */
+    const float* lgcp_linv;   /* lgcp: reserved (the kernels use the K^-1 form), may be NULL */
     const float* lgcp_counts; /* lgcp: [dim] */
     float lgcp_mu0;           /* lgcp: constant prior mean */
     float lgcp_log_norm;      /* lgcp: -d/2 log(2 pi) - sum log diag L */
@@ -101,11 +101,14 @@ int cmcd_num_sms(void);
  *   seeds[N] int32; vd_mean[d], vd_logdiag[d]; betas[K]; eps[K] (per-step step size after
  *   the eps schedule, mcd_cais.py:34-44,54-59); out_negw[N] = -w (the per-particle loss);
  *   out_z[N][d] = z_K; traj = NULL or [K+1][d][N] (z_k for the reverse pass).
+ *   workspace: scratch of cmcd_bridge_fwd_workspace_bytes() bytes (0 for the small-d targets; the lgcp wide
+ *   path keeps its [N][1600] state, split-K partials and key chain there).
  */
+size_t cmcd_bridge_fwd_workspace_bytes(const cmcd_bridge_desc* desc, const cmcd_net* net, const cmcd_target* target);
 int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* seeds,
                     const float* vd_mean, const float* vd_logdiag, const float* betas, const float* eps,
                     const cmcd_net* net, const cmcd_target* target,
-                    float* out_negw, float* out_z, float* traj);
+                    float* out_negw, float* out_z, float* traj, void* workspace, size_t workspace_bytes);
 
 /*
  * Reverse bridge: replaces jax.grad(compute_bound, argnum=1) (main.py:174-176) for the part

@@ -27,6 +27,10 @@ CONFIGS = {
                          eps_schedule="cos_sq", clip=True, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
     "ULAsn_gmm_dds": dict(model="gmm", mode="MCD_ULA_sn", N=300, K=8, nn_arch="dds", emb_dim=20, eps=0.02, sigma=1.5,
                           eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    "D_lgcp": dict(model="lgcp", mode="MCD_CAIS_sn", N=20, K=8, nn_arch="geffner", emb_dim=20, eps=1e-3, sigma=0.3,
+                   vd_mean=3.5, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    "D_lgcp_ula": dict(model="lgcp", mode="MCD_ULA", N=11, K=4, nn_arch="geffner", emb_dim=20, eps=5e-4, sigma=0.3,
+                       vd_mean=3.5, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
     "lin_funnel": dict(model="funnel", mode="MCD_CAIS_sn", N=200, K=12, nn_arch="dds", emb_dim=20, eps=0.05, sigma=1.0,
                        eps_schedule="linear", clip=True, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
 }
@@ -47,7 +51,7 @@ def oracle_problem(name, dtype=torch.float32, N=None, K=None):
     # parameters are always drawn in float32 (identical values for every dtype), then cast
     vdp = OM.vd_initialize(dim, c["sigma"])
     g = torch.Generator().manual_seed(7)
-    vdp["mean"] = vdp["mean"] + 0.1 * torch.randn(dim, generator=g)  # non-trivial mean
+    vdp["mean"] = vdp["mean"] + 0.1 * torch.randn(dim, generator=g) + c.get("vd_mean", 0.0)  # non-trivial mean
     mgrid = 1.0 + 0.3 * torch.rand(min(32, c["K"]) + 1, generator=g)
     pf, unf, fixed = OM.initialize(dim, vdparams=vdp, nbridges=c["K"], eps=c["eps"], trainable=c["trainable"],
                                    emb_dim=c["emb_dim"], mode=c["mode"], nn_arch=c["nn_arch"], mgridref_y=mgrid,
