@@ -1,0 +1,349 @@
+// Forward bridge kernel, tensor-core variant (hidden width 64): the 64x64 layer of the drift network runs as
+// tcgen05 tiles over 128-particle batches, everything else stays per-thread in registers.
+//
+// Same contract as bridge_fwd_kernel (bridge_fwd.cu): replaces vmap(compute_log_elbo)
+// (src/mcdboundingmachine.py:126-205) over src/mcd_cais.py:46-89 / src/mcd_cais_var.py:56-101 /
+// src/mcd_over_orig.py:18-55 with apply_fun_sn = PISNet (src/nn_dds.py:145-164) or the geffner net
+// (src/nn.py:66-70) in table form (include/cmcd_b200.h, cmcd_net).
+//
+// Mapping: one CTA = 128 threads = 128 particles = the 128 TMEM lanes.  Thread p owns particle p of the tile:
+//   layer 1   a1 = act(U1^T x + c1[t])  per thread; split into tf32 hi/lo and written with tcgen05.st into the
+//             thread's own TMEM lane (columns AH.., AL..) -- this *is* the A operand [128 x 64] of the MMA;
+//   layer 2   one thread issues 24 x tcgen05.mma kind::tf32 (M=128, N=64, K=8): D = A_hi B_lo + A_lo B_hi + A_hi B_hi
+//             with B = W2^T split hi/lo once per CTA in shared memory (K-major core-matrix tiles);
+//   epilogue  each thread reads its lane of D with tcgen05.ld (64 columns), adds c2[t], activation, and folds
+//             the 64 x d output layer in registers.
+// While the MMA batch runs (~1.6k cycles) the thread does the work that does not depend on the network output:
+// threefry split + Gaussian for the step, the target score at z', the key advance.  Two CTAs per SM (256 TMEM
+// columns each) alternate so the CUDA cores always have one tile's epilogue / layer 1 to run.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace cmcd {
+
+constexpr int TC_PB = 128;   // particles per CTA (TMEM lanes)
+constexpr int TC_H = 64;     // hidden width of this path
+constexpr uint32_t TC_COL_D = 0, TC_COL_AH = 64, TC_COL_AL = 128, TC_COLS = 256;
+constexpr int TC_B_BYTES = TC_H * TC_H * 4;   // one 64x64 fp32 operand tile
+
+template <int D>
+struct TcCtx {
+    const float *sU1, *sU2, *sW3, *sU3;   // shared memory
+    const float *c1, *c2, *c3;            // global per-step tables [T][64], [T][64], [T][D]
+    float out_scale, out_clip;
+    uint32_t tmem_base, tmem_lane;        // allocation base; base + this warp's lane quarter
+    uint32_t bhi, blo;                    // shared-memory addresses of the B tiles
+    uint64_t* mbar;
+    uint32_t parity;
+};
+
+// numpyro Normal.log_prob summed over dims (src/mcd_utils.py:19-21)
+template <int D>
+__device__ __forceinline__ float gauss_logprob_tc(const float (&x)[D], const float (&mean)[D], float scale, float lognorm) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const float v = (x[j] - mean[j]) / scale;
+        s += -0.5f * v * v - lognorm;
+    }
+    return s;
+}
+
+// layer 1 -> TMEM A operand -> issue the MMA batch.  skipacc += a1 W3 (geffner residual), 0 otherwise.
+template <int D, int ACT>
+__device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, const float (&x)[D], float (&skipacc)[D]) {
+    constexpr bool skip = (ACT == ACT_SOFTPLUS);
+    const float4* __restrict__ c1v = reinterpret_cast<const float4*>(cx.c1 + (size_t)t * TC_H);
+#pragma unroll
+    for (int m = 0; m < D; ++m) skipacc[m] = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        uint32_t h[16], l[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 cc = __ldg(c1v + c * 4 + q);
+            float p[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+                const float4 u = *reinterpret_cast<const float4*>(cx.sU1 + a * TC_H + c * 16 + q * 4);
+                p[0] = fmaf(x[a], u.x, p[0]); p[1] = fmaf(x[a], u.y, p[1]);
+                p[2] = fmaf(x[a], u.z, p[2]); p[3] = fmaf(x[a], u.w, p[3]);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float a1 = act_tc<ACT>(p[e]);
+                if (skip) {
+                    const int j = c * 16 + q * 4 + e;
+#pragma unroll
+                    for (int m = 0; m < D; ++m) skipacc[m] = fmaf(a1, cx.sW3[j * D + m], skipacc[m]);
+                }
+                float hi, lo;
+                umma::split_tf32(a1, hi, lo);
+                h[q * 4 + e] = __float_as_uint(hi);
+                l[q * 4 + e] = __float_as_uint(lo);
+            }
+        }
+        umma::tmem_st16(cx.tmem_lane + TC_COL_AH + c * 16, h);
+        umma::tmem_st16(cx.tmem_lane + TC_COL_AL + c * 16, l);
+    }
+    umma::tmem_st_wait();
+    umma::fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        umma::fence_after();
+        const uint32_t idesc = umma::make_idesc_tf32(128, TC_H);
+        // small terms first: the fp32 accumulator truncates on every accumulate (tools/umma_probe2.cu, test 3)
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t acol = cx.tmem_base + (pass == 1 ? TC_COL_AL : TC_COL_AH);
+            const uint32_t baddr = (pass == 0) ? cx.blo : cx.bhi;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                umma::mma_tf32_ts(cx.tmem_base + TC_COL_D, acol + k * 8, umma::make_desc(baddr + k * 256, 128, 32 * TC_H), idesc,
+                                  (pass | k) > 0);
+        }
+        umma::commit(cx.mbar);
+    }
+}
+
+// wait for the MMA batch, epilogue: out = out_scale * clamp(W3^T (act(D + c2[t] + U2^T x) [+ a1]) + U3^T x + c3[t])
+template <int D, int ACT>
+__device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (&x)[D], const float (&skipacc)[D], float (&out)[D]) {
+    constexpr bool has_u = (ACT == ACT_SOFTPLUS);   // geffner: U2, U3 present
+    float o[D];
+#pragma unroll
+    for (int m = 0; m < D; ++m) {
+        float p = __ldg(cx.c3 + (size_t)t * D + m) + skipacc[m];
+        if (has_u) {
+#pragma unroll
+            for (int a = 0; a < D; ++a) p = fmaf(x[a], cx.sU3[a * D + m], p);
+        }
+        o[m] = p;
+    }
+    const float4* __restrict__ c2v = reinterpret_cast<const float4*>(cx.c2 + (size_t)t * TC_H);
+    umma::mbar_wait(cx.mbar, cx.parity);
+    cx.parity ^= 1u;
+    umma::fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        uint32_t v[16];
+        umma::tmem_ld16(cx.tmem_lane + TC_COL_D + c * 16, v);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 cc = __ldg(c2v + c * 4 + q);
+            float p[4] = {__uint_as_float(v[q * 4 + 0]) + cc.x, __uint_as_float(v[q * 4 + 1]) + cc.y,
+                          __uint_as_float(v[q * 4 + 2]) + cc.z, __uint_as_float(v[q * 4 + 3]) + cc.w};
+            if (has_u) {
+#pragma unroll
+                for (int a = 0; a < D; ++a) {
+                    const float4 u = *reinterpret_cast<const float4*>(cx.sU2 + a * TC_H + c * 16 + q * 4);
+                    p[0] = fmaf(x[a], u.x, p[0]); p[1] = fmaf(x[a], u.y, p[1]);
+                    p[2] = fmaf(x[a], u.z, p[2]); p[3] = fmaf(x[a], u.w, p[3]);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float a2 = act_tc<ACT>(p[e]);
+                const int j = c * 16 + q * 4 + e;
+#pragma unroll
+                for (int m = 0; m < D; ++m) o[m] = fmaf(a2, cx.sW3[j * D + m], o[m]);
+            }
+        }
+    }
+    umma::fence_before();   // orders these tcgen05.ld before the next batch's writes to D (via the next __syncthreads)
+#pragma unroll
+    for (int m = 0; m < D; ++m) out[m] = cx.out_scale * fminf(fmaxf(o[m], -cx.out_clip), cx.out_clip);
+}
+
+template <int D, int ACT>
+__global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t mbar;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const NetView& nv = a.net;
+    uint8_t* sBhi = smem_raw;
+    uint8_t* sBlo = smem_raw + TC_B_BYTES;
+    float* sf = reinterpret_cast<float*>(smem_raw + 2 * TC_B_BYTES);
+    float* sU1 = sf;
+    float* sU2 = sU1 + D * TC_H;
+    float* sW3 = sU2 + D * TC_H;
+    float* sU3 = sW3 + TC_H * D;
+    float* sTp = sU3 + ((D * D + 3) & ~3);
+    // B[n = j][k = i] = W2[i][j], split into tf32 hi / lo
+    for (int idx = tid; idx < TC_H * TC_H; idx += TC_PB) {
+        const int i = idx / TC_H, j = idx % TC_H;
+        float hi, lo;
+        umma::split_tf32(nv.W2[idx], hi, lo);
+        const int off = umma::core_off(j, i, TC_H);
+        *reinterpret_cast<float*>(sBhi + off) = hi;
+        *reinterpret_cast<float*>(sBlo + off) = lo;
+    }
+    for (int i = tid; i < D * TC_H; i += TC_PB) { sU1[i] = nv.U1[i]; sU2[i] = nv.U2 ? nv.U2[i] : 0.f; }
+    for (int i = tid; i < TC_H * D; i += TC_PB) sW3[i] = nv.W3[i];
+    for (int i = tid; i < D * D; i += TC_PB) sU3[i] = nv.U3 ? nv.U3[i] : 0.f;
+    const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
+    for (int i = tid; i < ntp; i += TC_PB) sTp[i] = a.tgt.mix[i];
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, TC_COLS);
+    if (tid == 0) umma::mbar_init(&mbar, 1);
+    umma::fence_async_smem();   // generic-proxy writes of the B tiles -> visible to the tensor core (async proxy)
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+
+    TcCtx<D> cx;
+    cx.sU1 = sU1; cx.sU2 = sU2; cx.sW3 = sW3; cx.sU3 = sU3;
+    cx.c1 = nv.c1; cx.c2 = nv.c2; cx.c3 = nv.c3;
+    cx.out_scale = nv.out_scale; cx.out_clip = nv.out_clip;
+    cx.tmem_base = tmem_slot;
+    cx.tmem_lane = tmem_slot + ((uint32_t)(warp * 32) << 16);
+    cx.bhi = umma::smem_u32(sBhi); cx.blo = umma::smem_u32(sBlo);
+    cx.mbar = &mbar; cx.parity = 0u;
+
+    const bool cais = (a.mode == CMCD_MODE_CAIS_SN || a.mode == CMCD_MODE_CAIS_VAR_SN);
+    const bool nn_b = (a.mode != CMCD_MODE_ULA);
+    const bool nn_f = cais;
+    const int K = a.K;
+
+    float mu[D], sig[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) { mu[j] = a.vd_mean[j]; sig[j] = expf(a.vd_logdiag[j]); }
+
+    const long long ntiles = (a.N + TC_PB - 1) / TC_PB;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long n_raw = tile * TC_PB + tid;
+        const bool active = n_raw < a.N;
+        const long long n = active ? n_raw : a.N - 1;   // tail lanes shadow the last particle (all 128 lanes take part in the MMA)
+        Key k = prng_key(a.seeds[n]);
+        Key ka;
+        split(k, ka, k);
+        float z[D], zn[D], xi[D];
+        normal_vec<D>(ka, xi);
+        float w = 0.f;
+        {   // z0 = sigma*xi + mu ; w = -log q(z0)   (vardist/diag_gauss.py:26-33,44-62)
+            float lq = 0.f;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                z[j] = sig[j] * xi[j] + mu[j];
+                const float v = (z[j] - mu[j]) / sig[j];
+                lq += -0.5f * v * v - logf(2.5066282746310002f * sig[j]);
+            }
+            w = -lq;
+        }
+        if (a.traj && active) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) a.traj[((size_t)0 * D + j) * a.N + n] = z[j];
+        }
+        float sp[D], dummy[D];
+        float lp = target_eval<D, false>(a.tgt, sTp, z, sp, dummy, dummy);
+        ka = split_first(k);    // mcdboundingmachine.py:162
+        k = split_second(ka);   // mcd_cais.py:94
+        float wm = 0.f;
+        // 2K half-steps, so that one copy of the network code serves both evaluations of a bridge step:
+        //   even h: NN(z, i)   -> forward kernel mean, sample z'      (mcd_cais.py:52-67)
+        //   odd  h: NN(z', tb) -> backward kernel mean, weight update (mcd_cais.py:71-87)
+        float mf[D], mb[D], nnv[D], skipacc[D];
+        float beta = 0.f, eps = 0.f, scale = 0.f;
+        for (int h = 0; h < 2 * K; ++h) {
+            const int i = h >> 1;
+            const bool bwd_half = (h & 1) != 0;
+            const int t = bwd_half ? (cais ? i + 1 : i) : i;
+            const bool use_nn = bwd_half ? nn_b : nn_f;
+            float xin[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) xin[j] = bwd_half ? zn[j] : z[j];
+            if (use_nn) tc_net_issue<D, ACT>(cx, t, xin, skipacc);
+            // ---- work that does not depend on the network output overlaps the MMA batch ----
+            if (!bwd_half) {
+                beta = __ldg(a.betas + i); eps = __ldg(a.eps + i);
+                scale = sqrtf(2.0f * eps);
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const float sq = -((z[j] - mu[j]) / sig[j]) / sig[j];
+                    const float gu = fminf(fmaxf(sp[j], -a.clip_t), a.clip_t);
+                    const float gq = fminf(fmaxf(sq, -a.clip_q), a.clip_q);
+                    const float uf = -(beta * gu + (1.0f - beta) * gq);
+                    mf[j] = z[j] - eps * uf;
+                }
+                split(k, ka, k);
+                normal_vec<D>(ka, xi);
+            } else {
+                lp = target_eval<D, false>(a.tgt, sTp, zn, sp, dummy, dummy);
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const float sq = -((zn[j] - mu[j]) / sig[j]) / sig[j];
+                    const float gu = fminf(fmaxf(sp[j], -a.clip_t), a.clip_t);
+                    const float gq = fminf(fmaxf(sq, -a.clip_q), a.clip_q);
+                    const float ub = -(beta * gu + (1.0f - beta) * gq);
+                    mb[j] = zn[j] - eps * ub;
+                }
+                k = split_second(k);
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j) nnv[j] = 0.f;
+            if (use_nn) tc_net_finish<D, ACT>(cx, t, xin, skipacc, nnv);
+            if (!bwd_half) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    mf[j] = mf[j] - eps * nnv[j];
+                    zn[j] = mf[j] + scale * xi[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < D; ++j) mb[j] = mb[j] + eps * nnv[j];
+                const float lognorm = logf(2.5066282746310002f * scale);
+                const float fk = gauss_logprob_tc<D>(zn, mf, scale, lognorm);
+                const float bk = gauss_logprob_tc<D>(z, mb, scale, lognorm);
+                wm += bk - fk;
+#pragma unroll
+                for (int j = 0; j < D; ++j) z[j] = zn[j];
+                if (a.traj && active) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) a.traj[((size_t)(i + 1) * D + j) * a.N + n] = z[j];
+                }
+            }
+        }
+        w += wm;
+        w += lp;
+        if (active) {
+            a.out_negw[n] = -w;
+#pragma unroll
+            for (int j = 0; j < D; ++j) a.out_z[n * D + j] = z[j];
+        }
+    }
+    umma::fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(cx.tmem_base, TC_COLS);
+}
+
+template <int D, int ACT>
+static int launch_fwd_tc_t(const BridgeArgs& a, cudaStream_t st, int num_sms) {
+    // request > 227/3 KB so that at most two CTAs (2 x 256 TMEM columns) share an SM
+    size_t smem = 2 * TC_B_BYTES + (2 * D * TC_H + TC_H * D + D * D + 4 + MIX_MAX * MIX_STRIDE + 8) * sizeof(float);
+    if (smem < 80 * 1024) smem = 80 * 1024;
+    auto kern = bridge_fwd_tc_kernel<D, ACT>;
+    CMCD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ntiles = (a.N + TC_PB - 1) / TC_PB;
+    long long grid = 2LL * num_sms;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, TC_PB, smem, st>>>(a);
+    CMCD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// hidden_pad == 64 networks (dds; geffner with x_dim + emb_dim in 57..64); K >= 1 and a network in use
+bool fwd_tc_supported(const BridgeArgs& a, int D) {
+    return a.net.arch != CMCD_ARCH_NONE && a.net.HP == TC_H && a.K >= 1 && a.mode != CMCD_MODE_ULA && (D == 2 || D == 10);
+}
+
+int launch_bridge_fwd_tc(const BridgeArgs& a, int D, cudaStream_t st, int num_sms) {
+    const bool dds = a.net.arch == CMCD_ARCH_DDS;
+    if (D == 2) return dds ? launch_fwd_tc_t<2, ACT_GELU>(a, st, num_sms) : launch_fwd_tc_t<2, ACT_SOFTPLUS>(a, st, num_sms);
+    if (D == 10) return dds ? launch_fwd_tc_t<10, ACT_GELU>(a, st, num_sms) : launch_fwd_tc_t<10, ACT_SOFTPLUS>(a, st, num_sms);
+    set_error("bridge_fwd_tc: dim=%d has no instantiation", D);
+    return 2;
+}
+
+}  // namespace cmcd

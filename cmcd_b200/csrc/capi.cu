@@ -2,6 +2,7 @@
 // marshalling into the kernel launchers.  No torch types, no allocation, enqueue-only.
 #include <cstdarg>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -17,6 +18,8 @@ void set_error(const char* fmt, ...) {
 }
 
 int launch_bridge_fwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sms);
+bool fwd_tc_supported(const BridgeArgs& a, int D);
+int launch_bridge_fwd_tc(const BridgeArgs& a, int D, cudaStream_t st, int num_sms);
 int launch_bridge_bwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, const float* cot_negw,
                       float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
                       const cmcd_net_grad* g_net, void* ws, size_t ws_bytes);
@@ -113,6 +116,9 @@ int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
     if (sms <= 0) { set_error("no CUDA device"); return 1; }
     if (target->kind == CMCD_TARGET_LGCP)
         return launch_wide_fwd(a, target, desc->dim, (cudaStream_t)stream, sms, workspace, workspace_bytes);
+    // hidden width 64: tcgen05 tiles; other widths: FP32 FMA kernel.  CMCD_DISABLE_TC=1 forces the FP32 kernel (A/B runs).
+    if (fwd_tc_supported(a, desc->dim) && !std::getenv("CMCD_DISABLE_TC"))
+        return launch_bridge_fwd_tc(a, desc->dim, (cudaStream_t)stream, sms);
     return launch_bridge_fwd(a, desc->dim, (cudaStream_t)stream, sms);
 }
 

@@ -68,6 +68,49 @@ __device__ __forceinline__ void act_fwd_grad(float x, float& a, float& da) {
     }
 }
 
+// ---- tensor-core path activations -------------------------------------------------------------------------
+// Exact-erf GELU via Abramowitz-Stegun 7.1.26: 0.5 erfc(|x|/sqrt 2) = t (a1 + t (a2 + ... a5 t)) exp(-x^2/2),
+// t = 1/(1 + p |x|/sqrt 2); |error| <= 7.5e-8 in exact arithmetic, 4.7e-7 on gelu in fp32 (the reference's own
+// fp32 formula x*0.5*(1+erf(x/sqrt 2)) carries 4.5e-7; tools/erf_accuracy.py).  14 instructions, 2 of them MUFU,
+// no predicate: gelu(x) = 0.5 x + |x| (0.5 - h).
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float gelu_half_erfc(float x, float& e_out) {
+    const float u = fabsf(x) * 0.84932180028801907f;               // u^2 = (x^2/2) log2 e
+    const float t = rcp_ftz(fmaf(u, 0.27273748088f, 1.0f));        // p / sqrt(log2 e), p = 0.3275911 (A&S 7.1.26)
+    const float e = ex2_ftz(-u * u);                               // exp(-x^2/2); flushes below 2^-126 (|x| > 13.2)
+    float q = 0.5307027145f;
+    q = fmaf(q, t, -0.7265760135f);
+    q = fmaf(q, t, 0.7107068705f);
+    q = fmaf(q, t, -0.142248368f);
+    q = fmaf(q, t, 0.127414796f);
+    e_out = e;
+    return (q * t) * e;                                            // h = 0.5 erfc(|x|/sqrt 2) in (0, 0.5]
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+    float e;
+    const float h = gelu_half_erfc(x, e);
+    return fmaf(fabsf(x), 0.5f - h, 0.5f * x);
+}
+__device__ __forceinline__ void gelu_fast_grad(float x, float& a, float& da) {
+    float e;
+    const float h = gelu_half_erfc(x, e);
+    const float w = 0.5f - h;                                      // >= 0
+    a = fmaf(fabsf(x), w, 0.5f * x);
+    const float cdf = 0.5f + copysignf(w, x);
+    da = fmaf(x * 0.3989422804014327f, e, cdf);
+}
+template <int ACT>
+__device__ __forceinline__ float act_tc(float x) {
+    if constexpr (ACT == ACT_GELU) return gelu_fast(x);
+    else return act_fwd<ACT>(x);
+}
+template <int ACT>
+__device__ __forceinline__ void act_tc_grad(float x, float& a, float& da) {
+    if constexpr (ACT == ACT_GELU) gelu_fast_grad(x, a, da);
+    else act_fwd_grad<ACT>(x, a, da);
+}
+
 // Device-side view of the network (pointers may be shared or global memory).
 struct NetView {
     int arch, H, HP, T;

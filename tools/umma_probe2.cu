@@ -1,0 +1,167 @@
+// tcgen05 probe 2: A operand from TMEM (the layout the tensor-core bridge kernels use), 3-pass tf32 split accuracy,
+// MMA batch latency, and the rounding behaviour of the fp32 accumulator.
+//   test 0: D[128x64] = A[128x64] * B[64x64]^T, A in TMEM (lane = row, column = k), B K-major core-matrix smem.
+//           Single pass: compared against the tf32-truncated product.
+//   test 1: same with the 3-pass split (hi/lo): compared against the exact fp64 product; reports max |err| / (|a|.|b|).
+//   test 2: cycles for the 24-MMA batch (issue -> mbarrier completion), and for 8 MMAs.
+//   test 3: accumulate 1.0 + 4096 x (0.75 ulp): round-to-nearest gives 1 + 4096 ulp = 1.00048828, truncation stays at 1.0,
+//           a wider internal accumulator gives ~1 + 3072 ulp = 1.00036621.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I cmcd_b200/csrc -o tools/build/umma_probe2 tools/umma_probe2.cu
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "umma.cuh"
+
+using namespace cmcd::umma;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("ERR %s line %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+__global__ void __launch_bounds__(128) probe2_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ Dout,
+                                                     long long* __restrict__ cycles, int test) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sBhi = smem;            // 64 x 64 fp32 = 16 KB
+    uint8_t* sBlo = smem + 16384;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t mbar;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 64 * 64; i += 128) {
+        const int n = i / 64, k = i % 64;
+        float hi, lo;
+        if (test == 0 || test == 3) { hi = B[i]; lo = 0.f; } else split_tf32(B[i], hi, lo);
+        *(float*)(sBhi + core_off(n, k, 64)) = hi;
+        *(float*)(sBlo + core_off(n, k, 64)) = lo;
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) mbar_init(&mbar, 1);
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t D_COL = 0, AH_COL = 64, AL_COL = 128;
+    // each thread writes its own row of A (hi / lo) into TMEM
+    for (int c = 0; c < 4; ++c) {
+        uint32_t h[16], l[16];
+        for (int j = 0; j < 16; ++j) {
+            float hi, lo;
+            const float a = A[tid * 64 + c * 16 + j];
+            if (test == 0 || test == 3) { hi = a; lo = 0.f; } else split_tf32(a, hi, lo);
+            h[j] = __float_as_uint(hi); l[j] = __float_as_uint(lo);
+        }
+        tmem_st16(lane_base + AH_COL + c * 16, h);
+        tmem_st16(lane_base + AL_COL + c * 16, l);
+    }
+    tmem_st_wait();
+    fence_before();
+    __syncthreads();
+    long long t0 = 0, t1 = 0;
+    uint32_t parity = 0;
+    const int reps = (test == 2) ? 2 : 1;
+    for (int rep = 0; rep < reps; ++rep) {
+        if (tid == 0) {
+            fence_after();
+            const uint32_t idesc = make_idesc_tf32(128, 64);
+            t0 = clock64();
+            const int npass = (test == 1 || (test == 2 && rep == 0)) ? 3 : 1;
+            for (int pass = 0; pass < npass; ++pass) {
+                const uint32_t acol = (pass == 2) ? AL_COL : AH_COL;
+                uint8_t* sB = (pass == 1) ? sBlo : sBhi;
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t bd = make_desc(smem_u32(sB) + k * 256, 128, 2048);
+                    mma_tf32_ts(tmem + D_COL, tmem + acol + k * 8, bd, idesc, (pass | k) > 0);
+                }
+            }
+            commit(&mbar);
+        }
+        mbar_wait(&mbar, parity);
+        parity ^= 1;
+        if (tid == 0) { t1 = clock64(); cycles[rep] = t1 - t0; }
+        fence_after();
+        __syncthreads();
+    }
+    if (test == 3) {
+        // accumulator rounding: accumulate 4096 more MMAs, each adding 0.75 ulp onto D ~ 1
+        // (host fills A row 0 = [1,0,...], B = identity-ish for the first MMA; here: re-issue with accumulate using the lo buffers)
+        for (int i = tid; i < 64 * 64; i += 128) {
+            const int n = i / 64, k = i % 64;
+            *(float*)(sBlo + core_off(n, k, 64)) = (n == k && k < 8) ? 8.940696716308594e-08f : 0.f;  // 0.75 ulp(1.0) = 1.5 * 2^-24 on the diagonal (first K block)
+        }
+        uint32_t ones[16];
+        for (int j = 0; j < 16; ++j) ones[j] = __float_as_uint(1.0f);
+        tmem_st16(lane_base + AL_COL, ones);
+        tmem_st_wait();
+        fence_async_smem();
+        fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after();
+            const uint32_t idesc = make_idesc_tf32(128, 64);
+            const uint64_t bd = make_desc(smem_u32(sBlo), 128, 2048);
+            for (int it = 0; it < 4096; ++it) mma_tf32_ts(tmem + D_COL, tmem + AL_COL, bd, idesc, 1);
+            commit(&mbar);
+        }
+        mbar_wait(&mbar, parity);
+        fence_after();
+    }
+    for (int c = 0; c < 4; ++c) {
+        uint32_t v[16];
+        tmem_ld16(lane_base + D_COL + c * 16, v);
+        tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) Dout[tid * 64 + c * 16 + j] = __uint_as_float(v[j]);
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+static float tf32_trunc(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
+
+int main() {
+    std::vector<float> A(128 * 64), B(64 * 64), D(128 * 64);
+    srand(1);
+    for (auto& x : A) x = (rand() / (float)RAND_MAX - 0.5f) * 4.f;
+    for (auto& x : B) x = (rand() / (float)RAND_MAX - 0.5f);
+    float *dA, *dB, *dD; long long* dC;
+    CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4)); CK(cudaMalloc(&dC, 64));
+    CK(cudaFuncSetAttribute(probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 1024));
+    for (int test = 0; test < 4; ++test) {
+        std::vector<float> At = A, Bt = B;
+        if (test == 3) {  // D starts as exactly 1.0 in column n<8 of every row: A = e_0-ish, B rows n<8 = e_0
+            for (auto& x : At) x = 0.f;
+            for (auto& x : Bt) x = 0.f;
+            for (int m = 0; m < 128; ++m) At[m * 64 + 0] = 1.0f;
+            for (int n = 0; n < 8; ++n) Bt[n * 64 + 0] = 1.0f;
+        }
+        CK(cudaMemcpy(dA, At.data(), At.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dB, Bt.data(), Bt.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemset(dD, 0xFF, D.size() * 4));
+        CK(cudaMemset(dC, 0, 64));
+        probe2_kernel<<<1, 128, 32768, 0>>>(dA, dB, dD, dC, test);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+        long long cyc[2]; CK(cudaMemcpy(cyc, dC, 16, cudaMemcpyDeviceToHost));
+        if (test == 3) {
+            printf("test 3: 1 + 4096 * 0.75ulp (RN 1.00048828, RZ 1.0, exact 1.00036621): D[0][0]=%.9f D[5][3]=%.9f D[100][7]=%.9f D[0][8]=%.9f\n", D[0], D[5 * 64 + 3], D[100 * 64 + 7], D[8]);
+            continue;
+        }
+        double maxerr = 0, maxrel = 0;
+        for (int m = 0; m < 128; ++m)
+            for (int n = 0; n < 64; ++n) {
+                double r = 0, nrm = 0;
+                for (int k = 0; k < 64; ++k) {
+                    const float a = At[m * 64 + k], b = Bt[n * 64 + k];
+                    r += (test == 0) ? (double)tf32_trunc(a) * tf32_trunc(b) : (double)a * b;
+                    nrm += fabs((double)a * b);
+                }
+                const double e = fabs(D[m * 64 + n] - r);
+                maxerr = fmax(maxerr, e); maxrel = fmax(maxrel, e / nrm);
+            }
+        printf("test %d: max abs err %.3e, max err/(|a|.|b|) %.3e, D[0][0..2]=%.5f %.5f %.5f, cycles batch0=%lld batch1=%lld\n", test, maxerr, maxrel,
+               D[0], D[1], D[2], cyc[0], cyc[1]);
+    }
+    return 0;
+}
