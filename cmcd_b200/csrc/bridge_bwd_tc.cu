@@ -1,0 +1,615 @@
+// Reverse-mode (adjoint) bridge kernel, tensor-core variant for the dds network (hidden width 64, d = 2).
+//
+// Same contract as bridge_bwd_kernel (bridge_bwd.cu): replaces the transposed scan of
+// jax.grad(compute_bound / compute_bound_var) (src/main.py:174-176 over src/mcdboundingmachine.py:126-231,
+// src/mcd_cais.py:46-89, src/mcd_cais_var.py:56-101, src/mcd_over_orig.py:18-55) with apply_fun_sn = PISNet
+// (src/nn_dds.py:145-164) in table form.  The per-step algebra is the one documented at the top of bridge_bwd.cu.
+//
+// Mapping: one CTA per SM, 256 threads = two independent 128-particle tiles (one warpgroup each, thread = particle =
+// TMEM lane) that alternate between CUDA-core phases and tensor-core batches:
+//   GEMM1  pre2 = a1 W2            A = a1 (tf32 hi/lo, TMEM, written by the owning threads), B = W2^T tile (smem)
+//   GEMM2  da1  = dp2 W2^T         A = dp2 (tf32 hi/lo, TMEM),                              B = W2 tile (smem)
+//   WGRAD  gW2 += a1^T dp2         kind::f16, bf16 hi+lo operands staged row-major per particle in shared memory
+//                                  (MN-major, 128B swizzle), M = 128 = [a1_hi ; a1_lo] stacked, N = 64, K = 128 particles;
+//                                  accumulates in TMEM across steps, flushed to a thread-private row every few steps
+//                                  (the tensor-core accumulator truncates, tools/umma_probe2.cu test 3).
+// TMEM per tile (256 columns): A_hi | A_lo | D (pre2, then da1) | gW2 accumulator.  Between GEMM1 and GEMM2 the dead
+// A region doubles as per-thread scratch for a2 / act'(pre2).  The skinny gradients (per-step bias tables, U1, W3)
+// are reduced over the 32 particles of a warp with a 16-wide shuffle butterfly and then added atomically.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace cmcd {
+
+constexpr int BT_H = 64;
+constexpr int BT_THREADS = 256;
+constexpr int BT_PB = 128;                    // particles per tile
+constexpr uint32_t BT_A_HI = 0, BT_A_LO = 64, BT_D12 = 128, BT_D3 = 192, BT_TILE_COLS = 256;
+constexpr int BT_T16K = 16384;                // one 64x64 fp32 tile, or one [128][64] bf16 tile
+constexpr int BT_OFF_BF_HI = 0, BT_OFF_BF_LO = BT_T16K, BT_OFF_BD_HI = 2 * BT_T16K, BT_OFF_BD_LO = 3 * BT_T16K;
+constexpr int BT_OFF_TILE = 4 * BT_T16K;      // + wg * 4 * BT_T16K : X_H1, X_H2 (a1), Z_G1, Z_G2 (dp2)
+constexpr int BT_OFF_SMALL = 12 * BT_T16K;    // 196608
+constexpr int BT_FLUSH_STEPS = 2;             // bridge steps between flushes of the TMEM gW2 accumulator
+
+struct BtLayout {  // offsets (floats) into one CTA's partial-gradient slice
+    int W2rows, c1, c2, c3, U1, W3, os, beta, eps, mu, ls, P;
+};
+
+static BtLayout bt_make_layout(int D, int K) {
+    BtLayout l;
+    int o = 0;
+    const int T = K + 1;
+    l.W2rows = o; o += 2 * BT_PB * BT_H;
+    l.c1 = o; o += T * BT_H;
+    l.c2 = o; o += T * BT_H;
+    l.c3 = o; o += T * D;
+    l.U1 = o; o += D * BT_H;
+    l.W3 = o; o += BT_H * D;
+    l.os = o; o += 1;
+    l.beta = o; o += K;
+    l.eps = o; o += K;
+    l.mu = o; o += D;
+    l.ls = o; o += D;
+    l.P = (o + 3) & ~3;
+    return l;
+}
+
+__device__ __forceinline__ float bt_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum v[e] over the 32 lanes of the warp for all 16 e at once (halving butterfly): returns the total of element
+// (lane >> 1), valid in every lane (lane pairs hold the same element).
+__device__ __forceinline__ float bt_warp_reduce16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float send = up ? v[k] : v[k + 8], keep = up ? v[k + 8] : v[k];
+            a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float send = up ? a[k] : a[k + 4], keep = up ? a[k + 4] : a[k];
+            b[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float send = up ? b[k] : b[k + 2], keep = up ? b[k + 2] : b[k];
+            c[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    const bool up = lane & 2;
+    const float send = up ? c[0] : c[1], keep = up ? c[1] : c[0];
+    float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+
+// 16 values of row q (hidden units 16c..16c+15) -> bf16 hi + bf16 lo parts in two MN-major SW128 tiles
+__device__ __forceinline__ void bt_stage_bf16x2(uint8_t* t1, uint8_t* t2, int q, int c, const float (&v)[16]) {
+    uint32_t h1[8], h2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+        const float2 f = __bfloat1622float2(hi);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[2 * k] - f.x, v[2 * k + 1] - f.y);
+        h1[k] = *reinterpret_cast<const uint32_t*>(&hi);
+        h2[k] = *reinterpret_cast<const uint32_t*>(&lo);
+    }
+    const int row = q * 128, sw = q & 7;
+    const int o0 = row + (((2 * c) ^ sw) << 4), o1 = row + (((2 * c + 1) ^ sw) << 4);
+    *reinterpret_cast<uint4*>(t1 + o0) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+    *reinterpret_cast<uint4*>(t1 + o1) = make_uint4(h1[4], h1[5], h1[6], h1[7]);
+    *reinterpret_cast<uint4*>(t2 + o0) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+    *reinterpret_cast<uint4*>(t2 + o1) = make_uint4(h2[4], h2[5], h2[6], h2[7]);
+}
+
+__device__ __forceinline__ void bt_bar(int wg) { asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory"); }
+
+// 24 x tcgen05.mma kind::tf32: D = A_hi B_lo + A_lo B_hi + A_hi B_hi (small terms first: the accumulator truncates)
+__device__ __forceinline__ void bt_issue_gemm(uint32_t tmem_base, uint32_t d_col, uint32_t bhi, uint32_t blo) {
+    const uint32_t idesc = umma::make_idesc_tf32(128, BT_H);
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t acol = tmem_base + (pass == 1 ? BT_A_LO : BT_A_HI);
+        const uint32_t baddr = (pass == 0) ? blo : bhi;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            umma::mma_tf32_ts(tmem_base + d_col, acol + k * 8, umma::make_desc(baddr + k * 256, 128, 32 * BT_H), idesc, (pass | k) > 0);
+    }
+}
+// 16 x tcgen05.mma kind::f16: D3[128 x 64] (+)= [X_H1 ; X_H2]^T (Z_G1 + Z_G2) over K = 128 particles
+__device__ __forceinline__ void bt_issue_wgrad(uint32_t tmem_base, uint32_t x_addr, uint32_t z_addr, bool fresh) {
+    const uint32_t idesc = umma::make_idesc_bf16_mn(128, BT_H);
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            umma::mma_f16_ss(tmem_base + BT_D3, umma::make_desc_sw128(x_addr + k * 2048, BT_T16K, 1024),
+                             umma::make_desc_sw128(z_addr + part * BT_T16K + k * 2048, BT_T16K, 1024), idesc,
+                             (part | k) > 0 || !fresh);
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const BridgeArgs a, const float* __restrict__ cot_negw,
+                                                                      float* __restrict__ partials, const BtLayout L) {
+    constexpr int ACT = ACT_GELU;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t mbars[2][3];
+    const int tid = threadIdx.x, wg = tid >> 7, q = tid & 127, warp = tid >> 5, lane = tid & 31;
+    const NetView& nv = a.net;
+    float* sf = reinterpret_cast<float*>(smem + BT_OFF_SMALL);
+    float* sU1 = sf;                        // [D][64]
+    float* sW3 = sU1 + D * BT_H;            // [64][D]
+    float* sAccU1 = sW3 + BT_H * D;         // [D][64]  gradient accumulators shared by both tiles
+    float* sAccW3 = sAccU1 + D * BT_H;      // [64][D]
+    float* sTp = sAccW3 + BT_H * D;         // mixture parameters
+    for (int idx = tid; idx < BT_H * BT_H; idx += BT_THREADS) {
+        const int i = idx / BT_H, j = idx % BT_H;
+        float hi, lo;
+        umma::split_tf32(nv.W2[idx], hi, lo);
+        const int of = umma::core_off(j, i, BT_H);   // GEMM1: B[n = j][k = i] = W2[i][j]
+        const int od = umma::core_off(i, j, BT_H);   // GEMM2: B[n = i][k = j] = W2[i][j]
+        *reinterpret_cast<float*>(smem + BT_OFF_BF_HI + of) = hi;
+        *reinterpret_cast<float*>(smem + BT_OFF_BF_LO + of) = lo;
+        *reinterpret_cast<float*>(smem + BT_OFF_BD_HI + od) = hi;
+        *reinterpret_cast<float*>(smem + BT_OFF_BD_LO + od) = lo;
+    }
+    for (int i = tid; i < D * BT_H; i += BT_THREADS) { sU1[i] = nv.U1[i]; sAccU1[i] = 0.f; }
+    for (int i = tid; i < BT_H * D; i += BT_THREADS) { sW3[i] = nv.W3[i]; sAccW3[i] = 0.f; }
+    const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
+    for (int i = tid; i < ntp; i += BT_THREADS) sTp[i] = a.tgt.mix[i];
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) umma::mbar_init(&mbars[0][0] + i, 1);
+    }
+    umma::fence_async_smem();
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+
+    const uint32_t tmem_base = tmem_slot + (uint32_t)wg * BT_TILE_COLS;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t bf_hi = umma::smem_u32(smem + BT_OFF_BF_HI), bf_lo = umma::smem_u32(smem + BT_OFF_BF_LO);
+    const uint32_t bd_hi = umma::smem_u32(smem + BT_OFF_BD_HI), bd_lo = umma::smem_u32(smem + BT_OFF_BD_LO);
+    uint8_t* tX1 = smem + BT_OFF_TILE + wg * 4 * BT_T16K;
+    uint8_t* tX2 = tX1 + BT_T16K;
+    uint8_t* tZ1 = tX1 + 2 * BT_T16K;
+    uint8_t* tZ2 = tX1 + 3 * BT_T16K;
+    const uint32_t x_addr = umma::smem_u32(tX1), z_addr = umma::smem_u32(tZ1);
+    uint64_t* mb1 = &mbars[wg][0];
+    uint64_t* mb2 = &mbars[wg][1];
+    uint64_t* mb3 = &mbars[wg][2];
+    uint32_t par1 = 0, par2 = 0, par3 = 0;
+
+    float* part = partials + (size_t)blockIdx.x * L.P;
+    float* w2row = part + L.W2rows + (size_t)(wg * BT_PB + q) * BT_H;   // this thread's private row of the stacked gW2 tile
+
+    const bool cais = (a.mode == CMCD_MODE_CAIS_SN || a.mode == CMCD_MODE_CAIS_VAR_SN);
+    const bool pathwise = a.mode != CMCD_MODE_CAIS_VAR_SN;
+    const bool nn_b = (a.mode != CMCD_MODE_ULA);
+    const bool nn_f = cais;
+    const int K = a.K;
+
+    float mu[D], sig[D], ivar[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) { mu[j] = a.vd_mean[j]; sig[j] = expf(a.vd_logdiag[j]); ivar[j] = 1.0f / (sig[j] * sig[j]); }
+
+    bool wgrad_pending = false;   // a WGRAD batch has been committed to mb3 and not yet waited for
+    bool d3_fresh = true;         // the TMEM gW2 accumulator holds nothing (next WGRAD starts with accumulate = 0)
+    int d3_steps = 0;
+
+    // flush: gW2 accumulator (this thread's TMEM lane, 64 columns) += into the thread-private global row
+    auto flush_d3 = [&]() {
+        if (wgrad_pending) { umma::mbar_wait(mb3, par3); par3 ^= 1u; wgrad_pending = false; }
+        umma::fence_after();
+        if (!d3_fresh) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[16];
+                umma::tmem_ld16(tmem_lane + BT_D3 + c * 16, v);
+                float4* g = reinterpret_cast<float4*>(w2row + c * 16);
+                float4 r0 = g[0], r1 = g[1], r2 = g[2], r3 = g[3];
+                umma::tmem_ld_wait();
+                r0.x += __uint_as_float(v[0]); r0.y += __uint_as_float(v[1]); r0.z += __uint_as_float(v[2]); r0.w += __uint_as_float(v[3]);
+                r1.x += __uint_as_float(v[4]); r1.y += __uint_as_float(v[5]); r1.z += __uint_as_float(v[6]); r1.w += __uint_as_float(v[7]);
+                r2.x += __uint_as_float(v[8]); r2.y += __uint_as_float(v[9]); r2.z += __uint_as_float(v[10]); r2.w += __uint_as_float(v[11]);
+                r3.x += __uint_as_float(v[12]); r3.y += __uint_as_float(v[13]); r3.z += __uint_as_float(v[14]); r3.w += __uint_as_float(v[15]);
+                g[0] = r0; g[1] = r1; g[2] = r2; g[3] = r3;
+            }
+        }
+        d3_fresh = true;
+        d3_steps = 0;
+        umma::fence_before();
+    };
+
+    const long long ntiles = (a.N + BT_PB - 1) / BT_PB;
+    for (long long tile = (long long)blockIdx.x * 2 + wg; tile < ntiles; tile += 2LL * gridDim.x) {
+        const long long n_raw = tile * BT_PB + q;
+        const bool active = n_raw < a.N;
+        const long long n = active ? n_raw : a.N - 1;   // tail lanes shadow the last particle with zero cotangent
+        const float c = active ? -cot_negw[n] : 0.f;    // dL/dw_n
+        float zp[D], z[D], adj[D], abar[D], gmu[D], gls[D], zero[D], hv[D], sp[D], spp[D], r[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            zp[j] = a.traj[((size_t)K * D + j) * a.N + n];
+            gmu[j] = 0.f; gls[j] = 0.f; zero[j] = 0.f; adj[j] = 0.f; abar[j] = 0.f; z[j] = 0.f; sp[j] = 0.f; r[j] = 0.f; hv[j] = 0.f;
+        }
+        // terminal: w += log p(z_K)  (mcdboundingmachine.py:178); stop-gradiented in the log-var mode
+        target_eval<D, false>(a.tgt, sTp, zp, spp, zero, hv);
+        if (pathwise) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) adj[j] = c * spp[j];
+        }
+        float g1s[4][16];               // act'(pre1) of the current evaluation, chunk-indexed with static indices only
+        float beta = 0.f, eps = 0.f, ts = 1.f, omb = 0.f, gb = 0.f, ge = 0.f, rr = 0.f;
+
+        // 2K half-steps, last bridge step first; odd h: backward-kernel mean at z' (net t = tb), even h: forward-kernel mean at z
+        for (int h = 2 * K - 1; h >= 0; --h) {
+            const int i = h >> 1;
+            const bool isB = (h & 1) != 0;
+            if (isB) {
+                beta = __ldg(a.betas + i); eps = __ldg(a.eps + i);
+                ts = 2.0f * eps; omb = 1.0f - beta;
+#pragma unroll
+                for (int j = 0; j < D; ++j) z[j] = a.traj[((size_t)i * D + j) * a.N + n];
+                gb = 0.f; ge = 0.f;
+            }
+            const int t = isB ? (cais ? i + 1 : i) : i;
+            const bool use_nn = isB ? nn_b : nn_f;
+            const float sgn = isB ? 1.0f : -1.0f;
+            float x[D], sx[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) { x[j] = isB ? zp[j] : z[j]; sx[j] = isB ? spp[j] : sp[j]; }
+
+            // ---------------- layer 1, A operand, a1 staging; GEMM1 ----------------
+            if (use_nn) {
+                if (isB && d3_steps >= BT_FLUSH_STEPS) flush_d3();
+                if (wgrad_pending) { umma::mbar_wait(mb3, par3); par3 ^= 1u; wgrad_pending = false; }   // a1 / dp2 staging tiles are free again
+                const float4* __restrict__ c1v = reinterpret_cast<const float4*>(nv.c1 + (size_t)t * BT_H);
+#pragma unroll 1
+                for (int cc = 0; cc < 4; ++cc) {
+                    float a1[16], g1[16];
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const float4 cv = __ldg(c1v + cc * 4 + qq);
+                        float p[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            const float4 u = *reinterpret_cast<const float4*>(sU1 + d * BT_H + cc * 16 + qq * 4);
+                            p[0] = fmaf(x[d], u.x, p[0]); p[1] = fmaf(x[d], u.y, p[1]);
+                            p[2] = fmaf(x[d], u.z, p[2]); p[3] = fmaf(x[d], u.w, p[3]);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) act_tc_grad<ACT>(p[e], a1[qq * 4 + e], g1[qq * 4 + e]);
+                    }
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        if (k4 == cc) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) g1s[k4][e] = g1[e];
+                        }
+                    }
+                    uint32_t hh[16], ll[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        float hi, lo;
+                        umma::split_tf32(a1[e], hi, lo);
+                        hh[e] = __float_as_uint(hi); ll[e] = __float_as_uint(lo);
+                    }
+                    umma::tmem_st16(tmem_lane + BT_A_HI + cc * 16, hh);
+                    umma::tmem_st16(tmem_lane + BT_A_LO + cc * 16, ll);
+                    bt_stage_bf16x2(tX1, tX2, q, cc, a1);
+                }
+                umma::tmem_st_wait();
+                umma::fence_before();
+                umma::fence_async_smem();
+                bt_bar(wg);
+                if (q == 0) {
+                    umma::fence_after();
+                    bt_issue_gemm(tmem_base, BT_D12, bf_hi, bf_lo);
+                    umma::commit(mb1);
+                }
+            }
+
+            // ---------------- independent of the network: score-side terms at x ----------------
+            float sq[D], mk_t[D], mk_q[D], u[D], mean[D], dc[D], G[D], nn[D], dx[D], xs[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                sq[j] = -(x[j] - mu[j]) * ivar[j];
+                mk_t[j] = (fabsf(sx[j]) <= a.clip_t) ? 1.f : 0.f;
+                mk_q[j] = (fabsf(sq[j]) <= a.clip_q) ? 1.f : 0.f;
+                const float gu = fminf(fmaxf(sx[j], -a.clip_t), a.clip_t);
+                const float gq = fminf(fmaxf(sq[j], -a.clip_q), a.clip_q);
+                dc[j] = gu - gq;                       // d(-u)/dbeta
+                u[j] = -(beta * gu + omb * gq);
+                mean[j] = x[j] - eps * u[j];
+                nn[j] = 0.f; dx[j] = 0.f; xs[j] = 0.f;
+            }
+            if (isB) target_eval<D, false>(a.tgt, sTp, z, sp, zero, hv);   // score at z, used by the forward-kernel half
+
+            // ---------------- epilogue 1: a2, act'(pre2), raw network output ----------------
+            float o[D];
+#pragma unroll
+            for (int m = 0; m < D; ++m) o[m] = 0.f;
+            if (use_nn) {
+#pragma unroll
+                for (int m = 0; m < D; ++m) o[m] = __ldg(nv.c3 + (size_t)t * D + m);
+                const float4* __restrict__ c2v = reinterpret_cast<const float4*>(nv.c2 + (size_t)t * BT_H);
+                umma::mbar_wait(mb1, par1); par1 ^= 1u;
+                umma::fence_after();
+#pragma unroll 1
+                for (int cc = 0; cc < 4; ++cc) {
+                    uint32_t v[16], a2u[16], g2u[16];
+                    umma::tmem_ld16(tmem_lane + BT_D12 + cc * 16, v);
+                    umma::tmem_ld_wait();
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const float4 cv = __ldg(c2v + cc * 4 + qq);
+                        const float p[4] = {__uint_as_float(v[qq * 4 + 0]) + cv.x, __uint_as_float(v[qq * 4 + 1]) + cv.y,
+                                            __uint_as_float(v[qq * 4 + 2]) + cv.z, __uint_as_float(v[qq * 4 + 3]) + cv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float a2, g2;
+                            act_tc_grad<ACT>(p[e], a2, g2);
+                            const int j = cc * 16 + qq * 4 + e;
+#pragma unroll
+                            for (int m = 0; m < D; ++m) o[m] = fmaf(a2, sW3[j * D + m], o[m]);
+                            a2u[qq * 4 + e] = __float_as_uint(a2);
+                            g2u[qq * 4 + e] = __float_as_uint(g2);
+                        }
+                    }
+                    // the A region is dead between GEMM1 and GEMM2: park a2 / act'(pre2) in this thread's lane
+                    umma::tmem_st16(tmem_lane + BT_A_HI + cc * 16, a2u);
+                    umma::tmem_st16(tmem_lane + BT_A_LO + cc * 16, g2u);
+                }
+                umma::tmem_st_wait();
+#pragma unroll
+                for (int m = 0; m < D; ++m) nn[m] = nv.out_scale * fminf(fmaxf(o[m], -nv.out_clip), nv.out_clip);
+            }
+
+            // ---------------- kernel mean, residual, cotangent on the mean ----------------
+#pragma unroll
+            for (int j = 0; j < D; ++j) mean[j] = mean[j] + sgn * eps * nn[j];
+            if (isB) {
+                rr = 0.f;
+#pragma unroll
+                for (int j = 0; j < D; ++j) { r[j] = (z[j] - mean[j]) / ts; G[j] = c * r[j]; rr = fmaf(r[j], r[j], rr); }
+            } else {
+                float xx = 0.f;
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    xs[j] = (zp[j] - mean[j]) / ts;     // = xi / s
+                    xx = fmaf(xs[j], xs[j], xx);
+                    G[j] = pathwise ? abar[j] : -c * xs[j];
+                }
+                if (!pathwise) ge -= c * xx;
+            }
+
+            // ---------------- output-layer VJP, dp2, GEMM2 + WGRAD ----------------
+            if (use_nn) {
+                float vo[D], gos = 0.f;
+#pragma unroll
+                for (int m = 0; m < D; ++m) {
+                    const float v = sgn * eps * G[m];
+                    const float oc = fminf(fmaxf(o[m], -nv.out_clip), nv.out_clip);
+                    gos = fmaf(v, oc, gos);
+                    vo[m] = (fabsf(o[m]) <= nv.out_clip) ? v * nv.out_scale : 0.f;
+                    const float s = bt_warp_sum(vo[m]);
+                    if (lane == 0) atomicAdd(part + L.c3 + (size_t)t * D + m, s);
+                }
+                gos = bt_warp_sum(gos);
+                if (lane == 0 && gos != 0.f) atomicAdd(part + L.os, gos);
+#pragma unroll 1
+                for (int cc = 0; cc < 4; ++cc) {
+                    uint32_t a2u[16], g2u[16];
+                    umma::tmem_ld16(tmem_lane + BT_A_HI + cc * 16, a2u);
+                    umma::tmem_ld16(tmem_lane + BT_A_LO + cc * 16, g2u);
+                    umma::tmem_ld_wait();
+                    float dp2[16];
+                    uint32_t hh[16], ll[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int j = cc * 16 + e;
+                        float s = 0.f;
+#pragma unroll
+                        for (int m = 0; m < D; ++m) s = fmaf(sW3[j * D + m], vo[m], s);
+                        dp2[e] = s * __uint_as_float(g2u[e]);
+                        float hi, lo;
+                        umma::split_tf32(dp2[e], hi, lo);
+                        hh[e] = __float_as_uint(hi); ll[e] = __float_as_uint(lo);
+                    }
+                    umma::tmem_st16(tmem_lane + BT_A_HI + cc * 16, hh);
+                    umma::tmem_st16(tmem_lane + BT_A_LO + cc * 16, ll);
+                    bt_stage_bf16x2(tZ1, tZ2, q, cc, dp2);
+                    // gc2[t][j] += sum_p dp2 ; gW3[j][m] += sum_p a2 vo[m]
+                    const float s2 = bt_warp_reduce16(dp2, lane);
+                    if (!(lane & 1)) atomicAdd(part + L.c2 + (size_t)t * BT_H + cc * 16 + (lane >> 1), s2);
+#pragma unroll
+                    for (int m = 0; m < D; ++m) {
+                        float tmp[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) tmp[e] = __uint_as_float(a2u[e]) * vo[m];
+                        const float s3 = bt_warp_reduce16(tmp, lane);
+                        if (!(lane & 1)) atomicAdd(sAccW3 + (cc * 16 + (lane >> 1)) * D + m, s3);
+                    }
+                }
+                umma::tmem_st_wait();
+                umma::fence_before();
+                umma::fence_async_smem();
+                bt_bar(wg);
+                if (q == 0) {
+                    umma::fence_after();
+                    bt_issue_gemm(tmem_base, BT_D12, bd_hi, bd_lo);
+                    umma::commit(mb2);
+                    bt_issue_wgrad(tmem_base, x_addr, z_addr, d3_fresh);
+                    umma::commit(mb3);
+                }
+                wgrad_pending = true;
+                d3_fresh = false;
+            }
+
+            // ---------------- independent of the network: target Hessian-vector product at x ----------------
+            if (pathwise) {
+                float vm[D], dummy[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) vm[j] = mk_t[j] * G[j];
+                target_eval<D, true>(a.tgt, sTp, x, dummy, vm, hv);
+            }
+
+            // ---------------- epilogue 2: dp1 = da1 * act'(pre1), dx = U1 dp1, layer-1 gradients ----------------
+            if (use_nn) {
+                umma::mbar_wait(mb2, par2); par2 ^= 1u;
+                umma::fence_after();
+#pragma unroll 1
+                for (int cc = 0; cc < 4; ++cc) {
+                    uint32_t v[16];
+                    umma::tmem_ld16(tmem_lane + BT_D12 + cc * 16, v);
+                    umma::tmem_ld_wait();
+                    float dp1[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const float g = (cc == 0) ? g1s[0][e] : (cc == 1) ? g1s[1][e] : (cc == 2) ? g1s[2][e] : g1s[3][e];
+                        dp1[e] = __uint_as_float(v[e]) * g;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) dx[d] = fmaf(sU1[d * BT_H + cc * 16 + e], dp1[e], dx[d]);
+                    }
+                    const float s1 = bt_warp_reduce16(dp1, lane);
+                    if (!(lane & 1)) atomicAdd(part + L.c1 + (size_t)t * BT_H + cc * 16 + (lane >> 1), s1);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        float tmp[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) tmp[e] = x[d] * dp1[e];
+                        const float s4 = bt_warp_reduce16(tmp, lane);
+                        if (!(lane & 1)) atomicAdd(sAccU1 + d * BT_H + cc * 16 + (lane >> 1), s4);
+                    }
+                }
+                umma::fence_before();
+            }
+
+            // ---------------- combine ----------------
+            if (pathwise) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const float base = isB ? adj[j] : -c * r[j];
+                    const float res = base + G[j] + eps * (beta * hv[j] - omb * ivar[j] * mk_q[j] * G[j]) + dx[j];
+                    if (isB) abar[j] = res; else adj[j] = res;
+                }
+            }
+            if (isB) ge += c * rr;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                gb += eps * G[j] * dc[j];
+                ge += G[j] * (-u[j] + sgn * nn[j] + ((!isB && pathwise) ? xs[j] : 0.f));
+                const float wq = eps * omb;
+                gmu[j] += wq * ivar[j] * G[j] * mk_q[j];
+                gls[j] += wq * G[j] * mk_q[j] * (-2.0f * sq[j]);
+            }
+            if (!isB) {
+                const float gbs = bt_warp_sum(gb), ges = bt_warp_sum(ge);
+                if (lane == 0) { atomicAdd(part + L.beta + i, gbs); atomicAdd(part + L.eps + i, ges); }
+#pragma unroll
+                for (int j = 0; j < D; ++j) { zp[j] = z[j]; spp[j] = sp[j]; }
+                ++d3_steps;
+            }
+        }
+        // initial: z0 = mu + sigma xi0, w0 = -log q(z0) = 0.5|xi0|^2 + sum log(sqrt(2pi) sigma)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            if (pathwise) { gmu[j] += adj[j]; gls[j] += adj[j] * (zp[j] - mu[j]); }
+            gls[j] += c;
+            const float m1 = bt_warp_sum(gmu[j]), m2 = bt_warp_sum(gls[j]);
+            if (lane == 0) { atomicAdd(part + L.mu + j, m1); atomicAdd(part + L.ls + j, m2); }
+        }
+    }
+    flush_d3();
+    __syncthreads();
+    for (int i = tid; i < D * BT_H; i += BT_THREADS) part[L.U1 + i] = sAccU1[i];
+    for (int i = tid; i < BT_H * D; i += BT_THREADS) part[L.W3 + i] = sAccW3[i];
+    umma::fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_slot, 512);
+}
+
+// out[k] = sum over CTAs of the partial slices; gW2[i][j] = sum of the stacked rows i and 64 + i of both tiles
+struct BtOut {
+    float *W2, *U1, *W3, *c1, *c2, *c3, *os, *beta, *eps, *mu, *ls;
+};
+
+__global__ void bwd_tc_reduce_kernel(const float* __restrict__ partials, int nblocks, BtLayout L, BtOut o, int D, int K) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nW2 = BT_H * BT_H;
+    if (k < nW2) {
+        float s = 0.f;
+        for (int b = 0; b < nblocks; ++b) {
+            const float* p = partials + (size_t)b * L.P + L.W2rows;
+            s += (p[k] + p[nW2 + k]) + (p[2 * nW2 + k] + p[3 * nW2 + k]);   // tile 0 rows i, 64+i; tile 1 rows i, 64+i
+        }
+        if (o.W2) o.W2[k] = s;
+        return;
+    }
+    const int kk = L.c1 + (k - nW2);
+    if (kk >= L.P) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * L.P + kk];
+    auto put = [&](float* dst, int off, int len) { if (dst && kk >= off && kk < off + len) dst[kk - off] = s; };
+    put(o.c1, L.c1, L.c2 - L.c1); put(o.c2, L.c2, L.c3 - L.c2); put(o.c3, L.c3, L.U1 - L.c3);
+    put(o.U1, L.U1, L.W3 - L.U1); put(o.W3, L.W3, L.os - L.W3); put(o.os, L.os, 1);
+    put(o.beta, L.beta, K); put(o.eps, L.eps, K); put(o.mu, L.mu, D); put(o.ls, L.ls, D);
+}
+
+static size_t bt_smem_bytes(int D) {
+    return (size_t)BT_OFF_SMALL + (size_t)(4 * D * BT_H + MIX_MAX * MIX_STRIDE + 8) * sizeof(float);
+}
+
+bool bwd_tc_supported(const BridgeArgs& a, int D) {
+    return a.net.arch == CMCD_ARCH_DDS && a.net.HP == BT_H && a.K >= 1 && a.mode != CMCD_MODE_ULA && D == 2;
+}
+
+size_t bridge_bwd_tc_workspace_bytes(int D, int K, int num_sms) {
+    return (size_t)num_sms * bt_make_layout(D, K).P * sizeof(float);
+}
+
+int launch_bridge_bwd_tc(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, const float* cot_negw,
+                         float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
+                         const cmcd_net_grad* g, void* ws, size_t ws_bytes) {
+    if (D != 2) { set_error("bridge_bwd_tc: dim=%d has no instantiation", D); return 2; }
+    const BtLayout L = bt_make_layout(D, a.K);
+    const long long ntiles = (a.N + BT_PB - 1) / BT_PB;
+    long long grid = (ntiles + 1) / 2;
+    if (grid > num_sms) grid = num_sms;
+    if (grid < 1) grid = 1;
+    const size_t need = (size_t)grid * L.P * sizeof(float);
+    if (!ws || ws_bytes < need) { set_error("bridge_bwd_tc: workspace too small (%zu < %zu)", ws_bytes, need); return 2; }
+    const size_t smem = bt_smem_bytes(D);
+    auto kern = bridge_bwd_tc_kernel<2>;
+    CMCD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CMCD_CUDA_OK(cudaMemsetAsync(ws, 0, need, st));
+    kern<<<(unsigned)grid, BT_THREADS, smem, st>>>(a, cot_negw, (float*)ws, L);
+    CMCD_CUDA_OK(cudaGetLastError());
+    BtOut o{};
+    if (g) { o.W2 = g->W2; o.U1 = g->U1; o.W3 = g->W3; o.c1 = g->c1; o.c2 = g->c2; o.c3 = g->c3; o.os = g->out_scale; }
+    o.beta = g_betas; o.eps = g_eps; o.mu = g_vd_mean; o.ls = g_vd_logdiag;
+    const int nout = BT_H * BT_H + (L.P - L.c1);
+    bwd_tc_reduce_kernel<<<(nout + 255) / 256, 256, 0, st>>>((const float*)ws, (int)grid, L, o, D, a.K);
+    CMCD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace cmcd

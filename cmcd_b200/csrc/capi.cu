@@ -24,6 +24,11 @@ int launch_bridge_bwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, 
                       float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
                       const cmcd_net_grad* g_net, void* ws, size_t ws_bytes);
 size_t bridge_bwd_workspace_bytes(int D, int K, int HP, int arch, int num_sms);
+bool bwd_tc_supported(const BridgeArgs& a, int D);
+size_t bridge_bwd_tc_workspace_bytes(int D, int K, int num_sms);
+int launch_bridge_bwd_tc(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, const float* cot_negw,
+                         float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
+                         const cmcd_net_grad* g_net, void* ws, size_t ws_bytes);
 int launch_loss_stats(cudaStream_t st, const float* negw, long long n, float* out4);
 int launch_batched_elbo_lnz(cudaStream_t st, const float* losses, int batches, int n, float* elbo, float* lnz);
 int launch_threefry(cudaStream_t st, const uint32_t* key2, const uint32_t* x0, const uint32_t* x1, long long n, uint32_t* y0, uint32_t* y1);
@@ -125,7 +130,12 @@ int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
 size_t cmcd_bridge_bwd_workspace_bytes(const cmcd_bridge_desc* desc, const cmcd_net* net) {
     const int sms = num_sms() > 0 ? num_sms() : 148;
     const int arch = (net && desc->mode != CMCD_MODE_ULA) ? net->arch : CMCD_ARCH_NONE;
-    return bridge_bwd_workspace_bytes(desc->dim, desc->nbridges, net ? net->hidden_pad : 0, arch, sms);
+    size_t need = bridge_bwd_workspace_bytes(desc->dim, desc->nbridges, net ? net->hidden_pad : 0, arch, sms);
+    if (arch == CMCD_ARCH_DDS && net->hidden_pad == 64 && desc->dim == 2) {
+        const size_t tc = bridge_bwd_tc_workspace_bytes(desc->dim, desc->nbridges, sms);
+        if (tc > need) need = tc;
+    }
+    return need;
 }
 
 int cmcd_bridge_bwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* seeds, const float* vd_mean,
@@ -140,6 +150,9 @@ int cmcd_bridge_bwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
     if (sms <= 0) { set_error("no CUDA device"); return 1; }
     if (target->kind == CMCD_TARGET_LGCP) { set_error("lgcp reverse pass not implemented in this build"); return 2; }
     if (!traj || !cot_negw) { set_error("bridge_bwd needs traj and cot_negw"); return 2; }
+    if (bwd_tc_supported(a, desc->dim) && !std::getenv("CMCD_DISABLE_TC"))
+        return launch_bridge_bwd_tc(a, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
+                                    g_eps, g_net, workspace, workspace_bytes);
     return launch_bridge_bwd(a, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
                              g_eps, g_net, workspace, workspace_bytes);
 }

@@ -56,6 +56,39 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 
+// ---- kind::f16 with bf16 operands, both MN-major, SWIZZLE_128B (validated by tools/umma_probe3.cu) ----------------
+// An MN-major operand tile is a plain row-major [k][64] bf16 array (128 B per k row, the eight 16 B chunks of a row
+// XOR-ed with k % 8): exactly what a thread that owns row k can write with two STS.128 per 16 elements.  Groups of
+// 8 k-rows are SBO = 1024 B apart; further 64-wide groups of the M/N dimension are LBO bytes apart (stacked tiles).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ inline uint32_t make_idesc_bf16_mn(int M, int N) {
+    uint32_t d = 0;
+    d |= 1u << 4;                  // c_format = F32
+    d |= 1u << 7;                  // a_format = BF16
+    d |= 1u << 10;                 // b_format = BF16
+    d |= 1u << 15;                 // A MN-major
+    d |= 1u << 16;                 // B MN-major
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
+    return d;
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// byte offset of element (k, i) in an MN-major SW128 bf16 tile
+__host__ __device__ inline int sw128_off(int k, int i) { return k * 128 + ((((i / 8) ^ (k % 8)) * 16) + (i % 8) * 2); }
+
 // make all previously issued tcgen05.mma of this thread arrive on `mbar` when they complete
 __device__ __forceinline__ void commit(uint64_t* mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(mbar)) : "memory");
