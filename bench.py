@@ -33,6 +33,22 @@ FLOP_FWD = 35.0e3
 FLOP_TRAIN = 105.0e3
 
 
+# ncu --set full capture of bridge_bwd_tc_kernel at N=131072, K=256 (profiles/r1_ncu_summary.md):
+# dram__bytes_read.sum 339.5 MB + dram__bytes_write.sum 56.8 MB per launch
+NCU_BWD_DRAM_BYTES_PER_PARTICLE = (339.520256e6 + 56.849408e6) / 131072
+
+
+def _tensor_peak():
+    """Dense bf16 tensor peak for the roofline denominator: MEASURED_PEAKS.json (sustained: the kernel is timed inside a
+    long step), else the profiling recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mp = json.load(f)
+        return float(mp["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
+    except (OSError, KeyError, ValueError):
+        return 1400.0, "B200_PROFILING.md fallback, sustained bf16 (of fallback)"
+
+
 def _synthetic_params(unflatten, pf, dim, device):
     """SURVEY 8d convention: reference init distributions, but a live drift head so the network path is exercised."""
     pt, pn = unflatten(pf)
@@ -223,6 +239,27 @@ def main():
         sampler.terminate()
     lnz_est = global_ln_z(l)
 
+    # ---- sampling-only ln Z estimate (north_star's second throughput figure): forward bridge + global logsumexp ----
+    from cmcd_b200 import utils as U
+
+    def sample_step(seeds):
+        with torch.no_grad():
+            l, z = local_forward(seeds, pf)
+        st = U.loss_stats(l)           # [sum l, sum l^2, max(-l), sum exp(-l - max)] in one launch
+        return l, st
+
+    for i in range(min(2, args.warmup)):
+        sample_step(seeds_dev[i])
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(args.steps):
+        l_s, st = sample_step(seeds_dev[args.warmup + i])
+    s1.record()
+    barrier()
+    ms_sample = s0.elapsed_time(s1) / args.steps
+    lnz_sampling = global_ln_z(l_s)
+
     # ---- end-to-end timing: host seeds in (pinned), gradient + loss back on the host ----
     g_host = torch.empty(pf.numel(), dtype=torch.float32).pin_memory()
     barrier()
@@ -238,15 +275,17 @@ def main():
     barrier()
     ms_e2e = t0.elapsed_time(t1) / args.steps
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_e2e, ms_sample], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t[0].item(), t[1].item()
+    ms, ms_e2e, ms_sample = t[0].item(), t[1].item(), t[2].item()
     if rank == 0:
         value = n_global * NBRIDGES / (ms * 1e-3)
         e2e = n_global * NBRIDGES / (ms_e2e * 1e-3)
         ach_bwd = (FLOP_TRAIN - FLOP_FWD) * n_local * NBRIDGES / (bwd_ms * 1e-3) / 1e12
         ach_fwd = FLOP_FWD * n_local * NBRIDGES / (fwd_ms * 1e-3) / 1e12
+        tensor_peak, peak_source = _tensor_peak()
+        traffic_bwd = NCU_BWD_DRAM_BYTES_PER_PARTICLE * n_local
         out = {
             "metric": "particle_steps_per_sec_train_iter", "value": value, "unit": "particle-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -259,13 +298,28 @@ def main():
             "e2e": {"value": e2e, "unit": "particle-steps/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": 4 * n_local, "d2h_bytes_per_step": 4 * pf.numel() + 8},
             "gpu_launches": launches,
-            "roofline": {"bound": "fp32", "kernel": "bridge_bwd_kernel", "achieved": ach_bwd, "peak": fp32_peak_tflops,
-                         "unit": "TFLOP/s", "frac": ach_bwd / fp32_peak_tflops, "traffic": None,
-                         "peak_source": "measured live: cmcd_ffma_probe (FFMA dependent chains, CUDA events); "
-                                        "MEASURED_PEAKS.json has no FP32-pipe entry",
-                         "algorithmic_flops_per_particle_step": FLOP_TRAIN - FLOP_FWD, "avg_launch_ms": bwd_ms,
-                         "fwd_kernel": {"kernel": "bridge_fwd_kernel", "achieved": ach_fwd, "frac": ach_fwd / fp32_peak_tflops,
-                                        "algorithmic_flops_per_particle_step": FLOP_FWD, "avg_launch_ms": fwd_ms}},
+            "gpu_launches_note": "per timed region: (forward bridge + adjoint + partial-gradient reduce) x steps, this library only",
+            "roofline": {
+                "bound": "tensor", "kernel": "bridge_bwd_tc_kernel", "achieved": ach_bwd, "peak": tensor_peak, "unit": "TFLOP/s",
+                "frac": ach_bwd / tensor_peak, "traffic": traffic_bwd,
+                "peak_source": peak_source,
+                "algorithmic_flops_per_particle_step": FLOP_TRAIN - FLOP_FWD, "avg_launch_ms": bwd_ms,
+                "note": "the dense contractions (64x64 layer: forward, input-gradient and weight-gradient products) run on "
+                        "tcgen05 tiles (tf32 3-pass / bf16 hi+lo), so the contract's denominator is the tensor pipe; the kernel "
+                        "itself is bounded by CUDA-core issue slots (exact-erf GELU and derivative, threefry, mixture scores / "
+                        "HVPs, operand splitting) -- see profiles/r1_ncu_summary.md for the measured pipe utilisations",
+                "fp32_pipe": {"peak_measured_tflops": fp32_peak_tflops, "achieved_over_fp32_peak": ach_bwd / fp32_peak_tflops,
+                              "what": "algorithmic TFLOP/s over the measured FFMA peak (cmcd_ffma_probe): the ceiling of any "
+                                      "CUDA-core-only implementation is 1.0"},
+                "traffic_note": "dram__bytes_read+write of this kernel from the ncu --set full capture at N=131072 "
+                                "(profiles/r1_ncu_summary.md), scaled linearly to this run's particle count; algorithmic bytes "
+                                "= trajectory re-read 8(K+1) B + seed/cotangent 8 B per particle",
+                "fwd_kernel": {"kernel": "bridge_fwd_tc_kernel", "achieved": ach_fwd, "frac": ach_fwd / tensor_peak,
+                               "achieved_over_fp32_peak": ach_fwd / fp32_peak_tflops,
+                               "algorithmic_flops_per_particle_step": FLOP_FWD, "avg_launch_ms": fwd_ms}},
+            "sampling_ln_z": {"metric": "particle_steps_per_sec_sampling", "value": n_global * NBRIDGES / (ms_sample * 1e-3),
+                              "unit": "particle-steps/s", "ms_per_step": ms_sample, "ln_Z_estimate": lnz_sampling,
+                              "what": "forward bridge + one-launch logsumexp statistics + max/sum all-reduce (opt.sample path)"},
             "clocks": _parse_clocks(clock_file, local_rank),
             "quality": {"loss_mean_finite": float(l[torch.isfinite(l)].mean().item()),
                         "finite_frac": float(torch.isfinite(l).float().mean().item()), "ln_Z_estimate": lnz_est,

@@ -40,6 +40,7 @@ EXPORTS = {
     "cmcd_last_error": (C.c_char_p, []),
     "cmcd_version": (C.c_int, []),
     "cmcd_num_sms": (C.c_int, []),
+    "cmcd_xla_ffi_available": (C.c_int, []),
     "cmcd_bridge_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(CmcdBridgeDesc), C.POINTER(CmcdNet), C.POINTER(CmcdTarget)]),
     "cmcd_bridge_fwd": (C.c_int, [C.POINTER(CmcdBridgeDesc), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNet),
                                   C.POINTER(CmcdTarget), _fp, _fp, _fp, _fp, C.c_size_t]),

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcmcd_b200.so")
-SOURCES = ["capi.cu", "bridge_fwd.cu", "bridge_fwd_tc.cu", "bridge_bwd.cu", "bridge_bwd_tc.cu", "reduce.cu", "wide.cu"]
+SOURCES = ["capi.cu", "bridge_fwd.cu", "bridge_fwd_tc.cu", "bridge_bwd.cu", "bridge_bwd_tc.cu", "reduce.cu", "wide.cu", "xla_ffi.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--threads", "0"]
 
@@ -29,9 +29,11 @@ def build(force=False, verbose=False):
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(HERE, "build", os.path.splitext(src)[0] + ".o")
         objs.append(obj)
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if src == "xla_ffi.cc" and os.environ.get("CMCD_XLA_FFI_INCLUDE"):  # jax.ffi.include_dir(): enables the FFI handlers
+            cmd += ["-I", os.environ["CMCD_XLA_FFI_INCLUDE"]]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

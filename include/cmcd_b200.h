@@ -93,6 +93,10 @@ typedef struct cmcd_bridge_desc {
 const char* cmcd_last_error(void);
 int cmcd_version(void);
 int cmcd_num_sms(void);
+/* 1 if the library was built with the XLA-FFI handlers CmcdBridgeFwd / CmcdBridgeBwd (csrc/xla_ffi.cc; needs jaxlib's
+ * xla/ffi/api/ffi.h at build time), 0 otherwise.  The handlers wrap cmcd_bridge_fwd / cmcd_bridge_bwd for
+ * jax.ffi.ffi_call under the reference's jax.jit(jax.grad(compute_bound_fn)) (main.py:162-177); see INTEGRATION.md. */
+int cmcd_xla_ffi_available(void);
 
 /*
  * Forward bridge: replaces the jitted vmap(compute_log_elbo) of
