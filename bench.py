@@ -26,6 +26,15 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner, ...) are sent to stderr
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
 NBRIDGES = 256
 N_PER_GPU = 1 << 20
 # algorithmic flops per particle-step: forward 35.0 kflop, KL train 105 kflop
@@ -114,7 +123,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     v = n * NBRIDGES / dt
     sample = f"N={n} particles x K={NBRIDGES} bridges per step (README.md:26 config), fp32 torch-CPU autograd"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "particle_steps_per_sec_train_iter", "value": v, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -123,7 +132,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference JAX path cannot run here (no jax/jaxlib in the image); this is the oracle restatement",
-    }))
+    })
 
 
 def cpu_baseline_sample(budget_s=20.0):
@@ -327,7 +336,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample()
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -38,6 +38,10 @@ int launch_target_eval(cudaStream_t st, const TargetDesc& t, int D, const float*
 int launch_ffma_peak(cudaStream_t st, float* scratch, int blocks, int iters);
 int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStream_t st, int num_sms, void* ws, size_t ws_bytes);
 size_t wide_fwd_workspace_bytes(long long N, int d, int HP);
+size_t wide_bwd_workspace_bytes(long long N, int d, int HP);
+int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStream_t st, int num_sms, const float* cot_negw,
+                    float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps, const cmcd_net_grad* g,
+                    void* ws, size_t ws_bytes);
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -130,6 +134,8 @@ int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
 size_t cmcd_bridge_bwd_workspace_bytes(const cmcd_bridge_desc* desc, const cmcd_net* net) {
     const int sms = num_sms() > 0 ? num_sms() : 148;
     const int arch = (net && desc->mode != CMCD_MODE_ULA) ? net->arch : CMCD_ARCH_NONE;
+    if (desc->dim > 64)   // wide path (lgcp, d = 1600): [N x d] / [N x hidden] state + split-K partials
+        return wide_bwd_workspace_bytes(desc->n_particles, desc->dim, arch != CMCD_ARCH_NONE ? net->hidden_pad : 0);
     size_t need = bridge_bwd_workspace_bytes(desc->dim, desc->nbridges, net ? net->hidden_pad : 0, arch, sms);
     if (arch == CMCD_ARCH_DDS && net->hidden_pad == 64 && desc->dim == 2) {
         const size_t tc = bridge_bwd_tc_workspace_bytes(desc->dim, desc->nbridges, sms);
@@ -148,8 +154,11 @@ int cmcd_bridge_bwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
     a.traj = const_cast<float*>(traj);
     const int sms = num_sms();
     if (sms <= 0) { set_error("no CUDA device"); return 1; }
-    if (target->kind == CMCD_TARGET_LGCP) { set_error("lgcp reverse pass not implemented in this build"); return 2; }
     if (!traj || !cot_negw) { set_error("bridge_bwd needs traj and cot_negw"); return 2; }
+    if (a.N == 0) { set_error("bridge_bwd: empty particle batch"); return 2; }
+    if (target->kind == CMCD_TARGET_LGCP)
+        return launch_wide_bwd(a, target, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
+                               g_eps, g_net, workspace, workspace_bytes);
     if (bwd_tc_supported(a, desc->dim) && !std::getenv("CMCD_DISABLE_TC"))
         return launch_bridge_bwd_tc(a, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
                                     g_eps, g_net, workspace, workspace_bytes);

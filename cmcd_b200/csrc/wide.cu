@@ -159,6 +159,12 @@ __global__ void __launch_bounds__(256) wide_target_fin_kernel(const float* __res
 
 // ---- network finalize kernels (geffner table form with x folded into the first d hidden units) ----
 // stage 1: a1 = softplus(sum part + c1[t]); A1 = a1 + pad(x)
+__device__ __forceinline__ float sigmoid_f(float x) {
+    const float e = expf(-fabsf(x));
+    const float s = 1.0f / (1.0f + e);
+    return x >= 0.f ? s : 1.0f - s;
+}
+// (a1 / a2 outputs: if non-null they receive softplus'(pre) = sigmoid(pre), which is what the reverse pass needs)
 __global__ void wide_l1_fin_kernel(const float* __restrict__ part, int S, int N, int HP, int d, const float* __restrict__ c1t,
                                    const float* __restrict__ x, int fold_x, float* a1, float* A1) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,7 +173,7 @@ __global__ void wide_l1_fin_kernel(const float* __restrict__ part, int S, int N,
     float p = c1t[j];
     for (int s = 0; s < S; ++s) p += part[((size_t)s * N + n) * HP + j];
     const float a = softplus_f(p);
-    if (a1) a1[i] = a;
+    if (a1) a1[i] = sigmoid_f(p);
     A1[i] = a + ((fold_x && j < d) ? x[(size_t)n * d + j] : 0.f);
 }
 // stage 2: a2 = softplus(sum part + c2[t]); A2 = a2 + skip*A1   (A1 already holds a1 + pad(x))
@@ -179,7 +185,7 @@ __global__ void wide_l2_fin_kernel(const float* __restrict__ part, int S, int N,
     float p = c2t[j];
     for (int s = 0; s < S; ++s) p += part[((size_t)s * N + n) * HP + j];
     const float a = softplus_f(p);
-    if (a2) a2[i] = a;
+    if (a2) a2[i] = sigmoid_f(p);
     A2[i] = a + skip * A1[i];
 }
 
@@ -342,6 +348,360 @@ int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
     wide_final_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(w, lp, (int)N, a.out_negw);
     CMCD_CUDA_OK(cudaGetLastError());
     CMCD_CUDA_OK(cudaMemcpyAsync(a.out_z, z, (size_t)N * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+
+// =====================================================================================================================
+// Reverse pass of the wide path (lgcp): recompute from the stored z_k trajectory, same per-step algebra as
+// bridge_bwd.cu (documented there), every R^d / R^HP vector operation as a [N x .] kernel and every product with a
+// 1620-wide weight matrix or the dense K^-1 as a skinny GEMM served from L2.
+// Replaces jax.grad of compute_bound (src/main.py:174-176) for log_prob_model = LogGaussianCoxPines
+// (src/model_handler.py:287-409): H v = -K^-1 v - a exp(x) o v.
+// Table cotangents: the wide path folds x into the first d hidden units (A1 = a1 + pad(x)), so the x-rows of W2 / W3
+// receive the U2 / U3 cotangents too (U2 = W2[:d], U3 = W3[:d] for the geffner net, nn.py:45-52); g_U2 = g_U3 = 0.
+
+// Y[n][j] = sum_m X[n][m] W[j][m] (+ addend[n][j]);  Y2[n][j] = Y[n][j] * mult[n][j].  One warp per row j of W.
+constexpr int WT_NT = 10;   // particles per register tile
+__global__ void __launch_bounds__(256) wide_gemm_t_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
+                                                          int N, int J, int M, const float* __restrict__ addend, int lda,
+                                                          const float* __restrict__ mult, int ldm, float* __restrict__ Y,
+                                                          float* __restrict__ Y2, int ldy) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < J; j += gridDim.x * wpb) {
+        const float* __restrict__ wr = W + (size_t)j * ldw;
+        for (int n0 = 0; n0 < N; n0 += WT_NT) {
+            float acc[WT_NT];
+#pragma unroll
+            for (int r = 0; r < WT_NT; ++r) acc[r] = 0.f;
+            for (int m = lane * 4; m < M; m += 128) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(wr + m));
+#pragma unroll
+                for (int r = 0; r < WT_NT; ++r) {
+                    if (n0 + r < N) {
+                        const float4 x = *reinterpret_cast<const float4*>(X + (size_t)(n0 + r) * ldx + m);
+                        acc[r] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[r]))));
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < WT_NT; ++r) {
+                float v = acc[r];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && n0 + r < N) {
+                    const int n = n0 + r;
+                    if (addend) v += addend[(size_t)n * lda + j];
+                    Y[(size_t)n * ldy + j] = v;
+                    if (Y2) Y2[(size_t)n * ldy + j] = v * mult[(size_t)n * ldm + j];
+                }
+            }
+        }
+    }
+}
+
+// G[i][j] += sum_n A[n][i] B[n][j]
+__global__ void __launch_bounds__(128) wide_outer_acc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                             int N, int I, int J, float* __restrict__ G, int ldg) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int i = blockIdx.y;
+    if (j >= J || i >= I) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = 0; n < N; ++n) {
+        const float a = __ldg(A + (size_t)n * lda + i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(B + (size_t)n * ldb + j));
+        acc.x = fmaf(a, b.x, acc.x); acc.y = fmaf(a, b.y, acc.y); acc.z = fmaf(a, b.z, acc.z); acc.w = fmaf(a, b.w, acc.w);
+    }
+    float4* g = reinterpret_cast<float4*>(G + (size_t)i * ldg + j);
+    float4 o = *g;
+    o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+    *g = o;
+}
+
+// g[j] += sum_n V[n][j]
+__global__ void wide_colsum_acc_kernel(const float* __restrict__ V, int ldv, int N, int J, float* __restrict__ g) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= J) return;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += V[(size_t)n * ldv + j];
+    g[j] += s;
+}
+
+__global__ void wide_neg_kernel(const float* __restrict__ cot, int N, float* __restrict__ c) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) c[n] = -cot[n];
+}
+
+// out[n][j] = traj[j][n]  (trajectory rows are stored particle-fastest)
+__global__ void wide_gather_kernel(const float* __restrict__ traj_row, int N, int d, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * d) return;
+    const int n = i / d, j = i % d;
+    out[i] = traj_row[(size_t)j * N + n];
+}
+
+// adj = scale[n] * sp   (terminal term w += log p(z_K))
+__global__ void wide_scale_rows_kernel(const float* __restrict__ c, const float* __restrict__ v, int N, int d, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N * d) out[i] = c[i / d] * v[i];
+}
+
+// One half-step (isB: backward-kernel mean at x = z', else forward-kernel mean at x = z): network output from the
+// layer-3 partials, kernel mean, residual, cotangent G on the mean, output-layer cotangent vo, HVP input vm, and the
+// per-step scalar / vd cotangents.  One block per particle.
+struct WideHalfArgs {
+    const float *part3, *c3t, *x, *sx, *z, *zp, *abar, *c, *mu, *logdiag, *betas, *epss;
+    float *G, *vo, *vm, *r, *gmu_acc, *gls_acc, *g_beta, *g_eps, *g_os;
+    int S3, N, d, step, isB, pathwise, use_nn;
+    float out_scale, out_clip, clip_t, clip_q;
+};
+__global__ void __launch_bounds__(256) wide_half_kernel(const WideHalfArgs a) {
+    __shared__ float sh[32];
+    const int n = blockIdx.x;
+    const float beta = a.betas[a.step], eps = a.epss[a.step], omb = 1.0f - beta, ts = 2.0f * eps;
+    const float sgn = a.isB ? 1.0f : -1.0f, c = a.c[n], wq = eps * omb;
+    float gb = 0.f, ge = 0.f, gos = 0.f, q2 = 0.f;
+    for (int j = threadIdx.x; j < a.d; j += blockDim.x) {
+        const size_t e = (size_t)n * a.d + j;
+        float o = 0.f, nn = 0.f;
+        if (a.use_nn) {
+            o = a.c3t[j];
+            for (int s = 0; s < a.S3; ++s) o += a.part3[((size_t)s * a.N + n) * a.d + j];
+            nn = a.out_scale * fminf(fmaxf(o, -a.out_clip), a.out_clip);
+        }
+        const float sg = expf(a.logdiag[j]), ivar = 1.0f / (sg * sg);
+        const float x = a.x[e], sx = a.sx[e];
+        const float sq = -(x - a.mu[j]) * ivar;
+        const float mk_t = (fabsf(sx) <= a.clip_t) ? 1.f : 0.f, mk_q = (fabsf(sq) <= a.clip_q) ? 1.f : 0.f;
+        const float gu = fminf(fmaxf(sx, -a.clip_t), a.clip_t), gq = fminf(fmaxf(sq, -a.clip_q), a.clip_q);
+        const float dc = gu - gq, u = -(beta * gu + omb * gq);
+        const float mean = (x - eps * u) + sgn * eps * nn;
+        float G, xs = 0.f;
+        if (a.isB) {
+            const float r = (a.z[e] - mean) / ts;
+            a.r[e] = r;
+            G = c * r;
+            q2 = fmaf(r, r, q2);
+        } else {
+            xs = (a.zp[e] - mean) / ts;
+            q2 = fmaf(xs, xs, q2);
+            G = a.pathwise ? a.abar[e] : -c * xs;
+        }
+        const float v = sgn * eps * G;
+        gos = fmaf(v, fminf(fmaxf(o, -a.out_clip), a.out_clip), gos);
+        a.vo[e] = (a.use_nn && fabsf(o) <= a.out_clip) ? v * a.out_scale : 0.f;
+        a.G[e] = G;
+        a.vm[e] = mk_t * G;
+        gb += eps * G * dc;
+        ge += G * (-u + sgn * nn + ((!a.isB && a.pathwise) ? xs : 0.f));
+        a.gmu_acc[e] += wq * ivar * G * mk_q;
+        a.gls_acc[e] += wq * G * mk_q * (-2.0f * sq);
+    }
+    gb = block_sum(gb, sh);
+    ge = block_sum(ge, sh);
+    gos = block_sum(gos, sh);
+    q2 = block_sum(q2, sh);
+    if (threadIdx.x == 0) {
+        if (a.isB) ge += c * q2;                       // c |r|^2
+        else if (!a.pathwise) ge -= c * q2;            // -c |xi/s|^2
+        atomicAdd(a.g_beta + a.step, gb);
+        atomicAdd(a.g_eps + a.step, ge);
+        if (a.use_nn && a.g_os) atomicAdd(a.g_os, gos);
+    }
+}
+
+// res = base + G + eps (beta H vm - (1-beta) ivar mk_q G) + dx,  H vm = -K^-1 vm - a exp(x) vm,  dx = dA1[:, :d] + dp1 U1^T
+// (already summed into dxnet); base = adj (isB) or -c r.
+struct WideCombineArgs {
+    const float *kpart, *x, *G, *vm, *dxnet, *base_adj, *r, *c, *mu, *logdiag, *betas, *epss;
+    float* out;
+    int S, N, d, step, isB, use_nn;
+    float area, clip_q;
+};
+__global__ void wide_combine_kernel(const WideCombineArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N * a.d) return;
+    const int n = i / a.d, j = i % a.d;
+    const float beta = a.betas[a.step], eps = a.epss[a.step], omb = 1.0f - beta;
+    float kd = 0.f;
+    for (int s = 0; s < a.S; ++s) kd += a.kpart[((size_t)s * a.N + n) * a.d + j];
+    const float x = a.x[i];
+    const float hv = -kd - a.area * expf(x) * a.vm[i];
+    const float sg = expf(a.logdiag[j]), ivar = 1.0f / (sg * sg);
+    const float sq = -(x - a.mu[j]) * ivar;
+    const float mk_q = (fabsf(sq) <= a.clip_q) ? 1.f : 0.f;
+    const float G = a.G[i];
+    const float base = a.isB ? a.base_adj[i] : -a.c[n] * a.r[i];
+    a.out[i] = base + G + eps * (beta * hv - omb * ivar * mk_q * G) + (a.use_nn ? a.dxnet[i] : 0.f);
+}
+
+// g_mu[j] = sum_n (gmu_acc + adj), g_ls[j] = sum_n (gls_acc + adj (z0 - mu) + c)
+__global__ void wide_vd_final_kernel(const float* __restrict__ gmu_acc, const float* __restrict__ gls_acc, const float* __restrict__ adj,
+                                     const float* __restrict__ z0, const float* __restrict__ c, const float* __restrict__ mu,
+                                     int N, int d, int pathwise, float* __restrict__ g_mu, float* __restrict__ g_ls) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    float m = 0.f, l = 0.f;
+    for (int n = 0; n < N; ++n) {
+        const size_t e = (size_t)n * d + j;
+        m += gmu_acc[e]; l += gls_acc[e] + c[n];
+        if (pathwise) { m += adj[e]; l += adj[e] * (z0[e] - mu[j]); }
+    }
+    if (g_mu) g_mu[j] = m;
+    if (g_ls) g_ls[j] = l;
+}
+
+struct WideBwdWs {
+    size_t zp, z, spp, sp, adj, abar, G, vo, vm, r, dx, gmu, gls, lp, c, A1, A2, s1, s2, dA, dp, part, total;
+};
+static WideBwdWs wide_bwd_layout(long long N, int d, int HP) {
+    WideBwdWs L;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
+    const size_t nd = (size_t)N * d, nh = (size_t)N * HP;
+    L.zp = take(nd); L.z = take(nd); L.spp = take(nd); L.sp = take(nd); L.adj = take(nd); L.abar = take(nd);
+    L.G = take(nd); L.vo = take(nd); L.vm = take(nd); L.r = take(nd); L.dx = take(nd); L.gmu = take(nd); L.gls = take(nd);
+    L.lp = take(N); L.c = take(N);
+    L.A1 = take(nh); L.A2 = take(nh); L.s1 = take(nh); L.s2 = take(nh); L.dA = take(nh); L.dp = take(nh);
+    const int mx = HP > d ? HP : d;
+    L.part = take((size_t)64 * N * mx);
+    L.total = o;
+    return L;
+}
+size_t wide_bwd_workspace_bytes(long long N, int d, int HP) { return wide_bwd_layout(N, d, HP > 0 ? HP : 8).total * sizeof(float); }
+
+int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStream_t st, int num_sms, const float* cot_negw,
+                    float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps, const cmcd_net_grad* g,
+                    void* ws, size_t ws_bytes) {
+    const long long N = a.N;
+    const int d = D, K = a.K;
+    const NetView& nv = a.net;
+    const bool has_net = nv.arch != CMCD_ARCH_NONE;
+    const int HP = has_net ? nv.HP : 8;
+    if (has_net && nv.arch != CMCD_ARCH_GEFFNER) { set_error("lgcp wide path: only nn_arch=geffner is implemented (README.md:63 config)"); return 2; }
+    if ((d & 3) || (HP & 3)) { set_error("lgcp wide path: dim and hidden_pad must be multiples of 4"); return 2; }
+    const WideBwdWs L = wide_bwd_layout(N, d, HP);
+    if (!ws || ws_bytes < L.total * sizeof(float)) { set_error("wide_bwd: workspace too small (%zu < %zu)", ws_bytes, L.total * sizeof(float)); return 2; }
+    float* f = (float*)ws;
+    float *zp = f + L.zp, *z = f + L.z, *spp = f + L.spp, *sp = f + L.sp, *adj = f + L.adj, *abar = f + L.abar;
+    float *G = f + L.G, *vo = f + L.vo, *vm = f + L.vm, *r = f + L.r, *dx = f + L.dx, *gmu = f + L.gmu, *gls = f + L.gls;
+    float *lp = f + L.lp, *c = f + L.c, *A1 = f + L.A1, *A2 = f + L.A2, *s1 = f + L.s1, *s2 = f + L.s2, *dA = f + L.dA, *dp = f + L.dp;
+    float* part = f + L.part;
+    const bool cais = (a.mode == CMCD_MODE_CAIS_SN || a.mode == CMCD_MODE_CAIS_VAR_SN);
+    const bool pathwise = a.mode != CMCD_MODE_CAIS_VAR_SN;
+    const bool nn_b = (a.mode != CMCD_MODE_ULA) && has_net, nn_f = cais && has_net;
+    const int nd = (int)N * d, nh = (int)N * HP;
+    const int T = K + 1;
+    int S = 1;
+
+    // outputs are overwritten: zero the accumulators
+    CMCD_CUDA_OK(cudaMemsetAsync(gmu, 0, (size_t)nd * sizeof(float), st));
+    CMCD_CUDA_OK(cudaMemsetAsync(gls, 0, (size_t)nd * sizeof(float), st));
+    CMCD_CUDA_OK(cudaMemsetAsync(adj, 0, (size_t)nd * sizeof(float), st));
+    if (g_betas && K) CMCD_CUDA_OK(cudaMemsetAsync(g_betas, 0, (size_t)K * sizeof(float), st));
+    if (g_eps && K) CMCD_CUDA_OK(cudaMemsetAsync(g_eps, 0, (size_t)K * sizeof(float), st));
+    float *gU1 = nullptr, *gW2 = nullptr, *gW3 = nullptr, *gc1 = nullptr, *gc2 = nullptr, *gc3 = nullptr, *gos = nullptr;
+    if (g && has_net) {
+        gU1 = g->U1; gW2 = g->W2; gW3 = g->W3; gc1 = g->c1; gc2 = g->c2; gc3 = g->c3; gos = g->out_scale;
+        if (!gU1 || !gW2 || !gW3 || !gc1 || !gc2 || !gc3 || !gos) { set_error("wide_bwd: every network cotangent buffer is required"); return 2; }
+        CMCD_CUDA_OK(cudaMemsetAsync(gU1, 0, (size_t)d * HP * sizeof(float), st));
+        CMCD_CUDA_OK(cudaMemsetAsync(gW2, 0, (size_t)HP * HP * sizeof(float), st));
+        CMCD_CUDA_OK(cudaMemsetAsync(gW3, 0, (size_t)HP * d * sizeof(float), st));
+        CMCD_CUDA_OK(cudaMemsetAsync(gc1, 0, (size_t)T * HP * sizeof(float), st));
+        CMCD_CUDA_OK(cudaMemsetAsync(gc2, 0, (size_t)T * HP * sizeof(float), st));
+        CMCD_CUDA_OK(cudaMemsetAsync(gc3, 0, (size_t)T * d * sizeof(float), st));
+        CMCD_CUDA_OK(cudaMemsetAsync(gos, 0, sizeof(float), st));
+        if (g->U2) CMCD_CUDA_OK(cudaMemsetAsync(g->U2, 0, (size_t)d * HP * sizeof(float), st));
+        if (g->U3) CMCD_CUDA_OK(cudaMemsetAsync(g->U3, 0, (size_t)d * d * sizeof(float), st));
+    }
+    // scalar cotangents need a buffer even if the caller passes NULL
+    float* gbeta_buf = g_betas ? g_betas : part;   // (NULL only when K == 0: never touched)
+    float* geps_buf = g_eps ? g_eps : part;
+
+    auto ew = [&](int n) { return dim3((unsigned)((n + 255) / 256)); };
+    auto target_at = [&](const float* x, float* score) -> int {
+        if (int rc = run_gemm(st, x, d, tg->lgcp_mu0, tg->lgcp_kinv, d, (int)N, d, d, num_sms, part, &S)) return rc;
+        wide_target_fin_kernel<<<(unsigned)N, 256, 0, st>>>(part, S, (int)N, d, x, tg->lgcp_counts, tg->lgcp_mu0,
+                                                            tg->lgcp_log_norm, tg->lgcp_bin_area, score, lp);
+        CMCD_CUDA_OK(cudaGetLastError());
+        return 0;
+    };
+    auto net_fwd_store = [&](const float* x, int t, int* S3) -> int {
+        const int blk = (nh + 255) / 256;
+        if (int rc = run_gemm(st, x, d, 0.f, nv.U1, HP, (int)N, d, HP, num_sms, part, &S)) return rc;
+        wide_l1_fin_kernel<<<blk, 256, 0, st>>>(part, S, (int)N, HP, d, nv.c1 + (size_t)t * HP, x, 1, s1, A1);
+        CMCD_CUDA_OK(cudaGetLastError());
+        if (int rc = run_gemm(st, A1, HP, 0.f, nv.W2, HP, (int)N, HP, HP, num_sms, part, &S)) return rc;
+        wide_l2_fin_kernel<<<blk, 256, 0, st>>>(part, S, (int)N, HP, nv.c2 + (size_t)t * HP, A1, 1.f, s2, A2);
+        CMCD_CUDA_OK(cudaGetLastError());
+        return run_gemm(st, A2, HP, 0.f, nv.W3, d, (int)N, HP, d, num_sms, part, S3);
+    };
+    const int tgrid = 2 * num_sms;
+    // network VJP for cotangent vo on the raw output at (x, t): parameter cotangents accumulate, dx -> `dx`
+    auto net_bwd = [&](const float* x, int t) -> int {
+        // dA2 = vo W3^T ; dp2 = dA2 * softplus'(pre2)
+        wide_gemm_t_kernel<<<tgrid, 256, 0, st>>>(vo, d, nv.W3, d, (int)N, HP, d, nullptr, 0, s2, HP, dA, dp, HP);
+        CMCD_CUDA_OK(cudaGetLastError());
+        wide_outer_acc_kernel<<<dim3((d / 4 + 127) / 128, HP), 128, 0, st>>>(A2, HP, vo, d, (int)N, HP, d, gW3, d);
+        wide_colsum_acc_kernel<<<ew(d), 256, 0, st>>>(vo, d, (int)N, d, gc3 + (size_t)t * d);
+        wide_outer_acc_kernel<<<dim3((HP / 4 + 127) / 128, HP), 128, 0, st>>>(A1, HP, dp, HP, (int)N, HP, HP, gW2, HP);
+        wide_colsum_acc_kernel<<<ew(HP), 256, 0, st>>>(dp, HP, (int)N, HP, gc2 + (size_t)t * HP);
+        CMCD_CUDA_OK(cudaGetLastError());
+        // dA1 = dA2 + dp2 W2^T ; dp1 = dA1 * softplus'(pre1)     (in place: dA <- dA1, dp <- dp1 after the products above)
+        wide_gemm_t_kernel<<<tgrid, 256, 0, st>>>(dp, HP, nv.W2, HP, (int)N, HP, HP, dA, HP, s1, HP, A2, s2, HP);   // A2 <- dA1, s2 <- dp1 (both dead)
+        CMCD_CUDA_OK(cudaGetLastError());
+        wide_outer_acc_kernel<<<dim3((HP / 4 + 127) / 128, d), 128, 0, st>>>(x, d, s2, HP, (int)N, d, HP, gU1, HP);
+        wide_colsum_acc_kernel<<<ew(HP), 256, 0, st>>>(s2, HP, (int)N, HP, gc1 + (size_t)t * HP);
+        // dx = dA1[:, :d] + dp1 U1^T
+        wide_gemm_t_kernel<<<tgrid, 256, 0, st>>>(s2, HP, nv.U1, HP, (int)N, d, HP, A2, HP, nullptr, 0, dx, nullptr, d);
+        CMCD_CUDA_OK(cudaGetLastError());
+        return 0;
+    };
+
+    wide_neg_kernel<<<ew((int)N), 256, 0, st>>>(cot_negw, (int)N, c);
+    wide_gather_kernel<<<ew(nd), 256, 0, st>>>(a.traj + (size_t)K * d * N, (int)N, d, zp);
+    CMCD_CUDA_OK(cudaGetLastError());
+    if (int rc = target_at(zp, spp)) return rc;
+    if (pathwise) wide_scale_rows_kernel<<<ew(nd), 256, 0, st>>>(c, spp, (int)N, d, adj);
+    for (int i = K - 1; i >= 0; --i) {
+        wide_gather_kernel<<<ew(nd), 256, 0, st>>>(a.traj + (size_t)i * d * N, (int)N, d, z);
+        CMCD_CUDA_OK(cudaGetLastError());
+        for (int half = 1; half >= 0; --half) {
+            const bool isB = half == 1;
+            const float* x = isB ? zp : z;
+            const float* sx = isB ? spp : sp;
+            const int t = isB ? (cais ? i + 1 : i) : i;
+            const bool use_nn = isB ? nn_b : nn_f;
+            int S3 = 1;
+            if (!isB) { if (int rc = target_at(z, sp)) return rc; }
+            if (use_nn) { if (int rc = net_fwd_store(x, t, &S3)) return rc; }
+            WideHalfArgs h{};
+            h.part3 = part; h.c3t = has_net ? nv.c3 + (size_t)t * d : nullptr; h.x = x; h.sx = sx; h.z = z; h.zp = zp; h.abar = abar;
+            h.c = c; h.mu = a.vd_mean; h.logdiag = a.vd_logdiag; h.betas = a.betas; h.epss = a.eps;
+            h.G = G; h.vo = vo; h.vm = vm; h.r = r; h.gmu_acc = gmu; h.gls_acc = gls; h.g_beta = gbeta_buf; h.g_eps = geps_buf; h.g_os = gos;
+            h.S3 = S3; h.N = (int)N; h.d = d; h.step = i; h.isB = isB; h.pathwise = pathwise; h.use_nn = use_nn;
+            h.out_scale = nv.out_scale; h.out_clip = nv.out_clip; h.clip_t = a.clip_t; h.clip_q = a.clip_q;
+            wide_half_kernel<<<(unsigned)N, 256, 0, st>>>(h);
+            CMCD_CUDA_OK(cudaGetLastError());
+            if (use_nn) { if (int rc = net_bwd(x, t)) return rc; }
+            if (pathwise) {
+                if (int rc = run_gemm(st, vm, d, 0.f, tg->lgcp_kinv, d, (int)N, d, d, num_sms, part, &S)) return rc;
+                WideCombineArgs cb{};
+                cb.kpart = part; cb.x = x; cb.G = G; cb.vm = vm; cb.dxnet = dx; cb.base_adj = adj; cb.r = r; cb.c = c;
+                cb.mu = a.vd_mean; cb.logdiag = a.vd_logdiag; cb.betas = a.betas; cb.epss = a.eps;
+                cb.out = isB ? abar : adj;
+                cb.S = S; cb.N = (int)N; cb.d = d; cb.step = i; cb.isB = isB; cb.use_nn = use_nn;
+                cb.area = tg->lgcp_bin_area; cb.clip_q = a.clip_q;
+                wide_combine_kernel<<<ew(nd), 256, 0, st>>>(cb);
+                CMCD_CUDA_OK(cudaGetLastError());
+            }
+        }
+        float* tmp = zp; zp = z; z = tmp;
+        tmp = spp; spp = sp; sp = tmp;
+    }
+    wide_vd_final_kernel<<<ew(d), 256, 0, st>>>(gmu, gls, adj, zp, c, a.vd_mean, (int)N, d, pathwise ? 1 : 0, g_vd_mean, g_vd_logdiag);
+    CMCD_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

@@ -61,6 +61,32 @@ def test_gradient_parity(name):
     assert all((l == 0).all() for l in tree_leaves(pn))
 
 
+@pytest.mark.parametrize("name", ["D_lgcp", "D_lgcp_ula"])
+def test_gradient_parity_lgcp(name):
+    """README.md:63 target (d=1600, geffner in=1620, eps / vd / betas trained) through the wide reverse path."""
+    c, unf, g32, g64, gp, l64, lp_ = _grads(name)
+    assert torch.isfinite(gp).all()
+    e_kernel = _leaf_errs(gp, g64, unf)
+    e_oracle32 = _leaf_errs(g32, g64, unf)
+    print(f"{name}: kernel-vs-fp64 max {e_kernel.max():.2e}; fp32-oracle-vs-fp64 max {e_oracle32.max():.2e}")
+    assert (e_kernel <= np.maximum(GRAD_TOL, 2 * e_oracle32)).all(), (name, e_kernel, e_oracle32)
+
+
+def test_gradient_parity_mfvi_lgcp():
+    """MFVI pretrain of the lgcp config (main.py:83-89): jax.grad(bm.compute_bound), nbridges = 0, d = 1600."""
+    lp64, dim = OH.load_model("lgcp", dtype=torch.float64)
+    seeds = seeds_for(20)
+    pf, unf, fixed = OM.bm_initialize(dim, init_sigma=0.3)
+    pf = pf.clone()
+    pf[dim:2 * dim] += 3.5   # vd mean (leaves are ordered logdiag, mean): start near the prior mean 3.88
+    g64, _ = OM.grad_and_loss(OM.bm_compute_bound, seeds, pf.double(), unf, fixed, lp64)
+    target = PH.load_model("lgcp")[0]
+    pfp, unfp, fixedp = PB.initialize(dim, trainable=("vd",), init_sigma=0.3)
+    gp, _ = PM.grad_and_loss(PB.compute_bound)(torch.from_numpy(seeds), pf.cuda(), unfp, fixedp, target)
+    e = _leaf_errs(gp.cpu(), g64, unf)
+    assert (e < GRAD_TOL).all(), e
+
+
 def test_gradient_parity_mfvi():
     """jax.grad(bm.compute_bound) with nbridges=0 (main.py:87-89)."""
     for model in ("gmm", "many_gmm", "funnel"):
