@@ -119,26 +119,27 @@ __device__ __forceinline__ void bt_stage_bf16x2(uint8_t* t1, uint8_t* t2, int q,
 __device__ __forceinline__ void bt_bar(int wg) { asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory"); }
 
 // 24 x tcgen05.mma kind::tf32: D = A_hi B_lo + A_lo B_hi + A_hi B_hi (small terms first: the accumulator truncates)
-__device__ __forceinline__ void bt_issue_gemm(uint32_t tmem_base, uint32_t d_col, uint32_t bhi, uint32_t blo) {
+// (dhi / dlo: shared-memory descriptors of the B tile's first K block; one K block further = +256 B = +16 in the address field)
+__device__ __forceinline__ void bt_issue_gemm(uint32_t tmem_base, uint32_t d_col, uint64_t dhi, uint64_t dlo) {
     const uint32_t idesc = umma::make_idesc_tf32(128, BT_H);
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
         const uint32_t acol = tmem_base + (pass == 1 ? BT_A_LO : BT_A_HI);
-        const uint32_t baddr = (pass == 0) ? blo : bhi;
+        const uint64_t bd = (pass == 0) ? dlo : dhi;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            umma::mma_tf32_ts(tmem_base + d_col, acol + k * 8, umma::make_desc(baddr + k * 256, 128, 32 * BT_H), idesc, (pass | k) > 0);
+            umma::mma_tf32_ts(tmem_base + d_col, acol + k * 8, bd + (uint64_t)(k * 16), idesc, (pass | k) > 0);
     }
 }
 // 16 x tcgen05.mma kind::f16: D3[128 x 64] (+)= [X_H1 ; X_H2]^T (Z_G1 + Z_G2) over K = 128 particles
-__device__ __forceinline__ void bt_issue_wgrad(uint32_t tmem_base, uint32_t x_addr, uint32_t z_addr, bool fresh) {
+// (dx / dz: descriptors of the first 16-particle K block of the a1 / dp2 staging tiles; +2048 B per K block, +16 KB for the low part)
+__device__ __forceinline__ void bt_issue_wgrad(uint32_t tmem_base, uint64_t dx, uint64_t dz, bool fresh) {
     const uint32_t idesc = umma::make_idesc_bf16_mn(128, BT_H);
 #pragma unroll
     for (int part = 0; part < 2; ++part) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            umma::mma_f16_ss(tmem_base + BT_D3, umma::make_desc_sw128(x_addr + k * 2048, BT_T16K, 1024),
-                             umma::make_desc_sw128(z_addr + part * BT_T16K + k * 2048, BT_T16K, 1024), idesc,
+            umma::mma_f16_ss(tmem_base + BT_D3, dx + (uint64_t)(k * 128), dz + (uint64_t)(part * (BT_T16K >> 4) + k * 128), idesc,
                              (part | k) > 0 || !fresh);
     }
 }
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
     constexpr int ACT = ACT_GELU;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(8) uint64_t mbars[2][3];
+    __shared__ __align__(8) uint64_t mbars[2][4];   // per tile: GEMM1 done, GEMM2 done, WGRAD done, operands staged (128 arrivals)
     const int tid = threadIdx.x, wg = tid >> 7, q = tid & 127, warp = tid >> 5, lane = tid & 31;
     const NetView& nv = a.net;
     float* sf = reinterpret_cast<float*>(smem + BT_OFF_SMALL);
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
     float* sW3 = sU1 + D * BT_H;            // [64][D]
     float* sAccU1 = sW3 + BT_H * D;         // [D][64]  gradient accumulators shared by both tiles
     float* sAccW3 = sAccU1 + D * BT_H;      // [64][D]
-    float* sTp = sAccW3 + BT_H * D;         // mixture parameters
+    float* sTp = sAccW3 + BT_H * D;         // mixture parameters (generic layout, MIX_STRIDE floats per component)
+    float2* sMu = reinterpret_cast<float2*>(sTp + MIX_MAX * MIX_STRIDE);   // many_gmm: dense component means
     for (int idx = tid; idx < BT_H * BT_H; idx += BT_THREADS) {
         const int i = idx / BT_H, j = idx % BT_H;
         float hi, lo;
@@ -173,10 +175,14 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
     for (int i = tid; i < BT_H * D; i += BT_THREADS) { sW3[i] = nv.W3[i]; sAccW3[i] = 0.f; }
     const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
     for (int i = tid; i < ntp; i += BT_THREADS) sTp[i] = a.tgt.mix[i];
+    const bool fast_gmm = (a.tgt.kind == TGT_MANY_GMM);
+    if (fast_gmm)
+        for (int i = tid; i < a.tgt.ncomp; i += BT_THREADS) sMu[i] = make_float2(a.tgt.mix[i * MIX_STRIDE], a.tgt.mix[i * MIX_STRIDE + 1]);
+    const ManyGmmConst gc = many_gmm_const(a.tgt);
     if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) umma::mbar_init(&mbars[0][0] + i, 1);
+        for (int i = 0; i < 8; ++i) umma::mbar_init(&mbars[0][0] + i, (i & 3) == 3 ? BT_PB : 1);
     }
     umma::fence_async_smem();
     umma::fence_before();
@@ -185,17 +191,21 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 
     const uint32_t tmem_base = tmem_slot + (uint32_t)wg * BT_TILE_COLS;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t bf_hi = umma::smem_u32(smem + BT_OFF_BF_HI), bf_lo = umma::smem_u32(smem + BT_OFF_BF_LO);
-    const uint32_t bd_hi = umma::smem_u32(smem + BT_OFF_BD_HI), bd_lo = umma::smem_u32(smem + BT_OFF_BD_LO);
+    const uint64_t bf_hi = umma::make_desc(umma::smem_u32(smem + BT_OFF_BF_HI), 128, 32 * BT_H);
+    const uint64_t bf_lo = umma::make_desc(umma::smem_u32(smem + BT_OFF_BF_LO), 128, 32 * BT_H);
+    const uint64_t bd_hi = umma::make_desc(umma::smem_u32(smem + BT_OFF_BD_HI), 128, 32 * BT_H);
+    const uint64_t bd_lo = umma::make_desc(umma::smem_u32(smem + BT_OFF_BD_LO), 128, 32 * BT_H);
     uint8_t* tX1 = smem + BT_OFF_TILE + wg * 4 * BT_T16K;
     uint8_t* tX2 = tX1 + BT_T16K;
     uint8_t* tZ1 = tX1 + 2 * BT_T16K;
     uint8_t* tZ2 = tX1 + 3 * BT_T16K;
-    const uint32_t x_addr = umma::smem_u32(tX1), z_addr = umma::smem_u32(tZ1);
+    const uint64_t x_desc = umma::make_desc_sw128(umma::smem_u32(tX1), BT_T16K, 1024);
+    const uint64_t z_desc = umma::make_desc_sw128(umma::smem_u32(tZ1), BT_T16K, 1024);
     uint64_t* mb1 = &mbars[wg][0];
     uint64_t* mb2 = &mbars[wg][1];
     uint64_t* mb3 = &mbars[wg][2];
-    uint32_t par1 = 0, par2 = 0, par3 = 0;
+    uint64_t* mbR = &mbars[wg][3];
+    uint32_t par1 = 0, par2 = 0, par3 = 0, parR = 0;
 
     float* part = partials + (size_t)blockIdx.x * L.P;
     float* w2row = part + L.W2rows + (size_t)(wg * BT_PB + q) * BT_H;   // this thread's private row of the stacked gW2 tile
@@ -209,6 +219,14 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
     float mu[D], sig[D], ivar[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) { mu[j] = a.vd_mean[j]; sig[j] = expf(a.vd_logdiag[j]); ivar[j] = 1.0f / (sig[j] * sig[j]); }
+
+    // per-lane accumulators of the skinny gradients that are not indexed by the step: after a butterfly, lane l holds the
+    // warp's sum for hidden unit 16 cc + (l >> 1); summed over the whole kernel, flushed once at the end
+    float aW3[4][D], aU1[4][D];
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4)
+#pragma unroll
+        for (int m = 0; m < D; ++m) { aW3[k4][m] = 0.f; aU1[k4][m] = 0.f; }
 
     bool wgrad_pending = false;   // a WGRAD batch has been committed to mb3 and not yet waited for
     bool d3_fresh = true;         // the TMEM gW2 accumulator holds nothing (next WGRAD starts with accumulate = 0)
@@ -298,12 +316,23 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 #pragma unroll
                         for (int e = 0; e < 4; ++e) act_tc_grad<ACT>(p[e], a1[qq * 4 + e], g1[qq * 4 + e]);
                     }
+                    switch (cc) {   // warp-uniform: keeps g1s in registers with static indices
+                        case 0:
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        if (k4 == cc) {
+                            for (int e = 0; e < 16; ++e) g1s[0][e] = g1[e];
+                            break;
+                        case 1:
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) g1s[k4][e] = g1[e];
-                        }
+                            for (int e = 0; e < 16; ++e) g1s[1][e] = g1[e];
+                            break;
+                        case 2:
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) g1s[2][e] = g1[e];
+                            break;
+                        default:
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) g1s[3][e] = g1[e];
+                            break;
                     }
                     uint32_t hh[16], ll[16];
 #pragma unroll
@@ -319,8 +348,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 umma::tmem_st_wait();
                 umma::fence_before();
                 umma::fence_async_smem();
-                bt_bar(wg);
+                umma::mbar_arrive(mbR);     // only the issuing thread waits for the tile's 128 arrivals; the rest moves on
                 if (q == 0) {
+                    umma::mbar_wait(mbR, parR); parR ^= 1u;
                     umma::fence_after();
                     bt_issue_gemm(tmem_base, BT_D12, bf_hi, bf_lo);
                     umma::commit(mb1);
@@ -341,7 +371,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 mean[j] = x[j] - eps * u[j];
                 nn[j] = 0.f; dx[j] = 0.f; xs[j] = 0.f;
             }
-            if (isB) target_eval<D, false>(a.tgt, sTp, z, sp, zero, hv);   // score at z, used by the forward-kernel half
+            if (isB) {   // score at z, used by the forward-kernel half
+                if (fast_gmm) { float d0, d1; many_gmm_eval<false>(gc, sMu, z[0], z[1], sp[0], sp[1], 0.f, 0.f, d0, d1); }
+                else target_eval<D, false>(a.tgt, sTp, z, sp, zero, hv);
+            }
 
             // ---------------- epilogue 1: a2, act'(pre2), raw network output ----------------
             float o[D];
@@ -446,18 +479,20 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 #pragma unroll
                         for (int e = 0; e < 16; ++e) tmp[e] = __uint_as_float(a2u[e]) * vo[m];
                         const float s3 = bt_warp_reduce16(tmp, lane);
-                        if (!(lane & 1)) atomicAdd(sAccW3 + (cc * 16 + (lane >> 1)) * D + m, s3);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) aW3[k4][m] += (k4 == cc) ? s3 : 0.f;
                     }
                 }
                 umma::tmem_st_wait();
                 umma::fence_before();
                 umma::fence_async_smem();
-                bt_bar(wg);
+                umma::mbar_arrive(mbR);
                 if (q == 0) {
+                    umma::mbar_wait(mbR, parR); parR ^= 1u;
                     umma::fence_after();
                     bt_issue_gemm(tmem_base, BT_D12, bd_hi, bd_lo);
                     umma::commit(mb2);
-                    bt_issue_wgrad(tmem_base, x_addr, z_addr, d3_fresh);
+                    bt_issue_wgrad(tmem_base, x_desc, z_desc, d3_fresh);
                     umma::commit(mb3);
                 }
                 wgrad_pending = true;
@@ -469,7 +504,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 float vm[D], dummy[D];
 #pragma unroll
                 for (int j = 0; j < D; ++j) vm[j] = mk_t[j] * G[j];
-                target_eval<D, true>(a.tgt, sTp, x, dummy, vm, hv);
+                if (fast_gmm) many_gmm_eval<true>(gc, sMu, x[0], x[1], dummy[0], dummy[1], vm[0], vm[1], hv[0], hv[1]);
+                else target_eval<D, true>(a.tgt, sTp, x, dummy, vm, hv);
             }
 
             // ---------------- epilogue 2: dp1 = da1 * act'(pre1), dx = U1 dp1, layer-1 gradients ----------------
@@ -482,10 +518,26 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                     umma::tmem_ld16(tmem_lane + BT_D12 + cc * 16, v);
                     umma::tmem_ld_wait();
                     float dp1[16];
+                    switch (cc) {
+                        case 0:
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) dp1[e] = __uint_as_float(v[e]) * g1s[0][e];
+                            break;
+                        case 1:
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) dp1[e] = __uint_as_float(v[e]) * g1s[1][e];
+                            break;
+                        case 2:
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) dp1[e] = __uint_as_float(v[e]) * g1s[2][e];
+                            break;
+                        default:
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) dp1[e] = __uint_as_float(v[e]) * g1s[3][e];
+                            break;
+                    }
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        const float g = (cc == 0) ? g1s[0][e] : (cc == 1) ? g1s[1][e] : (cc == 2) ? g1s[2][e] : g1s[3][e];
-                        dp1[e] = __uint_as_float(v[e]) * g;
 #pragma unroll
                         for (int d = 0; d < D; ++d) dx[d] = fmaf(sU1[d * BT_H + cc * 16 + e], dp1[e], dx[d]);
                     }
@@ -497,7 +549,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 #pragma unroll
                         for (int e = 0; e < 16; ++e) tmp[e] = x[d] * dp1[e];
                         const float s4 = bt_warp_reduce16(tmp, lane);
-                        if (!(lane & 1)) atomicAdd(sAccU1 + d * BT_H + cc * 16 + (lane >> 1), s4);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) aU1[k4][d] += (k4 == cc) ? s4 : 0.f;
                     }
                 }
                 umma::fence_before();
@@ -539,6 +592,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
         }
     }
     flush_d3();
+    if (!(lane & 1)) {
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+#pragma unroll
+            for (int m = 0; m < D; ++m) {
+                atomicAdd(sAccW3 + (k4 * 16 + (lane >> 1)) * D + m, aW3[k4][m]);
+                atomicAdd(sAccU1 + m * BT_H + k4 * 16 + (lane >> 1), aU1[k4][m]);
+            }
+    }
     __syncthreads();
     for (int i = tid; i < D * BT_H; i += BT_THREADS) part[L.U1 + i] = sAccU1[i];
     for (int i = tid; i < BT_H * D; i += BT_THREADS) part[L.W3 + i] = sAccW3[i];
@@ -575,7 +637,7 @@ __global__ void bwd_tc_reduce_kernel(const float* __restrict__ partials, int nbl
 }
 
 static size_t bt_smem_bytes(int D) {
-    return (size_t)BT_OFF_SMALL + (size_t)(4 * D * BT_H + MIX_MAX * MIX_STRIDE + 8) * sizeof(float);
+    return (size_t)BT_OFF_SMALL + (size_t)(4 * D * BT_H + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 8) * sizeof(float);
 }
 
 bool bwd_tc_supported(const BridgeArgs& a, int D) {

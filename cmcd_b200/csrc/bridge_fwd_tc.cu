@@ -32,9 +32,10 @@ struct TcCtx {
     const float *c1, *c2, *c3;            // global per-step tables [T][64], [T][64], [T][D]
     float out_scale, out_clip;
     uint32_t tmem_base, tmem_lane;        // allocation base; base + this warp's lane quarter
-    uint32_t bhi, blo;                    // shared-memory addresses of the B tiles
-    uint64_t* mbar;
-    uint32_t parity;
+    uint64_t bhi, blo;                    // shared-memory descriptors of the B tiles (first K block)
+    uint64_t* mbar;                       // MMA batch complete
+    uint64_t* mbar_ready;                 // A operand staged by all 128 threads
+    uint32_t parity, parity_ready;
 };
 
 // numpyro Normal.log_prob summed over dims (src/mcd_utils.py:19-21)
@@ -88,19 +89,20 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, const float (&
     }
     umma::tmem_st_wait();
     umma::fence_before();
-    __syncthreads();
+    umma::mbar_arrive(cx.mbar_ready);   // only the issuing thread waits for the 128 arrivals; the other warps move on
     if (threadIdx.x == 0) {
+        umma::mbar_wait(cx.mbar_ready, cx.parity_ready);
+        cx.parity_ready ^= 1u;
         umma::fence_after();
         const uint32_t idesc = umma::make_idesc_tf32(128, TC_H);
         // small terms first: the fp32 accumulator truncates on every accumulate (tools/umma_probe2.cu, test 3)
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
             const uint32_t acol = cx.tmem_base + (pass == 1 ? TC_COL_AL : TC_COL_AH);
-            const uint32_t baddr = (pass == 0) ? cx.blo : cx.bhi;
+            const uint64_t bd = (pass == 0) ? cx.blo : cx.bhi;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                umma::mma_tf32_ts(cx.tmem_base + TC_COL_D, acol + k * 8, umma::make_desc(baddr + k * 256, 128, 32 * TC_H), idesc,
-                                  (pass | k) > 0);
+            for (int k = 0; k < 8; ++k)   // next K block: +256 B = +16 in the descriptor's address field
+                umma::mma_tf32_ts(cx.tmem_base + TC_COL_D, acol + k * 8, bd + (uint64_t)(k * 16), idesc, (pass | k) > 0);
         }
         umma::commit(cx.mbar);
     }
@@ -160,7 +162,7 @@ template <int D, int ACT>
 __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar, mbar_ready;
     const int tid = threadIdx.x, warp = tid >> 5;
     const NetView& nv = a.net;
     uint8_t* sBhi = smem_raw;
@@ -185,8 +187,13 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
     for (int i = tid; i < D * D; i += TC_PB) sU3[i] = nv.U3 ? nv.U3[i] : 0.f;
     const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
     for (int i = tid; i < ntp; i += TC_PB) sTp[i] = a.tgt.mix[i];
+    float2* sMu = reinterpret_cast<float2*>(sTp + MIX_MAX * MIX_STRIDE);   // many_gmm: dense component means
+    const bool fast_gmm = (D == 2) && (a.tgt.kind == TGT_MANY_GMM);
+    if (fast_gmm)
+        for (int i = tid; i < a.tgt.ncomp; i += TC_PB) sMu[i] = make_float2(a.tgt.mix[i * MIX_STRIDE], a.tgt.mix[i * MIX_STRIDE + 1]);
+    const ManyGmmConst gc = many_gmm_const(a.tgt);
     if (warp == 0) umma::tmem_alloc(&tmem_slot, TC_COLS);
-    if (tid == 0) umma::mbar_init(&mbar, 1);
+    if (tid == 0) { umma::mbar_init(&mbar, 1); umma::mbar_init(&mbar_ready, TC_PB); }
     umma::fence_async_smem();   // generic-proxy writes of the B tiles -> visible to the tensor core (async proxy)
     umma::fence_before();
     __syncthreads();
@@ -198,8 +205,10 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
     cx.out_scale = nv.out_scale; cx.out_clip = nv.out_clip;
     cx.tmem_base = tmem_slot;
     cx.tmem_lane = tmem_slot + ((uint32_t)(warp * 32) << 16);
-    cx.bhi = umma::smem_u32(sBhi); cx.blo = umma::smem_u32(sBlo);
+    cx.bhi = umma::make_desc(umma::smem_u32(sBhi), 128, 32 * TC_H);
+    cx.blo = umma::make_desc(umma::smem_u32(sBlo), 128, 32 * TC_H);
     cx.mbar = &mbar; cx.parity = 0u;
+    cx.mbar_ready = &mbar_ready; cx.parity_ready = 0u;
 
     const bool cais = (a.mode == CMCD_MODE_CAIS_SN || a.mode == CMCD_MODE_CAIS_VAR_SN);
     const bool nn_b = (a.mode != CMCD_MODE_ULA);
@@ -269,7 +278,8 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
                 split(k, ka, k);
                 normal_vec<D>(ka, xi);
             } else {
-                lp = target_eval<D, false>(a.tgt, sTp, zn, sp, dummy, dummy);
+                if (fast_gmm) { float d0, d1; lp = many_gmm_eval<false>(gc, sMu, zn[0], zn[1], sp[0], sp[1], 0.f, 0.f, d0, d1); }
+                else lp = target_eval<D, false>(a.tgt, sTp, zn, sp, dummy, dummy);
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
                     const float sq = -((zn[j] - mu[j]) / sig[j]) / sig[j];
@@ -320,7 +330,7 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
 template <int D, int ACT>
 static int launch_fwd_tc_t(const BridgeArgs& a, cudaStream_t st, int num_sms) {
     // request > 227/3 KB so that at most two CTAs (2 x 256 TMEM columns) share an SM
-    size_t smem = 2 * TC_B_BYTES + (2 * D * TC_H + TC_H * D + D * D + 4 + MIX_MAX * MIX_STRIDE + 8) * sizeof(float);
+    size_t smem = 2 * TC_B_BYTES + (2 * D * TC_H + TC_H * D + D * D + 4 + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 8) * sizeof(float);
     if (smem < 80 * 1024) smem = 80 * 1024;
     auto kern = bridge_fwd_tc_kernel<D, ACT>;
     CMCD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

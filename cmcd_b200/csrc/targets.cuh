@@ -119,6 +119,70 @@ __device__ __forceinline__ float mixture2_eval(const TargetDesc& t, const float*
     return logf(S) + m;
 }
 
+// ---- 40-GMM fast path (many_gmm, d = 2) -----------------------------------------------------------------------
+// Same mathematics as the TGT_MANY_GMM branch of mixture2_eval, specialised for the tensor-core kernels: scalars in
+// registers (no array references -> no stack traffic, inlined), component means read as float2 from a dense
+// shared-memory array, exp2 with flush-to-zero (arguments are <= 0), displacement-based HVP
+//   H v = (1/s^4) [ sum_k r_k delta_k (delta_k . v) - ebar (ebar . v) ] - v / s^2,  delta_k = mu_k - mu_piv,
+// which is the pivoted form above written in units of the displacement (one scaling by 1/s^4 at the end).
+struct ManyGmmConst {
+    float inv_var, hl2, norm_const, invalid_below;   // hl2 = -0.5 inv_var log2(e); norm_const = -2 comp_norm + log_mix
+    int nc;
+};
+__device__ __forceinline__ ManyGmmConst many_gmm_const(const TargetDesc& t) {
+    ManyGmmConst c;
+    c.inv_var = t.inv_var;
+    c.hl2 = -0.5f * t.inv_var * 1.4426950408889634f;
+    c.norm_const = -2.0f * t.comp_norm + t.log_mix;
+    c.invalid_below = t.invalid_below;
+    c.nc = t.ncomp;
+    return c;
+}
+template <bool WANT_HVP>
+__device__ __forceinline__ float many_gmm_eval(const ManyGmmConst& c, const float2* __restrict__ smu, float z0, float z1,
+                                               float& g0, float& g1, float v0, float v1, float& hv0, float& hv1) {
+    float qmin = CUDART_INF_F, p0 = 0.f, p1 = 0.f;   // pivot displacement d_piv = z - mu_piv
+#pragma unroll 8
+    for (int k = 0; k < c.nc; ++k) {
+        const float2 m = smu[k];
+        const float d0 = z0 - m.x, d1 = z1 - m.y;
+        const float q = fmaf(d0, d0, d1 * d1);
+        if (q < qmin) { qmin = q; p0 = d0; p1 = d1; }
+    }
+    const float off = -c.hl2 * qmin;
+    float S = 0.f, G0 = 0.f, G1 = 0.f, Q0 = 0.f, Q1 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < c.nc; ++k) {
+        const float2 m = smu[k];
+        const float d0 = z0 - m.x, d1 = z1 - m.y;
+        float e;
+        {
+            const float arg = fmaf(c.hl2, fmaf(d0, d0, d1 * d1), off);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
+        }
+        S += e; G0 = fmaf(e, d0, G0); G1 = fmaf(e, d1, G1);
+        if (WANT_HVP) {
+            const float e0 = d0 - p0, e1 = d1 - p1;       // = -(delta_k) ; sign cancels in the quadratic form
+            const float t = e * fmaf(e0, v0, e1 * v1);
+            Q0 = fmaf(t, e0, Q0); Q1 = fmaf(t, e1, Q1);
+        }
+    }
+    const float lp = logf(S) + fmaf(-0.5f * qmin, c.inv_var, c.norm_const);
+    const bool valid = lp > c.invalid_below;
+    const float inv = 1.0f / S;
+    const float m0 = G0 * inv, m1 = G1 * inv;              // responsibility-weighted mean displacement
+    g0 = valid ? -m0 * c.inv_var : 0.f;
+    g1 = valid ? -m1 * c.inv_var : 0.f;
+    if (WANT_HVP) {
+        const float b0 = m0 - p0, b1 = m1 - p1;
+        const float bv = fmaf(b0, v0, b1 * v1);
+        const float iv2 = c.inv_var * c.inv_var;
+        hv0 = valid ? fmaf(iv2, fmaf(Q0, inv, -b0 * bv), -v0 * c.inv_var) : 0.f;
+        hv1 = valid ? fmaf(iv2, fmaf(Q1, inv, -b1 * bv), -v1 * c.inv_var) : 0.f;
+    }
+    return valid ? lp : -CUDART_INF_F;
+}
+
 // ---- funnel (any D >= 2) --------------------------------------------------------------------
 template <int D, bool WANT_HVP>
 __device__ __forceinline__ float funnel_eval(const float (&z)[D], float (&g)[D], const float (&v)[D], float (&hv)[D]) {

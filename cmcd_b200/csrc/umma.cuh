@@ -98,6 +98,10 @@ __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar)), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;");
 }
+// plain arrive (release.cta): counts one of the `count` arrivals of the current phase
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(mbar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
     uint32_t done = 0;
     const uint32_t addr = smem_u32(mbar);
