@@ -313,8 +313,13 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                             p[0] = fmaf(x[d], u.x, p[0]); p[1] = fmaf(x[d], u.y, p[1]);
                             p[2] = fmaf(x[d], u.z, p[2]); p[3] = fmaf(x[d], u.w, p[3]);
                         }
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) act_tc_grad<ACT>(p[e], a1[qq * 4 + e], g1[qq * 4 + e]);
+                        {   // two activations (+ derivatives) per instruction slot (FFMA2)
+                            f32x2_t A, DA;
+                            gelu_fast_grad2(p[0], p[1], A, DA);
+                            upk2(A, a1[qq * 4 + 0], a1[qq * 4 + 1]); upk2(DA, g1[qq * 4 + 0], g1[qq * 4 + 1]);
+                            gelu_fast_grad2(p[2], p[3], A, DA);
+                            upk2(A, a1[qq * 4 + 2], a1[qq * 4 + 3]); upk2(DA, g1[qq * 4 + 2], g1[qq * 4 + 3]);
+                        }
                     }
                     switch (cc) {   // warp-uniform: keeps g1s in registers with static indices
                         case 0:
@@ -396,15 +401,21 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                         const float4 cv = __ldg(c2v + cc * 4 + qq);
                         const float p[4] = {__uint_as_float(v[qq * 4 + 0]) + cv.x, __uint_as_float(v[qq * 4 + 1]) + cv.y,
                                             __uint_as_float(v[qq * 4 + 2]) + cv.z, __uint_as_float(v[qq * 4 + 3]) + cv.w};
+                        float a2v[4], g2v[4];
+                        {
+                            f32x2_t A, DA;
+                            gelu_fast_grad2(p[0], p[1], A, DA);
+                            upk2(A, a2v[0], a2v[1]); upk2(DA, g2v[0], g2v[1]);
+                            gelu_fast_grad2(p[2], p[3], A, DA);
+                            upk2(A, a2v[2], a2v[3]); upk2(DA, g2v[2], g2v[3]);
+                        }
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            float a2, g2;
-                            act_tc_grad<ACT>(p[e], a2, g2);
                             const int j = cc * 16 + qq * 4 + e;
 #pragma unroll
-                            for (int m = 0; m < D; ++m) o[m] = fmaf(a2, sW3[j * D + m], o[m]);
-                            a2u[qq * 4 + e] = __float_as_uint(a2);
-                            g2u[qq * 4 + e] = __float_as_uint(g2);
+                            for (int m = 0; m < D; ++m) o[m] = fmaf(a2v[e], sW3[j * D + m], o[m]);
+                            a2u[qq * 4 + e] = __float_as_uint(a2v[e]);
+                            g2u[qq * 4 + e] = __float_as_uint(g2v[e]);
                         }
                     }
                     // the A region is dead between GEMM1 and GEMM2: park a2 / act'(pre2) in this thread's lane

@@ -70,9 +70,17 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, const float (&
                 p[0] = fmaf(x[a], u.x, p[0]); p[1] = fmaf(x[a], u.y, p[1]);
                 p[2] = fmaf(x[a], u.z, p[2]); p[3] = fmaf(x[a], u.w, p[3]);
             }
+            float av[4];
+            if constexpr (ACT == ACT_GELU) {   // two activations per instruction slot (FFMA2)
+                upk2(gelu_fast2(p[0], p[1]), av[0], av[1]);
+                upk2(gelu_fast2(p[2], p[3]), av[2], av[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) av[e] = act_tc<ACT>(p[e]);
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float a1 = act_tc<ACT>(p[e]);
+                const float a1 = av[e];
                 if (skip) {
                     const int j = c * 16 + q * 4 + e;
 #pragma unroll
@@ -144,12 +152,19 @@ __device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (
                     p[2] = fmaf(x[a], u.z, p[2]); p[3] = fmaf(x[a], u.w, p[3]);
                 }
             }
+            float av[4];
+            if constexpr (ACT == ACT_GELU) {
+                upk2(gelu_fast2(p[0], p[1]), av[0], av[1]);
+                upk2(gelu_fast2(p[2], p[3]), av[2], av[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) av[e] = act_tc<ACT>(p[e]);
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float a2 = act_tc<ACT>(p[e]);
                 const int j = c * 16 + q * 4 + e;
 #pragma unroll
-                for (int m = 0; m < D; ++m) o[m] = fmaf(a2, cx.sW3[j * D + m], o[m]);
+                for (int m = 0; m < D; ++m) o[m] = fmaf(av[e], cx.sW3[j * D + m], o[m]);
             }
         }
     }

@@ -100,6 +100,51 @@ __device__ __forceinline__ void gelu_fast_grad(float x, float& a, float& da) {
     const float cdf = 0.5f + copysignf(w, x);
     da = fmaf(x * 0.3989422804014327f, e, cdf);
 }
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2: one issue slot, two lanes of the FMA pipe) ------------------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float a, float b) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// Two GELUs at once (same formula as gelu_fast, written as gelu(x) = max(x, 0) - |x| h):
+// 10 packed FMA-pipe instructions + 4 ALU + 4 MUFU per pair instead of 2 x 14.  E receives exp(-x^2/2) of both lanes.
+__device__ __forceinline__ f32x2_t gelu_half_erfc2(float x0, float x1, f32x2_t& NAX, f32x2_t& E) {
+    NAX = pk2(__uint_as_float(__float_as_uint(x0) | 0x80000000u), __uint_as_float(__float_as_uint(x1) | 0x80000000u));   // -|x|
+    const f32x2_t NU = mul2(NAX, pk2(0.84932180028801907f, 0.84932180028801907f));       // -u
+    const f32x2_t DEN = fma2(NU, pk2(-0.27273748088f, -0.27273748088f), pk2(1.0f, 1.0f));  // 1 + p' u
+    const f32x2_t U2 = mul2(NU, NU);
+    float d0, d1, s0, s1;
+    upk2(DEN, d0, d1);
+    upk2(U2, s0, s1);
+    const f32x2_t T = pk2(rcp_ftz(d0), rcp_ftz(d1));
+    E = pk2(ex2_ftz(-s0), ex2_ftz(-s1));
+    f32x2_t Q = fma2(pk2(0.5307027145f, 0.5307027145f), T, pk2(-0.7265760135f, -0.7265760135f));
+    Q = fma2(Q, T, pk2(0.7107068705f, 0.7107068705f));
+    Q = fma2(Q, T, pk2(-0.142248368f, -0.142248368f));
+    Q = fma2(Q, T, pk2(0.127414796f, 0.127414796f));
+    return mul2(mul2(Q, T), E);   // h
+}
+__device__ __forceinline__ f32x2_t gelu_fast2(float x0, float x1) {
+    f32x2_t NAX, E;
+    const f32x2_t H = gelu_half_erfc2(x0, x1, NAX, E);
+    return fma2(NAX, H, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+}
+// value and derivative of two GELUs: A = gelu, DA = Phi(x) + x phi(x)
+__device__ __forceinline__ void gelu_fast_grad2(float x0, float x1, f32x2_t& A, f32x2_t& DA) {
+    f32x2_t NAX, E;
+    const f32x2_t H = gelu_half_erfc2(x0, x1, NAX, E);
+    A = fma2(NAX, H, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+    const f32x2_t W = fma2(H, pk2(-1.0f, -1.0f), pk2(0.5f, 0.5f));   // 0.5 - h >= 0
+    float w0, w1;
+    upk2(W, w0, w1);
+    const f32x2_t WS = pk2(__uint_as_float(__float_as_uint(w0) | (__float_as_uint(x0) & 0x80000000u)),
+                           __uint_as_float(__float_as_uint(w1) | (__float_as_uint(x1) & 0x80000000u)));   // copysign(w, x)
+    const f32x2_t CDF = add2(WS, pk2(0.5f, 0.5f));
+    DA = fma2(mul2(pk2(x0, x1), pk2(0.3989422804014327f, 0.3989422804014327f)), E, CDF);
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_tc(float x) {
     if constexpr (ACT == ACT_GELU) return gelu_fast(x);
