@@ -263,13 +263,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
         const long long n = active ? n_raw : a.N - 1;   // tail lanes shadow the last particle with zero cotangent
         const float c = active ? -cot_negw[n] : 0.f;    // dL/dw_n
         float zp[D], z[D], adj[D], abar[D], gmu[D], gls[D], zero[D], hv[D], sp[D], spp[D], r[D];
+        float hz[3] = {0.f, 0.f, 0.f}, hzp[3] = {0.f, 0.f, 0.f};   // many_gmm fast path: Hessian of log p at z / z' (h00, h01, h11)
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             zp[j] = a.traj[((size_t)K * D + j) * a.N + n];
             gmu[j] = 0.f; gls[j] = 0.f; zero[j] = 0.f; adj[j] = 0.f; abar[j] = 0.f; z[j] = 0.f; sp[j] = 0.f; r[j] = 0.f; hv[j] = 0.f;
         }
         // terminal: w += log p(z_K)  (mcdboundingmachine.py:178); stop-gradiented in the log-var mode
-        target_eval<D, false>(a.tgt, sTp, zp, spp, zero, hv);
+        if (fast_gmm) many_gmm_eval_hess(gc, sMu, zp[0], zp[1], spp[0], spp[1], hzp[0], hzp[1], hzp[2]);
+        else target_eval<D, false>(a.tgt, sTp, zp, spp, zero, hv);
         if (pathwise) {
 #pragma unroll
             for (int j = 0; j < D; ++j) adj[j] = c * spp[j];
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 nn[j] = 0.f; dx[j] = 0.f; xs[j] = 0.f;
             }
             if (isB) {   // score at z, used by the forward-kernel half
-                if (fast_gmm) { float d0, d1; many_gmm_eval<false>(gc, sMu, z[0], z[1], sp[0], sp[1], 0.f, 0.f, d0, d1); }
+                if (fast_gmm) many_gmm_eval_hess(gc, sMu, z[0], z[1], sp[0], sp[1], hz[0], hz[1], hz[2]);   // + Hessian: both HVPs at z come from it
                 else target_eval<D, false>(a.tgt, sTp, z, sp, zero, hv);
             }
 
@@ -515,8 +517,11 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 float vm[D], dummy[D];
 #pragma unroll
                 for (int j = 0; j < D; ++j) vm[j] = mk_t[j] * G[j];
-                if (fast_gmm) many_gmm_eval<true>(gc, sMu, x[0], x[1], dummy[0], dummy[1], vm[0], vm[1], hv[0], hv[1]);
-                else target_eval<D, true>(a.tgt, sTp, x, dummy, vm, hv);
+                if (fast_gmm) {
+                    const float h00 = isB ? hzp[0] : hz[0], h01 = isB ? hzp[1] : hz[1], h11 = isB ? hzp[2] : hz[2];
+                    hv[0] = fmaf(h00, vm[0], h01 * vm[1]);
+                    hv[1] = fmaf(h01, vm[0], h11 * vm[1]);
+                } else target_eval<D, true>(a.tgt, sTp, x, dummy, vm, hv);
             }
 
             // ---------------- epilogue 2: dp1 = da1 * act'(pre1), dx = U1 dp1, layer-1 gradients ----------------
@@ -590,6 +595,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 if (lane == 0) { atomicAdd(part + L.beta + i, gbs); atomicAdd(part + L.eps + i, ges); }
 #pragma unroll
                 for (int j = 0; j < D; ++j) { zp[j] = z[j]; spp[j] = sp[j]; }
+                hzp[0] = hz[0]; hzp[1] = hz[1]; hzp[2] = hz[2];
                 ++d3_steps;
             }
         }

@@ -183,6 +183,50 @@ __device__ __forceinline__ float many_gmm_eval(const ManyGmmConst& c, const floa
     return valid ? lp : -CUDART_INF_F;
 }
 
+// Score and full 2x2 Hessian of the 40-GMM log-density in one sweep over the components:
+//   H = (1/s^4) [ M / S - b b^T ] - I / s^2,   M = sum_k e_k delta_k delta_k^T (3 numbers), b = mbar - d_piv,
+// so that every later Hessian-vector product at this point costs 4 FMAs (the adjoint needs H(z_k) v for two different
+// v per bridge step: once as z of step k, once as z' of step k-1).
+__device__ __forceinline__ float many_gmm_eval_hess(const ManyGmmConst& c, const float2* __restrict__ smu, float z0, float z1,
+                                                    float& g0, float& g1, float& h00, float& h01, float& h11) {
+    float qmin = CUDART_INF_F, p0 = 0.f, p1 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < c.nc; ++k) {
+        const float2 m = smu[k];
+        const float d0 = z0 - m.x, d1 = z1 - m.y;
+        const float q = fmaf(d0, d0, d1 * d1);
+        if (q < qmin) { qmin = q; p0 = d0; p1 = d1; }
+    }
+    const float off = -c.hl2 * qmin;
+    float S = 0.f, G0 = 0.f, G1 = 0.f, M00 = 0.f, M01 = 0.f, M11 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < c.nc; ++k) {
+        const float2 m = smu[k];
+        const float d0 = z0 - m.x, d1 = z1 - m.y;
+        float e;
+        {
+            const float arg = fmaf(c.hl2, fmaf(d0, d0, d1 * d1), off);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
+        }
+        S += e; G0 = fmaf(e, d0, G0); G1 = fmaf(e, d1, G1);
+        const float e0 = d0 - p0, e1 = d1 - p1;
+        const float t0 = e * e0;
+        M00 = fmaf(t0, e0, M00); M01 = fmaf(t0, e1, M01); M11 = fmaf(e * e1, e1, M11);
+    }
+    const float lp = logf(S) + fmaf(-0.5f * qmin, c.inv_var, c.norm_const);
+    const bool valid = lp > c.invalid_below;
+    const float inv = 1.0f / S;
+    const float m0 = G0 * inv, m1 = G1 * inv;
+    g0 = valid ? -m0 * c.inv_var : 0.f;
+    g1 = valid ? -m1 * c.inv_var : 0.f;
+    const float b0 = m0 - p0, b1 = m1 - p1;
+    const float iv2 = c.inv_var * c.inv_var;
+    h00 = valid ? fmaf(iv2, fmaf(M00, inv, -b0 * b0), -c.inv_var) : 0.f;
+    h01 = valid ? iv2 * fmaf(M01, inv, -b0 * b1) : 0.f;
+    h11 = valid ? fmaf(iv2, fmaf(M11, inv, -b1 * b1), -c.inv_var) : 0.f;
+    return valid ? lp : -CUDART_INF_F;
+}
+
 // ---- funnel (any D >= 2) --------------------------------------------------------------------
 template <int D, bool WANT_HVP>
 __device__ __forceinline__ float funnel_eval(const float (&z)[D], float (&g)[D], const float (&v)[D], float (&hv)[D]) {
