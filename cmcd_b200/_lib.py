@@ -53,6 +53,9 @@ EXPORTS = {
     "cmcd_bridge_fwd_host": (C.c_int, [C.POINTER(CmcdBridgeDesc), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNet),
                                        C.POINTER(CmcdTarget), _fp, _fp, _fp, _fp, _fp]),
     "cmcd_target_eval": (C.c_int, [C.POINTER(CmcdTarget), C.c_int32, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp]),
+    "cmcd_adam_project_step": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
+                                         C.c_float, C.c_int32, _fp, C.c_float, _fp]),
+    "cmcd_randint": (C.c_int, [_fp, C.c_uint32, C.c_uint32, C.c_int64, C.c_int32, C.c_int32, _fp]),
     "cmcd_ffma_probe": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32]),
     "cmcd_threefry2x32": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp, _fp]),
     "cmcd_particle_noise": (C.c_int, [_fp, _fp, C.c_int64, C.c_int32, C.c_int32, _fp, _fp]),

@@ -43,6 +43,11 @@ int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
                     float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps, const cmcd_net_grad* g,
                     void* ws, size_t ws_bytes);
 
+int launch_adam_project(cudaStream_t st, float* p, const float* g, float* m, float* v, const float* lo, const float* hi, long long n,
+                        float lr, float b1, float b2, float eps, float clip, int step, float* ema, float ema_step,
+                        const int32_t* skip_flag);
+int launch_randint(cudaStream_t st, uint32_t key0, uint32_t key1, long long n, int32_t minval, int32_t maxval, int32_t* out);
+
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {
@@ -199,6 +204,19 @@ int cmcd_target_eval(const cmcd_target* target, int32_t dim, void* stream, const
     if (target->kind == CMCD_TARGET_LGCP) { set_error("target_eval: lgcp is served by the wide path"); return 2; }
     if (n == 0) return 0;
     return launch_target_eval((cudaStream_t)stream, a.tgt, dim, x, n, v, out_logp, out_score, out_hvp);
+}
+
+int cmcd_adam_project_step(void* stream, float* params, const float* grad, float* m, float* v, const float* lo, const float* hi,
+                           int64_t n, float lr, float b1, float b2, float eps, float clip, int32_t step, float* ema,
+                           float ema_step, const int32_t* skip_flag) {
+    if (!params || !grad || !m || !v || n < 0 || step < 1) { set_error("adam_project_step: bad arguments"); return 2; }
+    if (n == 0) return 0;
+    return launch_adam_project((cudaStream_t)stream, params, grad, m, v, lo, hi, n, lr, b1, b2, eps, clip, step, ema, ema_step, skip_flag);
+}
+int cmcd_randint(void* stream, uint32_t key0, uint32_t key1, int64_t n, int32_t minval, int32_t maxval, int32_t* out) {
+    if (!out || n < 0) { set_error("randint: bad arguments"); return 2; }
+    if (n == 0) return 0;
+    return launch_randint((cudaStream_t)stream, key0, key1, n, minval, maxval, out);
 }
 
 int cmcd_ffma_probe(void* stream, float* scratch, int32_t blocks, int32_t iters) {

@@ -159,6 +159,23 @@ int cmcd_target_eval(const cmcd_target* target, int32_t dim, void* stream, const
                      const float* v, float* out_logp, float* out_score, float* out_hvp);
 
 /*
+ * Training-loop step of opt.run (opt.py:92-132), device side ("next" rows of the scope table):
+ * cmcd_adam_project_step = optimizer.update + optax.apply_updates + project (opt.py:126-128, :14-24) for
+ * optimizer = optax.chain(optax.clip(clip), optax.adam(lr, b1, b2, eps)) (opt.py:26-35), fused in one launch.
+ *   params, m, v [n] are updated in place (m, v: Adam first / second moments, zero-initialised by the caller);
+ *   step = 1-based update count (bias correction); lo / hi [n] or NULL: per-element projection bounds
+ *   (eps in [1e-7, 0.5], eta in [0, 0.99], gamma >= 1e-3, mgridref_y >= 1e-3; -inf / +inf elsewhere);
+ *   ema [n] or NULL: ema = ema_step * params_new + (1 - ema_step) * ema (optax.incremental_update, opt.py:129-132);
+ *   skip_flag (device int32*) or NULL: if *skip_flag != 0 the launch changes nothing -- the NaN "Diverged" guard of
+ *   opt.py:122-124 without a host synchronisation.
+ * cmcd_randint = jax.random.randint(key, (n,), minval, maxval) int32 (opt.py:93-94, :182-184), key = (key0, key1).
+ */
+int cmcd_adam_project_step(void* stream, float* params, const float* grad, float* m, float* v, const float* lo,
+                           const float* hi, int64_t n, float lr, float b1, float b2, float eps, float clip, int32_t step,
+                           float* ema, float ema_step, const int32_t* skip_flag);
+int cmcd_randint(void* stream, uint32_t key0, uint32_t key1, int64_t n, int32_t minval, int32_t maxval, int32_t* out);
+
+/*
  * FP32 FMA-pipe probe: `blocks` x 256 threads each run iters*16 dependent-chain FFMAs (2*16*iters*256*blocks
  * flops); scratch needs blocks*256 floats.  bench.py times it with CUDA events to get the measured FP32 roofline
  * denominator (no reference counterpart).
