@@ -237,18 +237,22 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
         if (wgrad_pending) { umma::mbar_wait(mb3, par3); par3 ^= 1u; wgrad_pending = false; }
         umma::fence_after();
         if (!d3_fresh) {
-#pragma unroll 1
+            float4* g = reinterpret_cast<float4*>(w2row);
+            float4 r[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) r[k] = g[k];      // the whole row in flight at once (L2-resident, written 2 steps ago)
+#pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[16];
                 umma::tmem_ld16(tmem_lane + BT_D3 + c * 16, v);
-                float4* g = reinterpret_cast<float4*>(w2row + c * 16);
-                float4 r0 = g[0], r1 = g[1], r2 = g[2], r3 = g[3];
                 umma::tmem_ld_wait();
-                r0.x += __uint_as_float(v[0]); r0.y += __uint_as_float(v[1]); r0.z += __uint_as_float(v[2]); r0.w += __uint_as_float(v[3]);
-                r1.x += __uint_as_float(v[4]); r1.y += __uint_as_float(v[5]); r1.z += __uint_as_float(v[6]); r1.w += __uint_as_float(v[7]);
-                r2.x += __uint_as_float(v[8]); r2.y += __uint_as_float(v[9]); r2.z += __uint_as_float(v[10]); r2.w += __uint_as_float(v[11]);
-                r3.x += __uint_as_float(v[12]); r3.y += __uint_as_float(v[13]); r3.z += __uint_as_float(v[14]); r3.w += __uint_as_float(v[15]);
-                g[0] = r0; g[1] = r1; g[2] = r2; g[3] = r3;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float4 t = r[c * 4 + k];
+                    t.x += __uint_as_float(v[4 * k + 0]); t.y += __uint_as_float(v[4 * k + 1]);
+                    t.z += __uint_as_float(v[4 * k + 2]); t.w += __uint_as_float(v[4 * k + 3]);
+                    g[c * 4 + k] = t;
+                }
             }
         }
         d3_fresh = true;
@@ -276,6 +280,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 #pragma unroll
             for (int j = 0; j < D; ++j) adj[j] = c * spp[j];
         }
+        float znext[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) znext[j] = (K > 0) ? a.traj[((size_t)(K - 1) * D + j) * a.N + n] : 0.f;
         float g1s[4][16];               // act'(pre1) of the current evaluation, chunk-indexed with static indices only
         float beta = 0.f, eps = 0.f, ts = 1.f, omb = 0.f, gb = 0.f, ge = 0.f, rr = 0.f;
 
@@ -287,11 +294,21 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 beta = __ldg(a.betas + i); eps = __ldg(a.eps + i);
                 ts = 2.0f * eps; omb = 1.0f - beta;
 #pragma unroll
-                for (int j = 0; j < D; ++j) z[j] = a.traj[((size_t)i * D + j) * a.N + n];
+                for (int j = 0; j < D; ++j) {
+                    z[j] = znext[j];                          // loaded one bridge step ahead (HBM latency off the critical path)
+                    if (i > 0) znext[j] = a.traj[((size_t)(i - 1) * D + j) * a.N + n];
+                }
                 gb = 0.f; ge = 0.f;
             }
             const int t = isB ? (cais ? i + 1 : i) : i;
             const bool use_nn = isB ? nn_b : nn_f;
+            {   // next half-step's c1 / c2 rows (2 x 128 B each) -> L1 while this half computes
+                const int tn = isB ? i : (cais ? i : i - 1);
+                if (tn >= 0 && lane < 4) {
+                    const float* pf = ((lane & 2) ? nv.c2 : nv.c1) + (size_t)tn * BT_H + (lane & 1) * 32;
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(pf));
+                }
+            }
             const float sgn = isB ? 1.0f : -1.0f;
             float x[D], sx[D];
 #pragma unroll
@@ -323,23 +340,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                             upk2(A, a1[qq * 4 + 2], a1[qq * 4 + 3]); upk2(DA, g1[qq * 4 + 2], g1[qq * 4 + 3]);
                         }
                     }
-                    switch (cc) {   // warp-uniform: keeps g1s in registers with static indices
-                        case 0:
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) g1s[0][e] = g1[e];
-                            break;
-                        case 1:
+                    for (int k4 = 0; k4 < 4; ++k4) {   // predicated moves: static register indices, no control-flow merge
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) g1s[1][e] = g1[e];
-                            break;
-                        case 2:
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) g1s[2][e] = g1[e];
-                            break;
-                        default:
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) g1s[3][e] = g1[e];
-                            break;
+                        for (int e = 0; e < 16; ++e) g1s[k4][e] = (k4 == cc) ? g1[e] : g1s[k4][e];
                     }
                     uint32_t hh[16], ll[16];
 #pragma unroll

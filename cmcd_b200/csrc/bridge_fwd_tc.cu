@@ -274,6 +274,13 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
             const bool bwd_half = (h & 1) != 0;
             const int t = bwd_half ? (cais ? i + 1 : i) : i;
             const bool use_nn = bwd_half ? nn_b : nn_f;
+            {   // next half-step's c1 / c2 rows (2 x 128 B each) -> L1 while this half computes
+                const int tn = bwd_half ? i + 1 : (cais ? i + 1 : i);
+                if ((tid & 31) < 4) {
+                    const float* pf = ((tid & 2) ? nv.c2 : nv.c1) + (size_t)tn * TC_H + (tid & 1) * 32;
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(pf));
+                }
+            }
             float xin[D];
 #pragma unroll
             for (int j = 0; j < D; ++j) xin[j] = bwd_half ? zn[j] : z[j];
