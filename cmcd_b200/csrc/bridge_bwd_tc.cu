@@ -160,6 +160,13 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
     float* sAccW3 = sAccU1 + D * BT_H;      // [64][D]
     float* sTp = sAccW3 + BT_H * D;         // mixture parameters (generic layout, MIX_STRIDE floats per component)
     float2* sMu = reinterpret_cast<float2*>(sTp + MIX_MAX * MIX_STRIDE);   // many_gmm: dense component means
+    // per-warp double buffer for the per-step table rows c1[t] | c2[t] (cp.async one half-step ahead)
+    float* sTab = reinterpret_cast<float*>(sMu + MIX_MAX) + warp * (2 * 2 * BT_H);
+    auto stage_tab = [&](int t, int buf) {   // 32 lanes x 16 B = c1 row (256 B) + c2 row (256 B)
+        const float* src = (lane < 16 ? nv.c1 : nv.c2) + (size_t)t * BT_H + (lane & 15) * 4;
+        umma::cp_async16(sTab + buf * (2 * BT_H) + lane * 4, src);
+        umma::cp_async_commit();
+    };
     for (int idx = tid; idx < BT_H * BT_H; idx += BT_THREADS) {
         const int i = idx / BT_H, j = idx % BT_H;
         float hi, lo;
@@ -286,6 +293,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
         float g1s[4][16];               // act'(pre1) of the current evaluation, chunk-indexed with static indices only
         float beta = 0.f, eps = 0.f, ts = 1.f, omb = 0.f, gb = 0.f, ge = 0.f, rr = 0.f;
 
+        if (K > 0) stage_tab(cais ? K : K - 1, (2 * K - 1) & 1);
         // 2K half-steps, last bridge step first; odd h: backward-kernel mean at z' (net t = tb), even h: forward-kernel mean at z
         for (int h = 2 * K - 1; h >= 0; --h) {
             const int i = h >> 1;
@@ -302,13 +310,11 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
             }
             const int t = isB ? (cais ? i + 1 : i) : i;
             const bool use_nn = isB ? nn_b : nn_f;
-            {   // next half-step's c1 / c2 rows (2 x 128 B each) -> L1 while this half computes
-                const int tn = isB ? i : (cais ? i : i - 1);
-                if (tn >= 0 && lane < 4) {
-                    const float* pf = ((lane & 2) ? nv.c2 : nv.c1) + (size_t)tn * BT_H + (lane & 1) * 32;
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(pf));
-                }
-            }
+            // table rows of this half-step were requested one half-step ago; request the next ones
+            umma::cp_async_wait_all();
+            __syncwarp();
+            const float* tab = sTab + (h & 1) * (2 * BT_H);
+            if (h > 0) stage_tab(isB ? i : (cais ? i : i - 1), (h - 1) & 1);
             const float sgn = isB ? 1.0f : -1.0f;
             float x[D], sx[D];
 #pragma unroll
@@ -318,13 +324,13 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
             if (use_nn) {
                 if (isB && d3_steps >= BT_FLUSH_STEPS) flush_d3();
                 if (wgrad_pending) { umma::mbar_wait(mb3, par3); par3 ^= 1u; wgrad_pending = false; }   // a1 / dp2 staging tiles are free again
-                const float4* __restrict__ c1v = reinterpret_cast<const float4*>(nv.c1 + (size_t)t * BT_H);
+                const float4* __restrict__ c1v = reinterpret_cast<const float4*>(tab);
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
                     float a1[16], g1[16];
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) {
-                        const float4 cv = __ldg(c1v + cc * 4 + qq);
+                        const float4 cv = c1v[cc * 4 + qq];
                         float p[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
             if (use_nn) {
 #pragma unroll
                 for (int m = 0; m < D; ++m) o[m] = __ldg(nv.c3 + (size_t)t * D + m);
-                const float4* __restrict__ c2v = reinterpret_cast<const float4*>(nv.c2 + (size_t)t * BT_H);
+                const float4* __restrict__ c2v = reinterpret_cast<const float4*>(tab + BT_H);
                 umma::mbar_wait(mb1, par1); par1 ^= 1u;
                 umma::fence_after();
 #pragma unroll 1
@@ -404,7 +410,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                     umma::tmem_ld_wait();
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) {
-                        const float4 cv = __ldg(c2v + cc * 4 + qq);
+                        const float4 cv = c2v[cc * 4 + qq];
                         const float p[4] = {__uint_as_float(v[qq * 4 + 0]) + cv.x, __uint_as_float(v[qq * 4 + 1]) + cv.y,
                                             __uint_as_float(v[qq * 4 + 2]) + cv.z, __uint_as_float(v[qq * 4 + 3]) + cv.w};
                         float a2v[4], g2v[4];
@@ -658,7 +664,7 @@ __global__ void bwd_tc_reduce_kernel(const float* __restrict__ partials, int nbl
 }
 
 static size_t bt_smem_bytes(int D) {
-    return (size_t)BT_OFF_SMALL + (size_t)(4 * D * BT_H + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 8) * sizeof(float);
+    return (size_t)BT_OFF_SMALL + (size_t)(4 * D * BT_H + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 8 * 4 * BT_H + 8) * sizeof(float);
 }
 
 bool bwd_tc_supported(const BridgeArgs& a, int D) {

@@ -30,6 +30,7 @@ template <int D>
 struct TcCtx {
     const float *sU1, *sU2, *sW3, *sU3;   // shared memory
     const float *c1, *c2, *c3;            // global per-step tables [T][64], [T][64], [T][D]
+    const float* tab;                     // this warp's staged rows c1[t] | c2[t] of the current half-step (shared memory)
     float out_scale, out_clip;
     uint32_t tmem_base, tmem_lane;        // allocation base; base + this warp's lane quarter
     uint64_t bhi, blo;                    // shared-memory descriptors of the B tiles (first K block)
@@ -54,7 +55,7 @@ __device__ __forceinline__ float gauss_logprob_tc(const float (&x)[D], const flo
 template <int D, int ACT>
 __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, const float (&x)[D], float (&skipacc)[D]) {
     constexpr bool skip = (ACT == ACT_SOFTPLUS);
-    const float4* __restrict__ c1v = reinterpret_cast<const float4*>(cx.c1 + (size_t)t * TC_H);
+    const float4* __restrict__ c1v = reinterpret_cast<const float4*>(cx.tab);
 #pragma unroll
     for (int m = 0; m < D; ++m) skipacc[m] = 0.f;
 #pragma unroll 1
@@ -62,7 +63,7 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, const float (&
         uint32_t h[16], l[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float4 cc = __ldg(c1v + c * 4 + q);
+            const float4 cc = c1v[c * 4 + q];
             float p[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
             for (int a = 0; a < D; ++a) {
@@ -130,7 +131,7 @@ __device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (
         }
         o[m] = p;
     }
-    const float4* __restrict__ c2v = reinterpret_cast<const float4*>(cx.c2 + (size_t)t * TC_H);
+    const float4* __restrict__ c2v = reinterpret_cast<const float4*>(cx.tab + TC_H);
     umma::mbar_wait(cx.mbar, cx.parity);
     cx.parity ^= 1u;
     umma::fence_after();
@@ -141,7 +142,7 @@ __device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (
         umma::tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float4 cc = __ldg(c2v + c * 4 + q);
+            const float4 cc = c2v[c * 4 + q];
             float p[4] = {__uint_as_float(v[q * 4 + 0]) + cc.x, __uint_as_float(v[q * 4 + 1]) + cc.y,
                           __uint_as_float(v[q * 4 + 2]) + cc.z, __uint_as_float(v[q * 4 + 3]) + cc.w};
             if (has_u) {
@@ -203,6 +204,14 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
     const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
     for (int i = tid; i < ntp; i += TC_PB) sTp[i] = a.tgt.mix[i];
     float2* sMu = reinterpret_cast<float2*>(sTp + MIX_MAX * MIX_STRIDE);   // many_gmm: dense component means
+    // per-warp double buffer for the per-step table rows c1[t] | c2[t] (cp.async one half-step ahead)
+    float* sTab = reinterpret_cast<float*>(sMu + MIX_MAX) + warp * (2 * 2 * TC_H);
+    const int lane_ = tid & 31;
+    auto stage_tab = [&](int t, int buf) {   // 32 lanes x 16 B = c1 row (256 B) + c2 row (256 B)
+        const float* src = (lane_ < 16 ? nv.c1 : nv.c2) + (size_t)t * TC_H + (lane_ & 15) * 4;
+        umma::cp_async16(sTab + buf * (2 * TC_H) + lane_ * 4, src);
+        umma::cp_async_commit();
+    };
     const bool fast_gmm = (D == 2) && (a.tgt.kind == TGT_MANY_GMM);
     if (fast_gmm)
         for (int i = tid; i < a.tgt.ncomp; i += TC_PB) sMu[i] = make_float2(a.tgt.mix[i * MIX_STRIDE], a.tgt.mix[i * MIX_STRIDE + 1]);
@@ -264,6 +273,7 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
         ka = split_first(k);    // mcdboundingmachine.py:162
         k = split_second(ka);   // mcd_cais.py:94
         float wm = 0.f;
+        if (K > 0) stage_tab(0, 0);
         // 2K half-steps, so that one copy of the network code serves both evaluations of a bridge step:
         //   even h: NN(z, i)   -> forward kernel mean, sample z'      (mcd_cais.py:52-67)
         //   odd  h: NN(z', tb) -> backward kernel mean, weight update (mcd_cais.py:71-87)
@@ -274,13 +284,11 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
             const bool bwd_half = (h & 1) != 0;
             const int t = bwd_half ? (cais ? i + 1 : i) : i;
             const bool use_nn = bwd_half ? nn_b : nn_f;
-            {   // next half-step's c1 / c2 rows (2 x 128 B each) -> L1 while this half computes
-                const int tn = bwd_half ? i + 1 : (cais ? i + 1 : i);
-                if ((tid & 31) < 4) {
-                    const float* pf = ((tid & 2) ? nv.c2 : nv.c1) + (size_t)tn * TC_H + (tid & 1) * 32;
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(pf));
-                }
-            }
+            // table rows of this half-step were requested one half-step ago; request the next ones
+            umma::cp_async_wait_all();
+            __syncwarp();
+            cx.tab = sTab + (h & 1) * (2 * TC_H);
+            if (h + 1 < 2 * K) stage_tab(bwd_half ? i + 1 : (cais ? i + 1 : i), (h + 1) & 1);
             float xin[D];
 #pragma unroll
             for (int j = 0; j < D; ++j) xin[j] = bwd_half ? zn[j] : z[j];
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
 template <int D, int ACT>
 static int launch_fwd_tc_t(const BridgeArgs& a, cudaStream_t st, int num_sms) {
     // request > 227/3 KB so that at most two CTAs (2 x 256 TMEM columns) share an SM
-    size_t smem = 2 * TC_B_BYTES + (2 * D * TC_H + TC_H * D + D * D + 4 + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 8) * sizeof(float);
+    size_t smem = 2 * TC_B_BYTES + (2 * D * TC_H + TC_H * D + D * D + 4 + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 4 * 4 * TC_H + 8) * sizeof(float);
     if (smem < 80 * 1024) smem = 80 * 1024;
     auto kern = bridge_fwd_tc_kernel<D, ACT>;
     CMCD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -143,6 +143,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS) and its group bookkeeping
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // fp32 -> (hi, lo) with hi = RN to 11 significant bits (tf32 grid), lo = x - hi exact in fp32
 __host__ __device__ inline void split_tf32(float x, float& hi, float& lo) {
 #ifdef __CUDA_ARCH__
