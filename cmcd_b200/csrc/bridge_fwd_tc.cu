@@ -305,8 +305,7 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
                     const float uf = -(beta * gu + (1.0f - beta) * gq);
                     mf[j] = z[j] - eps * uf;
                 }
-                split(k, ka, k);
-                normal_vec<D>(ka, xi);
+                step_keys_and_normal<D>(k, xi);   // split + Gaussian + key advance as two interleaved threefry batches
             } else {
                 if (fast_gmm) { float d0, d1; lp = many_gmm_eval<false>(gc, sMu, zn[0], zn[1], sp[0], sp[1], 0.f, 0.f, d0, d1); }
                 else lp = target_eval<D, false>(a.tgt, sTp, zn, sp, dummy, dummy);
@@ -318,7 +317,6 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
                     const float ub = -(beta * gu + (1.0f - beta) * gq);
                     mb[j] = zn[j] - eps * ub;
                 }
-                k = split_second(k);
             }
 #pragma unroll
             for (int j = 0; j < D; ++j) nnv[j] = 0.f;

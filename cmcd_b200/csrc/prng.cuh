@@ -126,6 +126,56 @@ __device__ __forceinline__ void normal_vec(Key key, float (&out)[D]) {
     }
 }
 
+// N independent Threefry-2x32 blocks advanced in lock step (fully inlined): the 20 rounds of one block are a serial
+// dependency chain, interleaving N of them gives the scheduler N-way instruction-level parallelism.
+template <int N>
+__device__ __forceinline__ void threefry2x32_multi(const Key (&key)[N], uint32_t (&x0)[N], uint32_t (&x1)[N]) {
+    uint32_t ks2[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) { ks2[n] = key[n].k0 ^ key[n].k1 ^ 0x1BD11BDAu; x0[n] += key[n].k0; x1[n] += key[n].k1; }
+#define CMCD_TFM_R(r) { _Pragma("unroll") for (int n = 0; n < N; ++n) { x0[n] += x1[n]; x1[n] = rotl32(x1[n], r); x1[n] ^= x0[n]; } }
+#define CMCD_TFM_INJ(a, b, c) { _Pragma("unroll") for (int n = 0; n < N; ++n) { x0[n] += (a); x1[n] += (b) + (c); } }
+    CMCD_TFM_R(13) CMCD_TFM_R(15) CMCD_TFM_R(26) CMCD_TFM_R(6)
+    CMCD_TFM_INJ(key[n].k1, ks2[n], 1u)
+    CMCD_TFM_R(17) CMCD_TFM_R(29) CMCD_TFM_R(16) CMCD_TFM_R(24)
+    CMCD_TFM_INJ(ks2[n], key[n].k0, 2u)
+    CMCD_TFM_R(13) CMCD_TFM_R(15) CMCD_TFM_R(26) CMCD_TFM_R(6)
+    CMCD_TFM_INJ(key[n].k0, key[n].k1, 3u)
+    CMCD_TFM_R(17) CMCD_TFM_R(29) CMCD_TFM_R(16) CMCD_TFM_R(24)
+    CMCD_TFM_INJ(key[n].k1, ks2[n], 4u)
+    CMCD_TFM_R(13) CMCD_TFM_R(15) CMCD_TFM_R(26) CMCD_TFM_R(6)
+    CMCD_TFM_INJ(ks2[n], key[n].k0, 5u)
+#undef CMCD_TFM_R
+#undef CMCD_TFM_INJ
+}
+
+// One bridge step's key traffic in two interleaved batches (same values as split / normal_vec / split_second):
+//   (ka, kn) = split(k);  xi = normal(ka, (D,));  k <- second half of split(kn)      (mcd_cais.py:66-67,87)
+template <int D>
+__device__ __forceinline__ void step_keys_and_normal(Key& k, float (&xi)[D]) {
+    constexpr int M = (D + 1) / 2;
+    Key ka, kn;
+    {
+        Key kk[2] = {k, k};
+        uint32_t x0[2] = {0u, 1u}, x1[2] = {2u, 3u};
+        threefry2x32_multi<2>(kk, x0, x1);
+        ka.k0 = x0[0]; ka.k1 = x0[1]; kn.k0 = x1[0]; kn.k1 = x1[1];
+    }
+    Key kk[M + 2];
+    uint32_t x0[M + 2], x1[M + 2];
+#pragma unroll
+    for (int j = 0; j < M; ++j) { kk[j] = ka; x0[j] = (uint32_t)j; x1[j] = (j + M < D) ? (uint32_t)(j + M) : 0u; }
+    kk[M] = kn; x0[M] = 0u; x1[M] = 2u;
+    kk[M + 1] = kn; x0[M + 1] = 1u; x1[M + 1] = 3u;
+    threefry2x32_multi<M + 2>(kk, x0, x1);
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        xi[j] = bits_to_normal(x0[j]);
+        if (j + M < D) xi[j + M] = bits_to_normal(x1[j]);
+    }
+    k.k0 = x1[M]; k.k1 = x1[M + 1];
+}
+
 // Runtime-d element access (wide path, d=1600): element j of normal(key,(d,)).
 __device__ __forceinline__ uint32_t random_bits_at(Key key, int j, int d) {
     const int m = (d + 1) / 2;
