@@ -97,6 +97,55 @@ __device__ __forceinline__ float bt_warp_reduce16(const float (&v)[16], int lane
     return d;
 }
 
+// Three independent 16-wide butterflies advanced stage by stage (explicit 3-way ILP across the shuffle latency).
+__device__ __forceinline__ void bt_warp_reduce16x3(const float (&v0)[16], const float (&v1)[16], const float (&v2)[16], int lane,
+                                                   float& r0, float& r1, float& r2) {
+    float a[3][8], b[3][4], c[3][2], d[3];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float s0 = up ? v0[k] : v0[k + 8], k0 = up ? v0[k + 8] : v0[k];
+            const float s1 = up ? v1[k] : v1[k + 8], k1 = up ? v1[k + 8] : v1[k];
+            const float s2 = up ? v2[k] : v2[k + 8], k2 = up ? v2[k + 8] : v2[k];
+            a[0][k] = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+            a[1][k] = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+            a[2][k] = k2 + __shfl_xor_sync(0xffffffffu, s2, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const float send = up ? a[s][k] : a[s][k + 4], keep = up ? a[s][k + 4] : a[s][k];
+                b[s][k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const float send = up ? b[s][k] : b[s][k + 2], keep = up ? b[s][k + 2] : b[s][k];
+                c[s][k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+    }
+    {
+        const bool up = lane & 2;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const float send = up ? c[s][0] : c[s][1], keep = up ? c[s][1] : c[s][0];
+            d[s] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 3; ++s) d[s] += __shfl_xor_sync(0xffffffffu, d[s], 1);
+    r0 = d[0]; r1 = d[1]; r2 = d[2];
+}
+
 // 16 values of row q (hidden units 16c..16c+15) -> bf16 hi + bf16 lo parts in two MN-major SW128 tiles
 __device__ __forceinline__ void bt_stage_bf16x2(uint8_t* t1, uint8_t* t2, int q, int c, const float (&v)[16]) {
     uint32_t h1[8], h2[8];
@@ -493,17 +542,17 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                     umma::tmem_st16(tmem_lane + BT_A_HI + cc * 16, hh);
                     umma::tmem_st16(tmem_lane + BT_A_LO + cc * 16, ll);
                     bt_stage_bf16x2(tZ1, tZ2, q, cc, dp2);
-                    // gc2[t][j] += sum_p dp2 ; gW3[j][m] += sum_p a2 vo[m]
-                    const float s2 = bt_warp_reduce16(dp2, lane);
-                    if (!(lane & 1)) atomicAdd(part + L.c2 + (size_t)t * BT_H + cc * 16 + (lane >> 1), s2);
+                    // gc2[t][j] += sum_p dp2 ; gW3[j][m] += sum_p a2 vo[m]   (three butterflies in lock step; D == 2)
+                    {
+                        static_assert(D == 2, "the interleaved reductions assume d = 2");
+                        float t0[16], t1[16];
 #pragma unroll
-                    for (int m = 0; m < D; ++m) {
-                        float tmp[16];
+                        for (int e = 0; e < 16; ++e) { t0[e] = __uint_as_float(a2u[e]) * vo[0]; t1[e] = __uint_as_float(a2u[e]) * vo[1]; }
+                        float s2, s30, s31;
+                        bt_warp_reduce16x3(dp2, t0, t1, lane, s2, s30, s31);
+                        if (!(lane & 1)) atomicAdd(part + L.c2 + (size_t)t * BT_H + cc * 16 + (lane >> 1), s2);
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) tmp[e] = __uint_as_float(a2u[e]) * vo[m];
-                        const float s3 = bt_warp_reduce16(tmp, lane);
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) aW3[k4][m] += (k4 == cc) ? s3 : 0.f;
+                        for (int k4 = 0; k4 < 4; ++k4) { aW3[k4][0] += (k4 == cc) ? s30 : 0.f; aW3[k4][1] += (k4 == cc) ? s31 : 0.f; }
                     }
                 }
                 umma::tmem_st_wait();
@@ -567,16 +616,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 #pragma unroll
                         for (int d = 0; d < D; ++d) dx[d] = fmaf(sU1[d * BT_H + cc * 16 + e], dp1[e], dx[d]);
                     }
-                    const float s1 = bt_warp_reduce16(dp1, lane);
-                    if (!(lane & 1)) atomicAdd(part + L.c1 + (size_t)t * BT_H + cc * 16 + (lane >> 1), s1);
+                    {
+                        float t0[16], t1[16];
 #pragma unroll
-                    for (int d = 0; d < D; ++d) {
-                        float tmp[16];
+                        for (int e = 0; e < 16; ++e) { t0[e] = x[0] * dp1[e]; t1[e] = x[1] * dp1[e]; }
+                        float s1, s40, s41;
+                        bt_warp_reduce16x3(dp1, t0, t1, lane, s1, s40, s41);
+                        if (!(lane & 1)) atomicAdd(part + L.c1 + (size_t)t * BT_H + cc * 16 + (lane >> 1), s1);
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) tmp[e] = x[d] * dp1[e];
-                        const float s4 = bt_warp_reduce16(tmp, lane);
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) aU1[k4][d] += (k4 == cc) ? s4 : 0.f;
+                        for (int k4 = 0; k4 < 4; ++k4) { aU1[k4][0] += (k4 == cc) ? s40 : 0.f; aU1[k4][1] += (k4 == cc) ? s41 : 0.f; }
                     }
                 }
                 umma::fence_before();
