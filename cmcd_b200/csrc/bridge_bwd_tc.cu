@@ -415,11 +415,14 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 umma::fence_before();
                 umma::fence_async_smem();
                 umma::mbar_arrive(mbR);     // only the issuing thread waits for the tile's 128 arrivals; the rest moves on
-                if (q == 0) {
+                if (q < 32) {   // first warp of the tile (converged): wait for the 128 arrivals, one elected lane issues
                     umma::mbar_wait(mbR, parR); parR ^= 1u;
                     umma::fence_after();
-                    bt_issue_gemm(tmem_base, BT_D12, bf_hi, bf_lo);
-                    umma::commit(mb1);
+                    if (umma::elect_one()) {
+                        bt_issue_gemm(tmem_base, BT_D12, bf_hi, bf_lo);
+                        umma::commit(mb1);
+                    }
+                    __syncwarp();
                 }
             }
 
@@ -559,13 +562,16 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 umma::fence_before();
                 umma::fence_async_smem();
                 umma::mbar_arrive(mbR);
-                if (q == 0) {
+                if (q < 32) {
                     umma::mbar_wait(mbR, parR); parR ^= 1u;
                     umma::fence_after();
-                    bt_issue_gemm(tmem_base, BT_D12, bd_hi, bd_lo);
-                    umma::commit(mb2);
-                    bt_issue_wgrad(tmem_base, x_desc, z_desc, d3_fresh);
-                    umma::commit(mb3);
+                    if (umma::elect_one()) {
+                        bt_issue_gemm(tmem_base, BT_D12, bd_hi, bd_lo);
+                        umma::commit(mb2);
+                        bt_issue_wgrad(tmem_base, x_desc, z_desc, d3_fresh);
+                        umma::commit(mb3);
+                    }
+                    __syncwarp();
                 }
                 wgrad_pending = true;
                 d3_fresh = false;

@@ -99,21 +99,24 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, const float (&
     umma::tmem_st_wait();
     umma::fence_before();
     umma::mbar_arrive(cx.mbar_ready);   // only the issuing thread waits for the 128 arrivals; the other warps move on
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {   // warp 0 (converged): wait for the tile's 128 arrivals, one elected lane issues the batch
         umma::mbar_wait(cx.mbar_ready, cx.parity_ready);
         cx.parity_ready ^= 1u;
         umma::fence_after();
-        const uint32_t idesc = umma::make_idesc_tf32(128, TC_H);
-        // small terms first: the fp32 accumulator truncates on every accumulate (tools/umma_probe2.cu, test 3)
+        if (umma::elect_one()) {
+            const uint32_t idesc = umma::make_idesc_tf32(128, TC_H);
+            // small terms first: the fp32 accumulator truncates on every accumulate (tools/umma_probe2.cu, test 3)
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t acol = cx.tmem_base + (pass == 1 ? TC_COL_AL : TC_COL_AH);
-            const uint64_t bd = (pass == 0) ? cx.blo : cx.bhi;
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t acol = cx.tmem_base + (pass == 1 ? TC_COL_AL : TC_COL_AH);
+                const uint64_t bd = (pass == 0) ? cx.blo : cx.bhi;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)   // next K block: +256 B = +16 in the descriptor's address field
-                umma::mma_tf32_ts(cx.tmem_base + TC_COL_D, acol + k * 8, bd + (uint64_t)(k * 16), idesc, (pass | k) > 0);
+                for (int k = 0; k < 8; ++k)   // next K block: +256 B = +16 in the descriptor's address field
+                    umma::mma_tf32_ts(cx.tmem_base + TC_COL_D, acol + k * 8, bd + (uint64_t)(k * 16), idesc, (pass | k) > 0);
+            }
+            umma::commit(cx.mbar);
         }
-        umma::commit(cx.mbar);
+        __syncwarp();
     }
 }
 

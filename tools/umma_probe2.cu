@@ -27,12 +27,15 @@ __global__ void __launch_bounds__(128) probe2_kernel(const float* __restrict__ A
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t mbar;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const bool sw = (test == 4);   // test 4: B tiles in the K-major SWIZZLE_128B layout (8 rows x 128 B atoms)
     for (int i = tid; i < 64 * 64; i += 128) {
         const int n = i / 64, k = i % 64;
         float hi, lo;
         if (test == 0 || test == 3) { hi = B[i]; lo = 0.f; } else split_tf32(B[i], hi, lo);
-        *(float*)(sBhi + core_off(n, k, 64)) = hi;
-        *(float*)(sBlo + core_off(n, k, 64)) = lo;
+        const int off = sw ? (n / 8) * 2048 + (k / 32) * 1024 + (n % 8) * 128 + ((((k % 32) / 4) ^ (n % 8)) * 16) + (k % 4) * 4
+                           : core_off(n, k, 64);
+        *(float*)(sBhi + off) = hi;
+        *(float*)(sBlo + off) = lo;
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, 256);
     if (tid == 0) mbar_init(&mbar, 1);
@@ -60,18 +63,19 @@ __global__ void __launch_bounds__(128) probe2_kernel(const float* __restrict__ A
     __syncthreads();
     long long t0 = 0, t1 = 0;
     uint32_t parity = 0;
-    const int reps = (test == 2) ? 2 : 1;
+    const int reps = (test == 2 || test == 4) ? 2 : 1;
     for (int rep = 0; rep < reps; ++rep) {
         if (tid == 0) {
             fence_after();
             const uint32_t idesc = make_idesc_tf32(128, 64);
             t0 = clock64();
-            const int npass = (test == 1 || (test == 2 && rep == 0)) ? 3 : 1;
+            const int npass = (test == 1 || ((test == 2 || test == 4) && rep == 0)) ? 3 : 1;
             for (int pass = 0; pass < npass; ++pass) {
                 const uint32_t acol = (pass == 2) ? AL_COL : AH_COL;
                 uint8_t* sB = (pass == 1) ? sBlo : sBhi;
                 for (int k = 0; k < 8; ++k) {
-                    const uint64_t bd = make_desc(smem_u32(sB) + k * 256, 128, 2048);
+                    const uint64_t bd = sw ? make_desc_sw128(smem_u32(sB) + (k / 4) * 1024 + (k % 4) * 32, 16, 2048)
+                                           : make_desc(smem_u32(sB) + k * 256, 128, 2048);
                     mma_tf32_ts(tmem + D_COL, tmem + acol + k * 8, bd, idesc, (pass | k) > 0);
                 }
             }
@@ -128,7 +132,7 @@ int main() {
     float *dA, *dB, *dD; long long* dC;
     CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4)); CK(cudaMalloc(&dC, 64));
     CK(cudaFuncSetAttribute(probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 1024));
-    for (int test = 0; test < 4; ++test) {
+    for (int test = 0; test < 5; ++test) {
         std::vector<float> At = A, Bt = B;
         if (test == 3) {  // D starts as exactly 1.0 in column n<8 of every row: A = e_0-ish, B rows n<8 = e_0
             for (auto& x : At) x = 0.f;
@@ -154,7 +158,7 @@ int main() {
                 double r = 0, nrm = 0;
                 for (int k = 0; k < 64; ++k) {
                     const float a = At[m * 64 + k], b = Bt[n * 64 + k];
-                    r += (test == 0) ? (double)tf32_trunc(a) * tf32_trunc(b) : (double)a * b;
+                    r += (test == 0) ? (double)tf32_trunc(a) * tf32_trunc(b) : (double)a * b;   // tests 2 / 4 end with a single-pass batch: large error expected
                     nrm += fabs((double)a * b);
                 }
                 const double e = fabs(D[m * 64 + n] - r);
