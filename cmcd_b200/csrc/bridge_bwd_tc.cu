@@ -62,36 +62,49 @@ __device__ __forceinline__ float bt_warp_sum(float v) {
     return v;
 }
 
+// Branch-free pair exchange for the butterflies: with m = all-ones in the upper half of the lane group and 0 in the
+// lower half, send = m ? a : b and keep = m ? b : a as two 3-input logic ops (LOP3) -- selects written with ?: compile to
+// pairs of predicated moves here, which made MOV the most executed opcode of the kernel.
+__device__ __forceinline__ void bt_pick(float a, float b, uint32_t m, float& send, float& keep) {
+    const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+    const uint32_t us = (ua & m) | (ub & ~m);
+    send = __uint_as_float(us);
+    keep = __uint_as_float(ua ^ ub ^ us);
+}
+
 // Sum v[e] over the 32 lanes of the warp for all 16 e at once (halving butterfly): returns the total of element
 // (lane >> 1), valid in every lane (lane pairs hold the same element).
 __device__ __forceinline__ float bt_warp_reduce16(const float (&v)[16], int lane) {
     float a[8], b[4], c[2];
     {
-        const bool up = lane & 16;
+        const uint32_t m = (lane & 16) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float send = up ? v[k] : v[k + 8], keep = up ? v[k + 8] : v[k];
+            float send, keep;
+            bt_pick(v[k], v[k + 8], m, send, keep);
             a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
     }
     {
-        const bool up = lane & 8;
+        const uint32_t m = (lane & 8) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float send = up ? a[k] : a[k + 4], keep = up ? a[k + 4] : a[k];
+            float send, keep;
+            bt_pick(a[k], a[k + 4], m, send, keep);
             b[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
         }
     }
     {
-        const bool up = lane & 4;
+        const uint32_t m = (lane & 4) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const float send = up ? b[k] : b[k + 2], keep = up ? b[k + 2] : b[k];
+            float send, keep;
+            bt_pick(b[k], b[k + 2], m, send, keep);
             c[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
         }
     }
-    const bool up = lane & 2;
-    const float send = up ? c[0] : c[1], keep = up ? c[1] : c[0];
+    float send, keep;
+    bt_pick(c[0], c[1], (lane & 2) ? 0xFFFFFFFFu : 0u, send, keep);
     float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
     d += __shfl_xor_sync(0xffffffffu, d, 1);
     return d;
@@ -102,42 +115,46 @@ __device__ __forceinline__ void bt_warp_reduce16x3(const float (&v0)[16], const 
                                                    float& r0, float& r1, float& r2) {
     float a[3][8], b[3][4], c[3][2], d[3];
     {
-        const bool up = lane & 16;
+        const uint32_t m = (lane & 16) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float s0 = up ? v0[k] : v0[k + 8], k0 = up ? v0[k + 8] : v0[k];
-            const float s1 = up ? v1[k] : v1[k + 8], k1 = up ? v1[k + 8] : v1[k];
-            const float s2 = up ? v2[k] : v2[k + 8], k2 = up ? v2[k + 8] : v2[k];
+            float s0, k0, s1, k1, s2, k2;
+            bt_pick(v0[k], v0[k + 8], m, s0, k0);
+            bt_pick(v1[k], v1[k + 8], m, s1, k1);
+            bt_pick(v2[k], v2[k + 8], m, s2, k2);
             a[0][k] = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
             a[1][k] = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
             a[2][k] = k2 + __shfl_xor_sync(0xffffffffu, s2, 16);
         }
     }
     {
-        const bool up = lane & 8;
+        const uint32_t m = (lane & 8) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                const float send = up ? a[s][k] : a[s][k + 4], keep = up ? a[s][k + 4] : a[s][k];
+                float send, keep;
+                bt_pick(a[s][k], a[s][k + 4], m, send, keep);
                 b[s][k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
             }
     }
     {
-        const bool up = lane & 4;
+        const uint32_t m = (lane & 4) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
         for (int k = 0; k < 2; ++k)
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                const float send = up ? b[s][k] : b[s][k + 2], keep = up ? b[s][k + 2] : b[s][k];
+                float send, keep;
+                bt_pick(b[s][k], b[s][k + 2], m, send, keep);
                 c[s][k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
             }
     }
     {
-        const bool up = lane & 2;
+        const uint32_t m = (lane & 2) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-            const float send = up ? c[s][0] : c[s][1], keep = up ? c[s][1] : c[s][0];
+            float send, keep;
+            bt_pick(c[s][0], c[s][1], m, send, keep);
             d[s] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
         }
     }
