@@ -15,7 +15,8 @@
 //                                  (the tensor-core accumulator truncates, tools/umma_probe2.cu test 3).
 // TMEM per tile (256 columns): A_hi | A_lo | D (pre2, then da1) | gW2 accumulator.  Between GEMM1 and GEMM2 the dead
 // A region doubles as per-thread scratch for a2 / act'(pre2).  The skinny gradients (per-step bias tables, U1, W3)
-// are reduced over the 32 particles of a warp with a 16-wide shuffle butterfly and then added atomically.
+// are reduced over the 32 particles of a warp with 16-wide shuffle butterflies (three in lock step) and then added
+// atomically (step-indexed tables) or kept in per-lane register accumulators (U1, W3).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -72,45 +73,9 @@ __device__ __forceinline__ void bt_pick(float a, float b, uint32_t m, float& sen
     keep = __uint_as_float(ua ^ ub ^ us);
 }
 
-// Sum v[e] over the 32 lanes of the warp for all 16 e at once (halving butterfly): returns the total of element
-// (lane >> 1), valid in every lane (lane pairs hold the same element).
-__device__ __forceinline__ float bt_warp_reduce16(const float (&v)[16], int lane) {
-    float a[8], b[4], c[2];
-    {
-        const uint32_t m = (lane & 16) ? 0xFFFFFFFFu : 0u;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float send, keep;
-            bt_pick(v[k], v[k + 8], m, send, keep);
-            a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-    }
-    {
-        const uint32_t m = (lane & 8) ? 0xFFFFFFFFu : 0u;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float send, keep;
-            bt_pick(a[k], a[k + 4], m, send, keep);
-            b[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    {
-        const uint32_t m = (lane & 4) ? 0xFFFFFFFFu : 0u;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            float send, keep;
-            bt_pick(b[k], b[k + 2], m, send, keep);
-            c[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-    }
-    float send, keep;
-    bt_pick(c[0], c[1], (lane & 2) ? 0xFFFFFFFFu : 0u, send, keep);
-    float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
-    return d;
-}
-
-// Three independent 16-wide butterflies advanced stage by stage (explicit 3-way ILP across the shuffle latency).
+// Halving butterfly: sums v[e] over the 32 lanes of the warp for all 16 e at once; the result for element (lane >> 1) ends
+// up in every lane (lane pairs hold the same element).  Three independent butterflies are advanced stage by stage
+// (explicit 3-way ILP across the shuffle latency).
 __device__ __forceinline__ void bt_warp_reduce16x3(const float (&v0)[16], const float (&v1)[16], const float (&v2)[16], int lane,
                                                    float& r0, float& r1, float& r2) {
     float a[3][8], b[3][4], c[3][2], d[3];
@@ -181,8 +146,6 @@ __device__ __forceinline__ void bt_stage_bf16x2(uint8_t* t1, uint8_t* t2, int q,
     *reinterpret_cast<uint4*>(t2 + o0) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
     *reinterpret_cast<uint4*>(t2 + o1) = make_uint4(h2[4], h2[5], h2[6], h2[7]);
 }
-
-__device__ __forceinline__ void bt_bar(int wg) { asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory"); }
 
 // 24 x tcgen05.mma kind::tf32: D = A_hi B_lo + A_lo B_hi + A_hi B_hi (small terms first: the accumulator truncates)
 // (dhi / dlo: shared-memory descriptors of the B tile's first K block; one K block further = +256 B = +16 in the address field)

@@ -9,7 +9,8 @@
 // Mapping: one CTA = 128 threads = 128 particles = the 128 TMEM lanes.  Thread p owns particle p of the tile:
 //   layer 1   a1 = act(U1^T x + c1[t])  per thread; split into tf32 hi/lo and written with tcgen05.st into the
 //             thread's own TMEM lane (columns AH.., AL..) -- this *is* the A operand [128 x 64] of the MMA;
-//   layer 2   one thread issues 24 x tcgen05.mma kind::tf32 (M=128, N=64, K=8): D = A_hi B_lo + A_lo B_hi + A_hi B_hi
+//   layer 2   every thread arrives on an mbarrier; one elected lane of warp 0 issues 24 x tcgen05.mma kind::tf32
+//             (M=128, N=64, K=8): D = A_hi B_lo + A_lo B_hi + A_hi B_hi
 //             with B = W2^T split hi/lo once per CTA in shared memory (K-major core-matrix tiles);
 //   epilogue  each thread reads its lane of D with tcgen05.ld (64 columns), adds c2[t], activation, and folds
 //             the 64 x d output layer in registers.
@@ -172,7 +173,7 @@ __device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (
             }
         }
     }
-    umma::fence_before();   // orders these tcgen05.ld before the next batch's writes to D (via the next __syncthreads)
+    umma::fence_before();   // orders these tcgen05.ld before the next batch's writes to D (via the next mbarrier arrive / wait)
 #pragma unroll
     for (int m = 0; m < D; ++m) out[m] = cx.out_scale * fminf(fmaxf(o[m], -cx.out_clip), cx.out_clip);
 }
