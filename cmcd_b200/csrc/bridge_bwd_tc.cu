@@ -15,8 +15,8 @@
 //                                  (the tensor-core accumulator truncates, tools/umma_probe2.cu test 3).
 // TMEM per tile (256 columns): A_hi | A_lo | D (pre2, then da1) | gW2 accumulator.  Between GEMM1 and GEMM2 the dead
 // A region doubles as per-thread scratch for a2 / act'(pre2).  The skinny gradients (per-step bias tables, U1, W3)
-// are reduced over the 32 particles of a warp with 16-wide shuffle butterflies (three in lock step) and then added
-// atomically (step-indexed tables) or kept in per-lane register accumulators (U1, W3).
+// are reduced over the 32 particles of a warp by a transposition through TMEM (32x32b store, 16x256b load) plus three
+// shuffle stages, then added atomically (step-indexed tables) or kept in per-lane register accumulators (U1, W3).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -63,7 +63,7 @@ __device__ __forceinline__ float bt_warp_sum(float v) {
     return v;
 }
 
-// Branch-free pair exchange for the butterflies: with m = all-ones in the upper half of the lane group and 0 in the
+// Branch-free pair exchange for the reduction stages: with m = all-ones in the upper half of the lane group and 0 in the
 // lower half, send = m ? a : b and keep = m ? b : a as two 3-input logic ops (LOP3) -- selects written with ?: compile to
 // pairs of predicated moves here, which made MOV the most executed opcode of the kernel.
 __device__ __forceinline__ void bt_pick(float a, float b, uint32_t m, float& send, float& keep) {
@@ -73,58 +73,65 @@ __device__ __forceinline__ void bt_pick(float a, float b, uint32_t m, float& sen
     keep = __uint_as_float(ua ^ ub ^ us);
 }
 
-// Halving butterfly: sums v[e] over the 32 lanes of the warp for all 16 e at once; the result for element (lane >> 1) ends
-// up in every lane (lane pairs hold the same element).  Three independent butterflies are advanced stage by stage
-// (explicit 3-way ILP across the shuffle latency).
-__device__ __forceinline__ void bt_warp_reduce16x3(const float (&v0)[16], const float (&v1)[16], const float (&v2)[16], int lane,
-                                                   float& r0, float& r1, float& r2) {
-    float a[3][8], b[3][4], c[3][2], d[3];
+// Column sums over the 32 particles of a warp through TMEM: every thread stores its 16 values into its own lane
+// (32x32b), the warp reads the block back as 16x256b fragments -- thread t then holds 4 lanes x 4 columns -- sums its
+// lanes, and three exchange stages over lane bits 4, 3, 2 finish the reduction.  Half the instruction slots of the
+// shuffle butterfly.  `scratch` = 48 free TMEM columns of this warp's lane quarter.  Result: the total of element
+// bt_red_col(lane) in every lane (lanes differing in bit 2 hold the same element).
+__device__ __forceinline__ int bt_red_col(int lane) { return ((lane >> 4) & 1) * 8 + (lane & 3) * 2 + ((lane >> 3) & 1); }
+__device__ __forceinline__ void bt_tmem_reduce16x3(uint32_t scratch, const float (&v0)[16], const float (&v1)[16], const float (&v2)[16],
+                                                   int lane, float& r0, float& r1, float& r2) {
+    {
+        uint32_t w[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) w[e] = __float_as_uint(v0[e]);
+        umma::tmem_st16(scratch, w);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) w[e] = __float_as_uint(v1[e]);
+        umma::tmem_st16(scratch + 16, w);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) w[e] = __float_as_uint(v2[e]);
+        umma::tmem_st16(scratch + 32, w);
+    }
+    umma::tmem_st_wait();
+    uint32_t a[3][8], b[3][8];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        umma::tmem_ld_16x256b_x2(scratch + 16 * s, a[s]);
+        umma::tmem_ld_16x256b_x2(scratch + 16 * s + (16u << 16), b[s]);
+    }
+    umma::tmem_ld_wait();
+    float p[3][4];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = (j >> 1) * 4 + (j & 1);   // registers r, r + 2 of both loads hold column 8 (j / 2) + 2 (t % 4) + j % 2
+            p[s][j] = (__uint_as_float(a[s][r]) + __uint_as_float(a[s][r + 2])) + (__uint_as_float(b[s][r]) + __uint_as_float(b[s][r + 2]));
+        }
+    float q[3][2], d[3];
     {
         const uint32_t m = (lane & 16) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float s0, k0, s1, k1, s2, k2;
-            bt_pick(v0[k], v0[k + 8], m, s0, k0);
-            bt_pick(v1[k], v1[k + 8], m, s1, k1);
-            bt_pick(v2[k], v2[k + 8], m, s2, k2);
-            a[0][k] = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
-            a[1][k] = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
-            a[2][k] = k2 + __shfl_xor_sync(0xffffffffu, s2, 16);
-        }
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float send, keep;
+                bt_pick(p[s][j], p[s][j + 2], m, send, keep);
+                q[s][j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
     }
     {
         const uint32_t m = (lane & 8) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                float send, keep;
-                bt_pick(a[s][k], a[s][k + 4], m, send, keep);
-                b[s][k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-    }
-    {
-        const uint32_t m = (lane & 4) ? 0xFFFFFFFFu : 0u;
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-#pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                float send, keep;
-                bt_pick(b[s][k], b[s][k + 2], m, send, keep);
-                c[s][k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-    }
-    {
-        const uint32_t m = (lane & 2) ? 0xFFFFFFFFu : 0u;
-#pragma unroll
         for (int s = 0; s < 3; ++s) {
             float send, keep;
-            bt_pick(c[s][0], c[s][1], m, send, keep);
-            d[s] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            bt_pick(q[s][0], q[s][1], m, send, keep);
+            d[s] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
         }
     }
 #pragma unroll
-    for (int s = 0; s < 3; ++s) d[s] += __shfl_xor_sync(0xffffffffu, d[s], 1);
+    for (int s = 0; s < 3; ++s) d[s] += __shfl_xor_sync(0xffffffffu, d[s], 4);
     r0 = d[0]; r1 = d[1]; r2 = d[2];
 }
 
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
     for (int j = 0; j < D; ++j) { mu[j] = a.vd_mean[j]; sig[j] = expf(a.vd_logdiag[j]); ivar[j] = 1.0f / (sig[j] * sig[j]); }
 
     // per-lane accumulators of the skinny gradients that are not indexed by the step: after a butterfly, lane l holds the
-    // warp's sum for hidden unit 16 cc + (l >> 1); summed over the whole kernel, flushed once at the end
+    // warp's sum for hidden unit 16 cc + bt_red_col(l); summed over the whole kernel, flushed once at the end
     float aW3[4][D], aU1[4][D];
 #pragma unroll
     for (int k4 = 0; k4 < 4; ++k4)
@@ -532,8 +539,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 #pragma unroll
                         for (int e = 0; e < 16; ++e) { t0[e] = __uint_as_float(a2u[e]) * vo[0]; t1[e] = __uint_as_float(a2u[e]) * vo[1]; }
                         float s2, s30, s31;
-                        bt_warp_reduce16x3(dp2, t0, t1, lane, s2, s30, s31);
-                        if (!(lane & 1)) atomicAdd(part + L.c2 + (size_t)t * BT_H + cc * 16 + (lane >> 1), s2);
+                        bt_tmem_reduce16x3(tmem_lane + BT_D12, dp2, t0, t1, lane, s2, s30, s31);   // D is free between GEMM1's epilogue and GEMM2
+                        if (!(lane & 4)) atomicAdd(part + L.c2 + (size_t)t * BT_H + cc * 16 + bt_red_col(lane), s2);
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) { aW3[k4][0] += (k4 == cc) ? s30 : 0.f; aW3[k4][1] += (k4 == cc) ? s31 : 0.f; }
                     }
@@ -607,8 +614,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 #pragma unroll
                         for (int e = 0; e < 16; ++e) { t0[e] = x[0] * dp1[e]; t1[e] = x[1] * dp1[e]; }
                         float s1, s40, s41;
-                        bt_warp_reduce16x3(dp1, t0, t1, lane, s1, s40, s41);
-                        if (!(lane & 1)) atomicAdd(part + L.c1 + (size_t)t * BT_H + cc * 16 + (lane >> 1), s1);
+                        bt_tmem_reduce16x3(tmem_lane + BT_A_HI, dp1, t0, t1, lane, s1, s40, s41);   // the A region is dead after GEMM2
+                        if (!(lane & 4)) atomicAdd(part + L.c1 + (size_t)t * BT_H + cc * 16 + bt_red_col(lane), s1);
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) { aU1[k4][0] += (k4 == cc) ? s40 : 0.f; aU1[k4][1] += (k4 == cc) ? s41 : 0.f; }
                     }
@@ -653,13 +660,13 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
         }
     }
     flush_d3();
-    if (!(lane & 1)) {
+    if (!(lane & 4)) {
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4)
 #pragma unroll
             for (int m = 0; m < D; ++m) {
-                atomicAdd(sAccW3 + (k4 * 16 + (lane >> 1)) * D + m, aW3[k4][m]);
-                atomicAdd(sAccU1 + m * BT_H + k4 * 16 + (lane >> 1), aU1[k4][m]);
+                atomicAdd(sAccW3 + (k4 * 16 + bt_red_col(lane)) * D + m, aW3[k4][m]);
+                atomicAdd(sAccU1 + m * BT_H + k4 * 16 + bt_red_col(lane), aU1[k4][m]);
             }
     }
     __syncthreads();
