@@ -17,6 +17,8 @@
 // While the MMA batch runs (~1.6k cycles) the thread does the work that does not depend on the network output:
 // threefry split + Gaussian for the step, the target score at z', the key advance.  Two CTAs per SM (256 TMEM
 // columns each) alternate so the CUDA cores always have one tile's epilogue / layer 1 to run.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -24,8 +26,11 @@ namespace cmcd {
 
 constexpr int TC_PB = 128;   // particles per CTA (TMEM lanes)
 constexpr int TC_H = 64;     // hidden width of this path
-constexpr uint32_t TC_COL_D = 0, TC_COL_AH = 64, TC_COL_AL = 128, TC_COLS = 256;
+// TMEM: 128 columns (accumulator D, A_hi as tf32) + 32 columns (A_lo as packed bf16 pairs) = 160 per CTA -> three CTAs per SM
+constexpr uint32_t TC_COL_D = 0, TC_COL_AH = 64, TC_COLS_MAIN = 128, TC_COLS_LO = 32;
 constexpr int TC_B_BYTES = TC_H * TC_H * 4;   // one 64x64 fp32 operand tile
+constexpr int TC_B16_BYTES = TC_H * TC_H * 2; // the bf16 copy of B_hi for the A_lo pass
+constexpr int TC_CTAS_PER_SM = 3;
 
 template <int D>
 struct TcCtx {
@@ -33,8 +38,9 @@ struct TcCtx {
     const float *c1, *c2, *c3;            // global per-step tables [T][64], [T][64], [T][D]
     const float* tab;                     // this warp's staged rows c1[t] | c2[t] of the current half-step (shared memory)
     float out_scale, out_clip;
-    uint32_t tmem_base, tmem_lane;        // allocation base; base + this warp's lane quarter
-    uint64_t bhi, blo;                    // shared-memory descriptors of the B tiles (first K block)
+    uint32_t tmem_base, tmem_lane;        // main allocation (D | A_hi): base; base + this warp's lane quarter
+    uint32_t tmem_lo_base, tmem_lo_lane;  // second allocation: A_lo as packed bf16 pairs
+    uint64_t bhi, blo, bhi16;             // shared-memory descriptors of the B tiles (first K block)
     uint64_t* mbar;                       // MMA batch complete
     uint64_t* mbar_ready;                 // A operand staged by all 128 threads
     uint32_t parity, parity_ready;
@@ -61,7 +67,7 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, const float (&
     for (int m = 0; m < D; ++m) skipacc[m] = 0.f;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
-        uint32_t h[16], l[16];
+        uint32_t h[16], l[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 cc = c1v[c * 4 + q];
@@ -80,6 +86,7 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, const float (&
 #pragma unroll
                 for (int e = 0; e < 4; ++e) av[e] = act_tc<ACT>(p[e]);
             }
+            float lov[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float a1 = av[e];
@@ -88,14 +95,17 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, const float (&
 #pragma unroll
                     for (int m = 0; m < D; ++m) skipacc[m] = fmaf(a1, cx.sW3[j * D + m], skipacc[m]);
                 }
-                float hi, lo;
-                umma::split_tf32(a1, hi, lo);
+                float hi;
+                umma::split_tf32(a1, hi, lov[e]);
                 h[q * 4 + e] = __float_as_uint(hi);
-                l[q * 4 + e] = __float_as_uint(lo);
             }
+            // the low part only has to carry ~9 more bits: bf16, two K elements per TMEM column (even k in the low half)
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(lov[0], lov[1]), l23 = __floats2bfloat162_rn(lov[2], lov[3]);
+            l[q * 2 + 0] = *reinterpret_cast<const uint32_t*>(&l01);
+            l[q * 2 + 1] = *reinterpret_cast<const uint32_t*>(&l23);
         }
         umma::tmem_st16(cx.tmem_lane + TC_COL_AH + c * 16, h);
-        umma::tmem_st16(cx.tmem_lane + TC_COL_AL + c * 16, l);
+        umma::tmem_st8(cx.tmem_lo_lane + c * 8, l);
     }
     umma::tmem_st_wait();
     umma::fence_before();
@@ -105,16 +115,16 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, const float (&
         cx.parity_ready ^= 1u;
         umma::fence_after();
         if (umma::elect_one()) {
-            const uint32_t idesc = umma::make_idesc_tf32(128, TC_H);
-            // small terms first: the fp32 accumulator truncates on every accumulate (tools/umma_probe2.cu, test 3)
+            const uint32_t idesc = umma::make_idesc_tf32(128, TC_H), idesc16 = umma::make_idesc_bf16_k(128, TC_H);
+            const uint32_t dcol = cx.tmem_base + TC_COL_D, ahi = cx.tmem_base + TC_COL_AH;
+            // D = A_hi B_lo + A_lo B_hi + A_hi B_hi, small terms first: the fp32 accumulator truncates on every accumulate
+            // (tools/umma_probe2.cu, test 3).  Next K block of a B tile: +256 B = +16 in the descriptor's address field.
 #pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t acol = cx.tmem_base + (pass == 1 ? TC_COL_AL : TC_COL_AH);
-                const uint64_t bd = (pass == 0) ? cx.blo : cx.bhi;
+            for (int k = 0; k < 8; ++k) umma::mma_tf32_ts(dcol, ahi + k * 8, cx.blo + (uint64_t)(k * 16), idesc, k > 0);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)   // next K block: +256 B = +16 in the descriptor's address field
-                    umma::mma_tf32_ts(cx.tmem_base + TC_COL_D, acol + k * 8, bd + (uint64_t)(k * 16), idesc, (pass | k) > 0);
-            }
+            for (int k = 0; k < 4; ++k) umma::mma_f16_ts(dcol, cx.tmem_lo_base + k * 8, cx.bhi16 + (uint64_t)(k * 16), idesc16, 1);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) umma::mma_tf32_ts(dcol, ahi + k * 8, cx.bhi + (uint64_t)(k * 16), idesc, 1);
             umma::commit(cx.mbar);
         }
         __syncwarp();
@@ -179,15 +189,16 @@ __device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (
 }
 
 template <int D, int ACT>
-__global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArgs a) {
+__global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(const BridgeArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint32_t tmem_slot;
+    __shared__ uint32_t tmem_slot, tmem_slot_lo;
     __shared__ __align__(8) uint64_t mbar, mbar_ready;
     const int tid = threadIdx.x, warp = tid >> 5;
     const NetView& nv = a.net;
     uint8_t* sBhi = smem_raw;
     uint8_t* sBlo = smem_raw + TC_B_BYTES;
-    float* sf = reinterpret_cast<float*>(smem_raw + 2 * TC_B_BYTES);
+    uint8_t* sBhi16 = smem_raw + 2 * TC_B_BYTES;
+    float* sf = reinterpret_cast<float*>(smem_raw + 2 * TC_B_BYTES + TC_B16_BYTES);
     float* sU1 = sf;
     float* sU2 = sU1 + D * TC_H;
     float* sW3 = sU2 + D * TC_H;
@@ -201,6 +212,7 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
         const int off = umma::core_off(j, i, TC_H);
         *reinterpret_cast<float*>(sBhi + off) = hi;
         *reinterpret_cast<float*>(sBlo + off) = lo;
+        *reinterpret_cast<__nv_bfloat16*>(sBhi16 + umma::core_off16(j, i, TC_H)) = __float2bfloat16(hi);
     }
     for (int i = tid; i < D * TC_H; i += TC_PB) { sU1[i] = nv.U1[i]; sU2[i] = nv.U2 ? nv.U2[i] : 0.f; }
     for (int i = tid; i < TC_H * D; i += TC_PB) sW3[i] = nv.W3[i];
@@ -220,7 +232,7 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
     if (fast_gmm)
         for (int i = tid; i < a.tgt.ncomp; i += TC_PB) sMu[i] = make_float2(a.tgt.mix[i * MIX_STRIDE], a.tgt.mix[i * MIX_STRIDE + 1]);
     const ManyGmmConst gc = many_gmm_const(a.tgt);
-    if (warp == 0) umma::tmem_alloc(&tmem_slot, TC_COLS);
+    if (warp == 0) { umma::tmem_alloc(&tmem_slot, TC_COLS_MAIN, false); umma::tmem_alloc(&tmem_slot_lo, TC_COLS_LO, true); }
     if (tid == 0) { umma::mbar_init(&mbar, 1); umma::mbar_init(&mbar_ready, TC_PB); }
     umma::fence_async_smem();   // generic-proxy writes of the B tiles -> visible to the tensor core (async proxy)
     umma::fence_before();
@@ -233,6 +245,9 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
     cx.out_scale = nv.out_scale; cx.out_clip = nv.out_clip;
     cx.tmem_base = tmem_slot;
     cx.tmem_lane = tmem_slot + ((uint32_t)(warp * 32) << 16);
+    cx.tmem_lo_base = tmem_slot_lo;
+    cx.tmem_lo_lane = tmem_slot_lo + ((uint32_t)(warp * 32) << 16);
+    cx.bhi16 = umma::make_desc(umma::smem_u32(sBhi16), 128, 16 * TC_H);
     cx.bhi = umma::make_desc(umma::smem_u32(sBhi), 128, 32 * TC_H);
     cx.blo = umma::make_desc(umma::smem_u32(sBlo), 128, 32 * TC_H);
     cx.mbar = &mbar; cx.parity = 0u;
@@ -356,18 +371,18 @@ __global__ void __launch_bounds__(TC_PB, 2) bridge_fwd_tc_kernel(const BridgeArg
     }
     umma::fence_before();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(cx.tmem_base, TC_COLS);
+    if (warp == 0) { umma::tmem_dealloc(cx.tmem_base, TC_COLS_MAIN); umma::tmem_dealloc(cx.tmem_lo_base, TC_COLS_LO); }
 }
 
 template <int D, int ACT>
 static int launch_fwd_tc_t(const BridgeArgs& a, cudaStream_t st, int num_sms) {
-    // request > 227/3 KB so that at most two CTAs (2 x 256 TMEM columns) share an SM
-    size_t smem = 2 * TC_B_BYTES + (2 * D * TC_H + TC_H * D + D * D + 4 + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 4 * 4 * TC_H + 8) * sizeof(float);
-    if (smem < 80 * 1024) smem = 80 * 1024;
+    // request > 227/4 KB so that at most three CTAs (3 x 160 TMEM columns) share an SM
+    size_t smem = 2 * TC_B_BYTES + TC_B16_BYTES + (2 * D * TC_H + TC_H * D + D * D + 4 + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 4 * 4 * TC_H + 8) * sizeof(float);
+    if (smem < 58 * 1024) smem = 58 * 1024;
     auto kern = bridge_fwd_tc_kernel<D, ACT>;
     CMCD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ntiles = (a.N + TC_PB - 1) / TC_PB;
-    long long grid = 2LL * num_sms;
+    long long grid = (long long)TC_CTAS_PER_SM * num_sms;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, TC_PB, smem, st>>>(a);

@@ -86,6 +86,23 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
         :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// kind::f16, bf16 x bf16 -> fp32, both operands K-major; A may come from TMEM as packed pairs: column c of lane m holds
+// (A[m][2c] in the low half, A[m][2c+1] in the high half) -- validated by tools/umma_probe5.cu.  One MMA consumes K = 16
+// = 8 packed TMEM columns and two 8x16 B core matrices of the B tile (element (n, k) at (n/8)*16*K + (k/8)*128 + (n%8)*16 + (k%8)*2).
+__host__ __device__ inline uint32_t make_idesc_bf16_k(int M, int N) {
+    uint32_t d = 0;
+    d |= 1u << 4; d |= 1u << 7; d |= 1u << 10;
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
+    return d;
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__host__ __device__ inline int core_off16(int n, int k, int kdim) { return (n / 8) * (16 * kdim) + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2; }
 // byte offset of element (k, i) in an MN-major SW128 bf16 tile
 __host__ __device__ inline int sw128_off(int k, int i) { return k * 128 + ((((i / 8) ^ (k % 8)) * 16) + (i % 8) * 2); }
 
@@ -123,9 +140,10 @@ __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::aft
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // one warp allocates `ncols` (power of two >= 32) TMEM columns; base address lands in *slot (shared memory)
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+// (last = false: more allocations follow -- the permit is relinquished only after the CTA's final allocation)
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols, bool last = true) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (last) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(base), "r"(ncols) : "memory");
@@ -155,6 +173,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
            "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
