@@ -42,9 +42,9 @@ FLOP_FWD = 35.0e3
 FLOP_TRAIN = 105.0e3
 
 
-# ncu --set full capture of bridge_bwd_tc_kernel at N=131072, K=256 (profiles/r1_ncu_summary.md, third capture):
-# dram__bytes_read.sum 334.5 MB + dram__bytes_write.sum 54.2 MB per launch
-NCU_BWD_DRAM_BYTES_PER_PARTICLE = (334.516480e6 + 54.152448e6) / 131072
+# ncu --set full capture of bridge_bwd_tc_kernel at N=131072, K=256 (profiles/r1_ncu_summary.md, fourth capture):
+# dram__bytes_read.sum 337.1 MB + dram__bytes_write.sum 55.6 MB per launch
+NCU_BWD_DRAM_BYTES_PER_PARTICLE = (337.088256e6 + 55.577856e6) / 131072
 
 
 def _tensor_peak():
