@@ -18,7 +18,7 @@ _fp = C.c_void_p  # device pointers travel as integers
 class CmcdNet(C.Structure):
     _fields_ = [("arch", C.c_int32), ("hidden", C.c_int32), ("hidden_pad", C.c_int32), ("n_rows", C.c_int32),
                 ("U1", _fp), ("U2", _fp), ("U3", _fp), ("W2", _fp), ("W3", _fp), ("c1", _fp), ("c2", _fp), ("c3", _fp),
-                ("out_scale", C.c_float), ("out_clip", C.c_float)]
+                ("out_scale", C.c_float), ("out_clip", C.c_float), ("out_scale_dev", _fp)]
 
 
 class CmcdNetGrad(C.Structure):

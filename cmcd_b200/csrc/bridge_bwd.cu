@@ -159,7 +159,7 @@ __device__ CMCD_NETB_INL void net_bwd(const NetView& nv, const NetSmem& s, int t
     for (int m = 0; m < D; ++m) {
         const float oc = fminf(fmaxf(o[m], -nv.out_clip), nv.out_clip);
         gos = fmaf(v[m], oc, gos);
-        vo[m] = (fabsf(o[m]) <= nv.out_clip) ? v[m] * nv.out_scale : 0.f;
+        vo[m] = (fabsf(o[m]) <= nv.out_clip) ? v[m] * net_out_scale(nv) : 0.f;
         sVo[m * RS + tid] = vo[m];
         sX[m * RS + tid] = x[m];
     }
@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(BPB, 1) bridge_bwd_kernel(const BridgeArgs a, 
     const NetView& nv = a.net;
     const int HP = HPT ? HPT : nv.HP;
     const bool has_net = nv.arch != CMCD_ARCH_NONE;
+    const float out_scale = has_net ? net_out_scale(nv) : 1.0f;
     NetSmem ns = net_stage_smem(nv, D, sm);
     float* sTp = sm + (has_net ? net_smem_floats(D, HP) : 0);
     const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(BPB, 1) bridge_bwd_kernel(const BridgeArgs a, 
                 net_fwd_store<D, ACT, HPT, JC, RS>(nv, ns, tb, zp, ob, S1 + tid, S2 + tid, S3 + tid);
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
-                    nnb[j] = nv.out_scale * fminf(fmaxf(ob[j], -nv.out_clip), nv.out_clip);
+                    nnb[j] = out_scale * fminf(fmaxf(ob[j], -nv.out_clip), nv.out_clip);
                     mb[j] = mb[j] + eps * nnb[j];
                 }
             }
@@ -456,7 +457,7 @@ __global__ void __launch_bounds__(BPB, 1) bridge_bwd_kernel(const BridgeArgs a, 
                 net_fwd_store<D, ACT, HPT, JC, RS>(nv, ns, i, z, of, S1 + tid, S2 + tid, S3 + tid);
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
-                    nnf[j] = nv.out_scale * fminf(fmaxf(of[j], -nv.out_clip), nv.out_clip);
+                    nnf[j] = out_scale * fminf(fmaxf(of[j], -nv.out_clip), nv.out_clip);
                     mf[j] = mf[j] - eps * nnf[j];
                 }
             }

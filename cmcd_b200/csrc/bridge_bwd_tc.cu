@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
     const bool nn_b = (a.mode != CMCD_MODE_ULA);
     const bool nn_f = cais;
     const int K = a.K;
+    const float out_scale = net_out_scale(nv);
 
     float mu[D], sig[D], ivar[D];
 #pragma unroll
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 }
                 umma::tmem_st_wait();
 #pragma unroll
-                for (int m = 0; m < D; ++m) nn[m] = nv.out_scale * fminf(fmaxf(o[m], -nv.out_clip), nv.out_clip);
+                for (int m = 0; m < D; ++m) nn[m] = out_scale * fminf(fmaxf(o[m], -nv.out_clip), nv.out_clip);
             }
 
             // ---------------- kernel mean, residual, cotangent on the mean ----------------
@@ -504,7 +505,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                     const float v = sgn * eps * G[m];
                     const float oc = fminf(fmaxf(o[m], -nv.out_clip), nv.out_clip);
                     gos = fmaf(v, oc, gos);
-                    vo[m] = (fabsf(o[m]) <= nv.out_clip) ? v * nv.out_scale : 0.f;
+                    vo[m] = (fabsf(o[m]) <= nv.out_clip) ? v * out_scale : 0.f;
                     const float s = bt_warp_sum(vo[m]);
                     if (lane == 0) atomicAdd(part + L.c3 + (size_t)t * D + m, s);
                 }

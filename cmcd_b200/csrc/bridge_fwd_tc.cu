@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
     TcCtx<D> cx;
     cx.sU1 = sU1; cx.sU2 = sU2; cx.sW3 = sW3; cx.sU3 = sU3;
     cx.c1 = nv.c1; cx.c2 = nv.c2; cx.c3 = nv.c3;
-    cx.out_scale = nv.out_scale; cx.out_clip = nv.out_clip;
+    cx.out_scale = net_out_scale(nv); cx.out_clip = nv.out_clip;
     cx.tmem_base = tmem_slot;
     cx.tmem_lane = tmem_slot + ((uint32_t)(warp * 32) << 16);
     cx.tmem_lo_base = tmem_slot_lo;

@@ -76,7 +76,7 @@ static int build_args(const cmcd_bridge_desc* d, const int32_t* seeds, const flo
         a.net.arch = net->arch; a.net.H = net->hidden; a.net.HP = net->hidden_pad; a.net.T = net->n_rows;
         a.net.U1 = net->U1; a.net.U2 = net->U2; a.net.U3 = net->U3; a.net.W2 = net->W2; a.net.W3 = net->W3;
         a.net.c1 = net->c1; a.net.c2 = net->c2; a.net.c3 = net->c3;
-        a.net.out_scale = net->out_scale; a.net.out_clip = net->out_clip;
+        a.net.out_scale = net->out_scale; a.net.out_clip = net->out_clip; a.net.out_scale_dev = net->out_scale_dev;
     } else {
         a.net.arch = CMCD_ARCH_NONE;
     }

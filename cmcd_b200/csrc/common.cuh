@@ -161,7 +161,10 @@ struct NetView {
     int arch, H, HP, T;
     const float *U1, *U2, *U3, *W2, *W3, *c1, *c2, *c3;
     float out_scale, out_clip;
+    const float* out_scale_dev;   // optional device scalar overriding out_scale
 };
+// the output gate of the network: device scalar if the caller provided one (trainable factor_sn), else the by-value field
+__device__ __forceinline__ float net_out_scale(const NetView& nv) { return nv.out_scale_dev ? __ldg(nv.out_scale_dev) : nv.out_scale; }
 
 struct BridgeArgs {
     int mode, K;

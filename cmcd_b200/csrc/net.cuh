@@ -131,7 +131,9 @@ __device__ __noinline__ void net_fwd(const NetView& nv, const NetSmem& s, int t,
         }
     }
 #pragma unroll
-    for (int m = 0; m < D; ++m) out[m] = nv.out_scale * fminf(fmaxf(o[m], -nv.out_clip), nv.out_clip);
+    const float out_scale = net_out_scale(nv);
+#pragma unroll
+    for (int m = 0; m < D; ++m) out[m] = out_scale * fminf(fmaxf(o[m], -nv.out_clip), nv.out_clip);
 }
 
 }  // namespace cmcd

@@ -192,13 +192,14 @@ __global__ void wide_l2_fin_kernel(const float* __restrict__ part, int S, int N,
 // ---- forward-kernel mean + sample:  mf = z - eps uf - eps NN ; zn = mf + s xi ; fkterm kept per element ----
 // One block per particle.  NN output = out_scale * clamp(sum part3 + c3[t]).  Advances the key chain.
 __global__ void __launch_bounds__(256) wide_fwd_mean_kernel(const float* __restrict__ part3, int S, int N, int d,
-                                                            const float* __restrict__ c3t, float out_scale, float out_clip,
+                                                            const float* __restrict__ c3t, float out_scale_v, const float* __restrict__ out_scale_dev, float out_clip,
                                                             int use_nn, const float* __restrict__ z, const float* __restrict__ sp,
                                                             const float* __restrict__ mu, const float* __restrict__ logdiag,
                                                             const float* __restrict__ betas, const float* __restrict__ epss, int step,
                                                             float clip_t, float clip_q,
                                                             uint32_t* keys, float* zn, float* mf_out, float* traj_row) {
     const int n = blockIdx.x;
+    const float out_scale = out_scale_dev ? __ldg(out_scale_dev) : out_scale_v;
     const float beta = betas[step], eps = epss[step];
     Key k; k.k0 = keys[2 * n]; k.k1 = keys[2 * n + 1];
     Key ka, kn;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(256) wide_fwd_mean_kernel(const float* __restr
 
 // ---- backward-kernel mean + weight update:  mb = zn - eps ub + eps NN ; w += logN(z; mb, s) - logN(zn; mf, s) ----
 __global__ void __launch_bounds__(256) wide_bwd_mean_kernel(const float* __restrict__ part3, int S, int N, int d,
-                                                            const float* __restrict__ c3t, float out_scale, float out_clip,
+                                                            const float* __restrict__ c3t, float out_scale_v, const float* __restrict__ out_scale_dev, float out_clip,
                                                             int use_nn, const float* __restrict__ z, const float* __restrict__ zn,
                                                             const float* __restrict__ mf, const float* __restrict__ spn,
                                                             const float* __restrict__ mu, const float* __restrict__ logdiag,
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(256) wide_bwd_mean_kernel(const float* __restr
                                                             float clip_t, float clip_q, float* w) {
     __shared__ float sh[32];
     const int n = blockIdx.x;
+    const float out_scale = out_scale_dev ? __ldg(out_scale_dev) : out_scale_v;
     const float beta = betas[step], eps = epss[step];
     const float scale = sqrtf(2.0f * eps);
     float acc = 0.f;
@@ -332,7 +334,7 @@ int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
         int S3 = 1;
         if (nn_f) { if (int rc = net_at(z, i, &S3)) return rc; }
         wide_fwd_mean_kernel<<<(unsigned)N, 256, 0, st>>>(part, S3, (int)N, d, has_net ? nv.c3 + (size_t)i * d : nullptr,
-                                                          nv.out_scale, nv.out_clip, nn_f ? 1 : 0, z, sp, a.vd_mean, a.vd_logdiag,
+                                                          nv.out_scale, nv.out_scale_dev, nv.out_clip, nn_f ? 1 : 0, z, sp, a.vd_mean, a.vd_logdiag,
                                                           a.betas, a.eps, i, a.clip_t, a.clip_q, keys, zn, mf,
                                                           a.traj ? a.traj + (size_t)(i + 1) * d * N : nullptr);
         CMCD_CUDA_OK(cudaGetLastError());
@@ -340,7 +342,7 @@ int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
         const int tb = cais ? i + 1 : i;
         if (nn_b) { if (int rc = net_at(zn, tb, &S3)) return rc; }
         wide_bwd_mean_kernel<<<(unsigned)N, 256, 0, st>>>(part, S3, (int)N, d, has_net ? nv.c3 + (size_t)tb * d : nullptr,
-                                                          nv.out_scale, nv.out_clip, nn_b ? 1 : 0, z, zn, mf, sp, a.vd_mean,
+                                                          nv.out_scale, nv.out_scale_dev, nv.out_clip, nn_b ? 1 : 0, z, zn, mf, sp, a.vd_mean,
                                                           a.vd_logdiag, a.betas, a.eps, i, a.clip_t, a.clip_q, w);
         CMCD_CUDA_OK(cudaGetLastError());
         float* t = z; z = zn; zn = t;
@@ -455,10 +457,12 @@ struct WideHalfArgs {
     float *G, *vo, *vm, *r, *gmu_acc, *gls_acc, *g_beta, *g_eps, *g_os;
     int S3, N, d, step, isB, pathwise, use_nn;
     float out_scale, out_clip, clip_t, clip_q;
+    const float* out_scale_dev;
 };
 __global__ void __launch_bounds__(256) wide_half_kernel(const WideHalfArgs a) {
     __shared__ float sh[32];
     const int n = blockIdx.x;
+    const float out_scale = a.out_scale_dev ? __ldg(a.out_scale_dev) : a.out_scale;
     const float beta = a.betas[a.step], eps = a.epss[a.step], omb = 1.0f - beta, ts = 2.0f * eps;
     const float sgn = a.isB ? 1.0f : -1.0f, c = a.c[n], wq = eps * omb;
     float gb = 0.f, ge = 0.f, gos = 0.f, q2 = 0.f;
@@ -468,7 +472,7 @@ __global__ void __launch_bounds__(256) wide_half_kernel(const WideHalfArgs a) {
         if (a.use_nn) {
             o = a.c3t[j];
             for (int s = 0; s < a.S3; ++s) o += a.part3[((size_t)s * a.N + n) * a.d + j];
-            nn = a.out_scale * fminf(fmaxf(o, -a.out_clip), a.out_clip);
+            nn = out_scale * fminf(fmaxf(o, -a.out_clip), a.out_clip);
         }
         const float sg = expf(a.logdiag[j]), ivar = 1.0f / (sg * sg);
         const float x = a.x[e], sx = a.sx[e];
@@ -490,7 +494,7 @@ __global__ void __launch_bounds__(256) wide_half_kernel(const WideHalfArgs a) {
         }
         const float v = sgn * eps * G;
         gos = fmaf(v, fminf(fmaxf(o, -a.out_clip), a.out_clip), gos);
-        a.vo[e] = (a.use_nn && fabsf(o) <= a.out_clip) ? v * a.out_scale : 0.f;
+        a.vo[e] = (a.use_nn && fabsf(o) <= a.out_clip) ? v * out_scale : 0.f;
         a.G[e] = G;
         a.vm[e] = mk_t * G;
         gb += eps * G * dc;
@@ -681,7 +685,7 @@ int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
             h.c = c; h.mu = a.vd_mean; h.logdiag = a.vd_logdiag; h.betas = a.betas; h.epss = a.eps;
             h.G = G; h.vo = vo; h.vm = vm; h.r = r; h.gmu_acc = gmu; h.gls_acc = gls; h.g_beta = gbeta_buf; h.g_eps = geps_buf; h.g_os = gos;
             h.S3 = S3; h.N = (int)N; h.d = d; h.step = i; h.isB = isB; h.pathwise = pathwise; h.use_nn = use_nn;
-            h.out_scale = nv.out_scale; h.out_clip = nv.out_clip; h.clip_t = a.clip_t; h.clip_q = a.clip_q;
+            h.out_scale = nv.out_scale; h.out_scale_dev = nv.out_scale_dev; h.out_clip = nv.out_clip; h.clip_t = a.clip_t; h.clip_q = a.clip_q;
             wide_half_kernel<<<(unsigned)N, 256, 0, st>>>(h);
             CMCD_CUDA_OK(cudaGetLastError());
             if (use_nn) { if (int rc = net_bwd(x, t)) return rc; }

@@ -60,7 +60,8 @@ def _make_net(apply_fun, tabs, nbridges):
     net.arch, net.hidden, net.hidden_pad, net.n_rows = ARCH[apply_fun.arch], apply_fun.hidden, apply_fun.hidden_pad, nbridges + 1
     for k in _NET_KEYS[:-1]:
         setattr(net, k, _lib.ptr(tabs[k]))
-    net.out_scale = float(tabs["out_scale_host"])
+    net.out_scale = 1.0
+    net.out_scale_dev = _lib.ptr(tabs["out_scale"]) if apply_fun.arch == "geffner" else None   # factor_sn stays on the device
     net.out_clip = 1.0e4 if apply_fun.arch == "dds" else float("inf")
     return net
 
@@ -79,7 +80,6 @@ class _Bridge(torch.autograd.Function):
         tabs = None
         if apply_fun is not None:
             tabs = {k: f32(t) for k, t in zip(_NET_KEYS, net_t)}
-            tabs["out_scale_host"] = float(tabs["out_scale"].item()) if apply_fun.arch == "geffner" else 1.0
         negw = torch.empty(n, device=dev, dtype=torch.float32)
         z = torch.empty(n, dim, device=dev, dtype=torch.float32)
         traj = torch.empty((K + 1, dim, n), device=dev, dtype=torch.float32) if need_grad else None

@@ -100,9 +100,16 @@ def _pad_cols(t, hp):
     return t if t.shape[-1] == hp else F.pad(t, (0, hp - t.shape[-1]))
 
 
+_COEFF_CACHE = {}
+
+
 def dds_timestep_coeff(device, dtype=torch.float32):
+    """linspace(0.1, 100, 64) (nn_dds.py:108), cached per device so that build_tables does no host->device copy."""
     import numpy as np
-    return torch.tensor(np.linspace(0.1, 100.0, DDS_CHANNELS).astype(np.float32), dtype=dtype, device=device)
+    key = (str(device), dtype)
+    if key not in _COEFF_CACHE:
+        _COEFF_CACHE[key] = torch.tensor(np.linspace(0.1, 100.0, DDS_CHANNELS).astype(np.float32), dtype=dtype, device=device)
+    return _COEFF_CACHE[key]
 
 
 def build_tables(apply_fun: ApplyFun, sn):

@@ -57,6 +57,8 @@ typedef struct cmcd_net {
     const float* c3;     /* [n_rows][dim] */
     float out_scale;     /* factor_sn (geffner) | 1 (dds) */
     float out_clip;      /* +inf (geffner) | 1e4 (dds) */
+    const float* out_scale_dev; /* optional device scalar: if non-NULL the kernels read out_scale from here instead (keeps the
+                                   trainable factor_sn, nn.py:63, on the device: no host read-back per iteration, CUDA-graph safe) */
 } cmcd_net;
 
 /* Cotangents of every differentiable cmcd_net field (same shapes); NULL members are skipped. */

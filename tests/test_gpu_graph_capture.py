@@ -35,4 +35,4 @@ def test_train_step_replays_from_a_cuda_graph(name):
         torch.cuda.synchronize()
         assert torch.equal(l_s, l_ref) and torch.equal(z_s, z_ref)       # forward is bitwise reproducible
         scale = g_ref.abs().max().item()
-        assert (g_s - g_ref).abs().max().item() <= 1e-5 * scale           # gradient: atomics change the summation order
+        assert (g_s - g_ref).abs().max().item() <= 5e-5 * scale           # gradient: atomics change the fp32 summation order
