@@ -32,7 +32,7 @@ constexpr int BT_T16K = 16384;                // one 64x64 fp32 tile, or one [12
 constexpr int BT_OFF_BF_HI = 0, BT_OFF_BF_LO = BT_T16K, BT_OFF_BD_HI = 2 * BT_T16K, BT_OFF_BD_LO = 3 * BT_T16K;
 constexpr int BT_OFF_TILE = 4 * BT_T16K;      // + wg * 4 * BT_T16K : X_H1, X_H2 (a1), Z_G1, Z_G2 (dp2)
 constexpr int BT_OFF_SMALL = 12 * BT_T16K;    // 196608
-constexpr int BT_FLUSH_STEPS = 2;             // bridge steps between flushes of the TMEM gW2 accumulator
+constexpr int BT_FLUSH_NODES = 4;             // weight-gradient batches (nodes) between flushes of the TMEM gW2 accumulator
 
 struct BtLayout {  // offsets (floats) into one CTA's partial-gradient slice
     int W2rows, c1, c2, c3, U1, W3, os, beta, eps, mu, ls, P;
@@ -310,56 +310,52 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
         const bool active = n_raw < a.N;
         const long long n = active ? n_raw : a.N - 1;   // tail lanes shadow the last particle with zero cotangent
         const float c = active ? -cot_negw[n] : 0.f;    // dL/dw_n
-        float zp[D], z[D], adj[D], abar[D], gmu[D], gls[D], zero[D], hv[D], sp[D], spp[D], r[D];
-        float hz[3] = {0.f, 0.f, 0.f}, hzp[3] = {0.f, 0.f, 0.f};   // many_gmm fast path: Hessian of log p at z / z' (h00, h01, h11)
+        // Node form: K + 1 nodes z_K .. z_0, ONE network evaluation / VJP / weight-gradient batch per node.  In the CAIS
+        // modes NN(z_j, j) is used twice by the reference -- backward-kernel mean of step j-1 (mcd_cais.py:78) and
+        // forward-kernel mean of step j (mcd_cais.py:60) -- and the VJP is linear in the output cotangent, so both uses
+        // share one recompute and one pull-back of  v = eps_{j-1} G_B - eps_j G_F.  Likewise one score / Hessian of the
+        // target per node serves both kernel means (beta differs, the point does not).
+        //   B use (j > 0, step iB = j-1): mean_b = x - eps_B u_B + eps_B nn ; r = (z_{j-1} - mean_b) / (2 eps_B) ; G_B = c r
+        //   F use (j < K, step iF = j)  : mean_f = x - eps_F u_F - eps_F nn ; xs = (z_{j+1} - mean_f) / (2 eps_F) ;
+        //                                 G_F = abar_j (pathwise: carried from node j+1) or -c xs (log-var mode)
+        //   carry_{j-1} = [-c r_j + G_F (1 - eps_F (1-beta_F) mk_q / sigma^2)] + [G_B (1 - eps_B (1-beta_B) mk_q / sigma^2)]
+        //                 + H_p(x) mk_t (beta_F eps_F G_F + beta_B eps_B G_B) + J_x^T v          (node K: first bracket = c grad log p)
+        float x[D], zup[D], zprev[D], zpre2[D], carry[D], rS[D], gmu[D], gls[D], zero[D], hv[D], sx[D];
+        float hx[3] = {0.f, 0.f, 0.f};   // many_gmm fast path: Hessian of log p at x (h00, h01, h11)
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-            zp[j] = a.traj[((size_t)K * D + j) * a.N + n];
-            gmu[j] = 0.f; gls[j] = 0.f; zero[j] = 0.f; adj[j] = 0.f; abar[j] = 0.f; z[j] = 0.f; sp[j] = 0.f; r[j] = 0.f; hv[j] = 0.f;
+            x[j] = a.traj[((size_t)K * D + j) * a.N + n];
+            zprev[j] = a.traj[((size_t)(K - 1) * D + j) * a.N + n];
+            zpre2[j] = (K > 1) ? a.traj[((size_t)(K - 2) * D + j) * a.N + n] : 0.f;
+            gmu[j] = 0.f; gls[j] = 0.f; zero[j] = 0.f; carry[j] = 0.f; rS[j] = 0.f; zup[j] = 0.f; sx[j] = 0.f; hv[j] = 0.f;
         }
-        // terminal: w += log p(z_K)  (mcdboundingmachine.py:178); stop-gradiented in the log-var mode
-        if (fast_gmm) many_gmm_eval_hess(gc, sMu, zp[0], zp[1], spp[0], spp[1], hzp[0], hzp[1], hzp[2]);
-        else target_eval<D, false>(a.tgt, sTp, zp, spp, zero, hv);
-        if (pathwise) {
-#pragma unroll
-            for (int j = 0; j < D; ++j) adj[j] = c * spp[j];
-        }
-        float znext[D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) znext[j] = (K > 0) ? a.traj[((size_t)(K - 1) * D + j) * a.N + n] : 0.f;
         float g1s[4][16];               // act'(pre1) of the current evaluation, chunk-indexed with static indices only
-        float beta = 0.f, eps = 0.f, ts = 1.f, omb = 0.f, gb = 0.f, ge = 0.f, rr = 0.f;
+        float cgb = 0.f, cge = 0.f;     // beta_i / eps_i gradient of step j: B-use part, carried from node j+1 to node j
 
-        if (K > 0) stage_tab(cais ? K : K - 1, (2 * K - 1) & 1);
-        // 2K half-steps, last bridge step first; odd h: backward-kernel mean at z' (net t = tb), even h: forward-kernel mean at z
-        for (int h = 2 * K - 1; h >= 0; --h) {
-            const int i = h >> 1;
-            const bool isB = (h & 1) != 0;
-            if (isB) {
-                beta = __ldg(a.betas + i); eps = __ldg(a.eps + i);
-                ts = 2.0f * eps; omb = 1.0f - beta;
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    z[j] = znext[j];                          // loaded one bridge step ahead (HBM latency off the critical path)
-                    if (i > 0) znext[j] = a.traj[((size_t)(i - 1) * D + j) * a.N + n];
-                }
-                gb = 0.f; ge = 0.f;
+        const int t0 = cais ? 0 : -1;   // table row of node j: t0 + j
+        stage_tab(t0 + K, (t0 + K) & 1);
+        for (int j = K; j >= 0; --j) {
+            const bool hasB = j > 0, hasF = j < K;
+            const int t = t0 + j;
+            const bool use_nn = cais || hasB;
+            // step constants of both uses; an absent use gets eps = 0, c = 0 so that all of its terms vanish
+            const float bB = hasB ? __ldg(a.betas + j - 1) : 0.f, eB = hasB ? __ldg(a.eps + j - 1) : 0.f;
+            const float bF = hasF ? __ldg(a.betas + j) : 0.f, eF = hasF ? __ldg(a.eps + j) : 0.f;
+            const float tsB = hasB ? 2.0f * eB : 1.f, tsF = hasF ? 2.0f * eF : 1.f;
+            const float ombB = 1.0f - bB, ombF = 1.0f - bF;
+            const float cB = hasB ? c : 0.f, cF = hasF ? c : 0.f;
+            const float eFn = nn_f ? eF : 0.f;   // MCD_ULA_sn: the forward-kernel mean has no network term
+            const float* tab = sTab + (t & 1) * (2 * BT_H);
+            if (use_nn) {
+                // table rows of this node were requested one node ago; request the next ones
+                umma::cp_async_wait_all();
+                __syncwarp();
+                if (j > 0 && (cais || j > 1)) stage_tab(t - 1, (t - 1) & 1);
             }
-            const int t = isB ? (cais ? i + 1 : i) : i;
-            const bool use_nn = isB ? nn_b : nn_f;
-            // table rows of this half-step were requested one half-step ago; request the next ones
-            umma::cp_async_wait_all();
-            __syncwarp();
-            const float* tab = sTab + (h & 1) * (2 * BT_H);
-            if (h > 0) stage_tab(isB ? i : (cais ? i : i - 1), (h - 1) & 1);
-            const float sgn = isB ? 1.0f : -1.0f;
-            float x[D], sx[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) { x[j] = isB ? zp[j] : z[j]; sx[j] = isB ? spp[j] : sp[j]; }
 
             // ---------------- layer 1, A operand, a1 staging; GEMM1 ----------------
             if (use_nn) {
-                if (isB && d3_steps >= BT_FLUSH_STEPS) flush_d3();
+                if (d3_steps >= BT_FLUSH_NODES) flush_d3();
                 if (wgrad_pending) { umma::mbar_wait(mb3, par3); par3 ^= 1u; wgrad_pending = false; }   // a1 / dp2 staging tiles are free again
                 const float4* __restrict__ c1v = reinterpret_cast<const float4*>(tab);
 #pragma unroll 1
@@ -414,23 +410,23 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 }
             }
 
-            // ---------------- independent of the network: score-side terms at x ----------------
-            float sq[D], mk_t[D], mk_q[D], u[D], mean[D], dc[D], G[D], nn[D], dx[D], xs[D];
+            // ---------------- independent of the network: target score (+ Hessian) and score-side terms at x ----------------
+            if (fast_gmm) many_gmm_eval_hess(gc, sMu, x[0], x[1], sx[0], sx[1], hx[0], hx[1], hx[2]);   // every HVP at x comes from it
+            else target_eval<D, false>(a.tgt, sTp, x, sx, zero, hv);
+            float sq[D], mk_t[D], mk_q[D], uB[D], uF[D], mB[D], mF[D], dc[D], nn[D], dx[D];
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
-                sq[j] = -(x[j] - mu[j]) * ivar[j];
-                mk_t[j] = (fabsf(sx[j]) <= a.clip_t) ? 1.f : 0.f;
-                mk_q[j] = (fabsf(sq[j]) <= a.clip_q) ? 1.f : 0.f;
-                const float gu = fminf(fmaxf(sx[j], -a.clip_t), a.clip_t);
-                const float gq = fminf(fmaxf(sq[j], -a.clip_q), a.clip_q);
-                dc[j] = gu - gq;                       // d(-u)/dbeta
-                u[j] = -(beta * gu + omb * gq);
-                mean[j] = x[j] - eps * u[j];
-                nn[j] = 0.f; dx[j] = 0.f; xs[j] = 0.f;
-            }
-            if (isB) {   // score at z, used by the forward-kernel half
-                if (fast_gmm) many_gmm_eval_hess(gc, sMu, z[0], z[1], sp[0], sp[1], hz[0], hz[1], hz[2]);   // + Hessian: both HVPs at z come from it
-                else target_eval<D, false>(a.tgt, sTp, z, sp, zero, hv);
+            for (int d = 0; d < D; ++d) {
+                sq[d] = -(x[d] - mu[d]) * ivar[d];
+                mk_t[d] = (fabsf(sx[d]) <= a.clip_t) ? 1.f : 0.f;
+                mk_q[d] = (fabsf(sq[d]) <= a.clip_q) ? 1.f : 0.f;
+                const float gu = fminf(fmaxf(sx[d], -a.clip_t), a.clip_t);
+                const float gq = fminf(fmaxf(sq[d], -a.clip_q), a.clip_q);
+                dc[d] = gu - gq;                       // d(-u)/dbeta
+                uB[d] = -(bB * gu + ombB * gq);
+                uF[d] = -(bF * gu + ombF * gq);
+                mB[d] = x[d] - eB * uB[d];
+                mF[d] = x[d] - eF * uF[d];
+                nn[d] = 0.f; dx[d] = 0.f;
             }
 
             // ---------------- epilogue 1: a2, act'(pre2), raw network output ----------------
@@ -463,9 +459,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                         }
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const int j = cc * 16 + qq * 4 + e;
+                            const int jj = cc * 16 + qq * 4 + e;
 #pragma unroll
-                            for (int m = 0; m < D; ++m) o[m] = fmaf(a2v[e], sW3[j * D + m], o[m]);
+                            for (int m = 0; m < D; ++m) o[m] = fmaf(a2v[e], sW3[jj * D + m], o[m]);
                             a2u[qq * 4 + e] = __float_as_uint(a2v[e]);
                             g2u[qq * 4 + e] = __float_as_uint(g2v[e]);
                         }
@@ -479,22 +475,22 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 for (int m = 0; m < D; ++m) nn[m] = out_scale * fminf(fmaxf(o[m], -nv.out_clip), nv.out_clip);
             }
 
-            // ---------------- kernel mean, residual, cotangent on the mean ----------------
+            // ---------------- kernel means, residuals, cotangents on the two means ----------------
+            float GB[D], GF[D], rB[D], xs[D], vv[D], wq[D];
+            float rr = 0.f, xx = 0.f;
 #pragma unroll
-            for (int j = 0; j < D; ++j) mean[j] = mean[j] + sgn * eps * nn[j];
-            if (isB) {
-                rr = 0.f;
-#pragma unroll
-                for (int j = 0; j < D; ++j) { r[j] = (z[j] - mean[j]) / ts; G[j] = c * r[j]; rr = fmaf(r[j], r[j], rr); }
-            } else {
-                float xx = 0.f;
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    xs[j] = (zp[j] - mean[j]) / ts;     // = xi / s
-                    xx = fmaf(xs[j], xs[j], xx);
-                    G[j] = pathwise ? abar[j] : -c * xs[j];
-                }
-                if (!pathwise) ge -= c * xx;
+            for (int d = 0; d < D; ++d) {
+                const float meanB = mB[d] + eB * nn[d];
+                const float meanF = mF[d] - eFn * nn[d];
+                rB[d] = (zprev[d] - meanB) / tsB;
+                GB[d] = cB * rB[d];
+                rr = fmaf(rB[d], rB[d], rr);
+                xs[d] = (zup[d] - meanF) / tsF;      // = xi / s
+                xx = fmaf(xs[d], xs[d], xx);
+                GF[d] = pathwise ? carry[d] : -cF * xs[d];
+                if (!hasF) GF[d] = 0.f;
+                vv[d] = eB * GB[d] - eFn * GF[d];                      // cotangent on the network output
+                wq[d] = eB * ombB * GB[d] + eF * ombF * GF[d];         // weight of the q-score terms
             }
 
             // ---------------- output-layer VJP, dp2, GEMM2 + WGRAD ----------------
@@ -502,7 +498,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 float vo[D], gos = 0.f;
 #pragma unroll
                 for (int m = 0; m < D; ++m) {
-                    const float v = sgn * eps * G[m];
+                    const float v = vv[m];
                     const float oc = fminf(fmaxf(o[m], -nv.out_clip), nv.out_clip);
                     gos = fmaf(v, oc, gos);
                     vo[m] = (fabsf(o[m]) <= nv.out_clip) ? v * out_scale : 0.f;
@@ -521,10 +517,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                     uint32_t hh[16], ll[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        const int j = cc * 16 + e;
+                        const int jj = cc * 16 + e;
                         float s = 0.f;
 #pragma unroll
-                        for (int m = 0; m < D; ++m) s = fmaf(sW3[j * D + m], vo[m], s);
+                        for (int m = 0; m < D; ++m) s = fmaf(sW3[jj * D + m], vo[m], s);
                         dp2[e] = s * __uint_as_float(g2u[e]);
                         float hi, lo;
                         umma::split_tf32(dp2[e], hi, lo);
@@ -536,11 +532,11 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                     // gc2[t][j] += sum_p dp2 ; gW3[j][m] += sum_p a2 vo[m]   (three butterflies in lock step; D == 2)
                     {
                         static_assert(D == 2, "the interleaved reductions assume d = 2");
-                        float t0[16], t1[16];
+                        float t0v[16], t1v[16];
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) { t0[e] = __uint_as_float(a2u[e]) * vo[0]; t1[e] = __uint_as_float(a2u[e]) * vo[1]; }
+                        for (int e = 0; e < 16; ++e) { t0v[e] = __uint_as_float(a2u[e]) * vo[0]; t1v[e] = __uint_as_float(a2u[e]) * vo[1]; }
                         float s2, s30, s31;
-                        bt_tmem_reduce16x3(tmem_lane + BT_D12, dp2, t0, t1, lane, s2, s30, s31);   // D is free between GEMM1's epilogue and GEMM2
+                        bt_tmem_reduce16x3(tmem_lane + BT_D12, dp2, t0v, t1v, lane, s2, s30, s31);   // D is free between GEMM1's epilogue and GEMM2
                         if (!(lane & 4)) atomicAdd(part + L.c2 + (size_t)t * BT_H + cc * 16 + bt_red_col(lane), s2);
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) { aW3[k4][0] += (k4 == cc) ? s30 : 0.f; aW3[k4][1] += (k4 == cc) ? s31 : 0.f; }
@@ -563,18 +559,37 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 }
                 wgrad_pending = true;
                 d3_fresh = false;
+                ++d3_steps;
             }
 
-            // ---------------- independent of the network: target Hessian-vector product at x ----------------
+            // ---------------- independent of the network: target Hessian-vector product at x, scalar gradients ----------------
             if (pathwise) {
                 float vm[D], dummy[D];
 #pragma unroll
-                for (int j = 0; j < D; ++j) vm[j] = mk_t[j] * G[j];
+                for (int d = 0; d < D; ++d) vm[d] = mk_t[d] * (bB * eB * GB[d] + bF * eF * GF[d]);
                 if (fast_gmm) {
-                    const float h00 = isB ? hzp[0] : hz[0], h01 = isB ? hzp[1] : hz[1], h11 = isB ? hzp[2] : hz[2];
-                    hv[0] = fmaf(h00, vm[0], h01 * vm[1]);
-                    hv[1] = fmaf(h01, vm[0], h11 * vm[1]);
+                    hv[0] = fmaf(hx[0], vm[0], hx[1] * vm[1]);
+                    hv[1] = fmaf(hx[1], vm[0], hx[2] * vm[1]);
                 } else target_eval<D, true>(a.tgt, sTp, x, dummy, vm, hv);
+            }
+            {
+                float gb = cgb, ge = cge;      // step j: B-use part from node j+1, F-use part here
+                float ngb = 0.f, nge = cB * rr;   // step j-1: B-use part, completed at node j-1
+                if (!pathwise) ge -= cF * xx;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    gb += eF * GF[d] * dc[d];
+                    ge += GF[d] * (-uF[d] - (nn_f ? nn[d] : 0.f) + (pathwise ? xs[d] : 0.f));
+                    ngb += eB * GB[d] * dc[d];
+                    nge += GB[d] * (-uB[d] + nn[d]);
+                    gmu[d] += wq[d] * ivar[d] * mk_q[d];
+                    gls[d] += wq[d] * mk_q[d] * (-2.0f * sq[d]);
+                }
+                if (hasF) {
+                    const float gbs = bt_warp_sum(gb), ges = bt_warp_sum(ge);
+                    if (lane == 0) { atomicAdd(part + L.beta + j, gbs); atomicAdd(part + L.eps + j, ges); }
+                }
+                cgb = ngb; cge = nge;
             }
 
             // ---------------- epilogue 2: dp1 = da1 * act'(pre1), dx = U1 dp1, layer-1 gradients ----------------
@@ -611,11 +626,11 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                         for (int d = 0; d < D; ++d) dx[d] = fmaf(sU1[d * BT_H + cc * 16 + e], dp1[e], dx[d]);
                     }
                     {
-                        float t0[16], t1[16];
+                        float t0v[16], t1v[16];
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) { t0[e] = x[0] * dp1[e]; t1[e] = x[1] * dp1[e]; }
+                        for (int e = 0; e < 16; ++e) { t0v[e] = x[0] * dp1[e]; t1v[e] = x[1] * dp1[e]; }
                         float s1, s40, s41;
-                        bt_tmem_reduce16x3(tmem_lane + BT_A_HI, dp1, t0, t1, lane, s1, s40, s41);   // the A region is dead after GEMM2
+                        bt_tmem_reduce16x3(tmem_lane + BT_A_HI, dp1, t0v, t1v, lane, s1, s40, s41);   // the A region is dead after GEMM2
                         if (!(lane & 4)) atomicAdd(part + L.c1 + (size_t)t * BT_H + cc * 16 + bt_red_col(lane), s1);
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) { aU1[k4][0] += (k4 == cc) ? s40 : 0.f; aU1[k4][1] += (k4 == cc) ? s41 : 0.f; }
@@ -624,37 +639,25 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 umma::fence_before();
             }
 
-            // ---------------- combine ----------------
+            // ---------------- combine: cotangent carried to node j-1 (abar_{j-1}); at node 0 it is dL/dz_0 ----------------
             if (pathwise) {
 #pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    const float base = isB ? adj[j] : -c * r[j];
-                    const float res = base + G[j] + eps * (beta * hv[j] - omb * ivar[j] * mk_q[j] * G[j]) + dx[j];
-                    if (isB) abar[j] = res; else adj[j] = res;
+                for (int d = 0; d < D; ++d) {
+                    const float fpart = hasF ? (GF[d] - cF * rS[d]) : c * sx[d];   // node K: terminal w += log p(z_K) (mcdboundingmachine.py:178)
+                    carry[d] = fpart + GB[d] - wq[d] * ivar[d] * mk_q[d] + hv[d] + dx[d];
                 }
             }
-            if (isB) ge += c * rr;
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
-                gb += eps * G[j] * dc[j];
-                ge += G[j] * (-u[j] + sgn * nn[j] + ((!isB && pathwise) ? xs[j] : 0.f));
-                const float wq = eps * omb;
-                gmu[j] += wq * ivar[j] * G[j] * mk_q[j];
-                gls[j] += wq * G[j] * mk_q[j] * (-2.0f * sq[j]);
-            }
-            if (!isB) {
-                const float gbs = bt_warp_sum(gb), ges = bt_warp_sum(ge);
-                if (lane == 0) { atomicAdd(part + L.beta + i, gbs); atomicAdd(part + L.eps + i, ges); }
-#pragma unroll
-                for (int j = 0; j < D; ++j) { zp[j] = z[j]; spp[j] = sp[j]; }
-                hzp[0] = hz[0]; hzp[1] = hz[1]; hzp[2] = hz[2];
-                ++d3_steps;
+            for (int d = 0; d < D; ++d) {
+                rS[d] = rB[d];
+                zup[d] = x[d]; x[d] = zprev[d]; zprev[d] = zpre2[d];   // trajectory rows are loaded two nodes ahead (HBM latency off the critical path)
+                if (j > 2) zpre2[d] = a.traj[((size_t)(j - 3) * D + d) * a.N + n];
             }
         }
-        // initial: z0 = mu + sigma xi0, w0 = -log q(z0) = 0.5|xi0|^2 + sum log(sqrt(2pi) sigma)
+        // initial: z0 = mu + sigma xi0, w0 = -log q(z0) = 0.5|xi0|^2 + sum log(sqrt(2pi) sigma)   (zup = z_0 after the last shift)
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-            if (pathwise) { gmu[j] += adj[j]; gls[j] += adj[j] * (zp[j] - mu[j]); }
+            if (pathwise) { gmu[j] += carry[j]; gls[j] += carry[j] * (zup[j] - mu[j]); }
             gls[j] += c;
             const float m1 = bt_warp_sum(gmu[j]), m2 = bt_warp_sum(gls[j]);
             if (lane == 0) { atomicAdd(part + L.mu + j, m1); atomicAdd(part + L.ls + j, m2); }

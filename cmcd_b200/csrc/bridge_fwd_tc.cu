@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
         Key k = prng_key(a.seeds[n]);
         Key ka;
         split(k, ka, k);
-        float z[D], zn[D], xi[D];
+        float z[D], xi[D];
         normal_vec<D>(ka, xi);
         float w = 0.f;
         {   // z0 = sigma*xi + mu ; w = -log q(z0)   (vardist/diag_gauss.py:26-33,44-62)
@@ -288,76 +288,73 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
             for (int j = 0; j < D; ++j) a.traj[((size_t)0 * D + j) * a.N + n] = z[j];
         }
         float sp[D], dummy[D];
-        float lp = target_eval<D, false>(a.tgt, sTp, z, sp, dummy, dummy);
+        float lp = 0.f;
         ka = split_first(k);    // mcdboundingmachine.py:162
         k = split_second(ka);   // mcd_cais.py:94
         float wm = 0.f;
-        if (K > 0) stage_tab(0, 0);
-        // 2K half-steps, so that one copy of the network code serves both evaluations of a bridge step:
-        //   even h: NN(z, i)   -> forward kernel mean, sample z'      (mcd_cais.py:52-67)
-        //   odd  h: NN(z', tb) -> backward kernel mean, weight update (mcd_cais.py:71-87)
-        float mf[D], mb[D], nnv[D], skipacc[D];
-        float beta = 0.f, eps = 0.f, scale = 0.f;
-        for (int h = 0; h < 2 * K; ++h) {
-            const int i = h >> 1;
-            const bool bwd_half = (h & 1) != 0;
-            const int t = bwd_half ? (cais ? i + 1 : i) : i;
-            const bool use_nn = bwd_half ? nn_b : nn_f;
-            // table rows of this half-step were requested one half-step ago; request the next ones
-            umma::cp_async_wait_all();
-            __syncwarp();
-            cx.tab = sTab + (h & 1) * (2 * TC_H);
-            if (h + 1 < 2 * K) stage_tab(bwd_half ? i + 1 : (cais ? i + 1 : i), (h + 1) & 1);
-            float xin[D];
+        // K + 1 nodes z_0 .. z_K, ONE network evaluation per node: in the CAIS modes NN(z_j, j) serves both the
+        // backward-kernel mean of step j-1 (mcd_cais.py:78, called there as NN(z', i + 1)) and the forward-kernel mean of
+        // step j (mcd_cais.py:60) -- same point, same time index, so the reference's 2K evaluations are K + 1 distinct
+        // ones.  MCD_ULA_sn (mcd_over_orig.py:45): NN(z_j, j - 1), backward-kernel mean only.
+        const int t0 = cais ? 0 : -1;
+        if (K > 0 && nn_b) stage_tab(0, 0);   // first evaluation: node 0 (CAIS) or node 1 (ULA_sn), t = 0 either way
+        float x[D], mf[D], nnv[D], skipacc[D];
 #pragma unroll
-            for (int j = 0; j < D; ++j) xin[j] = bwd_half ? zn[j] : z[j];
-            if (use_nn) tc_net_issue<D, ACT>(cx, t, xin, skipacc);
-            // ---- work that does not depend on the network output overlaps the MMA batch ----
-            if (!bwd_half) {
-                beta = __ldg(a.betas + i); eps = __ldg(a.eps + i);
-                scale = sqrtf(2.0f * eps);
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    const float sq = -((z[j] - mu[j]) / sig[j]) / sig[j];
-                    const float gu = fminf(fmaxf(sp[j], -a.clip_t), a.clip_t);
-                    const float gq = fminf(fmaxf(sq, -a.clip_q), a.clip_q);
-                    const float uf = -(beta * gu + (1.0f - beta) * gq);
-                    mf[j] = z[j] - eps * uf;
-                }
-                step_keys_and_normal<D>(k, xi);   // split + Gaussian + key advance as two interleaved threefry batches
-            } else {
-                if (fast_gmm) { float d0, d1; lp = many_gmm_eval<false>(gc, sMu, zn[0], zn[1], sp[0], sp[1], 0.f, 0.f, d0, d1); }
-                else lp = target_eval<D, false>(a.tgt, sTp, zn, sp, dummy, dummy);
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    const float sq = -((zn[j] - mu[j]) / sig[j]) / sig[j];
-                    const float gu = fminf(fmaxf(sp[j], -a.clip_t), a.clip_t);
-                    const float gq = fminf(fmaxf(sq, -a.clip_q), a.clip_q);
-                    const float ub = -(beta * gu + (1.0f - beta) * gq);
-                    mb[j] = zn[j] - eps * ub;
-                }
+        for (int j = 0; j < D; ++j) { x[j] = z[j]; mf[j] = 0.f; }
+        float beta = 0.f, eps = 0.f, scale = 1.f;
+        for (int nd = 0; nd <= K; ++nd) {
+            const int t = t0 + nd;
+            const bool use_nn = nn_b && (cais || nd > 0) && K > 0;
+            if (use_nn) {
+                // table rows of this node were requested one node ago; request the next ones
+                umma::cp_async_wait_all();
+                __syncwarp();
+                cx.tab = sTab + (t & 1) * (2 * TC_H);
+                if (nd < K) stage_tab(t + 1, (t + 1) & 1);
+                tc_net_issue<D, ACT>(cx, t, x, skipacc);
             }
+            // ---- work that does not depend on the network output overlaps the MMA batch ----
+            if (fast_gmm) { float d0, d1; lp = many_gmm_eval<false>(gc, sMu, x[0], x[1], sp[0], sp[1], 0.f, 0.f, d0, d1); }
+            else lp = target_eval<D, false>(a.tgt, sTp, x, sp, dummy, dummy);
+            float gu[D], gq[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const float sq = -((x[j] - mu[j]) / sig[j]) / sig[j];
+                gu[j] = fminf(fmaxf(sp[j], -a.clip_t), a.clip_t);
+                gq[j] = fminf(fmaxf(sq, -a.clip_q), a.clip_q);
+            }
+            if (nd < K) step_keys_and_normal<D>(k, xi);   // split + Gaussian + key advance of step nd (two interleaved threefry batches)
 #pragma unroll
             for (int j = 0; j < D; ++j) nnv[j] = 0.f;
-            if (use_nn) tc_net_finish<D, ACT>(cx, t, xin, skipacc, nnv);
-            if (!bwd_half) {
+            if (use_nn) tc_net_finish<D, ACT>(cx, t, x, skipacc, nnv);
+            if (nd > 0) {   // backward kernel of step nd - 1 (beta, eps, scale, mf still hold that step's values), weight update
+                float mb[D];
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
-                    mf[j] = mf[j] - eps * nnv[j];
-                    zn[j] = mf[j] + scale * xi[j];
+                    const float ub = -(beta * gu[j] + (1.0f - beta) * gq[j]);
+                    mb[j] = x[j] - eps * ub;
+                    mb[j] = mb[j] + eps * nnv[j];
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < D; ++j) mb[j] = mb[j] + eps * nnv[j];
                 const float lognorm = logf(2.5066282746310002f * scale);
-                const float fk = gauss_logprob_tc<D>(zn, mf, scale, lognorm);
+                const float fk = gauss_logprob_tc<D>(x, mf, scale, lognorm);
                 const float bk = gauss_logprob_tc<D>(z, mb, scale, lognorm);
                 wm += bk - fk;
 #pragma unroll
-                for (int j = 0; j < D; ++j) z[j] = zn[j];
+                for (int j = 0; j < D; ++j) z[j] = x[j];
                 if (a.traj && active) {
 #pragma unroll
-                    for (int j = 0; j < D; ++j) a.traj[((size_t)(i + 1) * D + j) * a.N + n] = z[j];
+                    for (int j = 0; j < D; ++j) a.traj[((size_t)nd * D + j) * a.N + n] = z[j];
+                }
+            }
+            if (nd < K) {   // forward kernel of step nd: mean, sample z_{nd+1}
+                beta = __ldg(a.betas + nd); eps = __ldg(a.eps + nd);
+                scale = sqrtf(2.0f * eps);
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const float uf = -(beta * gu[j] + (1.0f - beta) * gq[j]);
+                    mf[j] = z[j] - eps * uf;
+                    if (nn_f) mf[j] = mf[j] - eps * nnv[j];
+                    x[j] = mf[j] + scale * xi[j];
                 }
             }
         }
