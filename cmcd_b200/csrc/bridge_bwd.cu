@@ -378,130 +378,107 @@ __global__ void __launch_bounds__(BPB, 1) bridge_bwd_kernel(const BridgeArgs a, 
         const long long n = tile * BPB + tid;
         const bool active = n < a.N;
         const float c = active ? -cot_negw[n] : 0.f;   // dL/dw_n
-        float zp[D], z[D], adj[D], gmu[D], gls[D], zero[D], hv[D], sp[D], spp[D];
+        // Node form: K + 1 nodes z_K .. z_0, one target score, one network recompute and ONE network pull-back per node.
+        // In the CAIS modes NN(z_j, j) serves the backward-kernel mean of step j-1 and the forward-kernel mean of step j
+        // (mcd_cais.py:78 / :60: same point, same time index) and the VJP is linear in the output cotangent, so both uses
+        // share  v = eps_{j-1} G_mb - eps_j G_mf ; the two Hessian-vector products at z_j merge the same way.
+        //   carry_{j-1} = [-c r_j + G_mf (1 - eps_F (1-beta_F) mk_q / sigma^2)] + [G_mb (1 - eps_B (1-beta_B) mk_q / sigma^2)]
+        //                 + H_p(z_j) mk_t (beta_F eps_F G_mf + beta_B eps_B G_mb) + J_x^T v     (node K: first bracket = c grad log p)
+        float x[D], zup[D], zprev[D], carry[D], rS[D], gmu[D], gls[D], zero[D], hv[D], sx[D];
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-            zp[j] = active ? a.traj[((size_t)K * D + j) * a.N + n] : 0.f;
-            gmu[j] = 0.f; gls[j] = 0.f; zero[j] = 0.f; adj[j] = 0.f;
+            x[j] = active ? a.traj[((size_t)K * D + j) * a.N + n] : 0.f;
+            gmu[j] = 0.f; gls[j] = 0.f; zero[j] = 0.f; carry[j] = 0.f; rS[j] = 0.f; zup[j] = 0.f; hv[j] = 0.f;
         }
-        // terminal: w += log p(z_K)  (mcdboundingmachine.py:178); stop-gradiented in the log-var mode
-        target_eval<D, false>(a.tgt, sTp, zp, spp, zero, hv);
-        if (pathwise) {
+        float cgb = 0.f, cge = 0.f;     // beta_i / eps_i cotangent of step j: backward-kernel part, carried from node j+1 to node j
+        const int t0 = cais ? 0 : -1;   // table row of node j: t0 + j  (MCD_ULA_sn: NN(z_j, j-1), mcd_over_orig.py:45)
+        for (int j = K; j >= 0; --j) {
+            const bool hasB = j > 0, hasF = j < K;
+            const int t = t0 + j;
+            const bool use_nn = has_net && K > 0 && (cais || (nn_b && hasB));
+            // step constants of both uses; an absent use gets eps = 0, c = 0 so that all of its terms vanish
+            const float bB = hasB ? __ldg(a.betas + j - 1) : 0.f, eB = hasB ? __ldg(a.eps + j - 1) : 0.f;
+            const float bF = hasF ? __ldg(a.betas + j) : 0.f, eF = hasF ? __ldg(a.eps + j) : 0.f;
+            const float tsB = hasB ? 2.0f * eB : 1.f, tsF = hasF ? 2.0f * eF : 1.f;
+            const float ombB = 1.0f - bB, ombF = 1.0f - bF;
+            const float cB = hasB ? c : 0.f, cF = hasF ? c : 0.f;
+            const float eFn = nn_f ? eF : 0.f;
 #pragma unroll
-            for (int j = 0; j < D; ++j) adj[j] = c * spp[j];
-        }
-        for (int i = K - 1; i >= 0; --i) {
-            const float beta = __ldg(a.betas + i), eps = __ldg(a.eps + i);
-            const float ts = 2.0f * eps, omb = 1.0f - beta;
+            for (int d = 0; d < D; ++d) zprev[d] = (active && hasB) ? a.traj[((size_t)(j - 1) * D + d) * a.N + n] : 0.f;
+            target_eval<D, false>(a.tgt, sTp, x, sx, zero, hv);
+            float sq[D], mk_t[D], mk_q[D], uB[D], uF[D], dc[D], nn[D], o[D], dx[D];
 #pragma unroll
-            for (int j = 0; j < D; ++j) z[j] = active ? a.traj[((size_t)i * D + j) * a.N + n] : 0.f;
-            // ---------------- backward kernel mean at z' ----------------
-            float sqp[D], mkp_t[D], mkp_q[D], ub[D], mb[D], nnb[D], ob[D], Gmb[D], dxb[D], dcb[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                sqp[j] = -(zp[j] - mu[j]) * ivar[j];
-                mkp_t[j] = (fabsf(spp[j]) <= a.clip_t) ? 1.f : 0.f;
-                mkp_q[j] = (fabsf(sqp[j]) <= a.clip_q) ? 1.f : 0.f;
-                const float gu = fminf(fmaxf(spp[j], -a.clip_t), a.clip_t);
-                const float gq = fminf(fmaxf(sqp[j], -a.clip_q), a.clip_q);
-                dcb[j] = gu - gq;                       // d(-ub)/dbeta
-                ub[j] = -(beta * gu + omb * gq);
-                mb[j] = zp[j] - eps * ub[j];
-                nnb[j] = 0.f; dxb[j] = 0.f; ob[j] = 0.f;
+            for (int d = 0; d < D; ++d) {
+                sq[d] = -(x[d] - mu[d]) * ivar[d];
+                mk_t[d] = (fabsf(sx[d]) <= a.clip_t) ? 1.f : 0.f;
+                mk_q[d] = (fabsf(sq[d]) <= a.clip_q) ? 1.f : 0.f;
+                const float gu = fminf(fmaxf(sx[d], -a.clip_t), a.clip_t);
+                const float gq = fminf(fmaxf(sq[d], -a.clip_q), a.clip_q);
+                dc[d] = gu - gq;                       // d(-u)/dbeta
+                uB[d] = -(bB * gu + ombB * gq);
+                uF[d] = -(bF * gu + ombF * gq);
+                nn[d] = 0.f; dx[d] = 0.f; o[d] = 0.f;
             }
-            const int tb = cais ? i + 1 : i;
-            if (nn_b) {
-                net_fwd_store<D, ACT, HPT, JC, RS>(nv, ns, tb, zp, ob, S1 + tid, S2 + tid, S3 + tid);
+            if (use_nn) {
+                net_fwd_store<D, ACT, HPT, JC, RS>(nv, ns, t, x, o, S1 + tid, S2 + tid, S3 + tid);
 #pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    nnb[j] = out_scale * fminf(fmaxf(ob[j], -nv.out_clip), nv.out_clip);
-                    mb[j] = mb[j] + eps * nnb[j];
-                }
+                for (int d = 0; d < D; ++d) nn[d] = out_scale * fminf(fmaxf(o[d], -nv.out_clip), nv.out_clip);
             }
-            float r[D], rr = 0.f;
+            float GB[D], GF[D], rB[D], xs[D], vv[D], wq[D];
+            float rr = 0.f, xx = 0.f;
 #pragma unroll
-            for (int j = 0; j < D; ++j) { r[j] = (z[j] - mb[j]) / ts; Gmb[j] = c * r[j]; rr = fmaf(r[j], r[j], rr); }
-            if (nn_b) {
-                float vB[D];
-#pragma unroll
-                for (int j = 0; j < D; ++j) vB[j] = eps * Gmb[j];
-                net_bwd<D, ACT, HPT, JC, BPB>(nv, ns, tb, zp, ob, vB, dxb, S1, S2, S3, sX, sVo, part, L);
+            for (int d = 0; d < D; ++d) {
+                const float meanB = (x[d] - eB * uB[d]) + eB * nn[d];
+                const float meanF = (x[d] - eF * uF[d]) - eFn * nn[d];
+                rB[d] = (zprev[d] - meanB) / tsB;
+                GB[d] = cB * rB[d];
+                rr = fmaf(rB[d], rB[d], rr);
+                xs[d] = (zup[d] - meanF) / tsF;      // = xi / s
+                xx = fmaf(xs[d], xs[d], xx);
+                GF[d] = pathwise ? carry[d] : -cF * xs[d];
+                if (!hasF) GF[d] = 0.f;
+                vv[d] = eB * GB[d] - eFn * GF[d];                      // cotangent on the network output
+                wq[d] = eB * ombB * GB[d] + eF * ombF * GF[d];         // weight of the q-score terms
             }
-            float abar[D];
-            if (pathwise) {
-                float vm[D];
-#pragma unroll
-                for (int j = 0; j < D; ++j) vm[j] = mkp_t[j] * Gmb[j];
-                float dummy[D];
-                target_eval<D, true>(a.tgt, sTp, zp, dummy, vm, hv);
-#pragma unroll
-                for (int j = 0; j < D; ++j)
-                    abar[j] = adj[j] + Gmb[j] + eps * (beta * hv[j] - omb * ivar[j] * mkp_q[j] * Gmb[j]) + dxb[j];
-            }
-            // ---------------- forward kernel mean at z ----------------
-            float sq[D], mk_t[D], mk_q[D], uf[D], mf[D], nnf[D], of[D], Gmf[D], dxf[D], dcf[D];
-            target_eval<D, false>(a.tgt, sTp, z, sp, zero, hv);
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                sq[j] = -(z[j] - mu[j]) * ivar[j];
-                mk_t[j] = (fabsf(sp[j]) <= a.clip_t) ? 1.f : 0.f;
-                mk_q[j] = (fabsf(sq[j]) <= a.clip_q) ? 1.f : 0.f;
-                const float gu = fminf(fmaxf(sp[j], -a.clip_t), a.clip_t);
-                const float gq = fminf(fmaxf(sq[j], -a.clip_q), a.clip_q);
-                dcf[j] = gu - gq;
-                uf[j] = -(beta * gu + omb * gq);
-                mf[j] = z[j] - eps * uf[j];
-                nnf[j] = 0.f; dxf[j] = 0.f; of[j] = 0.f;
-            }
-            if (nn_f) {
-                net_fwd_store<D, ACT, HPT, JC, RS>(nv, ns, i, z, of, S1 + tid, S2 + tid, S3 + tid);
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    nnf[j] = out_scale * fminf(fmaxf(of[j], -nv.out_clip), nv.out_clip);
-                    mf[j] = mf[j] - eps * nnf[j];
-                }
-            }
-            float xs[D], xx = 0.f;   // xs = (z' - m_f)/s^2 = xi/s
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                xs[j] = (zp[j] - mf[j]) / ts;
-                xx = fmaf(xs[j], xs[j], xx);
-                Gmf[j] = pathwise ? abar[j] : -c * xs[j];
-            }
-            if (nn_f) {
-                float vA[D];
-#pragma unroll
-                for (int j = 0; j < D; ++j) vA[j] = -eps * Gmf[j];
-                net_bwd<D, ACT, HPT, JC, BPB>(nv, ns, i, z, of, vA, dxf, S1, S2, S3, sX, sVo, part, L);
-            }
+            if (use_nn) net_bwd<D, ACT, HPT, JC, BPB>(nv, ns, t, x, o, vv, dx, S1, S2, S3, sX, sVo, part, L);
             if (pathwise) {
                 float vm[D], dummy[D];
 #pragma unroll
-                for (int j = 0; j < D; ++j) vm[j] = mk_t[j] * Gmf[j];
-                target_eval<D, true>(a.tgt, sTp, z, dummy, vm, hv);
+                for (int d = 0; d < D; ++d) vm[d] = mk_t[d] * (bB * eB * GB[d] + bF * eF * GF[d]);
+                target_eval<D, true>(a.tgt, sTp, x, dummy, vm, hv);
 #pragma unroll
-                for (int j = 0; j < D; ++j)
-                    adj[j] = -c * r[j] + Gmf[j] + eps * (beta * hv[j] - omb * ivar[j] * mk_q[j] * Gmf[j]) + dxf[j];
+                for (int d = 0; d < D; ++d) {
+                    const float fpart = hasF ? (GF[d] - cF * rS[d]) : c * sx[d];   // node K: terminal w += log p(z_K) (mcdboundingmachine.py:178)
+                    carry[d] = fpart + GB[d] - wq[d] * ivar[d] * mk_q[d] + hv[d] + dx[d];
+                }
             }
             // ---------------- per-step scalar cotangents ----------------
-            float gb = 0.f, ge = pathwise ? c * rr : c * (rr - xx);
+            {
+                float gb = cgb, ge = cge;         // step j: backward-kernel part from node j+1, forward-kernel part here
+                float ngb = 0.f, nge = cB * rr;   // step j-1: backward-kernel part, completed at node j-1
+                if (!pathwise) ge -= cF * xx;
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
-                gb += eps * (Gmb[j] * dcb[j] + Gmf[j] * dcf[j]);
-                ge += Gmb[j] * (-ub[j] + nnb[j]) + Gmf[j] * (-uf[j] - nnf[j] + (pathwise ? xs[j] : 0.f));
-                const float wq = eps * omb;
-                gmu[j] += wq * ivar[j] * (Gmf[j] * mk_q[j] + Gmb[j] * mkp_q[j]);
-                gls[j] += wq * (Gmf[j] * mk_q[j] * (-2.0f * sq[j]) + Gmb[j] * mkp_q[j] * (-2.0f * sqp[j]));
+                for (int d = 0; d < D; ++d) {
+                    gb += eF * GF[d] * dc[d];
+                    ge += GF[d] * (-uF[d] - (nn_f ? nn[d] : 0.f) + (pathwise ? xs[d] : 0.f));
+                    ngb += eB * GB[d] * dc[d];
+                    nge += GB[d] * (-uB[d] + nn[d]);
+                    gmu[d] += wq[d] * ivar[d] * mk_q[d];
+                    gls[d] += wq[d] * mk_q[d] * (-2.0f * sq[d]);
+                }
+                if (hasF) {
+                    gb = warp_sum_f(gb); ge = warp_sum_f(ge);
+                    if ((tid & 31) == 0) { atomicAdd(part + L.beta + j, gb); atomicAdd(part + L.eps + j, ge); }
+                }
+                cgb = ngb; cge = nge;
             }
-            gb = warp_sum_f(gb); ge = warp_sum_f(ge);
-            if ((tid & 31) == 0) { atomicAdd(part + L.beta + i, gb); atomicAdd(part + L.eps + i, ge); }
 #pragma unroll
-            for (int j = 0; j < D; ++j) { zp[j] = z[j]; spp[j] = sp[j]; }
+            for (int d = 0; d < D; ++d) { rS[d] = rB[d]; zup[d] = x[d]; x[d] = zprev[d]; }
         }
-        // initial: z0 = mu + sigma xi0, w0 = -log q(z0) = 0.5|xi0|^2 + sum log(sqrt(2pi) sigma)
+        // initial: z0 = mu + sigma xi0, w0 = -log q(z0) = 0.5|xi0|^2 + sum log(sqrt(2pi) sigma)   (zup = z_0 after the last shift)
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-            if (pathwise) { gmu[j] += adj[j]; gls[j] += adj[j] * (zp[j] - mu[j]); }
+            if (pathwise) { gmu[j] += carry[j]; gls[j] += carry[j] * (zup[j] - mu[j]); }
             gls[j] += c;
             const float m1 = warp_sum_f(gmu[j]), m2 = warp_sum_f(gls[j]);
             if ((tid & 31) == 0) { atomicAdd(part + L.mu + j, m1); atomicAdd(part + L.ls + j, m2); }

@@ -76,9 +76,16 @@ __global__ void __launch_bounds__(FWD_PB, (D <= 4 ? 4 : 2)) bridge_fwd_kernel(co
             ka = split_first(k);    // mcdboundingmachine.py:162
             k = split_second(ka);   // mcd_cais.py:94
             float wm = 0.f;
+            // One network evaluation per trajectory point: in the CAIS modes NN(z', i + 1) of step i's backward-kernel mean
+            // (mcd_cais.py:78) is the same evaluation as NN(z, i + 1) of step i + 1's forward-kernel mean (mcd_cais.py:60),
+            // so it is carried over in nnv: K + 1 evaluations instead of the reference's 2K.
+            float nnv[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) nnv[j] = 0.f;
+            if (nn_f) net_fwd<D, ACT, HPT, JC, FWD_PB>(nv, ns, 0, z, nnv, a1col);
             for (int i = 0; i < K; ++i) {
                 const float beta = __ldg(a.betas + i), eps = __ldg(a.eps + i);
-                float mf[D], mb[D], nnv[D];
+                float mf[D], mb[D];
                 // forward kernel mean
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
@@ -88,8 +95,7 @@ __global__ void __launch_bounds__(FWD_PB, (D <= 4 ? 4 : 2)) bridge_fwd_kernel(co
                     const float uf = -(beta * gu + (1.0f - beta) * gq);
                     mf[j] = z[j] - eps * uf;
                 }
-                if (nn_f) {
-                    net_fwd<D, ACT, HPT, JC, FWD_PB>(nv, ns, i, z, nnv, a1col);
+                if (nn_f) {   // nnv = NN(z_i, i), evaluated at the end of the previous step (or before the loop for i = 0)
 #pragma unroll
                     for (int j = 0; j < D; ++j) mf[j] = mf[j] - eps * nnv[j];
                 }

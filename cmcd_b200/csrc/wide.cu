@@ -330,9 +330,12 @@ int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
         return 0;
     };
     if (int rc = target_at(z)) return rc;
+    // One network evaluation per trajectory point: in the CAIS modes NN(z', i + 1) of step i's backward-kernel mean
+    // (mcd_cais.py:78) is the evaluation step i + 1's forward-kernel mean needs (mcd_cais.py:60); its layer-3 partials stay
+    // in `part` between wide_bwd_mean_kernel and the next wide_fwd_mean_kernel, so K + 1 evaluations serve 2K uses.
+    int S3 = 1;
+    if (nn_f && K > 0) { if (int rc = net_at(z, 0, &S3)) return rc; }
     for (int i = 0; i < K; ++i) {
-        int S3 = 1;
-        if (nn_f) { if (int rc = net_at(z, i, &S3)) return rc; }
         wide_fwd_mean_kernel<<<(unsigned)N, 256, 0, st>>>(part, S3, (int)N, d, has_net ? nv.c3 + (size_t)i * d : nullptr,
                                                           nv.out_scale, nv.out_scale_dev, nv.out_clip, nn_f ? 1 : 0, z, sp, a.vd_mean, a.vd_logdiag,
                                                           a.betas, a.eps, i, a.clip_t, a.clip_q, keys, zn, mf,
@@ -443,29 +446,30 @@ __global__ void wide_gather_kernel(const float* __restrict__ traj_row, int N, in
     out[i] = traj_row[(size_t)j * N + n];
 }
 
-// adj = scale[n] * sp   (terminal term w += log p(z_K))
-__global__ void wide_scale_rows_kernel(const float* __restrict__ c, const float* __restrict__ v, int N, int d, float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N * d) out[i] = c[i / d] * v[i];
-}
-
-// One half-step (isB: backward-kernel mean at x = z', else forward-kernel mean at x = z): network output from the
-// layer-3 partials, kernel mean, residual, cotangent G on the mean, output-layer cotangent vo, HVP input vm, and the
-// per-step scalar / vd cotangents.  One block per particle.
-struct WideHalfArgs {
-    const float *part3, *c3t, *x, *sx, *z, *zp, *abar, *c, *mu, *logdiag, *betas, *epss;
-    float *G, *vo, *vm, *r, *gmu_acc, *gls_acc, *g_beta, *g_eps, *g_os;
-    int S3, N, d, step, isB, pathwise, use_nn;
+// One node of the reverse pass (x = z_j): network output from the layer-3 partials, BOTH kernel means that use this
+// point -- backward-kernel mean of step j-1 (B use, needs z_{j-1}) and forward-kernel mean of step j (F use, needs
+// z_{j+1}) -- their residuals and cotangents G_B, G_F, the combined output-layer cotangent vo = out_scale (eps_B G_B -
+// eps_F G_F) (NN(z_j, j) is one evaluation used twice by the reference, mcd_cais.py:60,78, and its VJP is linear), the
+// combined HVP input vm = mk_t (beta_B eps_B G_B + beta_F eps_F G_F), everything of the carried cotangent that needs no
+// matrix product (base), and the per-step scalar / vd cotangents.  Same algebra as bridge_bwd.cu.  One block per particle.
+struct WideNodeArgs {
+    const float *part3, *c3t, *x, *sx, *zprev, *zup, *carry, *c, *mu, *logdiag, *betas, *epss;
+    float *base, *vo, *vm, *r, *gmu_acc, *gls_acc, *g_beta, *g_eps, *g_os;
+    int S3, N, d, j, K, pathwise, use_nn, nn_f;
     float out_scale, out_clip, clip_t, clip_q;
     const float* out_scale_dev;
 };
-__global__ void __launch_bounds__(256) wide_half_kernel(const WideHalfArgs a) {
+__global__ void __launch_bounds__(256) wide_node_kernel(const WideNodeArgs a) {
     __shared__ float sh[32];
     const int n = blockIdx.x;
+    const bool hasB = a.j > 0, hasF = a.j < a.K;
     const float out_scale = a.out_scale_dev ? __ldg(a.out_scale_dev) : a.out_scale;
-    const float beta = a.betas[a.step], eps = a.epss[a.step], omb = 1.0f - beta, ts = 2.0f * eps;
-    const float sgn = a.isB ? 1.0f : -1.0f, c = a.c[n], wq = eps * omb;
-    float gb = 0.f, ge = 0.f, gos = 0.f, q2 = 0.f;
+    const float bB = hasB ? a.betas[a.j - 1] : 0.f, eB = hasB ? a.epss[a.j - 1] : 0.f;
+    const float bF = hasF ? a.betas[a.j] : 0.f, eF = hasF ? a.epss[a.j] : 0.f;
+    const float ombB = 1.0f - bB, ombF = 1.0f - bF, tsB = hasB ? 2.0f * eB : 1.f, tsF = hasF ? 2.0f * eF : 1.f;
+    const float eFn = a.nn_f ? eF : 0.f;
+    const float c = a.c[n];
+    float gbB = 0.f, geB = 0.f, gbF = 0.f, geF = 0.f, gos = 0.f, rr = 0.f, xx = 0.f;
     for (int j = threadIdx.x; j < a.d; j += blockDim.x) {
         const size_t e = (size_t)n * a.d + j;
         float o = 0.f, nn = 0.f;
@@ -479,65 +483,71 @@ __global__ void __launch_bounds__(256) wide_half_kernel(const WideHalfArgs a) {
         const float sq = -(x - a.mu[j]) * ivar;
         const float mk_t = (fabsf(sx) <= a.clip_t) ? 1.f : 0.f, mk_q = (fabsf(sq) <= a.clip_q) ? 1.f : 0.f;
         const float gu = fminf(fmaxf(sx, -a.clip_t), a.clip_t), gq = fminf(fmaxf(sq, -a.clip_q), a.clip_q);
-        const float dc = gu - gq, u = -(beta * gu + omb * gq);
-        const float mean = (x - eps * u) + sgn * eps * nn;
-        float G, xs = 0.f;
-        if (a.isB) {
-            const float r = (a.z[e] - mean) / ts;
-            a.r[e] = r;
-            G = c * r;
-            q2 = fmaf(r, r, q2);
-        } else {
-            xs = (a.zp[e] - mean) / ts;
-            q2 = fmaf(xs, xs, q2);
-            G = a.pathwise ? a.abar[e] : -c * xs;
+        const float dc = gu - gq;
+        const float uB = -(bB * gu + ombB * gq), uF = -(bF * gu + ombF * gq);
+        float rB = 0.f, GB = 0.f, xs = 0.f, GF = 0.f;
+        if (hasB) {
+            const float meanB = (x - eB * uB) + eB * nn;
+            rB = (a.zprev[e] - meanB) / tsB;
+            GB = c * rB;
         }
-        const float v = sgn * eps * G;
+        if (hasF) {
+            const float meanF = (x - eF * uF) - eFn * nn;
+            xs = (a.zup[e] - meanF) / tsF;
+            GF = a.pathwise ? a.carry[e] : -c * xs;
+        }
+        rr = fmaf(rB, rB, rr);
+        xx = fmaf(xs, xs, xx);
+        const float v = eB * GB - eFn * GF;
         gos = fmaf(v, fminf(fmaxf(o, -a.out_clip), a.out_clip), gos);
         a.vo[e] = (a.use_nn && fabsf(o) <= a.out_clip) ? v * out_scale : 0.f;
-        a.G[e] = G;
-        a.vm[e] = mk_t * G;
-        gb += eps * G * dc;
-        ge += G * (-u + sgn * nn + ((!a.isB && a.pathwise) ? xs : 0.f));
-        a.gmu_acc[e] += wq * ivar * G * mk_q;
-        a.gls_acc[e] += wq * G * mk_q * (-2.0f * sq);
+        a.vm[e] = mk_t * (bB * eB * GB + bF * eF * GF);
+        const float wq = eB * ombB * GB + eF * ombF * GF;
+        a.gmu_acc[e] += wq * ivar * mk_q;
+        a.gls_acc[e] += wq * mk_q * (-2.0f * sq);
+        if (a.pathwise) {
+            const float fpart = hasF ? (GF - c * a.r[e]) : c * sx;   // node K: terminal w += log p(z_K) (mcdboundingmachine.py:178)
+            a.base[e] = fpart + GB - wq * ivar * mk_q;
+        }
+        a.r[e] = rB;
+        gbF += eF * GF * dc;
+        geF += GF * (-uF - (a.nn_f ? nn : 0.f) + (a.pathwise ? xs : 0.f));
+        gbB += eB * GB * dc;
+        geB += GB * (-uB + nn);
     }
-    gb = block_sum(gb, sh);
-    ge = block_sum(ge, sh);
+    gbB = block_sum(gbB, sh); geB = block_sum(geB, sh);
+    gbF = block_sum(gbF, sh); geF = block_sum(geF, sh);
     gos = block_sum(gos, sh);
-    q2 = block_sum(q2, sh);
+    rr = block_sum(rr, sh); xx = block_sum(xx, sh);
     if (threadIdx.x == 0) {
-        if (a.isB) ge += c * q2;                       // c |r|^2
-        else if (!a.pathwise) ge -= c * q2;            // -c |xi/s|^2
-        atomicAdd(a.g_beta + a.step, gb);
-        atomicAdd(a.g_eps + a.step, ge);
+        if (hasF) {
+            atomicAdd(a.g_beta + a.j, gbF);
+            atomicAdd(a.g_eps + a.j, a.pathwise ? geF : geF - c * xx);   // -c |xi/s|^2 in the log-var mode
+        }
+        if (hasB) {
+            atomicAdd(a.g_beta + a.j - 1, gbB);
+            atomicAdd(a.g_eps + a.j - 1, geB + c * rr);                  // c |r|^2
+        }
         if (a.use_nn && a.g_os) atomicAdd(a.g_os, gos);
     }
 }
 
-// res = base + G + eps (beta H vm - (1-beta) ivar mk_q G) + dx,  H vm = -K^-1 vm - a exp(x) vm,  dx = dA1[:, :d] + dp1 U1^T
-// (already summed into dxnet); base = adj (isB) or -c r.
-struct WideCombineArgs {
-    const float *kpart, *x, *G, *vm, *dxnet, *base_adj, *r, *c, *mu, *logdiag, *betas, *epss;
+// carry_{j-1} = base + H vm + dx,  H vm = -K^-1 vm - a exp(x) vm  (vm already carries the beta eps weights of both uses),
+// dx = dA1[:, :d] + dp1 U1^T (already summed into dxnet).
+struct WideNodeCombineArgs {
+    const float *kpart, *x, *base, *vm, *dxnet;
     float* out;
-    int S, N, d, step, isB, use_nn;
-    float area, clip_q;
+    int S, N, d, use_nn;
+    float area;
 };
-__global__ void wide_combine_kernel(const WideCombineArgs a) {
+__global__ void wide_node_combine_kernel(const WideNodeCombineArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N * a.d) return;
     const int n = i / a.d, j = i % a.d;
-    const float beta = a.betas[a.step], eps = a.epss[a.step], omb = 1.0f - beta;
     float kd = 0.f;
     for (int s = 0; s < a.S; ++s) kd += a.kpart[((size_t)s * a.N + n) * a.d + j];
-    const float x = a.x[i];
-    const float hv = -kd - a.area * expf(x) * a.vm[i];
-    const float sg = expf(a.logdiag[j]), ivar = 1.0f / (sg * sg);
-    const float sq = -(x - a.mu[j]) * ivar;
-    const float mk_q = (fabsf(sq) <= a.clip_q) ? 1.f : 0.f;
-    const float G = a.G[i];
-    const float base = a.isB ? a.base_adj[i] : -a.c[n] * a.r[i];
-    a.out[i] = base + G + eps * (beta * hv - omb * ivar * mk_q * G) + (a.use_nn ? a.dxnet[i] : 0.f);
+    const float hv = -kd - a.area * expf(a.x[i]) * a.vm[i];
+    a.out[i] = a.base[i] + hv + (a.use_nn ? a.dxnet[i] : 0.f);
 }
 
 // g_mu[j] = sum_n (gmu_acc + adj), g_ls[j] = sum_n (gls_acc + adj (z0 - mu) + c)
@@ -664,46 +674,44 @@ int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
     };
 
     wide_neg_kernel<<<ew((int)N), 256, 0, st>>>(cot_negw, (int)N, c);
-    wide_gather_kernel<<<ew(nd), 256, 0, st>>>(a.traj + (size_t)K * d * N, (int)N, d, zp);
+    // three rotating trajectory rows: zup = z_{j+1}, x = z_j, zprev = z_{j-1}; `abar` holds the carried cotangent, `G` the base
+    float *zup = zp, *x = z, *zprev = spp;
+    wide_gather_kernel<<<ew(nd), 256, 0, st>>>(a.traj + (size_t)K * d * N, (int)N, d, x);
     CMCD_CUDA_OK(cudaGetLastError());
-    if (int rc = target_at(zp, spp)) return rc;
-    if (pathwise) wide_scale_rows_kernel<<<ew(nd), 256, 0, st>>>(c, spp, (int)N, d, adj);
-    for (int i = K - 1; i >= 0; --i) {
-        wide_gather_kernel<<<ew(nd), 256, 0, st>>>(a.traj + (size_t)i * d * N, (int)N, d, z);
-        CMCD_CUDA_OK(cudaGetLastError());
-        for (int half = 1; half >= 0; --half) {
-            const bool isB = half == 1;
-            const float* x = isB ? zp : z;
-            const float* sx = isB ? spp : sp;
-            const int t = isB ? (cais ? i + 1 : i) : i;
-            const bool use_nn = isB ? nn_b : nn_f;
-            int S3 = 1;
-            if (!isB) { if (int rc = target_at(z, sp)) return rc; }
-            if (use_nn) { if (int rc = net_fwd_store(x, t, &S3)) return rc; }
-            WideHalfArgs h{};
-            h.part3 = part; h.c3t = has_net ? nv.c3 + (size_t)t * d : nullptr; h.x = x; h.sx = sx; h.z = z; h.zp = zp; h.abar = abar;
-            h.c = c; h.mu = a.vd_mean; h.logdiag = a.vd_logdiag; h.betas = a.betas; h.epss = a.eps;
-            h.G = G; h.vo = vo; h.vm = vm; h.r = r; h.gmu_acc = gmu; h.gls_acc = gls; h.g_beta = gbeta_buf; h.g_eps = geps_buf; h.g_os = gos;
-            h.S3 = S3; h.N = (int)N; h.d = d; h.step = i; h.isB = isB; h.pathwise = pathwise; h.use_nn = use_nn;
-            h.out_scale = nv.out_scale; h.out_scale_dev = nv.out_scale_dev; h.out_clip = nv.out_clip; h.clip_t = a.clip_t; h.clip_q = a.clip_q;
-            wide_half_kernel<<<(unsigned)N, 256, 0, st>>>(h);
+    CMCD_CUDA_OK(cudaMemsetAsync(r, 0, (size_t)nd * sizeof(float), st));
+    CMCD_CUDA_OK(cudaMemsetAsync(abar, 0, (size_t)nd * sizeof(float), st));
+    const int t0 = cais ? 0 : -1;   // table row of node j: t0 + j  (MCD_ULA_sn: NN(z_j, j-1), mcd_over_orig.py:45)
+    for (int j = K; j >= 0; --j) {
+        const bool hasB = j > 0;
+        const int t = t0 + j;
+        const bool use_nn = has_net && K > 0 && (cais || (nn_b && hasB));
+        if (hasB) {
+            wide_gather_kernel<<<ew(nd), 256, 0, st>>>(a.traj + (size_t)(j - 1) * d * N, (int)N, d, zprev);
             CMCD_CUDA_OK(cudaGetLastError());
-            if (use_nn) { if (int rc = net_bwd(x, t)) return rc; }
-            if (pathwise) {
-                if (int rc = run_gemm(st, vm, d, 0.f, tg->lgcp_kinv, d, (int)N, d, d, num_sms, part, &S)) return rc;
-                WideCombineArgs cb{};
-                cb.kpart = part; cb.x = x; cb.G = G; cb.vm = vm; cb.dxnet = dx; cb.base_adj = adj; cb.r = r; cb.c = c;
-                cb.mu = a.vd_mean; cb.logdiag = a.vd_logdiag; cb.betas = a.betas; cb.epss = a.eps;
-                cb.out = isB ? abar : adj;
-                cb.S = S; cb.N = (int)N; cb.d = d; cb.step = i; cb.isB = isB; cb.use_nn = use_nn;
-                cb.area = tg->lgcp_bin_area; cb.clip_q = a.clip_q;
-                wide_combine_kernel<<<ew(nd), 256, 0, st>>>(cb);
-                CMCD_CUDA_OK(cudaGetLastError());
-            }
         }
-        float* tmp = zp; zp = z; z = tmp;
-        tmp = spp; spp = sp; sp = tmp;
+        int S3 = 1;
+        if (int rc = target_at(x, sp)) return rc;
+        if (use_nn) { if (int rc = net_fwd_store(x, t, &S3)) return rc; }
+        WideNodeArgs h{};
+        h.part3 = part; h.c3t = use_nn ? nv.c3 + (size_t)t * d : nullptr; h.x = x; h.sx = sp; h.zprev = zprev; h.zup = zup; h.carry = abar;
+        h.c = c; h.mu = a.vd_mean; h.logdiag = a.vd_logdiag; h.betas = a.betas; h.epss = a.eps;
+        h.base = G; h.vo = vo; h.vm = vm; h.r = r; h.gmu_acc = gmu; h.gls_acc = gls; h.g_beta = gbeta_buf; h.g_eps = geps_buf; h.g_os = gos;
+        h.S3 = S3; h.N = (int)N; h.d = d; h.j = j; h.K = K; h.pathwise = pathwise; h.use_nn = use_nn; h.nn_f = nn_f;
+        h.out_scale = nv.out_scale; h.out_scale_dev = nv.out_scale_dev; h.out_clip = nv.out_clip; h.clip_t = a.clip_t; h.clip_q = a.clip_q;
+        wide_node_kernel<<<(unsigned)N, 256, 0, st>>>(h);
+        CMCD_CUDA_OK(cudaGetLastError());
+        if (use_nn) { if (int rc = net_bwd(x, t)) return rc; }
+        if (pathwise) {
+            if (int rc = run_gemm(st, vm, d, 0.f, tg->lgcp_kinv, d, (int)N, d, d, num_sms, part, &S)) return rc;
+            WideNodeCombineArgs cb{};
+            cb.kpart = part; cb.x = x; cb.base = G; cb.vm = vm; cb.dxnet = dx; cb.out = abar;
+            cb.S = S; cb.N = (int)N; cb.d = d; cb.use_nn = use_nn; cb.area = tg->lgcp_bin_area;
+            wide_node_combine_kernel<<<ew(nd), 256, 0, st>>>(cb);
+            CMCD_CUDA_OK(cudaGetLastError());
+        }
+        if (hasB) { float* tmp = zup; zup = x; x = zprev; zprev = tmp; }
     }
+    adj = abar; zp = x;   // after node 0: carried cotangent = dL/dz_0, x = z_0
     wide_vd_final_kernel<<<ew(d), 256, 0, st>>>(gmu, gls, adj, zp, c, a.vd_mean, (int)N, d, pathwise ? 1 : 0, g_vd_mean, g_vd_logdiag);
     CMCD_CUDA_OK(cudaGetLastError());
     return 0;
