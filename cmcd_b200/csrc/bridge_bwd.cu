@@ -101,7 +101,7 @@ __device__ CMCD_NETB_INL void net_fwd_store(const NetView& nv, const NetSmem& s,
             }
             acc[jj] = p;
         }
-#pragma unroll 2
+#pragma unroll (inner_unroll(JC))
         for (int i = 0; i < HP; ++i) {
             const float h = S1c[i * RS];
             const float4* __restrict__ w = reinterpret_cast<const float4*>(s.W2 + (size_t)i * HP + j0);
@@ -260,7 +260,7 @@ __device__ CMCD_NETB_INL void net_bwd(const NetView& nv, const NetSmem& s, int t
             float dreg[JC];
 #pragma unroll
             for (int jj = 0; jj < JC; ++jj) dreg[jj] = S3c[(j0 + jj) * RS];
-#pragma unroll 2
+#pragma unroll (inner_unroll(JC))
             for (int i = 0; i < HP; ++i) {
                 const float4* __restrict__ w = reinterpret_cast<const float4*>(s.W2 + (size_t)i * HP + j0);
                 float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
@@ -552,6 +552,9 @@ static int launch_bwd_d(const BridgeArgs& a, cudaStream_t st, int num_sms, const
         return launch_bwd_t<D, ACT_GELU, 0, 8, 64>(a, st, num_sms, cot, out, ws, ws_bytes);
     }
     if (HP == 64) return launch_bwd_t<D, ACT_SOFTPLUS, 64, 64, BIG>(a, st, num_sms, cot, out, ws, ws_bytes);
+    // README.md:30,34 (geffner, emb_dim 130, d = 2 -> hidden_pad 136): two register chunks of 68 output units per layer-2 pass
+    // (17 broadcast LDS.128 per 68 FMAs instead of 2 per 8 with the generic JC = 8 chunks)
+    if (HP == 136) return launch_bwd_t<D, ACT_SOFTPLUS, 136, 68, 64>(a, st, num_sms, cot, out, ws, ws_bytes);
     if (HP < 64) return launch_bwd_t<D, ACT_SOFTPLUS, 0, 8, BIG>(a, st, num_sms, cot, out, ws, ws_bytes);
     return launch_bwd_t<D, ACT_SOFTPLUS, 0, 8, 64>(a, st, num_sms, cot, out, ws, ws_bytes);
 }

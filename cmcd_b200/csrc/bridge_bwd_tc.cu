@@ -79,26 +79,27 @@ __device__ __forceinline__ void bt_pick(float a, float b, uint32_t m, float& sen
 // shuffle butterfly.  `scratch` = 48 free TMEM columns of this warp's lane quarter.  Result: the total of element
 // bt_red_col(lane) in every lane (lanes differing in bit 2 hold the same element).
 __device__ __forceinline__ int bt_red_col(int lane) { return ((lane >> 4) & 1) * 8 + (lane & 3) * 2 + ((lane >> 3) & 1); }
-__device__ __forceinline__ void bt_tmem_reduce16x3(uint32_t scratch, const float (&v0)[16], const float (&v1)[16], const float (&v2)[16],
-                                                   int lane, float& r0, float& r1, float& r2) {
+__device__ __forceinline__ void bt_tmem_reduce16x3(uint32_t sc0, uint32_t sc1, uint32_t sc2, const float (&v0)[16], const float (&v1)[16],
+                                                   const float (&v2)[16], int lane, float& r0, float& r1, float& r2) {
+    const uint32_t sc[3] = {sc0, sc1, sc2};
     {
         uint32_t w[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) w[e] = __float_as_uint(v0[e]);
-        umma::tmem_st16(scratch, w);
+        umma::tmem_st16(sc0, w);
 #pragma unroll
         for (int e = 0; e < 16; ++e) w[e] = __float_as_uint(v1[e]);
-        umma::tmem_st16(scratch + 16, w);
+        umma::tmem_st16(sc1, w);
 #pragma unroll
         for (int e = 0; e < 16; ++e) w[e] = __float_as_uint(v2[e]);
-        umma::tmem_st16(scratch + 32, w);
+        umma::tmem_st16(sc2, w);
     }
     umma::tmem_st_wait();
     uint32_t a[3][8], b[3][8];
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
-        umma::tmem_ld_16x256b_x2(scratch + 16 * s, a[s]);
-        umma::tmem_ld_16x256b_x2(scratch + 16 * s + (16u << 16), b[s]);
+        umma::tmem_ld_16x256b_x2(sc[s], a[s]);
+        umma::tmem_ld_16x256b_x2(sc[s] + (16u << 16), b[s]);
     }
     umma::tmem_ld_wait();
     float p[3][4];
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
     };
 
     const long long ntiles = (a.N + BT_PB - 1) / BT_PB;
-    for (long long tile = (long long)blockIdx.x * 2 + wg; tile < ntiles; tile += 2LL * gridDim.x) {
+    for (long long tile = (long long)wg * gridDim.x + blockIdx.x; tile < ntiles; tile += 2LL * gridDim.x) {   // few tiles: one per CTA
         const long long n_raw = tile * BT_PB + q;
         const bool active = n_raw < a.N;
         const long long n = active ? n_raw : a.N - 1;   // tail lanes shadow the last particle with zero cotangent
@@ -536,7 +537,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 #pragma unroll
                         for (int e = 0; e < 16; ++e) { t0v[e] = __uint_as_float(a2u[e]) * vo[0]; t1v[e] = __uint_as_float(a2u[e]) * vo[1]; }
                         float s2, s30, s31;
-                        bt_tmem_reduce16x3(tmem_lane + BT_D12, dp2, t0v, t1v, lane, s2, s30, s31);   // D is free between GEMM1's epilogue and GEMM2
+                        bt_tmem_reduce16x3(tmem_lane + BT_D12, tmem_lane + BT_D12 + 16, tmem_lane + BT_D12 + 32, dp2, t0v, t1v, lane, s2, s30, s31);   // D is free between GEMM1's epilogue and GEMM2
                         if (!(lane & 4)) atomicAdd(part + L.c2 + (size_t)t * BT_H + cc * 16 + bt_red_col(lane), s2);
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) { aW3[k4][0] += (k4 == cc) ? s30 : 0.f; aW3[k4][1] += (k4 == cc) ? s31 : 0.f; }
@@ -630,7 +631,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 #pragma unroll
                         for (int e = 0; e < 16; ++e) { t0v[e] = x[0] * dp1[e]; t1v[e] = x[1] * dp1[e]; }
                         float s1, s40, s41;
-                        bt_tmem_reduce16x3(tmem_lane + BT_A_HI, dp1, t0v, t1v, lane, s1, s40, s41);   // the A region is dead after GEMM2
+                        bt_tmem_reduce16x3(tmem_lane + BT_A_HI, tmem_lane + BT_A_HI + 16, tmem_lane + BT_A_HI + 32, dp1, t0v, t1v, lane, s1, s40, s41);   // the A region is dead after GEMM2
                         if (!(lane & 4)) atomicAdd(part + L.c1 + (size_t)t * BT_H + cc * 16 + bt_red_col(lane), s1);
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) { aU1[k4][0] += (k4 == cc) ? s40 : 0.f; aU1[k4][1] += (k4 == cc) ? s41 : 0.f; }
@@ -726,15 +727,15 @@ int launch_bridge_bwd_tc(const BridgeArgs& a, int D, cudaStream_t st, int num_sm
     if (D != 2) { set_error("bridge_bwd_tc: dim=%d has no instantiation", D); return 2; }
     const BtLayout L = bt_make_layout(D, a.K);
     const long long ntiles = (a.N + BT_PB - 1) / BT_PB;
-    long long grid = (ntiles + 1) / 2;
+    long long grid = ntiles;   // up to num_sms tiles: one tile per CTA (the second tile slot idles, the tile has the SM to itself)
     if (grid > num_sms) grid = num_sms;
     if (grid < 1) grid = 1;
     const size_t need = (size_t)grid * L.P * sizeof(float);
     if (!ws || ws_bytes < need) { set_error("bridge_bwd_tc: workspace too small (%zu < %zu)", ws_bytes, need); return 2; }
+    CMCD_CUDA_OK(cudaMemsetAsync(ws, 0, need, st));
     const size_t smem = bt_smem_bytes(D);
     auto kern = bridge_bwd_tc_kernel<2>;
     CMCD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CMCD_CUDA_OK(cudaMemsetAsync(ws, 0, need, st));
     kern<<<(unsigned)grid, BT_THREADS, smem, st>>>(a, cot_negw, (float*)ws, L);
     CMCD_CUDA_OK(cudaGetLastError());
     BtOut o{};

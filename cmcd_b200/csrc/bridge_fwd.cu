@@ -24,7 +24,7 @@ __device__ __forceinline__ float gauss_logprob(const float (&x)[D], const float 
 }
 
 template <int D, int ACT, int HPT, int JC>
-__global__ void __launch_bounds__(FWD_PB, (D <= 4 ? 4 : 2)) bridge_fwd_kernel(const BridgeArgs a) {
+__global__ void __launch_bounds__(FWD_PB, (HPT > 64 ? 1 : (D <= 4 ? 4 : 2))) bridge_fwd_kernel(const BridgeArgs a) {   // wide nets: shared memory allows one CTA per SM anyway
     extern __shared__ float4 smem4[];
     float* sm = reinterpret_cast<float*>(smem4);
     const int tid = threadIdx.x;
@@ -168,6 +168,7 @@ static int launch_fwd_d(const BridgeArgs& a, cudaStream_t st, int num_sms) {
         return launch_fwd_t<D, ACT_GELU, 0, 8>(a, st, num_sms);
     }
     if (a.net.HP == 64) return launch_fwd_t<D, ACT_SOFTPLUS, 64, 64>(a, st, num_sms);
+    if (a.net.HP == 136) return launch_fwd_t<D, ACT_SOFTPLUS, 136, 68>(a, st, num_sms);   // README.md:30,34 (emb_dim 130, d = 2)
     return launch_fwd_t<D, ACT_SOFTPLUS, 0, 8>(a, st, num_sms);
 }
 

@@ -8,7 +8,15 @@
 #pragma once
 #include "common.cuh"
 
+// Unroll depth of the layer-2 inner loops (one private LDS + JC/4 broadcast LDS.128 + JC FMAs per iteration): the narrow
+// register chunks (JC = 8) need several iterations in flight to cover the shared-memory latency when few warps are resident.
+#ifndef CMCD_UNROLL_NARROW
+#define CMCD_UNROLL_NARROW 2
+#endif
+
 namespace cmcd {
+
+__host__ __device__ constexpr int inner_unroll(int jc) { return jc >= 32 ? 2 : CMCD_UNROLL_NARROW; }
 
 // Shared-memory carve-up of the network weights (all HP-padded).
 struct NetSmem {
@@ -88,7 +96,7 @@ __device__ __noinline__ void net_fwd(const NetView& nv, const NetSmem& s, int t,
             }
             acc[jj] = p;
         }
-#pragma unroll 2
+#pragma unroll (inner_unroll(JC))
         for (int i = 0; i < HP; ++i) {
             const float h = a1col[i * PBS];
             const float4* __restrict__ w = reinterpret_cast<const float4*>(s.W2 + (size_t)i * HP + j0);
@@ -130,7 +138,6 @@ __device__ __noinline__ void net_fwd(const NetView& nv, const NetSmem& s, int t,
             }
         }
     }
-#pragma unroll
     const float out_scale = net_out_scale(nv);
 #pragma unroll
     for (int m = 0; m < D; ++m) out[m] = out_scale * fminf(fmaxf(o[m], -nv.out_clip), nv.out_clip);

@@ -1,7 +1,7 @@
 """Device time of one train iteration (forward bridge + adjoint + table chain) and of one sampling pass for every
 BASELINE.json / README config at its README size, CUDA events, median of `reps` (dev tool).
 
-    python tools/config_times.py [reps] > gpurun_out/config_times.json
+    python tools/config_times.py [reps] [config ...] > gpurun_out/config_times.json
 """
 import json
 import os
@@ -18,7 +18,7 @@ from cmcd_b200 import model_handler as PH
 from cmcd_b200 import variationaldist as PV
 
 # README sizes (the parity tests run some of these at reduced N / K)
-SIZES = {"A_gmm": (300, 8), "B_funnel": (300, 8), "C_manygmm_dds": (2000, 256), "Cvar_manygmm": (2000, 256),
+SIZES = {"A_gmm": (300, 8), "B_funnel": (300, 8), "C_manygmm_dds": (2000, 256), "C_manygmm_dds_16k": (16384, 256), "Cvar_manygmm": (2000, 256),
          "Ckl_manygmm_geffner": (2000, 256), "D_lgcp": (20, 8), "ULAsn_funnel": (300, 8)}
 
 
@@ -40,9 +40,12 @@ def timed(fn, reps):
 
 def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 11
+    only = sys.argv[2:]   # optional: config names to run
     rows = []
     for name, (N, K) in SIZES.items():
-        c = dict(CONFIGS[name])
+        if only and name not in only:
+            continue
+        c = dict(CONFIGS[name.replace("_16k", "")])
         out = PH.load_model(c["model"], device="cuda")
         target, dim = out[0], out[1]
         pf, unf, fixed = PM.initialize(dim, vdparams=PV.initialize(dim, c["sigma"], device="cuda"), nbridges=K, eps=c["eps"],
