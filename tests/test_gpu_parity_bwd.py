@@ -44,6 +44,7 @@ def _grads(name, N=None, K=None):
     fn = PM.compute_bound_var if var else PM.compute_bound
     gl = PM.grad_and_loss(lambda *a: fn(*a, **kw))
     gp, (lp_, zp_) = gl(torch.from_numpy(seeds), pf_p, unf_p, fixed_p, target)
+    c["l32"] = l32   # fp32 oracle loss per particle: its distance to l64 bounds what an fp32 implementation can match
     return c, unf, g32, g64, gp.cpu(), l64, lp_.cpu()
 
 
@@ -59,6 +60,24 @@ def test_gradient_parity(name):
     # frozen (params_notrain) entries get exactly zero gradient, like stop_gradient (mcdboundingmachine.py:142)
     pt, pn = unf(gp)
     assert all((l == 0).all() for l in tree_leaves(pn))
+
+
+@pytest.mark.parametrize("name,K", [("C_manygmm_dds_small", 2), ("ULAsn_gmm_dds", 1), ("ULAsn_gmm_dds", 2), ("A_gmm", 1), ("A_gmm", 2),
+                                    ("Cvar_manygmm", 1), ("Cvar_manygmm", 2), ("ULAsn_funnel", 1), ("D_lgcp", 1), ("D_lgcp", 2),
+                                    ("D_lgcp_ula", 1)])
+def test_short_bridges_every_path(name, K):
+    """Node-form boundaries: with K = 1 and 2 every trajectory point is a first or last node (a single use of the network
+    evaluation), on the tensor-core, FP32-FMA and lgcp wide paths and for both time-index conventions (CAIS: NN(z_j, j);
+    MCD_ULA_sn: NN(z_j, j-1), mcd_over_orig.py:45)."""
+    c, unf, g32, g64, gp, l64, lp_ = _grads(name, K=K)
+    assert torch.isfinite(gp).all()
+    fin = torch.isfinite(l64)
+    assert (torch.isfinite(lp_) == fin).all()
+    rel = lambda l: ((l.double() - l64)[fin].abs() / l64[fin].abs().clamp(min=1)).max().item()
+    assert rel(lp_) < max(1e-4, 2 * rel(c["l32"])), (rel(lp_), rel(c["l32"]))
+    e_kernel = _leaf_errs(gp, g64, unf)
+    e_oracle32 = _leaf_errs(g32, g64, unf)
+    assert (e_kernel <= np.maximum(GRAD_TOL, 2 * e_oracle32)).all(), (name, K, e_kernel, e_oracle32)
 
 
 @pytest.mark.parametrize("name", ["D_lgcp", "D_lgcp_ula"])
