@@ -85,11 +85,15 @@ def create_optimizer(step_size, b1=0.9, b2=0.999, eps=1e-8, trainable=None):
 
 # ------------------------------------------------------------------ loops
 def run(info, lr, iters, params_flat, unflatten, params_fixed, log_prob_model, grad_and_loss, trainable, rng_key_gen,
-        extra=True, log_prefix="", target_samples=None, use_ema=False, log_fn=None, sync_every=1):
+        extra=True, log_prefix="", target_samples=None, use_ema=False, log_fn=None, sync_every=1, graph=False):
     """opt.py:67-164.  Returns (losses, params_flat, ema_params); on divergence prints "Diverged" and returns
     (params_flat, ema_params) exactly like the reference (:122-124).  ``sync_every``: how often the device-side
     divergence flag is read back (1 = the reference's per-iteration check; the update itself is always guarded on
-    the device, so a larger value never applies a NaN gradient)."""
+    the device, so a larger value never applies a NaN gradient).  ``graph=True`` captures one iteration's device work
+    (table chain, forward bridge, adjoint, loss mean, divergence flag) into a CUDA graph once and replays it: per
+    iteration the host then issues three launches (seeds, graph, optimizer) instead of the ~100 small ones of the
+    O(K) table chain -- the launch-bound README configs (nbridges = 8, N = 300) run several times faster.  Same
+    arithmetic, same order; every C-ABI entry point is enqueue-only, which is what makes the capture legal."""
     optimizer = create_optimizer(lr, trainable=trainable)
     params_flat = params_flat.detach().clone()
     opt_state = optimizer.init(params_flat)
@@ -98,24 +102,52 @@ def run(info, lr, iters, params_flat, unflatten, params_fixed, log_prob_model, g
     n_particles = int(getattr(info, "N"))
     losses = []
     flag = torch.zeros((), dtype=torch.int32, device=params_flat.device)
-    for i in range(iters):
-        rng_key, rng_key_gen = split_key(rng_key_gen)
-        seeds = randint_seeds(rng_key, n_particles, 1, 10**6, device=params_flat.device)
+
+    def device_work(seeds):
+        """One iteration up to (not including) the optimizer update; writes the sticky divergence flag in place."""
         grad, (loss, z) = grad_and_loss(seeds, params_flat, unflatten, params_fixed, log_prob_model)
         ema_loss = None
         if use_ema:
             _, (ema_loss, _z_ema) = grad_and_loss(seeds, ema_params, unflatten, params_fixed, log_prob_model)
+            ema_loss = ema_loss.mean()
         mean_loss = loss.mean()
-        flag = torch.logical_or(flag.bool(), torch.isnan(mean_loss)).to(torch.int32)   # sticky divergence flag (device)
+        flag.copy_(torch.logical_or(flag.bool(), torch.isnan(mean_loss)).to(torch.int32))   # sticky divergence flag (device)
+        return grad, mean_loss, ema_loss
+
+    cuda_graph = None
+    if graph and iters > 0:
+        static_seeds = torch.zeros(n_particles, dtype=torch.int32, device=params_flat.device)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):      # warm-up on a side stream (workspaces, lazily created handles), flag restored after
+            static_seeds.fill_(1)
+            for _ in range(2):
+                device_work(static_seeds)
+            flag.zero_()
+        torch.cuda.current_stream().wait_stream(side)
+        cuda_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cuda_graph):
+            g_grad, g_mean, g_ema = device_work(static_seeds)
+        flag.zero_()                       # the capture pass does not execute, but keep the invariant explicit
+
+    for i in range(iters):
+        rng_key, rng_key_gen = split_key(rng_key_gen)
+        seeds = randint_seeds(rng_key, n_particles, 1, 10**6, device=params_flat.device)
+        if cuda_graph is not None:
+            static_seeds.copy_(seeds)
+            cuda_graph.replay()
+            grad, mean_loss, ema_loss = g_grad, g_mean, g_ema
+        else:
+            grad, mean_loss, ema_loss = device_work(seeds)
         if (i + 1) % max(sync_every, 1) == 0 and flag.item():
             print("Diverged")
             return params_flat, ema_params
         optimizer.step(params_flat, grad, opt_state, lo, hi, ema_params, 0.001, skip_flag=flag)
         if i % max(iters // 1000, 1) == 0:
-            losses.append(mean_loss)      # stays on the device; converted once at the end
+            losses.append(mean_loss.clone() if cuda_graph is not None else mean_loss)   # stays on the device; converted once at the end
             if log_fn is not None:
                 log_fn({f"{log_prefix}/loss": mean_loss, f"{log_prefix}/grad": grad.mean(), "train_step": i,
-                        f"{log_prefix}/ema_loss": None if ema_loss is None else ema_loss.mean()})
+                        f"{log_prefix}/ema_loss": ema_loss})
     if flag.item():
         print("Diverged")
         return params_flat, ema_params

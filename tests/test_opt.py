@@ -100,6 +100,30 @@ def test_run_matches_oracle_loop():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["A_gmm", "B_funnel", "C_manygmm_dds_small"])
+def test_run_graph_mode_matches_eager(name):
+    """opt.run(graph=True) replays one captured iteration (table chain + forward bridge + adjoint + loss mean + flag):
+    same parameters and losses as the eager loop after 6 iterations (gradient atomics change the fp32 summation order)."""
+    from cmcd_b200 import mcdboundingmachine as PM
+    from cmcd_b200 import opt as PO
+
+    class Info:
+        pass
+    c, lp, dim, pf, unf, fixed = oracle_problem(name, torch.float32)
+    Info.N = c["N"]
+    _, target, _, pf_p, unf_p, fixed_p = product_problem(name, pf)
+    kw = dict(eps_schedule=c["eps_schedule"], grad_clipping=c["clip"])
+    gl = PM.grad_and_loss(lambda *a: PM.compute_bound(*a, **kw))
+    out = {}
+    for mode in (False, True):
+        losses, p, ema = PO.run(Info, 1e-3, 6, pf_p, unf_p, fixed_p, target, gl, c["trainable"], PO.prng_key(5), use_ema=True, graph=mode)
+        out[mode] = (np.asarray(losses), p.cpu().numpy(), ema.cpu().numpy())
+    np.testing.assert_allclose(out[True][0], out[False][0], rtol=1e-5)
+    np.testing.assert_allclose(out[True][1], out[False][1], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(out[True][2], out[False][2], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.gpu
 def test_sample_and_final_losses():
     from cmcd_b200 import mcdboundingmachine as PM
     from cmcd_b200 import opt as PO
