@@ -335,13 +335,17 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 
         const int t0 = cais ? 0 : -1;   // table row of node j: t0 + j
         stage_tab(t0 + K, (t0 + K) & 1);
+        float bnext = __ldg(a.betas + K - 1), enext = __ldg(a.eps + K - 1);   // step K-1 (B use of node K)
+        float bprev = 0.f, eprev = 0.f;                                       // step j (F use): none at node K
         for (int j = K; j >= 0; --j) {
             const bool hasB = j > 0, hasF = j < K;
             const int t = t0 + j;
             const bool use_nn = cais || hasB;
             // step constants of both uses; an absent use gets eps = 0, c = 0 so that all of its terms vanish
-            const float bB = hasB ? __ldg(a.betas + j - 1) : 0.f, eB = hasB ? __ldg(a.eps + j - 1) : 0.f;
-            const float bF = hasF ? __ldg(a.betas + j) : 0.f, eF = hasF ? __ldg(a.eps + j) : 0.f;
+            // step constants: (beta, eps) of step j-1 were requested one node ago; those of step j are last node's B-use values
+            const float bB = hasB ? bnext : 0.f, eB = hasB ? enext : 0.f;
+            const float bF = bprev, eF = eprev;
+            if (j > 1) { bnext = __ldg(a.betas + j - 2); enext = __ldg(a.eps + j - 2); }
             const float tsB = hasB ? 2.0f * eB : 1.f, tsF = hasF ? 2.0f * eF : 1.f;
             const float ombB = 1.0f - bB, ombF = 1.0f - bF;
             const float cB = hasB ? c : 0.f, cF = hasF ? c : 0.f;
@@ -648,6 +652,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                     carry[d] = fpart + GB[d] - wq[d] * ivar[d] * mk_q[d] + hv[d] + dx[d];
                 }
             }
+            bprev = bB; eprev = eB;
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 rS[d] = rB[d];
