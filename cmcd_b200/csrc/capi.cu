@@ -29,6 +29,11 @@ size_t bridge_bwd_tc_workspace_bytes(int D, int K, int num_sms);
 int launch_bridge_bwd_tc(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, const float* cot_negw,
                          float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
                          const cmcd_net_grad* g_net, void* ws, size_t ws_bytes);
+int launch_bridge_ud_fwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sms);
+int launch_bridge_ud_bwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, const float* cot_negw,
+                         float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
+                         const cmcd_net_grad* g_net, void* ws, size_t ws_bytes);
+size_t bridge_ud_bwd_workspace_bytes(int mode, int D, int K, int HP, int arch, int num_sms);
 int launch_loss_stats(cudaStream_t st, const float* negw, long long n, float* out4);
 int launch_batched_elbo_lnz(cudaStream_t st, const float* losses, int batches, int n, float* elbo, float* lnz);
 int launch_threefry(cudaStream_t st, const uint32_t* key2, const uint32_t* x0, const uint32_t* x1, long long n, uint32_t* y0, uint32_t* y1);
@@ -58,16 +63,19 @@ static int num_sms() {
     return g_num_sms;
 }
 
+static bool is_ud(int mode) { return mode >= CMCD_MODE_UD_LP_A && mode <= CMCD_MODE_UD_LP_A_SN; }
+static bool mode_uses_net(int mode) { return mode != CMCD_MODE_ULA && mode != CMCD_MODE_UD_LP_A; }
+
 static int build_args(const cmcd_bridge_desc* d, const int32_t* seeds, const float* vd_mean, const float* vd_logdiag,
                       const float* betas, const float* eps, const cmcd_net* net, const cmcd_target* tg, BridgeArgs& a) {
     if (!d || !tg) { set_error("null descriptor"); return 2; }
-    if (d->mode < CMCD_MODE_ULA || d->mode > CMCD_MODE_CAIS_VAR_SN) { set_error("Mode not implemented."); return 2; }
+    if (d->mode < CMCD_MODE_ULA || d->mode > CMCD_MODE_UD_LP_A_SN) { set_error("Mode not implemented."); return 2; }
     if (d->nbridges < 0 || d->n_particles < 0 || d->dim < 1) { set_error("bad sizes N=%d K=%d d=%d", d->n_particles, d->nbridges, d->dim); return 2; }
     std::memset(&a, 0, sizeof(a));
     a.mode = d->mode; a.K = d->nbridges; a.N = d->n_particles;
     a.clip_t = d->clip_target; a.clip_q = d->clip_q;
     a.seeds = seeds; a.vd_mean = vd_mean; a.vd_logdiag = vd_logdiag; a.betas = betas; a.eps = eps;
-    const bool needs_net = d->mode != CMCD_MODE_ULA && d->nbridges >= 1;
+    const bool needs_net = mode_uses_net(d->mode) && d->nbridges >= 1;
     if (needs_net && (!net || net->arch == CMCD_ARCH_NONE)) { set_error("mode %d needs a drift network", d->mode); return 2; }
     if (net && net->arch != CMCD_ARCH_NONE && needs_net) {
         if (net->arch != CMCD_ARCH_GEFFNER && net->arch != CMCD_ARCH_DDS) { set_error("nn_arch %d not implemented", net->arch); return 2; }
@@ -96,6 +104,7 @@ static int build_args(const cmcd_bridge_desc* d, const int32_t* seeds, const flo
             break;
         case CMCD_TARGET_LGCP:
             if (!tg->lgcp_kinv || !tg->lgcp_counts) { set_error("lgcp needs kinv and counts"); return 2; }
+            if (is_ud(d->mode)) { set_error("the underdamped modes have no wide (lgcp) path"); return 2; }
             break;
         default: set_error("target kind %d not in the registry", tg->kind); return 2;
     }
@@ -114,7 +123,7 @@ int cmcd_num_sms(void) { return num_sms(); }
 
 size_t cmcd_bridge_fwd_workspace_bytes(const cmcd_bridge_desc* desc, const cmcd_net* net, const cmcd_target* target) {
     if (!desc || !target || target->kind != CMCD_TARGET_LGCP) return 0;
-    const bool uses_net = net && net->arch != CMCD_ARCH_NONE && desc->mode != CMCD_MODE_ULA && desc->nbridges >= 1;
+    const bool uses_net = net && net->arch != CMCD_ARCH_NONE && mode_uses_net(desc->mode) && desc->nbridges >= 1;
     return wide_fwd_workspace_bytes(desc->n_particles, desc->dim, uses_net ? net->hidden_pad : 0);
 }
 
@@ -130,6 +139,7 @@ int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
     if (sms <= 0) { set_error("no CUDA device"); return 1; }
     if (target->kind == CMCD_TARGET_LGCP)
         return launch_wide_fwd(a, target, desc->dim, (cudaStream_t)stream, sms, workspace, workspace_bytes);
+    if (is_ud(desc->mode)) return launch_bridge_ud_fwd(a, desc->dim, (cudaStream_t)stream, sms);
     // hidden width 64: tcgen05 tiles; other widths: FP32 FMA kernel.  CMCD_DISABLE_TC=1 forces the FP32 kernel (A/B runs).
     if (fwd_tc_supported(a, desc->dim) && !std::getenv("CMCD_DISABLE_TC"))
         return launch_bridge_fwd_tc(a, desc->dim, (cudaStream_t)stream, sms);
@@ -138,7 +148,9 @@ int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
 
 size_t cmcd_bridge_bwd_workspace_bytes(const cmcd_bridge_desc* desc, const cmcd_net* net) {
     const int sms = num_sms() > 0 ? num_sms() : 148;
-    const int arch = (net && desc->mode != CMCD_MODE_ULA) ? net->arch : CMCD_ARCH_NONE;
+    const int arch = (net && mode_uses_net(desc->mode)) ? net->arch : CMCD_ARCH_NONE;
+    if (is_ud(desc->mode))
+        return bridge_ud_bwd_workspace_bytes(desc->mode, desc->dim, desc->nbridges, net ? net->hidden_pad : 0, arch, sms);
     if (desc->dim > 64)   // wide path (lgcp, d = 1600): [N x d] / [N x hidden] state + split-K partials
         return wide_bwd_workspace_bytes(desc->n_particles, desc->dim, arch != CMCD_ARCH_NONE ? net->hidden_pad : 0);
     size_t need = bridge_bwd_workspace_bytes(desc->dim, desc->nbridges, net ? net->hidden_pad : 0, arch, sms);
@@ -164,6 +176,9 @@ int cmcd_bridge_bwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
     if (target->kind == CMCD_TARGET_LGCP)
         return launch_wide_bwd(a, target, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
                                g_eps, g_net, workspace, workspace_bytes);
+    if (is_ud(desc->mode))
+        return launch_bridge_ud_bwd(a, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
+                                    g_eps, g_net, workspace, workspace_bytes);
     if (bwd_tc_supported(a, desc->dim) && !std::getenv("CMCD_DISABLE_TC"))
         return launch_bridge_bwd_tc(a, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
                                     g_eps, g_net, workspace, workspace_bytes);

@@ -23,26 +23,30 @@ struct NetSmem {
     const float *W2, *U1, *U2, *W3, *U3;  // shared memory copies
 };
 
-__host__ __device__ inline size_t net_smem_floats(int D, int HP) {
-    return (size_t)HP * HP + 2 * (size_t)D * HP + (size_t)HP * D + (size_t)D * D;
+// DI = input width of the network (D for the overdamped modes; 2D for the (z, rho) networks of the underdamped modes,
+// mcdboundingmachine.py:84-102), D = output width.
+__host__ __device__ inline size_t net_smem_floats(int D, int HP, int DI = 0) {
+    if (DI == 0) DI = D;
+    return (size_t)HP * HP + 2 * (size_t)DI * HP + (size_t)HP * D + (size_t)DI * D;
 }
 
 // cooperative copy global -> shared; call from all threads, followed by __syncthreads()
-__device__ inline NetSmem net_stage_smem(const NetView& nv, int D, float* sm) {
+__device__ inline NetSmem net_stage_smem(const NetView& nv, int D, float* sm, int DI = 0) {
+    if (DI == 0) DI = D;
     const int HP = nv.HP;
     float* sW2 = sm;
     float* sU1 = sW2 + (size_t)HP * HP;
-    float* sU2 = sU1 + D * HP;
-    float* sW3 = sU2 + D * HP;
+    float* sU2 = sU1 + DI * HP;
+    float* sW3 = sU2 + DI * HP;
     float* sU3 = sW3 + HP * D;
     if (nv.arch != CMCD_ARCH_NONE) {
         for (int i = threadIdx.x; i < HP * HP; i += blockDim.x) sW2[i] = nv.W2[i];
-        for (int i = threadIdx.x; i < D * HP; i += blockDim.x) {
+        for (int i = threadIdx.x; i < DI * HP; i += blockDim.x) {
             sU1[i] = nv.U1[i];
             sU2[i] = nv.U2 ? nv.U2[i] : 0.f;
         }
         for (int i = threadIdx.x; i < HP * D; i += blockDim.x) sW3[i] = nv.W3[i];
-        for (int i = threadIdx.x; i < D * D; i += blockDim.x) sU3[i] = nv.U3 ? nv.U3[i] : 0.f;
+        for (int i = threadIdx.x; i < DI * D; i += blockDim.x) sU3[i] = nv.U3 ? nv.U3[i] : 0.f;
     }
     NetSmem s;
     s.W2 = sW2; s.U1 = sU1; s.U2 = sU2; s.W3 = sW3; s.U3 = sU3;
@@ -52,7 +56,7 @@ __device__ inline NetSmem net_stage_smem(const NetView& nv, int D, float* sm) {
 // out = NN(x, t).  a1col: this thread's private activation column (element j at a1col[j*PBS]).
 // __noinline__: the two evaluations per bridge step share one copy of the code (the fully inlined kernel was
 // 146 KB of SASS and stalled on instruction fetch, profiles/r1_ncu_summary.md).
-template <int D, int ACT, int HPT, int JC, int PBS>
+template <int D, int ACT, int HPT, int JC, int PBS, int DI = D>
 __device__ __noinline__ void net_fwd(const NetView& nv, const NetSmem& s, int t, const float* __restrict__ x,
                                      float* __restrict__ out, float* __restrict__ a1col) {
     const int HP = HPT ? HPT : nv.HP;
@@ -62,15 +66,15 @@ __device__ __noinline__ void net_fwd(const NetView& nv, const NetSmem& s, int t,
     // geffner <=> softplus, residual skip, U2/U3 present; dds <=> gelu, no skip, U2 = U3 = 0 (compile-time)
     constexpr bool has_u2 = (ACT == ACT_SOFTPLUS), has_u3 = (ACT == ACT_SOFTPLUS);
     constexpr float skip = (ACT == ACT_SOFTPLUS) ? 1.f : 0.f;
-    float xr[D];
+    float xr[DI];
 #pragma unroll
-    for (int a = 0; a < D; ++a) xr[a] = x[a];
+    for (int a = 0; a < DI; ++a) xr[a] = x[a];
     // layer 1
 #pragma unroll 4
     for (int j = 0; j < HP; ++j) {
         float p = __ldg(c1 + j);
 #pragma unroll
-        for (int a = 0; a < D; ++a) p = fmaf(xr[a], s.U1[a * HP + j], p);
+        for (int a = 0; a < DI; ++a) p = fmaf(xr[a], s.U1[a * HP + j], p);
         a1col[j * PBS] = act_fwd<ACT>(p);
     }
     float o[D];
@@ -79,7 +83,7 @@ __device__ __noinline__ void net_fwd(const NetView& nv, const NetSmem& s, int t,
         float p = __ldg(c3 + m);
         if (has_u3) {
 #pragma unroll
-            for (int a = 0; a < D; ++a) p = fmaf(xr[a], s.U3[a * D + m], p);
+            for (int a = 0; a < DI; ++a) p = fmaf(xr[a], s.U3[a * D + m], p);
         }
         o[m] = p;
     }
@@ -92,7 +96,7 @@ __device__ __noinline__ void net_fwd(const NetView& nv, const NetSmem& s, int t,
             float p = __ldg(c2 + j0 + jj);
             if (has_u2) {
 #pragma unroll
-                for (int a = 0; a < D; ++a) p = fmaf(xr[a], s.U2[a * HP + j0 + jj], p);
+                for (int a = 0; a < DI; ++a) p = fmaf(xr[a], s.U2[a * HP + j0 + jj], p);
             }
             acc[jj] = p;
         }

@@ -2,7 +2,8 @@
 
 Mirrors /root/reference/src/mcd_utils.py:24-190 (``evolve``: dispatch on ``params_fixed[2]``)
 for the overdamped modes on the hot path: MCD_ULA / MCD_ULA_sn (src/mcd_over_orig.py),
-MCD_CAIS_sn (src/mcd_cais.py), MCD_CAIS_var_sn (src/mcd_cais_var.py).  Unknown modes raise
+MCD_CAIS_sn (src/mcd_cais.py), MCD_CAIS_var_sn (src/mcd_cais_var.py), and the underdamped "LDVI" family
+MCD_U_a-lp / MCD_U_a-lp-sna / MCD_U_a-lp-sn (src/mcd_under_lp_a.py).  Unknown modes raise
 ``NotImplementedError("Mode not implemented.")`` like mcd_utils.py:190.
 
 The reference's per-particle ``evolve(z, betas, params, rng_key_gen, ...)`` runs under
@@ -17,7 +18,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import ARCH, MODE, CmcdBridgeDesc, CmcdNet, CmcdNetGrad
+from ._lib import ARCH, MODE, UD_MODES, CmcdBridgeDesc, CmcdNet, CmcdNetGrad
 from .nn import build_tables
 
 SUPPORTED_MODES = tuple(MODE)
@@ -40,7 +41,7 @@ def _clips(mode, grad_clipping):
     """grad_clipping -> (clip_target, clip_q).  mcd_cais.py:24-30 (1e3, target only);
     mcd_cais_var.py:33-40 (1e2, both); mcd_over_orig.py never clips."""
     inf = float("inf")
-    if not grad_clipping or mode in ("MCD_ULA", "MCD_ULA_sn"):
+    if not grad_clipping or mode in ("MCD_ULA", "MCD_ULA_sn") or mode in UD_MODES:   # mcd_under_lp_a.py takes no grad_clipping
         return inf, inf
     return (1e2, 1e2) if mode == "MCD_CAIS_var_sn" else (1e3, inf)
 
@@ -82,7 +83,8 @@ class _Bridge(torch.autograd.Function):
             tabs = {k: f32(t) for k, t in zip(_NET_KEYS, net_t)}
         negw = torch.empty(n, device=dev, dtype=torch.float32)
         z = torch.empty(n, dim, device=dev, dtype=torch.float32)
-        traj = torch.empty((K + 1, dim, n), device=dev, dtype=torch.float32) if need_grad else None
+        rows = 3 * dim if mode in UD_MODES else dim   # underdamped: (z_j, rho_j, rho'_j) per node
+        traj = torch.empty((K + 1, rows, n), device=dev, dtype=torch.float32) if need_grad else None
         desc, net, tg = _make_desc(mode, dim, K, n, clip_t, clip_q), _make_net(apply_fun, tabs, K), target.desc()
         L = _lib.lib()
         ws_bytes = L.cmcd_bridge_fwd_workspace_bytes(desc, net, tg)
@@ -107,7 +109,7 @@ class _Bridge(torch.autograd.Function):
         cot = cot_negw.detach().to(torch.float32).contiguous()
         g_mean, g_logdiag = torch.zeros_like(vd_mean), torch.zeros_like(vd_logdiag)
         g_betas = torch.zeros(max(K, 1), device=dev)
-        g_eps = torch.zeros(max(K, 1), device=dev)
+        g_eps = torch.zeros_like(eps) if mode in UD_MODES else torch.zeros(max(K, 1), device=dev)
         desc, net, tg = _make_desc(mode, dim, K, n, clip_t, clip_q), _make_net(apply_fun, tabs, K), target.desc()
         gnet, gt = CmcdNetGrad(), {}
         if apply_fun is not None:
@@ -125,6 +127,8 @@ class _Bridge(torch.autograd.Function):
                                          _lib.ptr(g_eps), gnet, _lib.ptr(ws), ws_bytes))
         _lib.count_launches(2)  # adjoint kernel + partial-gradient reduce kernel
         net_grads = tuple(gt.get(k) for k in _NET_KEYS) if apply_fun is not None else ()
+        if mode in UD_MODES:
+            return (None, None, g_mean, g_logdiag, g_betas[:K] if K else None, g_eps if K else None, *net_grads)
         return (None, None, g_mean, g_logdiag, g_betas[:K] if K else None, g_eps[:K] if K else None, *net_grads)
 
 
@@ -137,11 +141,15 @@ def bridge(seeds, params, betas, params_fixed, log_prob_model, eps_schedule=None
         raise NotImplementedError("Mode not implemented.")
     vd = params["vd"]
     dev = vd["mean"].device
-    uses_net = mode != "MCD_ULA" and nbridges >= 1
+    uses_net = mode not in ("MCD_ULA", "MCD_U_a-lp") and nbridges >= 1
     if uses_net and apply_fun is None:
         raise RuntimeError(f"mode {mode} needs a score network")
     clip_t, clip_q = _clips(mode, grad_clipping)
-    if nbridges >= 1:
+    if nbridges >= 1 and mode in UD_MODES:
+        # (eps_i, eta_i) rows: eta_aux = gamma * eps (mcd_under_lp_a.py:28), constant over the steps; [2, K]
+        e = eps_table(params["eps"], nbridges, None)
+        eps = torch.stack([e, params["gamma"] * e])
+    elif nbridges >= 1:
         sched = eps_schedule if mode in ("MCD_CAIS_sn", "MCD_CAIS_var_sn") else None  # orig ignores the schedule
         eps = eps_table(params["eps"], nbridges, sched)
     else:

@@ -15,7 +15,8 @@ from . import variationaldist as vd
 from .nn import initialize_network
 from .pytree import ravel_pytree, tree_map
 
-_SN_MODES = ("MCD_ULA_sn", "MCD_CAIS_sn", "MCD_CAIS_var_sn")
+_SN_MODES = ("MCD_ULA_sn", "MCD_CAIS_sn", "MCD_CAIS_var_sn", "MCD_U_a-lp-sna")   # mcdboundingmachine.py:67-83
+_SN_RHO_MODES = ("MCD_U_a-lp-sn",)                                                # :84-102: network on (z, rho), rho_dim = dim
 
 
 def initialize(dim, vdparams=None, nbridges=0, eps=0.01, gamma=10.0, eta=0.5, ngridb=32, mgridref_y=None,
@@ -33,6 +34,10 @@ def initialize(dim, vdparams=None, nbridges=0, eps=0.01, gamma=10.0, eta=0.5, ng
         (pt if name in trainable else pn)[name] = f(val)
     if mode in _SN_MODES:
         init_fun_sn, apply_fun_sn = initialize_network(dim, emb_dim, nbridges, nlayers=nlayers, nn_arch=nn_arch,
+                                                       fully_connected_units=fully_connected_units)
+        pt["sn"] = init_fun_sn(seed, None, device=dev)[1]
+    elif mode in _SN_RHO_MODES:
+        init_fun_sn, apply_fun_sn = initialize_network(dim, emb_dim, nbridges, rho_dim=dim, nlayers=nlayers, nn_arch=nn_arch,
                                                        fully_connected_units=fully_connected_units)
         pt["sn"] = init_fun_sn(seed, None, device=dev)[1]
     else:

@@ -25,9 +25,10 @@ def _pad8(n):
 class ApplyFun:
     """Tag returned in ``params_fixed[3]`` (the reference stores the apply function there)."""
 
-    def __init__(self, arch, x_dim, emb_dim, nbridges):
-        self.arch, self.x_dim, self.emb_dim, self.nbridges = arch, x_dim, emb_dim, nbridges
-        self.hidden = DDS_CHANNELS if arch == "dds" else x_dim + emb_dim
+    def __init__(self, arch, x_dim, emb_dim, nbridges, rho_dim=0):
+        self.arch, self.x_dim, self.emb_dim, self.nbridges, self.rho_dim = arch, x_dim, emb_dim, nbridges, rho_dim
+        self.in_dim = x_dim + rho_dim   # per-particle input: z, or (z, rho) for the underdamped networks (nn.py:43, nn_dds.py:56)
+        self.hidden = DDS_CHANNELS if arch == "dds" else self.in_dim + emb_dim
         self.hidden_pad = _pad8(self.hidden)
 
     def __call__(self, params, inputs, i, **kwargs):
@@ -35,17 +36,17 @@ class ApplyFun:
                            "call mcd_utils.evolve / mcdboundingmachine.compute_bound instead")
 
     def __hash__(self):
-        return hash((self.arch, self.x_dim, self.emb_dim, self.nbridges))
+        return hash((self.arch, self.x_dim, self.emb_dim, self.nbridges, self.rho_dim))
 
     def __eq__(self, o):
-        return isinstance(o, ApplyFun) and (self.arch, self.x_dim, self.emb_dim, self.nbridges) == \
-            (o.arch, o.x_dim, o.emb_dim, o.nbridges)
+        return isinstance(o, ApplyFun) and (self.arch, self.x_dim, self.emb_dim, self.nbridges, self.rho_dim) == \
+            (o.arch, o.x_dim, o.emb_dim, o.nbridges, o.rho_dim)
 
 
 # ------------------------------------------------------------------ init (same distributions as stax / haiku)
-def init_geffner(x_dim, emb_dim, nbridges, gen, device=None, dtype=torch.float32):
+def init_geffner(x_dim, emb_dim, nbridges, gen, device=None, dtype=torch.float32, rho_dim=0):
     """nn.py:42-64: Dense = glorot-normal W [in,out] + 1e-2 N(0,1) b; emb = 0.05 N(0,1); factor_sn = 0."""
-    in_dim = x_dim + emb_dim
+    in_dim = x_dim + rho_dim + emb_dim
 
     def dense(i, o):
         std = math.sqrt(2.0 / (i + o))
@@ -57,7 +58,7 @@ def init_geffner(x_dim, emb_dim, nbridges, gen, device=None, dtype=torch.float32
             "factor_sn": torch.tensor(0.0, dtype=dtype, device=device)}
 
 
-def init_dds(x_dim, gen, device=None, dtype=torch.float32):
+def init_dds(x_dim, gen, device=None, dtype=torch.float32, rho_dim=0):
     """nn_dds.py:91-127,179-192: haiku Linear (trunc-normal 1/sqrt(fan_in), zero bias); zero head; zero phase."""
     c = DDS_CHANNELS
 
@@ -68,7 +69,7 @@ def init_dds(x_dim, gen, device=None, dtype=torch.float32):
         return {"w": w.to(device), "b": torch.zeros(o, dtype=dtype, device=device)}
 
     return {"timestep_phase": torch.zeros(1, c, dtype=dtype, device=device),
-            "tc1": lin(2 * c, c), "tc2": lin(c, c), "st1": lin(x_dim + c, c), "st2": lin(c, c),
+            "tc1": lin(2 * c, c), "tc2": lin(c, c), "st1": lin(x_dim + rho_dim + c, c), "st2": lin(c, c),
             "out": {"w": torch.zeros(c, x_dim, dtype=dtype, device=device),
                     "b": torch.zeros(x_dim, dtype=dtype, device=device)}}
 
@@ -76,17 +77,15 @@ def init_dds(x_dim, gen, device=None, dtype=torch.float32):
 def initialize_network(x_dim, emb_dim, nbridges, rho_dim=0, nlayers=4, nn_arch="geffner",
                        fully_connected_units=None):
     """nn.py:21-39 -> (init_fun(rng, input_shape) -> (None, params), apply_fun)."""
-    if rho_dim:
-        raise NotImplementedError("rho_dim > 0 (underdamped modes) is outside the hot-path scope")
     if nn_arch not in ("geffner", "dds"):
         raise NotImplementedError(f"nn_arch {nn_arch!r} not implemented (dds_grad is broken in the reference)")
-    apply_fun = ApplyFun(nn_arch, x_dim, emb_dim, nbridges)
+    apply_fun = ApplyFun(nn_arch, x_dim, emb_dim, nbridges, rho_dim)
 
     def init_fun(rng, input_shape=None, device=None):
         gen = rng if isinstance(rng, torch.Generator) else torch.Generator().manual_seed(int(rng))
         if nn_arch == "geffner":
-            return None, init_geffner(x_dim, emb_dim, nbridges, gen, device)
-        return None, init_dds(x_dim, gen, device)
+            return None, init_geffner(x_dim, emb_dim, nbridges, gen, device, rho_dim=rho_dim)
+        return None, init_dds(x_dim, gen, device, rho_dim=rho_dim)
 
     return init_fun, apply_fun
 
@@ -114,7 +113,7 @@ def dds_timestep_coeff(device, dtype=torch.float32):
 
 def build_tables(apply_fun: ApplyFun, sn):
     """params["sn"] -> dict(U1,U2,U3,W2,W3,c1,c2,c3,out_scale) in the layout of ``cmcd_net`` (differentiable)."""
-    d, K, hp = apply_fun.x_dim, apply_fun.nbridges, apply_fun.hidden_pad
+    d, K, hp = apply_fun.in_dim, apply_fun.nbridges, apply_fun.hidden_pad   # d: rows of the weights that see the particle
     if apply_fun.arch == "geffner":
         (l1, l2, l3) = sn["nn"]
         rows = torch.clamp(torch.arange(K + 1, device=sn["emb"].device), max=K - 1)  # JAX clamps emb[K] (nn.py:68)

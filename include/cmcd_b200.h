@@ -21,8 +21,16 @@
 extern "C" {
 #endif
 
-/* boundmode -- the `mode` string of mcd_utils.evolve (mcd_utils.py:34-190) */
-enum { CMCD_MODE_ULA = 0, CMCD_MODE_ULA_SN = 1, CMCD_MODE_CAIS_SN = 2, CMCD_MODE_CAIS_VAR_SN = 3 };
+/* boundmode -- the `mode` string of mcd_utils.evolve (mcd_utils.py:34-190).
+ * 4..6: the underdamped "LDVI" family, evolve_underdamped_lp_a (mcd_under_lp_a.py:6-87; mcd_utils.py:83-118):
+ *   MCD_U_a-lp (no network), MCD_U_a-lp-sna (network on z), MCD_U_a-lp-sn (network on (z, rho'), rho_dim = dim,
+ *   mcdboundingmachine.py:84-102).  For these modes:
+ *     eps / g_eps = [2][K] = (eps_i, eta_i) with eta_i = gamma * eps_i (mcd_under_lp_a.py:28) -- the host forms eta;
+ *     traj        = [K+1][3 dim][N] = (z_j, rho_j, rho'_j) per node;
+ *     cmcd_net    U1 / U2 = [in][HP], U3 = [in][dim] with in = dim (sna) or 2 dim (sn);
+ *     clip_target / clip_q are ignored (the operator has no grad_clipping). */
+enum { CMCD_MODE_ULA = 0, CMCD_MODE_ULA_SN = 1, CMCD_MODE_CAIS_SN = 2, CMCD_MODE_CAIS_VAR_SN = 3,
+       CMCD_MODE_UD_LP_A = 4, CMCD_MODE_UD_LP_A_SNA = 5, CMCD_MODE_UD_LP_A_SN = 6 };
 /* target registry -- model_handler.load_model (model_handler.py:30-43) */
 enum { CMCD_TARGET_GMM = 0, CMCD_TARGET_MANY_GMM = 1, CMCD_TARGET_FUNNEL = 2, CMCD_TARGET_LGCP = 3 };
 /* drift network -- nn.initialize_network (nn.py:21-39) */

@@ -4,6 +4,7 @@ ORACLE / TEST INFRASTRUCTURE ONLY.  Follows, under /root/reference/src:
   mcdboundingmachine.py:11-123 (initialize), :126-179 (compute_log_elbo), :183-231 (compute_bound[_var])
   mcd_utils.py:14-33 (sample_kernel / log_prob_kernel / evolve dispatch)
   mcd_cais.py:6-99, mcd_cais_var.py:7-112, mcd_over_orig.py:6-65 (the three step bodies)
+  mcd_under_lp_a.py:6-87 (underdamped "LDVI" family: MCD_U_a-lp, MCD_U_a-lp-sna, MCD_U_a-lp-sn)
   vardist/diag_gauss.py:20-62, boundingmachine.py:73-111 (nbridges=0 MFVI bound)
   utils.py:219-248 (ELBO / ln Z estimators)
 Particles are a leading batch axis (the reference vmaps a per-particle function).  Gaussians
@@ -57,7 +58,15 @@ def initialize(dim, vdparams=None, nbridges=0, eps=0.01, gamma=10.0, eta=0.5, ng
         sn, apply_fun_sn = initialize_network(dim, emb_dim, nbridges, nn_arch,
                                               torch.Generator().manual_seed(seed), live, dtype)
         pt["sn"] = sn
-    elif mode == "MCD_ULA":
+    elif mode == "MCD_U_a-lp-sna":   # mcdboundingmachine.py:67-83: network on z only
+        sn, apply_fun_sn = initialize_network(dim, emb_dim, nbridges, nn_arch,
+                                              torch.Generator().manual_seed(seed), live, dtype)
+        pt["sn"] = sn
+    elif mode == "MCD_U_a-lp-sn":    # :84-102: network on (z, rho), rho_dim = dim
+        sn, apply_fun_sn = initialize_network(dim, emb_dim, nbridges, nn_arch,
+                                              torch.Generator().manual_seed(seed), live, dtype, rho_dim=dim)
+        pt["sn"] = sn
+    elif mode in ("MCD_ULA", "MCD_U_a-lp"):
         apply_fun_sn = None
     else:
         raise NotImplementedError("Mode not implemented.")
@@ -110,6 +119,47 @@ def _score(fn, z):
 
 
 # ---------------------------------------------------------------- the step bodies
+UD_MODES = ("MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn")
+
+
+def evolve_underdamped_lp_a(z, betas, params, rho0, xi, params_fixed, log_prob_model, traj=None):
+    """mcd_under_lp_a.py:6-87 (use_sn / full_sn from the mode, mcd_utils.py:83-118).  rho0 [N,d], xi [K,N,d]."""
+    dim, nbridges, mode, apply_fun_sn = params_fixed
+    vd = params["vd"]
+    use_sn, full_sn = mode != "MCD_U_a-lp", mode == "MCD_U_a-lp-sn"
+    eps, gamma = params["eps"], params["gamma"]
+    zero, one = torch.zeros((), dtype=z.dtype), torch.ones((), dtype=z.dtype)
+
+    def gradU(x, beta):  # jax.grad(U)(z, beta), :18-21
+        U = lambda y: -1.0 * (beta * log_prob_model(y) + (1.0 - beta) * vd_log_prob(vd, y))
+        return _score(U, x)
+
+    rho = rho0                                           # :62-63
+    w = -normal_log_prob(rho, zero, one)                 # :66-67
+    if traj is not None:
+        traj[-1] = (traj[-1], rho.detach().clone(), None)
+    for i in range(nbridges):                            # :23-60
+        beta = betas[i]
+        eta_aux = gamma * eps
+        fk_rho_mean = rho * (1.0 - eta_aux)
+        scale = torch.sqrt(2.0 * eta_aux)
+        rho_prime = fk_rho_mean + scale * xi[i]
+        rho_pp = rho_prime - eps * gradU(z, beta) / 2.0
+        z_new = z + eps * rho_pp
+        rho_new = rho_pp - eps * gradU(z_new, beta) / 2.0
+        bk_rho_mean = rho_prime * (1.0 - eta_aux)
+        if use_sn:
+            inp = torch.cat([z, rho_prime], dim=-1) if full_sn else z
+            bk_rho_mean = bk_rho_mean + 2 * eta_aux * apply_fun_sn(params["sn"], inp, i)
+        w = w + normal_log_prob(rho, bk_rho_mean, scale) - normal_log_prob(rho_prime, fk_rho_mean, scale)
+        if traj is not None:
+            traj[-1] = (traj[-1][0], traj[-1][1], rho_prime.detach().clone())
+            traj.append((z_new.detach().clone(), rho_new.detach().clone(), None))
+        z, rho = z_new, rho_new
+    w = w + normal_log_prob(rho, zero, one)              # :83-84
+    return z, w
+
+
 def evolve(z, betas, params, xi, params_fixed, log_prob_model, eps_schedule=None, grad_clipping=False, traj=None):
     """mcd_utils.py:24-190 dispatch + the three scan bodies.  xi [K,N,d] are the per-step Gaussians."""
     dim, nbridges, mode, apply_fun_sn = params_fixed
@@ -174,7 +224,12 @@ def compute_log_elbo(seeds, params_flat, unflatten, params_fixed, log_prob, eps_
     params = {**pt, **pn}
     dim, nbridges = params_fixed[0], params_fixed[1]
     dtype = params_flat.dtype
-    xi0_np, xi_np = prng.particle_noise(np.asarray(seeds), dim, nbridges)
+    ud = params_fixed[2] in UD_MODES
+    if ud:
+        xi0_np, rho0_np, xi_np = prng.particle_noise_ud(np.asarray(seeds), dim, nbridges)
+        rho0 = torch.tensor(rho0_np, dtype=dtype)
+    else:
+        xi0_np, xi_np = prng.particle_noise(np.asarray(seeds), dim, nbridges)
     xi0, xi = torch.tensor(xi0_np, dtype=dtype), torch.tensor(xi_np, dtype=dtype)
     z = vd_sample_rep(params["vd"], xi0)
     w = -vd_log_prob(params["vd"], z)
@@ -182,7 +237,10 @@ def compute_log_elbo(seeds, params_flat, unflatten, params_fixed, log_prob, eps_
         traj.append(z.detach().clone())
     if nbridges >= 1:
         betas = make_betas(params)
-        z, w_mom = evolve(z, betas, params, xi, params_fixed, log_prob, eps_schedule, grad_clipping, traj)
+        if ud:
+            z, w_mom = evolve_underdamped_lp_a(z, betas, params, rho0, xi, params_fixed, log_prob, traj)
+        else:
+            z, w_mom = evolve(z, betas, params, xi, params_fixed, log_prob, eps_schedule, grad_clipping, traj)
         w = w + w_mom
     w = w + log_prob(z)
     return -1.0 * w, z

@@ -16,11 +16,11 @@ import torch.nn.functional as F
 
 
 # --------------------------------------------------------------------------- geffner (nn.py:42-72)
-def init_geffner(x_dim, emb_dim, nbridges, gen, live=False, dtype=torch.float32):
+def init_geffner(x_dim, emb_dim, nbridges, gen, live=False, dtype=torch.float32, rho_dim=0):
     """stax Dense init: glorot-normal W [in,out], b ~ 1e-2*N(0,1); emb ~ 0.05 N(0,1) (nn.py:17-18);
     factor_sn = 0 (nn.py:63).  ``live=True`` sets factor_sn=0.1 so the drift path is numerically
     active (SURVEY section 8d synthetic-input convention)."""
-    in_dim = x_dim + emb_dim
+    in_dim = x_dim + rho_dim + emb_dim   # nn.py:43 (rho_dim = dim for the (z, rho) networks of the underdamped modes)
 
     def dense(i, o):
         std = math.sqrt(2.0 / (i + o))
@@ -52,7 +52,7 @@ def dds_timestep_coeff(dtype=torch.float32):
     return torch.tensor(np.linspace(0.1, 100.0, DDS_CHANNELS).astype(np.float32), dtype=dtype)
 
 
-def init_dds(x_dim, gen, live=False, dtype=torch.float32):
+def init_dds(x_dim, gen, live=False, dtype=torch.float32, rho_dim=0):
     """haiku Linear init: W ~ truncated-normal(1/sqrt(fan_in)), b = 0; LinearZero head zeros
     (nn_dds.py:179-192).  ``live=True``: head W ~ 0.01 N(0,1) so the drift is non-zero."""
     c = DDS_CHANNELS
@@ -68,7 +68,7 @@ def init_dds(x_dim, gen, live=False, dtype=torch.float32):
         head["b"] = torch.randn(x_dim, generator=gen, dtype=dtype) * 0.01
     return {"timestep_phase": torch.zeros(1, c, dtype=dtype) if not live else torch.randn(1, c, generator=gen, dtype=dtype) * 0.1,
             "tc1": lin(2 * c, c), "tc2": lin(c, c),
-            "st1": lin(x_dim + c, c), "st2": lin(c, c), "out": head}
+            "st1": lin(x_dim + rho_dim + c, c), "st2": lin(c, c), "out": head}   # nn_dds.py:56,159
 
 
 def gelu_exact(x):
@@ -96,11 +96,11 @@ def apply_dds(params, x, t):
     return torch.clamp(out, -1.0e4, 1.0e4)
 
 
-def initialize_network(x_dim, emb_dim, nbridges, nn_arch="geffner", gen=None, live=False, dtype=torch.float32):
-    """nn.py:21-39 -> (init_params, apply_fun(params, x, i))."""
+def initialize_network(x_dim, emb_dim, nbridges, nn_arch="geffner", gen=None, live=False, dtype=torch.float32, rho_dim=0):
+    """nn.py:21-39 -> (init_params, apply_fun(params, x, i)); x = [z] or [z, rho] (rho_dim > 0)."""
     gen = gen or torch.Generator().manual_seed(1)
     if nn_arch == "geffner":
-        return init_geffner(x_dim, emb_dim, nbridges, gen, live, dtype), apply_geffner
+        return init_geffner(x_dim, emb_dim, nbridges, gen, live, dtype, rho_dim), apply_geffner
     if nn_arch == "dds":
-        return init_dds(x_dim, gen, live, dtype), apply_dds
+        return init_dds(x_dim, gen, live, dtype, rho_dim), apply_dds
     raise NotImplementedError(f"nn_arch {nn_arch!r}: dds_grad is broken in the reference (SURVEY section 2 row 7)")

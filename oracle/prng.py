@@ -175,3 +175,23 @@ def particle_noise(seeds, dim, nbridges):
             xi[i] = normal(a, dim)   # mcd_utils.py:15
             _, k = split(k)          # mcd_cais.py:87
     return xi0, xi
+
+
+def particle_noise_ud(seeds, dim, nbridges):
+    """Key chain of the underdamped lp_a operator (mcdboundingmachine.py:151-162 + mcd_under_lp_a.py:62-73,31,59):
+    returns (xi0 [N,d], rho0 [N,d], xi [K,N,d])."""
+    k0 = prng_key(np.asarray(seeds))
+    a, k = split(k0)                 # mcdboundingmachine.py:153
+    xi0 = normal(a, dim)             # :156
+    rho0 = np.zeros_like(xi0)
+    xi = np.zeros((nbridges,) + xi0.shape, _f)
+    if nbridges >= 1:
+        g, _ = split(k)              # :162 (rng_key handed to evolve as rng_key_gen)
+        a, g = split(g)              # mcd_under_lp_a.py:62
+        rho0 = normal(a, dim)        # :63
+        _, g = split(g)              # :70
+        for i in range(nbridges):
+            a, g = split(g)          # :31
+            xi[i] = normal(a, dim)   # :32 -> mcd_utils.py:15
+            _, g = split(g)          # :59
+    return xi0, rho0, xi

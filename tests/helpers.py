@@ -33,6 +33,17 @@ CONFIGS = {
                        vd_mean=3.5, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
     "lin_funnel": dict(model="funnel", mode="MCD_CAIS_sn", N=200, K=12, nn_arch="dds", emb_dim=20, eps=0.05, sigma=1.0,
                        eps_schedule="linear", clip=True, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    # underdamped "LDVI" family (mcd_under_lp_a.py): network on (z, rho), on z only, and none
+    "LDVI_gmm": dict(model="gmm", mode="MCD_U_a-lp-sn", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.05, sigma=1.0,
+                     eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    "LDVI_funnel_dds": dict(model="funnel", mode="MCD_U_a-lp-sn", N=300, K=8, nn_arch="dds", emb_dim=20, eps=0.04, sigma=1.0,
+                            gamma=6.0, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    "LDVI_manygmm_dds": dict(model="many_gmm", mode="MCD_U_a-lp-sn", N=300, K=16, nn_arch="dds", emb_dim=20, eps=0.2, sigma=15.0,
+                             gamma=2.0, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "mgridref_y")),
+    "UDsna_funnel": dict(model="funnel", mode="MCD_U_a-lp-sna", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.04, sigma=1.0,
+                         eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    "UD_gmm": dict(model="gmm", mode="MCD_U_a-lp", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.05, sigma=1.0,
+                   eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
 }
 
 
@@ -53,7 +64,7 @@ def oracle_problem(name, dtype=torch.float32, N=None, K=None):
     g = torch.Generator().manual_seed(7)
     vdp["mean"] = vdp["mean"] + 0.1 * torch.randn(dim, generator=g) + c.get("vd_mean", 0.0)  # non-trivial mean
     mgrid = 1.0 + 0.3 * torch.rand(min(32, c["K"]) + 1, generator=g)
-    pf, unf, fixed = OM.initialize(dim, vdparams=vdp, nbridges=c["K"], eps=c["eps"], trainable=c["trainable"],
+    pf, unf, fixed = OM.initialize(dim, vdparams=vdp, nbridges=c["K"], eps=c["eps"], gamma=c.get("gamma", 10.0), trainable=c["trainable"],
                                    emb_dim=c["emb_dim"], mode=c["mode"], nn_arch=c["nn_arch"], mgridref_y=mgrid,
                                    live=True)
     return c, log_prob, dim, pf.to(dtype), unf, fixed
@@ -72,7 +83,7 @@ def product_problem(name, pf_oracle, device="cuda", N=None, K=None):
     out = PH.load_model(c["model"], device=device)
     target, dim = out[0], out[1]
     mgrid = torch.ones(min(32, c["K"]) + 1)
-    pf, unf, fixed = PM.initialize(dim, vdparams=PV.initialize(dim, device=device), nbridges=c["K"], eps=c["eps"],
+    pf, unf, fixed = PM.initialize(dim, vdparams=PV.initialize(dim, device=device), nbridges=c["K"], eps=c["eps"], gamma=c.get("gamma", 10.0),
                                    trainable=c["trainable"], emb_dim=c["emb_dim"], mode=c["mode"],
                                    nn_arch=c["nn_arch"], mgridref_y=mgrid, device=device)
     assert pf.numel() == pf_oracle.numel(), (pf.numel(), pf_oracle.numel())

@@ -93,3 +93,45 @@ def test_log_final_losses():
     assert abs(r["elbo"] + e.mean().item()) < 1e-12
     lnz = np.log(np.exp(-e.numpy()).mean(1))
     assert abs(r["ln_Z"] - lnz.mean()) < 1e-10 and abs(r["ln_Z_std"] - lnz.std()) < 1e-10
+
+
+# ---------------------------------------------------------------- underdamped "LDVI" family (mcd_under_lp_a.py)
+def test_ldvi_zero_drift_equals_no_network():
+    # reference init: factor_sn = 0 -> the (z, rho) network contributes exactly 0 -> MCD_U_a-lp-sn == MCD_U_a-lp
+    lp, dim = OH.load_model("gmm")
+    seeds = seeds_for(64)
+    out = {}
+    for mode in ("MCD_U_a-lp-sn", "MCD_U_a-lp-sna", "MCD_U_a-lp"):
+        pf, unf, fixed = OM.initialize(dim, nbridges=6, eps=0.05, gamma=4.0, trainable=("vd",), emb_dim=8, mode=mode,
+                                       nn_arch="geffner", live=False)
+        out[mode] = OM.compute_bound(seeds, pf, unf, fixed, lp)[1][0]
+    torch.testing.assert_close(out["MCD_U_a-lp-sn"], out["MCD_U_a-lp"], rtol=0, atol=0)
+    torch.testing.assert_close(out["MCD_U_a-lp-sna"], out["MCD_U_a-lp"], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("mode", ["MCD_U_a-lp", "MCD_U_a-lp-sn"])
+def test_ldvi_weights_are_unbiased(mode):
+    """E[exp(w)] = Z = 1 for ANY parameters: the momentum refresh is a proper Markov kernel, the leapfrog step a
+    volume-preserving bijection, the backward kernel a normalised density (Geffner & Domke 2021, eq. 9).  Pins the
+    operator restatement (signs of the log-ratio, which momentum enters which kernel) without a running reference."""
+    lp, dim = OH.load_model("gmm", dtype=torch.float64)
+    n = 40000
+    pf, unf, fixed = OM.initialize(dim, vdparams=OM.vd_initialize(dim, 2.0, torch.float64), nbridges=4, eps=0.2, gamma=3.0,
+                                   trainable=("vd",), emb_dim=8, mode=mode, nn_arch="geffner", live=True, dtype=torch.float64)
+    with torch.no_grad():
+        l = OM.compute_bound(np.arange(1, n + 1, dtype=np.int32), pf, unf, fixed, lp)[1][0]
+    wts = torch.exp(-l)
+    se = wts.std().item() / math.sqrt(n)
+    assert abs(wts.mean().item() - 1.0) < 4 * se + 1e-3, (wts.mean().item(), se)
+
+
+def test_ldvi_grad_matches_finite_difference_fp64():
+    c, lp, dim, pf, unf, fixed = oracle_problem("LDVI_gmm", torch.float64, N=20)
+    seeds = seeds_for(20)
+    g, _ = OM.grad_and_loss(OM.compute_bound, seeds, pf, unf, fixed, lp)
+    rng = np.random.default_rng(1)
+    for idx in rng.choice(np.nonzero(g.numpy())[0], 6, replace=False):
+        e = torch.zeros_like(pf)
+        e[idx] = 1e-6
+        fd = (OM.compute_bound(seeds, pf + e, unf, fixed, lp)[0] - OM.compute_bound(seeds, pf - e, unf, fixed, lp)[0]) / 2e-6
+        assert abs(fd.item() - g[idx].item()) < 1e-6 * max(1, abs(g[idx].item())), (idx, fd.item(), g[idx].item())
