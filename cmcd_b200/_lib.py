@@ -7,9 +7,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CMCD_B200_LIB") or os.path.join(_HERE, "libcmcd_b200.so")  # env override: A/B builds
 
+# 4-6: the underdamped operators (mcd_utils.py:59-133); the kernel mode only says what the network sees (none / z / (z, rho'))
 MODE = {"MCD_ULA": 0, "MCD_ULA_sn": 1, "MCD_CAIS_sn": 2, "MCD_CAIS_var_sn": 3,
-        "MCD_U_a-lp": 4, "MCD_U_a-lp-sna": 5, "MCD_U_a-lp-sn": 6}   # 4-6: evolve_underdamped_lp_a (mcd_utils.py:83-118)
-UD_MODES = ("MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn")
+        "MCD_U_a-lp": 4, "MCD_U_a-lp-sna": 5, "MCD_U_a-lp-sn": 6,       # evolve_underdamped_lp_a ("LDVI")
+        "MCD_U_e-lp": 4, "MCD_U_e-lp-sna": 5,                           # evolve_underdamped_lp_e
+        "MCD_U_ea-lp-sn": 6}                                            # evolve_underdamped_lp_ea
+UD_MODES = ("MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn", "MCD_U_e-lp", "MCD_U_e-lp-sna", "MCD_U_ea-lp-sn")
 TARGET = {"gmm": 0, "many_gmm": 1, "funnel": 2, "lgcp": 3}
 ARCH = {None: 0, "none": 0, "geffner": 1, "dds": 2}
 MIX_STRIDE = 6

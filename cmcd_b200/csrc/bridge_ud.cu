@@ -1,38 +1,45 @@
-// Underdamped bridge kernels ("LDVI" family): forward and reverse mode, one thread per particle, FP32-FMA path.
+// Underdamped bridge kernels (the momentum-augmented operators of mcd_utils.evolve): forward and reverse mode, one thread
+// per particle, FP32-FMA path.
 //
 // Replaces the XLA program of vmap(compute_log_elbo) (src/mcdboundingmachine.py:126-205) and its jax.grad
-// (src/main.py:174-176) when mcd_utils.evolve dispatches to evolve_underdamped_lp_a (src/mcd_utils.py:83-118):
-//   MCD_U_a-lp      no network                         (use_sn = False)
-//   MCD_U_a-lp-sna  network on z                       (use_sn, full_sn = False,  src/mcd_under_lp_a.py:43-46)
-//   MCD_U_a-lp-sn   network on (z, rho')  "LDVI"       (use_sn, full_sn = True,   src/mcd_under_lp_a.py:47-51)
-// Per particle (src/mcd_under_lp_a.py:18-85), state (z, rho), eta = gamma eps, s = sqrt(2 eta):
+// (src/main.py:174-176) when mcd_utils.evolve (src/mcd_utils.py:59-133) dispatches to
+//   evolve_underdamped_lp_a   MCD_U_a-lp | MCD_U_a-lp-sna | MCD_U_a-lp-sn ("LDVI")      src/mcd_under_lp_a.py:6-87
+//   evolve_underdamped_lp_e   MCD_U_e-lp | MCD_U_e-lp-sna                                src/mcd_under_lp_e.py:6-74
+//   evolve_underdamped_lp_ea  MCD_U_ea-lp-sn                                             src/mcd_under_lp_ea.py:6-104
+// All three scan bodies are one step with different coefficients (state (z, rho); x = network input):
 //   rho0 ~ N(0, I); w = -log N(rho0; 0, 1)
-//   step i:  m_f = rho (1 - eta);  rho' = m_f + s xi;  rho'' = rho' - eps gradU(z)/2;  z' = z + eps rho'';
-//            rho_new = rho'' - eps gradU(z')/2;  m_b = rho' (1 - eta) + 2 eta NN(x, i),  x = (z, rho') | z
-//            w += log N(rho; m_b, s) - log N(rho'; m_f, s)
+//   step i:  m_f = a_f rho;  rho' = m_f + s_f xi;  rho'' = rho' - eps gradU(z)/2;  z' = z + eps rho'';
+//            rho_new = rho'' - eps gradU(z')/2;  m_b = a_b rho' + c_n NN(x, i),  x = (z, rho') | z | -
+//            w += log N(rho; m_b, s_b) - log N(rho'; m_f, s_f)
 //   w += log N(rho_K; 0, 1)        (+ log p(z_K) - log q(z_0) in compute_log_elbo)
-// with gradU(z) = -(beta_i grad log p(z) + (1 - beta_i) grad log q(z)), never clipped (the operator has no grad_clipping).
+//   lp_a : a_f = a_b = 1 - g eps, s_f = s_b = sqrt(2 g eps), c_n = 2 g eps                (g = gamma)
+//   lp_e : a_f = a_b = eta, s_f = s_b = sqrt(1 - eta^2), c_n = 2 (1 - eta)
+//   lp_ea: a_f = exp(-g eps), s_f = sqrt(1 - a_f^2), a_b = 1 - g eps, c_n = 2 g eps, s_b = sqrt(2 g eps)
+// with gradU(z) = -(beta_i grad log p(z) + (1 - beta_i) grad log q(z)), never clipped (these operators take no
+// grad_clipping).  The kernel mode only says what the network sees (CMCD_MODE_UD_NONE / _NET_Z / _NET_ZRHO).
 //
-// ABI conventions for these modes (include/cmcd_b200.h): eps = [2][K] = (eps_i, eta_i) -- the host forms eta = gamma eps
-// so that the cotangents chain into both scalars; g_eps = [2][K]; traj = [K+1][3d][N] = (z_j, rho_j, rho'_j) per node
-// (rho'_j: the refreshed momentum of step j, stored so that the adjoint does not have to walk the key chain backwards).
+// ABI conventions for these modes (include/cmcd_b200.h): eps = [6][K] = rows (eps, a_f, s_f, a_b, c_n, s_b) -- the host
+// forms the coefficient rows from (eps, gamma, eta) with differentiable ops, so the cotangents g_eps = [6][K] chain into
+// those scalars; traj = [K+1][3d][N] = (z_j, rho_j, rho'_j) per node (rho'_j: the refreshed momentum of step j, stored
+// so that the adjoint does not have to walk the key chain backwards).
 //
 // Adjoint of step i (c = dL/dw; zb', rb' = cotangents of z', rho_new; pathwise in xi):
 //   g1b = -(eps/2) rb'                       zb'' = zb' - beta H_p(z') g1b + (1-beta) g1b / sigma^2
 //   rb'' = rb' + eps zb''                    g0b = -(eps/2) rb''
 //   zb   = zb'' - beta H_p(z) g0b + (1-beta) g0b / sigma^2 + J_z^T v
-//   r = (rho - m_b) / (2 eta);  G = c r;  v = 2 eta G (cotangent of the network output)
-//   rbp  = rb'' + (1 - eta) G + J_rho'^T v   (cotangent of rho')
-//   rb   = -G + (1 - eta) rbp
-//   d eta += c |r|^2 + G.(2 NN - rho') + rbp.(rho' - m_f)/(2 eta) - rbp.rho
-//   d eps += -rb'.gradU(z')/2 + zb''.rho'' - rb''.gradU(z)/2
-//   d beta += -g1b.(s_p(z') - s_q(z')) - g0b.(s_p(z) - s_q(z));  vd: through s_q at both points and z_0 = mu + sigma xi0.
-// (log N(rho; m_b, s) - log N(rho'; m_f, s): the -d log s terms cancel, the second one is -|xi|^2/2 with xi fixed.)
+//   r = (rho - m_b) / s_b^2;  G = c r;  v = c_n G (cotangent of the network output)
+//   rbp  = rb'' + a_b G + J_rho'^T v         (cotangent of rho')
+//   rb   = -G + a_f rbp
+//   d a_f = rbp.rho;  d s_f = rbp.xi + c d / s_f;  d a_b = G.rho';  d c_n = G.NN;  d s_b = c (s_b |r|^2 - d / s_b)
+//   d eps = -rb'.gradU(z')/2 + zb''.rho'' - rb''.gradU(z)/2
+//   d beta = -g1b.(s_p(z') - s_q(z')) - g0b.(s_p(z) - s_q(z));  vd: through s_q at both points and z_0 = mu + sigma xi0.
+// (log N(rho'; m_f, s_f) = -|xi|^2/2 - d log s_f - const with xi fixed.)
 #include "net_bwd.cuh"
 
 namespace cmcd {
 
 constexpr int UD_FWD_PB = 128;
+constexpr int UD_ROWS = 6;   // rows of the eps table: eps, a_f, s_f, a_b, c_n, s_b
 
 template <int D>
 __device__ __forceinline__ float ud_gauss_logprob(const float (&x)[D], const float (&mean)[D], float scale, float lognorm) {
@@ -102,14 +109,15 @@ __global__ void __launch_bounds__(UD_FWD_PB, (HPT > 64 ? 1 : 2)) bridge_ud_fwd_k
             wm = wm - ud_gauss_logprob<D>(rho, zeros, 1.0f, ln1);   // :66-67
             g = split_second(g);             // :70
             for (int i = 0; i < K; ++i) {
-                const float beta = __ldg(a.betas + i), eps = __ldg(a.eps + i), eta = __ldg(a.eps + K + i);
+                const float beta = __ldg(a.betas + i), eps = __ldg(a.eps + i);
+                const float af = __ldg(a.eps + K + i), sf = __ldg(a.eps + 2 * K + i), ab = __ldg(a.eps + 3 * K + i);
+                const float cn = __ldg(a.eps + 4 * K + i), sb = __ldg(a.eps + 5 * K + i);
                 float mf[D], mb[D], rp[D], rpp[D], rn[D];
-                const float scale = sqrtf(2.0f * eta);
                 step_keys_and_normal<D>(g, xi);   // :31-32 and :59
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
-                    mf[j] = rho[j] * (1.0f - eta);
-                    rp[j] = mf[j] + scale * xi[j];
+                    mf[j] = rho[j] * af;
+                    rp[j] = mf[j] + sf * xi[j];
                     const float sq = -((z[j] - mu[j]) / sig[j]) / sig[j];
                     const float g0 = -(beta * sp[j] + (1.0f - beta) * sq);
                     rpp[j] = rp[j] - eps * g0 / 2.0f;
@@ -125,7 +133,7 @@ __global__ void __launch_bounds__(UD_FWD_PB, (HPT > 64 ? 1 : 2)) bridge_ud_fwd_k
                 }
                 // backward-kernel mean: the network sees the OLD position and the refreshed momentum (:47-51)
 #pragma unroll
-                for (int j = 0; j < D; ++j) mb[j] = rp[j] * (1.0f - eta);
+                for (int j = 0; j < D; ++j) mb[j] = rp[j] * ab;
                 if constexpr (DI != 0) {
                     if (has_net) {
                         float x[DIN], nnv[D];
@@ -136,7 +144,7 @@ __global__ void __launch_bounds__(UD_FWD_PB, (HPT > 64 ? 1 : 2)) bridge_ud_fwd_k
                         }
                         net_fwd<D, ACT, HPT, JC, UD_FWD_PB, DIN>(nv, ns, i, x, nnv, a1col);
 #pragma unroll
-                        for (int j = 0; j < D; ++j) mb[j] = mb[j] + 2.0f * eta * nnv[j];
+                        for (int j = 0; j < D; ++j) mb[j] = mb[j] + cn * nnv[j];
                     }
                 }
                 lp = target_eval<D, false>(a.tgt, sTp, zn, sp, dummy, dummy);
@@ -146,9 +154,8 @@ __global__ void __launch_bounds__(UD_FWD_PB, (HPT > 64 ? 1 : 2)) bridge_ud_fwd_k
                     const float g1 = -(beta * sp[j] + (1.0f - beta) * sq);
                     rn[j] = rpp[j] - eps * g1 / 2.0f;
                 }
-                const float lognorm = logf(2.5066282746310002f * scale);
-                const float fk = ud_gauss_logprob<D>(rp, mf, scale, lognorm);
-                const float bk = ud_gauss_logprob<D>(rho, mb, scale, lognorm);
+                const float fk = ud_gauss_logprob<D>(rp, mf, sf, logf(2.5066282746310002f * sf));
+                const float bk = ud_gauss_logprob<D>(rho, mb, sb, logf(2.5066282746310002f * sb));
                 wm += bk - fk;
 #pragma unroll
                 for (int j = 0; j < D; ++j) { z[j] = zn[j]; rho[j] = rn[j]; }
@@ -228,8 +235,10 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
         for (int j = 0; j < D; ++j) { zb[j] = c * sp1[j]; rb[j] = (K >= 1) ? -c * rhoK[j] : 0.f; }
 
         for (int i = K - 1; i >= 0; --i) {
-            const float beta = __ldg(a.betas + i), eps = __ldg(a.eps + i), eta = __ldg(a.eps + K + i);
-            const float omb = 1.0f - beta, ome = 1.0f - eta, s2 = 2.0f * eta, he = 0.5f * eps;
+            const float beta = __ldg(a.betas + i), eps = __ldg(a.eps + i);
+            const float af = __ldg(a.eps + K + i), sf = __ldg(a.eps + 2 * K + i), ab = __ldg(a.eps + 3 * K + i);
+            const float cn = __ldg(a.eps + 4 * K + i), sb = __ldg(a.eps + 5 * K + i);
+            const float omb = 1.0f - beta, s2 = sb * sb, he = 0.5f * eps;
             float z[D], rho[D], rp[D];
 #pragma unroll
             for (int j = 0; j < D; ++j) {
@@ -237,7 +246,7 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
                 rho[j] = a.traj[((size_t)i * TS + D + j) * a.N + n];
                 rp[j] = a.traj[((size_t)i * TS + 2 * D + j) * a.N + n];
             }
-            float gbeta = 0.f, geps = 0.f, geta = 0.f;
+            float gbeta = 0.f, geps = 0.f, gaf = 0.f, gsf = 0.f, gab = 0.f, gcn = 0.f, gsb = 0.f;
             // ---- second half kick: rho_new = rho'' - (eps/2) gradU(z')
             float g1b[D], zbn[D], rbpp[D], g0b[D], sp0[D];
 #pragma unroll
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
                 zbc[j] = zbn[j] - beta * hv[j] + omb * ivar[j] * g0b[j];
                 rbp[j] = rbpp[j];
             }
-            // ---- backward-kernel log-density: recompute NN(x, i), pull back v = 2 eta c r
+            // ---- backward-kernel log-density: recompute NN(x, i), pull back v = c_n c r
             float x[DIN], o[D], nn[D], vv[D], dx[DIN], G[D];
 #pragma unroll
             for (int j = 0; j < D; ++j) {
@@ -292,15 +301,17 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
             float rr = 0.f;
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                const float mb = rp[j] * ome + 2.0f * eta * nn[j];
+                const float mb = rp[j] * ab + cn * nn[j];
                 const float r = (rho[j] - mb) / s2;
                 G[j] = c * r;
                 rr = fmaf(r, r, rr);
-                vv[j] = s2 * G[j];
-                geta = fmaf(G[j], 2.0f * nn[j] - rp[j], geta);
-                rbp[j] = fmaf(ome, G[j], rbp[j]);
+                vv[j] = cn * G[j];
+                gab = fmaf(G[j], rp[j], gab);
+                gcn = fmaf(G[j], nn[j], gcn);
+                rbp[j] = fmaf(ab, G[j], rbp[j]);
             }
-            geta = fmaf(c, rr, geta);
+            gsb = c * (sb * rr - (float)D / sb);
+            gsf = c * (float)D / sf;
             if constexpr (DI != 0) {
                 if (has_net) {
                     net_bwd<D, ACT, HPT, JC, BPB, DIN>(nv, ns, i, x, o, vv, dx, S1, S2, S3, sX, sVo, part, L);
@@ -311,21 +322,26 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
                     }
                 }
             }
-            // ---- momentum refresh: rho' = rho (1 - eta) + sqrt(2 eta) xi
+            // ---- momentum refresh: rho' = a_f rho + s_f xi
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                const float mf = rho[j] * ome;
-                geta = fmaf(rbp[j], (rp[j] - mf) / s2, geta);
-                geta = fmaf(-rho[j], rbp[j], geta);
-                rb[j] = fmaf(ome, rbp[j], -G[j]);
+                const float mf = rho[j] * af;
+                gsf = fmaf(rbp[j], (rp[j] - mf) / sf, gsf);
+                gaf = fmaf(rho[j], rbp[j], gaf);
+                rb[j] = fmaf(af, rbp[j], -G[j]);
                 zb[j] = zbc[j];
                 zn[j] = z[j];
             }
-            gbeta = warp_sum_f(gbeta); geps = warp_sum_f(geps); geta = warp_sum_f(geta);
+            gbeta = warp_sum_f(gbeta); geps = warp_sum_f(geps);
+            gaf = warp_sum_f(gaf); gsf = warp_sum_f(gsf); gab = warp_sum_f(gab); gcn = warp_sum_f(gcn); gsb = warp_sum_f(gsb);
             if ((tid & 31) == 0) {
                 atomicAdd(part + L.beta + i, gbeta);
                 atomicAdd(part + L.eps + i, geps);
-                atomicAdd(part + L.eps + K + i, geta);
+                atomicAdd(part + L.eps + K + i, gaf);
+                atomicAdd(part + L.eps + 2 * K + i, gsf);
+                atomicAdd(part + L.eps + 3 * K + i, gab);
+                atomicAdd(part + L.eps + 4 * K + i, gcn);
+                atomicAdd(part + L.eps + 5 * K + i, gsb);
             }
         }
         // initial: z0 = mu + sigma xi0, w0 = -log q(z0) = 0.5|xi0|^2 + sum log(sqrt(2pi) sigma); rho0 is pure noise   (zn = z_0 here)
@@ -341,7 +357,7 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
 
 // ---------------------------------------------------------------------------------------------------------------- launchers
 static int ud_net_in(int mode, int D) {
-    return mode == CMCD_MODE_UD_LP_A_SN ? 2 * D : (mode == CMCD_MODE_UD_LP_A_SNA ? D : 0);
+    return mode == CMCD_MODE_UD_NET_ZRHO ? 2 * D : (mode == CMCD_MODE_UD_NET_Z ? D : 0);
 }
 
 template <int D, int ACT, int HPT, int JC, int DI>
@@ -398,9 +414,9 @@ int launch_bridge_ud_fwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sm
 }
 
 static BwdLayout ud_layout(int D, int K, int HP, int arch, int din) {
-    // eps slot holds (eps_i, eta_i): 2K entries
+    // the eps slot holds the UD_ROWS coefficient rows
     BwdLayout l = make_layout(D, K, HP, arch, din ? din : D);
-    const int extra = K > 0 ? K : 1;
+    const int extra = (UD_ROWS - 1) * (K > 0 ? K : 1);
     l.mu += extra; l.ls += extra; l.P = (l.ls + D + 3) & ~3;
     return l;
 }

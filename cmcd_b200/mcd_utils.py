@@ -3,7 +3,8 @@
 Mirrors /root/reference/src/mcd_utils.py:24-190 (``evolve``: dispatch on ``params_fixed[2]``)
 for the overdamped modes on the hot path: MCD_ULA / MCD_ULA_sn (src/mcd_over_orig.py),
 MCD_CAIS_sn (src/mcd_cais.py), MCD_CAIS_var_sn (src/mcd_cais_var.py), and the underdamped "LDVI" family
-MCD_U_a-lp / MCD_U_a-lp-sna / MCD_U_a-lp-sn (src/mcd_under_lp_a.py).  Unknown modes raise
+MCD_U_a-lp / -sna / -sn (src/mcd_under_lp_a.py), MCD_U_e-lp / -sna (src/mcd_under_lp_e.py), MCD_U_ea-lp-sn
+(src/mcd_under_lp_ea.py) -- SURVEY section 8f row 3.  Unknown modes raise
 ``NotImplementedError("Mode not implemented.")`` like mcd_utils.py:190.
 
 The reference's per-particle ``evolve(z, betas, params, rng_key_gen, ...)`` runs under
@@ -35,6 +36,33 @@ def eps_table(eps0, nbridges, eps_schedule=None):
     if eps_schedule == "linear":
         return (0.0001 - eps0) / (nbridges - 1) * i + eps0
     return eps0 * torch.ones_like(i)
+
+
+def ud_coeff_table(mode, params, nbridges):
+    """[6, K] rows (eps, a_f, s_f, a_b, c_n, s_b) of the underdamped step (csrc/bridge_ud.cu), formed from the reference's
+    scalars with differentiable ops so the kernel's row cotangents chain into eps / gamma / eta:
+      forward kernel  rho' ~ N(a_f rho, s_f);  backward kernel  rho ~ N(a_b rho' + c_n NN, s_b)."""
+    eps, gamma, eta = params["eps"], params["gamma"], params["eta"]
+    if mode in ("MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn"):        # mcd_under_lp_a.py:28-51
+        eta_aux = gamma * eps
+        a_f = a_b = 1.0 - eta_aux
+        s_f = s_b = torch.sqrt(2.0 * eta_aux)
+        c_n = 2 * eta_aux
+    elif mode in ("MCD_U_e-lp", "MCD_U_e-lp-sna"):                       # mcd_under_lp_e.py:27-43
+        a_f = a_b = eta * torch.ones_like(eps)
+        s_f = s_b = torch.sqrt(1.0 - eta ** 2)
+        c_n = 2 * (1.0 - eta)
+    elif mode == "MCD_U_ea-lp-sn":                                       # mcd_under_lp_ea.py:28-57
+        eta_aux = gamma * eps
+        a_f = torch.exp(-gamma * eps)
+        s_f = torch.sqrt(1.0 - a_f ** 2)
+        a_b = 1.0 - eta_aux
+        c_n = 2 * eta_aux
+        s_b = torch.sqrt(2.0 * eta_aux)
+    else:
+        raise NotImplementedError("Mode not implemented.")
+    one = torch.ones(nbridges, device=eps.device, dtype=torch.float32)
+    return torch.stack([v * one for v in (eps, a_f, s_f, a_b, c_n, s_b)])
 
 
 def _clips(mode, grad_clipping):
@@ -141,14 +169,12 @@ def bridge(seeds, params, betas, params_fixed, log_prob_model, eps_schedule=None
         raise NotImplementedError("Mode not implemented.")
     vd = params["vd"]
     dev = vd["mean"].device
-    uses_net = mode not in ("MCD_ULA", "MCD_U_a-lp") and nbridges >= 1
+    uses_net = mode not in ("MCD_ULA", "MCD_U_a-lp", "MCD_U_e-lp") and nbridges >= 1
     if uses_net and apply_fun is None:
         raise RuntimeError(f"mode {mode} needs a score network")
     clip_t, clip_q = _clips(mode, grad_clipping)
     if nbridges >= 1 and mode in UD_MODES:
-        # (eps_i, eta_i) rows: eta_aux = gamma * eps (mcd_under_lp_a.py:28), constant over the steps; [2, K]
-        e = eps_table(params["eps"], nbridges, None)
-        eps = torch.stack([e, params["gamma"] * e])
+        eps = ud_coeff_table(mode, params, nbridges)   # [6, K]: eps and the kernel coefficients, constant over the steps
     elif nbridges >= 1:
         sched = eps_schedule if mode in ("MCD_CAIS_sn", "MCD_CAIS_var_sn") else None  # orig ignores the schedule
         eps = eps_table(params["eps"], nbridges, sched)

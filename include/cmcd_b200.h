@@ -22,15 +22,19 @@ extern "C" {
 #endif
 
 /* boundmode -- the `mode` string of mcd_utils.evolve (mcd_utils.py:34-190).
- * 4..6: the underdamped "LDVI" family, evolve_underdamped_lp_a (mcd_under_lp_a.py:6-87; mcd_utils.py:83-118):
- *   MCD_U_a-lp (no network), MCD_U_a-lp-sna (network on z), MCD_U_a-lp-sn (network on (z, rho'), rho_dim = dim,
- *   mcdboundingmachine.py:84-102).  For these modes:
- *     eps / g_eps = [2][K] = (eps_i, eta_i) with eta_i = gamma * eps_i (mcd_under_lp_a.py:28) -- the host forms eta;
+ * 4..6: the underdamped (momentum-augmented) operators evolve_underdamped_lp_a / _lp_e / _lp_ea
+ *   (mcd_under_lp_a.py:6-87 "LDVI", mcd_under_lp_e.py:6-74, mcd_under_lp_ea.py:6-104; dispatch mcd_utils.py:59-133).
+ *   The three scan bodies are one step with different coefficients, so the kernel mode only says what the score
+ *   network sees: nothing (MCD_U_a-lp, MCD_U_e-lp), z (MCD_U_a-lp-sna, MCD_U_e-lp-sna) or (z, rho') (MCD_U_a-lp-sn,
+ *   MCD_U_ea-lp-sn; rho_dim = dim, mcdboundingmachine.py:84-102).  For these modes:
+ *     eps / g_eps = [6][K] = rows (eps, a_f, s_f, a_b, c_n, s_b): forward-kernel mean a_f rho and scale s_f, backward-
+ *                   kernel mean a_b rho' + c_n NN and scale s_b (formulas per operator in csrc/bridge_ud.cu) -- the host
+ *                   forms the rows from (eps, gamma, eta) and chains the cotangents back;
  *     traj        = [K+1][3 dim][N] = (z_j, rho_j, rho'_j) per node;
- *     cmcd_net    U1 / U2 = [in][HP], U3 = [in][dim] with in = dim (sna) or 2 dim (sn);
- *     clip_target / clip_q are ignored (the operator has no grad_clipping). */
+ *     cmcd_net    U1 / U2 = [in][HP], U3 = [in][dim] with in = dim (NET_Z) or 2 dim (NET_ZRHO);
+ *     clip_target / clip_q are ignored (these operators take no grad_clipping). */
 enum { CMCD_MODE_ULA = 0, CMCD_MODE_ULA_SN = 1, CMCD_MODE_CAIS_SN = 2, CMCD_MODE_CAIS_VAR_SN = 3,
-       CMCD_MODE_UD_LP_A = 4, CMCD_MODE_UD_LP_A_SNA = 5, CMCD_MODE_UD_LP_A_SN = 6 };
+       CMCD_MODE_UD_NONE = 4, CMCD_MODE_UD_NET_Z = 5, CMCD_MODE_UD_NET_ZRHO = 6 };
 /* target registry -- model_handler.load_model (model_handler.py:30-43) */
 enum { CMCD_TARGET_GMM = 0, CMCD_TARGET_MANY_GMM = 1, CMCD_TARGET_FUNNEL = 2, CMCD_TARGET_LGCP = 3 };
 /* drift network -- nn.initialize_network (nn.py:21-39) */

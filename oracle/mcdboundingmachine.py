@@ -5,6 +5,7 @@ ORACLE / TEST INFRASTRUCTURE ONLY.  Follows, under /root/reference/src:
   mcd_utils.py:14-33 (sample_kernel / log_prob_kernel / evolve dispatch)
   mcd_cais.py:6-99, mcd_cais_var.py:7-112, mcd_over_orig.py:6-65 (the three step bodies)
   mcd_under_lp_a.py:6-87 (underdamped "LDVI" family: MCD_U_a-lp, MCD_U_a-lp-sna, MCD_U_a-lp-sn)
+  mcd_under_lp_e.py:6-74 (MCD_U_e-lp, MCD_U_e-lp-sna), mcd_under_lp_ea.py:6-104 (MCD_U_ea-lp-sn)
   vardist/diag_gauss.py:20-62, boundingmachine.py:73-111 (nbridges=0 MFVI bound)
   utils.py:219-248 (ELBO / ln Z estimators)
 Particles are a leading batch axis (the reference vmaps a per-particle function).  Gaussians
@@ -58,15 +59,15 @@ def initialize(dim, vdparams=None, nbridges=0, eps=0.01, gamma=10.0, eta=0.5, ng
         sn, apply_fun_sn = initialize_network(dim, emb_dim, nbridges, nn_arch,
                                               torch.Generator().manual_seed(seed), live, dtype)
         pt["sn"] = sn
-    elif mode == "MCD_U_a-lp-sna":   # mcdboundingmachine.py:67-83: network on z only
+    elif mode in ("MCD_U_a-lp-sna", "MCD_U_e-lp-sna"):   # mcdboundingmachine.py:67-83: network on z only
         sn, apply_fun_sn = initialize_network(dim, emb_dim, nbridges, nn_arch,
                                               torch.Generator().manual_seed(seed), live, dtype)
         pt["sn"] = sn
-    elif mode == "MCD_U_a-lp-sn":    # :84-102: network on (z, rho), rho_dim = dim
+    elif mode in ("MCD_U_a-lp-sn", "MCD_U_ea-lp-sn"):    # :84-102: network on (z, rho), rho_dim = dim
         sn, apply_fun_sn = initialize_network(dim, emb_dim, nbridges, nn_arch,
                                               torch.Generator().manual_seed(seed), live, dtype, rho_dim=dim)
         pt["sn"] = sn
-    elif mode in ("MCD_ULA", "MCD_U_a-lp"):
+    elif mode in ("MCD_ULA", "MCD_U_a-lp", "MCD_U_e-lp"):
         apply_fun_sn = None
     else:
         raise NotImplementedError("Mode not implemented.")
@@ -119,12 +120,16 @@ def _score(fn, z):
 
 
 # ---------------------------------------------------------------- the step bodies
-UD_MODES = ("MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn")
+UD_MODES = ("MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn", "MCD_U_e-lp", "MCD_U_e-lp-sna", "MCD_U_ea-lp-sn")
 
 
 def evolve_underdamped_lp_a(z, betas, params, rho0, xi, params_fixed, log_prob_model, traj=None):
     """mcd_under_lp_a.py:6-87 (use_sn / full_sn from the mode, mcd_utils.py:83-118).  rho0 [N,d], xi [K,N,d]."""
     dim, nbridges, mode, apply_fun_sn = params_fixed
+    if mode in ("MCD_U_e-lp", "MCD_U_e-lp-sna"):
+        return evolve_underdamped_lp_e(z, betas, params, rho0, xi, params_fixed, log_prob_model, traj)
+    if mode == "MCD_U_ea-lp-sn":
+        return evolve_underdamped_lp_ea(z, betas, params, rho0, xi, params_fixed, log_prob_model, traj)
     vd = params["vd"]
     use_sn, full_sn = mode != "MCD_U_a-lp", mode == "MCD_U_a-lp-sn"
     eps, gamma = params["eps"], params["gamma"]
@@ -158,6 +163,79 @@ def evolve_underdamped_lp_a(z, betas, params, rho0, xi, params_fixed, log_prob_m
         z, rho = z_new, rho_new
     w = w + normal_log_prob(rho, zero, one)              # :83-84
     return z, w
+
+
+def _ud_scan(z, betas, params, rho0, xi, nbridges, log_prob_model, kernels, traj):
+    """Shared scaffolding of the three underdamped scans (initial / final momentum terms, leapfrog); ``kernels(i, z, rho)``
+    returns (fk_mean, fk_scale, bk(rho_prime) -> (bk_mean, bk_scale)) exactly as the respective reference body forms them."""
+    vd = params["vd"]
+    eps = params["eps"]
+    zero, one = torch.zeros((), dtype=z.dtype), torch.ones((), dtype=z.dtype)
+
+    def gradU(x, beta):
+        U = lambda y: -1.0 * (beta * log_prob_model(y) + (1.0 - beta) * vd_log_prob(vd, y))
+        return _score(U, x)
+
+    rho = rho0
+    w = -normal_log_prob(rho, zero, one)
+    if traj is not None:
+        traj[-1] = (traj[-1], rho.detach().clone(), None)
+    for i in range(nbridges):
+        beta = betas[i]
+        fk_rho_mean, scale_f, bk = kernels(i, z, rho)
+        rho_prime = fk_rho_mean + scale_f * xi[i]
+        rho_pp = rho_prime - eps * gradU(z, beta) / 2.0
+        z_new = z + eps * rho_pp
+        rho_new = rho_pp - eps * gradU(z_new, beta) / 2.0
+        bk_rho_mean, scale_b = bk(rho_prime)
+        w = w + normal_log_prob(rho, bk_rho_mean, scale_b) - normal_log_prob(rho_prime, fk_rho_mean, scale_f)
+        if traj is not None:
+            traj[-1] = (traj[-1][0], traj[-1][1], rho_prime.detach().clone())
+            traj.append((z_new.detach().clone(), rho_new.detach().clone(), None))
+        z, rho = z_new, rho_new
+    w = w + normal_log_prob(rho, zero, one)
+    return z, w
+
+
+def evolve_underdamped_lp_e(z, betas, params, rho0, xi, params_fixed, log_prob_model, traj=None):
+    """mcd_under_lp_e.py:6-74: exact OU momentum refresh rho' ~ N(eta rho, 1 - eta^2); MCD_U_e-lp / MCD_U_e-lp-sna."""
+    dim, nbridges, mode, apply_fun_sn = params_fixed
+    use_sn = mode == "MCD_U_e-lp-sna"
+    eta = params["eta"]
+
+    def kernels(i, z_, rho):
+        fk_rho_mean = eta * rho                              # :27
+        scale = torch.sqrt(1.0 - eta ** 2)                   # :28
+
+        def bk(rho_prime):
+            m = eta * rho_prime                              # :39
+            if use_sn:
+                m = m + 2 * apply_fun_sn(params["sn"], z_, i) * (1.0 - eta)   # :41-43
+            return m, scale
+        return fk_rho_mean, scale, bk
+
+    return _ud_scan(z, betas, params, rho0, xi, nbridges, log_prob_model, kernels, traj)
+
+
+def evolve_underdamped_lp_ea(z, betas, params, rho0, xi, params_fixed, log_prob_model, traj=None):
+    """mcd_under_lp_ea.py:6-104 (MCD_U_ea-lp-sn: use_sn, full_sn): exact refresh forward, Euler-type backward kernel."""
+    dim, nbridges, mode, apply_fun_sn = params_fixed
+    eps, gamma = params["eps"], params["gamma"]
+
+    def kernels(i, z_, rho):
+        eta = torch.exp(-gamma * eps)                        # :28
+        eta_aux = gamma * eps                                # :29
+        scale = torch.sqrt(2.0 * eta_aux)                    # :31
+        fk_rho_mean = rho * eta                              # :32
+        scale_f = torch.sqrt(1.0 - eta ** 2)                 # :33
+
+        def bk(rho_prime):
+            inp = torch.cat([z_, rho_prime], dim=-1)         # :54
+            m = rho_prime * (1.0 - eta_aux) + 2 * eta_aux * apply_fun_sn(params["sn"], inp, i)   # :55-57
+            return m, scale
+        return fk_rho_mean, scale_f, bk
+
+    return _ud_scan(z, betas, params, rho0, xi, nbridges, log_prob_model, kernels, traj)
 
 
 def evolve(z, betas, params, xi, params_fixed, log_prob_model, eps_schedule=None, grad_clipping=False, traj=None):
@@ -296,6 +374,79 @@ def bm_compute_bound(seeds, params_flat, unflatten, params_fixed, log_prob):
     xi0 = torch.tensor(xi0_np, dtype=params_flat.dtype)
     z = vd_sample_rep(params["vd"], xi0)
     w = -vd_log_prob(params["vd"], z) + log_prob(z)
+    l = -1.0 * w
+    return l.mean(), (l, z)
+
+
+# ---------------------------------------------------------------- boundingmachine.py + ais_utils.py (UHA, nbridges >= 1)
+def uha_initialize(dim, vdparams=None, nbridges=1, lfsteps=1, eps=0.05, eta=0.5, mdparams=None, ngridb=32, mgridref_y=None,
+                   trainable=("eps", "eta"), init_sigma=1.0, dtype=torch.float32):
+    """boundingmachine.py:9-70 (boundmode "UHA", main.py:115-131): vd, eps, eta, md (momentum log-scales, momdist.py:9-11),
+    mgridref_y; params_fixed = (dim, nbridges, lfsteps)."""
+    pt, pn = {}, {}
+    (pt if "vd" in trainable else pn)["vd"] = vdparams if vdparams is not None else vd_initialize(dim, init_sigma, dtype)
+    for name, val in (("eps", eps), ("eta", eta)):
+        (pt if name in trainable else pn)[name] = torch.tensor(float(val), dtype=dtype)
+    (pt if "md" in trainable else pn)["md"] = mdparams if mdparams is not None else torch.zeros(dim, dtype=dtype)
+    if mgridref_y is not None:
+        ngridb = mgridref_y.shape[0] - 1
+    else:
+        ngridb = min(ngridb, nbridges)
+        mgridref_y = torch.ones(ngridb + 1, dtype=dtype)
+    pn["gridref_x"] = torch.linspace(0, 1, ngridb + 2, dtype=dtype)
+    pn["target_x"] = torch.linspace(0, 1, nbridges + 2, dtype=dtype)[1:-1]
+    (pt if "mgridref_y" in trainable else pn)["mgridref_y"] = mgridref_y
+    flat, unflatten = ravel_pytree((pt, pn), dtype)
+    return flat, unflatten, (dim, nbridges, lfsteps)
+
+
+def uha_evolve(z, betas, params, rho_noise0, xi, params_fixed, log_prob):
+    """ais_utils.py:7-69.  rho_noise0 [N,d], xi [K,N,d]: the N(0,1) draws of md.sample (momdist.py:14-22)."""
+    dim, nbridges, lfsteps = params_fixed
+    vd, eps, eta, mdp = params["vd"], params["eps"], params["eta"], params["md"]
+    zero = torch.zeros((), dtype=z.dtype)
+    md_scale = torch.exp(mdp)
+    md_log_prob = lambda r: normal_log_prob(r, zero, md_scale)            # momdist.py:25-29
+
+    def gradU(x, beta):                                                   # ais_utils.py:8-9
+        U = lambda y: -1.0 * (beta * log_prob(y) + (1.0 - beta) * vd_log_prob(vd, y))
+        return _score(U, x)
+
+    gradK = lambda r: _score(lambda y: -1.0 * md_log_prob(y), r)          # :28-29
+
+    rho = md_scale * rho_noise0                                           # :62 -> momdist.py:17-19
+    w = torch.zeros(z.shape[0], dtype=z.dtype)
+    for i in range(nbridges):                                             # :11-26
+        beta = betas[i]
+        rho_r = eta * rho + torch.sqrt(1.0 - eta ** 2) * (md_scale * xi[i])   # momdist.py:21
+        # leapfrog (:27-56)
+        r = rho_r - eps * gradU(z, beta) / 2.0
+        zz = z + eps * gradK(r)
+        for _ in range(lfsteps - 1):
+            r = r - eps * gradU(zz, beta)
+            zz = zz + eps * gradK(r)
+        r = r - eps * gradU(zz, beta) / 2.0
+        w = w + md_log_prob(r) - md_log_prob(rho_r)                       # :21
+        z, rho = zz, r
+    return z, w
+
+
+def uha_compute_bound(seeds, params_flat, unflatten, params_fixed, log_prob):
+    """boundingmachine.py:73-111 with nbridges >= 1 (the key chain is the one of the underdamped MCD operators:
+    one split for the initial momentum, one discarded, then two per bridge; ais_utils.py:61-66,15,22)."""
+    pt, pn = unflatten(params_flat)
+    params = {**pt, **_detach_tree(pn)}
+    dim, nbridges = params_fixed[0], params_fixed[1]
+    dtype = params_flat.dtype
+    xi0_np, rho0_np, xi_np = prng.particle_noise_ud(np.asarray(seeds), dim, nbridges)
+    xi0, rho0, xi = (torch.tensor(a, dtype=dtype) for a in (xi0_np, rho0_np, xi_np))
+    z = vd_sample_rep(params["vd"], xi0)
+    w = -vd_log_prob(params["vd"], z)
+    if nbridges >= 1:
+        betas = make_betas(params)
+        z, w_mom = uha_evolve(z, betas, params, rho0, xi, params_fixed, log_prob)
+        w = w + w_mom
+    w = w + log_prob(z)
     l = -1.0 * w
     return l.mean(), (l, z)
 

@@ -42,6 +42,12 @@ CONFIGS = {
                              gamma=2.0, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "mgridref_y")),
     "UDsna_funnel": dict(model="funnel", mode="MCD_U_a-lp-sna", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.04, sigma=1.0,
                          eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    "UDe_gmm": dict(model="gmm", mode="MCD_U_e-lp", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.05, sigma=1.0, eta=0.6,
+                    eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    "UDesna_funnel_dds": dict(model="funnel", mode="MCD_U_e-lp-sna", N=300, K=8, nn_arch="dds", emb_dim=20, eps=0.04, sigma=1.0,
+                              eta=0.5, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    "UDea_gmm": dict(model="gmm", mode="MCD_U_ea-lp-sn", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.05, sigma=1.0,
+                     gamma=5.0, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
     "UD_gmm": dict(model="gmm", mode="MCD_U_a-lp", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.05, sigma=1.0,
                    eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
 }
@@ -64,7 +70,7 @@ def oracle_problem(name, dtype=torch.float32, N=None, K=None):
     g = torch.Generator().manual_seed(7)
     vdp["mean"] = vdp["mean"] + 0.1 * torch.randn(dim, generator=g) + c.get("vd_mean", 0.0)  # non-trivial mean
     mgrid = 1.0 + 0.3 * torch.rand(min(32, c["K"]) + 1, generator=g)
-    pf, unf, fixed = OM.initialize(dim, vdparams=vdp, nbridges=c["K"], eps=c["eps"], gamma=c.get("gamma", 10.0), trainable=c["trainable"],
+    pf, unf, fixed = OM.initialize(dim, vdparams=vdp, nbridges=c["K"], eps=c["eps"], gamma=c.get("gamma", 10.0), eta=c.get("eta", 0.5), trainable=c["trainable"],
                                    emb_dim=c["emb_dim"], mode=c["mode"], nn_arch=c["nn_arch"], mgridref_y=mgrid,
                                    live=True)
     return c, log_prob, dim, pf.to(dtype), unf, fixed
@@ -83,7 +89,7 @@ def product_problem(name, pf_oracle, device="cuda", N=None, K=None):
     out = PH.load_model(c["model"], device=device)
     target, dim = out[0], out[1]
     mgrid = torch.ones(min(32, c["K"]) + 1)
-    pf, unf, fixed = PM.initialize(dim, vdparams=PV.initialize(dim, device=device), nbridges=c["K"], eps=c["eps"], gamma=c.get("gamma", 10.0),
+    pf, unf, fixed = PM.initialize(dim, vdparams=PV.initialize(dim, device=device), nbridges=c["K"], eps=c["eps"], gamma=c.get("gamma", 10.0), eta=c.get("eta", 0.5),
                                    trainable=c["trainable"], emb_dim=c["emb_dim"], mode=c["mode"],
                                    nn_arch=c["nn_arch"], mgridref_y=mgrid, device=device)
     assert pf.numel() == pf_oracle.numel(), (pf.numel(), pf_oracle.numel())

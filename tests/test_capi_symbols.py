@@ -40,7 +40,7 @@ def test_no_cpu_fallback():
 def test_unknown_mode_and_target_raise():
     from cmcd_b200 import mcdboundingmachine as M, model_handler as H, mcd_utils
     with pytest.raises(NotImplementedError):
-        M.initialize(2, nbridges=4, mode="MCD_U_e-lp", device="cpu")   # not built: the other underdamped variants (mcd_under_lp_e / _ea)
+        M.initialize(2, nbridges=4, mode="MCD_DNF", device="cpu")   # not built (broken at the reference HEAD)
     for mode in ("MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn"):          # built: the evolve_underdamped_lp_a family
         pf, unf, fixed = M.initialize(2, nbridges=4, mode=mode, emb_dim=6, nn_arch="geffner", device="cpu")
         assert fixed[2] == mode and (fixed[3] is None) == (mode == "MCD_U_a-lp")

@@ -82,4 +82,4 @@ def test_empty_batch_and_bad_arguments():
         l, (lv, z) = PM.compute_bound(torch.zeros(0, dtype=torch.int32), pf, unf, fixed, target, **kw)
     assert lv.numel() == 0 and z.shape == (0, 2)
     with pytest.raises(NotImplementedError):
-        PM.compute_bound(torch.arange(1, 5), pf, unf, (fixed[0], fixed[1], "MCD_U_ea-lp-sn", fixed[3]), target, **kw)
+        PM.compute_bound(torch.arange(1, 5), pf, unf, (fixed[0], fixed[1], "MCD_DNF", fixed[3]), target, **kw)

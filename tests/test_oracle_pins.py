@@ -109,14 +109,30 @@ def test_ldvi_zero_drift_equals_no_network():
     torch.testing.assert_close(out["MCD_U_a-lp-sna"], out["MCD_U_a-lp"], rtol=0, atol=0)
 
 
-@pytest.mark.parametrize("mode", ["MCD_U_a-lp", "MCD_U_a-lp-sn"])
+def test_underdamped_variants_agree_where_the_reference_formulas_coincide():
+    # lp_ea differs from lp_a only in the forward kernel (exact OU refresh instead of its first-order expansion):
+    # as gamma*eps -> 0 both refreshes coincide to O((gamma eps)^2) -- the two restatements must converge at that rate
+    lp, dim = OH.load_model("gmm", dtype=torch.float64)
+    seeds = seeds_for(200)
+    gaps = []
+    for gamma in (0.4, 0.2):
+        out = {}
+        for mode in ("MCD_U_a-lp-sn", "MCD_U_ea-lp-sn"):
+            pf, unf, fixed = OM.initialize(dim, nbridges=4, eps=0.05, gamma=gamma, trainable=("vd",), emb_dim=8, mode=mode,
+                                           nn_arch="geffner", live=True, dtype=torch.float64)
+            out[mode] = OM.compute_bound(seeds, pf, unf, fixed, lp)[1][1]   # z_K depends on the refresh only
+        gaps.append((out["MCD_U_a-lp-sn"] - out["MCD_U_ea-lp-sn"]).abs().max().item())
+    assert gaps[1] < gaps[0] / 2.5 and gaps[0] < 1e-2, gaps
+
+
+@pytest.mark.parametrize("mode", ["MCD_U_a-lp", "MCD_U_a-lp-sn", "MCD_U_e-lp-sna", "MCD_U_ea-lp-sn"])
 def test_ldvi_weights_are_unbiased(mode):
     """E[exp(w)] = Z = 1 for ANY parameters: the momentum refresh is a proper Markov kernel, the leapfrog step a
     volume-preserving bijection, the backward kernel a normalised density (Geffner & Domke 2021, eq. 9).  Pins the
     operator restatement (signs of the log-ratio, which momentum enters which kernel) without a running reference."""
     lp, dim = OH.load_model("gmm", dtype=torch.float64)
     n = 40000
-    pf, unf, fixed = OM.initialize(dim, vdparams=OM.vd_initialize(dim, 2.0, torch.float64), nbridges=4, eps=0.2, gamma=3.0,
+    pf, unf, fixed = OM.initialize(dim, vdparams=OM.vd_initialize(dim, 2.0, torch.float64), nbridges=4, eps=0.2, gamma=3.0, eta=0.4,
                                    trainable=("vd",), emb_dim=8, mode=mode, nn_arch="geffner", live=True, dtype=torch.float64)
     with torch.no_grad():
         l = OM.compute_bound(np.arange(1, n + 1, dtype=np.int32), pf, unf, fixed, lp)[1][0]
