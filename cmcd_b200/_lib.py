@@ -11,7 +11,8 @@ LIB_PATH = os.environ.get("CMCD_B200_LIB") or os.path.join(_HERE, "libcmcd_b200.
 MODE = {"MCD_ULA": 0, "MCD_ULA_sn": 1, "MCD_CAIS_sn": 2, "MCD_CAIS_var_sn": 3,
         "MCD_U_a-lp": 4, "MCD_U_a-lp-sna": 5, "MCD_U_a-lp-sn": 6,       # evolve_underdamped_lp_a ("LDVI")
         "MCD_U_e-lp": 4, "MCD_U_e-lp-sna": 5,                           # evolve_underdamped_lp_e
-        "MCD_U_ea-lp-sn": 6}                                            # evolve_underdamped_lp_ea
+        "MCD_U_ea-lp-sn": 6,                                            # evolve_underdamped_lp_ea
+        "UHA": 7}                                                       # boundingmachine + ais_utils (config.boundmode "UHA")
 UD_MODES = ("MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn", "MCD_U_e-lp", "MCD_U_e-lp-sna", "MCD_U_ea-lp-sn")
 TARGET = {"gmm": 0, "many_gmm": 1, "funnel": 2, "lgcp": 3}
 ARCH = {None: 0, "none": 0, "geffner": 1, "dds": 2}
@@ -38,7 +39,7 @@ class CmcdTarget(C.Structure):
 
 class CmcdBridgeDesc(C.Structure):
     _fields_ = [("mode", C.c_int32), ("dim", C.c_int32), ("nbridges", C.c_int32), ("n_particles", C.c_int32),
-                ("clip_target", C.c_float), ("clip_q", C.c_float)]
+                ("clip_target", C.c_float), ("clip_q", C.c_float), ("lfsteps", C.c_int32)]
 
 
 EXPORTS = {

@@ -34,6 +34,10 @@ int launch_bridge_ud_bwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sm
                          float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
                          const cmcd_net_grad* g_net, void* ws, size_t ws_bytes);
 size_t bridge_ud_bwd_workspace_bytes(int mode, int D, int K, int HP, int arch, int num_sms);
+int launch_bridge_uha_fwd(const BridgeArgs& a, int D, int lfsteps, cudaStream_t st, int num_sms);
+int launch_bridge_uha_bwd(const BridgeArgs& a, int D, int lfsteps, cudaStream_t st, int num_sms, const float* cot_negw,
+                          float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps, void* ws, size_t ws_bytes);
+size_t bridge_uha_bwd_workspace_bytes(int D, int K, int num_sms);
 int launch_loss_stats(cudaStream_t st, const float* negw, long long n, float* out4);
 int launch_batched_elbo_lnz(cudaStream_t st, const float* losses, int batches, int n, float* elbo, float* lnz);
 int launch_threefry(cudaStream_t st, const uint32_t* key2, const uint32_t* x0, const uint32_t* x1, long long n, uint32_t* y0, uint32_t* y1);
@@ -64,12 +68,12 @@ static int num_sms() {
 }
 
 static bool is_ud(int mode) { return mode >= CMCD_MODE_UD_NONE && mode <= CMCD_MODE_UD_NET_ZRHO; }
-static bool mode_uses_net(int mode) { return mode != CMCD_MODE_ULA && mode != CMCD_MODE_UD_NONE; }
+static bool mode_uses_net(int mode) { return mode != CMCD_MODE_ULA && mode != CMCD_MODE_UD_NONE && mode != CMCD_MODE_UHA; }
 
 static int build_args(const cmcd_bridge_desc* d, const int32_t* seeds, const float* vd_mean, const float* vd_logdiag,
                       const float* betas, const float* eps, const cmcd_net* net, const cmcd_target* tg, BridgeArgs& a) {
     if (!d || !tg) { set_error("null descriptor"); return 2; }
-    if (d->mode < CMCD_MODE_ULA || d->mode > CMCD_MODE_UD_NET_ZRHO) { set_error("Mode not implemented."); return 2; }
+    if (d->mode < CMCD_MODE_ULA || d->mode > CMCD_MODE_UHA) { set_error("Mode not implemented."); return 2; }
     if (d->nbridges < 0 || d->n_particles < 0 || d->dim < 1) { set_error("bad sizes N=%d K=%d d=%d", d->n_particles, d->nbridges, d->dim); return 2; }
     std::memset(&a, 0, sizeof(a));
     a.mode = d->mode; a.K = d->nbridges; a.N = d->n_particles;
@@ -104,7 +108,7 @@ static int build_args(const cmcd_bridge_desc* d, const int32_t* seeds, const flo
             break;
         case CMCD_TARGET_LGCP:
             if (!tg->lgcp_kinv || !tg->lgcp_counts) { set_error("lgcp needs kinv and counts"); return 2; }
-            if (is_ud(d->mode)) { set_error("the underdamped modes have no wide (lgcp) path"); return 2; }
+            if (is_ud(d->mode) || d->mode == CMCD_MODE_UHA) { set_error("the underdamped modes have no wide (lgcp) path"); return 2; }
             break;
         default: set_error("target kind %d not in the registry", tg->kind); return 2;
     }
@@ -140,6 +144,8 @@ int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
     if (target->kind == CMCD_TARGET_LGCP)
         return launch_wide_fwd(a, target, desc->dim, (cudaStream_t)stream, sms, workspace, workspace_bytes);
     if (is_ud(desc->mode)) return launch_bridge_ud_fwd(a, desc->dim, (cudaStream_t)stream, sms);
+    if (desc->mode == CMCD_MODE_UHA)
+        return launch_bridge_uha_fwd(a, desc->dim, desc->lfsteps > 0 ? desc->lfsteps : 1, (cudaStream_t)stream, sms);
     // hidden width 64: tcgen05 tiles; other widths: FP32 FMA kernel.  CMCD_DISABLE_TC=1 forces the FP32 kernel (A/B runs).
     if (fwd_tc_supported(a, desc->dim) && !std::getenv("CMCD_DISABLE_TC"))
         return launch_bridge_fwd_tc(a, desc->dim, (cudaStream_t)stream, sms);
@@ -149,6 +155,7 @@ int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
 size_t cmcd_bridge_bwd_workspace_bytes(const cmcd_bridge_desc* desc, const cmcd_net* net) {
     const int sms = num_sms() > 0 ? num_sms() : 148;
     const int arch = (net && mode_uses_net(desc->mode)) ? net->arch : CMCD_ARCH_NONE;
+    if (desc->mode == CMCD_MODE_UHA) return bridge_uha_bwd_workspace_bytes(desc->dim, desc->nbridges, sms);
     if (is_ud(desc->mode))
         return bridge_ud_bwd_workspace_bytes(desc->mode, desc->dim, desc->nbridges, net ? net->hidden_pad : 0, arch, sms);
     if (desc->dim > 64)   // wide path (lgcp, d = 1600): [N x d] / [N x hidden] state + split-K partials
@@ -176,6 +183,9 @@ int cmcd_bridge_bwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
     if (target->kind == CMCD_TARGET_LGCP)
         return launch_wide_bwd(a, target, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
                                g_eps, g_net, workspace, workspace_bytes);
+    if (desc->mode == CMCD_MODE_UHA)
+        return launch_bridge_uha_bwd(a, desc->dim, desc->lfsteps > 0 ? desc->lfsteps : 1, (cudaStream_t)stream, sms, cot_negw,
+                                     g_vd_mean, g_vd_logdiag, g_betas, g_eps, workspace, workspace_bytes);
     if (is_ud(desc->mode))
         return launch_bridge_ud_bwd(a, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
                                     g_eps, g_net, workspace, workspace_bytes);
@@ -214,6 +224,7 @@ int cmcd_target_eval(const cmcd_target* target, int32_t dim, void* stream, const
     cmcd_bridge_desc d;
     d.mode = CMCD_MODE_ULA; d.dim = dim; d.nbridges = 0; d.n_particles = (int32_t)n;
     d.clip_target = d.clip_q = INFINITY;
+    d.lfsteps = 0;
     BridgeArgs a;
     if (int rc = build_args(&d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, target, a)) return rc;
     if (target->kind == CMCD_TARGET_LGCP) { set_error("target_eval: lgcp is served by the wide path"); return 2; }

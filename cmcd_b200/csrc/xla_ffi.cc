@@ -52,6 +52,7 @@ void fill(const Static& s, const S32& seeds, const F32& vd_mean, const F32& beta
     d.n_particles = (int32_t)seeds.element_count();
     d.clip_target = s.clip_target;
     d.clip_q = s.clip_q;
+    d.lfsteps = 0;
     net = cmcd_net{};
     net.arch = s.arch;
     net.hidden = s.hidden;

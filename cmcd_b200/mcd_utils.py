@@ -74,8 +74,9 @@ def _clips(mode, grad_clipping):
     return (1e2, 1e2) if mode == "MCD_CAIS_var_sn" else (1e3, inf)
 
 
-def _make_desc(mode, dim, nbridges, n, clip_t, clip_q):
+def _make_desc(mode, dim, nbridges, n, clip_t, clip_q, lfsteps=0):
     d = CmcdBridgeDesc()
+    d.lfsteps = lfsteps
     d.mode, d.dim, d.nbridges, d.n_particles = MODE[mode], dim, nbridges, n
     d.clip_target, d.clip_q = clip_t, clip_q
     return d
@@ -100,7 +101,8 @@ class _Bridge(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, seeds, vd_mean, vd_logdiag, betas, eps, *net_t):
-        mode, dim, K, apply_fun, target, clip_t, clip_q, need_grad = cfg
+        mode, dim, K, apply_fun, target, clip_t, clip_q, need_grad = cfg[:8]
+        lfsteps = cfg[8] if len(cfg) > 8 else 0
         _lib.require_cuda(seeds, vd_mean)
         dev = vd_mean.device
         n = seeds.numel()
@@ -111,9 +113,9 @@ class _Bridge(torch.autograd.Function):
             tabs = {k: f32(t) for k, t in zip(_NET_KEYS, net_t)}
         negw = torch.empty(n, device=dev, dtype=torch.float32)
         z = torch.empty(n, dim, device=dev, dtype=torch.float32)
-        rows = 3 * dim if mode in UD_MODES else dim   # underdamped: (z_j, rho_j, rho'_j) per node
+        rows = 3 * dim if (mode in UD_MODES or mode == "UHA") else dim   # underdamped: (z_j, rho_j, rho'_j) per node
         traj = torch.empty((K + 1, rows, n), device=dev, dtype=torch.float32) if need_grad else None
-        desc, net, tg = _make_desc(mode, dim, K, n, clip_t, clip_q), _make_net(apply_fun, tabs, K), target.desc()
+        desc, net, tg = _make_desc(mode, dim, K, n, clip_t, clip_q, lfsteps), _make_net(apply_fun, tabs, K), target.desc()
         L = _lib.lib()
         ws_bytes = L.cmcd_bridge_fwd_workspace_bytes(desc, net, tg)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
@@ -128,7 +130,8 @@ class _Bridge(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, cot_negw, _cot_z):
-        mode, dim, K, apply_fun, target, clip_t, clip_q, need_grad = ctx.cfg
+        mode, dim, K, apply_fun, target, clip_t, clip_q, need_grad = ctx.cfg[:8]
+        lfsteps = ctx.cfg[8] if len(ctx.cfg) > 8 else 0
         seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj = ctx.saved
         if traj is None:
             raise RuntimeError("bridge was run without a trajectory; cannot differentiate")
@@ -137,8 +140,9 @@ class _Bridge(torch.autograd.Function):
         cot = cot_negw.detach().to(torch.float32).contiguous()
         g_mean, g_logdiag = torch.zeros_like(vd_mean), torch.zeros_like(vd_logdiag)
         g_betas = torch.zeros(max(K, 1), device=dev)
-        g_eps = torch.zeros_like(eps) if mode in UD_MODES else torch.zeros(max(K, 1), device=dev)
-        desc, net, tg = _make_desc(mode, dim, K, n, clip_t, clip_q), _make_net(apply_fun, tabs, K), target.desc()
+        wide_rows = mode in UD_MODES or mode == "UHA"   # eps carries several coefficient rows
+        g_eps = torch.zeros_like(eps) if wide_rows else torch.zeros(max(K, 1), device=dev)
+        desc, net, tg = _make_desc(mode, dim, K, n, clip_t, clip_q, lfsteps), _make_net(apply_fun, tabs, K), target.desc()
         gnet, gt = CmcdNetGrad(), {}
         if apply_fun is not None:
             for k in _NET_KEYS:
@@ -155,7 +159,7 @@ class _Bridge(torch.autograd.Function):
                                          _lib.ptr(g_eps), gnet, _lib.ptr(ws), ws_bytes))
         _lib.count_launches(2)  # adjoint kernel + partial-gradient reduce kernel
         net_grads = tuple(gt.get(k) for k in _NET_KEYS) if apply_fun is not None else ()
-        if mode in UD_MODES:
+        if wide_rows:
             return (None, None, g_mean, g_logdiag, g_betas[:K] if K else None, g_eps if K else None, *net_grads)
         return (None, None, g_mean, g_logdiag, g_betas[:K] if K else None, g_eps[:K] if K else None, *net_grads)
 
@@ -190,6 +194,22 @@ def bridge(seeds, params, betas, params_fixed, log_prob_model, eps_schedule=None
     cfg = (mode, dim, nbridges, apply_fun if uses_net else None, log_prob_model, clip_t, clip_q, need_grad)
     seeds = torch.as_tensor(seeds, dtype=torch.int32, device=dev).contiguous()
     return _Bridge.apply(cfg, seeds, vd["mean"], vd["logdiag"], betas, eps, *net_t)
+
+
+def uha_bridge(seeds, params, betas, params_fixed, log_prob_model):
+    """Fused per-particle program of boundingmachine.compute_log_elbo (boundingmachine.py:73-104) for nbridges >= 1 =
+    ais_utils.evolve (ais_utils.py:7-69).  Returns (-w[N], z_K[N,d]); differentiable w.r.t. vd, eps, eta, md, betas."""
+    dim, nbridges, lfsteps = params_fixed
+    vd = params["vd"]
+    dev = vd["mean"].device
+    eps, eta = params["eps"], params["eta"]
+    one = torch.ones(nbridges, device=dev, dtype=torch.float32)
+    rows = torch.stack([eps * one, eta * one, torch.sqrt(1.0 - eta ** 2) * one])   # momdist.py:21
+    scales = torch.stack([vd["logdiag"], params["md"]])                            # [2, d]: q log-scales, momentum log-scales
+    need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (vd["mean"], scales, betas, rows))
+    cfg = ("UHA", dim, nbridges, None, log_prob_model, float("inf"), float("inf"), need_grad, int(lfsteps))
+    seeds = torch.as_tensor(seeds, dtype=torch.int32, device=dev).contiguous()
+    return _Bridge.apply(cfg, seeds, vd["mean"], scales, betas, rows)
 
 
 def evolve(z, betas, params, rng_key_gen, params_fixed, log_prob_model, eps_schedule=None, grad_clipping=False):

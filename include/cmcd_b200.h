@@ -32,9 +32,14 @@ extern "C" {
  *                   forms the rows from (eps, gamma, eta) and chains the cotangents back;
  *     traj        = [K+1][3 dim][N] = (z_j, rho_j, rho'_j) per node;
  *     cmcd_net    U1 / U2 = [in][HP], U3 = [in][dim] with in = dim (NET_Z) or 2 dim (NET_ZRHO);
- *     clip_target / clip_q are ignored (these operators take no grad_clipping). */
+ *     clip_target / clip_q are ignored (these operators take no grad_clipping).
+ * 7: UHA -- boundmode "UHA" (main.py:115-133): boundingmachine.compute_log_elbo (boundingmachine.py:73-111) over
+ *   ais_utils.evolve (ais_utils.py:7-69) with the diagonal momentum distribution of momdist.py; no score network.
+ *     eps / g_eps = [3][K] = rows (eps, a, s): momentum refresh rho_r = a rho + s exp(md) xi (a = eta, s = sqrt(1 - eta^2));
+ *     vd_logdiag / g_vd_logdiag = [2][dim] = (q log-scales, md = momentum log-scales, momdist.py:9-11);
+ *     desc.lfsteps = leapfrog steps per bridge (1..8, configs/base.py:83); traj = [K+1][3 dim][N] = (z_j, rho_j, rho_r_j). */
 enum { CMCD_MODE_ULA = 0, CMCD_MODE_ULA_SN = 1, CMCD_MODE_CAIS_SN = 2, CMCD_MODE_CAIS_VAR_SN = 3,
-       CMCD_MODE_UD_NONE = 4, CMCD_MODE_UD_NET_Z = 5, CMCD_MODE_UD_NET_ZRHO = 6 };
+       CMCD_MODE_UD_NONE = 4, CMCD_MODE_UD_NET_Z = 5, CMCD_MODE_UD_NET_ZRHO = 6, CMCD_MODE_UHA = 7 };
 /* target registry -- model_handler.load_model (model_handler.py:30-43) */
 enum { CMCD_TARGET_GMM = 0, CMCD_TARGET_MANY_GMM = 1, CMCD_TARGET_FUNNEL = 2, CMCD_TARGET_LGCP = 3 };
 /* drift network -- nn.initialize_network (nn.py:21-39) */
@@ -102,6 +107,7 @@ typedef struct cmcd_bridge_desc {
     int32_t n_particles; /* N (this rank's shard) */
     float clip_target;   /* grad_clipping: clip on the target score (1e3 KL, 1e2 log-var; +inf = off) */
     float clip_q;        /* clip on the q score (log-var mode only, mcd_cais_var.py:33-40; +inf = off) */
+    int32_t lfsteps;     /* CMCD_MODE_UHA only: leapfrog steps per bridge (params_fixed[2], boundingmachine.py:66); 0 reads as 1 */
 } cmcd_bridge_desc;
 
 const char* cmcd_last_error(void);

@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from helpers import oracle_problem, seeds_for  # noqa: E402
+from helpers import UHA_CONFIGS, oracle_problem, seeds_for, uha_oracle_problem  # noqa: E402
 from oracle import mcdboundingmachine as OM  # noqa: E402
 
 # name -> particles in the fixture (kept small: the whole directory stays well under 1 MB)
@@ -76,6 +76,26 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"bridge_{name}.npz"), seeds=seeds, params_flat=pf.numpy().astype(np.float32),
                             loss=np.float64(loss.item()), l=l.numpy(), z=z.numpy(), grad=g.numpy().astype(np.float32), grad_fp32_floor=np.array(floor))
         print(f"{name}: N={n} P={pf.numel()} loss={loss.item():.6f}")
+    # UHA (boundingmachine.py + ais_utils.py): uha_<config>.npz, same fields
+    from cmcd_b200.pytree import tree_leaves
+    for name in UHA_CONFIGS:
+        n = 64
+        c, lp, dim, pf, unf, fixed = uha_oracle_problem(name, torch.float64, N=n)
+        seeds = seeds_for(n)
+        g, (l, z) = OM.grad_and_loss(OM.uha_compute_bound, seeds, pf, unf, fixed, lp)
+        _, lp32, _, pf32, unf32, fixed32 = uha_oracle_problem(name, torch.float32, N=n)
+        g32, _ = OM.grad_and_loss(OM.uha_compute_bound, seeds, pf32, unf32, fixed32, lp32)
+        floor = []
+        for a_, b_ in zip(tree_leaves(unf32(g32)), tree_leaves(unf(g))):
+            a_, b_ = a_.double().reshape(-1), b_.double().reshape(-1)
+            if b_.numel() == 0:
+                continue
+            sc = b_.abs().max().item()
+            floor.append((a_ - b_).abs().max().item() / sc if sc > 0 else (a_ - b_).abs().max().item())
+        np.savez_compressed(os.path.join(HERE, f"uha_{name}.npz"), seeds=seeds, params_flat=pf.numpy().astype(np.float32),
+                            loss=np.float64(l.mean().item()), l=l.numpy(), z=z.numpy(), grad=g.numpy().astype(np.float32),
+                            grad_fp32_floor=np.array(floor))
+        print(f"{name}: N={n} P={pf.numel()} loss={l.mean().item():.6f}")
 
 
 if __name__ == "__main__":

@@ -100,3 +100,45 @@ def rel_err(a, b, floor=1.0):
     """|a-b| / max(|b|, floor) elementwise (numpy)."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+# ---------------------------------------------------------------- UHA (boundingmachine.py + ais_utils.py, boundmode "UHA")
+UHA_CONFIGS = {
+    "UHA_gmm": dict(model="gmm", N=300, K=8, lfsteps=1, eps=0.1, eta=0.5, sigma=1.0),
+    "UHA_funnel_lf3": dict(model="funnel", N=300, K=6, lfsteps=3, eps=0.05, eta=0.7, sigma=1.0),
+    "UHA_manygmm_lf2": dict(model="many_gmm", N=300, K=16, lfsteps=2, eps=0.3, eta=0.3, sigma=15.0),
+}
+UHA_TRAINABLE = ("eps", "eta", "vd", "md", "mgridref_y")
+
+
+def uha_oracle_problem(name, dtype=torch.float32, N=None, K=None):
+    c = dict(UHA_CONFIGS[name])
+    if N:
+        c["N"] = N
+    if K:
+        c["K"] = K
+    log_prob, dim = OH.load_model(c["model"], dtype=dtype)
+    g = torch.Generator().manual_seed(11)
+    vdp = OM.vd_initialize(dim, c["sigma"])
+    vdp["mean"] = vdp["mean"] + 0.1 * torch.randn(dim, generator=g)
+    md = 0.2 * torch.randn(dim, generator=g)                       # non-trivial momentum scales
+    mgrid = 1.0 + 0.3 * torch.rand(min(32, c["K"]) + 1, generator=g)
+    pf, unf, fixed = OM.uha_initialize(dim, vdparams=vdp, nbridges=c["K"], lfsteps=c["lfsteps"], eps=c["eps"], eta=c["eta"],
+                                       mdparams=md, mgridref_y=mgrid, trainable=UHA_TRAINABLE)
+    return c, log_prob, dim, pf.to(dtype), unf, fixed
+
+
+def uha_product_problem(name, pf_oracle, device="cuda", N=None, K=None):
+    from cmcd_b200 import boundingmachine as PB
+    from cmcd_b200 import model_handler as PH
+    c = dict(UHA_CONFIGS[name])
+    if N:
+        c["N"] = N
+    if K:
+        c["K"] = K
+    out = PH.load_model(c["model"], device=device)
+    target, dim = out[0], out[1]
+    pf, unf, fixed = PB.initialize(dim, nbridges=c["K"], lfsteps=c["lfsteps"], eps=c["eps"], eta=c["eta"],
+                                   mgridref_y=torch.ones(min(32, c["K"]) + 1), trainable=UHA_TRAINABLE, device=device)
+    assert pf.numel() == pf_oracle.numel(), (pf.numel(), pf_oracle.numel())
+    return c, target, dim, pf_oracle.to(torch.float32).to(device), unf, fixed

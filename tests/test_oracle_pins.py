@@ -151,3 +151,44 @@ def test_ldvi_grad_matches_finite_difference_fp64():
         e[idx] = 1e-6
         fd = (OM.compute_bound(seeds, pf + e, unf, fixed, lp)[0] - OM.compute_bound(seeds, pf - e, unf, fixed, lp)[0]) / 2e-6
         assert abs(fd.item() - g[idx].item()) < 1e-6 * max(1, abs(g[idx].item())), (idx, fd.item(), g[idx].item())
+
+
+# ---------------------------------------------------------------- UHA (boundingmachine.py + ais_utils.py)
+@pytest.mark.parametrize("lfsteps", [1, 3])
+def test_uha_weights_are_unbiased(lfsteps):
+    """E[exp(w)] = 1 for any eps / eta / md: the refresh leaves N(0, sigma_m^2) invariant-in-law per step and the leapfrog
+    is a volume-preserving bijection (Geffner & Domke 2021, UHA).  Pins the restatement of ais_utils.evolve."""
+    lp, dim = OH.load_model("gmm", dtype=torch.float64)
+    n = 40000
+    pf, unf, fixed = OM.uha_initialize(dim, vdparams=OM.vd_initialize(dim, 2.0, torch.float64), nbridges=4, lfsteps=lfsteps,
+                                       eps=0.2, eta=0.4, mdparams=torch.tensor([0.2, -0.1], dtype=torch.float64),
+                                       trainable=("vd",), dtype=torch.float64)
+    with torch.no_grad():
+        l = OM.uha_compute_bound(np.arange(1, n + 1, dtype=np.int32), pf, unf, fixed, lp)[1][0]
+    wts = torch.exp(-l)
+    se = wts.std().item() / math.sqrt(n)
+    assert abs(wts.mean().item() - 1.0) < 4 * se + 1e-3, (wts.mean().item(), se)
+
+
+def test_uha_grad_matches_finite_difference_fp64():
+    lp, dim = OH.load_model("funnel", dtype=torch.float64)
+    pf, unf, fixed = OM.uha_initialize(dim, nbridges=3, lfsteps=2, eps=0.05, eta=0.4, mdparams=0.1 * torch.ones(dim, dtype=torch.float64),
+                                       trainable=("eps", "eta", "vd", "md", "mgridref_y"), dtype=torch.float64)
+    seeds = seeds_for(16)
+    g, _ = OM.grad_and_loss(OM.uha_compute_bound, seeds, pf, unf, fixed, lp)
+    rng = np.random.default_rng(2)
+    for idx in rng.choice(np.nonzero(g.numpy())[0], 8, replace=False):
+        e = torch.zeros_like(pf)
+        e[idx] = 1e-6
+        fd = (OM.uha_compute_bound(seeds, pf + e, unf, fixed, lp)[0] - OM.uha_compute_bound(seeds, pf - e, unf, fixed, lp)[0]) / 2e-6
+        assert abs(fd.item() - g[idx].item()) < 2e-6 * max(1, abs(g[idx].item())), (idx, fd.item(), g[idx].item())
+
+
+def test_uha_k0_equals_mfvi():
+    lp, dim = OH.load_model("funnel")
+    seeds = seeds_for(50)
+    pf, unf, fixed = OM.uha_initialize(dim, nbridges=0, trainable=("vd",))
+    a = OM.uha_compute_bound(seeds, pf, unf, fixed, lp)[1][0]
+    pf2, unf2, fixed2 = OM.bm_initialize(dim)
+    b = OM.bm_compute_bound(seeds, pf2, unf2, fixed2, lp)[1][0]
+    torch.testing.assert_close(a, b, rtol=0, atol=0)
