@@ -14,7 +14,7 @@ MODE = {"MCD_ULA": 0, "MCD_ULA_sn": 1, "MCD_CAIS_sn": 2, "MCD_CAIS_var_sn": 3,
         "MCD_U_ea-lp-sn": 6,                                            # evolve_underdamped_lp_ea
         "UHA": 7}                                                       # boundingmachine + ais_utils (config.boundmode "UHA")
 UD_MODES = ("MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn", "MCD_U_e-lp", "MCD_U_e-lp-sna", "MCD_U_ea-lp-sn")
-TARGET = {"gmm": 0, "many_gmm": 1, "funnel": 2, "lgcp": 3}
+TARGET = {"gmm": 0, "many_gmm": 1, "funnel": 2, "lgcp": 3, "callback": 4}
 ARCH = {None: 0, "none": 0, "geffner": 1, "dds": 2}
 MIX_STRIDE = 6
 
@@ -34,7 +34,13 @@ class CmcdNetGrad(C.Structure):
 class CmcdTarget(C.Structure):
     _fields_ = [("kind", C.c_int32), ("ncomp", C.c_int32), ("scale", C.c_float), ("invalid_below", C.c_float),
                 ("mix", _fp), ("lgcp_kinv", _fp), ("lgcp_linv", _fp), ("lgcp_counts", _fp),
-                ("lgcp_mu0", C.c_float), ("lgcp_log_norm", C.c_float), ("lgcp_bin_area", C.c_float)]
+                ("lgcp_mu0", C.c_float), ("lgcp_log_norm", C.c_float), ("lgcp_bin_area", C.c_float),
+                ("eval", C.c_void_p), ("user", C.c_void_p)]
+
+
+# cmcd_target_fn (include/cmcd_b200.h): int f(user, stream, x, n, dim, v, out_logp, out_score, out_hvp)
+TARGET_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                        C.c_void_p, C.c_void_p)
 
 
 class CmcdBridgeDesc(C.Structure):
@@ -51,6 +57,7 @@ EXPORTS = {
     "cmcd_bridge_fwd": (C.c_int, [C.POINTER(CmcdBridgeDesc), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNet),
                                   C.POINTER(CmcdTarget), _fp, _fp, _fp, _fp, C.c_size_t]),
     "cmcd_bridge_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(CmcdBridgeDesc), C.POINTER(CmcdNet)]),
+    "cmcd_bridge_bwd_workspace_bytes_for_target": (C.c_size_t, [C.POINTER(CmcdBridgeDesc), C.POINTER(CmcdNet), C.POINTER(CmcdTarget)]),
     "cmcd_bridge_bwd": (C.c_int, [C.POINTER(CmcdBridgeDesc), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNet),
                                   C.POINTER(CmcdTarget), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNetGrad),
                                   _fp, C.c_size_t]),

@@ -110,6 +110,10 @@ static int build_args(const cmcd_bridge_desc* d, const int32_t* seeds, const flo
             if (!tg->lgcp_kinv || !tg->lgcp_counts) { set_error("lgcp needs kinv and counts"); return 2; }
             if (is_ud(d->mode) || d->mode == CMCD_MODE_UHA) { set_error("the underdamped modes have no wide (lgcp) path"); return 2; }
             break;
+        case CMCD_TARGET_CALLBACK:
+            if (!tg->eval) { set_error("callback target needs an eval function"); return 2; }
+            if (d->mode > CMCD_MODE_CAIS_VAR_SN) { set_error("callback targets are served for the overdamped modes (0..3)"); return 2; }
+            break;
         default: set_error("target kind %d not in the registry", tg->kind); return 2;
     }
     return 0;
@@ -126,7 +130,7 @@ int cmcd_version(void) { return 100; }
 int cmcd_num_sms(void) { return num_sms(); }
 
 size_t cmcd_bridge_fwd_workspace_bytes(const cmcd_bridge_desc* desc, const cmcd_net* net, const cmcd_target* target) {
-    if (!desc || !target || target->kind != CMCD_TARGET_LGCP) return 0;
+    if (!desc || !target || (target->kind != CMCD_TARGET_LGCP && target->kind != CMCD_TARGET_CALLBACK)) return 0;
     const bool uses_net = net && net->arch != CMCD_ARCH_NONE && mode_uses_net(desc->mode) && desc->nbridges >= 1;
     return wide_fwd_workspace_bytes(desc->n_particles, desc->dim, uses_net ? net->hidden_pad : 0);
 }
@@ -141,7 +145,7 @@ int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
     if (a.N == 0) return 0;
     const int sms = num_sms();
     if (sms <= 0) { set_error("no CUDA device"); return 1; }
-    if (target->kind == CMCD_TARGET_LGCP)
+    if (target->kind == CMCD_TARGET_LGCP || target->kind == CMCD_TARGET_CALLBACK)
         return launch_wide_fwd(a, target, desc->dim, (cudaStream_t)stream, sms, workspace, workspace_bytes);
     if (is_ud(desc->mode)) return launch_bridge_ud_fwd(a, desc->dim, (cudaStream_t)stream, sms);
     if (desc->mode == CMCD_MODE_UHA)
@@ -168,6 +172,14 @@ size_t cmcd_bridge_bwd_workspace_bytes(const cmcd_bridge_desc* desc, const cmcd_
     return need;
 }
 
+size_t cmcd_bridge_bwd_workspace_bytes_for_target(const cmcd_bridge_desc* desc, const cmcd_net* net, const cmcd_target* target) {
+    if (desc && target && target->kind == CMCD_TARGET_CALLBACK) {   // step-wise path at any dim
+        const int arch = (net && mode_uses_net(desc->mode)) ? net->arch : CMCD_ARCH_NONE;
+        return wide_bwd_workspace_bytes(desc->n_particles, desc->dim, arch != CMCD_ARCH_NONE ? net->hidden_pad : 0);
+    }
+    return cmcd_bridge_bwd_workspace_bytes(desc, net);
+}
+
 int cmcd_bridge_bwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* seeds, const float* vd_mean,
                     const float* vd_logdiag, const float* betas, const float* eps, const cmcd_net* net,
                     const cmcd_target* target, const float* traj, const float* cot_negw, float* g_vd_mean,
@@ -180,7 +192,7 @@ int cmcd_bridge_bwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
     if (sms <= 0) { set_error("no CUDA device"); return 1; }
     if (!traj || !cot_negw) { set_error("bridge_bwd needs traj and cot_negw"); return 2; }
     if (a.N == 0) { set_error("bridge_bwd: empty particle batch"); return 2; }
-    if (target->kind == CMCD_TARGET_LGCP)
+    if (target->kind == CMCD_TARGET_LGCP || target->kind == CMCD_TARGET_CALLBACK)
         return launch_wide_bwd(a, target, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
                                g_eps, g_net, workspace, workspace_bytes);
     if (desc->mode == CMCD_MODE_UHA)
@@ -211,7 +223,7 @@ int cmcd_bridge_fwd_host(const cmcd_bridge_desc* desc, void* stream, const int32
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = desc->n_particles;
     CMCD_CUDA_OK(cudaMemcpyAsync(seeds_dev, seeds_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (target->kind == CMCD_TARGET_LGCP) { set_error("bridge_fwd_host: lgcp needs the workspace entry point"); return 2; }
+    if (target->kind == CMCD_TARGET_LGCP || target->kind == CMCD_TARGET_CALLBACK) { set_error("bridge_fwd_host: lgcp / callback targets need the workspace entry point"); return 2; }
     if (int rc = cmcd_bridge_fwd(desc, stream, seeds_dev, vd_mean, vd_logdiag, betas, eps, net, target, negw_dev, z_dev, nullptr, nullptr, 0)) return rc;
     CMCD_CUDA_OK(cudaMemcpyAsync(out_negw_host, negw_dev, n * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (out_z_host) CMCD_CUDA_OK(cudaMemcpyAsync(out_z_host, z_dev, n * desc->dim * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -227,7 +239,7 @@ int cmcd_target_eval(const cmcd_target* target, int32_t dim, void* stream, const
     d.lfsteps = 0;
     BridgeArgs a;
     if (int rc = build_args(&d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, target, a)) return rc;
-    if (target->kind == CMCD_TARGET_LGCP) { set_error("target_eval: lgcp is served by the wide path"); return 2; }
+    if (target->kind == CMCD_TARGET_LGCP || target->kind == CMCD_TARGET_CALLBACK) { set_error("target_eval: lgcp / callback targets are served by the wide path"); return 2; }
     if (n == 0) return 0;
     return launch_target_eval((cudaStream_t)stream, a.tgt, dim, x, n, v, out_logp, out_score, out_hvp);
 }

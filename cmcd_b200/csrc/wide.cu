@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(WG_THREADS) skinny_gemm_kernel(const float* __
 #pragma unroll
     for (int r = 0; r < WG_ROWS; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
     if (m0 < M) {
-        const bool full = (m0 + 3 < M) && ((ldw & 3) == 0);
+        const bool full = (m0 + 3 < M) && ((ldw & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);   // W may be a view into the flat parameter vector
 #pragma unroll 4
         for (int k = 0; k < kl; ++k) {
             float4 w;
@@ -296,7 +296,7 @@ int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
     const NetView& nv = a.net;
     const bool has_net = nv.arch != CMCD_ARCH_NONE;
     const int HP = has_net ? nv.HP : 8;
-    if (has_net && nv.arch != CMCD_ARCH_GEFFNER) { set_error("lgcp wide path: only nn_arch=geffner is implemented (README.md:63 config)"); return 2; }
+    if (has_net && nv.arch != CMCD_ARCH_GEFFNER) { set_error("wide path (lgcp / callback targets): only nn_arch=geffner is implemented (README.md:63 config)"); return 2; }
     const WideWs L = wide_layout(N, d, HP);
     if (!ws || ws_bytes < L.total * sizeof(float)) { set_error("wide_fwd: workspace too small (%zu < %zu)", ws_bytes, L.total * sizeof(float)); return 2; }
     float* f = (float*)ws;
@@ -311,6 +311,10 @@ int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
     wide_init_kernel<<<(unsigned)N, 256, 0, st>>>(a.seeds, d, a.vd_mean, a.vd_logdiag, z, w, keys, a.traj, N);
     CMCD_CUDA_OK(cudaGetLastError());
     auto target_at = [&](const float* x) -> int {
+        if (tg->kind == CMCD_TARGET_CALLBACK) {   // generic target: the caller's batched score, enqueued on the same stream
+            if (int rc = tg->eval(tg->user, (void*)st, x, (int64_t)N, d, nullptr, lp, sp, nullptr)) { set_error("target callback failed (rc=%d)", rc); return 3; }
+            return 0;
+        }
         if (int rc = run_gemm(st, x, d, tg->lgcp_mu0, tg->lgcp_kinv, d, (int)N, d, d, num_sms, part, &S)) return rc;
         wide_target_fin_kernel<<<(unsigned)N, 256, 0, st>>>(part, S, (int)N, d, x, tg->lgcp_counts, tg->lgcp_mu0,
                                                             tg->lgcp_log_norm, tg->lgcp_bin_area, sp, lp);
@@ -374,20 +378,30 @@ __global__ void __launch_bounds__(256) wide_gemm_t_kernel(const float* __restric
                                                           float* __restrict__ Y2, int ldy) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
+    const bool vec = !((M | ldx | ldw) & 3) && !((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W)) & 15);
     for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < J; j += gridDim.x * wpb) {
         const float* __restrict__ wr = W + (size_t)j * ldw;
         for (int n0 = 0; n0 < N; n0 += WT_NT) {
             float acc[WT_NT];
 #pragma unroll
             for (int r = 0; r < WT_NT; ++r) acc[r] = 0.f;
-            for (int m = lane * 4; m < M; m += 128) {
-                const float4 w = __ldg(reinterpret_cast<const float4*>(wr + m));
+            if (vec) {
+                for (int m = lane * 4; m < M; m += 128) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(wr + m));
 #pragma unroll
-                for (int r = 0; r < WT_NT; ++r) {
-                    if (n0 + r < N) {
-                        const float4 x = *reinterpret_cast<const float4*>(X + (size_t)(n0 + r) * ldx + m);
-                        acc[r] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[r]))));
+                    for (int r = 0; r < WT_NT; ++r) {
+                        if (n0 + r < N) {
+                            const float4 x = *reinterpret_cast<const float4*>(X + (size_t)(n0 + r) * ldx + m);
+                            acc[r] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[r]))));
+                        }
                     }
+                }
+            } else {   // rows not 16-byte aligned (generic targets with dim % 4 != 0)
+                for (int m = lane; m < M; m += 32) {
+                    const float w = __ldg(wr + m);
+#pragma unroll
+                    for (int r = 0; r < WT_NT; ++r)
+                        if (n0 + r < N) acc[r] = fmaf(X[(size_t)(n0 + r) * ldx + m], w, acc[r]);
                 }
             }
 #pragma unroll
@@ -412,6 +426,14 @@ __global__ void __launch_bounds__(128) wide_outer_acc_kernel(const float* __rest
     const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int i = blockIdx.y;
     if (j >= J || i >= I) return;
+    if (((J | ldb | ldg) & 3) || ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(G)) & 15)) {   // rows not 16-byte aligned (dim % 4 != 0, or views at odd offsets)
+        for (int q = 0; q < 4 && j + q < J; ++q) {
+            float acc1 = 0.f;
+            for (int n = 0; n < N; ++n) acc1 = fmaf(__ldg(A + (size_t)n * lda + i), __ldg(B + (size_t)n * ldb + j + q), acc1);
+            G[(size_t)i * ldg + j + q] += acc1;
+        }
+        return;
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int n = 0; n < N; ++n) {
         const float a = __ldg(A + (size_t)n * lda + i);
@@ -539,6 +561,7 @@ struct WideNodeCombineArgs {
     float* out;
     int S, N, d, use_nn;
     float area;
+    int generic;   // callback targets: kpart holds H vm itself
 };
 __global__ void wide_node_combine_kernel(const WideNodeCombineArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -546,7 +569,7 @@ __global__ void wide_node_combine_kernel(const WideNodeCombineArgs a) {
     const int n = i / a.d, j = i % a.d;
     float kd = 0.f;
     for (int s = 0; s < a.S; ++s) kd += a.kpart[((size_t)s * a.N + n) * a.d + j];
-    const float hv = -kd - a.area * expf(a.x[i]) * a.vm[i];
+    const float hv = a.generic ? kd : -kd - a.area * expf(a.x[i]) * a.vm[i];
     a.out[i] = a.base[i] + hv + (a.use_nn ? a.dxnet[i] : 0.f);
 }
 
@@ -593,8 +616,8 @@ int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
     const NetView& nv = a.net;
     const bool has_net = nv.arch != CMCD_ARCH_NONE;
     const int HP = has_net ? nv.HP : 8;
-    if (has_net && nv.arch != CMCD_ARCH_GEFFNER) { set_error("lgcp wide path: only nn_arch=geffner is implemented (README.md:63 config)"); return 2; }
-    if ((d & 3) || (HP & 3)) { set_error("lgcp wide path: dim and hidden_pad must be multiples of 4"); return 2; }
+    if (has_net && nv.arch != CMCD_ARCH_GEFFNER) { set_error("wide path (lgcp / callback targets): only nn_arch=geffner is implemented (README.md:63 config)"); return 2; }
+    if (HP & 3) { set_error("wide path: hidden_pad must be a multiple of 4"); return 2; }
     const WideBwdWs L = wide_bwd_layout(N, d, HP);
     if (!ws || ws_bytes < L.total * sizeof(float)) { set_error("wide_bwd: workspace too small (%zu < %zu)", ws_bytes, L.total * sizeof(float)); return 2; }
     float* f = (float*)ws;
@@ -634,7 +657,12 @@ int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
     float* geps_buf = g_eps ? g_eps : part;
 
     auto ew = [&](int n) { return dim3((unsigned)((n + 255) / 256)); };
+    const bool generic = tg->kind == CMCD_TARGET_CALLBACK;
     auto target_at = [&](const float* x, float* score) -> int {
+        if (generic) {
+            if (int rc = tg->eval(tg->user, (void*)st, x, (int64_t)N, d, nullptr, lp, score, nullptr)) { set_error("target callback failed (rc=%d)", rc); return 3; }
+            return 0;
+        }
         if (int rc = run_gemm(st, x, d, tg->lgcp_mu0, tg->lgcp_kinv, d, (int)N, d, d, num_sms, part, &S)) return rc;
         wide_target_fin_kernel<<<(unsigned)N, 256, 0, st>>>(part, S, (int)N, d, x, tg->lgcp_counts, tg->lgcp_mu0,
                                                             tg->lgcp_log_norm, tg->lgcp_bin_area, score, lp);
@@ -657,7 +685,7 @@ int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
         // dA2 = vo W3^T ; dp2 = dA2 * softplus'(pre2)
         wide_gemm_t_kernel<<<tgrid, 256, 0, st>>>(vo, d, nv.W3, d, (int)N, HP, d, nullptr, 0, s2, HP, dA, dp, HP);
         CMCD_CUDA_OK(cudaGetLastError());
-        wide_outer_acc_kernel<<<dim3((d / 4 + 127) / 128, HP), 128, 0, st>>>(A2, HP, vo, d, (int)N, HP, d, gW3, d);
+        wide_outer_acc_kernel<<<dim3(((d + 3) / 4 + 127) / 128, HP), 128, 0, st>>>(A2, HP, vo, d, (int)N, HP, d, gW3, d);
         wide_colsum_acc_kernel<<<ew(d), 256, 0, st>>>(vo, d, (int)N, d, gc3 + (size_t)t * d);
         wide_outer_acc_kernel<<<dim3((HP / 4 + 127) / 128, HP), 128, 0, st>>>(A1, HP, dp, HP, (int)N, HP, HP, gW2, HP);
         wide_colsum_acc_kernel<<<ew(HP), 256, 0, st>>>(dp, HP, (int)N, HP, gc2 + (size_t)t * HP);
@@ -702,10 +730,13 @@ int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
         CMCD_CUDA_OK(cudaGetLastError());
         if (use_nn) { if (int rc = net_bwd(x, t)) return rc; }
         if (pathwise) {
-            if (int rc = run_gemm(st, vm, d, 0.f, tg->lgcp_kinv, d, (int)N, d, d, num_sms, part, &S)) return rc;
+            if (generic) {   // H(x) vm from the caller's batched Hessian-vector product
+                if (int rc = tg->eval(tg->user, (void*)st, x, (int64_t)N, d, vm, nullptr, nullptr, part)) { set_error("target callback failed (rc=%d)", rc); return 3; }
+                S = 1;
+            } else if (int rc = run_gemm(st, vm, d, 0.f, tg->lgcp_kinv, d, (int)N, d, d, num_sms, part, &S)) return rc;
             WideNodeCombineArgs cb{};
             cb.kpart = part; cb.x = x; cb.base = G; cb.vm = vm; cb.dxnet = dx; cb.out = abar;
-            cb.S = S; cb.N = (int)N; cb.d = d; cb.use_nn = use_nn; cb.area = tg->lgcp_bin_area;
+            cb.S = S; cb.N = (int)N; cb.d = d; cb.use_nn = use_nn; cb.area = tg->lgcp_bin_area; cb.generic = generic ? 1 : 0;
             wide_node_combine_kernel<<<ew(nd), 256, 0, st>>>(cb);
             CMCD_CUDA_OK(cudaGetLastError());
         }

@@ -96,6 +96,15 @@ def _make_net(apply_fun, tabs, nbridges):
     return net
 
 
+def _check_cb(rc, target):
+    """_lib.check, but a Python exception raised inside a callback target's log density is re-raised as itself."""
+    err = getattr(target, "error", None)
+    if rc != 0 and err is not None:
+        target.error = None
+        raise err
+    _lib.check(rc)
+
+
 class _Bridge(torch.autograd.Function):
     """(-w[N], z_K[N,d]) = bridge(seeds; vd, betas, eps, net tables)."""
 
@@ -120,9 +129,10 @@ class _Bridge(torch.autograd.Function):
         ws_bytes = L.cmcd_bridge_fwd_workspace_bytes(desc, net, tg)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
         with _lib.timed("fwd"):
-            _lib.check(L.cmcd_bridge_fwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean),
-                                         _lib.ptr(vd_logdiag), _lib.ptr(betas), _lib.ptr(eps), net, tg,
-                                         _lib.ptr(negw), _lib.ptr(z), _lib.ptr(traj), _lib.ptr(ws), ws_bytes))
+            rc = L.cmcd_bridge_fwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean),
+                                   _lib.ptr(vd_logdiag), _lib.ptr(betas), _lib.ptr(eps), net, tg,
+                                   _lib.ptr(negw), _lib.ptr(z), _lib.ptr(traj), _lib.ptr(ws), ws_bytes)
+            _check_cb(rc, target)
         _lib.count_launches(1 if ws is None else 3 + 16 * K)
         ctx.cfg, ctx.saved = cfg, (seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj)
         ctx.mark_non_differentiable(z)
@@ -150,13 +160,14 @@ class _Bridge(torch.autograd.Function):
                     gt[k] = torch.zeros_like(tabs[k])
                     setattr(gnet, k, _lib.ptr(gt[k]))
         L = _lib.lib()
-        ws_bytes = L.cmcd_bridge_bwd_workspace_bytes(desc, net)
+        ws_bytes = L.cmcd_bridge_bwd_workspace_bytes_for_target(desc, net, tg)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
         with _lib.timed("bwd"):
-            _lib.check(L.cmcd_bridge_bwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean),
-                                         _lib.ptr(vd_logdiag), _lib.ptr(betas), _lib.ptr(eps), net, tg, _lib.ptr(traj),
-                                         _lib.ptr(cot), _lib.ptr(g_mean), _lib.ptr(g_logdiag), _lib.ptr(g_betas),
-                                         _lib.ptr(g_eps), gnet, _lib.ptr(ws), ws_bytes))
+            rc = L.cmcd_bridge_bwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean),
+                                   _lib.ptr(vd_logdiag), _lib.ptr(betas), _lib.ptr(eps), net, tg, _lib.ptr(traj),
+                                   _lib.ptr(cot), _lib.ptr(g_mean), _lib.ptr(g_logdiag), _lib.ptr(g_betas),
+                                   _lib.ptr(g_eps), gnet, _lib.ptr(ws), ws_bytes)
+            _check_cb(rc, target)
         _lib.count_launches(2)  # adjoint kernel + partial-gradient reduce kernel
         net_grads = tuple(gt.get(k) for k in _NET_KEYS) if apply_fun is not None else ()
         if wide_rows:

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import CmcdTarget, MIX_STRIDE, TARGET
+from ._lib import CmcdTarget, MIX_STRIDE, TARGET, TARGET_FN
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
@@ -89,6 +89,81 @@ class Target:
         single = x.dim() == 1
         lp = self.evaluate(x[None] if single else x)[0]
         return lp[0] if single else lp
+
+
+class _DevArray:
+    """Raw device pointer -> torch tensor view (through __cuda_array_interface__, no copy)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def _view(ptr, shape, device):
+    return torch.as_tensor(_DevArray(ptr, shape), device=device)
+
+
+class CallbackTarget:
+    """A target outside the registry, given as a batched torch log density ``log_prob(x[N,d]) -> [N]`` on the device --
+    what the reference gets from an arbitrary ``log_prob_model`` (inference-gym / numpyro models, model_handler.py:46-86) and
+    differentiates with jax.grad inside the step body.  The bridge's step-wise CUDA path calls back between half-steps
+    (``cmcd_target_fn``, include/cmcd_b200.h): score by torch autograd, Hessian-vector product by double backward, both
+    enqueued on the stream the bridge runs on.  The O(N K) bridge arithmetic stays in the CUDA kernels."""
+
+    kind = "callback"
+
+    def __init__(self, log_prob, dim, device="cuda"):
+        self.log_prob, self.dim, self.device = log_prob, int(dim), torch.device(device)
+        self.calls = 0
+
+        def _eval(user, stream, x, n, dim_, v, out_logp, out_score, out_hvp):
+            try:
+                with torch.cuda.stream(torch.cuda.ExternalStream(int(stream or 0), device=self.device)), torch.enable_grad():
+                    self.calls += 1
+                    xt = _view(x, (n, dim_), self.device).detach().clone().requires_grad_(True)
+                    lp = self.log_prob(xt)
+                    want_hvp = bool(v) and bool(out_hvp)
+                    (sc,) = torch.autograd.grad(lp.sum(), xt, create_graph=want_hvp)
+                    if out_logp:
+                        _view(out_logp, (n,), self.device).copy_(lp.detach())
+                    if out_score:
+                        _view(out_score, (n, dim_), self.device).copy_(sc.detach())
+                    if want_hvp:
+                        (hv,) = torch.autograd.grad((sc * _view(v, (n, dim_), self.device)).sum(), xt)
+                        _view(out_hvp, (n, dim_), self.device).copy_(hv)
+                return 0
+            except Exception as e:  # a Python exception must not unwind through the C caller
+                self.error = e
+                return 1
+
+        self._cb = TARGET_FN(_eval)   # keep the trampoline alive as long as the target
+
+    def desc(self):
+        import ctypes
+        t = CmcdTarget()
+        t.kind = TARGET["callback"]
+        t.eval = ctypes.cast(self._cb, ctypes.c_void_p).value
+        t.user = None
+        return t
+
+    def evaluate(self, x, v=None):
+        x = x.detach().to(torch.float32).clone().requires_grad_(True)
+        with torch.enable_grad():
+            lp = self.log_prob(x)
+            (sc,) = torch.autograd.grad(lp.sum(), x, create_graph=v is not None)
+            if v is None:
+                return lp.detach(), sc.detach()
+            (hv,) = torch.autograd.grad((sc * v).sum(), x)
+        return lp.detach(), sc.detach(), hv
+
+    def __call__(self, x):
+        single = x.dim() == 1
+        lp = self.log_prob(x[None] if single else x)
+        return lp[0] if single else lp
+
+
+def callback_target(log_prob, dim, device="cuda"):
+    """(log_prob_model, dim) for a target that is not in the fused registry (model_handler.py:66-86 returns the same pair)."""
+    return CallbackTarget(log_prob, dim, device), int(dim)
 
 
 def _gmm2_components():

@@ -41,7 +41,20 @@ extern "C" {
 enum { CMCD_MODE_ULA = 0, CMCD_MODE_ULA_SN = 1, CMCD_MODE_CAIS_SN = 2, CMCD_MODE_CAIS_VAR_SN = 3,
        CMCD_MODE_UD_NONE = 4, CMCD_MODE_UD_NET_Z = 5, CMCD_MODE_UD_NET_ZRHO = 6, CMCD_MODE_UHA = 7 };
 /* target registry -- model_handler.load_model (model_handler.py:30-43) */
-enum { CMCD_TARGET_GMM = 0, CMCD_TARGET_MANY_GMM = 1, CMCD_TARGET_FUNNEL = 2, CMCD_TARGET_LGCP = 3 };
+enum { CMCD_TARGET_GMM = 0, CMCD_TARGET_MANY_GMM = 1, CMCD_TARGET_FUNNEL = 2, CMCD_TARGET_LGCP = 3,
+       CMCD_TARGET_CALLBACK = 4 };
+
+/*
+ * Generic target (CMCD_TARGET_CALLBACK): a batched score callback for densities outside the registry -- what the
+ * reference gets from jax.grad of an arbitrary log_prob_model (inference-gym and numpyro models, model_handler.py:46-86).
+ * Called between the half-steps of every bridge step (once per trajectory point; in the reverse pass once more with v for
+ * the Hessian-vector product).  It must ENQUEUE its work on `stream` and return 0:
+ *   x[n][dim] -> out_logp[n] (if non-NULL), out_score[n][dim] = grad log p (if non-NULL),
+ *   out_hvp[n][dim] = Hessian(log p)(x) v (if v and out_hvp non-NULL).  All pointers are device pointers.
+ * Served by the step-wise ("wide") path: any dim, modes 0..3, nn_arch none / geffner.
+ */
+typedef int (*cmcd_target_fn)(void* user, void* stream, const float* x, int64_t n, int32_t dim, const float* v,
+                              float* out_logp, float* out_score, float* out_hvp);
 /* drift network -- nn.initialize_network (nn.py:21-39) */
 enum { CMCD_ARCH_NONE = 0, CMCD_ARCH_GEFFNER = 1, CMCD_ARCH_DDS = 2 };
 
@@ -97,6 +110,8 @@ typedef struct cmcd_target {
     float lgcp_mu0;           /* lgcp: constant prior mean */
     float lgcp_log_norm;      /* lgcp: -d/2 log(2 pi) - sum log diag L */
     float lgcp_bin_area;      /* lgcp: 1/dim */
+    cmcd_target_fn eval;      /* CMCD_TARGET_CALLBACK: the batched score callback */
+    void* user;               /* CMCD_TARGET_CALLBACK: passed back to eval */
 } cmcd_target;
 
 /* Static description of one bridge problem (params_fixed + the flags of main.py:162-172). */
@@ -143,6 +158,8 @@ int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
  * bytes is scratch.  Outputs are overwritten (not accumulated into).
  */
 size_t cmcd_bridge_bwd_workspace_bytes(const cmcd_bridge_desc* desc, const cmcd_net* net);
+/* same, given the target too: callback targets take the step-wise path at any dim and need its (larger) scratch */
+size_t cmcd_bridge_bwd_workspace_bytes_for_target(const cmcd_bridge_desc* desc, const cmcd_net* net, const cmcd_target* target);
 int cmcd_bridge_bwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* seeds,
                     const float* vd_mean, const float* vd_logdiag, const float* betas, const float* eps,
                     const cmcd_net* net, const cmcd_target* target,
