@@ -12,8 +12,10 @@ MODE = {"MCD_ULA": 0, "MCD_ULA_sn": 1, "MCD_CAIS_sn": 2, "MCD_CAIS_var_sn": 3,
         "MCD_U_a-lp": 4, "MCD_U_a-lp-sna": 5, "MCD_U_a-lp-sn": 6,       # evolve_underdamped_lp_a ("LDVI")
         "MCD_U_e-lp": 4, "MCD_U_e-lp-sna": 5,                           # evolve_underdamped_lp_e
         "MCD_U_ea-lp-sn": 6,                                            # evolve_underdamped_lp_ea
-        "UHA": 7}                                                       # boundingmachine + ais_utils (config.boundmode "UHA")
-UD_MODES = ("MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn", "MCD_U_e-lp", "MCD_U_e-lp-sna", "MCD_U_ea-lp-sn")
+        "UHA": 7,                                                       # boundingmachine + ais_utils (config.boundmode "UHA")
+        "MCD_CAIS_UHA_sn": 8}                                           # evolve_underdamped_lp_a_cais ("2nd order CMCD")
+UD_MODES = ("MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn", "MCD_U_e-lp", "MCD_U_e-lp-sna", "MCD_U_ea-lp-sn",
+            "MCD_CAIS_UHA_sn")
 TARGET = {"gmm": 0, "many_gmm": 1, "funnel": 2, "lgcp": 3, "callback": 4}
 ARCH = {None: 0, "none": 0, "geffner": 1, "dds": 2}
 MIX_STRIDE = 6

@@ -15,11 +15,15 @@
 //   lp_a : a_f = a_b = 1 - g eps, s_f = s_b = sqrt(2 g eps), c_n = 2 g eps                (g = gamma)
 //   lp_e : a_f = a_b = eta, s_f = s_b = sqrt(1 - eta^2), c_n = 2 (1 - eta)
 //   lp_ea: a_f = exp(-g eps), s_f = sqrt(1 - a_f^2), a_b = 1 - g eps, c_n = 2 g eps, s_b = sqrt(2 g eps)
+//   evolve_underdamped_lp_a_cais  MCD_CAIS_UHA_sn ("2nd order CMCD", README.md:16)     src/mcd_under_lp_a_cais.py:6-115
+//     (CMCD_MODE_UD_CAIS; a TypeError at the reference HEAD -- mcd_utils.py:176-188 passes keywords the function does not
+//      take -- built to the body as written): lp_a with eps_i on the cosine schedule, the target score clipped at 1e2, and
+//      the network ALSO in the forward-kernel mean, m_f = a_f rho + c_f NN((z, rho), i), c_f = -2 g eps_i (row 7; 0 elsewhere).
 // with gradU(z) = -(beta_i grad log p(z) + (1 - beta_i) grad log q(z)), never clipped (these operators take no
 // grad_clipping).  The kernel mode only says what the network sees (CMCD_MODE_UD_NONE / _NET_Z / _NET_ZRHO).
 //
-// ABI conventions for these modes (include/cmcd_b200.h): eps = [6][K] = rows (eps, a_f, s_f, a_b, c_n, s_b) -- the host
-// forms the coefficient rows from (eps, gamma, eta) with differentiable ops, so the cotangents g_eps = [6][K] chain into
+// ABI conventions for these modes (include/cmcd_b200.h): eps = [7][K] = rows (eps, a_f, s_f, a_b, c_n, s_b, c_f) -- the host
+// forms the coefficient rows from (eps, gamma, eta) with differentiable ops, so the cotangents g_eps = [7][K] chain into
 // those scalars; traj = [K+1][3d][N] = (z_j, rho_j, rho'_j) per node (rho'_j: the refreshed momentum of step j, stored
 // so that the adjoint does not have to walk the key chain backwards).
 //
@@ -31,6 +35,8 @@
 //   rbp  = rb'' + a_b G + J_rho'^T v         (cotangent of rho')
 //   rb   = -G + a_f rbp
 //   d a_f = rbp.rho;  d s_f = rbp.xi + c d / s_f;  d a_b = G.rho';  d c_n = G.NN;  d s_b = c (s_b |r|^2 - d / s_b)
+//   CMCD_MODE_UD_CAIS: second pull-back v_f = c_f rbp at (z, rho) -> zb, rb;  d c_f = rbp.NN_f;  clipped scores: the
+//   Hessian-vector products take mk o gb (mk = 1 where |s_p| <= clip), beta sees clip(s_p) - s_q.
 //   d eps = -rb'.gradU(z')/2 + zb''.rho'' - rb''.gradU(z)/2
 //   d beta = -g1b.(s_p(z') - s_q(z')) - g0b.(s_p(z) - s_q(z));  vd: through s_q at both points and z_0 = mu + sigma xi0.
 // (log N(rho'; m_f, s_f) = -|xi|^2/2 - d log s_f - const with xi fixed.)
@@ -39,7 +45,7 @@
 namespace cmcd {
 
 constexpr int UD_FWD_PB = 128;
-constexpr int UD_ROWS = 6;   // rows of the eps table: eps, a_f, s_f, a_b, c_n, s_b
+constexpr int UD_ROWS = 7;   // rows of the eps table: eps, a_f, s_f, a_b, c_n, s_b, c_f
 
 template <int D>
 __device__ __forceinline__ float ud_gauss_logprob(const float (&x)[D], const float (&mean)[D], float scale, float lognorm) {
@@ -62,6 +68,7 @@ __global__ void __launch_bounds__(UD_FWD_PB, (HPT > 64 ? 1 : 2)) bridge_ud_fwd_k
     const NetView& nv = a.net;
     const int HP = HPT ? HPT : nv.HP;
     const bool has_net = DI != 0 && nv.arch != CMCD_ARCH_NONE;
+    const bool nn_fm = has_net && a.mode == CMCD_MODE_UD_CAIS;   // network in the forward-kernel mean too
     NetSmem ns = net_stage_smem(nv, D, sm, DIN);
     float* sTp = sm + (has_net ? net_smem_floats(D, HP, DIN) : 0);
     const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
@@ -111,15 +118,25 @@ __global__ void __launch_bounds__(UD_FWD_PB, (HPT > 64 ? 1 : 2)) bridge_ud_fwd_k
             for (int i = 0; i < K; ++i) {
                 const float beta = __ldg(a.betas + i), eps = __ldg(a.eps + i);
                 const float af = __ldg(a.eps + K + i), sf = __ldg(a.eps + 2 * K + i), ab = __ldg(a.eps + 3 * K + i);
-                const float cn = __ldg(a.eps + 4 * K + i), sb = __ldg(a.eps + 5 * K + i);
-                float mf[D], mb[D], rp[D], rpp[D], rn[D];
+                const float cn = __ldg(a.eps + 4 * K + i), sb = __ldg(a.eps + 5 * K + i), cf = __ldg(a.eps + 6 * K + i);
+                float mf[D], mb[D], rp[D], rpp[D], rn[D], nnf[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) nnf[j] = 0.f;
+                if constexpr (DIN > D) {
+                    if (nn_fm) {   // mcd_under_lp_a_cais.py:52-56: NN((z, rho), i) in the forward-kernel mean
+                        float x[DIN];
+#pragma unroll
+                        for (int j = 0; j < D; ++j) { x[j] = z[j]; x[D + j] = rho[j]; }
+                        net_fwd<D, ACT, HPT, JC, UD_FWD_PB, DIN>(nv, ns, i, x, nnf, a1col);
+                    }
+                }
                 step_keys_and_normal<D>(g, xi);   // :31-32 and :59
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
-                    mf[j] = rho[j] * af;
+                    mf[j] = rho[j] * af + cf * nnf[j];
                     rp[j] = mf[j] + sf * xi[j];
                     const float sq = -((z[j] - mu[j]) / sig[j]) / sig[j];
-                    const float g0 = -(beta * sp[j] + (1.0f - beta) * sq);
+                    const float g0 = -(beta * fminf(fmaxf(sp[j], -a.clip_t), a.clip_t) + (1.0f - beta) * sq);
                     rpp[j] = rp[j] - eps * g0 / 2.0f;
                     zn[j] = z[j] + eps * rpp[j];
                 }
@@ -151,7 +168,7 @@ __global__ void __launch_bounds__(UD_FWD_PB, (HPT > 64 ? 1 : 2)) bridge_ud_fwd_k
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
                     const float sq = -((zn[j] - mu[j]) / sig[j]) / sig[j];
-                    const float g1 = -(beta * sp[j] + (1.0f - beta) * sq);
+                    const float g1 = -(beta * fminf(fmaxf(sp[j], -a.clip_t), a.clip_t) + (1.0f - beta) * sq);
                     rn[j] = rpp[j] - eps * g1 / 2.0f;
                 }
                 const float fk = ud_gauss_logprob<D>(rp, mf, sf, logf(2.5066282746310002f * sf));
@@ -196,6 +213,8 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
     const NetView& nv = a.net;
     const int HP = HPT ? HPT : nv.HP;
     const bool has_net = DI != 0 && nv.arch != CMCD_ARCH_NONE;
+    const bool nn_fm = has_net && a.mode == CMCD_MODE_UD_CAIS;
+    const bool clipped = a.clip_t < 3.0e38f;
     const float out_scale = has_net ? net_out_scale(nv) : 1.0f;
     NetSmem ns = net_stage_smem(nv, D, sm, DIN);
     float* sTp = sm + (has_net ? net_smem_floats(D, HP, DIN) : 0);
@@ -237,7 +256,7 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
         for (int i = K - 1; i >= 0; --i) {
             const float beta = __ldg(a.betas + i), eps = __ldg(a.eps + i);
             const float af = __ldg(a.eps + K + i), sf = __ldg(a.eps + 2 * K + i), ab = __ldg(a.eps + 3 * K + i);
-            const float cn = __ldg(a.eps + 4 * K + i), sb = __ldg(a.eps + 5 * K + i);
+            const float cn = __ldg(a.eps + 4 * K + i), sb = __ldg(a.eps + 5 * K + i), cf = __ldg(a.eps + 6 * K + i);
             const float omb = 1.0f - beta, s2 = sb * sb, he = 0.5f * eps;
             float z[D], rho[D], rp[D];
 #pragma unroll
@@ -246,19 +265,23 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
                 rho[j] = a.traj[((size_t)i * TS + D + j) * a.N + n];
                 rp[j] = a.traj[((size_t)i * TS + 2 * D + j) * a.N + n];
             }
-            float gbeta = 0.f, geps = 0.f, gaf = 0.f, gsf = 0.f, gab = 0.f, gcn = 0.f, gsb = 0.f;
+            float gbeta = 0.f, geps = 0.f, gaf = 0.f, gsf = 0.f, gab = 0.f, gcn = 0.f, gsb = 0.f, gcf = 0.f;
             // ---- second half kick: rho_new = rho'' - (eps/2) gradU(z')
-            float g1b[D], zbn[D], rbpp[D], g0b[D], sp0[D];
+            float g1b[D], zbn[D], rbpp[D], g0b[D], sp0[D], hvin[D];
 #pragma unroll
-            for (int j = 0; j < D; ++j) g1b[j] = -he * rb[j];
-            target_eval<D, true>(a.tgt, sTp, zn, sp1, g1b, hv);
+            for (int j = 0; j < D; ++j) {   // sp1 = score at z' (from the previous iteration / the terminal evaluation): clip mask
+                g1b[j] = -he * rb[j];
+                hvin[j] = (fabsf(sp1[j]) <= a.clip_t) ? g1b[j] : 0.f;
+            }
+            target_eval<D, true>(a.tgt, sTp, zn, sp1, hvin, hv);
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 const float sq1 = -(zn[j] - mu[j]) * ivar[j];
-                const float g1 = -(beta * sp1[j] + omb * sq1);
+                const float c1 = fminf(fmaxf(sp1[j], -a.clip_t), a.clip_t);
+                const float g1 = -(beta * c1 + omb * sq1);
                 zbn[j] = zb[j] - beta * hv[j] + omb * ivar[j] * g1b[j];
                 geps = fmaf(-0.5f * rb[j], g1, geps);
-                gbeta = fmaf(g1b[j], -(sp1[j] - sq1), gbeta);
+                gbeta = fmaf(g1b[j], -(c1 - sq1), gbeta);
                 gmu[j] = fmaf(-omb * ivar[j], g1b[j], gmu[j]);
                 gls[j] = fmaf(2.0f * omb * sq1, g1b[j], gls[j]);
                 // ---- drift: z' = z + eps rho''
@@ -266,16 +289,25 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
                 g0b[j] = -he * rbpp[j];
             }
             // ---- first half kick: rho'' = rho' - (eps/2) gradU(z)
-            target_eval<D, true>(a.tgt, sTp, z, sp0, g0b, hv);
+            if (clipped) {   // the mask needs the score at z before the Hessian-vector product
+                target_eval<D, false>(a.tgt, sTp, z, sp0, zero, hv);
+#pragma unroll
+                for (int j = 0; j < D; ++j) hvin[j] = (fabsf(sp0[j]) <= a.clip_t) ? g0b[j] : 0.f;
+            } else {
+#pragma unroll
+                for (int j = 0; j < D; ++j) hvin[j] = g0b[j];
+            }
+            target_eval<D, true>(a.tgt, sTp, z, sp0, hvin, hv);
             float zbc[D], rbp[D];
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 const float sq0 = -(z[j] - mu[j]) * ivar[j];
-                const float g0 = -(beta * sp0[j] + omb * sq0);
+                const float c0 = fminf(fmaxf(sp0[j], -a.clip_t), a.clip_t);
+                const float g0 = -(beta * c0 + omb * sq0);
                 const float rpp = rp[j] - eps * g0 / 2.0f;
                 geps = fmaf(zbn[j], rpp, geps);
                 geps = fmaf(-0.5f * rbpp[j], g0, geps);
-                gbeta = fmaf(g0b[j], -(sp0[j] - sq0), gbeta);
+                gbeta = fmaf(g0b[j], -(c0 - sq0), gbeta);
                 gmu[j] = fmaf(-omb * ivar[j], g0b[j], gmu[j]);
                 gls[j] = fmaf(2.0f * omb * sq0, g0b[j], gls[j]);
                 zbc[j] = zbn[j] - beta * hv[j] + omb * ivar[j] * g0b[j];
@@ -322,18 +354,41 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
                     }
                 }
             }
-            // ---- momentum refresh: rho' = a_f rho + s_f xi
+            // ---- forward-kernel mean network (CMCD_MODE_UD_CAIS): m_f = a_f rho + c_f NN((z, rho), i), cotangent of m_f = rbp
+            float nnf[D], rext[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) { nnf[j] = 0.f; rext[j] = 0.f; }
+            if constexpr (DIN > D) {
+                if (nn_fm) {
+                    float of[D], vf[D];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) { x[j] = z[j]; x[D + j] = rho[j]; }
+                    net_fwd_store<D, ACT, HPT, JC, RS, DIN>(nv, ns, i, x, of, S1 + tid, S2 + tid, S3 + tid);
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        nnf[j] = out_scale * fminf(fmaxf(of[j], -nv.out_clip), nv.out_clip);
+                        vf[j] = cf * rbp[j];
+                        gcf = fmaf(rbp[j], nnf[j], gcf);
+                    }
+                    net_bwd<D, ACT, HPT, JC, BPB, DIN>(nv, ns, i, x, of, vf, dx, S1, S2, S3, sX, sVo, part, L);
+#pragma unroll
+                    for (int j = 0; j < D; ++j) { zbc[j] += dx[j]; rext[j] = dx[D + j]; }
+                }
+            }
+            // ---- momentum refresh: rho' = m_f + s_f xi,  m_f = a_f rho (+ c_f NN_f)
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                const float mf = rho[j] * af;
+                const float mf = rho[j] * af + cf * nnf[j];
                 gsf = fmaf(rbp[j], (rp[j] - mf) / sf, gsf);
                 gaf = fmaf(rho[j], rbp[j], gaf);
-                rb[j] = fmaf(af, rbp[j], -G[j]);
+                rb[j] = fmaf(af, rbp[j], -G[j]) + rext[j];
                 zb[j] = zbc[j];
                 zn[j] = z[j];
+                sp1[j] = sp0[j];
             }
             gbeta = warp_sum_f(gbeta); geps = warp_sum_f(geps);
             gaf = warp_sum_f(gaf); gsf = warp_sum_f(gsf); gab = warp_sum_f(gab); gcn = warp_sum_f(gcn); gsb = warp_sum_f(gsb);
+            if (nn_fm) gcf = warp_sum_f(gcf);
             if ((tid & 31) == 0) {
                 atomicAdd(part + L.beta + i, gbeta);
                 atomicAdd(part + L.eps + i, geps);
@@ -342,6 +397,7 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
                 atomicAdd(part + L.eps + 3 * K + i, gab);
                 atomicAdd(part + L.eps + 4 * K + i, gcn);
                 atomicAdd(part + L.eps + 5 * K + i, gsb);
+                if (nn_fm) atomicAdd(part + L.eps + 6 * K + i, gcf);
             }
         }
         // initial: z0 = mu + sigma xi0, w0 = -log q(z0) = 0.5|xi0|^2 + sum log(sqrt(2pi) sigma); rho0 is pure noise   (zn = z_0 here)
@@ -357,7 +413,7 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
 
 // ---------------------------------------------------------------------------------------------------------------- launchers
 static int ud_net_in(int mode, int D) {
-    return mode == CMCD_MODE_UD_NET_ZRHO ? 2 * D : (mode == CMCD_MODE_UD_NET_Z ? D : 0);
+    return (mode == CMCD_MODE_UD_NET_ZRHO || mode == CMCD_MODE_UD_CAIS) ? 2 * D : (mode == CMCD_MODE_UD_NET_Z ? D : 0);
 }
 
 template <int D, int ACT, int HPT, int JC, int DI>

@@ -67,13 +67,13 @@ static int num_sms() {
     return g_num_sms;
 }
 
-static bool is_ud(int mode) { return mode >= CMCD_MODE_UD_NONE && mode <= CMCD_MODE_UD_NET_ZRHO; }
+static bool is_ud(int mode) { return (mode >= CMCD_MODE_UD_NONE && mode <= CMCD_MODE_UD_NET_ZRHO) || mode == CMCD_MODE_UD_CAIS; }
 static bool mode_uses_net(int mode) { return mode != CMCD_MODE_ULA && mode != CMCD_MODE_UD_NONE && mode != CMCD_MODE_UHA; }
 
 static int build_args(const cmcd_bridge_desc* d, const int32_t* seeds, const float* vd_mean, const float* vd_logdiag,
                       const float* betas, const float* eps, const cmcd_net* net, const cmcd_target* tg, BridgeArgs& a) {
     if (!d || !tg) { set_error("null descriptor"); return 2; }
-    if (d->mode < CMCD_MODE_ULA || d->mode > CMCD_MODE_UHA) { set_error("Mode not implemented."); return 2; }
+    if (d->mode < CMCD_MODE_ULA || d->mode > CMCD_MODE_UD_CAIS) { set_error("Mode not implemented."); return 2; }
     if (d->nbridges < 0 || d->n_particles < 0 || d->dim < 1) { set_error("bad sizes N=%d K=%d d=%d", d->n_particles, d->nbridges, d->dim); return 2; }
     std::memset(&a, 0, sizeof(a));
     a.mode = d->mode; a.K = d->nbridges; a.N = d->n_particles;

@@ -39,10 +39,18 @@ def eps_table(eps0, nbridges, eps_schedule=None):
 
 
 def ud_coeff_table(mode, params, nbridges):
-    """[6, K] rows (eps, a_f, s_f, a_b, c_n, s_b) of the underdamped step (csrc/bridge_ud.cu), formed from the reference's
+    """[7, K] rows (eps, a_f, s_f, a_b, c_n, s_b, c_f) of the underdamped step (csrc/bridge_ud.cu), formed from the reference's
     scalars with differentiable ops so the kernel's row cotangents chain into eps / gamma / eta:
-      forward kernel  rho' ~ N(a_f rho, s_f);  backward kernel  rho ~ N(a_b rho' + c_n NN, s_b)."""
+      forward kernel  rho' ~ N(a_f rho + c_f NN, s_f);  backward kernel  rho ~ N(a_b rho' + c_n NN, s_b)."""
     eps, gamma, eta = params["eps"], params["gamma"], params["eta"]
+    c_f = torch.zeros((), device=eps.device)
+    if mode == "MCD_CAIS_UHA_sn":                                          # mcd_under_lp_a_cais.py:33-40,50-58,79-82
+        eps = eps_table(eps, nbridges, "cos_sq")                           # the body hard-codes the cosine schedule
+        eta_aux = gamma * eps
+        a_f = a_b = 1.0 - eta_aux
+        s_f = s_b = torch.sqrt(2.0 * eta_aux)
+        c_n, c_f = 2.0 * eta_aux, -2.0 * eta_aux
+        return torch.stack([eps, a_f, s_f, a_b, c_n, s_b, c_f])
     if mode in ("MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn"):        # mcd_under_lp_a.py:28-51
         eta_aux = gamma * eps
         a_f = a_b = 1.0 - eta_aux
@@ -62,13 +70,15 @@ def ud_coeff_table(mode, params, nbridges):
     else:
         raise NotImplementedError("Mode not implemented.")
     one = torch.ones(nbridges, device=eps.device, dtype=torch.float32)
-    return torch.stack([v * one for v in (eps, a_f, s_f, a_b, c_n, s_b)])
+    return torch.stack([v * one for v in (eps, a_f, s_f, a_b, c_n, s_b, c_f)])
 
 
 def _clips(mode, grad_clipping):
     """grad_clipping -> (clip_target, clip_q).  mcd_cais.py:24-30 (1e3, target only);
     mcd_cais_var.py:33-40 (1e2, both); mcd_over_orig.py never clips."""
     inf = float("inf")
+    if mode == "MCD_CAIS_UHA_sn":   # mcd_under_lp_a_cais.py:23-30,48: stable=True -> the target score is always clipped at 1e2
+        return 1e2, inf
     if not grad_clipping or mode in ("MCD_ULA", "MCD_ULA_sn") or mode in UD_MODES:   # mcd_under_lp_a.py takes no grad_clipping
         return inf, inf
     return (1e2, 1e2) if mode == "MCD_CAIS_var_sn" else (1e3, inf)
@@ -189,7 +199,7 @@ def bridge(seeds, params, betas, params_fixed, log_prob_model, eps_schedule=None
         raise RuntimeError(f"mode {mode} needs a score network")
     clip_t, clip_q = _clips(mode, grad_clipping)
     if nbridges >= 1 and mode in UD_MODES:
-        eps = ud_coeff_table(mode, params, nbridges)   # [6, K]: eps and the kernel coefficients, constant over the steps
+        eps = ud_coeff_table(mode, params, nbridges)   # [7, K]: eps and the kernel coefficients, constant over the steps
     elif nbridges >= 1:
         sched = eps_schedule if mode in ("MCD_CAIS_sn", "MCD_CAIS_var_sn") else None  # orig ignores the schedule
         eps = eps_table(params["eps"], nbridges, sched)

@@ -16,7 +16,7 @@ from .nn import initialize_network
 from .pytree import ravel_pytree, tree_map
 
 _SN_MODES = ("MCD_ULA_sn", "MCD_CAIS_sn", "MCD_CAIS_var_sn", "MCD_U_a-lp-sna", "MCD_U_e-lp-sna")   # mcdboundingmachine.py:67-83
-_SN_RHO_MODES = ("MCD_U_a-lp-sn", "MCD_U_ea-lp-sn")                               # :84-102: network on (z, rho), rho_dim = dim
+_SN_RHO_MODES = ("MCD_U_a-lp-sn", "MCD_U_ea-lp-sn", "MCD_CAIS_UHA_sn")                               # :84-102: network on (z, rho), rho_dim = dim
 
 
 def initialize(dim, vdparams=None, nbridges=0, eps=0.01, gamma=10.0, eta=0.5, ngridb=32, mgridref_y=None,

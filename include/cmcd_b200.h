@@ -27,19 +27,24 @@ extern "C" {
  *   The three scan bodies are one step with different coefficients, so the kernel mode only says what the score
  *   network sees: nothing (MCD_U_a-lp, MCD_U_e-lp), z (MCD_U_a-lp-sna, MCD_U_e-lp-sna) or (z, rho') (MCD_U_a-lp-sn,
  *   MCD_U_ea-lp-sn; rho_dim = dim, mcdboundingmachine.py:84-102).  For these modes:
- *     eps / g_eps = [6][K] = rows (eps, a_f, s_f, a_b, c_n, s_b): forward-kernel mean a_f rho and scale s_f, backward-
- *                   kernel mean a_b rho' + c_n NN and scale s_b (formulas per operator in csrc/bridge_ud.cu) -- the host
+ *     eps / g_eps = [7][K] = rows (eps, a_f, s_f, a_b, c_n, s_b, c_f): forward-kernel mean a_f rho (+ c_f NN, mode 8)
+ *                   and scale s_f, backward-kernel mean a_b rho' + c_n NN and scale s_b (formulas per operator in
+ *                   csrc/bridge_ud.cu) -- the host
  *                   forms the rows from (eps, gamma, eta) and chains the cotangents back;
  *     traj        = [K+1][3 dim][N] = (z_j, rho_j, rho'_j) per node;
  *     cmcd_net    U1 / U2 = [in][HP], U3 = [in][dim] with in = dim (NET_Z) or 2 dim (NET_ZRHO);
- *     clip_target / clip_q are ignored (these operators take no grad_clipping).
+ *     clip_target / clip_q are ignored in modes 4..6 (these operators take no grad_clipping).
+ * 8: MCD_CAIS_UHA_sn ("2nd order CMCD", README.md:16; evolve_underdamped_lp_a_cais, mcd_under_lp_a_cais.py:6-115): as mode 6
+ *   with the network also in the forward-kernel mean (row c_f), eps_i on the cosine schedule and the target score clipped at
+ *   clip_target (1e2 in the reference body).  The reference dispatcher cannot call it at HEAD (keyword mismatch,
+ *   mcd_utils.py:176-188); built to the function body as written.
  * 7: UHA -- boundmode "UHA" (main.py:115-133): boundingmachine.compute_log_elbo (boundingmachine.py:73-111) over
  *   ais_utils.evolve (ais_utils.py:7-69) with the diagonal momentum distribution of momdist.py; no score network.
  *     eps / g_eps = [3][K] = rows (eps, a, s): momentum refresh rho_r = a rho + s exp(md) xi (a = eta, s = sqrt(1 - eta^2));
  *     vd_logdiag / g_vd_logdiag = [2][dim] = (q log-scales, md = momentum log-scales, momdist.py:9-11);
  *     desc.lfsteps = leapfrog steps per bridge (1..8, configs/base.py:83); traj = [K+1][3 dim][N] = (z_j, rho_j, rho_r_j). */
 enum { CMCD_MODE_ULA = 0, CMCD_MODE_ULA_SN = 1, CMCD_MODE_CAIS_SN = 2, CMCD_MODE_CAIS_VAR_SN = 3,
-       CMCD_MODE_UD_NONE = 4, CMCD_MODE_UD_NET_Z = 5, CMCD_MODE_UD_NET_ZRHO = 6, CMCD_MODE_UHA = 7 };
+       CMCD_MODE_UD_NONE = 4, CMCD_MODE_UD_NET_Z = 5, CMCD_MODE_UD_NET_ZRHO = 6, CMCD_MODE_UHA = 7, CMCD_MODE_UD_CAIS = 8 };
 /* target registry -- model_handler.load_model (model_handler.py:30-43) */
 enum { CMCD_TARGET_GMM = 0, CMCD_TARGET_MANY_GMM = 1, CMCD_TARGET_FUNNEL = 2, CMCD_TARGET_LGCP = 3,
        CMCD_TARGET_CALLBACK = 4 };

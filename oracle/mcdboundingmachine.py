@@ -6,6 +6,9 @@ ORACLE / TEST INFRASTRUCTURE ONLY.  Follows, under /root/reference/src:
   mcd_cais.py:6-99, mcd_cais_var.py:7-112, mcd_over_orig.py:6-65 (the three step bodies)
   mcd_under_lp_a.py:6-87 (underdamped "LDVI" family: MCD_U_a-lp, MCD_U_a-lp-sna, MCD_U_a-lp-sn)
   mcd_under_lp_e.py:6-74 (MCD_U_e-lp, MCD_U_e-lp-sna), mcd_under_lp_ea.py:6-104 (MCD_U_ea-lp-sn)
+  mcd_under_lp_a_cais.py:6-115 (MCD_CAIS_UHA_sn, "2nd order CMCD": the dispatcher mcd_utils.py:176-188 passes eps_schedule /
+    grad_clipping keywords this function does not take -- a TypeError at HEAD; restated BY SPECIFICATION: the body as written,
+    which hard-codes the cosine schedule (:33-40,50) and the 1e2 clip on the target score (:23-30,48, stable=True))
   vardist/diag_gauss.py:20-62, boundingmachine.py:73-111 (nbridges=0 MFVI bound)
   utils.py:219-248 (ELBO / ln Z estimators)
 Particles are a leading batch axis (the reference vmaps a per-particle function).  Gaussians
@@ -63,7 +66,7 @@ def initialize(dim, vdparams=None, nbridges=0, eps=0.01, gamma=10.0, eta=0.5, ng
         sn, apply_fun_sn = initialize_network(dim, emb_dim, nbridges, nn_arch,
                                               torch.Generator().manual_seed(seed), live, dtype)
         pt["sn"] = sn
-    elif mode in ("MCD_U_a-lp-sn", "MCD_U_ea-lp-sn"):    # :84-102: network on (z, rho), rho_dim = dim
+    elif mode in ("MCD_U_a-lp-sn", "MCD_U_ea-lp-sn", "MCD_CAIS_UHA_sn"):    # :84-102: network on (z, rho), rho_dim = dim
         sn, apply_fun_sn = initialize_network(dim, emb_dim, nbridges, nn_arch,
                                               torch.Generator().manual_seed(seed), live, dtype, rho_dim=dim)
         pt["sn"] = sn
@@ -120,7 +123,7 @@ def _score(fn, z):
 
 
 # ---------------------------------------------------------------- the step bodies
-UD_MODES = ("MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn", "MCD_U_e-lp", "MCD_U_e-lp-sna", "MCD_U_ea-lp-sn")
+UD_MODES = ("MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn", "MCD_U_e-lp", "MCD_U_e-lp-sna", "MCD_U_ea-lp-sn", "MCD_CAIS_UHA_sn")
 
 
 def evolve_underdamped_lp_a(z, betas, params, rho0, xi, params_fixed, log_prob_model, traj=None):
@@ -130,6 +133,8 @@ def evolve_underdamped_lp_a(z, betas, params, rho0, xi, params_fixed, log_prob_m
         return evolve_underdamped_lp_e(z, betas, params, rho0, xi, params_fixed, log_prob_model, traj)
     if mode == "MCD_U_ea-lp-sn":
         return evolve_underdamped_lp_ea(z, betas, params, rho0, xi, params_fixed, log_prob_model, traj)
+    if mode == "MCD_CAIS_UHA_sn":
+        return evolve_underdamped_lp_a_cais(z, betas, params, rho0, xi, params_fixed, log_prob_model, traj)
     vd = params["vd"]
     use_sn, full_sn = mode != "MCD_U_a-lp", mode == "MCD_U_a-lp-sn"
     eps, gamma = params["eps"], params["gamma"]
@@ -194,6 +199,44 @@ def _ud_scan(z, betas, params, rho0, xi, nbridges, log_prob_model, kernels, traj
             traj.append((z_new.detach().clone(), rho_new.detach().clone(), None))
         z, rho = z_new, rho_new
     w = w + normal_log_prob(rho, zero, one)
+    return z, w
+
+
+def evolve_underdamped_lp_a_cais(z, betas, params, rho0, xi, params_fixed, log_prob_model, traj=None):
+    """mcd_under_lp_a_cais.py:6-115 as written (see the module header): controlled underdamped step -- the network enters the
+    forward-kernel mean at (z, rho) and the backward-kernel mean at (z, rho'), eps follows the cosine schedule, the target
+    score is clipped at 1e2."""
+    dim, nbridges, mode, apply_fun_sn = params_fixed
+    vd = params["vd"]
+    gamma = params["gamma"]
+    zero, one = torch.zeros((), dtype=z.dtype), torch.ones((), dtype=z.dtype)
+
+    def gradU(x, beta, clip=1e2):                                         # :23-30
+        gp = _score(lambda y: vd_log_prob(vd, y), x)
+        gu = _score(log_prob_model, x)
+        guc = torch.clamp(gu, -clip, clip)
+        return -1.0 * (beta * guc + (1.0 - beta) * gp)
+
+    rho = rho0                                                            # :94-95
+    w = -normal_log_prob(rho, zero, one)                                  # :98-99
+    for i in range(nbridges):                                             # :42-90
+        beta = betas[i]
+        uf = gradU(z, beta)                                               # :47
+        eps = eps_at(params["eps"], i, nbridges, "cos_sq")                # :50 -> :33-40
+        eta_aux = gamma * eps
+        input_sn_old = torch.cat([z, rho], dim=-1)
+        fk_rho_mean = rho * (1.0 - eta_aux) - 2.0 * eta_aux * apply_fun_sn(params["sn"], input_sn_old, i)   # :53-56
+        scale = torch.sqrt(2.0 * eta_aux)
+        rho_prime = fk_rho_mean + scale * xi[i]
+        rho_pp = rho_prime - eps * uf / 2.0                               # :64
+        z_new = z + eps * rho_pp
+        ub = gradU(z_new, beta)
+        rho_new = rho_pp - eps * ub / 2.0
+        input_sn = torch.cat([z, rho_prime], dim=-1)
+        bk_rho_mean = rho_prime * (1.0 - eta_aux) + 2.0 * eta_aux * apply_fun_sn(params["sn"], input_sn, i)  # :79-82
+        w = w + normal_log_prob(rho, bk_rho_mean, scale) - normal_log_prob(rho_prime, fk_rho_mean, scale)
+        z, rho = z_new, rho_new
+    w = w + normal_log_prob(rho, zero, one)                               # :113
     return z, w
 
 

@@ -31,7 +31,7 @@ from oracle import mcdboundingmachine as OM  # noqa: E402
 # name -> particles in the fixture (kept small: the whole directory stays well under 1 MB)
 GOLDEN_CONFIGS = {"A_gmm": 64, "B_funnel": 64, "C_manygmm_dds_small": 96, "Cvar_manygmm": 48, "ULA_gmm": 64,
                   "ULAsn_gmm_dds": 64, "lin_funnel": 48, "LDVI_gmm": 64, "LDVI_funnel_dds": 48, "UDsna_funnel": 48,
-                  "UDe_gmm": 64, "UDesna_funnel_dds": 48, "UDea_gmm": 64}
+                  "UDe_gmm": 64, "UDesna_funnel_dds": 48, "UDea_gmm": 64, "CAISUHA_gmm": 64, "CAISUHA_manygmm_dds": 48}
 
 PRNG_KAT = {
     "source": "Random123 Threefry-2x32-20 known-answer tests; JAX documentation (jax.random.split / normal examples)",

@@ -48,6 +48,12 @@ CONFIGS = {
                               eta=0.5, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
     "UDea_gmm": dict(model="gmm", mode="MCD_U_ea-lp-sn", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.05, sigma=1.0,
                      gamma=5.0, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    "CAISUHA_gmm": dict(model="gmm", mode="MCD_CAIS_UHA_sn", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.08, sigma=1.0,
+                        gamma=4.0, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    # (eps = 0.3 makes the leapfrog unstable between mixture modes: one particle's cotangent recursion then amplifies fp32
+    #  rounding to 1e-3 in BOTH fp32 implementations -- tools/dbg_cais.py; 0.1 keeps the chain well conditioned)
+    "CAISUHA_manygmm_dds": dict(model="many_gmm", mode="MCD_CAIS_UHA_sn", N=300, K=16, nn_arch="dds", emb_dim=20, eps=0.1, sigma=15.0,
+                                gamma=2.0, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "mgridref_y")),
     "UD_gmm": dict(model="gmm", mode="MCD_U_a-lp", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.05, sigma=1.0,
                    eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
 }

@@ -51,7 +51,7 @@ def _grads(name, N=None, K=None):
 @pytest.mark.parametrize("name", ["A_gmm", "B_funnel", "C_manygmm_dds_small", "Cvar_manygmm", "Ckl_manygmm_geffner",
                                   "ULA_gmm", "ULAsn_funnel", "ULAsn_gmm_dds", "lin_funnel",
                                   "LDVI_gmm", "LDVI_funnel_dds", "LDVI_manygmm_dds", "UDsna_funnel", "UD_gmm",
-                                  "UDe_gmm", "UDesna_funnel_dds", "UDea_gmm"])
+                                  "UDe_gmm", "UDesna_funnel_dds", "UDea_gmm", "CAISUHA_gmm", "CAISUHA_manygmm_dds"])
 def test_gradient_parity(name):
     c, unf, g32, g64, gp, l64, lp_ = _grads(name)
     assert torch.isfinite(gp).all()
@@ -67,7 +67,7 @@ def test_gradient_parity(name):
 @pytest.mark.parametrize("name,K", [("C_manygmm_dds_small", 2), ("ULAsn_gmm_dds", 1), ("ULAsn_gmm_dds", 2), ("A_gmm", 1), ("A_gmm", 2),
                                     ("Cvar_manygmm", 1), ("Cvar_manygmm", 2), ("ULAsn_funnel", 1), ("D_lgcp", 1), ("D_lgcp", 2),
                                     ("D_lgcp_ula", 1), ("LDVI_gmm", 1), ("LDVI_gmm", 2), ("LDVI_funnel_dds", 1), ("UD_gmm", 1),
-                                    ("UDea_gmm", 1), ("UDesna_funnel_dds", 2)])
+                                    ("UDea_gmm", 1), ("UDesna_funnel_dds", 2), ("CAISUHA_gmm", 1), ("CAISUHA_manygmm_dds", 2)])
 def test_short_bridges_every_path(name, K):
     """Node-form boundaries: with K = 1 and 2 every trajectory point is a first or last node (a single use of the network
     evaluation), on the tensor-core, FP32-FMA and lgcp wide paths and for both time-index conventions (CAIS: NN(z_j, j);

@@ -42,7 +42,7 @@ def _run_both(name, N=None, K=None, dtype=torch.float32):
 @pytest.mark.parametrize("name", ["A_gmm", "B_funnel", "C_manygmm_dds_small", "Cvar_manygmm", "Ckl_manygmm_geffner",
                                   "ULA_gmm", "ULAsn_funnel", "ULAsn_gmm_dds", "lin_funnel",
                                   "LDVI_gmm", "LDVI_funnel_dds", "LDVI_manygmm_dds", "UDsna_funnel", "UD_gmm",
-                                  "UDe_gmm", "UDesna_funnel_dds", "UDea_gmm"])
+                                  "UDe_gmm", "UDesna_funnel_dds", "UDea_gmm", "CAISUHA_gmm", "CAISUHA_manygmm_dds"])
 def test_forward_parity_small(name):
     c, (loss_o, l_o, z_o), (loss_p, l_p, z_p) = _run_both(name)
     fin = torch.isfinite(l_o)

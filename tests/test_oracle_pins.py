@@ -125,7 +125,7 @@ def test_underdamped_variants_agree_where_the_reference_formulas_coincide():
     assert gaps[1] < gaps[0] / 2.5 and gaps[0] < 1e-2, gaps
 
 
-@pytest.mark.parametrize("mode", ["MCD_U_a-lp", "MCD_U_a-lp-sn", "MCD_U_e-lp-sna", "MCD_U_ea-lp-sn"])
+@pytest.mark.parametrize("mode", ["MCD_U_a-lp", "MCD_U_a-lp-sn", "MCD_U_e-lp-sna", "MCD_U_ea-lp-sn", "MCD_CAIS_UHA_sn"])
 def test_ldvi_weights_are_unbiased(mode):
     """E[exp(w)] = Z = 1 for ANY parameters: the momentum refresh is a proper Markov kernel, the leapfrog step a
     volume-preserving bijection, the backward kernel a normalised density (Geffner & Domke 2021, eq. 9).  Pins the
