@@ -1,0 +1,676 @@
+// Block-cooperative FP32 path for FEW particles x WIDE networks (the README's geffner emb_dim-130 configs: N = 2000, K = 256,
+// hidden_pad 136, README.md:30,34 -- and every small-N run of the overdamped modes that the tensor-core kernels do not take).
+//
+// Same contract as bridge_fwd_kernel / bridge_bwd_kernel (bridge_fwd.cu, bridge_bwd.cu; the step algebra and its citations
+// are documented there): replaces vmap(compute_log_elbo) (src/mcdboundingmachine.py:126-205) over src/mcd_cais.py:46-89 /
+// src/mcd_cais_var.py:56-101 / src/mcd_over_orig.py:18-55 and its jax.grad (src/main.py:174-176).
+//
+// Why a second mapping: with one thread per particle, N = 2000 gives 63 warps for 592 scheduler slots and every warp walks
+// 257 nodes of ~70 k serial instructions (53 ms per train iteration at hidden_pad 136).  Here a CTA owns 32 particles and
+// ALL of its warps work on the network of those 32 particles as shared-memory matrix operations:
+//   S1 = act(U1^T X + c1[t])                    [HP][32]   element-wise over all threads
+//   S2 = act(W2^T S1 + U2^T X + c2[t])          [HP][32]   register-tiled GEMM (8 units x 2 particles per thread), operands in smem
+//   O  = W3^T (S2 + skip S1) + U3^T X + c3[t]   [d][32]
+// and in the reverse pass dP2 = (W3 Vo) o act'(pre2), gW2 += S1 dP2^T (4x4 register tiles that stay in registers over ALL
+// nodes and particle tiles of the CTA: one flush at the end instead of 18 k atomics per node), dA1 = W2 dP2 from a
+// transposed copy of W2, dP1 = dA1 o act'(pre1), dX = U1 dP1 + U2 dP2 + U3 Vo.  The per-particle step algebra (keys, Gaussians,
+// target score / HVP, kernel means, log-weights, cotangent carry) runs on the first warp between the matrix phases.
+// Shared memory at hidden_pad 136: W2 + W2^T 148 KB, three [136][32] activation arrays 52 KB, small tables 5 KB.
+#include "net_bwd.cuh"
+
+namespace cmcd {
+
+constexpr int BK_T = 384;      // threads per CTA (12 warps)
+constexpr int BK_P = 32;       // particles per CTA (= the first warp)
+constexpr int BK_MAXT = 4;     // 4x4 weight-gradient tiles per thread held in registers: (HP/4)^2 <= BK_MAXT * BK_T  =>  HP <= 156
+constexpr int BK_HP_MAX = 156;
+
+template <int D>
+__device__ __forceinline__ float bk_gauss_logprob(const float (&x)[D], const float (&mean)[D], float scale, float lognorm) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const float v = (x[j] - mean[j]) / scale;
+        s += -0.5f * v * v - lognorm;
+    }
+    return s;
+}
+
+// ---- network forward on the CTA's 32 particles.  In: sX [D][32].  Out: sO [D][32] = RAW output (before clamp / out_scale),
+// S1 = a1, S2 = a2, S3 = act'(pre2) if STORE.  Contains two __syncthreads(); the caller synchronises before (sX written) and
+// after (sO complete).
+template <int D, int ACT, bool STORE>
+__device__ __forceinline__ void bk_net_fwd(const NetView& nv, const NetSmem& s, int HP, int t, float* __restrict__ S1,
+                                           float* __restrict__ S2, float* __restrict__ S3, const float* __restrict__ sX,
+                                           float* __restrict__ sO) {
+    constexpr bool has_u2 = (ACT == ACT_SOFTPLUS), has_u3 = (ACT == ACT_SOFTPLUS);
+    constexpr float skip = (ACT == ACT_SOFTPLUS) ? 1.f : 0.f;
+    const int tid = threadIdx.x;
+    const float* __restrict__ c1 = nv.c1 + (size_t)t * HP;
+    const float* __restrict__ c2 = nv.c2 + (size_t)t * HP;
+    const float* __restrict__ c3 = nv.c3 + (size_t)t * D;
+    // layer 1
+    for (int idx = tid; idx < HP * BK_P; idx += BK_T) {
+        const int j = idx >> 5, p = idx & 31;
+        float pre = __ldg(c1 + j);
+#pragma unroll
+        for (int a = 0; a < D; ++a) pre = fmaf(sX[a * BK_P + p], s.U1[a * HP + j], pre);
+        S1[idx] = act_fwd<ACT>(pre);
+    }
+    __syncthreads();
+    // layer 2: thread tile = 8 units x 2 particles
+    const int ntile = (HP >> 3) * (BK_P >> 1);
+    for (int tile = tid; tile < ntile; tile += BK_T) {
+        const int j0 = (tile >> 4) << 3, p0 = (tile & 15) << 1;
+        float acc[8][2];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            float b0 = __ldg(c2 + j0 + jj), b1 = b0;
+            if (has_u2) {
+#pragma unroll
+                for (int a = 0; a < D; ++a) {
+                    const float u = s.U2[a * HP + j0 + jj];
+                    b0 = fmaf(sX[a * BK_P + p0], u, b0);
+                    b1 = fmaf(sX[a * BK_P + p0 + 1], u, b1);
+                }
+            }
+            acc[jj][0] = b0; acc[jj][1] = b1;
+        }
+#pragma unroll 4
+        for (int i = 0; i < HP; ++i) {
+            const float4 w0 = *reinterpret_cast<const float4*>(s.W2 + (size_t)i * HP + j0);
+            const float4 w1 = *reinterpret_cast<const float4*>(s.W2 + (size_t)i * HP + j0 + 4);
+            const float2 h = *reinterpret_cast<const float2*>(S1 + i * BK_P + p0);
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                acc[jj][0] = fmaf(h.x, w[jj], acc[jj][0]);
+                acc[jj][1] = fmaf(h.y, w[jj], acc[jj][1]);
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int o = (j0 + jj) * BK_P + p0 + q;
+                if constexpr (STORE) {
+                    float a2, g2;
+                    act_fwd_grad<ACT>(acc[jj][q], a2, g2);
+                    S2[o] = a2; S3[o] = g2;
+                } else {
+                    S2[o] = act_fwd<ACT>(acc[jj][q]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // layer 3: one output element per thread
+    for (int idx = tid; idx < D * BK_P; idx += BK_T) {
+        const int m = idx >> 5, p = idx & 31;
+        float o = __ldg(c3 + m);
+        if (has_u3) {
+#pragma unroll
+            for (int a = 0; a < D; ++a) o = fmaf(sX[a * BK_P + p], s.U3[a * D + m], o);
+        }
+        for (int j = 0; j < HP; ++j) o = fmaf(S2[j * BK_P + p] + skip * S1[j * BK_P + p], s.W3[j * D + m], o);
+        sO[idx] = o;
+    }
+}
+
+template <int D, int ACT>
+__global__ void __launch_bounds__(BK_T, 1) bridge_fwd_blk_kernel(const BridgeArgs a) {
+    extern __shared__ float4 smem4[];
+    float* sm = reinterpret_cast<float*>(smem4);
+    const int tid = threadIdx.x;
+    const NetView& nv = a.net;
+    const int HP = nv.HP;
+    NetSmem ns = net_stage_smem(nv, D, sm);
+    float* sTp = sm + net_smem_floats(D, HP);
+    const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
+    for (int i = tid; i < ntp; i += blockDim.x) sTp[i] = a.tgt.mix[i];
+    float* S1 = sTp + ((ntp + 3) & ~3);
+    float* S2 = S1 + (size_t)HP * BK_P;
+    float* sX = S2 + (size_t)HP * BK_P;
+    float* sO = sX + D * BK_P;
+    __syncthreads();
+
+    const bool cais = (a.mode == CMCD_MODE_CAIS_SN || a.mode == CMCD_MODE_CAIS_VAR_SN);
+    const bool nn_b = (a.mode != CMCD_MODE_ULA);
+    const bool nn_f = cais;
+    const int K = a.K;
+    const float out_scale = net_out_scale(nv);
+    const bool pt = tid < BK_P;   // particle thread
+
+    float mu[D], sig[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) { mu[j] = a.vd_mean[j]; sig[j] = expf(a.vd_logdiag[j]); }
+
+    const long long ntiles = (a.N + BK_P - 1) / BK_P;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long n_raw = tile * BK_P + tid;
+        const bool active = pt && n_raw < a.N;
+        const long long n = (pt && n_raw < a.N) ? n_raw : a.N - 1;   // idle lanes shadow the last particle, never store
+        Key k, ka;
+        float z[D], zn[D], xi[D], sp[D], dummy[D], nnv[D], mf[D];
+        float w = 0.f, wm = 0.f, lp = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) { nnv[j] = 0.f; z[j] = 0.f; sp[j] = 0.f; mf[j] = 0.f; }
+        if (pt) {
+            k = prng_key(a.seeds[n]);
+            split(k, ka, k);
+            normal_vec<D>(ka, xi);
+            float lq = 0.f;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                z[j] = sig[j] * xi[j] + mu[j];
+                const float v = (z[j] - mu[j]) / sig[j];
+                lq += -0.5f * v * v - logf(2.5066282746310002f * sig[j]);
+            }
+            w = -lq;
+            if (a.traj && active) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) a.traj[((size_t)0 * D + j) * a.N + n] = z[j];
+            }
+            lp = target_eval<D, false>(a.tgt, sTp, z, sp, dummy, dummy);
+            ka = split_first(k);    // mcdboundingmachine.py:162
+            k = split_second(ka);   // mcd_cais.py:94
+#pragma unroll
+            for (int j = 0; j < D; ++j) sX[j * BK_P + tid] = z[j];
+        }
+        if (nn_f) {   // NN(z_0, 0)
+            __syncthreads();
+            bk_net_fwd<D, ACT, false>(nv, ns, HP, 0, S1, S2, nullptr, sX, sO);
+            __syncthreads();
+            if (pt) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) nnv[j] = out_scale * fminf(fmaxf(sO[j * BK_P + tid], -nv.out_clip), nv.out_clip);
+            }
+        }
+        for (int i = 0; i < K; ++i) {
+            const float beta = __ldg(a.betas + i), eps = __ldg(a.eps + i);
+            const float scale = sqrtf(2.0f * eps);
+            if (pt) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const float sq = -((z[j] - mu[j]) / sig[j]) / sig[j];
+                    const float gu = fminf(fmaxf(sp[j], -a.clip_t), a.clip_t);
+                    const float gq = fminf(fmaxf(sq, -a.clip_q), a.clip_q);
+                    const float uf = -(beta * gu + (1.0f - beta) * gq);
+                    mf[j] = z[j] - eps * uf;
+                }
+                if (nn_f) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) mf[j] = mf[j] - eps * nnv[j];
+                }
+                split(k, ka, k);
+                normal_vec<D>(ka, xi);
+#pragma unroll
+                for (int j = 0; j < D; ++j) { zn[j] = mf[j] + scale * xi[j]; sX[j * BK_P + tid] = zn[j]; }
+                lp = target_eval<D, false>(a.tgt, sTp, zn, sp, dummy, dummy);
+            }
+            if (nn_b) {
+                __syncthreads();
+                bk_net_fwd<D, ACT, false>(nv, ns, HP, cais ? i + 1 : i, S1, S2, nullptr, sX, sO);
+                __syncthreads();
+            }
+            if (pt) {
+                float mb[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const float sq = -((zn[j] - mu[j]) / sig[j]) / sig[j];
+                    const float gu = fminf(fmaxf(sp[j], -a.clip_t), a.clip_t);
+                    const float gq = fminf(fmaxf(sq, -a.clip_q), a.clip_q);
+                    const float ub = -(beta * gu + (1.0f - beta) * gq);
+                    mb[j] = zn[j] - eps * ub;
+                }
+                if (nn_b) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        nnv[j] = out_scale * fminf(fmaxf(sO[j * BK_P + tid], -nv.out_clip), nv.out_clip);
+                        mb[j] = mb[j] + eps * nnv[j];
+                    }
+                }
+                const float lognorm = logf(2.5066282746310002f * scale);
+                const float fk = bk_gauss_logprob<D>(zn, mf, scale, lognorm);
+                const float bk = bk_gauss_logprob<D>(z, mb, scale, lognorm);
+                wm += bk - fk;
+                k = split_second(k);
+#pragma unroll
+                for (int j = 0; j < D; ++j) z[j] = zn[j];
+                if (a.traj && active) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) a.traj[((size_t)(i + 1) * D + j) * a.N + n] = z[j];
+                }
+            }
+        }
+        if (active) {
+            w += wm;
+            w += lp;
+            a.out_negw[n] = -w;
+#pragma unroll
+            for (int j = 0; j < D; ++j) a.out_z[n * D + j] = z[j];
+        }
+        __syncthreads();   // sX / sO are rewritten by the next particle tile
+    }
+}
+
+// =====================================================================================================================
+// Reverse pass.  Node form exactly as bridge_bwd_kernel (bridge_bwd.cu): K + 1 nodes z_K .. z_0, one network recompute and one
+// pull-back per node with the combined output cotangent, one target score and one combined HVP per node.
+template <int D, int ACT>
+__global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArgs a, const float* __restrict__ cot_negw,
+                                                                 float* __restrict__ partials, const BwdLayout L) {
+    constexpr bool has_u2 = (ACT == ACT_SOFTPLUS), has_u3 = (ACT == ACT_SOFTPLUS);
+    constexpr float skip = (ACT == ACT_SOFTPLUS) ? 1.f : 0.f;
+    extern __shared__ float4 smem4[];
+    float* sm = reinterpret_cast<float*>(smem4);
+    const int tid = threadIdx.x;
+    const NetView& nv = a.net;
+    const int HP = nv.HP;
+    NetSmem ns = net_stage_smem(nv, D, sm);
+    float* sW2T = sm + net_smem_floats(D, HP);
+    for (int idx = tid; idx < HP * HP; idx += blockDim.x) { const int i = idx / HP, j = idx % HP; sW2T[(size_t)j * HP + i] = nv.W2[idx]; }
+    float* sTp = sW2T + (size_t)HP * HP;
+    const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
+    for (int i = tid; i < ntp; i += blockDim.x) sTp[i] = a.tgt.mix[i];
+    float* S1 = sTp + ((ntp + 3) & ~3);
+    float* S2 = S1 + (size_t)HP * BK_P;
+    float* S3 = S2 + (size_t)HP * BK_P;
+    float* sX = S3 + (size_t)HP * BK_P;
+    float* sO = sX + D * BK_P;
+    float* sVo = sO + D * BK_P;
+    float* sDx = sVo + D * BK_P;
+    __syncthreads();
+
+    float* part = partials + (size_t)blockIdx.x * L.P;
+    const bool cais = (a.mode == CMCD_MODE_CAIS_SN || a.mode == CMCD_MODE_CAIS_VAR_SN);
+    const bool pathwise = a.mode != CMCD_MODE_CAIS_VAR_SN;
+    const bool nn_b = (a.mode != CMCD_MODE_ULA);
+    const bool nn_f = cais;
+    const int K = a.K;
+    const float out_scale = net_out_scale(nv);
+    const bool pt = tid < BK_P;
+
+    float mu[D], sig[D], ivar[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) { mu[j] = a.vd_mean[j]; sig[j] = expf(a.vd_logdiag[j]); ivar[j] = 1.0f / (sig[j] * sig[j]); }
+
+    // weight-gradient accumulators: 4x4 tiles over interleaved rows (tile (ti, tj): rows ti + G r, columns tj + G q), fixed per thread
+    const int G = HP >> 2;
+    float gw[BK_MAXT][4][4];
+#pragma unroll
+    for (int r0 = 0; r0 < BK_MAXT; ++r0)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gw[r0][r][q] = 0.f;
+
+    const long long ntiles = (a.N + BK_P - 1) / BK_P;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long n_raw = tile * BK_P + tid;
+        const bool active = pt && n_raw < a.N;
+        const long long n = active ? n_raw : a.N - 1;
+        const float c = active ? -cot_negw[n] : 0.f;   // dL/dw_n (zero for shadow lanes: all their cotangents vanish)
+        float x[D], zup[D], zprev[D], carry[D], rS[D], gmu[D], gls[D], zero[D], hv[D], sx[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            x[j] = pt ? a.traj[((size_t)K * D + j) * a.N + n] : 0.f;
+            gmu[j] = 0.f; gls[j] = 0.f; zero[j] = 0.f; carry[j] = 0.f; rS[j] = 0.f; zup[j] = 0.f; hv[j] = 0.f; sx[j] = 0.f; zprev[j] = 0.f;
+        }
+        float cgb = 0.f, cge = 0.f;
+        const int t0 = cais ? 0 : -1;
+        for (int j = K; j >= 0; --j) {
+            const bool hasB = j > 0, hasF = j < K;
+            const int t = t0 + j;
+            const bool use_nn = K > 0 && (cais || (nn_b && hasB));
+            const float bB = hasB ? __ldg(a.betas + j - 1) : 0.f, eB = hasB ? __ldg(a.eps + j - 1) : 0.f;
+            const float bF = hasF ? __ldg(a.betas + j) : 0.f, eF = hasF ? __ldg(a.eps + j) : 0.f;
+            const float tsB = hasB ? 2.0f * eB : 1.f, tsF = hasF ? 2.0f * eF : 1.f;
+            const float ombB = 1.0f - bB, ombF = 1.0f - bF;
+            const float cB = hasB ? c : 0.f, cF = hasF ? c : 0.f;
+            const float eFn = nn_f ? eF : 0.f;
+            float sq[D], mk_t[D], mk_q[D], uB[D], uF[D], dc[D], nn[D], o[D], dx[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) { nn[d] = 0.f; dx[d] = 0.f; o[d] = 0.f; sq[d] = 0.f; mk_t[d] = 0.f; mk_q[d] = 0.f; uB[d] = 0.f; uF[d] = 0.f; dc[d] = 0.f; }
+            if (pt) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) zprev[d] = hasB ? a.traj[((size_t)(j - 1) * D + d) * a.N + n] : 0.f;
+                target_eval<D, false>(a.tgt, sTp, x, sx, zero, hv);
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    sq[d] = -(x[d] - mu[d]) * ivar[d];
+                    mk_t[d] = (fabsf(sx[d]) <= a.clip_t) ? 1.f : 0.f;
+                    mk_q[d] = (fabsf(sq[d]) <= a.clip_q) ? 1.f : 0.f;
+                    const float gu = fminf(fmaxf(sx[d], -a.clip_t), a.clip_t);
+                    const float gq = fminf(fmaxf(sq[d], -a.clip_q), a.clip_q);
+                    dc[d] = gu - gq;
+                    uB[d] = -(bB * gu + ombB * gq);
+                    uF[d] = -(bF * gu + ombF * gq);
+                    sX[d * BK_P + tid] = x[d];
+                }
+            }
+            if (use_nn) {
+                __syncthreads();
+                bk_net_fwd<D, ACT, true>(nv, ns, HP, t, S1, S2, S3, sX, sO);
+                __syncthreads();
+            }
+            float GB[D], GF[D], rB[D], xs[D], vv[D], wq[D];
+            float rr = 0.f, xx = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) { GB[d] = 0.f; GF[d] = 0.f; rB[d] = 0.f; xs[d] = 0.f; vv[d] = 0.f; wq[d] = 0.f; }
+            if (pt) {
+                if (use_nn) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) { o[d] = sO[d * BK_P + tid]; nn[d] = out_scale * fminf(fmaxf(o[d], -nv.out_clip), nv.out_clip); }
+                }
+                float gos = 0.f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const float meanB = (x[d] - eB * uB[d]) + eB * nn[d];
+                    const float meanF = (x[d] - eF * uF[d]) - eFn * nn[d];
+                    rB[d] = (zprev[d] - meanB) / tsB;
+                    GB[d] = cB * rB[d];
+                    rr = fmaf(rB[d], rB[d], rr);
+                    xs[d] = (zup[d] - meanF) / tsF;
+                    xx = fmaf(xs[d], xs[d], xx);
+                    GF[d] = pathwise ? carry[d] : -cF * xs[d];
+                    if (!hasF) GF[d] = 0.f;
+                    vv[d] = eB * GB[d] - eFn * GF[d];
+                    wq[d] = eB * ombB * GB[d] + eF * ombF * GF[d];
+                    if (use_nn) {   // output-layer cotangent on the raw output (clamp mask, out_scale)
+                        const float oc = fminf(fmaxf(o[d], -nv.out_clip), nv.out_clip);
+                        gos = fmaf(vv[d], oc, gos);
+                        sVo[d * BK_P + tid] = (fabsf(o[d]) <= nv.out_clip) ? vv[d] * out_scale : 0.f;
+                    }
+                }
+                if (use_nn) {
+                    gos = warp_sum_f(gos);
+                    if (tid == 0 && gos != 0.f) atomicAdd(part + L.os, gos);
+                }
+            }
+            if (use_nn) {
+                __syncthreads();
+                // ---- dP2 = (W3 Vo) o act'(pre2) -> S3
+                for (int idx = tid; idx < HP * BK_P; idx += BK_T) {
+                    const int jj = idx >> 5, p = idx & 31;
+                    float d2 = 0.f;
+#pragma unroll
+                    for (int m = 0; m < D; ++m) d2 = fmaf(ns.W3[jj * D + m], sVo[m * BK_P + p], d2);
+                    S3[idx] = d2 * S3[idx];
+                }
+                __syncthreads();
+                // ---- gW2 += S1 dP2^T into the register tiles
+#pragma unroll
+                for (int r0 = 0; r0 < BK_MAXT; ++r0) {
+                    const int tl = tid + r0 * BK_T;
+                    if (tl < G * G) {
+                        const int ti = tl / G, tj = tl % G;
+#pragma unroll 2
+                        for (int p = 0; p < BK_P; p += 4) {
+                            float4 A[4], B[4];
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                A[r] = *reinterpret_cast<const float4*>(S1 + (ti + G * r) * BK_P + p);
+                                B[r] = *reinterpret_cast<const float4*>(S3 + (tj + G * r) * BK_P + p);
+                            }
+#pragma unroll
+                            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    float s = gw[r0][r][q];
+                                    s = fmaf(A[r].x, B[q].x, s); s = fmaf(A[r].y, B[q].y, s);
+                                    s = fmaf(A[r].z, B[q].z, s); s = fmaf(A[r].w, B[q].w, s);
+                                    gw[r0][r][q] = s;
+                                }
+                        }
+                    }
+                }
+                // ---- skinny cotangents of this node: gc2[t], gU2, gW3 (one hidden unit per thread), gc3[t], gU3
+                for (int jj = tid; jj < HP; jj += BK_T) {
+                    float s2 = 0.f, gu2[D], gw3[D];
+#pragma unroll
+                    for (int m = 0; m < D; ++m) { gu2[m] = 0.f; gw3[m] = 0.f; }
+                    for (int p = 0; p < BK_P; ++p) {
+                        const float d2 = S3[jj * BK_P + p], h = S2[jj * BK_P + p] + skip * S1[jj * BK_P + p];
+                        s2 += d2;
+#pragma unroll
+                        for (int m = 0; m < D; ++m) {
+                            if (has_u2) gu2[m] = fmaf(d2, sX[m * BK_P + p], gu2[m]);
+                            gw3[m] = fmaf(h, sVo[m * BK_P + p], gw3[m]);
+                        }
+                    }
+                    atomicAdd(part + L.c2 + (size_t)t * HP + jj, s2);
+#pragma unroll
+                    for (int m = 0; m < D; ++m) {
+                        if (has_u2) atomicAdd(part + L.U2 + m * HP + jj, gu2[m]);
+                        atomicAdd(part + L.W3 + jj * D + m, gw3[m]);
+                    }
+                }
+                for (int job = tid; job < D + (has_u3 ? D * D : 0); job += BK_T) {
+                    float sacc = 0.f;
+                    if (job < D) {
+                        for (int p = 0; p < BK_P; ++p) sacc += sVo[job * BK_P + p];
+                        atomicAdd(part + L.c3 + (size_t)t * D + job, sacc);
+                    } else {
+                        const int aa = (job - D) / D, m = (job - D) % D;
+                        for (int p = 0; p < BK_P; ++p) sacc = fmaf(sX[aa * BK_P + p], sVo[m * BK_P + p], sacc);
+                        atomicAdd(part + L.U3 + aa * D + m, sacc);
+                    }
+                }
+                __syncthreads();
+                // ---- dA1 = W2 dP2 (+ skip W3 Vo); dP1 = dA1 o act'(pre1) -> S2   (thread tile = 8 units x 2 particles, W2^T rows)
+                {
+                    const float* __restrict__ c1 = nv.c1 + (size_t)t * HP;
+                    const int ntile = (HP >> 3) * (BK_P >> 1);
+                    for (int tl = tid; tl < ntile; tl += BK_T) {
+                        const int i0 = (tl >> 4) << 3, p0 = (tl & 15) << 1;
+                        float acc[8][2];
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) { acc[ii][0] = 0.f; acc[ii][1] = 0.f; }
+#pragma unroll 4
+                        for (int jj = 0; jj < HP; ++jj) {
+                            const float4 w0 = *reinterpret_cast<const float4*>(sW2T + (size_t)jj * HP + i0);
+                            const float4 w1 = *reinterpret_cast<const float4*>(sW2T + (size_t)jj * HP + i0 + 4);
+                            const float2 h = *reinterpret_cast<const float2*>(S3 + jj * BK_P + p0);
+                            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                            for (int ii = 0; ii < 8; ++ii) {
+                                acc[ii][0] = fmaf(h.x, wv[ii], acc[ii][0]);
+                                acc[ii][1] = fmaf(h.y, wv[ii], acc[ii][1]);
+                            }
+                        }
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) {
+                            const int i = i0 + ii;
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const int p = p0 + q;
+                                float da1 = acc[ii][q];
+                                if (skip != 0.f) {
+#pragma unroll
+                                    for (int m = 0; m < D; ++m) da1 = fmaf(ns.W3[i * D + m], sVo[m * BK_P + p], da1);
+                                }
+                                float pre = __ldg(c1 + i);
+#pragma unroll
+                                for (int m = 0; m < D; ++m) pre = fmaf(sX[m * BK_P + p], ns.U1[m * HP + i], pre);
+                                float a1, g1;
+                                act_fwd_grad<ACT>(pre, a1, g1);
+                                S2[i * BK_P + p] = da1 * g1;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                // ---- gc1[t], gU1 (one hidden unit per thread); dX = U1 dP1 + U2 dP2 + U3 Vo (one element per thread)
+                for (int jj = tid; jj < HP; jj += BK_T) {
+                    float s1 = 0.f, gu1[D];
+#pragma unroll
+                    for (int m = 0; m < D; ++m) gu1[m] = 0.f;
+                    for (int p = 0; p < BK_P; ++p) {
+                        const float d1 = S2[jj * BK_P + p];
+                        s1 += d1;
+#pragma unroll
+                        for (int m = 0; m < D; ++m) gu1[m] = fmaf(d1, sX[m * BK_P + p], gu1[m]);
+                    }
+                    atomicAdd(part + L.c1 + (size_t)t * HP + jj, s1);
+#pragma unroll
+                    for (int m = 0; m < D; ++m) atomicAdd(part + L.U1 + m * HP + jj, gu1[m]);
+                }
+                for (int idx = BK_T - 1 - tid; idx < D * BK_P; idx += BK_T) {   // reversed: the last warps have no hidden unit above
+                    const int aa = idx >> 5, p = idx & 31;
+                    float acc = 0.f;
+                    if (has_u3) {
+#pragma unroll
+                        for (int m = 0; m < D; ++m) acc = fmaf(ns.U3[aa * D + m], sVo[m * BK_P + p], acc);
+                    }
+                    for (int jj = 0; jj < HP; ++jj) {
+                        acc = fmaf(ns.U1[aa * HP + jj], S2[jj * BK_P + p], acc);
+                        if (has_u2) acc = fmaf(ns.U2[aa * HP + jj], S3[jj * BK_P + p], acc);
+                    }
+                    sDx[idx] = acc;
+                }
+                __syncthreads();
+            }
+            if (pt) {
+                if (use_nn) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) dx[d] = sDx[d * BK_P + tid];
+                }
+                if (pathwise) {
+                    float vm[D], dummy[D];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) vm[d] = mk_t[d] * (bB * eB * GB[d] + bF * eF * GF[d]);
+                    target_eval<D, true>(a.tgt, sTp, x, dummy, vm, hv);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        const float fpart = hasF ? (GF[d] - cF * rS[d]) : c * sx[d];
+                        carry[d] = fpart + GB[d] - wq[d] * ivar[d] * mk_q[d] + hv[d] + dx[d];
+                    }
+                }
+                {
+                    float gb = cgb, ge = cge;
+                    float ngb = 0.f, nge = cB * rr;
+                    if (!pathwise) ge -= cF * xx;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        gb += eF * GF[d] * dc[d];
+                        ge += GF[d] * (-uF[d] - (nn_f ? nn[d] : 0.f) + (pathwise ? xs[d] : 0.f));
+                        ngb += eB * GB[d] * dc[d];
+                        nge += GB[d] * (-uB[d] + nn[d]);
+                        gmu[d] += wq[d] * ivar[d] * mk_q[d];
+                        gls[d] += wq[d] * mk_q[d] * (-2.0f * sq[d]);
+                    }
+                    if (hasF) {
+                        gb = warp_sum_f(gb); ge = warp_sum_f(ge);
+                        if (tid == 0) { atomicAdd(part + L.beta + j, gb); atomicAdd(part + L.eps + j, ge); }
+                    }
+                    cgb = ngb; cge = nge;
+                }
+#pragma unroll
+                for (int d = 0; d < D; ++d) { rS[d] = rB[d]; zup[d] = x[d]; x[d] = zprev[d]; }
+            }
+        }
+        if (pt) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                if (pathwise) { gmu[j] += carry[j]; gls[j] += carry[j] * (zup[j] - mu[j]); }
+                gls[j] += c;
+                const float m1 = warp_sum_f(gmu[j]), m2 = warp_sum_f(gls[j]);
+                if (tid == 0) { atomicAdd(part + L.mu + j, m1); atomicAdd(part + L.ls + j, m2); }
+            }
+        }
+        __syncthreads();
+    }
+    // flush the weight-gradient tiles (each (i, j) has exactly one owner in the CTA)
+#pragma unroll
+    for (int r0 = 0; r0 < BK_MAXT; ++r0) {
+        const int tl = tid + r0 * BK_T;
+        if (tl < G * G) {
+            const int ti = tl / G, tj = tl % G;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) part[L.W2 + (ti + G * r) * HP + (tj + G * q)] = gw[r0][r][q];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- launchers
+static size_t blk_fwd_smem(int D, int HP) {
+    return (net_smem_floats(D, HP) + MIX_MAX * MIX_STRIDE + 2 * (size_t)HP * BK_P + 2 * (size_t)D * BK_P + 8) * sizeof(float);
+}
+static size_t blk_bwd_smem(int D, int HP) {
+    return (net_smem_floats(D, HP) + (size_t)HP * HP + MIX_MAX * MIX_STRIDE + 3 * (size_t)HP * BK_P + 4 * (size_t)D * BK_P + 8) * sizeof(float);
+}
+
+// Few particles (the one-thread-per-particle kernels would leave most SMs idle), a network, widths the register tiles cover.
+bool blk_supported(const BridgeArgs& a, int D, int num_sms) {
+    if (a.net.arch == CMCD_ARCH_NONE || a.K < 1 || a.mode > CMCD_MODE_CAIS_VAR_SN || a.mode == CMCD_MODE_ULA) return false;
+    if (D != 2 && D != 10) return false;
+    const int HP = a.net.HP;
+    if (HP > BK_HP_MAX || (HP & 7)) return false;
+    if (blk_bwd_smem(D, HP) > 227 * 1024) return false;
+    return a.N <= (long long)BK_P * num_sms * 2;
+}
+
+template <int D, int ACT>
+static int launch_fwd_blk_t(const BridgeArgs& a, cudaStream_t st, int num_sms) {
+    const size_t smem = blk_fwd_smem(D, a.net.HP);
+    auto kern = bridge_fwd_blk_kernel<D, ACT>;
+    CMCD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ntiles = (a.N + BK_P - 1) / BK_P;
+    const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    kern<<<grid < 1 ? 1 : grid, BK_T, smem, st>>>(a);
+    CMCD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_bridge_fwd_blk(const BridgeArgs& a, int D, cudaStream_t st, int num_sms) {
+    const bool gelu = a.net.arch == CMCD_ARCH_DDS;
+    if (D == 2) return gelu ? launch_fwd_blk_t<2, ACT_GELU>(a, st, num_sms) : launch_fwd_blk_t<2, ACT_SOFTPLUS>(a, st, num_sms);
+    if (D == 10) return gelu ? launch_fwd_blk_t<10, ACT_GELU>(a, st, num_sms) : launch_fwd_blk_t<10, ACT_SOFTPLUS>(a, st, num_sms);
+    set_error("bridge_fwd_blk: dim=%d has no instantiation", D);
+    return 2;
+}
+
+size_t bridge_bwd_blk_workspace_bytes(int D, int K, int HP, int arch, int num_sms) {
+    return (size_t)num_sms * make_layout(D, K, HP, arch).P * sizeof(float);
+}
+
+template <int D, int ACT>
+static int launch_bwd_blk_t(const BridgeArgs& a, cudaStream_t st, int num_sms, const float* cot, const BwdOut& out, void* ws, size_t ws_bytes) {
+    const int HP = a.net.HP;
+    const size_t smem = blk_bwd_smem(D, HP);
+    auto kern = bridge_bwd_blk_kernel<D, ACT>;
+    CMCD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const BwdLayout L = make_layout(D, a.K, HP, a.net.arch);
+    const long long ntiles = (a.N + BK_P - 1) / BK_P;
+    int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    if (grid < 1) grid = 1;
+    const size_t need = (size_t)grid * L.P * sizeof(float);
+    if (ws_bytes < need || !ws) { set_error("bridge_bwd_blk: workspace too small (%zu < %zu)", ws_bytes, need); return 2; }
+    CMCD_CUDA_OK(cudaMemsetAsync(ws, 0, need, st));
+    kern<<<grid, BK_T, smem, st>>>(a, cot, (float*)ws, L);
+    CMCD_CUDA_OK(cudaGetLastError());
+    return launch_bwd_reduce((const float*)ws, grid, L, out, HP, D, a.K, st);
+}
+
+int launch_bridge_bwd_blk(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, const float* cot_negw,
+                          float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
+                          const cmcd_net_grad* g, void* ws, size_t ws_bytes) {
+    BwdOut o{};
+    if (g) {
+        o.W2 = g->W2; o.U1 = g->U1; o.U2 = g->U2; o.U3 = g->U3; o.W3 = g->W3;
+        o.c1 = g->c1; o.c2 = g->c2; o.c3 = g->c3; o.os = g->out_scale;
+    }
+    o.beta = g_betas; o.eps = g_eps; o.mu = g_vd_mean; o.ls = g_vd_logdiag;
+    const bool gelu = a.net.arch == CMCD_ARCH_DDS;
+    if (D == 2) return gelu ? launch_bwd_blk_t<2, ACT_GELU>(a, st, num_sms, cot_negw, o, ws, ws_bytes)
+                            : launch_bwd_blk_t<2, ACT_SOFTPLUS>(a, st, num_sms, cot_negw, o, ws, ws_bytes);
+    if (D == 10) return gelu ? launch_bwd_blk_t<10, ACT_GELU>(a, st, num_sms, cot_negw, o, ws, ws_bytes)
+                             : launch_bwd_blk_t<10, ACT_SOFTPLUS>(a, st, num_sms, cot_negw, o, ws, ws_bytes);
+    set_error("bridge_bwd_blk: dim=%d has no instantiation", D);
+    return 2;
+}
+
+}  // namespace cmcd

@@ -29,6 +29,11 @@ size_t bridge_bwd_tc_workspace_bytes(int D, int K, int num_sms);
 int launch_bridge_bwd_tc(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, const float* cot_negw,
                          float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
                          const cmcd_net_grad* g_net, void* ws, size_t ws_bytes);
+bool blk_supported(const BridgeArgs& a, int D, int num_sms);
+int launch_bridge_fwd_blk(const BridgeArgs& a, int D, cudaStream_t st, int num_sms);
+int launch_bridge_bwd_blk(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, const float* cot_negw,
+                          float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
+                          const cmcd_net_grad* g_net, void* ws, size_t ws_bytes);
 int launch_bridge_ud_fwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sms);
 int launch_bridge_ud_bwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, const float* cot_negw,
                          float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
@@ -153,6 +158,9 @@ int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
     // hidden width 64: tcgen05 tiles; other widths: FP32 FMA kernel.  CMCD_DISABLE_TC=1 forces the FP32 kernel (A/B runs).
     if (fwd_tc_supported(a, desc->dim) && !std::getenv("CMCD_DISABLE_TC"))
         return launch_bridge_fwd_tc(a, desc->dim, (cudaStream_t)stream, sms);
+    // few particles x wide network: block-cooperative mapping (bridge_blk.cu).  CMCD_DISABLE_BLK=1 keeps one thread per particle.
+    if (blk_supported(a, desc->dim, sms) && !std::getenv("CMCD_DISABLE_BLK"))
+        return launch_bridge_fwd_blk(a, desc->dim, (cudaStream_t)stream, sms);
     return launch_bridge_fwd(a, desc->dim, (cudaStream_t)stream, sms);
 }
 
@@ -204,6 +212,9 @@ int cmcd_bridge_bwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
     if (bwd_tc_supported(a, desc->dim) && !std::getenv("CMCD_DISABLE_TC"))
         return launch_bridge_bwd_tc(a, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
                                     g_eps, g_net, workspace, workspace_bytes);
+    if (blk_supported(a, desc->dim, sms) && !std::getenv("CMCD_DISABLE_BLK"))
+        return launch_bridge_bwd_blk(a, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
+                                     g_eps, g_net, workspace, workspace_bytes);
     return launch_bridge_bwd(a, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
                              g_eps, g_net, workspace, workspace_bytes);
 }
