@@ -15,13 +15,16 @@
 // nodes and particle tiles of the CTA: one flush at the end instead of 18 k atomics per node), dA1 = W2 dP2 from a
 // transposed copy of W2, dP1 = dA1 o act'(pre1), dX = U1 dP1 + U2 dP2 + U3 Vo.  The per-particle step algebra (keys, Gaussians,
 // target score / HVP, kernel means, log-weights, cotangent carry) runs on the first warp between the matrix phases.
-// Shared memory at hidden_pad 136: W2 + W2^T 148 KB, three [136][32] activation arrays 52 KB, small tables 5 KB.
+// Shared memory at hidden_pad 136: W2 + W2^T 148 KB, three [136][36] activation arrays 59 KB, small tables 5 KB.
 #include "net_bwd.cuh"
 
 namespace cmcd {
 
 constexpr int BK_T = 384;      // threads per CTA (12 warps)
 constexpr int BK_P = 32;       // particles per CTA (= the first warp)
+constexpr int BK_RS = 36;      // row stride of the [HP][32] activation arrays: consecutive rows start 4 banks apart, so the float4
+                               // reads of the weight-gradient tiles (one row per lane) are conflict-free (ncu: 34 % of the stall
+                               // samples sat on that read at stride 32) and rows stay 16-byte aligned
 constexpr int BK_MAXT = 4;     // 4x4 weight-gradient tiles per thread held in registers: (HP/4)^2 <= BK_MAXT * BK_T  =>  HP <= 156
 constexpr int BK_HP_MAX = 156;
 
@@ -42,7 +45,7 @@ __device__ __forceinline__ float bk_gauss_logprob(const float (&x)[D], const flo
 template <int D, int ACT, bool STORE>
 __device__ __forceinline__ void bk_net_fwd(const NetView& nv, const NetSmem& s, int HP, int t, float* __restrict__ S1,
                                            float* __restrict__ S2, float* __restrict__ S3, const float* __restrict__ sX,
-                                           float* __restrict__ sO) {
+                                           float* __restrict__ sO, float* __restrict__ sPart) {
     constexpr bool has_u2 = (ACT == ACT_SOFTPLUS), has_u3 = (ACT == ACT_SOFTPLUS);
     constexpr float skip = (ACT == ACT_SOFTPLUS) ? 1.f : 0.f;
     const int tid = threadIdx.x;
@@ -55,12 +58,12 @@ __device__ __forceinline__ void bk_net_fwd(const NetView& nv, const NetSmem& s, 
         float pre = __ldg(c1 + j);
 #pragma unroll
         for (int a = 0; a < D; ++a) pre = fmaf(sX[a * BK_P + p], s.U1[a * HP + j], pre);
-        S1[idx] = act_fwd<ACT>(pre);
+        S1[j * BK_RS + p] = act_fwd<ACT>(pre);
     }
     __syncthreads();
     // layer 2: thread tile = 8 units x 2 particles
     const int ntile = (HP >> 3) * (BK_P >> 1);
-    for (int tile = tid; tile < ntile; tile += BK_T) {
+    for (int tile = BK_T - 1 - tid; tile < ntile; tile += BK_T) {   // reversed: the particle warp (warp 0) gets matrix work last
         const int j0 = (tile >> 4) << 3, p0 = (tile & 15) << 1;
         float acc[8][2];
 #pragma unroll
@@ -80,7 +83,7 @@ __device__ __forceinline__ void bk_net_fwd(const NetView& nv, const NetSmem& s, 
         for (int i = 0; i < HP; ++i) {
             const float4 w0 = *reinterpret_cast<const float4*>(s.W2 + (size_t)i * HP + j0);
             const float4 w1 = *reinterpret_cast<const float4*>(s.W2 + (size_t)i * HP + j0 + 4);
-            const float2 h = *reinterpret_cast<const float2*>(S1 + i * BK_P + p0);
+            const float2 h = *reinterpret_cast<const float2*>(S1 + i * BK_RS + p0);
             const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
@@ -88,23 +91,37 @@ __device__ __forceinline__ void bk_net_fwd(const NetView& nv, const NetSmem& s, 
                 acc[jj][1] = fmaf(h.y, w[jj], acc[jj][1]);
             }
         }
+        // activation, and this tile's share of layer 3 (8 of the HP terms of every output of its 2 particles)
+        float o3[D][2];
+#pragma unroll
+        for (int m = 0; m < D; ++m) { o3[m][0] = 0.f; o3[m][1] = 0.f; }
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const int o = (j0 + jj) * BK_P + p0 + q;
+                const int o = (j0 + jj) * BK_RS + p0 + q;
+                float a2;
                 if constexpr (STORE) {
-                    float a2, g2;
+                    float g2;
                     act_fwd_grad<ACT>(acc[jj][q], a2, g2);
                     S2[o] = a2; S3[o] = g2;
                 } else {
-                    S2[o] = act_fwd<ACT>(acc[jj][q]);
+                    a2 = act_fwd<ACT>(acc[jj][q]);
                 }
+                const float hs = a2 + skip * S1[o];
+#pragma unroll
+                for (int m = 0; m < D; ++m) o3[m][q] = fmaf(hs, s.W3[(j0 + jj) * D + m], o3[m][q]);
             }
+        }
+        const int jg = tile >> 4;
+#pragma unroll
+        for (int m = 0; m < D; ++m) {
+            sPart[(jg * D + m) * BK_P + p0] = o3[m][0];
+            sPart[(jg * D + m) * BK_P + p0 + 1] = o3[m][1];
         }
     }
     __syncthreads();
-    // layer 3: one output element per thread
+    // layer 3: fixed-order sum of the HP/8 partials (deterministic), one output element per thread
     for (int idx = tid; idx < D * BK_P; idx += BK_T) {
         const int m = idx >> 5, p = idx & 31;
         float o = __ldg(c3 + m);
@@ -112,7 +129,7 @@ __device__ __forceinline__ void bk_net_fwd(const NetView& nv, const NetSmem& s, 
 #pragma unroll
             for (int a = 0; a < D; ++a) o = fmaf(sX[a * BK_P + p], s.U3[a * D + m], o);
         }
-        for (int j = 0; j < HP; ++j) o = fmaf(S2[j * BK_P + p] + skip * S1[j * BK_P + p], s.W3[j * D + m], o);
+        for (int g = 0; g < (HP >> 3); ++g) o += sPart[(g * D + m) * BK_P + p];
         sO[idx] = o;
     }
 }
@@ -128,10 +145,16 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_fwd_blk_kernel(const BridgeArg
     float* sTp = sm + net_smem_floats(D, HP);
     const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
     for (int i = tid; i < ntp; i += blockDim.x) sTp[i] = a.tgt.mix[i];
-    float* S1 = sTp + ((ntp + 3) & ~3);
-    float* S2 = S1 + (size_t)HP * BK_P;
-    float* sX = S2 + (size_t)HP * BK_P;
+    float2* sMu = reinterpret_cast<float2*>(sTp + ((ntp + 3) & ~3));   // many_gmm: dense component means (fast path, D = 2)
+    const bool fast_gmm = (D == 2) && a.tgt.kind == TGT_MANY_GMM;
+    if (fast_gmm)
+        for (int i = tid; i < a.tgt.ncomp; i += blockDim.x) sMu[i] = make_float2(a.tgt.mix[i * MIX_STRIDE], a.tgt.mix[i * MIX_STRIDE + 1]);
+    const ManyGmmConst gc = many_gmm_const(a.tgt);
+    float* S1 = reinterpret_cast<float*>(sMu + MIX_MAX);
+    float* S2 = S1 + (size_t)HP * BK_RS;
+    float* sX = S2 + (size_t)HP * BK_RS;
     float* sO = sX + D * BK_P;
+    float* sPart = sO + D * BK_P;   // [HP/8][D][32] layer-3 partials
     __syncthreads();
 
     const bool cais = (a.mode == CMCD_MODE_CAIS_SN || a.mode == CMCD_MODE_CAIS_VAR_SN);
@@ -171,7 +194,10 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_fwd_blk_kernel(const BridgeArg
 #pragma unroll
                 for (int j = 0; j < D; ++j) a.traj[((size_t)0 * D + j) * a.N + n] = z[j];
             }
-            lp = target_eval<D, false>(a.tgt, sTp, z, sp, dummy, dummy);
+            if constexpr (D == 2) {
+                if (fast_gmm) lp = many_gmm_eval<false>(gc, sMu, z[0], z[1], sp[0], sp[1], 0.f, 0.f, dummy[0], dummy[1]);
+                else lp = target_eval<D, false>(a.tgt, sTp, z, sp, dummy, dummy);
+            } else lp = target_eval<D, false>(a.tgt, sTp, z, sp, dummy, dummy);
             ka = split_first(k);    // mcdboundingmachine.py:162
             k = split_second(ka);   // mcd_cais.py:94
 #pragma unroll
@@ -179,7 +205,7 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_fwd_blk_kernel(const BridgeArg
         }
         if (nn_f) {   // NN(z_0, 0)
             __syncthreads();
-            bk_net_fwd<D, ACT, false>(nv, ns, HP, 0, S1, S2, nullptr, sX, sO);
+            bk_net_fwd<D, ACT, false>(nv, ns, HP, 0, S1, S2, nullptr, sX, sO, sPart);
             __syncthreads();
             if (pt) {
 #pragma unroll
@@ -202,15 +228,17 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_fwd_blk_kernel(const BridgeArg
 #pragma unroll
                     for (int j = 0; j < D; ++j) mf[j] = mf[j] - eps * nnv[j];
                 }
-                split(k, ka, k);
-                normal_vec<D>(ka, xi);
+                step_keys_and_normal<D>(k, xi);   // split + normal + the discarded second split (mcd_cais.py:66-67,87), batched threefry
 #pragma unroll
                 for (int j = 0; j < D; ++j) { zn[j] = mf[j] + scale * xi[j]; sX[j * BK_P + tid] = zn[j]; }
-                lp = target_eval<D, false>(a.tgt, sTp, zn, sp, dummy, dummy);
+                if constexpr (D == 2) {
+                    if (fast_gmm) lp = many_gmm_eval<false>(gc, sMu, zn[0], zn[1], sp[0], sp[1], 0.f, 0.f, dummy[0], dummy[1]);
+                    else lp = target_eval<D, false>(a.tgt, sTp, zn, sp, dummy, dummy);
+                } else lp = target_eval<D, false>(a.tgt, sTp, zn, sp, dummy, dummy);
             }
             if (nn_b) {
                 __syncthreads();
-                bk_net_fwd<D, ACT, false>(nv, ns, HP, cais ? i + 1 : i, S1, S2, nullptr, sX, sO);
+                bk_net_fwd<D, ACT, false>(nv, ns, HP, cais ? i + 1 : i, S1, S2, nullptr, sX, sO, sPart);
                 __syncthreads();
             }
             if (pt) {
@@ -234,7 +262,6 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_fwd_blk_kernel(const BridgeArg
                 const float fk = bk_gauss_logprob<D>(zn, mf, scale, lognorm);
                 const float bk = bk_gauss_logprob<D>(z, mb, scale, lognorm);
                 wm += bk - fk;
-                k = split_second(k);
 #pragma unroll
                 for (int j = 0; j < D; ++j) z[j] = zn[j];
                 if (a.traj && active) {
@@ -273,13 +300,19 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
     float* sTp = sW2T + (size_t)HP * HP;
     const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
     for (int i = tid; i < ntp; i += blockDim.x) sTp[i] = a.tgt.mix[i];
-    float* S1 = sTp + ((ntp + 3) & ~3);
-    float* S2 = S1 + (size_t)HP * BK_P;
-    float* S3 = S2 + (size_t)HP * BK_P;
-    float* sX = S3 + (size_t)HP * BK_P;
+    float2* sMu = reinterpret_cast<float2*>(sTp + ((ntp + 3) & ~3));
+    const bool fast_gmm = (D == 2) && a.tgt.kind == TGT_MANY_GMM;
+    if (fast_gmm)
+        for (int i = tid; i < a.tgt.ncomp; i += blockDim.x) sMu[i] = make_float2(a.tgt.mix[i * MIX_STRIDE], a.tgt.mix[i * MIX_STRIDE + 1]);
+    const ManyGmmConst gc = many_gmm_const(a.tgt);
+    float* S1 = reinterpret_cast<float*>(sMu + MIX_MAX);
+    float* S2 = S1 + (size_t)HP * BK_RS;
+    float* S3 = S2 + (size_t)HP * BK_RS;
+    float* sX = S3 + (size_t)HP * BK_RS;
     float* sO = sX + D * BK_P;
     float* sVo = sO + D * BK_P;
     float* sDx = sVo + D * BK_P;
+    float* sPart = sDx + D * BK_P;   // [HP/8][D][32] layer-3 / input-cotangent partials
     __syncthreads();
 
     float* part = partials + (size_t)blockIdx.x * L.P;
@@ -311,10 +344,12 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
         const bool active = pt && n_raw < a.N;
         const long long n = active ? n_raw : a.N - 1;
         const float c = active ? -cot_negw[n] : 0.f;   // dL/dw_n (zero for shadow lanes: all their cotangents vanish)
-        float x[D], zup[D], zprev[D], carry[D], rS[D], gmu[D], gls[D], zero[D], hv[D], sx[D];
+        float x[D], zup[D], zprev[D], znext[D], carry[D], rS[D], gmu[D], gls[D], zero[D], hv[D], sx[D];
+        float hx[3] = {0.f, 0.f, 0.f};   // many_gmm fast path: Hessian of log p at x
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             x[j] = pt ? a.traj[((size_t)K * D + j) * a.N + n] : 0.f;
+            znext[j] = (pt && K > 0) ? a.traj[((size_t)(K - 1) * D + j) * a.N + n] : 0.f;   // rows are requested one node ahead
             gmu[j] = 0.f; gls[j] = 0.f; zero[j] = 0.f; carry[j] = 0.f; rS[j] = 0.f; zup[j] = 0.f; hv[j] = 0.f; sx[j] = 0.f; zprev[j] = 0.f;
         }
         float cgb = 0.f, cge = 0.f;
@@ -334,8 +369,14 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
             for (int d = 0; d < D; ++d) { nn[d] = 0.f; dx[d] = 0.f; o[d] = 0.f; sq[d] = 0.f; mk_t[d] = 0.f; mk_q[d] = 0.f; uB[d] = 0.f; uF[d] = 0.f; dc[d] = 0.f; }
             if (pt) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) zprev[d] = hasB ? a.traj[((size_t)(j - 1) * D + d) * a.N + n] : 0.f;
-                target_eval<D, false>(a.tgt, sTp, x, sx, zero, hv);
+                for (int d = 0; d < D; ++d) {
+                    zprev[d] = hasB ? znext[d] : 0.f;
+                    if (j > 1) znext[d] = a.traj[((size_t)(j - 2) * D + d) * a.N + n];
+                }
+                if constexpr (D == 2) {
+                    if (fast_gmm) many_gmm_eval_hess(gc, sMu, x[0], x[1], sx[0], sx[1], hx[0], hx[1], hx[2]);
+                    else target_eval<D, false>(a.tgt, sTp, x, sx, zero, hv);
+                } else target_eval<D, false>(a.tgt, sTp, x, sx, zero, hv);
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
                     sq[d] = -(x[d] - mu[d]) * ivar[d];
@@ -351,7 +392,7 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
             }
             if (use_nn) {
                 __syncthreads();
-                bk_net_fwd<D, ACT, true>(nv, ns, HP, t, S1, S2, S3, sX, sO);
+                bk_net_fwd<D, ACT, true>(nv, ns, HP, t, S1, S2, S3, sX, sO, sPart);
                 __syncthreads();
             }
             float GB[D], GF[D], rB[D], xs[D], vv[D], wq[D];
@@ -396,13 +437,13 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
                     float d2 = 0.f;
 #pragma unroll
                     for (int m = 0; m < D; ++m) d2 = fmaf(ns.W3[jj * D + m], sVo[m * BK_P + p], d2);
-                    S3[idx] = d2 * S3[idx];
+                    S3[jj * BK_RS + p] = d2 * S3[jj * BK_RS + p];
                 }
                 __syncthreads();
                 // ---- gW2 += S1 dP2^T into the register tiles
 #pragma unroll
                 for (int r0 = 0; r0 < BK_MAXT; ++r0) {
-                    const int tl = tid + r0 * BK_T;
+                    const int tl = (BK_T - 1 - tid) + r0 * BK_T;
                     if (tl < G * G) {
                         const int ti = tl / G, tj = tl % G;
 #pragma unroll 2
@@ -410,8 +451,8 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
                             float4 A[4], B[4];
 #pragma unroll
                             for (int r = 0; r < 4; ++r) {
-                                A[r] = *reinterpret_cast<const float4*>(S1 + (ti + G * r) * BK_P + p);
-                                B[r] = *reinterpret_cast<const float4*>(S3 + (tj + G * r) * BK_P + p);
+                                A[r] = *reinterpret_cast<const float4*>(S1 + (ti + G * r) * BK_RS + p);
+                                B[r] = *reinterpret_cast<const float4*>(S3 + (tj + G * r) * BK_RS + p);
                             }
 #pragma unroll
                             for (int r = 0; r < 4; ++r)
@@ -431,7 +472,7 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
 #pragma unroll
                     for (int m = 0; m < D; ++m) { gu2[m] = 0.f; gw3[m] = 0.f; }
                     for (int p = 0; p < BK_P; ++p) {
-                        const float d2 = S3[jj * BK_P + p], h = S2[jj * BK_P + p] + skip * S1[jj * BK_P + p];
+                        const float d2 = S3[jj * BK_RS + p], h = S2[jj * BK_RS + p] + skip * S1[jj * BK_RS + p];
                         s2 += d2;
 #pragma unroll
                         for (int m = 0; m < D; ++m) {
@@ -462,7 +503,7 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
                 {
                     const float* __restrict__ c1 = nv.c1 + (size_t)t * HP;
                     const int ntile = (HP >> 3) * (BK_P >> 1);
-                    for (int tl = tid; tl < ntile; tl += BK_T) {
+                    for (int tl = BK_T - 1 - tid; tl < ntile; tl += BK_T) {
                         const int i0 = (tl >> 4) << 3, p0 = (tl & 15) << 1;
                         float acc[8][2];
 #pragma unroll
@@ -471,7 +512,7 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
                         for (int jj = 0; jj < HP; ++jj) {
                             const float4 w0 = *reinterpret_cast<const float4*>(sW2T + (size_t)jj * HP + i0);
                             const float4 w1 = *reinterpret_cast<const float4*>(sW2T + (size_t)jj * HP + i0 + 4);
-                            const float2 h = *reinterpret_cast<const float2*>(S3 + jj * BK_P + p0);
+                            const float2 h = *reinterpret_cast<const float2*>(S3 + jj * BK_RS + p0);
                             const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
                             for (int ii = 0; ii < 8; ++ii) {
@@ -479,6 +520,9 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
                                 acc[ii][1] = fmaf(h.y, wv[ii], acc[ii][1]);
                             }
                         }
+                        float dxp[D][2];
+#pragma unroll
+                        for (int m = 0; m < D; ++m) { dxp[m][0] = 0.f; dxp[m][1] = 0.f; }
 #pragma unroll
                         for (int ii = 0; ii < 8; ++ii) {
                             const int i = i0 + ii;
@@ -495,8 +539,21 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
                                 for (int m = 0; m < D; ++m) pre = fmaf(sX[m * BK_P + p], ns.U1[m * HP + i], pre);
                                 float a1, g1;
                                 act_fwd_grad<ACT>(pre, a1, g1);
-                                S2[i * BK_P + p] = da1 * g1;
+                                const float dp1 = da1 * g1;
+                                S2[i * BK_RS + p] = dp1;
+                                const float dp2 = has_u2 ? S3[i * BK_RS + p] : 0.f;
+#pragma unroll
+                                for (int m = 0; m < D; ++m) {   // this tile's share of dX = U1 dP1 + U2 dP2
+                                    dxp[m][q] = fmaf(ns.U1[m * HP + i], dp1, dxp[m][q]);
+                                    if (has_u2) dxp[m][q] = fmaf(ns.U2[m * HP + i], dp2, dxp[m][q]);
+                                }
                             }
+                        }
+                        const int ig = tl >> 4;
+#pragma unroll
+                        for (int m = 0; m < D; ++m) {
+                            sPart[(ig * D + m) * BK_P + p0] = dxp[m][0];
+                            sPart[(ig * D + m) * BK_P + p0 + 1] = dxp[m][1];
                         }
                     }
                 }
@@ -507,7 +564,7 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
 #pragma unroll
                     for (int m = 0; m < D; ++m) gu1[m] = 0.f;
                     for (int p = 0; p < BK_P; ++p) {
-                        const float d1 = S2[jj * BK_P + p];
+                        const float d1 = S2[jj * BK_RS + p];
                         s1 += d1;
 #pragma unroll
                         for (int m = 0; m < D; ++m) gu1[m] = fmaf(d1, sX[m * BK_P + p], gu1[m]);
@@ -523,10 +580,7 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
 #pragma unroll
                         for (int m = 0; m < D; ++m) acc = fmaf(ns.U3[aa * D + m], sVo[m * BK_P + p], acc);
                     }
-                    for (int jj = 0; jj < HP; ++jj) {
-                        acc = fmaf(ns.U1[aa * HP + jj], S2[jj * BK_P + p], acc);
-                        if (has_u2) acc = fmaf(ns.U2[aa * HP + jj], S3[jj * BK_P + p], acc);
-                    }
+                    for (int g = 0; g < (HP >> 3); ++g) acc += sPart[(g * D + aa) * BK_P + p];
                     sDx[idx] = acc;
                 }
                 __syncthreads();
@@ -540,7 +594,12 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
                     float vm[D], dummy[D];
 #pragma unroll
                     for (int d = 0; d < D; ++d) vm[d] = mk_t[d] * (bB * eB * GB[d] + bF * eF * GF[d]);
-                    target_eval<D, true>(a.tgt, sTp, x, dummy, vm, hv);
+                    if constexpr (D == 2) {
+                        if (fast_gmm) {
+                            hv[0] = fmaf(hx[0], vm[0], hx[1] * vm[1]);
+                            hv[1] = fmaf(hx[1], vm[0], hx[2] * vm[1]);
+                        } else target_eval<D, true>(a.tgt, sTp, x, dummy, vm, hv);
+                    } else target_eval<D, true>(a.tgt, sTp, x, dummy, vm, hv);
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
                         const float fpart = hasF ? (GF[d] - cF * rS[d]) : c * sx[d];
@@ -584,7 +643,7 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
     // flush the weight-gradient tiles (each (i, j) has exactly one owner in the CTA)
 #pragma unroll
     for (int r0 = 0; r0 < BK_MAXT; ++r0) {
-        const int tl = tid + r0 * BK_T;
+        const int tl = (BK_T - 1 - tid) + r0 * BK_T;
         if (tl < G * G) {
             const int ti = tl / G, tj = tl % G;
 #pragma unroll
@@ -597,10 +656,10 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
 
 // ---------------------------------------------------------------------------------------------------------------- launchers
 static size_t blk_fwd_smem(int D, int HP) {
-    return (net_smem_floats(D, HP) + MIX_MAX * MIX_STRIDE + 2 * (size_t)HP * BK_P + 2 * (size_t)D * BK_P + 8) * sizeof(float);
+    return (net_smem_floats(D, HP) + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 2 * (size_t)HP * BK_RS + 2 * (size_t)D * BK_P + (size_t)(HP / 8) * D * BK_P + 8) * sizeof(float);
 }
 static size_t blk_bwd_smem(int D, int HP) {
-    return (net_smem_floats(D, HP) + (size_t)HP * HP + MIX_MAX * MIX_STRIDE + 3 * (size_t)HP * BK_P + 4 * (size_t)D * BK_P + 8) * sizeof(float);
+    return (net_smem_floats(D, HP) + (size_t)HP * HP + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 3 * (size_t)HP * BK_RS + 4 * (size_t)D * BK_P + (size_t)(HP / 8) * D * BK_P + 8) * sizeof(float);
 }
 
 // Few particles (the one-thread-per-particle kernels would leave most SMs idle), a network, widths the register tiles cover.
