@@ -42,10 +42,13 @@ __device__ __forceinline__ float bk_gauss_logprob(const float (&x)[D], const flo
 // ---- network forward on the CTA's 32 particles.  In: sX [D][32].  Out: sO [D][32] = RAW output (before clamp / out_scale),
 // S1 = a1, S2 = a2, S3 = act'(pre2) if STORE.  Contains two __syncthreads(); the caller synchronises before (sX written) and
 // after (sO complete).
-template <int D, int ACT, bool STORE>
+// `side()` runs on the particle warp while the other warps are in the layer-2 GEMM (its tiles are handed out from the last thread
+// downwards, so warp 0 has none up to hidden_pad 176): per-particle work that does not depend on the network output.
+struct BkNoSide { __device__ __forceinline__ void operator()() const {} };
+template <int D, int ACT, bool STORE, typename Side = BkNoSide>
 __device__ __forceinline__ void bk_net_fwd(const NetView& nv, const NetSmem& s, int HP, int t, float* __restrict__ S1,
                                            float* __restrict__ S2, float* __restrict__ S3, const float* __restrict__ sX,
-                                           float* __restrict__ sO, float* __restrict__ sPart) {
+                                           float* __restrict__ sO, float* __restrict__ sPart, Side side = Side()) {
     constexpr bool has_u2 = (ACT == ACT_SOFTPLUS), has_u3 = (ACT == ACT_SOFTPLUS);
     constexpr float skip = (ACT == ACT_SOFTPLUS) ? 1.f : 0.f;
     const int tid = threadIdx.x;
@@ -61,6 +64,7 @@ __device__ __forceinline__ void bk_net_fwd(const NetView& nv, const NetSmem& s, 
         S1[j * BK_RS + p] = act_fwd<ACT>(pre);
     }
     __syncthreads();
+    if (tid < BK_P) side();
     // layer 2: thread tile = 8 units x 2 particles
     const int ntile = (HP >> 3) * (BK_P >> 1);
     for (int tile = BK_T - 1 - tid; tile < ntile; tile += BK_T) {   // reversed: the particle warp (warp 0) gets matrix work last
@@ -212,9 +216,18 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_fwd_blk_kernel(const BridgeArg
                 for (int j = 0; j < D; ++j) nnv[j] = out_scale * fminf(fmaxf(sO[j * BK_P + tid], -nv.out_clip), nv.out_clip);
             }
         }
+        if (pt && K > 0) step_keys_and_normal<D>(k, xi);   // Gaussians of step 0 (split + normal + discarded split, mcd_cais.py:66-67,87)
         for (int i = 0; i < K; ++i) {
             const float beta = __ldg(a.betas + i), eps = __ldg(a.eps + i);
             const float scale = sqrtf(2.0f * eps);
+            // score at z' and the next step's Gaussians: independent of the network output -> in the shadow of the layer-2 GEMM
+            auto side = [&]() {
+                if constexpr (D == 2) {
+                    if (fast_gmm) lp = many_gmm_eval<false>(gc, sMu, zn[0], zn[1], sp[0], sp[1], 0.f, 0.f, dummy[0], dummy[1]);
+                    else lp = target_eval<D, false>(a.tgt, sTp, zn, sp, dummy, dummy);
+                } else lp = target_eval<D, false>(a.tgt, sTp, zn, sp, dummy, dummy);
+                if (i + 1 < K) step_keys_and_normal<D>(k, xi);
+            };
             if (pt) {
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
@@ -228,18 +241,15 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_fwd_blk_kernel(const BridgeArg
 #pragma unroll
                     for (int j = 0; j < D; ++j) mf[j] = mf[j] - eps * nnv[j];
                 }
-                step_keys_and_normal<D>(k, xi);   // split + normal + the discarded second split (mcd_cais.py:66-67,87), batched threefry
 #pragma unroll
                 for (int j = 0; j < D; ++j) { zn[j] = mf[j] + scale * xi[j]; sX[j * BK_P + tid] = zn[j]; }
-                if constexpr (D == 2) {
-                    if (fast_gmm) lp = many_gmm_eval<false>(gc, sMu, zn[0], zn[1], sp[0], sp[1], 0.f, 0.f, dummy[0], dummy[1]);
-                    else lp = target_eval<D, false>(a.tgt, sTp, zn, sp, dummy, dummy);
-                } else lp = target_eval<D, false>(a.tgt, sTp, zn, sp, dummy, dummy);
             }
             if (nn_b) {
                 __syncthreads();
-                bk_net_fwd<D, ACT, false>(nv, ns, HP, cais ? i + 1 : i, S1, S2, nullptr, sX, sO, sPart);
+                bk_net_fwd<D, ACT, false>(nv, ns, HP, cais ? i + 1 : i, S1, S2, nullptr, sX, sO, sPart, side);
                 __syncthreads();
+            } else if (pt) {
+                side();
             }
             if (pt) {
                 float mb[D];
@@ -354,6 +364,17 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
         }
         float cgb = 0.f, cge = 0.f;
         const int t0 = cais ? 0 : -1;
+        // target score (and, fast path, Hessian) at the node's point: evaluated one node ahead, in the shadow of the dA1 GEMM
+        float sxN[D], hxN[3] = {0.f, 0.f, 0.f}, hvN[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) { sxN[d] = 0.f; hvN[d] = 0.f; }
+        auto eval_point = [&](const float (&pnt)[D]) {
+            if constexpr (D == 2) {
+                if (fast_gmm) many_gmm_eval_hess(gc, sMu, pnt[0], pnt[1], sxN[0], sxN[1], hxN[0], hxN[1], hxN[2]);
+                else target_eval<D, false>(a.tgt, sTp, pnt, sxN, zero, hvN);
+            } else target_eval<D, false>(a.tgt, sTp, pnt, sxN, zero, hvN);
+        };
+        if (pt) eval_point(x);   // node K
         for (int j = K; j >= 0; --j) {
             const bool hasB = j > 0, hasF = j < K;
             const int t = t0 + j;
@@ -373,12 +394,10 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
                     zprev[d] = hasB ? znext[d] : 0.f;
                     if (j > 1) znext[d] = a.traj[((size_t)(j - 2) * D + d) * a.N + n];
                 }
-                if constexpr (D == 2) {
-                    if (fast_gmm) many_gmm_eval_hess(gc, sMu, x[0], x[1], sx[0], sx[1], hx[0], hx[1], hx[2]);
-                    else target_eval<D, false>(a.tgt, sTp, x, sx, zero, hv);
-                } else target_eval<D, false>(a.tgt, sTp, x, sx, zero, hv);
+                hx[0] = hxN[0]; hx[1] = hxN[1]; hx[2] = hxN[2];
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
+                    sx[d] = sxN[d];
                     sq[d] = -(x[d] - mu[d]) * ivar[d];
                     mk_t[d] = (fabsf(sx[d]) <= a.clip_t) ? 1.f : 0.f;
                     mk_q[d] = (fabsf(sq[d]) <= a.clip_q) ? 1.f : 0.f;
@@ -500,6 +519,7 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
                 }
                 __syncthreads();
                 // ---- dA1 = W2 dP2 (+ skip W3 Vo); dP1 = dA1 o act'(pre1) -> S2   (thread tile = 8 units x 2 particles, W2^T rows)
+                if (pt && hasB) eval_point(zprev);   // next node's score / Hessian: the particle warp has no tile in this GEMM
                 {
                     const float* __restrict__ c1 = nv.c1 + (size_t)t * HP;
                     const int ntile = (HP >> 3) * (BK_P >> 1);
@@ -627,6 +647,7 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
                 }
 #pragma unroll
                 for (int d = 0; d < D; ++d) { rS[d] = rB[d]; zup[d] = x[d]; x[d] = zprev[d]; }
+                if (!use_nn && hasB) eval_point(x);   // no GEMM to hide it in at this node (x is z_{j-1} now)
             }
         }
         if (pt) {
