@@ -83,7 +83,7 @@ __device__ __forceinline__ void bk_net_fwd(const NetView& nv, const NetSmem& s, 
             }
             acc[jj][0] = b0; acc[jj][1] = b1;
         }
-#pragma unroll 4
+#pragma unroll 8
         for (int i = 0; i < HP; ++i) {
             const float4 w0 = *reinterpret_cast<const float4*>(s.W2 + (size_t)i * HP + j0);
             const float4 w1 = *reinterpret_cast<const float4*>(s.W2 + (size_t)i * HP + j0 + 4);
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
                     const int tl = (BK_T - 1 - tid) + r0 * BK_T;
                     if (tl < G * G) {
                         const int ti = tl / G, tj = tl % G;
-#pragma unroll 2
+#pragma unroll 4
                         for (int p = 0; p < BK_P; p += 4) {
                             float4 A[4], B[4];
 #pragma unroll
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
                         float acc[8][2];
 #pragma unroll
                         for (int ii = 0; ii < 8; ++ii) { acc[ii][0] = 0.f; acc[ii][1] = 0.f; }
-#pragma unroll 4
+#pragma unroll 8
                         for (int jj = 0; jj < HP; ++jj) {
                             const float4 w0 = *reinterpret_cast<const float4*>(sW2T + (size_t)jj * HP + i0);
                             const float4 w1 = *reinterpret_cast<const float4*>(sW2T + (size_t)jj * HP + i0 + 4);
