@@ -1,0 +1,51 @@
+"""Host-side tables of the momentum-augmented operators (CPU): `mcd_utils.ud_coeff_table` must reproduce, row by row, the
+scalars the reference step bodies form in-line (mcd_under_lp_a.py:28-51, mcd_under_lp_e.py:27-43, mcd_under_lp_ea.py:28-57,
+mcd_under_lp_a_cais.py:33-58,79-82), and chain gradients into eps / gamma / eta."""
+import math
+
+import pytest
+import torch
+
+from cmcd_b200 import mcd_utils
+
+
+def _params(eps=0.07, gamma=3.0, eta=0.6):
+    return {k: torch.tensor(v, dtype=torch.float32, requires_grad=True) for k, v in (("eps", eps), ("gamma", gamma), ("eta", eta))}
+
+
+@pytest.mark.parametrize("mode", ["MCD_U_a-lp", "MCD_U_a-lp-sna", "MCD_U_a-lp-sn", "MCD_U_e-lp", "MCD_U_e-lp-sna", "MCD_U_ea-lp-sn",
+                                  "MCD_CAIS_UHA_sn"])
+def test_ud_coeff_rows_match_reference_formulas(mode):
+    K = 5
+    p = _params()
+    rows = mcd_utils.ud_coeff_table(mode, p, K)
+    assert rows.shape == (7, K)
+    eps, gamma, eta = (p[k].detach() for k in ("eps", "gamma", "eta"))
+    for i in range(K):
+        e = eps
+        if mode == "MCD_CAIS_UHA_sn":   # cosine schedule, mcd_under_lp_a_cais.py:33-40
+            e = eps * torch.cos(torch.tensor((i / K + 0.008) / 1.008 * 0.5 * math.pi)) ** 2
+        eta_aux = gamma * e
+        if mode.startswith("MCD_U_a") or mode == "MCD_CAIS_UHA_sn":
+            want = (e, 1.0 - eta_aux, torch.sqrt(2.0 * eta_aux), 1.0 - eta_aux, 2 * eta_aux, torch.sqrt(2.0 * eta_aux),
+                    -2.0 * eta_aux if mode == "MCD_CAIS_UHA_sn" else torch.tensor(0.0))
+        elif mode.startswith("MCD_U_e-"):
+            want = (e, eta, torch.sqrt(1.0 - eta ** 2), eta, 2 * (1.0 - eta), torch.sqrt(1.0 - eta ** 2), torch.tensor(0.0))
+        else:
+            a_f = torch.exp(-gamma * e)
+            want = (e, a_f, torch.sqrt(1.0 - a_f ** 2), 1.0 - eta_aux, 2 * eta_aux, torch.sqrt(2.0 * eta_aux), torch.tensor(0.0))
+        torch.testing.assert_close(rows[:, i].detach(), torch.stack([torch.as_tensor(w, dtype=torch.float32) for w in want]),
+                                   rtol=1e-6, atol=1e-7)
+    # cotangents reach the scalars each operator depends on (and only those)
+    g = torch.autograd.grad(rows.sum(), [p["eps"], p["gamma"], p["eta"]], allow_unused=True)
+    uses_eta = mode.startswith("MCD_U_e-")
+    assert (g[2] is not None and g[2].abs() > 0) == uses_eta
+    assert (g[1] is not None and g[1].abs() > 0) == (not uses_eta)
+    assert g[0] is not None and g[0].abs() > 0
+
+
+def test_clip_settings_follow_the_operator():
+    inf = float("inf")
+    assert mcd_utils._clips("MCD_CAIS_UHA_sn", False) == (1e2, inf)      # stable=True is hard-coded, mcd_under_lp_a_cais.py:48
+    assert mcd_utils._clips("MCD_U_a-lp-sn", True) == (inf, inf)        # the lp_a / lp_e / lp_ea operators never clip
+    assert mcd_utils._clips("MCD_CAIS_sn", True) == (1e3, inf) and mcd_utils._clips("MCD_CAIS_var_sn", True) == (1e2, 1e2)
