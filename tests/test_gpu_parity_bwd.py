@@ -136,3 +136,33 @@ def test_gradient_partition_sum():
     parts = [gl(seeds[a:b], pf_p, unf_p, fixed_p, target)[0] * ((b - a) / 1000.0) for a, b in ((0, 400), (400, 1000))]
     e = _leaf_errs((parts[0] + parts[1]).cpu(), g_full.cpu(), unf)
     assert (e < 1e-5).all(), e
+
+
+@pytest.mark.parametrize("name", ["A_gmm", "B_funnel", "Cvar_manygmm", "ULAsn_funnel", "lin_funnel"])
+def test_gradient_parity_one_thread_per_particle_path(name, monkeypatch):
+    """Small particle counts take the block-cooperative mapping (csrc/bridge_blk.cu); large ones keep one thread per particle
+    (csrc/bridge_fwd.cu / bridge_bwd.cu).  CMCD_DISABLE_BLK=1 (read at call time) pins the latter so both stay covered."""
+    monkeypatch.setenv("CMCD_DISABLE_BLK", "1")
+    c, unf, g32, g64, gp, l64, lp_ = _grads(name)
+    fin = torch.isfinite(l64)
+    rel = lambda l: ((l.double() - l64)[fin].abs() / l64[fin].abs().clamp(min=1)).max().item()
+    assert rel(lp_) < max(1e-4, 2 * rel(c["l32"])), (rel(lp_), rel(c["l32"]))
+    e_kernel = _leaf_errs(gp, g64, unf)
+    e_oracle32 = _leaf_errs(g32, g64, unf)
+    assert (e_kernel <= np.maximum(GRAD_TOL, 2 * e_oracle32)).all(), (name, e_kernel, e_oracle32)
+
+
+def test_block_path_matches_one_thread_path_bitwise_inputs(monkeypatch):
+    """Same seeds, same parameters through both mappings: per-particle losses agree to fp32 rounding of the network sums
+    (different summation order), far inside the parity tolerance."""
+    c, lp, dim, pf, unf, fixed = oracle_problem("Ckl_manygmm_geffner", torch.float32)
+    _, target, _, pf_p, unf_p, fixed_p = product_problem("Ckl_manygmm_geffner", pf)
+    seeds = torch.from_numpy(seeds_for(c["N"]))
+    kw = dict(eps_schedule=c["eps_schedule"], grad_clipping=c["clip"])
+    with torch.no_grad():
+        a = PM.compute_bound(seeds, pf_p, unf_p, fixed_p, target, **kw)[1][0]
+        monkeypatch.setenv("CMCD_DISABLE_BLK", "1")
+        b = PM.compute_bound(seeds, pf_p, unf_p, fixed_p, target, **kw)[1][0]
+    fin = torch.isfinite(b)
+    assert (torch.isfinite(a) == fin).all()
+    assert ((a - b)[fin].abs() / b[fin].abs().clamp(min=1)).max().item() < 2e-5
