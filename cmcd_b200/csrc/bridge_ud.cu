@@ -45,7 +45,6 @@
 namespace cmcd {
 
 constexpr int UD_FWD_PB = 128;
-constexpr int UD_ROWS = 7;   // rows of the eps table: eps, a_f, s_f, a_b, c_n, s_b, c_f
 
 template <int D>
 __device__ __forceinline__ float ud_gauss_logprob(const float (&x)[D], const float (&mean)[D], float scale, float lognorm) {
@@ -412,9 +411,6 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
 }
 
 // ---------------------------------------------------------------------------------------------------------------- launchers
-static int ud_net_in(int mode, int D) {
-    return (mode == CMCD_MODE_UD_NET_ZRHO || mode == CMCD_MODE_UD_CAIS) ? 2 * D : (mode == CMCD_MODE_UD_NET_Z ? D : 0);
-}
 
 template <int D, int ACT, int HPT, int JC, int DI>
 static int launch_ud_fwd_t(const BridgeArgs& a, cudaStream_t st, int num_sms) {
@@ -469,13 +465,6 @@ int launch_bridge_ud_fwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sm
     }
 }
 
-static BwdLayout ud_layout(int D, int K, int HP, int arch, int din) {
-    // the eps slot holds the UD_ROWS coefficient rows
-    BwdLayout l = make_layout(D, K, HP, arch, din ? din : D);
-    const int extra = (UD_ROWS - 1) * (K > 0 ? K : 1);
-    l.mu += extra; l.ls += extra; l.P = (l.ls + D + 3) & ~3;
-    return l;
-}
 
 template <int D, int ACT, int HPT, int JC, int BPB, int DI>
 static int launch_ud_bwd_t(const BridgeArgs& a, cudaStream_t st, int num_sms, const float* cot, const BwdOut& out,

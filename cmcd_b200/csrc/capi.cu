@@ -34,6 +34,11 @@ int launch_bridge_fwd_blk(const BridgeArgs& a, int D, cudaStream_t st, int num_s
 int launch_bridge_bwd_blk(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, const float* cot_negw,
                           float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
                           const cmcd_net_grad* g_net, void* ws, size_t ws_bytes);
+bool blk_ud_supported(const BridgeArgs& a, int D, int num_sms);
+int launch_bridge_ud_fwd_blk(const BridgeArgs& a, int D, cudaStream_t st, int num_sms);
+int launch_bridge_ud_bwd_blk(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, const float* cot_negw,
+                             float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
+                             const cmcd_net_grad* g_net, void* ws, size_t ws_bytes);
 int launch_bridge_ud_fwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sms);
 int launch_bridge_ud_bwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, const float* cot_negw,
                          float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
@@ -152,7 +157,11 @@ int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
     if (sms <= 0) { set_error("no CUDA device"); return 1; }
     if (target->kind == CMCD_TARGET_LGCP || target->kind == CMCD_TARGET_CALLBACK)
         return launch_wide_fwd(a, target, desc->dim, (cudaStream_t)stream, sms, workspace, workspace_bytes);
-    if (is_ud(desc->mode)) return launch_bridge_ud_fwd(a, desc->dim, (cudaStream_t)stream, sms);
+    if (is_ud(desc->mode)) {
+        if (blk_ud_supported(a, desc->dim, sms) && !std::getenv("CMCD_DISABLE_BLK"))
+            return launch_bridge_ud_fwd_blk(a, desc->dim, (cudaStream_t)stream, sms);
+        return launch_bridge_ud_fwd(a, desc->dim, (cudaStream_t)stream, sms);
+    }
     if (desc->mode == CMCD_MODE_UHA)
         return launch_bridge_uha_fwd(a, desc->dim, desc->lfsteps > 0 ? desc->lfsteps : 1, (cudaStream_t)stream, sms);
     // hidden width 64: tcgen05 tiles; other widths: FP32 FMA kernel.  CMCD_DISABLE_TC=1 forces the FP32 kernel (A/B runs).
@@ -206,6 +215,9 @@ int cmcd_bridge_bwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
     if (desc->mode == CMCD_MODE_UHA)
         return launch_bridge_uha_bwd(a, desc->dim, desc->lfsteps > 0 ? desc->lfsteps : 1, (cudaStream_t)stream, sms, cot_negw,
                                      g_vd_mean, g_vd_logdiag, g_betas, g_eps, workspace, workspace_bytes);
+    if (is_ud(desc->mode) && blk_ud_supported(a, desc->dim, sms) && !std::getenv("CMCD_DISABLE_BLK"))
+        return launch_bridge_ud_bwd_blk(a, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
+                                        g_eps, g_net, workspace, workspace_bytes);
     if (is_ud(desc->mode))
         return launch_bridge_ud_bwd(a, desc->dim, (cudaStream_t)stream, sms, cot_negw, g_vd_mean, g_vd_logdiag, g_betas,
                                     g_eps, g_net, workspace, workspace_bytes);

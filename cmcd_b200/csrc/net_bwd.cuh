@@ -339,6 +339,19 @@ __device__ CMCD_NETB_INL void net_bwd(const NetView& nv, const NetSmem& s, int t
     __syncthreads();
 }
 
+// ---- underdamped operators (bridge_ud.cu, bridge_blk.cu): the eps slot of the layout holds the coefficient rows
+constexpr int UD_ROWS = 7;   // rows of the eps table: eps, a_f, s_f, a_b, c_n, s_b, c_f
+static inline int ud_net_in(int mode, int D) {
+    return (mode == CMCD_MODE_UD_NET_ZRHO || mode == CMCD_MODE_UD_CAIS) ? 2 * D : (mode == CMCD_MODE_UD_NET_Z ? D : 0);
+}
+static inline BwdLayout ud_layout(int D, int K, int HP, int arch, int din) {
+    // the eps slot holds the UD_ROWS coefficient rows
+    BwdLayout l = make_layout(D, K, HP, arch, din ? din : D);
+    const int extra = (UD_ROWS - 1) * (K > 0 ? K : 1);
+    l.mu += extra; l.ls += extra; l.P = (l.ls + D + 3) & ~3;
+    return l;
+}
+
 // out[k] = sum_b partials[b][k], scattered into the caller's cotangent buffers (bridge_bwd.cu)
 struct BwdOut {
     float *W2, *U1, *U2, *U3, *W3, *c1, *c2, *c3, *os, *beta, *eps, *mu, *ls;

@@ -138,10 +138,11 @@ def test_gradient_partition_sum():
     assert (e < 1e-5).all(), e
 
 
-@pytest.mark.parametrize("name", ["A_gmm", "B_funnel", "Cvar_manygmm", "ULAsn_funnel", "lin_funnel"])
+@pytest.mark.parametrize("name", ["A_gmm", "B_funnel", "Cvar_manygmm", "ULAsn_funnel", "lin_funnel",
+                                  "LDVI_gmm", "LDVI_funnel_dds", "UDesna_funnel_dds", "CAISUHA_gmm", "CAISUHA_manygmm_dds"])
 def test_gradient_parity_one_thread_per_particle_path(name, monkeypatch):
     """Small particle counts take the block-cooperative mapping (csrc/bridge_blk.cu); large ones keep one thread per particle
-    (csrc/bridge_fwd.cu / bridge_bwd.cu).  CMCD_DISABLE_BLK=1 (read at call time) pins the latter so both stay covered."""
+    (csrc/bridge_fwd.cu / bridge_bwd.cu / bridge_ud.cu).  CMCD_DISABLE_BLK=1 (read at call time) pins the latter so both stay covered."""
     monkeypatch.setenv("CMCD_DISABLE_BLK", "1")
     c, unf, g32, g64, gp, l64, lp_ = _grads(name)
     fin = torch.isfinite(l64)
