@@ -16,6 +16,8 @@
 // transposed copy of W2, dP1 = dA1 o act'(pre1), dX = U1 dP1 + U2 dP2 + U3 Vo.  The per-particle step algebra (keys, Gaussians,
 // target score / HVP, kernel means, log-weights, cotangent carry) runs on the first warp between the matrix phases.
 // Shared memory at hidden_pad 136: W2 + W2^T 148 KB, three [136][36] activation arrays 59 KB, small tables 5 KB.
+#include <cstdlib>
+
 #include "net_bwd.cuh"
 
 namespace cmcd {
@@ -1137,6 +1139,15 @@ static size_t blk_bwd_smem(int D, int HP) {
     return (net_smem_floats(D, HP) + (size_t)HP * HP + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 3 * (size_t)HP * BK_RS + 4 * (size_t)D * BK_P + (size_t)(HP / 8) * D * BK_P + 8) * sizeof(float);
 }
 
+// When the block mapping wins over one thread per particle (measured, tools/blk_crossover.py): always for wide networks
+// (hidden_pad > 64: the one-thread kernels fit one 64-particle CTA per SM there and are bound by their serial chains), and for
+// narrower ones while the one-thread kernels would leave SMs idle.  CMCD_BLK_ALWAYS=1 / CMCD_DISABLE_BLK=1 force either side.
+static bool blk_particle_limit_ok(long long N, int HP, int num_sms) {
+    if (std::getenv("CMCD_BLK_ALWAYS")) return true;
+    if (HP > 64) return true;
+    return N <= (long long)BK_P * num_sms * 2;
+}
+
 // Few particles (the one-thread-per-particle kernels would leave most SMs idle), a network, widths the register tiles cover.
 bool blk_supported(const BridgeArgs& a, int D, int num_sms) {
     if (a.net.arch == CMCD_ARCH_NONE || a.K < 1 || a.mode > CMCD_MODE_CAIS_VAR_SN || a.mode == CMCD_MODE_ULA) return false;
@@ -1144,7 +1155,7 @@ bool blk_supported(const BridgeArgs& a, int D, int num_sms) {
     const int HP = a.net.HP;
     if (HP > BK_HP_MAX || (HP & 7)) return false;
     if (blk_bwd_smem(D, HP) > 227 * 1024) return false;
-    return a.N <= (long long)BK_P * num_sms * 2;
+    return blk_particle_limit_ok(a.N, HP, num_sms);
 }
 
 template <int D, int ACT>
@@ -1225,7 +1236,7 @@ bool blk_ud_supported(const BridgeArgs& a, int D, int num_sms) {
     const int HP = a.net.HP;
     if (HP > BK_HP_MAX || (HP & 7)) return false;
     if (blk_ud_bwd_smem(D, din, HP) > 227 * 1024) return false;
-    return a.N <= (long long)BK_P * num_sms * 2;
+    return blk_particle_limit_ok(a.N, HP, num_sms);
 }
 
 template <int D, int ACT, int DI>
