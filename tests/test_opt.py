@@ -66,8 +66,10 @@ def test_adam_project_matches_oracle():
 
 
 @pytest.mark.gpu
-def test_run_matches_oracle_loop():
-    """5 iterations of opt.run on the README gmm config vs the same loop driven by the oracle (grad + numpy Adam)."""
+@pytest.mark.parametrize("name", ["A_gmm", "LDVI_gmm", "CAISUHA_gmm"])
+def test_run_matches_oracle_loop(name):
+    """5 iterations of opt.run on the README gmm config (CMCD, LDVI and 2nd-order CMCD operators) vs the same loop driven by the
+    oracle (grad + numpy Adam): eps / gamma / mgridref_y projections included."""
     from cmcd_b200 import mcdboundingmachine as PM
     from cmcd_b200 import opt as PO
     from cmcd_b200.pytree import tree_map
@@ -75,8 +77,8 @@ def test_run_matches_oracle_loop():
     class Info:
         N = 300
         run_cluster = 1
-    c, lp, dim, pf, unf, fixed = oracle_problem("A_gmm", torch.float32)
-    _, target, _, pf_p, unf_p, fixed_p = product_problem("A_gmm", pf)
+    c, lp, dim, pf, unf, fixed = oracle_problem(name, torch.float32)
+    _, target, _, pf_p, unf_p, fixed_p = product_problem(name, pf)
     kw = dict(eps_schedule=c["eps_schedule"], grad_clipping=c["clip"])
     trainable = c["trainable"]
     iters, lr = 5, 1e-3
@@ -100,7 +102,7 @@ def test_run_matches_oracle_loop():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["A_gmm", "B_funnel", "C_manygmm_dds_small"])
+@pytest.mark.parametrize("name", ["A_gmm", "B_funnel", "C_manygmm_dds_small", "LDVI_gmm", "Ckl_manygmm_geffner"])
 def test_run_graph_mode_matches_eager(name):
     """opt.run(graph=True) replays one captured iteration (table chain + forward bridge + adjoint + loss mean + flag):
     same parameters and losses as the eager loop after 6 iterations (gradient atomics change the fp32 summation order)."""
