@@ -30,6 +30,34 @@ constexpr int BK_RS = 36;      // row stride of the [HP][32] activation arrays: 
 constexpr int BK_MAXT = 4;     // 4x4 weight-gradient tiles per thread held in registers: (HP/4)^2 <= BK_MAXT * BK_T  =>  HP <= 156
 constexpr int BK_HP_MAX = 156;
 
+// ---- activations of the block kernels: MUFU-based forms (ex2 / lg2 / rcp.approx), a quarter of the instructions of the
+// expf / log1pf / division forms used by the one-thread kernels -- the activations were 25 % of this path's instructions (ncu).
+//   softplus(x) = max(x, 0) + ln2 lg2(1 + e),  e = 2^(-|x| log2 e);  softplus'(x) = 1/(1+e) (x >= 0) | e/(1+e) (x < 0)
+// absolute error <= 1.5e-7 on the value (lg2.approx: 2^-22.6 absolute on [1, 2]) and 1.2e-7 on the derivative; the dds GELU uses
+// the Abramowitz-Stegun form of the tensor-core kernels (common.cuh, |error| <= 4.7e-7).
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <int ACT>
+__device__ __forceinline__ float bk_act(float x) {
+    if constexpr (ACT == ACT_SOFTPLUS) {
+        const float e = ex2_ftz(-fabsf(x) * 1.4426950408889634f);
+        return fmaf(0.6931471805599453f, lg2_ftz(1.0f + e), fmaxf(x, 0.f));
+    } else {
+        return gelu_fast(x);
+    }
+}
+template <int ACT>
+__device__ __forceinline__ void bk_act_grad(float x, float& a, float& da) {
+    if constexpr (ACT == ACT_SOFTPLUS) {
+        const float e = ex2_ftz(-fabsf(x) * 1.4426950408889634f);
+        const float t = 1.0f + e;
+        a = fmaf(0.6931471805599453f, lg2_ftz(t), fmaxf(x, 0.f));
+        const float s = rcp_ftz(t);
+        da = x >= 0.f ? s : e * s;
+    } else {
+        gelu_fast_grad(x, a, da);
+    }
+}
+
 template <int D>
 __device__ __forceinline__ float bk_gauss_logprob(const float (&x)[D], const float (&mean)[D], float scale, float lognorm) {
     float s = 0.f;
@@ -63,7 +91,7 @@ __device__ __forceinline__ void bk_net_fwd(const NetView& nv, const NetSmem& s, 
         float pre = __ldg(c1 + j);
 #pragma unroll
         for (int a = 0; a < DI; ++a) pre = fmaf(sX[a * BK_P + p], s.U1[a * HP + j], pre);
-        S1[j * BK_RS + p] = act_fwd<ACT>(pre);
+        S1[j * BK_RS + p] = bk_act<ACT>(pre);
     }
     __syncthreads();
     if (tid < BK_P) side();
@@ -109,10 +137,10 @@ __device__ __forceinline__ void bk_net_fwd(const NetView& nv, const NetSmem& s, 
                 float a2;
                 if constexpr (STORE) {
                     float g2;
-                    act_fwd_grad<ACT>(acc[jj][q], a2, g2);
+                    bk_act_grad<ACT>(acc[jj][q], a2, g2);
                     S2[o] = a2; S3[o] = g2;
                 } else {
-                    a2 = act_fwd<ACT>(acc[jj][q]);
+                    a2 = bk_act<ACT>(acc[jj][q]);
                 }
                 const float hs = a2 + skip * S1[o];
 #pragma unroll
@@ -266,7 +294,7 @@ __device__ __forceinline__ void bk_net_bwd(const NetView& nv, const NetSmem& ns,
 #pragma unroll
                     for (int m = 0; m < DI; ++m) pre = fmaf(sX[m * BK_P + p], ns.U1[m * HP + i], pre);
                     float a1, g1;
-                    act_fwd_grad<ACT>(pre, a1, g1);
+                    bk_act_grad<ACT>(pre, a1, g1);
                     const float dp1 = da1 * g1;
                     S2[i * BK_RS + p] = dp1;
                     const float dp2 = has_u2 ? S3[i * BK_RS + p] : 0.f;
