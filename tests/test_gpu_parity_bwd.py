@@ -167,3 +167,16 @@ def test_block_path_matches_one_thread_path_bitwise_inputs(monkeypatch):
     fin = torch.isfinite(b)
     assert (torch.isfinite(a) == fin).all()
     assert ((a - b)[fin].abs() / b[fin].abs().clamp(min=1)).max().item() < 2e-5
+
+
+@pytest.mark.parametrize("name,N", [("A_gmm", 1), ("A_gmm", 33), ("Ckl_manygmm_geffner", 65), ("LDVI_gmm", 1), ("LDVI_gmm", 31), ("CAISUHA_gmm", 97)])
+def test_block_path_ragged_particle_counts(name, N):
+    """Particle counts around the 32-particle tile of the block kernels (shadow lanes carry zero cotangent and never store)."""
+    c, unf, g32, g64, gp, l64, lp_ = _grads(name, N=N)
+    assert lp_.numel() == N and torch.isfinite(gp).all()
+    fin = torch.isfinite(l64)
+    rel = lambda l: ((l.double() - l64)[fin].abs() / l64[fin].abs().clamp(min=1)).max().item()
+    assert rel(lp_) < max(1e-4, 2 * rel(c["l32"])), (rel(lp_), rel(c["l32"]))
+    e_kernel = _leaf_errs(gp, g64, unf)
+    e_oracle32 = _leaf_errs(g32, g64, unf)
+    assert (e_kernel <= np.maximum(GRAD_TOL, 2 * e_oracle32)).all(), (name, N, e_kernel, e_oracle32)
