@@ -17,50 +17,65 @@ namespace cmcd {
 
 constexpr int WG_THREADS = 128;   // skinny GEMM: 128 threads x 4 columns
 constexpr int WG_COLS = WG_THREADS * 4;
-constexpr int WG_ROWS = 8;        // particle rows per block
 
 // Y_part[s][n][m] = sum_{k in slice s} (X[n][k] - shift) * W[k][m]
+// ROWS = particle rows per block: 8, or 24 so that the README lgcp batch (N = 20) is ONE row tile -- with 8-row tiles every
+// weight element was fetched from L2 three times and fed 8 FMAs per load instead of 20 (27 us per product, launch list
+// gpurun_out/launches_lgcp_warm.csv).  The k loop keeps 8 independent 16-byte weight loads in flight per thread.
+template <int ROWS>
 __global__ void __launch_bounds__(WG_THREADS) skinny_gemm_kernel(const float* __restrict__ X, int ldx, float shift,
                                                                  const float* __restrict__ W, int ldw, int N, int Kd,
                                                                  int M, int kslice, float* __restrict__ part) {
-    extern __shared__ float sx[];  // [WG_ROWS][kslice]
+    extern __shared__ float sx[];  // [ROWS][kslice]
     const int m0 = blockIdx.x * WG_COLS + threadIdx.x * 4;
     const int s = blockIdx.y;
-    const int n0 = blockIdx.z * WG_ROWS;
+    const int n0 = blockIdx.z * ROWS;
     const int k0 = s * kslice, k1 = min(Kd, k0 + kslice);
     const int kl = k1 - k0;
-    for (int i = threadIdx.x; i < WG_ROWS * kl; i += WG_THREADS) {
+    for (int i = threadIdx.x; i < ROWS * kl; i += WG_THREADS) {
         const int r = i / kl, k = i % kl;
         sx[r * kslice + k] = (n0 + r < N) ? X[(size_t)(n0 + r) * ldx + k0 + k] - shift : 0.f;
     }
     __syncthreads();
-    float acc[WG_ROWS][4];
+    float acc[ROWS][4];
 #pragma unroll
-    for (int r = 0; r < WG_ROWS; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+    for (int r = 0; r < ROWS; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
     if (m0 < M) {
         const bool full = (m0 + 3 < M) && ((ldw & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);   // W may be a view into the flat parameter vector
-#pragma unroll 4
-        for (int k = 0; k < kl; ++k) {
-            float4 w;
-            const float* wp = W + (size_t)(k0 + k) * ldw + m0;
-            if (full) w = __ldg(reinterpret_cast<const float4*>(wp));
-            else {
-                w.x = __ldg(wp);
-                w.y = (m0 + 1 < M) ? __ldg(wp + 1) : 0.f;
-                w.z = (m0 + 2 < M) ? __ldg(wp + 2) : 0.f;
-                w.w = (m0 + 3 < M) ? __ldg(wp + 3) : 0.f;
+        constexpr int KU = 8;
+        for (int kb = 0; kb < kl; kb += KU) {
+            float4 w[KU];
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                const int k = kb + u;
+                if (k < kl) {
+                    const float* wp = W + (size_t)(k0 + k) * ldw + m0;
+                    if (full) w[u] = __ldg(reinterpret_cast<const float4*>(wp));
+                    else {
+                        w[u].x = __ldg(wp);
+                        w[u].y = (m0 + 1 < M) ? __ldg(wp + 1) : 0.f;
+                        w[u].z = (m0 + 2 < M) ? __ldg(wp + 2) : 0.f;
+                        w[u].w = (m0 + 3 < M) ? __ldg(wp + 3) : 0.f;
+                    }
+                } else {
+                    w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
 #pragma unroll
-            for (int r = 0; r < WG_ROWS; ++r) {
-                const float x = sx[r * kslice + k];
-                acc[r][0] = fmaf(x, w.x, acc[r][0]);
-                acc[r][1] = fmaf(x, w.y, acc[r][1]);
-                acc[r][2] = fmaf(x, w.z, acc[r][2]);
-                acc[r][3] = fmaf(x, w.w, acc[r][3]);
+            for (int u = 0; u < KU; ++u) {
+                const int k = min(kb + u, kl - 1);   // (padding lanes multiply a zero weight)
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    const float x = sx[r * kslice + k];
+                    acc[r][0] = fmaf(x, w[u].x, acc[r][0]);
+                    acc[r][1] = fmaf(x, w[u].y, acc[r][1]);
+                    acc[r][2] = fmaf(x, w[u].z, acc[r][2]);
+                    acc[r][3] = fmaf(x, w[u].w, acc[r][3]);
+                }
             }
         }
 #pragma unroll
-        for (int r = 0; r < WG_ROWS; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
             if (n0 + r < N) {
                 float* dst = part + ((size_t)s * N + n0 + r) * M + m0;
 #pragma unroll
@@ -72,23 +87,27 @@ __global__ void __launch_bounds__(WG_THREADS) skinny_gemm_kernel(const float* __
 }
 
 struct WideGemm {
-    int S, kslice;
+    int S, kslice, rows;
 };
 static WideGemm plan_gemm(int N, int Kd, int M, int num_sms) {
-    const int cg = (M + WG_COLS - 1) / WG_COLS, rt = (N + WG_ROWS - 1) / WG_ROWS;
+    const int rows = (N > 8 && N <= 24) ? 24 : 8;
+    const int cg = (M + WG_COLS - 1) / WG_COLS, rt = (N + rows - 1) / rows;
     int S = (2 * num_sms + cg * rt - 1) / (cg * rt);
     if (S < 1) S = 1;
-    if (S > 64) S = 64;
+    const int smax = rows == 24 ? 32 : 64;   // the finalize kernels read S partials per element
+    if (S > smax) S = smax;
     int ks = (Kd + S - 1) / S;
-    ks = (ks + 3) & ~3;
+    ks = (ks + 7) & ~7;
     S = (Kd + ks - 1) / ks;
-    return {S, ks};
+    return {S, ks, rows};
 }
 static int run_gemm(cudaStream_t st, const float* X, int ldx, float shift, const float* W, int ldw, int N, int Kd, int M,
                     int num_sms, float* part, int* S_out) {
     const WideGemm g = plan_gemm(N, Kd, M, num_sms);
-    dim3 grid((M + WG_COLS - 1) / WG_COLS, g.S, (N + WG_ROWS - 1) / WG_ROWS);
-    skinny_gemm_kernel<<<grid, WG_THREADS, (size_t)WG_ROWS * g.kslice * sizeof(float), st>>>(X, ldx, shift, W, ldw, N, Kd, M, g.kslice, part);
+    dim3 grid((M + WG_COLS - 1) / WG_COLS, g.S, (N + g.rows - 1) / g.rows);
+    const size_t smem = (size_t)g.rows * g.kslice * sizeof(float);
+    if (g.rows == 24) skinny_gemm_kernel<24><<<grid, WG_THREADS, smem, st>>>(X, ldx, shift, W, ldw, N, Kd, M, g.kslice, part);
+    else skinny_gemm_kernel<8><<<grid, WG_THREADS, smem, st>>>(X, ldx, shift, W, ldw, N, Kd, M, g.kslice, part);
     CMCD_CUDA_OK(cudaGetLastError());
     *S_out = g.S;
     return 0;
@@ -371,7 +390,7 @@ int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
 // receive the U2 / U3 cotangents too (U2 = W2[:d], U3 = W3[:d] for the geffner net, nn.py:45-52); g_U2 = g_U3 = 0.
 
 // Y[n][j] = sum_m X[n][m] W[j][m] (+ addend[n][j]);  Y2[n][j] = Y[n][j] * mult[n][j].  One warp per row j of W.
-constexpr int WT_NT = 10;   // particles per register tile
+constexpr int WT_NT = 20;   // particles per register tile (the README lgcp batch in one pass over the weight row)
 __global__ void __launch_bounds__(256) wide_gemm_t_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
                                                           int N, int J, int M, const float* __restrict__ addend, int lda,
                                                           const float* __restrict__ mult, int ldm, float* __restrict__ Y,
@@ -418,6 +437,70 @@ __global__ void __launch_bounds__(256) wide_gemm_t_kernel(const float* __restric
             }
         }
     }
+}
+
+// Same product with X staged in shared memory once per CTA (persistent CTAs, one weight row per warp): the global-load
+// version above waits on 20 dependent L1/L2 loads of X per weight chunk (ncu: 63 % of its samples on that scoreboard, 18 %
+// issue utilisation, 36-55 us per call at N = 20, M = 1620).  Needs N * M floats of shared memory and 16-byte aligned rows.
+__global__ void __launch_bounds__(512) wide_gemm_t_smem_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
+                                                               int N, int J, int M, const float* __restrict__ addend, int lda,
+                                                               const float* __restrict__ mult, int ldm, float* __restrict__ Y,
+                                                               float* __restrict__ Y2, int ldy) {
+    extern __shared__ float4 sx4[];
+    float* sXs = reinterpret_cast<float*>(sx4);   // [N][M]
+    const int M4 = M >> 2;
+    for (int i = threadIdx.x; i < N * M4; i += blockDim.x) {
+        const int n = i / M4, m4 = i % M4;
+        sx4[i] = *reinterpret_cast<const float4*>(X + (size_t)n * ldx + 4 * m4);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < J; j += gridDim.x * wpb) {
+        const float* __restrict__ wr = W + (size_t)j * ldw;
+        for (int n0 = 0; n0 < N; n0 += WT_NT) {
+            float acc[WT_NT];
+#pragma unroll
+            for (int r = 0; r < WT_NT; ++r) acc[r] = 0.f;
+            for (int m = lane * 4; m < M; m += 128) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(wr + m));
+#pragma unroll
+                for (int r = 0; r < WT_NT; ++r) {
+                    if (n0 + r < N) {
+                        const float4 x = *reinterpret_cast<const float4*>(sXs + (size_t)(n0 + r) * M + m);
+                        acc[r] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[r]))));
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < WT_NT; ++r) {
+                float v = acc[r];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && n0 + r < N) {
+                    const int n = n0 + r;
+                    if (addend) v += addend[(size_t)n * lda + j];
+                    Y[(size_t)n * ldy + j] = v;
+                    if (Y2) Y2[(size_t)n * ldy + j] = v * mult[(size_t)n * ldm + j];
+                }
+            }
+        }
+    }
+}
+
+// picks the staged version when X fits shared memory and the rows are 16-byte aligned (same summation order either way)
+static int run_gemm_t(cudaStream_t st, int num_sms, const float* X, int ldx, const float* W, int ldw, int N, int J, int M,
+                      const float* addend, int lda, const float* mult, int ldm, float* Y, float* Y2, int ldy) {
+    const size_t smem = (size_t)N * M * sizeof(float);
+    const bool vec = !((M | ldx | ldw) & 3) && !((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W)) & 15);
+    if (vec && smem <= 200 * 1024) {
+        CMCD_CUDA_OK(cudaFuncSetAttribute(wide_gemm_t_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wide_gemm_t_smem_kernel<<<num_sms, 512, smem, st>>>(X, ldx, W, ldw, N, J, M, addend, lda, mult, ldm, Y, Y2, ldy);
+    } else {
+        wide_gemm_t_kernel<<<2 * num_sms, 256, 0, st>>>(X, ldx, W, ldw, N, J, M, addend, lda, mult, ldm, Y, Y2, ldy);
+    }
+    CMCD_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 // G[i][j] += sum_n A[n][i] B[n][j]
@@ -679,25 +762,21 @@ int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
         CMCD_CUDA_OK(cudaGetLastError());
         return run_gemm(st, A2, HP, 0.f, nv.W3, d, (int)N, HP, d, num_sms, part, S3);
     };
-    const int tgrid = 2 * num_sms;
     // network VJP for cotangent vo on the raw output at (x, t): parameter cotangents accumulate, dx -> `dx`
     auto net_bwd = [&](const float* x, int t) -> int {
         // dA2 = vo W3^T ; dp2 = dA2 * softplus'(pre2)
-        wide_gemm_t_kernel<<<tgrid, 256, 0, st>>>(vo, d, nv.W3, d, (int)N, HP, d, nullptr, 0, s2, HP, dA, dp, HP);
-        CMCD_CUDA_OK(cudaGetLastError());
+        if (int rc = run_gemm_t(st, num_sms, vo, d, nv.W3, d, (int)N, HP, d, nullptr, 0, s2, HP, dA, dp, HP)) return rc;
         wide_outer_acc_kernel<<<dim3(((d + 3) / 4 + 127) / 128, HP), 128, 0, st>>>(A2, HP, vo, d, (int)N, HP, d, gW3, d);
         wide_colsum_acc_kernel<<<ew(d), 256, 0, st>>>(vo, d, (int)N, d, gc3 + (size_t)t * d);
         wide_outer_acc_kernel<<<dim3((HP / 4 + 127) / 128, HP), 128, 0, st>>>(A1, HP, dp, HP, (int)N, HP, HP, gW2, HP);
         wide_colsum_acc_kernel<<<ew(HP), 256, 0, st>>>(dp, HP, (int)N, HP, gc2 + (size_t)t * HP);
         CMCD_CUDA_OK(cudaGetLastError());
         // dA1 = dA2 + dp2 W2^T ; dp1 = dA1 * softplus'(pre1)     (in place: dA <- dA1, dp <- dp1 after the products above)
-        wide_gemm_t_kernel<<<tgrid, 256, 0, st>>>(dp, HP, nv.W2, HP, (int)N, HP, HP, dA, HP, s1, HP, A2, s2, HP);   // A2 <- dA1, s2 <- dp1 (both dead)
-        CMCD_CUDA_OK(cudaGetLastError());
+        if (int rc = run_gemm_t(st, num_sms, dp, HP, nv.W2, HP, (int)N, HP, HP, dA, HP, s1, HP, A2, s2, HP)) return rc;   // A2 <- dA1, s2 <- dp1 (both dead)
         wide_outer_acc_kernel<<<dim3((HP / 4 + 127) / 128, d), 128, 0, st>>>(x, d, s2, HP, (int)N, d, HP, gU1, HP);
         wide_colsum_acc_kernel<<<ew(HP), 256, 0, st>>>(s2, HP, (int)N, HP, gc1 + (size_t)t * HP);
         // dx = dA1[:, :d] + dp1 U1^T
-        wide_gemm_t_kernel<<<tgrid, 256, 0, st>>>(s2, HP, nv.U1, HP, (int)N, d, HP, A2, HP, nullptr, 0, dx, nullptr, d);
-        CMCD_CUDA_OK(cudaGetLastError());
+        if (int rc = run_gemm_t(st, num_sms, s2, HP, nv.U1, HP, (int)N, d, HP, A2, HP, nullptr, 0, dx, nullptr, d)) return rc;
         return 0;
     };
 
