@@ -26,15 +26,15 @@ template <int ROWS>
 __global__ void __launch_bounds__(WG_THREADS) skinny_gemm_kernel(const float* __restrict__ X, int ldx, float shift,
                                                                  const float* __restrict__ W, int ldw, int N, int Kd,
                                                                  int M, int kslice, float* __restrict__ part) {
-    extern __shared__ float sx[];  // [ROWS][kslice]
+    extern __shared__ __align__(16) float sx[];  // [ROWS][kslice]
     const int m0 = blockIdx.x * WG_COLS + threadIdx.x * 4;
     const int s = blockIdx.y;
     const int n0 = blockIdx.z * ROWS;
     const int k0 = s * kslice, k1 = min(Kd, k0 + kslice);
     const int kl = k1 - k0;
-    for (int i = threadIdx.x; i < ROWS * kl; i += WG_THREADS) {
-        const int r = i / kl, k = i % kl;
-        sx[r * kslice + k] = (n0 + r < N) ? X[(size_t)(n0 + r) * ldx + k0 + k] - shift : 0.f;
+    for (int i = threadIdx.x; i < ROWS * kslice; i += WG_THREADS) {   // the tail of the last slice is zero-filled (read as float4 below)
+        const int r = i / kslice, k = i % kslice;
+        sx[i] = (n0 + r < N && k < kl) ? X[(size_t)(n0 + r) * ldx + k0 + k] - shift : 0.f;
     }
     __syncthreads();
     float acc[ROWS][4];
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(WG_THREADS) skinny_gemm_kernel(const float* __
     if (m0 < M) {
         const bool full = (m0 + 3 < M) && ((ldw & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);   // W may be a view into the flat parameter vector
         constexpr int KU = 8;
-        for (int kb = 0; kb < kl; kb += KU) {
+        for (int kb = 0; kb < kl; kb += KU) {   // kslice is a multiple of 8: kb + 7 < kslice
             float4 w[KU];
 #pragma unroll
             for (int u = 0; u < KU; ++u) {
@@ -62,15 +62,16 @@ __global__ void __launch_bounds__(WG_THREADS) skinny_gemm_kernel(const float* __
                 }
             }
 #pragma unroll
-            for (int u = 0; u < KU; ++u) {
-                const int k = min(kb + u, kl - 1);   // (padding lanes multiply a zero weight)
+            for (int r = 0; r < ROWS; ++r) {
+                const float4 xa = *reinterpret_cast<const float4*>(sx + r * kslice + kb);       // 2 LDS.128 per 32 FMAs
+                const float4 xb = *reinterpret_cast<const float4*>(sx + r * kslice + kb + 4);
+                const float xs[KU] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
-                    const float x = sx[r * kslice + k];
-                    acc[r][0] = fmaf(x, w[u].x, acc[r][0]);
-                    acc[r][1] = fmaf(x, w[u].y, acc[r][1]);
-                    acc[r][2] = fmaf(x, w[u].z, acc[r][2]);
-                    acc[r][3] = fmaf(x, w[u].w, acc[r][3]);
+                for (int u = 0; u < KU; ++u) {
+                    acc[r][0] = fmaf(xs[u], w[u].x, acc[r][0]);
+                    acc[r][1] = fmaf(xs[u], w[u].y, acc[r][1]);
+                    acc[r][2] = fmaf(xs[u], w[u].z, acc[r][2]);
+                    acc[r][3] = fmaf(xs[u], w[u].w, acc[r][3]);
                 }
             }
         }
