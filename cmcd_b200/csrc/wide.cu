@@ -87,6 +87,17 @@ __global__ void __launch_bounds__(WG_THREADS) skinny_gemm_kernel(const float* __
     }
 }
 
+// part[0][e] <- sum_s part[s][e] (ascending s: the order every consumer used when it summed the slices itself).  The
+// consumers are one-CTA-per-particle kernels (20 CTAs for the README lgcp batch) that spent most of their time on S dependent
+// L2 reads per element; here the same reads are spread over the whole GPU and the consumers see a single slice.
+__global__ void __launch_bounds__(256) wide_reduce_partials_kernel(float* __restrict__ part, int S, int nel) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nel) return;
+    float v = 0.f;
+    for (int s = 0; s < S; ++s) v += part[(size_t)s * nel + e];
+    part[e] = v;
+}
+
 struct WideGemm {
     int S, kslice, rows;
 };
@@ -110,7 +121,12 @@ static int run_gemm(cudaStream_t st, const float* X, int ldx, float shift, const
     if (g.rows == 24) skinny_gemm_kernel<24><<<grid, WG_THREADS, smem, st>>>(X, ldx, shift, W, ldw, N, Kd, M, g.kslice, part);
     else skinny_gemm_kernel<8><<<grid, WG_THREADS, smem, st>>>(X, ldx, shift, W, ldw, N, Kd, M, g.kslice, part);
     CMCD_CUDA_OK(cudaGetLastError());
-    *S_out = g.S;
+    if (g.S > 1) {
+        const int nel = N * M;
+        wide_reduce_partials_kernel<<<(nel + 255) / 256, 256, 0, st>>>(part, g.S, nel);
+        CMCD_CUDA_OK(cudaGetLastError());
+    }
+    *S_out = 1;
     return 0;
 }
 
