@@ -32,9 +32,21 @@ __global__ void __launch_bounds__(WG_THREADS) skinny_gemm_kernel(const float* __
     const int n0 = blockIdx.z * ROWS;
     const int k0 = s * kslice, k1 = min(Kd, k0 + kslice);
     const int kl = k1 - k0;
-    for (int i = threadIdx.x; i < ROWS * kslice; i += WG_THREADS) {   // the tail of the last slice is zero-filled (read as float4 below)
-        const int r = i / kslice, k = i % kslice;
-        sx[i] = (n0 + r < N && k < kl) ? X[(size_t)(n0 + r) * ldx + k0 + k] - shift : 0.f;
+    // stage the activations, four independent loads in flight per thread (the tail of the last slice is zero-filled: it is
+    // read as float4 below)
+    for (int base = threadIdx.x; base < ROWS * kslice; base += 4 * WG_THREADS) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * WG_THREADS;
+            const int r = i / kslice, k = i % kslice;
+            v[u] = (i < ROWS * kslice && n0 + r < N && k < kl) ? X[(size_t)(n0 + r) * ldx + k0 + k] - shift : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * WG_THREADS;
+            if (i < ROWS * kslice) sx[i] = v[u];
+        }
     }
     __syncthreads();
     float acc[ROWS][4];
@@ -466,9 +478,18 @@ __global__ void __launch_bounds__(512) wide_gemm_t_smem_kernel(const float* __re
     extern __shared__ float4 sx4[];
     float* sXs = reinterpret_cast<float*>(sx4);   // [N][M]
     const int M4 = M >> 2;
-    for (int i = threadIdx.x; i < N * M4; i += blockDim.x) {
-        const int n = i / M4, m4 = i % M4;
-        sx4[i] = *reinterpret_cast<const float4*>(X + (size_t)n * ldx + 4 * m4);
+    for (int base = threadIdx.x; base < N * M4; base += 4 * blockDim.x) {   // four independent 16-byte loads in flight per thread
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * blockDim.x;
+            if (i < N * M4) v[u] = *reinterpret_cast<const float4*>(X + (size_t)(i / M4) * ldx + 4 * (i % M4));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * blockDim.x;
+            if (i < N * M4) sx4[i] = v[u];
+        }
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -479,13 +500,24 @@ __global__ void __launch_bounds__(512) wide_gemm_t_smem_kernel(const float* __re
             float acc[WT_NT];
 #pragma unroll
             for (int r = 0; r < WT_NT; ++r) acc[r] = 0.f;
-            for (int m = lane * 4; m < M; m += 128) {
-                const float4 w = __ldg(reinterpret_cast<const float4*>(wr + m));
+            for (int mb = lane * 4; mb < M; mb += 4 * 128) {   // four weight chunks requested before the first is used
+                float4 w[4];
 #pragma unroll
-                for (int r = 0; r < WT_NT; ++r) {
-                    if (n0 + r < N) {
-                        const float4 x = *reinterpret_cast<const float4*>(sXs + (size_t)(n0 + r) * M + m);
-                        acc[r] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[r]))));
+                for (int u = 0; u < 4; ++u) {
+                    const int m = mb + u * 128;
+                    w[u] = (m < M) ? __ldg(reinterpret_cast<const float4*>(wr + m)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int m = mb + u * 128;
+                    if (m < M) {
+#pragma unroll
+                        for (int r = 0; r < WT_NT; ++r) {
+                            if (n0 + r < N) {
+                                const float4 x = *reinterpret_cast<const float4*>(sXs + (size_t)(n0 + r) * M + m);
+                                acc[r] = fmaf(x.x, w[u].x, fmaf(x.y, w[u].y, fmaf(x.z, w[u].z, fmaf(x.w, w[u].w, acc[r]))));
+                            }
+                        }
                     }
                 }
             }
