@@ -11,7 +11,10 @@
 //   log p(x) = -0.5 dv.(K^-1 dv) + log_norm + sum_j (x_j counts_j - a exp(x_j)),
 //   score(x) = -K^-1 dv + counts - a exp(x),   H v = -K^-1 v - a exp(x) o v
 // (the reference does two triangular solves per score; K is well conditioned, cond = 27.6).
+#include <cstdlib>
+
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace cmcd {
 
@@ -110,6 +113,139 @@ __global__ void __launch_bounds__(256) wide_reduce_partials_kernel(float* __rest
     part[e] = v;
 }
 
+// ---- the same split-K product on tcgen05 tiles (the lgcp K^-1 "whitening" product and the 1620-wide layers, served from L2)
+// One CTA = one 64-column tile of W x one K range; rows of X (particles) are the 128 TMEM lanes.  Per 64-deep K chunk: the W
+// block [64 k][64 n] is staged once as tf32 (hi, lo) K-major core-matrix tiles, every thread puts its particle's 64 activations
+// into its own TMEM lane as (hi, lo), one elected lane issues the 24 MMAs of the 3-pass split (a_hi b_lo + a_lo b_hi + a_hi b_hi,
+// same scheme and accuracy as the bridge kernels, umma.cuh) accumulating in TMEM over the chunks; the next chunk's operands are
+// requested from L2 while the tensor core works.  ~6 instructions per weight element instead of 24 FMAs + loads.
+constexpr int WTC_KC = 64, WTC_NT = 64;
+constexpr uint32_t WTC_A_HI = 0, WTC_A_LO = 64, WTC_D = 128, WTC_COLS = 256;
+__global__ void __launch_bounds__(128) skinny_gemm_tc_kernel(const float* __restrict__ X, int ldx, float shift,
+                                                             const float* __restrict__ W, int ldw, int N, int Kd, int M,
+                                                             int chunks_per_slice, float* __restrict__ part) {
+    __shared__ __align__(1024) uint8_t sB[2 * WTC_NT * WTC_KC * 4];   // B_hi | B_lo
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t mbar;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m0 = blockIdx.x * WTC_NT;
+    const int s = blockIdx.y;
+    const int n0 = blockIdx.z * 128;
+    const int row = n0 + tid;                   // this thread's particle (TMEM lane)
+    const bool rowok = row < N;
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, WTC_COLS);
+    if (tid == 0) umma::mbar_init(&mbar, 1);
+    umma::fence_async_smem();
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint64_t dhi = umma::make_desc(umma::smem_u32(sB), 128, 32 * WTC_KC);
+    const uint64_t dlo = umma::make_desc(umma::smem_u32(sB + WTC_NT * WTC_KC * 4), 128, 32 * WTC_KC);
+    const uint32_t idesc = umma::make_idesc_tf32(128, WTC_NT);
+    const int c0 = s * chunks_per_slice;
+    const int nchunk = min(chunks_per_slice, (Kd + WTC_KC - 1) / WTC_KC - c0);
+    const bool xvec = !(ldx & 3) && !(reinterpret_cast<uintptr_t>(X) & 15);
+
+    // operand registers of one chunk: 32 W elements per thread -- lane l of warp w takes (n % 8, k % 4) = (l / 4, l % 4) of the
+    // (n / 8, k / 4) block pair i * 4 + w, i.e. one 8 x 4 patch per warp instruction: its stores into the core-matrix tiles hit
+    // 32 different banks (a row-major float4 mapping was an 8-way conflict) and its loads are four 32-byte sectors -- and the X
+    // row as 64 floats
+    float wreg[32];
+    float xreg[WTC_KC];
+    const int lane = tid & 31;
+    auto request = [&](int c) {
+        const int kb = (c0 + c) * WTC_KC;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int pair = i * 4 + warp;                 // 0..127: n-group = pair % 8, k-group = pair / 8
+            const int n = (pair & 7) * 8 + (lane >> 2), k = kb + (pair >> 3) * 4 + (lane & 3);
+            wreg[i] = (k < Kd && m0 + n < M) ? __ldg(W + (size_t)k * ldw + m0 + n) : 0.f;
+        }
+        if (rowok) {
+            const float* xp = X + (size_t)row * ldx + kb;
+            if (xvec && kb + WTC_KC <= Kd) {
+#pragma unroll
+                for (int q = 0; q < WTC_KC / 4; ++q) {
+                    const float4 v = *reinterpret_cast<const float4*>(xp + 4 * q);
+                    xreg[4 * q] = v.x; xreg[4 * q + 1] = v.y; xreg[4 * q + 2] = v.z; xreg[4 * q + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < WTC_KC; ++q) xreg[q] = (kb + q < Kd) ? xp[q] : shift;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < WTC_KC; ++q) xreg[q] = shift;
+        }
+    };
+    uint32_t parity = 0;
+    if (nchunk > 0) request(0);
+    for (int c = 0; c < nchunk; ++c) {
+        if (c > 0) { umma::mbar_wait(&mbar, parity); parity ^= 1u; umma::fence_after(); }   // tensor core done with B tiles and A lanes
+        {   // W block -> tf32 hi / lo core-matrix tiles: element (n, k) = W[kb + k][m0 + n]
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int pair = i * 4 + warp;
+                const int n = (pair & 7) * 8 + (lane >> 2), k = (pair >> 3) * 4 + (lane & 3);
+                float hi, lo;
+                umma::split_tf32(wreg[i], hi, lo);
+                const int off = umma::core_off(n, k, WTC_KC);
+                *reinterpret_cast<float*>(sB + off) = hi;
+                *reinterpret_cast<float*>(sB + WTC_NT * WTC_KC * 4 + off) = lo;
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {   // X row -> this thread's TMEM lane
+            uint32_t hh[16], ll[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                float hi, lo;
+                umma::split_tf32(xreg[cc * 16 + e] - shift, hi, lo);
+                hh[e] = __float_as_uint(hi); ll[e] = __float_as_uint(lo);
+            }
+            umma::tmem_st16(tmem_lane + WTC_A_HI + cc * 16, hh);
+            umma::tmem_st16(tmem_lane + WTC_A_LO + cc * 16, ll);
+        }
+        umma::tmem_st_wait();
+        umma::fence_before();
+        umma::fence_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+            umma::fence_after();
+            if (umma::elect_one()) {
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t acol = tmem_base + (pass == 1 ? WTC_A_LO : WTC_A_HI);
+                    const uint64_t bd = (pass == 0) ? dlo : dhi;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        umma::mma_tf32_ts(tmem_base + WTC_D, acol + k * 8, bd + (uint64_t)(k * 16), idesc, (c | pass | k) > 0);
+                }
+                umma::commit(&mbar);
+            }
+            __syncwarp();
+        }
+        if (c + 1 < nchunk) request(c + 1);   // L2 latency of the next chunk overlaps the MMAs
+    }
+    if (nchunk > 0) { umma::mbar_wait(&mbar, parity); umma::fence_after(); }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[16];
+        if (nchunk > 0) { umma::tmem_ld16(tmem_lane + WTC_D + cc * 16, v); umma::tmem_ld_wait(); }
+        if (rowok) {
+            float* dst = part + ((size_t)s * N + row) * M + m0 + cc * 16;
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+                if (m0 + cc * 16 + e < M) dst[e] = nchunk > 0 ? __uint_as_float(v[e]) : 0.f;
+        }
+    }
+    umma::fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_slot, WTC_COLS);
+}
+
 struct WideGemm {
     int S, kslice, rows;
 };
@@ -127,6 +263,25 @@ static WideGemm plan_gemm(int N, int Kd, int M, int num_sms) {
 }
 static int run_gemm(cudaStream_t st, const float* X, int ldx, float shift, const float* W, int ldw, int N, int Kd, int M,
                     int num_sms, float* part, int* S_out) {
+    // large products: tcgen05 tiles (CMCD_DISABLE_WIDE_TC=1 keeps the FP32-FMA kernel for A/B runs)
+    if ((long long)Kd * M >= 256LL * 256 && !std::getenv("CMCD_DISABLE_WIDE_TC")) {
+        const int nchunks = (Kd + WTC_KC - 1) / WTC_KC;
+        const int ctiles = (M + WTC_NT - 1) / WTC_NT, rtiles = (N + 127) / 128;
+        int S = (2 * num_sms + ctiles * rtiles - 1) / (ctiles * rtiles);   // ~2 CTAs per SM
+        if (S < 1) S = 1;
+        if (S > nchunks) S = nchunks;
+        const int cps = (nchunks + S - 1) / S;
+        S = (nchunks + cps - 1) / cps;
+        skinny_gemm_tc_kernel<<<dim3(ctiles, S, rtiles), 128, 0, st>>>(X, ldx, shift, W, ldw, N, Kd, M, cps, part);
+        CMCD_CUDA_OK(cudaGetLastError());
+        if (S > 1) {
+            const int nel = N * M;
+            wide_reduce_partials_kernel<<<(nel + 255) / 256, 256, 0, st>>>(part, S, nel);
+            CMCD_CUDA_OK(cudaGetLastError());
+        }
+        *S_out = 1;
+        return 0;
+    }
     const WideGemm g = plan_gemm(N, Kd, M, num_sms);
     dim3 grid((M + WG_COLS - 1) / WG_COLS, g.S, (N + g.rows - 1) / g.rows);
     const size_t smem = (size_t)g.rows * g.kslice * sizeof(float);
