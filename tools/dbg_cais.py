@@ -35,9 +35,10 @@ def run(name, K=None, **over):
     print("   leaf errs", np.array2string(ek, precision=1, max_line_width=250))
     print(f"{name} K={K} {over}: loss err {el:.2e} (fp32 oracle {el32:.2e}); grad kernel max {ek.max():.2e} oracle32 max {eo.max():.2e}", flush=True)
 
-import cmcd_b200.mcd_utils as MU
-for K in (13, 14, 15, 16, 17, 20):
-    run("CAISUHA_manygmm_dds", K=K, N=64)
-for N in (8, 16, 32):
-    run("CAISUHA_manygmm_dds", K=16, N=N)
-run("CAISUHA_manygmm_dds", K=16, N=64, trainable=("eta", "gamma", "eps", "vd", "mgridref_y"))
+# eps = 0.3 (the first version of the parity config): the leapfrog is unstable between mixture modes and one particle's cotangent
+# recursion amplifies fp32 rounding in BOTH fp32 implementations; eps = 0.1 (the committed config) is well conditioned
+for K in (12, 16):
+    run("CAISUHA_manygmm_dds", K=K, N=64, eps=0.3)
+for N in (16, 32):
+    run("CAISUHA_manygmm_dds", K=16, N=N, eps=0.3)
+run("CAISUHA_manygmm_dds", K=16, N=64)
