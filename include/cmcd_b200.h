@@ -3,7 +3,8 @@
  *
  * Drop-in boundary for the data-parallel hot path of shreyaspadhy/CMCD: the per-particle
  * annealed-Langevin bridge loop behind the boundmodes MCD_ULA, MCD_ULA_sn, MCD_CAIS_sn,
- * MCD_CAIS_var_sn.  Every entry point cites the reference interface it replaces
+ * MCD_CAIS_var_sn -- and, behind the same entry points, the momentum-augmented operators of the
+ * dispatcher (LDVI family, 2nd-order CMCD, UHA) and targets given as a score callback.  Every entry point cites the reference interface it replaces
  * (paths relative to the reference's src/).  All pointers are DEVICE pointers unless the
  * name ends in _host; arrays are dense row-major float32 / int32; the callee only enqueues
  * work on `stream` (no allocation, no synchronisation) so the calls are CUDA-graph safe and
@@ -145,6 +146,7 @@ int cmcd_xla_ffi_available(void);
  *   seeds[N] int32; vd_mean[d], vd_logdiag[d]; betas[K]; eps[K] (per-step step size after
  *   the eps schedule, mcd_cais.py:34-44,54-59); out_negw[N] = -w (the per-particle loss);
  *   out_z[N][d] = z_K; traj = NULL or [K+1][d][N] (z_k for the reverse pass).
+ *   Modes 4..8 widen eps / vd_logdiag / traj as described at the mode enum (coefficient rows, momentum scales, (z, rho, rho')).
  *   workspace: scratch of cmcd_bridge_fwd_workspace_bytes() bytes (0 for the small-d targets; the lgcp wide
  *   path keeps its [N][1600] state, split-K partials and key chain there).
  */
