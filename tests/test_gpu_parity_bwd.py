@@ -180,3 +180,17 @@ def test_block_path_ragged_particle_counts(name, N):
     e_kernel = _leaf_errs(gp, g64, unf)
     e_oracle32 = _leaf_errs(g32, g64, unf)
     assert (e_kernel <= np.maximum(GRAD_TOL, 2 * e_oracle32)).all(), (name, N, e_kernel, e_oracle32)
+
+
+@pytest.mark.parametrize("name,N,K", [("A_gmm", 6000, 4), ("Ckl_manygmm_geffner", 5200, 4), ("LDVI_gmm", 5000, 4)])
+def test_block_path_several_tiles_per_cta(name, N, K):
+    """More than 148 x 32 particles: every CTA of the block kernels walks several particle tiles (register-resident weight-
+    gradient tiles and shared-memory state carried from tile to tile)."""
+    c, unf, g32, g64, gp, l64, lp_ = _grads(name, N=N, K=K)
+    assert lp_.numel() == N and torch.isfinite(gp).all()
+    fin = torch.isfinite(l64)
+    rel = lambda l: ((l.double() - l64)[fin].abs() / l64[fin].abs().clamp(min=1)).max().item()
+    assert rel(lp_) < max(1e-4, 2 * rel(c["l32"])), (rel(lp_), rel(c["l32"]))
+    e_kernel = _leaf_errs(gp, g64, unf)
+    e_oracle32 = _leaf_errs(g32, g64, unf)
+    assert (e_kernel <= np.maximum(GRAD_TOL, 2 * e_oracle32)).all(), (name, N, e_kernel, e_oracle32)
