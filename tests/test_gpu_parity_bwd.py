@@ -194,3 +194,17 @@ def test_block_path_several_tiles_per_cta(name, N, K):
     e_kernel = _leaf_errs(gp, g64, unf)
     e_oracle32 = _leaf_errs(g32, g64, unf)
     assert (e_kernel <= np.maximum(GRAD_TOL, 2 * e_oracle32)).all(), (name, N, e_kernel, e_oracle32)
+
+
+@pytest.mark.parametrize("name,N,K", [("A_gmm", 40000, 2), ("LDVI_gmm", 40000, 2), ("CAISUHA_gmm", 30000, 2)])
+def test_one_thread_path_several_tiles_per_cta(name, N, K):
+    """Particle counts past the block path's range for narrow networks: the persistent one-thread-per-particle kernels walk
+    several tiles per CTA (partial-gradient slices accumulated across tiles)."""
+    c, unf, g32, g64, gp, l64, lp_ = _grads(name, N=N, K=K)
+    assert lp_.numel() == N and torch.isfinite(gp).all()
+    fin = torch.isfinite(l64)
+    rel = lambda l: ((l.double() - l64)[fin].abs() / l64[fin].abs().clamp(min=1)).max().item()
+    assert rel(lp_) < max(1e-4, 2 * rel(c["l32"])), (rel(lp_), rel(c["l32"]))
+    e_kernel = _leaf_errs(gp, g64, unf)
+    e_oracle32 = _leaf_errs(g32, g64, unf)
+    assert (e_kernel <= np.maximum(GRAD_TOL, 2 * e_oracle32)).all(), (name, N, e_kernel, e_oracle32)

@@ -72,3 +72,22 @@ def test_uha_forward_only_and_partition_invariance():
         full = PB.compute_bound(seeds, pf_p, unf_p, fixed_p, target)[1]
         parts = [PB.compute_bound(seeds[a:b], pf_p, unf_p, fixed_p, target)[1] for a, b in ((0, 130), (130, 777))]
     assert torch.equal(full[0], torch.cat([p[0] for p in parts])) and torch.equal(full[1], torch.cat([p[1] for p in parts]))
+
+
+def test_uha_several_tiles_per_cta():
+    """N past one wave of CTAs: the persistent UHA kernels walk several particle tiles per CTA."""
+    unf, (g32, l32, z32), (g64, l64, z64), (gp, l_p, z_p) = _both_n("UHA_gmm", 90000, 2)
+    assert rel_err(l_p, l64).max() < max(1e-4, 2 * rel_err(l32, l64).max())
+    e_k, e_o = _leaf_errs(gp, g64, unf), _leaf_errs(g32, g64, unf)
+    assert (e_k <= np.maximum(1e-4, 2 * e_o)).all(), (e_k, e_o)
+
+
+def _both_n(name, N, K):
+    c, lp, dim, pf, unf, fixed = uha_oracle_problem(name, torch.float32, N=N, K=K)
+    _, lp64, _, pf64, unf64, fixed64 = uha_oracle_problem(name, torch.float64, N=N, K=K)
+    seeds = seeds_for(N)
+    g32, (l32, z32) = OM.grad_and_loss(OM.uha_compute_bound, seeds, pf, unf, fixed, lp)
+    g64, (l64, z64) = OM.grad_and_loss(OM.uha_compute_bound, seeds, pf64, unf64, fixed64, lp64)
+    _, target, _, pf_p, unf_p, fixed_p = uha_product_problem(name, pf, N=N, K=K)
+    gp, (l_p, z_p) = PM.grad_and_loss(PB.compute_bound)(torch.from_numpy(seeds), pf_p, unf_p, fixed_p, target)
+    return unf, (g32, l32, z32), (g64, l64, z64), (gp.cpu(), l_p.cpu(), z_p.cpu())
