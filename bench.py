@@ -4,8 +4,10 @@
 Metric (BASELINE.json): particle-steps/sec = N x nbridges / time of one full train iteration (forward bridge +
 reverse/adjoint + gradient all-reduce; optimizer excluded -- it is host code in the reference, opt.py:126-128) for
     many_gmm (40-GMM, d=2), MCD_CAIS_sn, nn_arch=dds, nbridges=256, eps=1 cos_sq, init_sigma=60, grad_clipping
-with N = 2^20 particles *per GPU* (weak scaling over ranks: particles shard with no data-path collective; the only
-collectives are the tiny loss-statistics and gradient all-reduces).
+with N = 2^20 particles GLOBALLY, sharded over the ranks (BASELINE.json configs[4]: strong scaling -- particles shard with no
+data-path collective; the only collective is one fused all-reduce of [gradient | loss statistics]).  The weak-scaling figure
+(2^20 particles per GPU) is measured as well when N > 1 and reported under "weak_scaling".  `--sweep` records the strong-scaling
+table N_global = 2^16 .. 2^20 for this world size under "sweep" (profiles/r2_scaling.md is assembled from those lines).
 
 One process per GPU (torchrun); rank 0 prints ONE JSON line.  `--impl reference` times the CPU oracle restatement
 (the reference's JAX path cannot run: no jax in this image) on a bounded sample of the same workload.
@@ -36,7 +38,7 @@ def emit(obj):
     _JSON_OUT.flush()
 
 NBRIDGES = 256
-N_PER_GPU = 1 << 20
+N_GLOBAL = 1 << 20
 # algorithmic flops per particle-step: forward 35.0 kflop, KL train 105 kflop
 FLOP_FWD = 35.0e3
 FLOP_TRAIN = 105.0e3
@@ -105,23 +107,51 @@ def _parse_clocks(path, dev_index):
     return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons)}
 
 
-def run_reference(args):
-    """CPU restatement oracle (torch, all host threads) on a bounded sample: N=2000 particles x K=256, train iteration."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+def _oracle_problem():
     from oracle import mcdboundingmachine as OM
     from oracle import model_handler as OH
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    n = 2000
     lp, dim = OH.load_model("many_gmm")
     pf, unf, fixed = OM.initialize(dim, vdparams=OM.vd_initialize(dim, 60.0), nbridges=NBRIDGES, eps=1.0,
                                    trainable=("eta", "gamma", "mgridref_y"), mode="MCD_CAIS_sn", nn_arch="dds", live=True)
-    seeds = np.random.default_rng(0).integers(1, 10**6, n).astype(np.int32)
     kw = dict(eps_schedule="cos_sq", grad_clipping=True)
-    step = lambda: OM.grad_and_loss(OM.compute_bound, seeds, pf, unf, fixed, lp, **kw)
+
+    def make_step(n, analytic):
+        seeds = np.random.default_rng(0).integers(1, 10**6, n).astype(np.int32)
+
+        def step():
+            if analytic:
+                with OM.analytic_scores():
+                    return OM.grad_and_loss(OM.compute_bound, seeds, pf, unf, fixed, lp, **kw)
+            return OM.grad_and_loss(OM.compute_bound, seeds, pf, unf, fixed, lp, **kw)
+        return step
+    return make_step
+
+
+def _time_cpu(step, reps, warm=1):
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    return (time.perf_counter() - t0) / reps
+
+
+CPU_VARIANT_NOTE = ("torch-CPU fp32 restatement of jit(grad(compute_bound)) on all host threads; 'autograd_scores' takes the target / q "
+                    "scores by create_graph autograd exactly like jax.grad inside the reference's step body, 'analytic_scores' uses their "
+                    "closed forms (what XLA's fused program amounts to) -- the stronger baseline is the headline")
+
+
+def run_reference(args):
+    """CPU restatement oracle (torch, all host threads) on bounded samples of the workload: N = 2^14 with
+    closed-form scores is the line's value; N = 2000 (README.md:26) and the autograd-score variant are listed beside it."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    make_step = _oracle_problem()
+    n = 1 << 14
+    step = make_step(n, analytic=True)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -129,41 +159,47 @@ def run_reference(args):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     v = n * NBRIDGES / dt
-    sample = f"N={n} particles x K={NBRIDGES} bridges per step (README.md:26 config), fp32 torch-CPU autograd"
+    variants = {f"N={n}_analytic_scores": v}
+    for nn, an in ((n, False), (2000, True), (2000, False)):
+        variants[f"N={nn}_{'analytic' if an else 'autograd'}_scores"] = nn * NBRIDGES / _time_cpu(make_step(nn, an), 1, warm=1)
+    sample = (f"{args.steps} train iterations of N={n} particles x K={NBRIDGES} bridges (config E workload at a CPU-sized particle "
+              f"count; the metric is size-normalised), closed-form scores")
     emit({
         "impl": "reference", "metric": "particle_steps_per_sec_train_iter", "value": v, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "many_gmm MCD_CAIS_sn dds K=256 cos_sq clip, train iteration (fwd+reverse)",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "many_gmm (40-GMM d=2) MCD_CAIS_sn nn_arch=dds nbridges=256 eps=1 cos_sq sigma0=60 grad_clipping: "
+                               "one train iteration (forward + reverse)",
                    "particles_per_step": n, "nbridges": NBRIDGES},
-        "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "variants_particle_steps_per_s": variants, "note": CPU_VARIANT_NOTE},
         "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference JAX path cannot run here (no jax/jaxlib in the image); this is the oracle restatement",
     })
 
 
-def cpu_baseline_sample(budget_s=20.0):
-    """Oracle ("port") timed on the host cores on a bounded sample of the workload."""
-    from oracle import mcdboundingmachine as OM
-    from oracle import model_handler as OH
+def cpu_baseline_sample():
+    """Oracle ("port") timed on the host cores on a bounded sample of the workload (about 20-30 s of CPU work)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n = 2000
-    lp, dim = OH.load_model("many_gmm")
-    pf, unf, fixed = OM.initialize(dim, vdparams=OM.vd_initialize(dim, 60.0), nbridges=NBRIDGES, eps=1.0,
-                                   trainable=("eta", "gamma", "mgridref_y"), mode="MCD_CAIS_sn", nn_arch="dds", live=True)
-    seeds = np.random.default_rng(0).integers(1, 10**6, n).astype(np.int32)
-    kw = dict(eps_schedule="cos_sq", grad_clipping=True)
-    OM.grad_and_loss(OM.compute_bound, seeds, pf, unf, fixed, lp, **kw)  # warm-up
-    t0, reps = time.perf_counter(), 0
-    while True:
-        OM.grad_and_loss(OM.compute_bound, seeds, pf, unf, fixed, lp, **kw)
-        reps += 1
-        if time.perf_counter() - t0 > budget_s or reps >= 8:
-            break
-    dt = (time.perf_counter() - t0) / reps
+    make_step = _oracle_problem()
+    n = 1 << 14
+    dt = _time_cpu(make_step(n, True), 1, warm=1)
+    variants = {f"N={n}_analytic_scores": n * NBRIDGES / dt,
+                "N=2000_analytic_scores": 2000 * NBRIDGES / _time_cpu(make_step(2000, True), 1, warm=0),
+                "N=2000_autograd_scores": 2000 * NBRIDGES / _time_cpu(make_step(2000, False), 1, warm=0)}
     return {"value": n * NBRIDGES / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{reps} train iterations of N={n} x K={NBRIDGES} (README.md:26 config), torch-CPU fp32 oracle"}
+            "sample": f"1 train iteration (after 1 warm-up) of N={n} x K={NBRIDGES}, torch-CPU fp32 oracle with closed-form scores",
+            "variants_particle_steps_per_s": variants, "note": CPU_VARIANT_NOTE}
+
+
+def _event_ms(fn, dev):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    fn()
+    b.record()
+    torch.cuda.synchronize(dev)
+    return a.elapsed_time(b)
 
 
 def main():
@@ -172,15 +208,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cmcd_b200", choices=["cmcd_b200", "reference"])
-    ap.add_argument("--particles-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--particles-global", type=int, default=N_GLOBAL, help="strong scaling: total particles, sharded over ranks")
+    ap.add_argument("--weak-particles-per-gpu", type=int, default=N_GLOBAL, help="secondary weak-scaling measurement (N > 1)")
+    ap.add_argument("--sweep", action="store_true", help="also time N_global = 2^16 .. 2^20 (strong scaling table)")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured per-rank step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch.distributed as dist
-    from cmcd_b200 import _lib, mcdboundingmachine as M, model_handler as H, variationaldist as V
-    from cmcd_b200.distributed import global_ln_z, sharded_grad_and_loss
+    from cmcd_b200 import _lib, mcdboundingmachine as M, model_handler as H, utils as U, variationaldist as V
+    from cmcd_b200.distributed import ShardedStep, global_ln_z, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -194,29 +233,87 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
 
-    n_local = args.particles_per_gpu
-    n_global = n_local * world
     target, dim, _ = H.load_model("many_gmm", device=dev)
     pf, unf, fixed = M.initialize(dim, vdparams=V.initialize(dim, 60.0), nbridges=NBRIDGES, eps=1.0,
                                   trainable=("eta", "gamma", "mgridref_y"), mode="MCD_CAIS_sn", nn_arch="dds", device=dev)
     pf = _synthetic_params(unf, pf, dim, dev)
     kw = dict(eps_schedule="cos_sq", grad_clipping=True)
-    rng = np.random.default_rng(rank)  # mirrors opt.py:94 randint(1, 1e6), a fresh batch of seeds every iteration
     nbatch = args.warmup + args.steps
-    seeds_host = [torch.from_numpy(rng.integers(1, 10**6, n_local).astype(np.int32)).pin_memory() for _ in range(nbatch)]
-    seeds_dev = [s.to(dev) for s in seeds_host]
 
     def local_forward(seeds, p):
         l, (z, _) = M.compute_log_elbo(seeds, p, unf, fixed, target, **kw)
         return l, z
 
-    def step(seeds):
-        return sharded_grad_and_loss(local_forward, seeds, pf, loss="kl")
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def seed_batches(n_local, salt=0):
+        rng = np.random.default_rng(1000 * salt + rank)  # mirrors opt.py:94 randint(1, 1e6), a fresh batch of seeds every iteration
+        host = [torch.from_numpy(rng.integers(1, 10**6, n_local).astype(np.int32)).pin_memory() for _ in range(nbatch)]
+        return host, [s.to(dev) for s in host]
+
+    def time_train(n_global, salt=0, e2e=False, detail=False):
+        """max-over-ranks ms per train iteration with N_global particles sharded over the ranks (device-resident seeds), and
+        optionally the end-to-end figure (pinned host seeds in, gradient + loss statistics back on the host every step)."""
+        lo, hi = shard_bounds(n_global, world, rank)
+        n_local = hi - lo
+        host, devs = seed_batches(n_local, salt)
+        step = ShardedStep(local_forward, pf, n_local, n_global=n_global, graph=not args.no_graph)
+        for i in range(args.warmup):
+            step(devs[i])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            g, loss_value, (l, z) = step(devs[args.warmup + i])
+        e1.record()
+        barrier()
+        out = {"ms": e0.elapsed_time(e1) / args.steps, "n_local": n_local}
+        if detail:
+            out.update(l=l.clone(), g=g.clone(), loss=float(loss_value))
+        if e2e:
+            back = torch.empty(pf.numel() + 3, dtype=torch.float32).pin_memory()
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for i in range(args.steps):
+                g, loss_value, (l, z) = step(host[args.warmup + i])      # H2D of the pinned seeds inside the step
+                back[:pf.numel()].copy_(g, non_blocking=True)             # gradient back on the host
+                back[pf.numel():pf.numel() + 1].copy_(loss_value.reshape(1), non_blocking=True)
+                torch.cuda.current_stream().synchronize()                 # the reference's isnan(mean(loss)) sync, opt.py:122
+                if not np.isfinite(back[pf.numel()].item()) and False:
+                    raise SystemExit("diverged")
+            t1.record()
+            barrier()
+            out["ms_e2e"] = t0.elapsed_time(t1) / args.steps
+            out["d2h_bytes"] = 4 * (pf.numel() + 1)
+        # per-kernel times: an eager pass with CUDA events around each of the library's launches on the launching stream
+        if detail:
+            eager = ShardedStep(local_forward, pf, n_local, n_global=n_global, graph=False)
+            eager(devs[0])
+            _lib.LAUNCHES["count"] = 0
+            eager(devs[1 % nbatch])
+            out["launches_per_step"] = _lib.LAUNCHES["count"]
+            _lib.TIMING.update(enabled=True, fwd=[], bwd=[])
+            for i in range(args.steps):
+                eager(devs[args.warmup + i])
+            torch.cuda.synchronize()
+            _lib.TIMING["enabled"] = False
+            out["fwd_ms"] = float(np.mean([a.elapsed_time(b) for a, b in _lib.TIMING["fwd"]]))
+            out["bwd_ms"] = float(np.mean([a.elapsed_time(b) for a, b in _lib.TIMING["bwd"]]))
+            if world > 1:
+                buf = torch.zeros(pf.numel() + 3, device=dev)
+                for _ in range(3):
+                    dist.all_reduce(buf)
+                out["allreduce_ms"] = _event_ms(lambda: [dist.all_reduce(buf) for _ in range(10)], dev) / 10
+        del step
+        t = torch.tensor([out["ms"], out.get("ms_e2e", 0.0)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["ms"], out["ms_e2e"] = t[0].item(), t[1].item()
+        return out
 
     # FP32 FMA-pipe probe (roofline denominator, "of measured")
     sms = _lib.lib().cmcd_num_sms()
@@ -225,38 +322,22 @@ def main():
     for _ in range(3):
         probe()
     torch.cuda.synchronize()
-    best = 1e30
-    for _ in range(5):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); probe(); b.record(); torch.cuda.synchronize()
-        best = min(best, a.elapsed_time(b))
+    best = min(_event_ms(probe, dev) for _ in range(5))
     fp32_peak_tflops = 2.0 * 16 * 4096 * sms * 8 * 256 / (best * 1e-3) / 1e12
 
-    # ---- device-resident timing (value) ----
-    for i in range(args.warmup):
-        step(seeds_dev[i])
+    # ---- headline: strong scaling, N_global sharded over the ranks ----
+    n_global = args.particles_global
     clock_file = os.path.join(tempfile.gettempdir(), f"cmcd_clocks_{os.getpid()}.csv")
     sampler = _clock_sampler(clock_file) if rank == 0 else None
-    _lib.LAUNCHES["count"] = 0
-    _lib.TIMING.update(enabled=True, fwd=[], bwd=[])
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        g, loss_value, (l, z) = step(seeds_dev[args.warmup + i])
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    launches = _lib.LAUNCHES["count"]
-    _lib.TIMING["enabled"] = False
-    fwd_ms = float(np.mean([a.elapsed_time(b) for a, b in _lib.TIMING["fwd"]]))
-    bwd_ms = float(np.mean([a.elapsed_time(b) for a, b in _lib.TIMING["bwd"]]))
+    r = time_train(n_global, e2e=True, detail=True)
     if sampler is not None:
         sampler.terminate()
+    n_local, ms, ms_e2e, fwd_ms, bwd_ms = r["n_local"], r["ms"], r["ms_e2e"], r["fwd_ms"], r["bwd_ms"]
+    l, g = r["l"], r["g"]
     lnz_est = global_ln_z(l)
 
     # ---- sampling-only ln Z estimate (north_star's second throughput figure): forward bridge + global logsumexp ----
-    from cmcd_b200 import utils as U
+    host, devs = seed_batches(n_local, salt=7)
 
     def sample_step(seeds):
         with torch.no_grad():
@@ -265,36 +346,49 @@ def main():
         return l, st
 
     for i in range(min(2, args.warmup)):
-        sample_step(seeds_dev[i])
+        sample_step(devs[i])
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
     for i in range(args.steps):
-        l_s, st = sample_step(seeds_dev[args.warmup + i])
+        l_s, st = sample_step(devs[args.warmup + i])
     s1.record()
     barrier()
     ms_sample = s0.elapsed_time(s1) / args.steps
     lnz_sampling = global_ln_z(l_s)
-
-    # ---- end-to-end timing: host seeds in (pinned), gradient + loss back on the host ----
-    g_host = torch.empty(pf.numel(), dtype=torch.float32).pin_memory()
+    # end to end through the C ABI's host-buffer entry (cmcd_bridge_fwd_host): pinned host seeds in, losses back on the host
+    from cmcd_b200.mcd_utils import sample_host
+    negw_host = torch.empty(n_local, dtype=torch.float32).pin_memory()
+    sample_host(host[0], pf, unf, fixed, target, negw_host, **kw)
     barrier()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
     for i in range(args.steps):
-        sd = seeds_host[args.warmup + i].to(dev, non_blocking=True)
-        g, loss_value, (l, z) = step(sd)
-        g_host.copy_(g, non_blocking=True)
-        loss_host = float(loss_value)  # already a host scalar (the reference's isnan(mean(loss)) sync, opt.py:122)
-        torch.cuda.current_stream().synchronize()
-    t1.record()
+        sample_host(host[args.warmup + i], pf, unf, fixed, target, negw_host, **kw)
+    h1.record()
     barrier()
-    ms_e2e = t0.elapsed_time(t1) / args.steps
-
-    t = torch.tensor([ms, ms_e2e, ms_sample], dtype=torch.float64, device=dev)
+    ms_sample_host = h0.elapsed_time(h1) / args.steps
+    t = torch.tensor([ms_sample, ms_sample_host], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_sample = t[0].item(), t[1].item(), t[2].item()
+    ms_sample, ms_sample_host = t[0].item(), t[1].item()
+
+    weak = None
+    if world > 1:
+        w = time_train(args.weak_particles_per_gpu * world, salt=3)
+        weak = {"scaling": "weak", "particles_per_gpu": args.weak_particles_per_gpu, "particles_global": args.weak_particles_per_gpu * world,
+                "ms_per_step": w["ms"], "value": args.weak_particles_per_gpu * world * NBRIDGES / (w["ms"] * 1e-3), "unit": "particle-steps/s"}
+    sweep = None
+    if args.sweep:
+        sweep = []
+        for e in range(16, 21):
+            ng = 1 << e
+            w = time_train(ng, salt=e, detail=True)
+            sweep.append({"particles_global": ng, "particles_per_gpu": w["n_local"], "ms_per_step": w["ms"],
+                          "value": ng * NBRIDGES / (w["ms"] * 1e-3), "fwd_kernel_ms": w["fwd_ms"], "bwd_kernel_ms": w["bwd_ms"],
+                          "allreduce_ms": w.get("allreduce_ms", 0.0),
+                          "rest_ms": w["ms"] - w["fwd_ms"] - w["bwd_ms"] - w.get("allreduce_ms", 0.0)})
+
     if rank == 0:
         value = n_global * NBRIDGES / (ms * 1e-3)
         e2e = n_global * NBRIDGES / (ms_e2e * 1e-3)
@@ -302,19 +396,23 @@ def main():
         ach_fwd = FLOP_FWD * n_local * NBRIDGES / (fwd_ms * 1e-3) / 1e12
         tensor_peak, peak_source = _tensor_peak()
         traffic_bwd = NCU_BWD_DRAM_BYTES_PER_PARTICLE * n_local
+        launches = r["launches_per_step"] * args.steps
         out = {
             "metric": "particle_steps_per_sec_train_iter", "value": value, "unit": "particle-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "many_gmm (40-GMM d=2) MCD_CAIS_sn nn_arch=dds nbridges=256 eps=1 cos_sq sigma0=60 "
-                                   "grad_clipping: one train iteration (forward bridge + adjoint + grad all-reduce)",
+                                   "grad_clipping: one train iteration (forward bridge + adjoint + fused grad/statistics all-reduce), "
+                                   "N_global particles sharded over the ranks (BASELINE.json configs[4])",
                        "particles_per_gpu": n_local, "particles_global": n_global, "nbridges": NBRIDGES,
-                       "l2_policy": "inputs larger than L2: a fresh 4 MiB seed vector per step and a 2.2 GB "
-                                    "trajectory written then re-read per step (> 126 MB L2)"},
+                       "step": "per-rank step captured once into a CUDA graph and replayed" if not args.no_graph else "eager launches",
+                       "l2_policy": "inputs larger than L2: a fresh seed vector per step and a trajectory of 8(K+1) B per particle "
+                                    f"({8 * (NBRIDGES + 1) * n_local / 1e6:.0f} MB per rank) written then re-read per step (L2 = 126 MB)"},
             "e2e": {"value": e2e, "unit": "particle-steps/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": 4 * n_local, "d2h_bytes_per_step": 4 * pf.numel() + 8},
+                    "h2d_bytes_per_step": 4 * n_local, "d2h_bytes_per_step": r["d2h_bytes"]},
             "gpu_launches": launches,
-            "gpu_launches_note": "per timed region: (forward bridge + adjoint + partial-gradient reduce) x steps, this library only",
+            "gpu_launches_note": "this library's kernels inside the timed region: (forward bridge + adjoint + partial-gradient reduce + "
+                                 "loss statistics) x steps, replayed from the captured graph",
             "roofline": {
                 "bound": "tensor", "kernel": "bridge_bwd_tc_kernel", "achieved": ach_bwd, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": ach_bwd / tensor_peak, "traffic": traffic_bwd,
@@ -326,28 +424,39 @@ def main():
                                  "pull-back per trajectory point (K+1 instead of 2K), so the kernel executes about half of the "
                                  "algorithmic flops the reference's formulation counts; `achieved` uses the algorithmic count",
                 "note": "the dense contractions (64x64 layer: forward, input-gradient and weight-gradient products) run on "
-                        "tcgen05 tiles (tf32 3-pass / bf16 hi+lo), so the contract's denominator is the tensor pipe; the kernel "
+                        "tcgen05 tiles, so the contract's denominator is the tensor pipe; the kernel "
                         "itself is bounded by CUDA-core issue slots (exact-erf GELU and derivative, threefry, mixture scores / "
-                        "HVPs, operand splitting) -- see profiles/r1_ncu_summary.md for the measured pipe utilisations",
+                        "HVPs, operand splitting) -- see profiles/ for the measured pipe utilisations; kernel times are CUDA "
+                        "events around each launch in an eager pass of the same step, on the launching stream",
                 "fp32_pipe": {"peak_measured_tflops": fp32_peak_tflops, "achieved_over_fp32_peak": ach_bwd / fp32_peak_tflops,
                               "what": "algorithmic TFLOP/s over the measured FFMA peak (cmcd_ffma_probe): the ceiling of any "
                                       "CUDA-core-only implementation is 1.0"},
                 "traffic_note": "dram__bytes_read+write of this kernel from the ncu --set full capture at N=131072 "
-                                "(profiles/r1_ncu_summary.md), scaled linearly to this run's particle count; algorithmic bytes "
+                                "(profiles/), scaled linearly to this run's particle count; algorithmic bytes "
                                 "= trajectory re-read 8(K+1) B + seed/cotangent 8 B per particle",
                 "fwd_kernel": {"kernel": "bridge_fwd_tc_kernel", "achieved": ach_fwd, "frac": ach_fwd / tensor_peak,
                                "achieved_over_fp32_peak": ach_fwd / fp32_peak_tflops,
                                "algorithmic_flops_per_particle_step": FLOP_FWD, "avg_launch_ms": fwd_ms,
                                "executed_flops_per_particle_step": FLOP_FWD_EXECUTED,
-                               "executed_tflops": FLOP_FWD_EXECUTED * n_local * NBRIDGES / (fwd_ms * 1e-3) / 1e12}},
+                               "executed_tflops": FLOP_FWD_EXECUTED * n_local * NBRIDGES / (fwd_ms * 1e-3) / 1e12},
+                "step_breakdown_ms": {"fwd_kernel": fwd_ms, "bwd_kernel": bwd_ms, "allreduce": r.get("allreduce_ms", 0.0),
+                                      "rest": ms - fwd_ms - bwd_ms - r.get("allreduce_ms", 0.0)}},
             "sampling_ln_z": {"metric": "particle_steps_per_sec_sampling", "value": n_global * NBRIDGES / (ms_sample * 1e-3),
                               "unit": "particle-steps/s", "ms_per_step": ms_sample, "ln_Z_estimate": lnz_sampling,
-                              "what": "forward bridge + one-launch logsumexp statistics + max/sum all-reduce (opt.sample path)"},
+                              "what": "forward bridge + one-launch logsumexp statistics + max/sum all-reduce (opt.sample path)",
+                              "e2e": {"value": n_global * NBRIDGES / (ms_sample_host * 1e-3), "ms_per_step": ms_sample_host,
+                                      "h2d_bytes_per_step": 4 * n_local, "d2h_bytes_per_step": 4 * n_local,
+                                      "what": "cmcd_bridge_fwd_host: pinned host seeds in, per-particle losses back on the host, "
+                                              "stream synchronised inside the call"}},
             "clocks": _parse_clocks(clock_file, local_rank),
             "quality": {"loss_mean_finite": float(l[torch.isfinite(l)].mean().item()),
                         "finite_frac": float(torch.isfinite(l).float().mean().item()), "ln_Z_estimate": lnz_est,
                         "grad_norm": float(g.norm().item())},
         }
+        if weak is not None:
+            out["weak_scaling"] = weak
+        if sweep is not None:
+            out["sweep"] = sweep
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample()
         emit(out)

@@ -67,6 +67,8 @@ EXPORTS = {
     "cmcd_batched_elbo_lnz": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
     "cmcd_bridge_fwd_host": (C.c_int, [C.POINTER(CmcdBridgeDesc), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNet),
                                        C.POINTER(CmcdTarget), _fp, _fp, _fp, _fp, _fp]),
+    "cmcd_bridge_evolve": (C.c_int, [C.POINTER(CmcdBridgeDesc), _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNet),
+                                     C.POINTER(CmcdTarget), _fp, _fp]),
     "cmcd_target_eval": (C.c_int, [C.POINTER(CmcdTarget), C.c_int32, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp]),
     "cmcd_adam_project_step": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                          C.c_float, C.c_int32, _fp, C.c_float, _fp]),

@@ -50,13 +50,20 @@ __global__ void __launch_bounds__(FWD_PB, (HPT > 64 ? 1 : (D <= 4 ? 4 : 2))) bri
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long n = tile * FWD_PB + tid;
         if (n >= a.N) continue;
-        Key k = prng_key(a.seeds[n]);
-        Key ka;
-        split(k, ka, k);
+        const bool ev = a.z0 != nullptr;   // mcd_utils.evolve entry: (z, rng_key_gen) given by the caller (mcd_utils.py:24-33)
+        Key k, ka;
         float z[D], zn[D], xi[D];
-        normal_vec<D>(ka, xi);
         float w = 0.f;
-        {   // z0 = sigma*xi + mu ; w = -log q(z0)   (vardist/diag_gauss.py:26-33,44-62)
+        if (ev) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) z[j] = a.z0[n * D + j];
+            ka.k0 = a.keys[2 * n]; ka.k1 = a.keys[2 * n + 1];
+        } else {
+            k = prng_key(a.seeds[n]);
+            split(k, ka, k);
+            normal_vec<D>(ka, xi);
+        }
+        if (!ev) {   // z0 = sigma*xi + mu ; w = -log q(z0)   (vardist/diag_gauss.py:26-33,44-62)
             float lq = 0.f;
 #pragma unroll
             for (int j = 0; j < D; ++j) {
@@ -73,8 +80,8 @@ __global__ void __launch_bounds__(FWD_PB, (HPT > 64 ? 1 : (D <= 4 ? 4 : 2))) bri
         float sp[D], dummy[D];
         float lp = target_eval<D, false>(a.tgt, sTp, z, sp, dummy, dummy);
         if (K >= 1) {
-            ka = split_first(k);    // mcdboundingmachine.py:162
-            k = split_second(ka);   // mcd_cais.py:94
+            if (!ev) ka = split_first(k);    // mcdboundingmachine.py:162 (evolve entry: ka is the caller's rng_key_gen)
+            k = split_second(ka);            // mcd_cais.py:94
             float wm = 0.f;
             // One network evaluation per trajectory point: in the CAIS modes NN(z', i + 1) of step i's backward-kernel mean
             // (mcd_cais.py:78) is the same evaluation as NN(z, i + 1) of step i + 1's forward-kernel mean (mcd_cais.py:60),
@@ -133,8 +140,8 @@ __global__ void __launch_bounds__(FWD_PB, (HPT > 64 ? 1 : (D <= 4 ? 4 : 2))) bri
             }
             w += wm;
         }
-        w += lp;
-        a.out_negw[n] = -w;
+        // evolve returns the steps' log-ratio sum w (mcd_cais.py:98-99); compute_log_elbo adds log p(z_K) (mcdboundingmachine.py:178)
+        a.out_negw[n] = ev ? w : -(w + lp);
 #pragma unroll
         for (int j = 0; j < D; ++j) a.out_z[n * D + j] = z[j];
     }

@@ -1,5 +1,6 @@
 // C ABI of libcmcd_b200.so (declared in include/cmcd_b200.h): argument validation and
 // marshalling into the kernel launchers.  No torch types, no allocation, enqueue-only.
+#include <atomic>
 #include <cstdarg>
 #include <cmath>
 #include <cstdlib>
@@ -67,14 +68,21 @@ int launch_adam_project(cudaStream_t st, float* p, const float* g, float* m, flo
                         const int32_t* skip_flag);
 int launch_randint(cudaStream_t st, uint32_t key0, uint32_t key1, long long n, int32_t minval, int32_t maxval, int32_t* out);
 
-static int g_num_sms = 0;
+// SM count of the CURRENT device, cached per device id (one process may drive several GPUs; relaxed atomics: the value is
+// idempotent, so a race only repeats the query)
 static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    constexpr int MAX_DEV = 64;
+    static std::atomic<int> cache[MAX_DEV];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev >= 0 && dev < MAX_DEV) {
+        const int c = cache[dev].load(std::memory_order_relaxed);
+        if (c > 0) return c;
     }
-    return g_num_sms;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (dev >= 0 && dev < MAX_DEV) cache[dev].store(n, std::memory_order_relaxed);
+    return n;
 }
 
 static bool is_ud(int mode) { return (mode >= CMCD_MODE_UD_NONE && mode <= CMCD_MODE_UD_NET_ZRHO) || mode == CMCD_MODE_UD_CAIS; }
@@ -239,14 +247,32 @@ int cmcd_batched_elbo_lnz(void* stream, const float* losses, int32_t batches, in
     return launch_batched_elbo_lnz((cudaStream_t)stream, losses, batches, n, elbo, lnz);
 }
 
+int cmcd_bridge_evolve(const cmcd_bridge_desc* desc, void* stream, const float* z0, const uint32_t* keys, const float* vd_mean,
+                       const float* vd_logdiag, const float* betas, const float* eps, const cmcd_net* net,
+                       const cmcd_target* target, float* out_z, float* out_w) {
+    BridgeArgs a;
+    if (int rc = build_args(desc, nullptr, vd_mean, vd_logdiag, betas, eps, net, target, a)) return rc;
+    if (!z0 || !keys || !out_z || !out_w) { set_error("bridge_evolve needs z0, keys, out_z and out_w"); return 2; }
+    if (desc->mode > CMCD_MODE_CAIS_VAR_SN) { set_error("Mode not implemented. (bridge_evolve serves the overdamped modes 0..3)"); return 2; }
+    if (target->kind == CMCD_TARGET_LGCP || target->kind == CMCD_TARGET_CALLBACK) { set_error("bridge_evolve: target kind %d not in the registry of the fused small-d kernels", target->kind); return 2; }
+    if (desc->nbridges < 1) { set_error("bridge_evolve needs nbridges >= 1"); return 2; }
+    a.z0 = z0; a.keys = keys; a.out_z = out_z; a.out_negw = out_w; a.traj = nullptr;
+    if (a.N == 0) return 0;
+    const int sms = num_sms();
+    if (sms <= 0) { set_error("no CUDA device"); return 1; }
+    return launch_bridge_fwd(a, desc->dim, (cudaStream_t)stream, sms);
+}
+
 int cmcd_bridge_fwd_host(const cmcd_bridge_desc* desc, void* stream, const int32_t* seeds_host, const float* vd_mean,
                          const float* vd_logdiag, const float* betas, const float* eps, const cmcd_net* net,
                          const cmcd_target* target, int32_t* seeds_dev, float* negw_dev, float* z_dev,
                          float* out_negw_host, float* out_z_host) {
+    if (!desc || !target) { set_error("null descriptor"); return 2; }
+    if (!seeds_host || !seeds_dev || !negw_dev || !z_dev || !out_negw_host) { set_error("bridge_fwd_host: null buffer"); return 2; }
+    if (target->kind == CMCD_TARGET_LGCP || target->kind == CMCD_TARGET_CALLBACK) { set_error("bridge_fwd_host: lgcp / callback targets need the workspace entry point"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = desc->n_particles;
     CMCD_CUDA_OK(cudaMemcpyAsync(seeds_dev, seeds_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (target->kind == CMCD_TARGET_LGCP || target->kind == CMCD_TARGET_CALLBACK) { set_error("bridge_fwd_host: lgcp / callback targets need the workspace entry point"); return 2; }
     if (int rc = cmcd_bridge_fwd(desc, stream, seeds_dev, vd_mean, vd_logdiag, betas, eps, net, target, negw_dev, z_dev, nullptr, nullptr, 0)) return rc;
     CMCD_CUDA_OK(cudaMemcpyAsync(out_negw_host, negw_dev, n * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (out_z_host) CMCD_CUDA_OK(cudaMemcpyAsync(out_z_host, z_dev, n * desc->dim * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -175,6 +175,10 @@ struct BridgeArgs {
     NetView net;
     TargetDesc tgt;
     float *out_negw, *out_z, *traj;
+    // evolve entry (cmcd_bridge_evolve): start from caller-supplied z0[N][d] and per-particle keys[N][2] instead of the integer
+    // seed; out_negw then receives +w of the K steps only (no -log q(z0), no log p(z_K)), like mcd_utils.evolve
+    const float* z0;
+    const uint32_t* keys;
 };
 
 // set the thread-local last-error string (capi.cu)

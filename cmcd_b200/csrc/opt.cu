@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) adam_project_kernel(float* __restrict__ p
 }
 
 // jax.random.randint(key, (n,), minval, maxval), int32 (jax/_src/random.py::_randint): two 32-bit draws per element
-// from the two halves of split(key), combined as ((hi % span) * (2^32 % span) + lo % span) % span in uint32 arithmetic.
+// from the two halves of split(key), combined as ((hi % span) * mult + lo % span) % span in uint32 arithmetic, mult = ((2^16 % span)^2 mod 2^32) % span.
 __global__ void __launch_bounds__(256) randint_kernel(uint32_t key0, uint32_t key1, long long n, int32_t minval, uint32_t span,
                                                       uint32_t mult, int32_t* __restrict__ out) {
     __shared__ Key k12[2];
@@ -68,7 +68,10 @@ int launch_adam_project(cudaStream_t st, float* p, const float* g, float* m, flo
 int launch_randint(cudaStream_t st, uint32_t key0, uint32_t key1, long long n, int32_t minval, int32_t maxval, int32_t* out) {
     uint32_t span = maxval > minval ? (uint32_t)((long long)maxval - (long long)minval) : 1u;
     uint32_t mult = 65536u % span;
-    mult = (uint32_t)(((unsigned long long)mult * mult) % span);   // 2^32 mod span; the product fits (mult < 2^16)
+    // lax.rem(lax.mul(multiplier, multiplier), span) is evaluated in uint32 by JAX: for span > 65536 the square of
+    // 2^16 wraps to 0, so the multiplier is 0 and the offset reduces to lower_bits % span (e.g. span = 999999 for
+    // randint(key, (N,), 1, 1e6), opt.py:94).  The wrap is part of the reference's stream and is reproduced here.
+    mult = (uint32_t)(mult * mult) % span;
     randint_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key0, key1, n, minval, span, mult, out);
     CMCD_CUDA_OK(cudaGetLastError());
     return 0;

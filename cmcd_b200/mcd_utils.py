@@ -233,12 +233,87 @@ def uha_bridge(seeds, params, betas, params_fixed, log_prob_model):
     return _Bridge.apply(cfg, seeds, vd["mean"], scales, betas, rows)
 
 
-def evolve(z, betas, params, rng_key_gen, params_fixed, log_prob_model, eps_schedule=None, grad_clipping=False):
-    """mcd_utils.py:24-33 signature.  The reference's per-particle (z, key) entry is fused away: the
-    CUDA path always starts from the integer seed (see ``bridge``).  Kept so unknown modes fail as in the
-    reference (mcd_utils.py:190) and callers get a pointer to the fused entry."""
-    mode = params_fixed[2]
+def _forward_inputs(params, betas, params_fixed, eps_schedule, grad_clipping):
+    """(vd_mean, vd_logdiag, betas, eps rows, tables, clip levels) of a forward-only call, detached and contiguous."""
+    dim, nbridges, mode, apply_fun = params_fixed
     if mode not in MODE:
         raise NotImplementedError("Mode not implemented.")
-    raise RuntimeError("cmcd_b200 fuses evolve() into the per-particle bridge kernel; "
-                       "call mcd_utils.bridge(seeds, ...) or mcdboundingmachine.compute_log_elbo")
+    uses_net = mode not in ("MCD_ULA", "MCD_U_a-lp", "MCD_U_e-lp") and nbridges >= 1
+    if uses_net and apply_fun is None:
+        raise RuntimeError(f"mode {mode} needs a score network")
+    f32 = lambda t: t.detach().to(torch.float32).contiguous()
+    sched = eps_schedule if mode in ("MCD_CAIS_sn", "MCD_CAIS_var_sn") else None
+    with torch.no_grad():
+        eps = f32(eps_table(params["eps"], nbridges, sched))
+        tabs = {k: (None if t is None else f32(t)) for k, t in build_tables(apply_fun, params["sn"]).items()} if uses_net else None
+    return f32(params["vd"]["mean"]), f32(params["vd"]["logdiag"]), f32(betas), eps, tabs, _clips(mode, grad_clipping), uses_net
+
+
+def evolve(z, betas, params, rng_key_gen, params_fixed, log_prob_model, eps_schedule=None, grad_clipping=False):
+    """mcd_utils.py:24-33: ``(z, w, None) = evolve(z, betas, params, rng_key_gen, ...)`` -- the K bridge steps from a given state and
+    PRNG key, dispatching on ``params_fixed[2]`` (mcd_cais.py:6-99, mcd_cais_var.py:7-112, mcd_over_orig.py:6-65).  The reference
+    calls it per particle under ``jax.vmap``; here ``z`` is ``[N, d]`` (or ``[d]``) and ``rng_key_gen`` the matching ``[N, 2]``
+    (or ``[2]``) uint32 keys, and the whole batch runs in one launch of ``cmcd_bridge_evolve``.  Forward only: the differentiable
+    entry is ``bridge`` / ``mcdboundingmachine.compute_log_elbo`` (whose kernels fuse the key chain, z0 ~ q and log p(z_K) around
+    these same steps).  Overdamped modes; unknown modes raise ``NotImplementedError("Mode not implemented.")`` (mcd_utils.py:190)."""
+    dim, nbridges, mode, apply_fun = params_fixed
+    if mode not in MODE:
+        raise NotImplementedError("Mode not implemented.")
+    if mode in UD_MODES or mode == "UHA":
+        raise NotImplementedError(f"Mode not implemented. (evolve() from a given (z, key) serves the overdamped modes; {mode} runs "
+                                  "through mcd_utils.bridge / boundingmachine.compute_log_elbo)")
+    single = z.dim() == 1
+    zz = (z[None] if single else z).detach().to(torch.float32).contiguous()
+    _lib.require_cuda(zz)
+    dev = zz.device
+    import numpy as np
+    keys = rng_key_gen.cpu().numpy() if isinstance(rng_key_gen, torch.Tensor) else np.asarray(rng_key_gen)
+    keys = np.ascontiguousarray(keys.astype(np.uint32).reshape(-1, 2))
+    n = zz.shape[0]
+    if keys.shape[0] != n:
+        raise ValueError(f"evolve: {n} states but {keys.shape[0]} keys")
+    keys_dev = torch.from_numpy(keys.view(np.int32)).to(dev)        # bit pattern travels as int32 (torch has no uint32 arithmetic)
+    vd_mean, vd_logdiag, betas_c, eps, tabs, (clip_t, clip_q), uses_net = _forward_inputs(params, betas, params_fixed, eps_schedule,
+                                                                                         grad_clipping)
+    out_z, out_w = torch.empty(n, dim, device=dev), torch.empty(n, device=dev)
+    desc, net = _make_desc(mode, dim, nbridges, n, clip_t, clip_q), _make_net(apply_fun if uses_net else None, tabs, nbridges)
+    _lib.check(_lib.lib().cmcd_bridge_evolve(desc, _lib.current_stream(), _lib.ptr(zz), _lib.ptr(keys_dev), _lib.ptr(vd_mean),
+                                             _lib.ptr(vd_logdiag), _lib.ptr(betas_c), _lib.ptr(eps), net, log_prob_model.desc(),
+                                             _lib.ptr(out_z), _lib.ptr(out_w)))
+    _lib.count_launches(1)
+    return (out_z[0], out_w[0], None) if single else (out_z, out_w, None)
+
+
+_HOST_SCRATCH = {}
+
+
+def sample_host(seeds_host, params_flat, unflatten, params_fixed, log_prob_model, out_negw_host, out_z_host=None,
+                eps_schedule=None, grad_clipping=False):
+    """Sampling pass with HOST buffers through ``cmcd_bridge_fwd_host``: ``seeds_host`` int32[N] (pinned for an asynchronous
+    copy) in, per-particle losses ``out_negw_host`` f32[N] (and optionally ``out_z_host`` f32[N, d]) back on the host; the call
+    returns after the device-to-host copy completed.  Parameters stay resident on the device.  Small-d registry targets."""
+    from .mcdboundingmachine import make_betas
+    pt, pn = unflatten(params_flat)
+    params = {**pt, **pn}
+    dim, nbridges, mode, apply_fun = params_fixed
+    dev = params_flat.device
+    _lib.require_cuda(params_flat)
+    if seeds_host.is_cuda or out_negw_host.is_cuda or seeds_host.dtype != torch.int32 or out_negw_host.dtype != torch.float32:
+        raise ValueError("sample_host takes host int32 seeds and a host float32 output buffer")
+    n = seeds_host.numel()
+    with torch.no_grad():
+        betas = make_betas(params)
+    vd_mean, vd_logdiag, betas_c, eps, tabs, (clip_t, clip_q), uses_net = _forward_inputs(params, betas, params_fixed, eps_schedule,
+                                                                                         grad_clipping)
+    key = (str(dev), n, dim)
+    if key not in _HOST_SCRATCH:
+        _HOST_SCRATCH.clear()
+        _HOST_SCRATCH[key] = (torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, device=dev), torch.empty(n, dim, device=dev))
+    seeds_dev, negw_dev, z_dev = _HOST_SCRATCH[key]
+    desc, net = _make_desc(mode, dim, nbridges, n, clip_t, clip_q), _make_net(apply_fun if uses_net else None, tabs, nbridges)
+    _lib.check(_lib.lib().cmcd_bridge_fwd_host(desc, _lib.current_stream(), seeds_host.data_ptr(), _lib.ptr(vd_mean), _lib.ptr(vd_logdiag),
+                                               _lib.ptr(betas_c), _lib.ptr(eps), net, log_prob_model.desc(), _lib.ptr(seeds_dev),
+                                               _lib.ptr(negw_dev), _lib.ptr(z_dev), out_negw_host.data_ptr(),
+                                               None if out_z_host is None else out_z_host.data_ptr()))
+    _lib.count_launches(1)
+    return out_negw_host

@@ -195,6 +195,20 @@ int cmcd_bridge_fwd_host(const cmcd_bridge_desc* desc, void* stream, const int32
                          float* out_negw_host, float* out_z_host);
 
 /*
+ * mcd_utils.evolve(z, betas, params, rng_key_gen, params_fixed, log_prob_model, eps_schedule, grad_clipping) -> (z, w, None)
+ * (src/mcd_utils.py:24-33; bodies src/mcd_cais.py:6-99, src/mcd_cais_var.py:7-112, src/mcd_over_orig.py:6-65), batched over
+ * particles: the K bridge steps started from caller-supplied states z0[N][dim] and per-particle PRNG keys keys[N][2] (uint32,
+ * the `rng_key_gen` argument: the body consumes it exactly like the reference -- split once, then split / normal / split per
+ * step).  out_z[N][dim] = z_K, out_w[N] = sum over the steps of log B_k - log F_k (NOT negated; no -log q(z0) and no
+ * log p(z_K): compute_log_elbo adds those, src/mcdboundingmachine.py:157,178).  Forward only (the differentiable entry is
+ * cmcd_bridge_fwd / cmcd_bridge_bwd); overdamped modes (0..3), dim 2 or 10, registry targets.  desc, vd_*, betas, eps, net,
+ * target as in cmcd_bridge_fwd.
+ */
+int cmcd_bridge_evolve(const cmcd_bridge_desc* desc, void* stream, const float* z0, const uint32_t* keys,
+                       const float* vd_mean, const float* vd_logdiag, const float* betas, const float* eps,
+                       const cmcd_net* net, const cmcd_target* target, float* out_z, float* out_w);
+
+/*
  * log p(x), grad log p(x) and (if v != NULL) Hessian(log p)(x) v for x[n][dim] -- replaces calling
  * log_prob_model / jax.grad(log_prob_model) on a batch (model_handler.py:124-284; used by
  * utils.py:54 for plotting and by the tests).  Any output pointer may be NULL.

@@ -114,8 +114,38 @@ def eps_at(eps0, i, nbridges, eps_schedule):
     return eps0
 
 
+_ANALYTIC = [False]
+
+
+class analytic_scores:
+    """Context manager for the CPU-BASELINE leg of bench.py only: densities that carry a closed-form ``.score`` (q, many_gmm) use
+    it instead of the create_graph autograd call, so the timed baseline is not an eager double-backward strawman.  Same values
+    up to rounding (tests/test_oracle_pins.py::test_analytic_scores_match_autograd); parity tests never enable it."""
+
+    def __enter__(self):
+        self.prev, _ANALYTIC[0] = _ANALYTIC[0], True
+
+    def __exit__(self, *a):
+        _ANALYTIC[0] = self.prev
+
+
+class _QLogProb:
+    """log q as a callable that also knows its closed-form score -(z - mean) / sigma^2 (vardist/diag_gauss.py:28-33)."""
+
+    def __init__(self, vd):
+        self.vd = vd
+
+    def __call__(self, x):
+        return vd_log_prob(self.vd, x)
+
+    def score(self, x):
+        return -(x - self.vd["mean"]) * torch.exp(-2.0 * self.vd["logdiag"])
+
+
 def _score(fn, z):
     """jax.grad(fn)(z) per particle; differentiable again (second order) when z carries a graph."""
+    if _ANALYTIC[0] and hasattr(fn, "score"):
+        return fn.score(z)
     zz = z if z.requires_grad else z.detach().requires_grad_(True)
     with torch.enable_grad():
         (g,) = torch.autograd.grad(fn(zz).sum(), zz, create_graph=True)
@@ -285,7 +315,7 @@ def evolve(z, betas, params, xi, params_fixed, log_prob_model, eps_schedule=None
     """mcd_utils.py:24-190 dispatch + the three scan bodies.  xi [K,N,d] are the per-step Gaussians."""
     dim, nbridges, mode, apply_fun_sn = params_fixed
     vd = params["vd"]
-    q_lp = lambda x: vd_log_prob(vd, x)
+    q_lp = _QLogProb(vd)
     w = torch.zeros(z.shape[0], dtype=z.dtype)
     if mode in ("MCD_ULA", "MCD_ULA_sn"):
         use_sn = mode == "MCD_ULA_sn"

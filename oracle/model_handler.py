@@ -98,6 +98,17 @@ def load_model_manygmm(config, dtype=torch.float32):
         valid = lp > -1e4  # :279-280
         return torch.where(valid, lp, torch.full_like(lp, -float("inf")))
 
+    def score(x):
+        """Closed form of grad log p (responsibility-weighted pull to the means; zero where the -inf override fires) -- used only
+        by the CPU-baseline timing leg (oracle.mcdboundingmachine.analytic_scores)."""
+        diff = means[None] - x[:, None, :]
+        lp_comp = (-0.5 * (diff / scale) ** 2).sum(-1)
+        r = torch.softmax(lp_comp, dim=-1)
+        sc = (r[..., None] * diff).sum(1) / (scale * scale)
+        lp = torch.logsumexp(lp_comp, dim=-1) - 2.0 * (_HALF_LOG2PI + math.log(scale)) + log_mix
+        return torch.where((lp > -1e4)[:, None], sc, torch.zeros_like(sc))
+
+    log_prob.score = score
     return log_prob, 2
 
 

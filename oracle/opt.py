@@ -21,7 +21,7 @@ def randint(key, n, minval, maxval):
     lo = prng.random_bits(k2, n).astype(np.uint64)
     span = np.uint64(maxval - minval if maxval > minval else 1)
     mult = (np.uint64(65536) % span)
-    mult = (mult * mult) % span
+    mult = ((mult * mult) & np.uint64(0xFFFFFFFF)) % span          # lax.mul(multiplier, multiplier) in uint32 wraps: 0 for span > 65536
     off = (((hi % span) * mult) & np.uint64(0xFFFFFFFF))          # lax.mul in uint32 wraps
     off = ((off + (lo % span)) & np.uint64(0xFFFFFFFF)) % span      # lax.add in uint32 wraps
     return (np.int64(minval) + off.astype(np.int64)).astype(np.int32)

@@ -177,6 +177,18 @@ def particle_noise(seeds, dim, nbridges):
     return xi0, xi
 
 
+def evolve_noise(keys, dim, nbridges):
+    """Gaussians consumed by mcd_utils.evolve(z, betas, params, rng_key_gen, ...) started from ``keys`` [N,2] = rng_key_gen
+    (mcd_cais.py:94 then :66,87 per step; identical in mcd_cais_var.py / mcd_over_orig.py).  Returns xi [K,N,d]."""
+    _, k = split(np.asarray(keys, _U32))     # mcd_cais.py:94
+    xi = np.zeros((nbridges, k.shape[0], dim), _f)
+    for i in range(nbridges):
+        a, k = split(k)                      # :66
+        xi[i] = normal(a, dim)
+        _, k = split(k)                      # :87
+    return xi
+
+
 def particle_noise_ud(seeds, dim, nbridges):
     """Key chain of the underdamped lp_a operator (mcdboundingmachine.py:151-162 + mcd_under_lp_a.py:62-73,31,59):
     returns (xi0 [N,d], rho0 [N,d], xi [K,N,d])."""

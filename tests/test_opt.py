@@ -19,6 +19,19 @@ def test_oracle_randint_properties():
     assert (OO.randint(key, 10, 5, 5) == 5).all()
 
 
+def test_oracle_randint_uint32_multiplier_wrap():
+    """jax/_src/random.py::_randint squares 2^16 % span with lax.mul in uint32: for span > 65536 the product wraps to 0 and
+    the draw is minval + lower_bits % span (the reference's randint(key, (N,), 1, 1e6), opt.py:94, is in that regime);
+    for span <= 65536 the multiplier is (2^32 mod span) and both words contribute."""
+    key = P.prng_key(3)
+    k1, k2 = P.split(np.asarray(key, np.uint32))
+    hi, lo = P.random_bits(k1, 1001).astype(np.uint64), P.random_bits(k2, 1001).astype(np.uint64)
+    np.testing.assert_array_equal(OO.randint(key, 1001, 1, 10**6), (1 + lo % 999999).astype(np.int32))
+    span = 1000
+    want = ((hi % span) * ((1 << 32) % span) + lo % span) % span
+    np.testing.assert_array_equal(OO.randint(key, 1001, 0, span), want.astype(np.int32))
+
+
 def test_host_key_split_matches_oracle():
     from cmcd_b200 import opt as PO
     k = PO.prng_key(1)
@@ -30,12 +43,15 @@ def test_host_key_split_matches_oracle():
 
 
 @pytest.mark.gpu
-def test_randint_bit_exact():
+def test_randint_matches_oracle():
+    """Kernel vs the oracle restatement of _randint (itself unpinned against a running JAX), both multiplier regimes."""
     from cmcd_b200 import opt as PO
     for seed, n in ((1, 300), (2, 2001), (3, 1 << 16)):
         key = PO.prng_key(seed)
         got = PO.randint_seeds(key, n).cpu().numpy()
         np.testing.assert_array_equal(got, OO.randint(key, n, 1, 10**6))
+        got = PO.randint_seeds(key, n, 0, 1000).cpu().numpy()
+        np.testing.assert_array_equal(got, OO.randint(key, n, 0, 1000))
 
 
 @pytest.mark.gpu

@@ -192,3 +192,19 @@ def test_uha_k0_equals_mfvi():
     pf2, unf2, fixed2 = OM.bm_initialize(dim)
     b = OM.bm_compute_bound(seeds, pf2, unf2, fixed2, lp)[1][0]
     torch.testing.assert_close(a, b, rtol=0, atol=0)
+
+
+def test_analytic_scores_match_autograd():
+    """bench.py's CPU-baseline leg may time the oracle with closed-form q / many_gmm scores (oracle.analytic_scores) instead of the
+    create_graph autograd scores: same losses and gradients up to rounding."""
+    from helpers import oracle_problem, seeds_for
+    c, lp, dim, pf, unf, fixed = oracle_problem("C_manygmm_dds_small", torch.float64, N=64, K=6)
+    seeds = seeds_for(64)
+    kw = dict(eps_schedule=c["eps_schedule"], grad_clipping=c["clip"])
+    g0, (l0, z0) = OM.grad_and_loss(OM.compute_bound, seeds, pf, unf, fixed, lp, **kw)
+    with OM.analytic_scores():
+        g1, (l1, z1) = OM.grad_and_loss(OM.compute_bound, seeds, pf, unf, fixed, lp, **kw)
+    fin = torch.isfinite(l0)
+    assert (torch.isfinite(l1) == fin).all()
+    torch.testing.assert_close(l1[fin], l0[fin], rtol=1e-10, atol=1e-10)
+    torch.testing.assert_close(g1, g0, rtol=1e-8, atol=1e-10)
