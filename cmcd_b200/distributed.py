@@ -93,7 +93,7 @@ def sharded_grad_and_loss(local_forward, seeds_local, params_flat, loss="kl", gr
         buf[P + 1] = (dev_l * dev_l).sum().to(buf.dtype)      # sum (l - mean)^2: the variance without cancellation
     else:
         raise ValueError(loss)
-    buf[P + 2] = float(n_local)
+    buf[P + 2:].fill_(float(n_local))
     if l.requires_grad and n_local:
         (g,) = torch.autograd.grad(l, p, grad_outputs=cot.to(l.dtype), allow_unused=True)
         if g is not None:
@@ -147,7 +147,7 @@ class ShardedStep:
         ld = l.detach()
         buf = torch.zeros(self.P + 3, dtype=torch.float32, device=p.device)
         buf[self.P:self.P + 2] = _loss_stats(ld)[:2].to(buf.dtype)
-        buf[self.P + 2] = float(self.n_local)
+        buf[self.P + 2:].fill_(float(self.n_local))        # fill_, not an indexed host-scalar copy: legal inside a graph capture
         (g,) = torch.autograd.grad(l, p, grad_outputs=torch.full_like(ld, 1.0 / self.n_global), allow_unused=True)
         if g is not None:
             buf[:self.P] = g

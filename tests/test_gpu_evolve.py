@@ -14,8 +14,8 @@ from helpers import oracle_problem, product_problem, rel_err, seeds_for
 pytestmark = pytest.mark.gpu
 
 
-def _both(name, N, single=False):
-    c, lp, dim, pf, unf, fixed = oracle_problem(name, torch.float32)
+def _both(name, N, single=False, dtype=torch.float32):
+    c, lp, dim, pf, unf, fixed = oracle_problem(name, dtype)
     K = c["K"]
     g = np.random.default_rng(5)
     z0 = (g.normal(size=(N, dim)) * c["sigma"]).astype(np.float32) + np.float32(c.get("vd_mean", 0.0))
@@ -24,8 +24,10 @@ def _both(name, N, single=False):
     params = {**pt, **pn}
     xi = P.evolve_noise(keys, dim, K)
     with torch.no_grad():
-        z_o, w_o = OM.evolve(torch.from_numpy(z0), OM.make_betas(params), params, torch.from_numpy(xi), fixed, lp,
+        z_o, w_o = OM.evolve(torch.from_numpy(z0).to(dtype), OM.make_betas(params), params, torch.from_numpy(xi).to(dtype), fixed, lp,
                              c["eps_schedule"], c["clip"])
+    if dtype == torch.float64:
+        return z_o, w_o
     _, target, _, pf_p, unf_p, fixed_p = product_problem(name, pf)
     ptp, pnp = unf_p(pf_p)
     pp = {**ptp, **pnp}
@@ -41,11 +43,12 @@ def _both(name, N, single=False):
                                   "ULAsn_gmm_dds", "lin_funnel"])
 def test_evolve_from_state_and_key(name):
     (z_o, w_o), (z_p, w_p), aux = _both(name, 257)
+    z_64, w_64 = _both(name, 257, dtype=torch.float64)      # ground truth; the fp32 oracle's distance to it is the floor
     assert aux is None and z_p.shape == z_o.shape and w_p.shape == w_o.shape
-    fin = torch.isfinite(w_o)
+    fin = torch.isfinite(w_64)
     assert (torch.isfinite(w_p) == fin).all()
-    assert rel_err(w_p[fin], w_o[fin]).max() < 1e-4
-    assert rel_err(z_p[fin], z_o[fin]).max() < 1e-4
+    assert rel_err(w_p[fin], w_64[fin]).max() < max(1e-4, 2 * rel_err(w_o[fin], w_64[fin]).max())
+    assert rel_err(z_p[fin], z_64[fin]).max() < max(1e-4, 2 * rel_err(z_o[fin], z_64[fin]).max())
 
 
 def test_evolve_single_particle_signature():
