@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_fwd_blk_kernel(const BridgeArg
     float2* sMu = reinterpret_cast<float2*>(sTp + ((ntp + 3) & ~3));   // many_gmm: dense component means (fast path, D = 2)
     const bool fast_gmm = (D == 2) && a.tgt.kind == TGT_MANY_GMM;
     if (fast_gmm)
-        for (int i = tid; i < a.tgt.ncomp; i += blockDim.x) sMu[i] = make_float2(a.tgt.mix[i * MIX_STRIDE], a.tgt.mix[i * MIX_STRIDE + 1]);
+        many_gmm_stage_means(a.tgt, sMu, tid, blockDim.x);
     const ManyGmmConst gc = many_gmm_const(a.tgt);
     float* S1 = reinterpret_cast<float*>(sMu + MIX_MAX);
     float* S2 = S1 + (size_t)HP * BK_RS;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(BK_T, 1) bridge_bwd_blk_kernel(const BridgeArg
     float2* sMu = reinterpret_cast<float2*>(sTp + ((ntp + 3) & ~3));
     const bool fast_gmm = (D == 2) && a.tgt.kind == TGT_MANY_GMM;
     if (fast_gmm)
-        for (int i = tid; i < a.tgt.ncomp; i += blockDim.x) sMu[i] = make_float2(a.tgt.mix[i * MIX_STRIDE], a.tgt.mix[i * MIX_STRIDE + 1]);
+        many_gmm_stage_means(a.tgt, sMu, tid, blockDim.x);
     const ManyGmmConst gc = many_gmm_const(a.tgt);
     float* S1 = reinterpret_cast<float*>(sMu + MIX_MAX);
     float* S2 = S1 + (size_t)HP * BK_RS;

@@ -181,6 +181,13 @@ __device__ __forceinline__ void bt_issue_wgrad(uint32_t tmem_base, uint64_t dx, 
     }
 }
 
+// timing experiments (tools/ab_variants.sh; results are WRONG with any of these defined): which phase sits on the critical path?
+#ifdef BT_X_NOG1
+#define BT_G1S(c, k) xb[0]
+#else
+#define BT_G1S(c, k) g1s[c][k]
+#endif
+
 template <int D>
 __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const BridgeArgs a, const float* __restrict__ cot_negw,
                                                                       float* __restrict__ partials, const BtLayout L) {
@@ -192,10 +199,12 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
     const NetView& nv = a.net;
     float* sf = reinterpret_cast<float*>(smem + BT_OFF_SMALL);
     float* sU1 = sf;                        // [D][64]
-    float* sW3 = sU1 + D * BT_H;            // [64][D]
+    float* sW3 = sU1 + D * BT_H;            // [D][64]: W3 TRANSPOSED (row m = output dim), so that pairs of hidden units are packed operands
     float* sAccU1 = sW3 + BT_H * D;         // [D][64]  gradient accumulators shared by both tiles
     float* sAccW3 = sAccU1 + D * BT_H;      // [64][D]
-    float* sTp = sAccW3 + BT_H * D;         // mixture parameters (generic layout, MIX_STRIDE floats per component)
+    float* sAccC2 = sAccW3 + BT_H * D;      // [64]  (dds: c2 = st2.b and c3 = out.b are the same row for every step, so their cotangents
+    float* sAccC3 = sAccC2 + BT_H;          // [D]    are accumulated over the steps here and reported in table row 0; [D + 1] = out_scale)
+    float* sTp = sAccC3 + 8;                // mixture parameters (generic layout, MIX_STRIDE floats per component)
     float2* sMu = reinterpret_cast<float2*>(sTp + MIX_MAX * MIX_STRIDE);   // many_gmm: dense component means
     // per-warp double buffer for the per-step table rows c1[t] | c2[t] (cp.async one half-step ahead)
     float* sTab = reinterpret_cast<float*>(sMu + MIX_MAX) + warp * (2 * 2 * BT_H);
@@ -216,12 +225,13 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
         *reinterpret_cast<float*>(smem + BT_OFF_BD_LO + od) = lo;
     }
     for (int i = tid; i < D * BT_H; i += BT_THREADS) { sU1[i] = nv.U1[i]; sAccU1[i] = 0.f; }
-    for (int i = tid; i < BT_H * D; i += BT_THREADS) { sW3[i] = nv.W3[i]; sAccW3[i] = 0.f; }
+    for (int i = tid; i < BT_H * D; i += BT_THREADS) { sW3[(i % D) * BT_H + i / D] = nv.W3[i]; sAccW3[i] = 0.f; }
+    for (int i = tid; i < BT_H + 8; i += BT_THREADS) sAccC2[i] = 0.f;
     const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
     for (int i = tid; i < ntp; i += BT_THREADS) sTp[i] = a.tgt.mix[i];
     const bool fast_gmm = (a.tgt.kind == TGT_MANY_GMM);
     if (fast_gmm)
-        for (int i = tid; i < a.tgt.ncomp; i += BT_THREADS) sMu[i] = make_float2(a.tgt.mix[i * MIX_STRIDE], a.tgt.mix[i * MIX_STRIDE + 1]);
+        many_gmm_stage_means(a.tgt, sMu, tid, BT_THREADS);
     const ManyGmmConst gc = many_gmm_const(a.tgt);
     if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
@@ -267,11 +277,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 
     // per-lane accumulators of the skinny gradients that are not indexed by the step: after a butterfly, lane l holds the
     // warp's sum for hidden unit 16 cc + bt_red_col(l); summed over the whole kernel, flushed once at the end
-    float aW3[4][D], aU1[4][D];
-#pragma unroll
-    for (int k4 = 0; k4 < 4; ++k4)
-#pragma unroll
-        for (int m = 0; m < D; ++m) { aW3[k4][m] = 0.f; aU1[k4][m] = 0.f; }
+    // (the step-independent skinny gradients -- U1, W3, c2, c3 -- go into shared-memory accumulators of the CTA with one
+    //  ATOMS per reduced element and warp: the select chains that kept per-chunk register accumulators statically indexed cost
+    //  16 instructions per 16-unit chunk)
 
     bool wgrad_pending = false;   // a WGRAD batch has been committed to mb3 and not yet waited for
     bool d3_fresh = true;         // the TMEM gW2 accumulator holds nothing (next WGRAD starts with accumulate = 0)
@@ -330,8 +338,11 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
             zpre2[j] = (K > 1) ? a.traj[((size_t)(K - 2) * D + j) * a.N + n] : 0.f;
             gmu[j] = 0.f; gls[j] = 0.f; zero[j] = 0.f; carry[j] = 0.f; rS[j] = 0.f; zup[j] = 0.f; sx[j] = 0.f; hv[j] = 0.f;
         }
-        float g1s[4][16];               // act'(pre1) of the current evaluation, chunk-indexed with static indices only
+        f32x2_t g1s[4][8];              // act'(pre1) of the current evaluation as packed pairs, chunk-indexed with static indices only
         float cgb = 0.f, cge = 0.f;     // beta_i / eps_i gradient of step j: B-use part, carried from node j+1 to node j
+        float c3Acc[D], gosAcc = 0.f;   // cotangents of the (step-independent) output bias and of out_scale, summed over the nodes
+#pragma unroll
+        for (int j = 0; j < D; ++j) c3Acc[j] = 0.f;
 
         const int t0 = cais ? 0 : -1;   // table row of node j: t0 + j
         stage_tab(t0 + K, (t0 + K) & 1);
@@ -340,6 +351,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
         for (int j = K; j >= 0; --j) {
             const bool hasB = j > 0, hasF = j < K;
             const int t = t0 + j;
+            f32x2_t xb[D];                    // (x_d, x_d): broadcast operands of the packed fp32x2 products
+#pragma unroll
+            for (int d = 0; d < D; ++d) xb[d] = pk2(x[d], x[d]);
             const bool use_nn = cais || hasB;
             // step constants of both uses; an absent use gets eps = 0, c = 0 so that all of its terms vanish
             // step constants: (beta, eps) of step j-1 were requested one node ago; those of step j are last node's B-use values
@@ -365,30 +379,36 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 const float4* __restrict__ c1v = reinterpret_cast<const float4*>(tab);
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
-                    float a1[16], g1[16];
+                    float a1[16];
+                    f32x2_t g1[8];
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) {
                         const float4 cv = c1v[cc * 4 + qq];
-                        float p[4] = {cv.x, cv.y, cv.z, cv.w};
+                        f32x2_t p01 = pk2(cv.x, cv.y), p23 = pk2(cv.z, cv.w);   // two hidden units per FFMA2 (x broadcast pairs built once per node)
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
                             const float4 u = *reinterpret_cast<const float4*>(sU1 + d * BT_H + cc * 16 + qq * 4);
-                            p[0] = fmaf(x[d], u.x, p[0]); p[1] = fmaf(x[d], u.y, p[1]);
-                            p[2] = fmaf(x[d], u.z, p[2]); p[3] = fmaf(x[d], u.w, p[3]);
+                            p01 = fma2(xb[d], pk2(u.x, u.y), p01);
+                            p23 = fma2(xb[d], pk2(u.z, u.w), p23);
                         }
                         {   // two activations (+ derivatives) per instruction slot (FFMA2)
+                            float q0, q1, q2, q3;
+                            upk2(p01, q0, q1); upk2(p23, q2, q3);
                             f32x2_t A, DA;
-                            gelu_fast_grad2(p[0], p[1], A, DA);
-                            upk2(A, a1[qq * 4 + 0], a1[qq * 4 + 1]); upk2(DA, g1[qq * 4 + 0], g1[qq * 4 + 1]);
-                            gelu_fast_grad2(p[2], p[3], A, DA);
-                            upk2(A, a1[qq * 4 + 2], a1[qq * 4 + 3]); upk2(DA, g1[qq * 4 + 2], g1[qq * 4 + 3]);
+                            gelu_fast_grad2(q0, q1, A, DA);
+                            upk2(A, a1[qq * 4 + 0], a1[qq * 4 + 1]); g1[qq * 2 + 0] = DA;
+                            gelu_fast_grad2(q2, q3, A, DA);
+                            upk2(A, a1[qq * 4 + 2], a1[qq * 4 + 3]); g1[qq * 2 + 1] = DA;
                         }
                     }
+#ifndef BT_X_NOG1
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {   // predicated moves: static register indices, no control-flow merge
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) g1s[k4][e] = (k4 == cc) ? g1[e] : g1s[k4][e];
+                        for (int e = 0; e < 8; ++e) g1s[k4][e] = (k4 == cc) ? g1[e] : g1s[k4][e];
                     }
+#endif
+#ifndef BT_X_NOSPLIT
                     uint32_t hh[16], ll[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
@@ -398,7 +418,12 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                     }
                     umma::tmem_st16(tmem_lane + BT_A_HI + cc * 16, hh);
                     umma::tmem_st16(tmem_lane + BT_A_LO + cc * 16, ll);
+#endif
+#ifndef BT_X_NOSTAGE
                     bt_stage_bf16x2(tX1, tX2, q, cc, a1);
+#else
+                    if (a1[3] == 12345.678f) bt_stage_bf16x2(tX1, tX2, q, cc, a1);
+#endif
                 }
                 umma::tmem_st_wait();
                 umma::fence_before();
@@ -416,7 +441,11 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
             }
 
             // ---------------- independent of the network: target score (+ Hessian) and score-side terms at x ----------------
+#ifdef BT_X_NOSCORE
+            if (fast_gmm) { sx[0] = -x[0]; sx[1] = -x[1]; hx[0] = -1.f; hx[1] = 0.f; hx[2] = -1.f; }
+#else
             if (fast_gmm) many_gmm_eval_hess(gc, sMu, x[0], x[1], sx[0], sx[1], hx[0], hx[1], hx[2]);   // every HVP at x comes from it
+#endif
             else target_eval<D, false>(a.tgt, sTp, x, sx, zero, hv);
             float sq[D], mk_t[D], mk_q[D], uB[D], uF[D], mB[D], mF[D], dc[D], nn[D], dx[D];
 #pragma unroll
@@ -444,6 +473,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                 const float4* __restrict__ c2v = reinterpret_cast<const float4*>(tab + BT_H);
                 umma::mbar_wait(mb1, par1); par1 ^= 1u;
                 umma::fence_after();
+                f32x2_t O2[D];                // output-layer partial sums over (even, odd) hidden units
+#pragma unroll
+                for (int m = 0; m < D; ++m) O2[m] = pk2(0.f, 0.f);
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
                     uint32_t v[16], a2u[16], g2u[16];
@@ -452,28 +484,34 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) {
                         const float4 cv = c2v[cc * 4 + qq];
-                        const float p[4] = {__uint_as_float(v[qq * 4 + 0]) + cv.x, __uint_as_float(v[qq * 4 + 1]) + cv.y,
-                                            __uint_as_float(v[qq * 4 + 2]) + cv.z, __uint_as_float(v[qq * 4 + 3]) + cv.w};
-                        float a2v[4], g2v[4];
-                        {
-                            f32x2_t A, DA;
-                            gelu_fast_grad2(p[0], p[1], A, DA);
-                            upk2(A, a2v[0], a2v[1]); upk2(DA, g2v[0], g2v[1]);
-                            gelu_fast_grad2(p[2], p[3], A, DA);
-                            upk2(A, a2v[2], a2v[3]); upk2(DA, g2v[2], g2v[3]);
-                        }
+                        const f32x2_t P01 = add2(pk2(__uint_as_float(v[qq * 4 + 0]), __uint_as_float(v[qq * 4 + 1])), pk2(cv.x, cv.y));
+                        const f32x2_t P23 = add2(pk2(__uint_as_float(v[qq * 4 + 2]), __uint_as_float(v[qq * 4 + 3])), pk2(cv.z, cv.w));
+                        float q0, q1, q2, q3;
+                        upk2(P01, q0, q1); upk2(P23, q2, q3);
+                        f32x2_t A01, D01, A23, D23;
+                        gelu_fast_grad2(q0, q1, A01, D01);
+                        gelu_fast_grad2(q2, q3, A23, D23);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int jj = cc * 16 + qq * 4 + e;
-#pragma unroll
-                            for (int m = 0; m < D; ++m) o[m] = fmaf(a2v[e], sW3[jj * D + m], o[m]);
-                            a2u[qq * 4 + e] = __float_as_uint(a2v[e]);
-                            g2u[qq * 4 + e] = __float_as_uint(g2v[e]);
+                        for (int m = 0; m < D; ++m) {
+                            const float4 w = *reinterpret_cast<const float4*>(sW3 + m * BT_H + cc * 16 + qq * 4);
+                            O2[m] = fma2(A01, pk2(w.x, w.y), O2[m]);
+                            O2[m] = fma2(A23, pk2(w.z, w.w), O2[m]);
                         }
+                        float f0, f1;
+                        upk2(A01, f0, f1); a2u[qq * 4 + 0] = __float_as_uint(f0); a2u[qq * 4 + 1] = __float_as_uint(f1);
+                        upk2(A23, f0, f1); a2u[qq * 4 + 2] = __float_as_uint(f0); a2u[qq * 4 + 3] = __float_as_uint(f1);
+                        upk2(D01, f0, f1); g2u[qq * 4 + 0] = __float_as_uint(f0); g2u[qq * 4 + 1] = __float_as_uint(f1);
+                        upk2(D23, f0, f1); g2u[qq * 4 + 2] = __float_as_uint(f0); g2u[qq * 4 + 3] = __float_as_uint(f1);
                     }
                     // the A region is dead between GEMM1 and GEMM2: park a2 / act'(pre2) in this thread's lane
                     umma::tmem_st16(tmem_lane + BT_A_HI + cc * 16, a2u);
                     umma::tmem_st16(tmem_lane + BT_A_LO + cc * 16, g2u);
+                }
+#pragma unroll
+                for (int m = 0; m < D; ++m) {
+                    float e0, e1;
+                    upk2(O2[m], e0, e1);
+                    o[m] += e0 + e1;
                 }
                 umma::tmem_st_wait();
 #pragma unroll
@@ -500,18 +538,18 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 
             // ---------------- output-layer VJP, dp2, GEMM2 + WGRAD ----------------
             if (use_nn) {
-                float vo[D], gos = 0.f;
+                float vo[D];
 #pragma unroll
                 for (int m = 0; m < D; ++m) {
                     const float v = vv[m];
                     const float oc = fminf(fmaxf(o[m], -nv.out_clip), nv.out_clip);
-                    gos = fmaf(v, oc, gos);
+                    gosAcc = fmaf(v, oc, gosAcc);
                     vo[m] = (fabsf(o[m]) <= nv.out_clip) ? v * out_scale : 0.f;
-                    const float s = bt_warp_sum(vo[m]);
-                    if (lane == 0) atomicAdd(part + L.c3 + (size_t)t * D + m, s);
+                    c3Acc[m] += vo[m];
                 }
-                gos = bt_warp_sum(gos);
-                if (lane == 0 && gos != 0.f) atomicAdd(part + L.os, gos);
+                f32x2_t vob[D];
+#pragma unroll
+                for (int m = 0; m < D; ++m) vob[m] = pk2(vo[m], vo[m]);
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
                     uint32_t a2u[16], g2u[16];
@@ -521,30 +559,50 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                     float dp2[16];
                     uint32_t hh[16], ll[16];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int jj = cc * 16 + e;
-                        float s = 0.f;
+                    for (int k = 0; k < 8; ++k) {     // dp2 = (W3 vo) * act'(pre2), two hidden units per packed instruction
+                        f32x2_t S = mul2(*reinterpret_cast<const f32x2_t*>(sW3 + cc * 16 + 2 * k), vob[0]);
 #pragma unroll
-                        for (int m = 0; m < D; ++m) s = fmaf(sW3[jj * D + m], vo[m], s);
-                        dp2[e] = s * __uint_as_float(g2u[e]);
+                        for (int m = 1; m < D; ++m) S = fma2(*reinterpret_cast<const f32x2_t*>(sW3 + m * BT_H + cc * 16 + 2 * k), vob[m], S);
+                        const f32x2_t DP = mul2(S, pk2(__uint_as_float(g2u[2 * k]), __uint_as_float(g2u[2 * k + 1])));
+                        upk2(DP, dp2[2 * k], dp2[2 * k + 1]);
+                    }
+#ifndef BT_X_NOSPLIT
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
                         float hi, lo;
                         umma::split_tf32(dp2[e], hi, lo);
                         hh[e] = __float_as_uint(hi); ll[e] = __float_as_uint(lo);
                     }
                     umma::tmem_st16(tmem_lane + BT_A_HI + cc * 16, hh);
                     umma::tmem_st16(tmem_lane + BT_A_LO + cc * 16, ll);
+#endif
+#ifndef BT_X_NOSTAGE
                     bt_stage_bf16x2(tZ1, tZ2, q, cc, dp2);
+#else
+                    if (dp2[3] == 12345.678f) bt_stage_bf16x2(tZ1, tZ2, q, cc, dp2);
+#endif
                     // gc2[t][j] += sum_p dp2 ; gW3[j][m] += sum_p a2 vo[m]   (three butterflies in lock step; D == 2)
                     {
                         static_assert(D == 2, "the interleaved reductions assume d = 2");
                         float t0v[16], t1v[16];
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) { t0v[e] = __uint_as_float(a2u[e]) * vo[0]; t1v[e] = __uint_as_float(a2u[e]) * vo[1]; }
+                        for (int k = 0; k < 8; ++k) {
+                            const f32x2_t A2 = pk2(__uint_as_float(a2u[2 * k]), __uint_as_float(a2u[2 * k + 1]));
+                            upk2(mul2(A2, vob[0]), t0v[2 * k], t0v[2 * k + 1]);
+                            upk2(mul2(A2, vob[1]), t1v[2 * k], t1v[2 * k + 1]);
+                        }
                         float s2, s30, s31;
-                        bt_tmem_reduce16x3(tmem_lane + BT_D12, tmem_lane + BT_D12 + 16, tmem_lane + BT_D12 + 32, dp2, t0v, t1v, lane, s2, s30, s31);   // D is free between GEMM1's epilogue and GEMM2
-                        if (!(lane & 4)) atomicAdd(part + L.c2 + (size_t)t * BT_H + cc * 16 + bt_red_col(lane), s2);
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) { aW3[k4][0] += (k4 == cc) ? s30 : 0.f; aW3[k4][1] += (k4 == cc) ? s31 : 0.f; }
+#ifdef BT_X_NOREDUCE
+                        s2 = dp2[0]; s30 = t0v[1]; s31 = t1v[2];
+#else
+                        bt_tmem_reduce16x3(tmem_lane + BT_D12, tmem_lane + BT_D12 + 16, tmem_lane + BT_D12 + 32, dp2, t0v, t1v, lane, s2, s30, s31);
+#endif   // D is free between GEMM1's epilogue and GEMM2
+                        if (!(lane & 4)) {
+                            const int jc = cc * 16 + bt_red_col(lane);
+                            atomicAdd(sAccC2 + jc, s2);
+                            atomicAdd(sAccW3 + jc * D + 0, s30);
+                            atomicAdd(sAccW3 + jc * D + 1, s31);
+                        }
                     }
                 }
                 umma::tmem_st_wait();
@@ -601,45 +659,64 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
             if (use_nn) {
                 umma::mbar_wait(mb2, par2); par2 ^= 1u;
                 umma::fence_after();
+                f32x2_t DX2[D];               // input cotangent partial sums over (even, odd) hidden units
+#pragma unroll
+                for (int d = 0; d < D; ++d) DX2[d] = pk2(0.f, 0.f);
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
                     uint32_t v[16];
                     umma::tmem_ld16(tmem_lane + BT_D12 + cc * 16, v);
                     umma::tmem_ld_wait();
                     float dp1[16];
+                    f32x2_t DP1[8];
                     switch (cc) {
                         case 0:
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) dp1[e] = __uint_as_float(v[e]) * g1s[0][e];
+                            for (int k = 0; k < 8; ++k) DP1[k] = mul2(pk2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])), BT_G1S(0, k));
                             break;
                         case 1:
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) dp1[e] = __uint_as_float(v[e]) * g1s[1][e];
+                            for (int k = 0; k < 8; ++k) DP1[k] = mul2(pk2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])), BT_G1S(1, k));
                             break;
                         case 2:
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) dp1[e] = __uint_as_float(v[e]) * g1s[2][e];
+                            for (int k = 0; k < 8; ++k) DP1[k] = mul2(pk2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])), BT_G1S(2, k));
                             break;
                         default:
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) dp1[e] = __uint_as_float(v[e]) * g1s[3][e];
+                            for (int k = 0; k < 8; ++k) DP1[k] = mul2(pk2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])), BT_G1S(3, k));
                             break;
                     }
+                    float t0v[16], t1v[16];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
+                    for (int k = 0; k < 8; ++k) {
 #pragma unroll
-                        for (int d = 0; d < D; ++d) dx[d] = fmaf(sU1[d * BT_H + cc * 16 + e], dp1[e], dx[d]);
+                        for (int d = 0; d < D; ++d)
+                            DX2[d] = fma2(*reinterpret_cast<const f32x2_t*>(sU1 + d * BT_H + cc * 16 + 2 * k), DP1[k], DX2[d]);
+                        upk2(DP1[k], dp1[2 * k], dp1[2 * k + 1]);
+                        upk2(mul2(DP1[k], xb[0]), t0v[2 * k], t0v[2 * k + 1]);
+                        upk2(mul2(DP1[k], xb[1]), t1v[2 * k], t1v[2 * k + 1]);
                     }
                     {
-                        float t0v[16], t1v[16];
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) { t0v[e] = x[0] * dp1[e]; t1v[e] = x[1] * dp1[e]; }
                         float s1, s40, s41;
-                        bt_tmem_reduce16x3(tmem_lane + BT_A_HI, tmem_lane + BT_A_HI + 16, tmem_lane + BT_A_HI + 32, dp1, t0v, t1v, lane, s1, s40, s41);   // the A region is dead after GEMM2
-                        if (!(lane & 4)) atomicAdd(part + L.c1 + (size_t)t * BT_H + cc * 16 + bt_red_col(lane), s1);
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) { aU1[k4][0] += (k4 == cc) ? s40 : 0.f; aU1[k4][1] += (k4 == cc) ? s41 : 0.f; }
+#ifdef BT_X_NOREDUCE
+                        s1 = dp1[0]; s40 = t0v[1]; s41 = t1v[2];
+#else
+                        bt_tmem_reduce16x3(tmem_lane + BT_A_HI, tmem_lane + BT_A_HI + 16, tmem_lane + BT_A_HI + 32, dp1, t0v, t1v, lane, s1, s40, s41);
+#endif   // the A region is dead after GEMM2
+                        if (!(lane & 4)) {
+                            const int jc = cc * 16 + bt_red_col(lane);
+                            atomicAdd(part + L.c1 + (size_t)t * BT_H + jc, s1);
+                            atomicAdd(sAccU1 + 0 * BT_H + jc, s40);
+                            atomicAdd(sAccU1 + 1 * BT_H + jc, s41);
+                        }
                     }
+                }
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    float e0, e1;
+                    upk2(DX2[d], e0, e1);
+                    dx[d] = e0 + e1;
                 }
                 umma::fence_before();
             }
@@ -665,23 +742,19 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
         for (int j = 0; j < D; ++j) {
             if (pathwise) { gmu[j] += carry[j]; gls[j] += carry[j] * (zup[j] - mu[j]); }
             gls[j] += c;
-            const float m1 = bt_warp_sum(gmu[j]), m2 = bt_warp_sum(gls[j]);
-            if (lane == 0) { atomicAdd(part + L.mu + j, m1); atomicAdd(part + L.ls + j, m2); }
+            const float m1 = bt_warp_sum(gmu[j]), m2 = bt_warp_sum(gls[j]), m3 = bt_warp_sum(c3Acc[j]);
+            if (lane == 0) { atomicAdd(part + L.mu + j, m1); atomicAdd(part + L.ls + j, m2); atomicAdd(sAccC3 + j, m3); }
         }
+        gosAcc = bt_warp_sum(gosAcc);
+        if (lane == 0 && gosAcc != 0.f) atomicAdd(sAccC3 + D, gosAcc);
     }
     flush_d3();
-    if (!(lane & 4)) {
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-#pragma unroll
-            for (int m = 0; m < D; ++m) {
-                atomicAdd(sAccW3 + (k4 * 16 + bt_red_col(lane)) * D + m, aW3[k4][m]);
-                atomicAdd(sAccU1 + m * BT_H + k4 * 16 + bt_red_col(lane), aU1[k4][m]);
-            }
-    }
     __syncthreads();
     for (int i = tid; i < D * BT_H; i += BT_THREADS) part[L.U1 + i] = sAccU1[i];
     for (int i = tid; i < BT_H * D; i += BT_THREADS) part[L.W3 + i] = sAccW3[i];
+    for (int i = tid; i < BT_H; i += BT_THREADS) part[L.c2 + i] = sAccC2[i];        // row 0 of the c2 table carries the sum over the steps
+    if (tid < D) part[L.c3 + tid] = sAccC3[tid];                                     // likewise c3
+    if (tid == D) part[L.os] = sAccC3[D];
     umma::fence_before();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem_slot, 512);
@@ -715,7 +788,7 @@ __global__ void bwd_tc_reduce_kernel(const float* __restrict__ partials, int nbl
 }
 
 static size_t bt_smem_bytes(int D) {
-    return (size_t)BT_OFF_SMALL + (size_t)(4 * D * BT_H + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 8 * 4 * BT_H + 8) * sizeof(float);
+    return (size_t)BT_OFF_SMALL + (size_t)(4 * D * BT_H + BT_H + 8 + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 8 * 4 * BT_H + 8) * sizeof(float);
 }
 
 bool bwd_tc_supported(const BridgeArgs& a, int D) {

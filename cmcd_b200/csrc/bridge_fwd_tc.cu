@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
     };
     const bool fast_gmm = (D == 2) && (a.tgt.kind == TGT_MANY_GMM);
     if (fast_gmm)
-        for (int i = tid; i < a.tgt.ncomp; i += TC_PB) sMu[i] = make_float2(a.tgt.mix[i * MIX_STRIDE], a.tgt.mix[i * MIX_STRIDE + 1]);
+        many_gmm_stage_means(a.tgt, sMu, tid, TC_PB);
     const ManyGmmConst gc = many_gmm_const(a.tgt);
     if (warp == 0) { umma::tmem_alloc(&tmem_slot, TC_COLS_MAIN, false); umma::tmem_alloc(&tmem_slot_lo, TC_COLS_LO, true); }
     if (tid == 0) { umma::mbar_init(&mbar, 1); umma::mbar_init(&mbar_ready, TC_PB); }

@@ -66,6 +66,12 @@ int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
 int launch_adam_project(cudaStream_t st, float* p, const float* g, float* m, float* v, const float* lo, const float* hi, long long n,
                         float lr, float b1, float b2, float eps, float clip, int step, float* ema, float ema_step,
                         const int32_t* skip_flag);
+int launch_chain_fwd(const cmcd_chain* c, cudaStream_t st, const float* params_flat, float* betas, float* eps, float* c1, float* c2, float* c3,
+                     float* U1p, float* U2p, float* W2p, float* W3p);
+size_t chain_bwd_scratch_floats(const cmcd_chain* c);
+int launch_chain_bwd(const cmcd_chain* c, cudaStream_t st, const float* params_flat, const float* g_betas, const float* g_eps,
+                     const float* g_vd_mean, const float* g_vd_logdiag, const cmcd_net_grad* gn, float* scratch, size_t scratch_floats,
+                     float* grad_flat);
 int launch_randint(cudaStream_t st, uint32_t key0, uint32_t key1, long long n, int32_t minval, int32_t maxval, int32_t* out);
 
 // SM count of the CURRENT device, cached per device id (one process may drive several GPUs; relaxed atomics: the value is
@@ -245,6 +251,18 @@ int cmcd_loss_stats(void* stream, const float* negw, int64_t n, float* out4) {
 int cmcd_batched_elbo_lnz(void* stream, const float* losses, int32_t batches, int32_t n, float* elbo, float* lnz) {
     if (batches < 1 || n < 1) { set_error("empty batch"); return 2; }
     return launch_batched_elbo_lnz((cudaStream_t)stream, losses, batches, n, elbo, lnz);
+}
+
+int cmcd_chain_fwd(const cmcd_chain* chain, void* stream, const float* params_flat, float* betas, float* eps, float* c1, float* c2,
+                   float* c3, float* U1_pad, float* U2_pad, float* W2_pad, float* W3_pad) {
+    return launch_chain_fwd(chain, (cudaStream_t)stream, params_flat, betas, eps, c1, c2, c3, U1_pad, U2_pad, W2_pad, W3_pad);
+}
+size_t cmcd_chain_bwd_scratch_floats(const cmcd_chain* chain) { return chain_bwd_scratch_floats(chain); }
+int cmcd_chain_bwd(const cmcd_chain* chain, void* stream, const float* params_flat, const float* g_betas, const float* g_eps,
+                   const float* g_vd_mean, const float* g_vd_logdiag, const cmcd_net_grad* g_net, float* scratch,
+                   size_t scratch_floats, float* grad_flat) {
+    return launch_chain_bwd(chain, (cudaStream_t)stream, params_flat, g_betas, g_eps, g_vd_mean, g_vd_logdiag, g_net, scratch,
+                            scratch_floats, grad_flat);
 }
 
 int cmcd_bridge_evolve(const cmcd_bridge_desc* desc, void* stream, const float* z0, const uint32_t* keys, const float* vd_mean,

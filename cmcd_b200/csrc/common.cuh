@@ -133,6 +133,9 @@ __device__ __forceinline__ f32x2_t gelu_fast2(float x0, float x1) {
 }
 // value and derivative of two GELUs: A = gelu, DA = Phi(x) + x phi(x)
 __device__ __forceinline__ void gelu_fast_grad2(float x0, float x1, f32x2_t& A, f32x2_t& DA) {
+#ifdef BT_X_NOGELU
+    A = mul2(pk2(x0, x1), pk2(0.5f, 0.5f)); DA = add2(pk2(x0, x1), pk2(0.5f, 0.5f)); return;
+#endif
     f32x2_t NAX, E;
     const f32x2_t H = gelu_half_erfc2(x0, x1, NAX, E);
     A = fma2(NAX, H, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));

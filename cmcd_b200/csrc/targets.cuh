@@ -138,47 +138,94 @@ __device__ __forceinline__ ManyGmmConst many_gmm_const(const TargetDesc& t) {
     c.nc = t.ncomp;
     return c;
 }
+// Component means are staged in shared memory as PAIRS of components, negated: float4 p = (-x_{2p}, -x_{2p+1}, -y_{2p}, -y_{2p+1})
+// (same footprint as a float2 per component), so that one LDS.128 feeds two components and the displacement, squared
+// distance, exponent argument and all moment accumulations run as packed fp32x2 instructions (FADD2 / FMUL2 / FFMA2: one
+// issue slot for two components).  An odd component count is padded with a component at 1e15 (weight exp(-inf) = 0).
+__device__ __forceinline__ void many_gmm_stage_means(const TargetDesc& t, float2* smu, int tid, int nthreads) {
+    float* f = reinterpret_cast<float*>(smu);
+    const int np = (t.ncomp + 1) >> 1;
+    for (int i = tid; i < 2 * np; i += nthreads) {
+        const bool real = i < t.ncomp;
+        const float mx = real ? t.mix[i * MIX_STRIDE] : 1e15f, my = real ? t.mix[i * MIX_STRIDE + 1] : 1e15f;
+        f[(i >> 1) * 4 + (i & 1)] = -mx;
+        f[(i >> 1) * 4 + 2 + (i & 1)] = -my;
+    }
+}
+__device__ __forceinline__ unsigned long long mg_pk2(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void mg_upk2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long mg_fma2(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ unsigned long long mg_mul2(unsigned long long a, unsigned long long b) { unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ unsigned long long mg_add2(unsigned long long a, unsigned long long b) { unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// Sweep 1: the nearest component.  Squared distances are >= 0, so their bit patterns order like the values: the component index
+// rides in the 6 low mantissa bits of the key and one integer min per component finds the argmin (ties / near-ties within
+// 2^-17 relative go to the lower index -- any near-nearest component is an equally good pivot).  Returns the pivot displacement.
+__device__ __forceinline__ void many_gmm_pivot(const ManyGmmConst& c, const float2* __restrict__ smu, float z0, float z1, float& p0, float& p1) {
+    const float4* __restrict__ m4 = reinterpret_cast<const float4*>(smu);
+    const unsigned long long Z0 = mg_pk2(z0, z0), Z1 = mg_pk2(z1, z1);
+    const int np = (c.nc + 1) >> 1;
+    uint32_t kmin = 0x7F800000u;
+#pragma unroll 4
+    for (int p = 0; p < np; ++p) {
+        const float4 m = m4[p];
+        const unsigned long long D0 = mg_add2(Z0, mg_pk2(m.x, m.y)), D1 = mg_add2(Z1, mg_pk2(m.z, m.w));
+        float qa, qb;
+        mg_upk2(mg_fma2(D0, D0, mg_mul2(D1, D1)), qa, qb);
+        kmin = min(kmin, (__float_as_uint(qa) & 0xFFFFFFC0u) | (uint32_t)(2 * p));
+        kmin = min(kmin, (__float_as_uint(qb) & 0xFFFFFFC0u) | (uint32_t)(2 * p + 1));
+    }
+    const int ks = (int)(kmin & 63u);
+    const float* f = reinterpret_cast<const float*>(smu) + (ks >> 1) * 4 + (ks & 1);
+    p0 = z0 + f[0];
+    p1 = z1 + f[2];
+}
+
 template <bool WANT_HVP>
 __device__ __forceinline__ float many_gmm_eval(const ManyGmmConst& c, const float2* __restrict__ smu, float z0, float z1,
                                                float& g0, float& g1, float v0, float v1, float& hv0, float& hv1) {
-    float qmin = CUDART_INF_F, p0 = 0.f, p1 = 0.f;   // pivot displacement d_piv = z - mu_piv
-#pragma unroll 8
-    for (int k = 0; k < c.nc; ++k) {
-        const float2 m = smu[k];
-        const float d0 = z0 - m.x, d1 = z1 - m.y;
-        const float q = fmaf(d0, d0, d1 * d1);
-        if (q < qmin) { qmin = q; p0 = d0; p1 = d1; }
-    }
+    float p0, p1;                                     // pivot displacement d_piv = z - mu_piv
+    many_gmm_pivot(c, smu, z0, z1, p0, p1);
+    const float qmin = fmaf(p0, p0, p1 * p1);
     const float off = -c.hl2 * qmin;
-    float S = 0.f, G0 = 0.f, G1 = 0.f, Q0 = 0.f, Q1 = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < c.nc; ++k) {
-        const float2 m = smu[k];
-        const float d0 = z0 - m.x, d1 = z1 - m.y;
-        float e;
-        {
-            const float arg = fmaf(c.hl2, fmaf(d0, d0, d1 * d1), off);
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
-        }
-        S += e; G0 = fmaf(e, d0, G0); G1 = fmaf(e, d1, G1);
+    const float4* __restrict__ m4 = reinterpret_cast<const float4*>(smu);
+    const unsigned long long Z0 = mg_pk2(z0, z0), Z1 = mg_pk2(z1, z1), HL2 = mg_pk2(c.hl2, c.hl2), OFF = mg_pk2(off, off);
+    const unsigned long long NP0 = mg_pk2(-p0, -p0), NP1 = mg_pk2(-p1, -p1), V0 = mg_pk2(v0, v0), V1 = mg_pk2(v1, v1);
+    unsigned long long S = mg_pk2(0.f, 0.f), G0 = S, G1 = S, Q0 = S, Q1 = S;
+    const int np = (c.nc + 1) >> 1;
+#pragma unroll 4
+    for (int p = 0; p < np; ++p) {
+        const float4 m = m4[p];
+        const unsigned long long D0 = mg_add2(Z0, mg_pk2(m.x, m.y)), D1 = mg_add2(Z1, mg_pk2(m.z, m.w));
+        float aa, ab, ea, eb;
+        mg_upk2(mg_fma2(HL2, mg_fma2(D0, D0, mg_mul2(D1, D1)), OFF), aa, ab);
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(aa));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(ab));
+        const unsigned long long E = mg_pk2(ea, eb);
+        S = mg_add2(S, E); G0 = mg_fma2(E, D0, G0); G1 = mg_fma2(E, D1, G1);
         if (WANT_HVP) {
-            const float e0 = d0 - p0, e1 = d1 - p1;       // = -(delta_k) ; sign cancels in the quadratic form
-            const float t = e * fmaf(e0, v0, e1 * v1);
-            Q0 = fmaf(t, e0, Q0); Q1 = fmaf(t, e1, Q1);
+            const unsigned long long E0 = mg_add2(D0, NP0), E1 = mg_add2(D1, NP1);   // = -(delta_k); the sign cancels in the quadratic form
+            const unsigned long long T = mg_mul2(E, mg_fma2(E0, V0, mg_mul2(E1, V1)));
+            Q0 = mg_fma2(T, E0, Q0); Q1 = mg_fma2(T, E1, Q1);
         }
     }
-    const float lp = logf(S) + fmaf(-0.5f * qmin, c.inv_var, c.norm_const);
+    float sa, sb, ga, gb, ha, hb;
+    mg_upk2(S, sa, sb); const float Ss = sa + sb;
+    mg_upk2(G0, ga, gb); mg_upk2(G1, ha, hb);
+    const float lp = logf(Ss) + fmaf(-0.5f * qmin, c.inv_var, c.norm_const);
     const bool valid = lp > c.invalid_below;
-    const float inv = 1.0f / S;
-    const float m0 = G0 * inv, m1 = G1 * inv;              // responsibility-weighted mean displacement
+    const float inv = 1.0f / Ss;
+    const float m0 = (ga + gb) * inv, m1 = (ha + hb) * inv;   // responsibility-weighted mean displacement
     g0 = valid ? -m0 * c.inv_var : 0.f;
     g1 = valid ? -m1 * c.inv_var : 0.f;
     if (WANT_HVP) {
+        float qa, qb, ra, rb;
+        mg_upk2(Q0, qa, qb); mg_upk2(Q1, ra, rb);
         const float b0 = m0 - p0, b1 = m1 - p1;
         const float bv = fmaf(b0, v0, b1 * v1);
         const float iv2 = c.inv_var * c.inv_var;
-        hv0 = valid ? fmaf(iv2, fmaf(Q0, inv, -b0 * bv), -v0 * c.inv_var) : 0.f;
-        hv1 = valid ? fmaf(iv2, fmaf(Q1, inv, -b1 * bv), -v1 * c.inv_var) : 0.f;
+        hv0 = valid ? fmaf(iv2, fmaf(qa + qb, inv, -b0 * bv), -v0 * c.inv_var) : 0.f;
+        hv1 = valid ? fmaf(iv2, fmaf(ra + rb, inv, -b1 * bv), -v1 * c.inv_var) : 0.f;
     }
     return valid ? lp : -CUDART_INF_F;
 }
@@ -189,41 +236,44 @@ __device__ __forceinline__ float many_gmm_eval(const ManyGmmConst& c, const floa
 // v per bridge step: once as z of step k, once as z' of step k-1).
 __device__ __forceinline__ float many_gmm_eval_hess(const ManyGmmConst& c, const float2* __restrict__ smu, float z0, float z1,
                                                     float& g0, float& g1, float& h00, float& h01, float& h11) {
-    float qmin = CUDART_INF_F, p0 = 0.f, p1 = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < c.nc; ++k) {
-        const float2 m = smu[k];
-        const float d0 = z0 - m.x, d1 = z1 - m.y;
-        const float q = fmaf(d0, d0, d1 * d1);
-        if (q < qmin) { qmin = q; p0 = d0; p1 = d1; }
-    }
+    float p0, p1;
+    many_gmm_pivot(c, smu, z0, z1, p0, p1);
+    const float qmin = fmaf(p0, p0, p1 * p1);
     const float off = -c.hl2 * qmin;
-    float S = 0.f, G0 = 0.f, G1 = 0.f, M00 = 0.f, M01 = 0.f, M11 = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < c.nc; ++k) {
-        const float2 m = smu[k];
-        const float d0 = z0 - m.x, d1 = z1 - m.y;
-        float e;
-        {
-            const float arg = fmaf(c.hl2, fmaf(d0, d0, d1 * d1), off);
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
-        }
-        S += e; G0 = fmaf(e, d0, G0); G1 = fmaf(e, d1, G1);
-        const float e0 = d0 - p0, e1 = d1 - p1;
-        const float t0 = e * e0;
-        M00 = fmaf(t0, e0, M00); M01 = fmaf(t0, e1, M01); M11 = fmaf(e * e1, e1, M11);
+    const float4* __restrict__ m4 = reinterpret_cast<const float4*>(smu);
+    const unsigned long long Z0 = mg_pk2(z0, z0), Z1 = mg_pk2(z1, z1), HL2 = mg_pk2(c.hl2, c.hl2), OFF = mg_pk2(off, off);
+    const unsigned long long NP0 = mg_pk2(-p0, -p0), NP1 = mg_pk2(-p1, -p1);
+    unsigned long long S = mg_pk2(0.f, 0.f), G0 = S, G1 = S, M00 = S, M01 = S, M11 = S;
+    const int np = (c.nc + 1) >> 1;
+#pragma unroll 4
+    for (int p = 0; p < np; ++p) {
+        const float4 m = m4[p];
+        const unsigned long long D0 = mg_add2(Z0, mg_pk2(m.x, m.y)), D1 = mg_add2(Z1, mg_pk2(m.z, m.w));
+        float aa, ab, ea, eb;
+        mg_upk2(mg_fma2(HL2, mg_fma2(D0, D0, mg_mul2(D1, D1)), OFF), aa, ab);
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(aa));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(ab));
+        const unsigned long long E = mg_pk2(ea, eb);
+        S = mg_add2(S, E); G0 = mg_fma2(E, D0, G0); G1 = mg_fma2(E, D1, G1);
+        const unsigned long long E0 = mg_add2(D0, NP0), E1 = mg_add2(D1, NP1);
+        const unsigned long long T0 = mg_mul2(E, E0);
+        M00 = mg_fma2(T0, E0, M00); M01 = mg_fma2(T0, E1, M01); M11 = mg_fma2(mg_mul2(E, E1), E1, M11);
     }
-    const float lp = logf(S) + fmaf(-0.5f * qmin, c.inv_var, c.norm_const);
+    float sa, sb, ga, gb, ha, hb, xa, xb, ya, yb, wa, wb;
+    mg_upk2(S, sa, sb); const float Ss = sa + sb;
+    mg_upk2(G0, ga, gb); mg_upk2(G1, ha, hb);
+    mg_upk2(M00, xa, xb); mg_upk2(M01, ya, yb); mg_upk2(M11, wa, wb);
+    const float lp = logf(Ss) + fmaf(-0.5f * qmin, c.inv_var, c.norm_const);
     const bool valid = lp > c.invalid_below;
-    const float inv = 1.0f / S;
-    const float m0 = G0 * inv, m1 = G1 * inv;
+    const float inv = 1.0f / Ss;
+    const float m0 = (ga + gb) * inv, m1 = (ha + hb) * inv;
     g0 = valid ? -m0 * c.inv_var : 0.f;
     g1 = valid ? -m1 * c.inv_var : 0.f;
     const float b0 = m0 - p0, b1 = m1 - p1;
     const float iv2 = c.inv_var * c.inv_var;
-    h00 = valid ? fmaf(iv2, fmaf(M00, inv, -b0 * b0), -c.inv_var) : 0.f;
-    h01 = valid ? iv2 * fmaf(M01, inv, -b0 * b1) : 0.f;
-    h11 = valid ? fmaf(iv2, fmaf(M11, inv, -b1 * b1), -c.inv_var) : 0.f;
+    h00 = valid ? fmaf(iv2, fmaf(xa + xb, inv, -b0 * b0), -c.inv_var) : 0.f;
+    h01 = valid ? iv2 * fmaf(ya + yb, inv, -b0 * b1) : 0.f;
+    h11 = valid ? fmaf(iv2, fmaf(wa + wb, inv, -b1 * b1), -c.inv_var) : 0.f;
     return valid ? lp : -CUDART_INF_F;
 }
 

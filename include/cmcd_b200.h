@@ -195,6 +195,48 @@ int cmcd_bridge_fwd_host(const cmcd_bridge_desc* desc, void* stream, const int32
                          float* out_negw_host, float* out_z_host);
 
 /*
+ * The O(K) chain around the bridge, fused ("prologue" / "epilogue" of one compute_log_elbo call and of its gradient).
+ * compute_log_elbo derives, from the flat parameter vector alone: betas (mcdboundingmachine.py:146-149: cumsum(mgridref_y) /
+ * sum, interp at target_x), the per-step step sizes (mcd_cais.py:34-44,54-59) and the step-dependent part of the drift
+ * network -- PISNet's time coder pushed through the first state layer (nn_dds.py:130-143,156-161) or the geffner net's
+ * clamped embedding gather pushed through the three Dense layers (nn.py:62-70); jax.grad then transposes all of it.  These
+ * two entry points do that directly on params_flat = ravel_pytree((params_train, params_notrain)) (mcdboundingmachine.py:122):
+ * cmcd_chain_fwd writes betas[K], eps[K] and the tables c1/c2/c3 of cmcd_net (plus zero-padded copies of the geffner
+ * weights when hidden != hidden_pad; for dds, U1 / W2 / W3 are views of params_flat); cmcd_chain_bwd takes the cotangents
+ * cmcd_bridge_bwd produced and writes the flat gradient (zero for leaves outside train_mask -- stop_gradient(params_notrain),
+ * mcdboundingmachine.py:142).  off[] holds the offset (in floats) of each pytree leaf inside params_flat, -1 if absent.
+ */
+enum { CMCD_EPS_CONST = 0, CMCD_EPS_LINEAR = 1, CMCD_EPS_COS_SQ = 2 };
+enum {
+    CMCD_LEAF_VD_MEAN = 0, CMCD_LEAF_VD_LOGDIAG, CMCD_LEAF_EPS, CMCD_LEAF_MGRID_Y, CMCD_LEAF_GRID_X, CMCD_LEAF_TARGET_X,
+    CMCD_LEAF_DDS_PHASE, CMCD_LEAF_DDS_TC1_W, CMCD_LEAF_DDS_TC1_B, CMCD_LEAF_DDS_TC2_W, CMCD_LEAF_DDS_TC2_B,
+    CMCD_LEAF_DDS_ST1_W, CMCD_LEAF_DDS_ST1_B, CMCD_LEAF_DDS_ST2_W, CMCD_LEAF_DDS_ST2_B, CMCD_LEAF_DDS_OUT_W, CMCD_LEAF_DDS_OUT_B,
+    CMCD_LEAF_GEF_EMB, CMCD_LEAF_GEF_FACTOR, CMCD_LEAF_GEF_W1, CMCD_LEAF_GEF_B1, CMCD_LEAF_GEF_W2, CMCD_LEAF_GEF_B2,
+    CMCD_LEAF_GEF_W3, CMCD_LEAF_GEF_B3, CMCD_LEAF_COUNT
+};
+typedef struct cmcd_chain {
+    int32_t arch;          /* CMCD_ARCH_* */
+    int32_t dim;           /* d: output width of the network = dimension of z */
+    int32_t in_dim;        /* rows of the first-layer weights that see the particle (d) */
+    int32_t nbridges;      /* K >= 1 */
+    int32_t emb_dim;       /* geffner: E */
+    int32_t hidden;        /* H (dds: 64; geffner: in_dim + E) */
+    int32_t hidden_pad;    /* HP */
+    int32_t eps_schedule;  /* CMCD_EPS_* */
+    int32_t ngrid;         /* len(mgridref_y) = ngridb + 1 <= 39 */
+    uint32_t train_mask;   /* bit CMCD_LEAF_x set: the leaf is in params_train */
+    int64_t n_params;      /* len(params_flat) */
+    int64_t off[CMCD_LEAF_COUNT];
+    const float* dds_coeff; /* device, 64 floats: linspace(0.1, 100, 64) (nn_dds.py:108) */
+} cmcd_chain;
+int cmcd_chain_fwd(const cmcd_chain* chain, void* stream, const float* params_flat, float* betas, float* eps,
+                   float* c1, float* c2, float* c3, float* U1_pad, float* U2_pad, float* W2_pad, float* W3_pad);
+size_t cmcd_chain_bwd_scratch_floats(const cmcd_chain* chain);
+int cmcd_chain_bwd(const cmcd_chain* chain, void* stream, const float* params_flat, const float* g_betas, const float* g_eps,
+                   const float* g_vd_mean, const float* g_vd_logdiag, const cmcd_net_grad* g_net,
+                   float* scratch, size_t scratch_floats, float* grad_flat);
+
+/*
  * mcd_utils.evolve(z, betas, params, rng_key_gen, params_fixed, log_prob_model, eps_schedule, grad_clipping) -> (z, w, None)
  * (src/mcd_utils.py:24-33; bodies src/mcd_cais.py:6-99, src/mcd_cais_var.py:7-112, src/mcd_over_orig.py:6-65), batched over
  * particles: the K bridge steps started from caller-supplied states z0[N][dim] and per-particle PRNG keys keys[N][2] (uint32,
