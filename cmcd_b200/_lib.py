@@ -50,6 +50,19 @@ class CmcdBridgeDesc(C.Structure):
                 ("clip_target", C.c_float), ("clip_q", C.c_float), ("lfsteps", C.c_int32)]
 
 
+LEAVES = ("VD_MEAN", "VD_LOGDIAG", "EPS", "MGRID_Y", "GRID_X", "TARGET_X",
+          "DDS_PHASE", "DDS_TC1_W", "DDS_TC1_B", "DDS_TC2_W", "DDS_TC2_B", "DDS_ST1_W", "DDS_ST1_B", "DDS_ST2_W", "DDS_ST2_B",
+          "DDS_OUT_W", "DDS_OUT_B", "GEF_EMB", "GEF_FACTOR", "GEF_W1", "GEF_B1", "GEF_W2", "GEF_B2", "GEF_W3", "GEF_B3")
+LEAF = {n: i for i, n in enumerate(LEAVES)}       # CMCD_LEAF_* (include/cmcd_b200.h)
+EPS_SCHEDULE = {None: 0, "": 0, "linear": 1, "cos_sq": 2}
+
+
+class CmcdChain(C.Structure):
+    _fields_ = [("arch", C.c_int32), ("dim", C.c_int32), ("in_dim", C.c_int32), ("nbridges", C.c_int32), ("emb_dim", C.c_int32),
+                ("hidden", C.c_int32), ("hidden_pad", C.c_int32), ("eps_schedule", C.c_int32), ("ngrid", C.c_int32),
+                ("train_mask", C.c_uint32), ("n_params", C.c_int64), ("off", C.c_int64 * len(LEAVES)), ("dds_coeff", _fp)]
+
+
 EXPORTS = {
     "cmcd_last_error": (C.c_char_p, []),
     "cmcd_version": (C.c_int, []),
@@ -69,6 +82,9 @@ EXPORTS = {
                                        C.POINTER(CmcdTarget), _fp, _fp, _fp, _fp, _fp]),
     "cmcd_bridge_evolve": (C.c_int, [C.POINTER(CmcdBridgeDesc), _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNet),
                                      C.POINTER(CmcdTarget), _fp, _fp]),
+    "cmcd_chain_fwd": (C.c_int, [C.POINTER(CmcdChain), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "cmcd_chain_bwd_scratch_floats": (C.c_size_t, [C.POINTER(CmcdChain)]),
+    "cmcd_chain_bwd": (C.c_int, [C.POINTER(CmcdChain), _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(CmcdNetGrad), _fp, C.c_size_t, _fp]),
     "cmcd_target_eval": (C.c_int, [C.POINTER(CmcdTarget), C.c_int32, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp]),
     "cmcd_adam_project_step": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                          C.c_float, C.c_int32, _fp, C.c_float, _fp]),

@@ -115,74 +115,238 @@ def _check_cb(rc, target):
     _lib.check(rc)
 
 
+def _launch_fwd(cfg, seeds, vd_mean, vd_logdiag, betas, eps, tabs):
+    """cmcd_bridge_fwd on detached, contiguous float32 device buffers -> (negw, z, traj)."""
+    mode, dim, K, apply_fun, target, clip_t, clip_q, need_grad = cfg[:8]
+    lfsteps = cfg[8] if len(cfg) > 8 else 0
+    dev = vd_mean.device
+    n = seeds.numel()
+    negw = torch.empty(n, device=dev, dtype=torch.float32)
+    z = torch.empty(n, dim, device=dev, dtype=torch.float32)
+    rows = 3 * dim if (mode in UD_MODES or mode == "UHA") else dim   # underdamped: (z_j, rho_j, rho'_j) per node
+    traj = torch.empty((K + 1, rows, n), device=dev, dtype=torch.float32) if need_grad else None
+    desc, net, tg = _make_desc(mode, dim, K, n, clip_t, clip_q, lfsteps), _make_net(apply_fun, tabs, K), target.desc()
+    L = _lib.lib()
+    ws_bytes = L.cmcd_bridge_fwd_workspace_bytes(desc, net, tg)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+    with _lib.timed("fwd"):
+        rc = L.cmcd_bridge_fwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean),
+                               _lib.ptr(vd_logdiag), _lib.ptr(betas), _lib.ptr(eps), net, tg,
+                               _lib.ptr(negw), _lib.ptr(z), _lib.ptr(traj), _lib.ptr(ws), ws_bytes)
+        _check_cb(rc, target)
+    _lib.count_launches(1 if ws is None else 3 + 16 * K)
+    return negw, z, traj
+
+
+def _launch_bwd(cfg, seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj, cot_negw):
+    """cmcd_bridge_bwd -> (g_mean, g_logdiag, g_betas, g_eps, {table name: cotangent})."""
+    mode, dim, K, apply_fun, target, clip_t, clip_q, need_grad = cfg[:8]
+    lfsteps = cfg[8] if len(cfg) > 8 else 0
+    if traj is None:
+        raise RuntimeError("bridge was run without a trajectory; cannot differentiate")
+    dev = vd_mean.device
+    n = seeds.numel()
+    cot = cot_negw.detach().to(torch.float32).contiguous()
+    wide_rows = mode in UD_MODES or mode == "UHA"   # eps carries several coefficient rows
+    desc, net, tg = _make_desc(mode, dim, K, n, clip_t, clip_q, lfsteps), _make_net(apply_fun, tabs, K), target.desc()
+    # every cotangent buffer is a view of ONE zero-filled allocation (one fill launch instead of a dozen)
+    shapes = [("mean", vd_mean.shape), ("logdiag", vd_logdiag.shape), ("betas", (max(K, 1),)),
+              ("eps", tuple(eps.shape) if wide_rows else (max(K, 1),))]
+    if apply_fun is not None:
+        shapes += [(k, tuple(tabs[k].shape)) for k in _NET_KEYS if tabs[k] is not None]
+    sizes = [(math.prod(sh) + 3) // 4 * 4 for _, sh in shapes]          # 16-byte aligned views
+    pool = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+    views, o = {}, 0
+    for (name, sh), sz in zip(shapes, sizes):
+        views[name] = pool[o:o + math.prod(sh)].view(sh)
+        o += sz
+    g_mean, g_logdiag, g_betas, g_eps = views["mean"], views["logdiag"], views["betas"], views["eps"]
+    gnet, gt = CmcdNetGrad(), {}
+    if apply_fun is not None:
+        for k in _NET_KEYS:
+            if tabs[k] is not None:
+                gt[k] = views[k]
+                setattr(gnet, k, _lib.ptr(gt[k]))
+    L = _lib.lib()
+    ws_bytes = L.cmcd_bridge_bwd_workspace_bytes_for_target(desc, net, tg)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    with _lib.timed("bwd"):
+        rc = L.cmcd_bridge_bwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean),
+                               _lib.ptr(vd_logdiag), _lib.ptr(betas), _lib.ptr(eps), net, tg, _lib.ptr(traj),
+                               _lib.ptr(cot), _lib.ptr(g_mean), _lib.ptr(g_logdiag), _lib.ptr(g_betas),
+                               _lib.ptr(g_eps), gnet, _lib.ptr(ws), ws_bytes)
+        _check_cb(rc, target)
+    _lib.count_launches(2)  # adjoint kernel + partial-gradient reduce kernel
+    return g_mean, g_logdiag, g_betas, g_eps, gt, gnet
+
+
 class _Bridge(torch.autograd.Function):
     """(-w[N], z_K[N,d]) = bridge(seeds; vd, betas, eps, net tables)."""
 
     @staticmethod
     def forward(ctx, cfg, seeds, vd_mean, vd_logdiag, betas, eps, *net_t):
-        mode, dim, K, apply_fun, target, clip_t, clip_q, need_grad = cfg[:8]
-        lfsteps = cfg[8] if len(cfg) > 8 else 0
+        apply_fun = cfg[3]
         _lib.require_cuda(seeds, vd_mean)
-        dev = vd_mean.device
-        n = seeds.numel()
         f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
         vd_mean, vd_logdiag, betas, eps = f32(vd_mean), f32(vd_logdiag), f32(betas), f32(eps)
-        tabs = None
-        if apply_fun is not None:
-            tabs = {k: f32(t) for k, t in zip(_NET_KEYS, net_t)}
-        negw = torch.empty(n, device=dev, dtype=torch.float32)
-        z = torch.empty(n, dim, device=dev, dtype=torch.float32)
-        rows = 3 * dim if (mode in UD_MODES or mode == "UHA") else dim   # underdamped: (z_j, rho_j, rho'_j) per node
-        traj = torch.empty((K + 1, rows, n), device=dev, dtype=torch.float32) if need_grad else None
-        desc, net, tg = _make_desc(mode, dim, K, n, clip_t, clip_q, lfsteps), _make_net(apply_fun, tabs, K), target.desc()
-        L = _lib.lib()
-        ws_bytes = L.cmcd_bridge_fwd_workspace_bytes(desc, net, tg)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
-        with _lib.timed("fwd"):
-            rc = L.cmcd_bridge_fwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean),
-                                   _lib.ptr(vd_logdiag), _lib.ptr(betas), _lib.ptr(eps), net, tg,
-                                   _lib.ptr(negw), _lib.ptr(z), _lib.ptr(traj), _lib.ptr(ws), ws_bytes)
-            _check_cb(rc, target)
-        _lib.count_launches(1 if ws is None else 3 + 16 * K)
+        tabs = {k: f32(t) for k, t in zip(_NET_KEYS, net_t)} if apply_fun is not None else None
+        negw, z, traj = _launch_fwd(cfg, seeds, vd_mean, vd_logdiag, betas, eps, tabs)
         ctx.cfg, ctx.saved = cfg, (seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj)
         ctx.mark_non_differentiable(z)
         return negw, z
 
     @staticmethod
     def backward(ctx, cot_negw, _cot_z):
-        mode, dim, K, apply_fun, target, clip_t, clip_q, need_grad = ctx.cfg[:8]
-        lfsteps = ctx.cfg[8] if len(ctx.cfg) > 8 else 0
-        seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj = ctx.saved
-        if traj is None:
-            raise RuntimeError("bridge was run without a trajectory; cannot differentiate")
-        dev = vd_mean.device
-        n = seeds.numel()
-        cot = cot_negw.detach().to(torch.float32).contiguous()
-        g_mean, g_logdiag = torch.zeros_like(vd_mean), torch.zeros_like(vd_logdiag)
-        g_betas = torch.zeros(max(K, 1), device=dev)
-        wide_rows = mode in UD_MODES or mode == "UHA"   # eps carries several coefficient rows
-        g_eps = torch.zeros_like(eps) if wide_rows else torch.zeros(max(K, 1), device=dev)
-        desc, net, tg = _make_desc(mode, dim, K, n, clip_t, clip_q, lfsteps), _make_net(apply_fun, tabs, K), target.desc()
-        gnet, gt = CmcdNetGrad(), {}
-        if apply_fun is not None:
-            for k in _NET_KEYS:
-                if tabs[k] is not None:
-                    gt[k] = torch.zeros_like(tabs[k])
-                    setattr(gnet, k, _lib.ptr(gt[k]))
-        L = _lib.lib()
-        ws_bytes = L.cmcd_bridge_bwd_workspace_bytes_for_target(desc, net, tg)
-        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-        with _lib.timed("bwd"):
-            rc = L.cmcd_bridge_bwd(desc, _lib.current_stream(), _lib.ptr(seeds), _lib.ptr(vd_mean),
-                                   _lib.ptr(vd_logdiag), _lib.ptr(betas), _lib.ptr(eps), net, tg, _lib.ptr(traj),
-                                   _lib.ptr(cot), _lib.ptr(g_mean), _lib.ptr(g_logdiag), _lib.ptr(g_betas),
-                                   _lib.ptr(g_eps), gnet, _lib.ptr(ws), ws_bytes)
-            _check_cb(rc, target)
-        _lib.count_launches(2)  # adjoint kernel + partial-gradient reduce kernel
+        mode, dim, K, apply_fun = ctx.cfg[:4]
+        g_mean, g_logdiag, g_betas, g_eps, gt, _ = _launch_bwd(ctx.cfg, *ctx.saved, cot_negw)
         net_grads = tuple(gt.get(k) for k in _NET_KEYS) if apply_fun is not None else ()
-        if wide_rows:
+        if mode in UD_MODES or mode == "UHA":
             return (None, None, g_mean, g_logdiag, g_betas[:K] if K else None, g_eps if K else None, *net_grads)
         return (None, None, g_mean, g_logdiag, g_betas[:K] if K else None, g_eps[:K] if K else None, *net_grads)
+
+
+# ------------------------------------------------------------------ fused O(K) chain (csrc/chain.cu)
+_CHAIN_MODES = ("MCD_ULA", "MCD_ULA_sn", "MCD_CAIS_sn", "MCD_CAIS_var_sn")
+_CHAIN_CACHE = {}
+
+
+def _chain_desc(unflatten, params_fixed, eps_schedule, device):
+    """cmcd_chain for this (pytree layout, problem) pair, or None when the fused chain does not serve it.  Cached: the
+    descriptor depends only on static data (the reference passes the same objects as static jit arguments)."""
+    import os
+    dim, nbridges, mode, apply_fun = params_fixed
+    if os.environ.get("CMCD_DISABLE_CHAIN") or mode not in _CHAIN_MODES or nbridges < 1 or not hasattr(unflatten, "leaf_offsets"):
+        return None
+    key = (id(unflatten), params_fixed, eps_schedule, str(device))
+    if key in _CHAIN_CACHE:
+        return _CHAIN_CACHE[key]
+    from ._lib import EPS_SCHEDULE, LEAF, CmcdChain
+    from .nn import dds_timestep_coeff
+    c = None
+    try:
+        pt, pn = unflatten.leaf_offsets()
+        uses_net = mode != "MCD_ULA"
+        arch = apply_fun.arch if (uses_net and apply_fun is not None) else None
+        if uses_net and (apply_fun is None or apply_fun.rho_dim != 0 or "sn" not in pt):
+            raise KeyError("network")
+        c = CmcdChain()
+        c.arch, c.dim, c.in_dim, c.nbridges = ARCH[arch], dim, dim, nbridges
+        c.emb_dim = apply_fun.emb_dim if arch == "geffner" else 0
+        c.hidden = apply_fun.hidden if arch else 0
+        c.hidden_pad = apply_fun.hidden_pad if arch else 0
+        c.eps_schedule = EPS_SCHEDULE[eps_schedule if mode in ("MCD_CAIS_sn", "MCD_CAIS_var_sn") else None]   # orig ignores the schedule
+        c.n_params = unflatten.size
+        for i in range(len(c.off)):
+            c.off[i] = -1
+        mask = 0
+
+        def put(name, tree_train, tree_fixed, *path):
+            nonlocal mask
+            for tree, trained in ((tree_train, True), (tree_fixed, False)):
+                node = tree
+                try:
+                    for k in path:
+                        node = node[k]
+                except (KeyError, IndexError, TypeError):
+                    continue
+                c.off[LEAF[name]] = node[0]
+                if trained:
+                    mask |= 1 << LEAF[name]
+                return node[1]
+            raise KeyError(path)
+
+        put("VD_MEAN", pt, pn, "vd", "mean"); put("VD_LOGDIAG", pt, pn, "vd", "logdiag"); put("EPS", pt, pn, "eps")
+        c.ngrid = put("MGRID_Y", pt, pn, "mgridref_y")[0]
+        put("GRID_X", pt, pn, "gridref_x"); put("TARGET_X", pt, pn, "target_x")
+        if c.ngrid > 39:
+            raise KeyError("ngrid")
+        if arch == "dds":
+            put("DDS_PHASE", pt, pn, "sn", "timestep_phase")
+            for nm, k in (("TC1", "tc1"), ("TC2", "tc2"), ("ST1", "st1"), ("ST2", "st2"), ("OUT", "out")):
+                put(f"DDS_{nm}_W", pt, pn, "sn", k, "w"); put(f"DDS_{nm}_B", pt, pn, "sn", k, "b")
+            c.dds_coeff = _lib.ptr(dds_timestep_coeff(device))
+        elif arch == "geffner":
+            put("GEF_EMB", pt, pn, "sn", "emb"); put("GEF_FACTOR", pt, pn, "sn", "factor_sn")
+            for l in range(3):
+                put(f"GEF_W{l + 1}", pt, pn, "sn", "nn", l, "w"); put(f"GEF_B{l + 1}", pt, pn, "sn", "nn", l, "b")
+        c.train_mask = mask
+    except KeyError:
+        c = None
+    _CHAIN_CACHE[key] = c
+    return c
+
+
+def chain_supported(params_flat, unflatten, params_fixed, eps_schedule=None):
+    return (isinstance(params_flat, torch.Tensor) and params_flat.is_cuda and params_flat.dtype == torch.float32
+            and _chain_desc(unflatten, params_fixed, eps_schedule, params_flat.device) is not None)
+
+
+class _FusedBridge(torch.autograd.Function):
+    """(-w[N], z_K[N,d]) = bridge(seeds; params_flat) with the O(K) chain fused: forward = cmcd_chain_fwd + cmcd_bridge_fwd,
+    backward = cmcd_bridge_bwd + cmcd_chain_bwd (flat gradient written directly)."""
+
+    @staticmethod
+    def forward(ctx, cfg, chain, seeds, params_flat):
+        mode, dim, K, apply_fun = cfg[:4]
+        _lib.require_cuda(seeds, params_flat)
+        dev = params_flat.device
+        p = params_flat.detach().contiguous()
+        T, hp = K + 1, chain.hidden_pad
+        betas, eps = torch.empty(K, device=dev), torch.empty(K, device=dev)
+        tabs, pads = None, [None] * 4
+        view = lambda leaf, *shape: p[chain.off[leaf]:chain.off[leaf] + math.prod(shape)].view(*shape)
+        from ._lib import LEAF
+        if apply_fun is not None:
+            c1, c2, c3 = torch.empty(T, hp, device=dev), torch.empty(T, hp, device=dev), torch.empty(T, dim, device=dev)
+            if apply_fun.arch == "dds":
+                tabs = {"U1": view(LEAF["DDS_ST1_W"], dim, hp), "U2": None, "U3": None, "W2": view(LEAF["DDS_ST2_W"], hp, hp),
+                        "W3": view(LEAF["DDS_OUT_W"], hp, dim), "out_scale": None}
+            else:
+                pads = [torch.empty(dim, hp, device=dev), torch.empty(dim, hp, device=dev), torch.empty(hp, hp, device=dev),
+                        torch.empty(hp, dim, device=dev)]
+                tabs = {"U1": pads[0], "U2": pads[1], "U3": view(LEAF["GEF_W3"], dim, dim), "W2": pads[2], "W3": pads[3],
+                        "out_scale": view(LEAF["GEF_FACTOR"], 1)}
+            tabs.update(c1=c1, c2=c2, c3=c3)
+        else:
+            c1 = c2 = c3 = None
+        _lib.check(_lib.lib().cmcd_chain_fwd(chain, _lib.current_stream(), _lib.ptr(p), _lib.ptr(betas), _lib.ptr(eps), _lib.ptr(c1),
+                                             _lib.ptr(c2), _lib.ptr(c3), *[_lib.ptr(t) for t in pads]))
+        _lib.count_launches(1)
+        vd_mean, vd_logdiag = view(LEAF["VD_MEAN"], dim), view(LEAF["VD_LOGDIAG"], dim)
+        negw, z, traj = _launch_fwd(cfg, seeds, vd_mean, vd_logdiag, betas, eps, tabs)
+        ctx.cfg, ctx.chain, ctx.saved = cfg, chain, (seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj)
+        ctx.p = p
+        ctx.mark_non_differentiable(z)
+        return negw, z
+
+    @staticmethod
+    def backward(ctx, cot_negw, _cot_z):
+        chain, p = ctx.chain, ctx.p
+        g_mean, g_logdiag, g_betas, g_eps, gt, gnet = _launch_bwd(ctx.cfg, *ctx.saved, cot_negw)
+        L = _lib.lib()
+        n_scratch = L.cmcd_chain_bwd_scratch_floats(chain)
+        scratch = torch.empty(n_scratch, device=p.device)
+        grad = torch.empty_like(p)
+        _lib.check(L.cmcd_chain_bwd(chain, _lib.current_stream(), _lib.ptr(p), _lib.ptr(g_betas), _lib.ptr(g_eps), _lib.ptr(g_mean),
+                                    _lib.ptr(g_logdiag), gnet, _lib.ptr(scratch), n_scratch, _lib.ptr(grad)))
+        _lib.count_launches(2)
+        return None, None, None, grad
+
+
+def fused_bridge(seeds, params_flat, unflatten, params_fixed, log_prob_model, eps_schedule=None, grad_clipping=False):
+    """``bridge`` for the overdamped modes straight from the flat parameter vector: betas, the step-size schedule and the
+    per-step network tables are formed by ONE prologue kernel and their transposes by TWO epilogue kernels (csrc/chain.cu)
+    instead of the ~100 framework launches of ``make_betas`` / ``eps_table`` / ``nn.build_tables`` and their autograd mirror.
+    Same values up to the summation order of the 64-wide time-coder products.  ``CMCD_DISABLE_CHAIN=1`` keeps the framework
+    chain (A/B runs, tests)."""
+    dim, nbridges, mode, apply_fun = params_fixed
+    chain = _chain_desc(unflatten, params_fixed, eps_schedule, params_flat.device)
+    uses_net = mode != "MCD_ULA"
+    clip_t, clip_q = _clips(mode, grad_clipping)
+    need_grad = torch.is_grad_enabled() and params_flat.requires_grad
+    cfg = (mode, dim, nbridges, apply_fun if uses_net else None, log_prob_model, clip_t, clip_q, need_grad)
+    seeds = torch.as_tensor(seeds, dtype=torch.int32, device=params_flat.device).contiguous()
+    return _FusedBridge.apply(cfg, chain, seeds, params_flat)
 
 
 def bridge(seeds, params, betas, params_fixed, log_prob_model, eps_schedule=None, grad_clipping=False):

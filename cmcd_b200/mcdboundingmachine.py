@@ -72,13 +72,18 @@ def make_betas(params):
 
 def compute_log_elbo(seed, params_flat, unflatten, params_fixed, log_prob, eps_schedule=None, grad_clipping=False):
     """mcdboundingmachine.py:126-179, batched: ``seed`` may be an int32 vector -> (-w[N], (z[N,d], None))."""
+    scalar = (seed.dim() == 0) if isinstance(seed, torch.Tensor) else not hasattr(seed, "__len__")
+    seeds = torch.as_tensor(seed, dtype=torch.int32).reshape(-1) if scalar else torch.as_tensor(seed, dtype=torch.int32)
+    if mcd_utils.chain_supported(params_flat, unflatten, params_fixed, eps_schedule):
+        # betas / eps schedule / per-step network tables and their transposes in the fused chain kernels (csrc/chain.cu);
+        # stop_gradient(params_notrain) (:142) is the chain's train mask
+        negw, z = mcd_utils.fused_bridge(seeds, params_flat, unflatten, params_fixed, log_prob, eps_schedule, grad_clipping)
+        return (negw[0], (z[0], None)) if scalar else (negw, (z, None))
     pt, pn = unflatten(params_flat)
     pn = tree_map(lambda t: t.detach(), pn)  # jax.lax.stop_gradient(params_notrain) :142
     params = {**pt, **pn}
     nbridges = params_fixed[1]
     betas = make_betas(params) if nbridges >= 1 else None
-    scalar = not hasattr(seed, "__len__") and not (isinstance(seed, torch.Tensor) and seed.dim() > 0)
-    seeds = torch.as_tensor([seed] if scalar else seed, dtype=torch.int32)
     negw, z = mcd_utils.bridge(seeds, params, betas, params_fixed, log_prob, eps_schedule, grad_clipping)
     return (negw[0], (z[0], None)) if scalar else (negw, (z, None))
 

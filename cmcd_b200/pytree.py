@@ -44,6 +44,19 @@ class Unflatten:
         parts = torch.split(vec, self._sizes)
         return _rebuild(self._tree, iter(p.reshape(s) for p, s in zip(parts, self._shapes)))
 
+    def leaf_offsets(self):
+        """The pytree with every leaf replaced by (offset into the flat vector, shape) -- what the fused O(K) chain kernels
+        (csrc/chain.cu) need to read the parameters from / write the gradient into the flat vector directly."""
+        offs, o = [], 0
+        for n in self._sizes:
+            offs.append(o)
+            o += n
+        return _rebuild(self._tree, iter(list(zip(offs, self._shapes))))
+
+    @property
+    def size(self):
+        return sum(self._sizes)
+
 
 def ravel_pytree(tree, dtype=torch.float32, device=None):
     leaves = [torch.as_tensor(l, dtype=dtype, device=device) for l in tree_leaves(tree)]

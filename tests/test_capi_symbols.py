@@ -59,3 +59,27 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 s = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in s and "from oracle" not in s, f
+
+
+def test_xla_ffi_shim_compiles_against_stub():
+    """cmcd_b200/csrc/xla_ffi.cc (the jax.ffi custom-call handlers) cannot be built against jaxlib here; a header-only stub of
+    the public xla/ffi/api/ffi.h surface it uses (tests/xla_ffi_stub) makes the compiler check that every handler's Ctx / Arg /
+    Ret / Attr list matches its implementation's parameter list and that the C ABI is called with the right types -- and the
+    check really bites: dropping one .Arg<>() from a binding fails the build."""
+    import subprocess
+    import tempfile
+    src = os.path.join(ROOT, "cmcd_b200", "csrc", "xla_ffi.cc")
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "tests", "xla_ffi_stub"), "-I", "/usr/local/cuda/include"]
+    ok = subprocess.run(cmd + [src], capture_output=True, text=True)
+    assert ok.returncode == 0, ok.stderr[-2000:]
+    text = open(src).read()
+    marker = ".Arg<F32>()                                                                 // mix"
+    assert marker in text
+    bad = text.replace(marker, "// mix", 1).replace('"../../include/cmcd_b200.h"', f'"{os.path.join(ROOT, "include", "cmcd_b200.h")}"')
+    with tempfile.NamedTemporaryFile("w", suffix=".cc", delete=False) as f:
+        f.write(bad)
+    try:
+        r = subprocess.run(cmd + [f.name], capture_output=True, text=True)
+    finally:
+        os.unlink(f.name)
+    assert r.returncode != 0 and "does not match" in r.stderr
