@@ -19,6 +19,8 @@
 // columns each) alternate so the CUDA cores always have one tile's epilogue / layer 1 to run.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -44,6 +46,11 @@ struct TcCtx {
     uint64_t* mbar;                       // MMA batch complete
     uint64_t* mbar_ready;                 // A operand staged by all 128 threads
     uint32_t parity, parity_ready;
+    // TMA staging of the table rows (a.tab_tma): CTA-shared double buffer, one mbarrier per buffer, phase bit per buffer
+    float* tab_shared;                    // [2][2 * 64]
+    uint64_t* tab_bar;                    // [2]
+    uint32_t tab_parity;                  // bit b = phase of buffer b
+    int tma;
 };
 
 // numpyro Normal.log_prob summed over dims (src/mcd_utils.py:19-21)
@@ -60,7 +67,7 @@ __device__ __forceinline__ float gauss_logprob_tc(const float (&x)[D], const flo
 
 // layer 1 -> TMEM A operand -> issue the MMA batch.  skipacc += a1 W3 (geffner residual), 0 otherwise.
 template <int D, int ACT>
-__device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, const float (&x)[D], float (&skipacc)[D]) {
+__device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, int next_t, const float (&x)[D], float (&skipacc)[D]) {
     constexpr bool skip = (ACT == ACT_SOFTPLUS);
     const float4* __restrict__ c1v = reinterpret_cast<const float4*>(cx.tab);
 #pragma unroll
@@ -115,6 +122,14 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, const float (&
         cx.parity_ready ^= 1u;
         umma::fence_after();
         if (umma::elect_one()) {
+            if (cx.tma && next_t >= 0) {
+                // every thread of the CTA has arrived for node t, i.e. is done with the rows of node t - 1: their buffer is free.
+                // One thread requests both rows of node t + 1 through the TMA engine (two 256-byte bulk copies, one mbarrier).
+                const int b = next_t & 1;
+                umma::mbar_arrive_expect_tx(cx.tab_bar + b, 2 * TC_H * sizeof(float));
+                umma::bulk_copy_g2s(cx.tab_shared + b * (2 * TC_H), cx.c1 + (size_t)next_t * TC_H, TC_H * sizeof(float), cx.tab_bar + b);
+                umma::bulk_copy_g2s(cx.tab_shared + b * (2 * TC_H) + TC_H, cx.c2 + (size_t)next_t * TC_H, TC_H * sizeof(float), cx.tab_bar + b);
+            }
             const uint32_t idesc = umma::make_idesc_tf32(128, TC_H), idesc16 = umma::make_idesc_bf16_k(128, TC_H);
             const uint32_t dcol = cx.tmem_base + TC_COL_D, ahi = cx.tmem_base + TC_COL_AH;
             // D = A_hi B_lo + A_lo B_hi + A_hi B_hi, small terms first: the fp32 accumulator truncates on every accumulate
@@ -192,7 +207,8 @@ template <int D, int ACT>
 __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(const BridgeArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t tmem_slot, tmem_slot_lo;
-    __shared__ __align__(8) uint64_t mbar, mbar_ready;
+    __shared__ __align__(8) uint64_t mbar, mbar_ready, tab_bar[2];
+    __shared__ __align__(128) float tab_shared[2][2 * TC_H];
     const int tid = threadIdx.x, warp = tid >> 5;
     const NetView& nv = a.net;
     uint8_t* sBhi = smem_raw;
@@ -233,7 +249,7 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
         many_gmm_stage_means(a.tgt, sMu, tid, TC_PB);
     const ManyGmmConst gc = many_gmm_const(a.tgt);
     if (warp == 0) { umma::tmem_alloc(&tmem_slot, TC_COLS_MAIN, false); umma::tmem_alloc(&tmem_slot_lo, TC_COLS_LO, true); }
-    if (tid == 0) { umma::mbar_init(&mbar, 1); umma::mbar_init(&mbar_ready, TC_PB); }
+    if (tid == 0) { umma::mbar_init(&mbar, 1); umma::mbar_init(&mbar_ready, TC_PB); umma::mbar_init(&tab_bar[0], 1); umma::mbar_init(&tab_bar[1], 1); }
     umma::fence_async_smem();   // generic-proxy writes of the B tiles -> visible to the tensor core (async proxy)
     umma::fence_before();
     __syncthreads();
@@ -252,6 +268,7 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
     cx.blo = umma::make_desc(umma::smem_u32(sBlo), 128, 32 * TC_H);
     cx.mbar = &mbar; cx.parity = 0u;
     cx.mbar_ready = &mbar_ready; cx.parity_ready = 0u;
+    cx.tab_shared = &tab_shared[0][0]; cx.tab_bar = tab_bar; cx.tab_parity = 0u; cx.tma = a.tab_tma;
 
     const bool cais = (a.mode == CMCD_MODE_CAIS_SN || a.mode == CMCD_MODE_CAIS_VAR_SN);
     const bool nn_b = (a.mode != CMCD_MODE_ULA);
@@ -297,7 +314,16 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
         // step j (mcd_cais.py:60) -- same point, same time index, so the reference's 2K evaluations are K + 1 distinct
         // ones.  MCD_ULA_sn (mcd_over_orig.py:45): NN(z_j, j - 1), backward-kernel mean only.
         const int t0 = cais ? 0 : -1;
-        if (K > 0 && nn_b) stage_tab(0, 0);   // first evaluation: node 0 (CAIS) or node 1 (ULA_sn), t = 0 either way
+        if (K > 0 && nn_b) {                  // first evaluation: node 0 (CAIS) or node 1 (ULA_sn), t = 0 either way
+            if (cx.tma) {
+                __syncthreads();              // the previous tile's last node may still be reading buffer 0 in a lagging warp
+                if (tid == 0) {
+                    umma::mbar_arrive_expect_tx(&tab_bar[0], 2 * TC_H * sizeof(float));
+                    umma::bulk_copy_g2s(&tab_shared[0][0], nv.c1, TC_H * sizeof(float), &tab_bar[0]);
+                    umma::bulk_copy_g2s(&tab_shared[0][TC_H], nv.c2, TC_H * sizeof(float), &tab_bar[0]);
+                }
+            } else stage_tab(0, 0);
+        }
         float x[D], mf[D], nnv[D], skipacc[D];
 #pragma unroll
         for (int j = 0; j < D; ++j) { x[j] = z[j]; mf[j] = 0.f; }
@@ -307,11 +333,18 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
             const bool use_nn = nn_b && (cais || nd > 0) && K > 0;
             if (use_nn) {
                 // table rows of this node were requested one node ago; request the next ones
-                umma::cp_async_wait_all();
-                __syncwarp();
-                cx.tab = sTab + (t & 1) * (2 * TC_H);
-                if (nd < K) stage_tab(t + 1, (t + 1) & 1);
-                tc_net_issue<D, ACT>(cx, t, x, skipacc);
+                if (cx.tma) {
+                    const int b = t & 1;
+                    umma::mbar_wait(&tab_bar[b], (cx.tab_parity >> b) & 1u);
+                    cx.tab_parity ^= 1u << b;
+                    cx.tab = &tab_shared[b][0];
+                } else {
+                    umma::cp_async_wait_all();
+                    __syncwarp();
+                    cx.tab = sTab + (t & 1) * (2 * TC_H);
+                    if (nd < K) stage_tab(t + 1, (t + 1) & 1);
+                }
+                tc_net_issue<D, ACT>(cx, t, nd < K ? t + 1 : -1, x, skipacc);
             }
             // ---- work that does not depend on the network output overlaps the MMA batch ----
             if (fast_gmm) { float d0, d1; lp = many_gmm_eval<false>(gc, sMu, x[0], x[1], sp[0], sp[1], 0.f, 0.f, d0, d1); }
@@ -372,12 +405,16 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
 }
 
 template <int D, int ACT>
-static int launch_fwd_tc_t(const BridgeArgs& a, cudaStream_t st, int num_sms) {
+static int launch_fwd_tc_t(const BridgeArgs& a_in, cudaStream_t st, int num_sms) {
     // request > 227/4 KB so that at most three CTAs (3 x 160 TMEM columns) share an SM
     size_t smem = 2 * TC_B_BYTES + TC_B16_BYTES + (2 * D * TC_H + TC_H * D + D * D + 4 + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 4 * 4 * TC_H + 8) * sizeof(float);
     if (smem < 58 * 1024) smem = 58 * 1024;
     auto kern = bridge_fwd_tc_kernel<D, ACT>;
     CMCD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // TMA bulk copies need 16-byte aligned rows; CMCD_TAB_TMA=0 keeps the per-warp cp.async staging (A/B runs)
+    BridgeArgs a = a_in;
+    const char* env = std::getenv("CMCD_TAB_TMA");
+    a.tab_tma = (!env || env[0] != '0') && !((reinterpret_cast<uintptr_t>(a.net.c1) | reinterpret_cast<uintptr_t>(a.net.c2)) & 15);
     const long long ntiles = (a.N + TC_PB - 1) / TC_PB;
     long long grid = (long long)TC_CTAS_PER_SM * num_sms;
     if (grid > ntiles) grid = ntiles;

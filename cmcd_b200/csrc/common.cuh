@@ -182,6 +182,7 @@ struct BridgeArgs {
     // seed; out_negw then receives +w of the K steps only (no -log q(z0), no log p(z_K)), like mcd_utils.evolve
     const float* z0;
     const uint32_t* keys;
+    int tab_tma;   // tensor-core forward kernel: stage the per-step table rows with TMA bulk copies (1) or per-warp cp.async (0)
 };
 
 // set the thread-local last-error string (capi.cu)

@@ -128,6 +128,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
     }
 }
 
+// TMA bulk copy (cp.async.bulk, non-tensor form): `bytes` (multiple of 16, 16-byte aligned on both sides) global -> shared,
+// completion signalled on `mbar` as transaction bytes; the issuing thread first arms the barrier with expect_tx.
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+
 // true in exactly one lane of a fully converged warp (the lane that issues tcgen05.mma / commit for the CTA)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
