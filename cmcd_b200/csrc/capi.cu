@@ -58,7 +58,7 @@ int launch_target_eval(cudaStream_t st, const TargetDesc& t, int D, const float*
 int launch_ffma_peak(cudaStream_t st, float* scratch, int blocks, int iters);
 int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStream_t st, int num_sms, void* ws, size_t ws_bytes);
 size_t wide_fwd_workspace_bytes(long long N, int d, int HP);
-size_t wide_bwd_workspace_bytes(long long N, int d, int HP);
+size_t wide_bwd_workspace_bytes(long long N, int d, int HP, int K);
 int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStream_t st, int num_sms, const float* cot_negw,
                     float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps, const cmcd_net_grad* g,
                     void* ws, size_t ws_bytes);
@@ -194,7 +194,7 @@ size_t cmcd_bridge_bwd_workspace_bytes(const cmcd_bridge_desc* desc, const cmcd_
     if (is_ud(desc->mode))
         return bridge_ud_bwd_workspace_bytes(desc->mode, desc->dim, desc->nbridges, net ? net->hidden_pad : 0, arch, sms);
     if (desc->dim > 64)   // wide path (lgcp, d = 1600): [N x d] / [N x hidden] state + split-K partials
-        return wide_bwd_workspace_bytes(desc->n_particles, desc->dim, arch != CMCD_ARCH_NONE ? net->hidden_pad : 0);
+        return wide_bwd_workspace_bytes(desc->n_particles, desc->dim, arch != CMCD_ARCH_NONE ? net->hidden_pad : 0, desc->nbridges);
     size_t need = bridge_bwd_workspace_bytes(desc->dim, desc->nbridges, net ? net->hidden_pad : 0, arch, sms);
     if (arch == CMCD_ARCH_DDS && net->hidden_pad == 64 && desc->dim == 2) {
         const size_t tc = bridge_bwd_tc_workspace_bytes(desc->dim, desc->nbridges, sms);
@@ -206,7 +206,7 @@ size_t cmcd_bridge_bwd_workspace_bytes(const cmcd_bridge_desc* desc, const cmcd_
 size_t cmcd_bridge_bwd_workspace_bytes_for_target(const cmcd_bridge_desc* desc, const cmcd_net* net, const cmcd_target* target) {
     if (desc && target && target->kind == CMCD_TARGET_CALLBACK) {   // step-wise path at any dim
         const int arch = (net && mode_uses_net(desc->mode)) ? net->arch : CMCD_ARCH_NONE;
-        return wide_bwd_workspace_bytes(desc->n_particles, desc->dim, arch != CMCD_ARCH_NONE ? net->hidden_pad : 0);
+        return wide_bwd_workspace_bytes(desc->n_particles, desc->dim, arch != CMCD_ARCH_NONE ? net->hidden_pad : 0, desc->nbridges);
     }
     return cmcd_bridge_bwd_workspace_bytes(desc, net);
 }

@@ -261,8 +261,10 @@ static WideGemm plan_gemm(int N, int Kd, int M, int num_sms) {
     S = (Kd + ks - 1) / ks;
     return {S, ks, rows};
 }
+// reduce = false: the consumer is an element-wise kernel spread over the whole GPU (layer finalizers) and sums the S slices
+// itself -- one launch less per product; one-CTA-per-particle consumers get the slices pre-summed (reduce = true).
 static int run_gemm(cudaStream_t st, const float* X, int ldx, float shift, const float* W, int ldw, int N, int Kd, int M,
-                    int num_sms, float* part, int* S_out) {
+                    int num_sms, float* part, int* S_out, bool reduce = true) {
     // large products: tcgen05 tiles (CMCD_DISABLE_WIDE_TC=1 keeps the FP32-FMA kernel for A/B runs)
     if ((long long)Kd * M >= 256LL * 256 && !std::getenv("CMCD_DISABLE_WIDE_TC")) {
         const int nchunks = (Kd + WTC_KC - 1) / WTC_KC;
@@ -276,12 +278,12 @@ static int run_gemm(cudaStream_t st, const float* X, int ldx, float shift, const
         S = (nchunks + cps - 1) / cps;
         skinny_gemm_tc_kernel<<<dim3(ctiles, S, rtiles), 128, 0, st>>>(X, ldx, shift, W, ldw, N, Kd, M, cps, part);
         CMCD_CUDA_OK(cudaGetLastError());
-        if (S > 1) {
+        if (S > 1 && reduce) {
             const int nel = N * M;
             wide_reduce_partials_kernel<<<(nel + 255) / 256, 256, 0, st>>>(part, S, nel);
             CMCD_CUDA_OK(cudaGetLastError());
         }
-        *S_out = 1;
+        *S_out = reduce ? 1 : S;
         return 0;
     }
     const WideGemm g = plan_gemm(N, Kd, M, num_sms);
@@ -290,12 +292,12 @@ static int run_gemm(cudaStream_t st, const float* X, int ldx, float shift, const
     if (g.rows == 24) skinny_gemm_kernel<24><<<grid, WG_THREADS, smem, st>>>(X, ldx, shift, W, ldw, N, Kd, M, g.kslice, part);
     else skinny_gemm_kernel<8><<<grid, WG_THREADS, smem, st>>>(X, ldx, shift, W, ldw, N, Kd, M, g.kslice, part);
     CMCD_CUDA_OK(cudaGetLastError());
-    if (g.S > 1) {
+    if (g.S > 1 && reduce) {
         const int nel = N * M;
         wide_reduce_partials_kernel<<<(nel + 255) / 256, 256, 0, st>>>(part, g.S, nel);
         CMCD_CUDA_OK(cudaGetLastError());
     }
-    *S_out = 1;
+    *S_out = reduce ? 1 : g.S;
     return 0;
 }
 
@@ -476,9 +478,32 @@ __global__ void wide_final_kernel(const float* w, const float* lp, int N, float*
     if (n < N) out_negw[n] = -(w[n] + lp[n]);
 }
 
+// Two independent chains meet at every trajectory point: the target score (dense K^-1 product + finalize) and the drift network
+// (three products + finalizers) -- and, in the reverse pass, the Hessian-vector product and the network pull-back.  Each of their
+// kernels is a short split-K product that cannot fill the GPU by itself for long (launch ramp, 3 chunks per CTA, tail), so the
+// two chains run on two streams and join where the step algebra needs both (fork / join with events: legal under stream
+// capture, so opt.run(graph=True) keeps working).  CMCD_WIDE_SERIAL=1 keeps everything on the caller's stream (A/B runs).
+struct WideAsync {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static WideAsync* wide_async() {
+    constexpr int MAX_DEV = 64;
+    static WideAsync tab[MAX_DEV];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV || std::getenv("CMCD_WIDE_SERIAL")) return nullptr;
+    WideAsync& w = tab[dev];
+    if (!w.side) {
+        if (cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&w.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&w.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return &w;
+}
+
 // workspace layout (floats)
 struct WideWs {
-    size_t z, zn, mf, sp, lp, w, keys, A1, A2, part, total;
+    size_t z, zn, mf, sp, lp, w, keys, A1, A2, part, partT, total;
 };
 static WideWs wide_layout(long long N, int d, int HP) {
     WideWs L;
@@ -489,6 +514,7 @@ static WideWs wide_layout(long long N, int d, int HP) {
     L.A1 = take(N * (size_t)HP); L.A2 = take(N * (size_t)HP);
     const int mx = HP > d ? HP : d;
     L.part = take((size_t)64 * N * mx);
+    L.partT = take((size_t)64 * N * d);     // split-K slices of the target's K^-1 product (runs concurrently with the network's)
     L.total = o;
     return L;
 }
@@ -506,8 +532,11 @@ int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
     if (!ws || ws_bytes < L.total * sizeof(float)) { set_error("wide_fwd: workspace too small (%zu < %zu)", ws_bytes, L.total * sizeof(float)); return 2; }
     float* f = (float*)ws;
     float *z = f + L.z, *zn = f + L.zn, *mf = f + L.mf, *sp = f + L.sp, *lp = f + L.lp, *w = f + L.w;
-    float *A1 = f + L.A1, *A2 = f + L.A2, *part = f + L.part;
+    float *A1 = f + L.A1, *A2 = f + L.A2, *part = f + L.part, *partT = f + L.partT;
     uint32_t* keys = (uint32_t*)(f + L.keys);
+    WideAsync* as = (tg->kind == CMCD_TARGET_CALLBACK) ? nullptr : wide_async();   // callbacks run on the caller's stream
+    cudaStream_t st_t = as ? as->side : st;                                          // stream of the target chain
+    int ST = 1;
     const bool cais = (a.mode == CMCD_MODE_CAIS_SN || a.mode == CMCD_MODE_CAIS_VAR_SN);
     const bool nn_b = (a.mode != CMCD_MODE_ULA) && has_net, nn_f = cais && has_net;
     const float skip = 1.f;
@@ -520,30 +549,37 @@ int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
             if (int rc = tg->eval(tg->user, (void*)st, x, (int64_t)N, d, nullptr, lp, sp, nullptr)) { set_error("target callback failed (rc=%d)", rc); return 3; }
             return 0;
         }
-        if (int rc = run_gemm(st, x, d, tg->lgcp_mu0, tg->lgcp_kinv, d, (int)N, d, d, num_sms, part, &S)) return rc;
-        wide_target_fin_kernel<<<(unsigned)N, 256, 0, st>>>(part, S, (int)N, d, x, tg->lgcp_counts, tg->lgcp_mu0,
-                                                            tg->lgcp_log_norm, tg->lgcp_bin_area, sp, lp);
+        if (as) { CMCD_CUDA_OK(cudaEventRecord(as->fork, st)); CMCD_CUDA_OK(cudaStreamWaitEvent(as->side, as->fork, 0)); }
+        if (int rc = run_gemm(st_t, x, d, tg->lgcp_mu0, tg->lgcp_kinv, d, (int)N, d, d, num_sms, partT, &ST)) return rc;
+        wide_target_fin_kernel<<<(unsigned)N, 256, 0, st_t>>>(partT, ST, (int)N, d, x, tg->lgcp_counts, tg->lgcp_mu0,
+                                                              tg->lgcp_log_norm, tg->lgcp_bin_area, sp, lp);
         CMCD_CUDA_OK(cudaGetLastError());
+        if (as) CMCD_CUDA_OK(cudaEventRecord(as->join, as->side));
+        return 0;
+    };
+    auto target_join = [&]() -> int {             // the caller's stream waits for the target chain
+        if (as) CMCD_CUDA_OK(cudaStreamWaitEvent(st, as->join, 0));
         return 0;
     };
     // NN(x, t) up to the layer-3 split-K partials (left in `part`, S3 slices)
     auto net_at = [&](const float* x, int t, int* S3) -> int {
         const int nel = (int)N * HP, blk = (nel + 255) / 256;
-        if (int rc = run_gemm(st, x, d, 0.f, nv.U1, HP, (int)N, d, HP, num_sms, part, &S)) return rc;
+        if (int rc = run_gemm(st, x, d, 0.f, nv.U1, HP, (int)N, d, HP, num_sms, part, &S, false)) return rc;
         wide_l1_fin_kernel<<<blk, 256, 0, st>>>(part, S, (int)N, HP, d, nv.c1 + (size_t)t * HP, x, 1, nullptr, A1);
         CMCD_CUDA_OK(cudaGetLastError());
-        if (int rc = run_gemm(st, A1, HP, 0.f, nv.W2, HP, (int)N, HP, HP, num_sms, part, &S)) return rc;
+        if (int rc = run_gemm(st, A1, HP, 0.f, nv.W2, HP, (int)N, HP, HP, num_sms, part, &S, false)) return rc;
         wide_l2_fin_kernel<<<blk, 256, 0, st>>>(part, S, (int)N, HP, nv.c2 + (size_t)t * HP, A1, skip, nullptr, A2);
         CMCD_CUDA_OK(cudaGetLastError());
         if (int rc = run_gemm(st, A2, HP, 0.f, nv.W3, d, (int)N, HP, d, num_sms, part, S3)) return rc;
         return 0;
     };
-    if (int rc = target_at(z)) return rc;
+    if (int rc = target_at(z)) return rc;         // (side stream) ...
     // One network evaluation per trajectory point: in the CAIS modes NN(z', i + 1) of step i's backward-kernel mean
     // (mcd_cais.py:78) is the evaluation step i + 1's forward-kernel mean needs (mcd_cais.py:60); its layer-3 partials stay
     // in `part` between wide_bwd_mean_kernel and the next wide_fwd_mean_kernel, so K + 1 evaluations serve 2K uses.
     int S3 = 1;
-    if (nn_f && K > 0) { if (int rc = net_at(z, 0, &S3)) return rc; }
+    if (nn_f && K > 0) { if (int rc = net_at(z, 0, &S3)) return rc; }   // ... while the network runs on the caller's stream
+    if (int rc = target_join()) return rc;
     for (int i = 0; i < K; ++i) {
         wide_fwd_mean_kernel<<<(unsigned)N, 256, 0, st>>>(part, S3, (int)N, d, has_net ? nv.c3 + (size_t)i * d : nullptr,
                                                           nv.out_scale, nv.out_scale_dev, nv.out_clip, nn_f ? 1 : 0, z, sp, a.vd_mean, a.vd_logdiag,
@@ -553,6 +589,7 @@ int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
         if (int rc = target_at(zn)) return rc;   // sp <- score at z' (reused as the next step's forward score)
         const int tb = cais ? i + 1 : i;
         if (nn_b) { if (int rc = net_at(zn, tb, &S3)) return rc; }
+        if (int rc = target_join()) return rc;
         wide_bwd_mean_kernel<<<(unsigned)N, 256, 0, st>>>(part, S3, (int)N, d, has_net ? nv.c3 + (size_t)tb * d : nullptr,
                                                           nv.out_scale, nv.out_scale_dev, nv.out_clip, nn_b ? 1 : 0, z, zn, mf, sp, a.vd_mean,
                                                           a.vd_logdiag, a.betas, a.eps, i, a.clip_t, a.clip_q, w);
@@ -736,6 +773,54 @@ __global__ void __launch_bounds__(128) wide_outer_acc_kernel(const float* __rest
 }
 
 // g[j] += sum_n V[n][j]
+// G[i][j] = sum_r A[r][i] B[r][j] over R stacked rows (all particles of all trajectory points): the weight cotangents of one
+// whole reverse pass as ONE product per layer instead of a rank-N read-modify-write of the 10 MB gradient per point.
+// 64 x 64 output tile per CTA, 4 x 4 per thread, 16-row slabs of A and B staged in shared memory.  Overwrites G.
+constexpr int WGR_T = 64, WGR_K = 16;
+__global__ void __launch_bounds__(256) wide_wgrad_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int R,
+                                                         int I, int J, float* __restrict__ G, int ldg) {
+    __shared__ float As[WGR_K][WGR_T + 4], Bs[WGR_K][WGR_T + 4];
+    const int i0 = blockIdx.y * WGR_T, j0 = blockIdx.x * WGR_T, tid = threadIdx.x;
+    const int ti = (tid / 16) * 4, tj = (tid % 16) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int r0 = 0; r0 < R; r0 += WGR_K) {
+        for (int e = tid; e < WGR_K * WGR_T; e += 256) {
+            const int r = e / WGR_T, c = e % WGR_T;
+            const bool rv = r0 + r < R;
+            As[r][c] = (rv && i0 + c < I) ? A[(size_t)(r0 + r) * lda + i0 + c] : 0.f;
+            Bs[r][c] = (rv && j0 + c < J) ? B[(size_t)(r0 + r) * ldb + j0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < WGR_K; ++r) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[r][ti]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[r][tj]);
+            const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], b4[b], acc[a][b]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (i0 + ti + a < I && j0 + tj + b < J) G[(size_t)(i0 + ti + a) * ldg + j0 + tj + b] = acc[a][b];
+}
+// g[t][j] = sum_n V[t][n][j] for the stacked per-point buffers (per-step bias-table cotangents); grid (J / 256, points)
+__global__ void wide_colsum_rows_kernel(const float* __restrict__ V, int ldv, int N, int J, float* __restrict__ g, int ldg) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+    if (j >= J) return;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += V[((size_t)t * N + n) * ldv + j];
+    g[(size_t)t * ldg + j] = s;
+}
 __global__ void wide_colsum_acc_kernel(const float* __restrict__ V, int ldv, int N, int J, float* __restrict__ g) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= J) return;
@@ -879,9 +964,12 @@ __global__ void wide_vd_final_kernel(const float* __restrict__ gmu_acc, const fl
 }
 
 struct WideBwdWs {
-    size_t zp, z, spp, sp, adj, abar, G, vo, vm, r, dx, gmu, gls, lp, c, A1, A2, s1, s2, dA, dp, part, total;
+    size_t zp, z, spp, sp, adj, abar, G, vo, vm, r, dx, gmu, gls, lp, c, A1, A2, s1, s2, dA, dp, part, partT, total;
+    // per-point stacks [T][N][.] kept for the end-of-pass weight-gradient products: network input x, A1, A2, output cotangent
+    // vo, dp2, dp1; dA1 = scratch for the layer-1 cotangent
+    size_t Xs, A1s, A2s, VOs, DPs, DP1s, dA1;
 };
-static WideBwdWs wide_bwd_layout(long long N, int d, int HP) {
+static WideBwdWs wide_bwd_layout(long long N, int d, int HP, int T = 0) {
     WideBwdWs L;
     size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
@@ -892,10 +980,17 @@ static WideBwdWs wide_bwd_layout(long long N, int d, int HP) {
     L.A1 = take(nh); L.A2 = take(nh); L.s1 = take(nh); L.s2 = take(nh); L.dA = take(nh); L.dp = take(nh);
     const int mx = HP > d ? HP : d;
     L.part = take((size_t)64 * N * mx);
+    L.partT = take((size_t)64 * N * d);     // K^-1 products (score, Hessian-vector product) on the side stream
+    L.Xs = L.A1s = L.A2s = L.VOs = L.DPs = L.DP1s = L.dA1 = 0;
+    if (T > 0) {
+        L.Xs = take((size_t)T * nd); L.VOs = take((size_t)T * nd);
+        L.A1s = take((size_t)T * nh); L.A2s = take((size_t)T * nh); L.DPs = take((size_t)T * nh); L.DP1s = take((size_t)T * nh);
+        L.dA1 = take(nh);
+    }
     L.total = o;
     return L;
 }
-size_t wide_bwd_workspace_bytes(long long N, int d, int HP) { return wide_bwd_layout(N, d, HP > 0 ? HP : 8).total * sizeof(float); }
+size_t wide_bwd_workspace_bytes(long long N, int d, int HP, int K) { return wide_bwd_layout(N, d, HP > 0 ? HP : 8, HP > 0 ? K + 1 : 0).total * sizeof(float); }
 
 int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStream_t st, int num_sms, const float* cot_negw,
                     float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps, const cmcd_net_grad* g,
@@ -907,13 +1002,17 @@ int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
     const int HP = has_net ? nv.HP : 8;
     if (has_net && nv.arch != CMCD_ARCH_GEFFNER) { set_error("wide path (lgcp / callback targets): only nn_arch=geffner is implemented (README.md:63 config)"); return 2; }
     if (HP & 3) { set_error("wide path: hidden_pad must be a multiple of 4"); return 2; }
-    const WideBwdWs L = wide_bwd_layout(N, d, HP);
+    const WideBwdWs L = wide_bwd_layout(N, d, HP, has_net ? K + 1 : 0);
     if (!ws || ws_bytes < L.total * sizeof(float)) { set_error("wide_bwd: workspace too small (%zu < %zu)", ws_bytes, L.total * sizeof(float)); return 2; }
     float* f = (float*)ws;
     float *zp = f + L.zp, *z = f + L.z, *spp = f + L.spp, *sp = f + L.sp, *adj = f + L.adj, *abar = f + L.abar;
     float *G = f + L.G, *vo = f + L.vo, *vm = f + L.vm, *r = f + L.r, *dx = f + L.dx, *gmu = f + L.gmu, *gls = f + L.gls;
     float *lp = f + L.lp, *c = f + L.c, *A1 = f + L.A1, *A2 = f + L.A2, *s1 = f + L.s1, *s2 = f + L.s2, *dA = f + L.dA, *dp = f + L.dp;
-    float* part = f + L.part;
+    float *part = f + L.part, *partT = f + L.partT;
+    float *Xs = f + L.Xs, *A1s = f + L.A1s, *A2s = f + L.A2s, *VOs = f + L.VOs, *DPs = f + L.DPs, *DP1s = f + L.DP1s, *dA1 = f + L.dA1;
+    WideAsync* as = (tg->kind == CMCD_TARGET_CALLBACK) ? nullptr : wide_async();
+    cudaStream_t st_t = as ? as->side : st;
+    int ST = 1;
     const bool cais = (a.mode == CMCD_MODE_CAIS_SN || a.mode == CMCD_MODE_CAIS_VAR_SN);
     const bool pathwise = a.mode != CMCD_MODE_CAIS_VAR_SN;
     const bool nn_b = (a.mode != CMCD_MODE_ULA) && has_net, nn_f = cais && has_net;
@@ -931,9 +1030,7 @@ int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
     if (g && has_net) {
         gU1 = g->U1; gW2 = g->W2; gW3 = g->W3; gc1 = g->c1; gc2 = g->c2; gc3 = g->c3; gos = g->out_scale;
         if (!gU1 || !gW2 || !gW3 || !gc1 || !gc2 || !gc3 || !gos) { set_error("wide_bwd: every network cotangent buffer is required"); return 2; }
-        CMCD_CUDA_OK(cudaMemsetAsync(gU1, 0, (size_t)d * HP * sizeof(float), st));
-        CMCD_CUDA_OK(cudaMemsetAsync(gW2, 0, (size_t)HP * HP * sizeof(float), st));
-        CMCD_CUDA_OK(cudaMemsetAsync(gW3, 0, (size_t)HP * d * sizeof(float), st));
+        // gU1 / gW2 / gW3 are overwritten by the end-of-pass products; the bias tables get every row a point used and zeros elsewhere
         CMCD_CUDA_OK(cudaMemsetAsync(gc1, 0, (size_t)T * HP * sizeof(float), st));
         CMCD_CUDA_OK(cudaMemsetAsync(gc2, 0, (size_t)T * HP * sizeof(float), st));
         CMCD_CUDA_OK(cudaMemsetAsync(gc3, 0, (size_t)T * d * sizeof(float), st));
@@ -947,87 +1044,126 @@ int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
 
     auto ew = [&](int n) { return dim3((unsigned)((n + 255) / 256)); };
     const bool generic = tg->kind == CMCD_TARGET_CALLBACK;
-    auto target_at = [&](const float* x, float* score) -> int {
+    auto fork = [&]() -> int {       // the side stream picks up after everything enqueued on the caller's stream so far
+        if (as) { CMCD_CUDA_OK(cudaEventRecord(as->fork, st)); CMCD_CUDA_OK(cudaStreamWaitEvent(as->side, as->fork, 0)); }
+        return 0;
+    };
+    auto join = [&]() -> int {       // the caller's stream waits for the side chain
+        if (as) { CMCD_CUDA_OK(cudaEventRecord(as->join, as->side)); CMCD_CUDA_OK(cudaStreamWaitEvent(st, as->join, 0)); }
+        return 0;
+    };
+    auto target_at = [&](const float* x, float* score) -> int {     // on the side stream (between fork and join)
         if (generic) {
             if (int rc = tg->eval(tg->user, (void*)st, x, (int64_t)N, d, nullptr, lp, score, nullptr)) { set_error("target callback failed (rc=%d)", rc); return 3; }
             return 0;
         }
-        if (int rc = run_gemm(st, x, d, tg->lgcp_mu0, tg->lgcp_kinv, d, (int)N, d, d, num_sms, part, &S)) return rc;
-        wide_target_fin_kernel<<<(unsigned)N, 256, 0, st>>>(part, S, (int)N, d, x, tg->lgcp_counts, tg->lgcp_mu0,
-                                                            tg->lgcp_log_norm, tg->lgcp_bin_area, score, lp);
+        if (int rc = run_gemm(st_t, x, d, tg->lgcp_mu0, tg->lgcp_kinv, d, (int)N, d, d, num_sms, partT, &ST)) return rc;
+        wide_target_fin_kernel<<<(unsigned)N, 256, 0, st_t>>>(partT, ST, (int)N, d, x, tg->lgcp_counts, tg->lgcp_mu0,
+                                                              tg->lgcp_log_norm, tg->lgcp_bin_area, score, lp);
         CMCD_CUDA_OK(cudaGetLastError());
         return 0;
     };
-    auto net_fwd_store = [&](const float* x, int t, int* S3) -> int {
+    // point j keeps its network input and activations in slice j of the stacks (A1 = A1s + j nh, ...)
+    auto net_fwd_store = [&](const float* x, int t, int j, int* S3) -> int {
         const int blk = (nh + 255) / 256;
-        if (int rc = run_gemm(st, x, d, 0.f, nv.U1, HP, (int)N, d, HP, num_sms, part, &S)) return rc;
-        wide_l1_fin_kernel<<<blk, 256, 0, st>>>(part, S, (int)N, HP, d, nv.c1 + (size_t)t * HP, x, 1, s1, A1);
+        float *A1j = A1s + (size_t)j * nh, *A2j = A2s + (size_t)j * nh;
+        if (int rc = run_gemm(st, x, d, 0.f, nv.U1, HP, (int)N, d, HP, num_sms, part, &S, false)) return rc;
+        wide_l1_fin_kernel<<<blk, 256, 0, st>>>(part, S, (int)N, HP, d, nv.c1 + (size_t)t * HP, x, 1, s1, A1j);
         CMCD_CUDA_OK(cudaGetLastError());
-        if (int rc = run_gemm(st, A1, HP, 0.f, nv.W2, HP, (int)N, HP, HP, num_sms, part, &S)) return rc;
-        wide_l2_fin_kernel<<<blk, 256, 0, st>>>(part, S, (int)N, HP, nv.c2 + (size_t)t * HP, A1, 1.f, s2, A2);
+        if (int rc = run_gemm(st, A1j, HP, 0.f, nv.W2, HP, (int)N, HP, HP, num_sms, part, &S, false)) return rc;
+        wide_l2_fin_kernel<<<blk, 256, 0, st>>>(part, S, (int)N, HP, nv.c2 + (size_t)t * HP, A1j, 1.f, s2, A2j);
         CMCD_CUDA_OK(cudaGetLastError());
-        return run_gemm(st, A2, HP, 0.f, nv.W3, d, (int)N, HP, d, num_sms, part, S3);
+        return run_gemm(st, A2j, HP, 0.f, nv.W3, d, (int)N, HP, d, num_sms, part, S3);
     };
-    // network VJP for cotangent vo on the raw output at (x, t): parameter cotangents accumulate, dx -> `dx`
-    auto net_bwd = [&](const float* x, int t) -> int {
+    // network VJP for cotangent vo (slice j of VOs) on the raw output at point j: dx -> `dx`; the factors of the parameter
+    // cotangents (dp2, dp1 next to x, A1, A2, vo) stay in their slices for the end-of-pass products
+    auto net_bwd = [&](int j) -> int {
+        float *voj = VOs + (size_t)j * nd, *dpj = DPs + (size_t)j * nh, *dp1j = DP1s + (size_t)j * nh;
         // dA2 = vo W3^T ; dp2 = dA2 * softplus'(pre2)
-        if (int rc = run_gemm_t(st, num_sms, vo, d, nv.W3, d, (int)N, HP, d, nullptr, 0, s2, HP, dA, dp, HP)) return rc;
-        wide_outer_acc_kernel<<<dim3(((d + 3) / 4 + 127) / 128, HP), 128, 0, st>>>(A2, HP, vo, d, (int)N, HP, d, gW3, d);
-        wide_colsum_acc_kernel<<<ew(d), 256, 0, st>>>(vo, d, (int)N, d, gc3 + (size_t)t * d);
-        wide_outer_acc_kernel<<<dim3((HP / 4 + 127) / 128, HP), 128, 0, st>>>(A1, HP, dp, HP, (int)N, HP, HP, gW2, HP);
-        wide_colsum_acc_kernel<<<ew(HP), 256, 0, st>>>(dp, HP, (int)N, HP, gc2 + (size_t)t * HP);
-        CMCD_CUDA_OK(cudaGetLastError());
-        // dA1 = dA2 + dp2 W2^T ; dp1 = dA1 * softplus'(pre1)     (in place: dA <- dA1, dp <- dp1 after the products above)
-        if (int rc = run_gemm_t(st, num_sms, dp, HP, nv.W2, HP, (int)N, HP, HP, dA, HP, s1, HP, A2, s2, HP)) return rc;   // A2 <- dA1, s2 <- dp1 (both dead)
-        wide_outer_acc_kernel<<<dim3((HP / 4 + 127) / 128, d), 128, 0, st>>>(x, d, s2, HP, (int)N, d, HP, gU1, HP);
-        wide_colsum_acc_kernel<<<ew(HP), 256, 0, st>>>(s2, HP, (int)N, HP, gc1 + (size_t)t * HP);
+        if (int rc = run_gemm_t(st, num_sms, voj, d, nv.W3, d, (int)N, HP, d, nullptr, 0, s2, HP, dA, dpj, HP)) return rc;
+        // dA1 = dA2 + dp2 W2^T ; dp1 = dA1 * softplus'(pre1)
+        if (int rc = run_gemm_t(st, num_sms, dpj, HP, nv.W2, HP, (int)N, HP, HP, dA, HP, s1, HP, dA1, dp1j, HP)) return rc;
         // dx = dA1[:, :d] + dp1 U1^T
-        if (int rc = run_gemm_t(st, num_sms, s2, HP, nv.U1, HP, (int)N, d, HP, A2, HP, nullptr, 0, dx, nullptr, d)) return rc;
+        if (int rc = run_gemm_t(st, num_sms, dp1j, HP, nv.U1, HP, (int)N, d, HP, dA1, HP, nullptr, 0, dx, nullptr, d)) return rc;
         return 0;
     };
 
     wide_neg_kernel<<<ew((int)N), 256, 0, st>>>(cot_negw, (int)N, c);
-    // three rotating trajectory rows: zup = z_{j+1}, x = z_j, zprev = z_{j-1}; `abar` holds the carried cotangent, `G` the base
-    float *zup = zp, *x = z, *zprev = spp;
-    wide_gather_kernel<<<ew(nd), 256, 0, st>>>(a.traj + (size_t)K * d * N, (int)N, d, x);
+    // trajectory rows z_j in particle-major form: with a network every point keeps its row in slice j of Xs (the end-of-pass
+    // weight-gradient products read them again); without one three rotating buffers do.  `abar` holds the carried cotangent.
+    float* rot[3] = {zp, z, spp};
+    auto row = [&](int j) -> float* { return has_net ? Xs + (size_t)j * nd : rot[((j % 3) + 3) % 3]; };
+    wide_gather_kernel<<<ew(nd), 256, 0, st>>>(a.traj + (size_t)K * d * N, (int)N, d, row(K));
     CMCD_CUDA_OK(cudaGetLastError());
     CMCD_CUDA_OK(cudaMemsetAsync(r, 0, (size_t)nd * sizeof(float), st));
     CMCD_CUDA_OK(cudaMemsetAsync(abar, 0, (size_t)nd * sizeof(float), st));
     const int t0 = cais ? 0 : -1;   // table row of node j: t0 + j  (MCD_ULA_sn: NN(z_j, j-1), mcd_over_orig.py:45)
+    float* x = row(K);
     for (int j = K; j >= 0; --j) {
         const bool hasB = j > 0;
         const int t = t0 + j;
         const bool use_nn = has_net && K > 0 && (cais || (nn_b && hasB));
+        x = row(j);
+        float *zprev = row(j - 1 >= 0 ? j - 1 : j), *zup = row(j + 1 <= K ? j + 1 : j);   // (absent neighbours are never read)
+        float* voj = use_nn ? VOs + (size_t)j * nd : vo;
         if (hasB) {
             wide_gather_kernel<<<ew(nd), 256, 0, st>>>(a.traj + (size_t)(j - 1) * d * N, (int)N, d, zprev);
             CMCD_CUDA_OK(cudaGetLastError());
         }
         int S3 = 1;
-        if (int rc = target_at(x, sp)) return rc;
-        if (use_nn) { if (int rc = net_fwd_store(x, t, &S3)) return rc; }
+        if (int rc = fork()) return rc;
+        if (int rc = target_at(x, sp)) return rc;                              // side stream: score at x
+        if (use_nn) { if (int rc = net_fwd_store(x, t, j, &S3)) return rc; }   // caller's stream: network recompute
+        if (int rc = join()) return rc;
         WideNodeArgs h{};
         h.part3 = part; h.c3t = use_nn ? nv.c3 + (size_t)t * d : nullptr; h.x = x; h.sx = sp; h.zprev = zprev; h.zup = zup; h.carry = abar;
         h.c = c; h.mu = a.vd_mean; h.logdiag = a.vd_logdiag; h.betas = a.betas; h.epss = a.eps;
-        h.base = G; h.vo = vo; h.vm = vm; h.r = r; h.gmu_acc = gmu; h.gls_acc = gls; h.g_beta = gbeta_buf; h.g_eps = geps_buf; h.g_os = gos;
+        h.base = G; h.vo = voj; h.vm = vm; h.r = r; h.gmu_acc = gmu; h.gls_acc = gls; h.g_beta = gbeta_buf; h.g_eps = geps_buf; h.g_os = gos;
         h.S3 = S3; h.N = (int)N; h.d = d; h.j = j; h.K = K; h.pathwise = pathwise; h.use_nn = use_nn; h.nn_f = nn_f;
         h.out_scale = nv.out_scale; h.out_scale_dev = nv.out_scale_dev; h.out_clip = nv.out_clip; h.clip_t = a.clip_t; h.clip_q = a.clip_q;
         wide_node_kernel<<<(unsigned)N, 256, 0, st>>>(h);
         CMCD_CUDA_OK(cudaGetLastError());
-        if (use_nn) { if (int rc = net_bwd(x, t)) return rc; }
+        // the Hessian-vector product K^-1 vm (side stream) overlaps the network pull-back (caller's stream)
+        if (pathwise && !generic) {
+            if (int rc = fork()) return rc;
+            if (int rc = run_gemm(st_t, vm, d, 0.f, tg->lgcp_kinv, d, (int)N, d, d, num_sms, partT, &ST)) return rc;
+        }
+        if (use_nn) { if (int rc = net_bwd(j)) return rc; }
         if (pathwise) {
             if (generic) {   // H(x) vm from the caller's batched Hessian-vector product
-                if (int rc = tg->eval(tg->user, (void*)st, x, (int64_t)N, d, vm, nullptr, nullptr, part)) { set_error("target callback failed (rc=%d)", rc); return 3; }
-                S = 1;
-            } else if (int rc = run_gemm(st, vm, d, 0.f, tg->lgcp_kinv, d, (int)N, d, d, num_sms, part, &S)) return rc;
+                if (int rc = tg->eval(tg->user, (void*)st, x, (int64_t)N, d, vm, nullptr, nullptr, partT)) { set_error("target callback failed (rc=%d)", rc); return 3; }
+                ST = 1;
+            } else if (int rc = join()) return rc;
             WideNodeCombineArgs cb{};
-            cb.kpart = part; cb.x = x; cb.base = G; cb.vm = vm; cb.dxnet = dx; cb.out = abar;
-            cb.S = S; cb.N = (int)N; cb.d = d; cb.use_nn = use_nn; cb.area = tg->lgcp_bin_area; cb.generic = generic ? 1 : 0;
+            cb.kpart = partT; cb.x = x; cb.base = G; cb.vm = vm; cb.dxnet = dx; cb.out = abar;
+            cb.S = ST; cb.N = (int)N; cb.d = d; cb.use_nn = use_nn; cb.area = tg->lgcp_bin_area; cb.generic = generic ? 1 : 0;
             wide_node_combine_kernel<<<ew(nd), 256, 0, st>>>(cb);
             CMCD_CUDA_OK(cudaGetLastError());
         }
-        if (hasB) { float* tmp = zup; zup = x; x = zprev; zprev = tmp; }
     }
-    adj = abar; zp = x;   // after node 0: carried cotangent = dL/dz_0, x = z_0
+    // end of pass: the weight cotangents as one product per layer over all points' stacked factors, the per-step bias tables as
+    // column sums of the same stacks
+    if (g && has_net) {
+        const bool any_nn = K > 0 && (cais || nn_b);
+        if (any_nn) {
+            const int j_lo = cais ? 0 : 1, P = K + 1 - j_lo, R = P * (int)N;
+            const float *A2p = A2s + (size_t)j_lo * nh, *A1p = A1s + (size_t)j_lo * nh, *VOp = VOs + (size_t)j_lo * nd;
+            const float *DPp = DPs + (size_t)j_lo * nh, *DP1p = DP1s + (size_t)j_lo * nh, *Xp = Xs + (size_t)j_lo * nd;
+            auto tiles = [](int n) { return (unsigned)((n + WGR_T - 1) / WGR_T); };
+            wide_wgrad_kernel<<<dim3(tiles(d), tiles(HP)), 256, 0, st>>>(A2p, HP, VOp, d, R, HP, d, gW3, d);
+            wide_wgrad_kernel<<<dim3(tiles(HP), tiles(HP)), 256, 0, st>>>(A1p, HP, DPp, HP, R, HP, HP, gW2, HP);
+            wide_wgrad_kernel<<<dim3(tiles(HP), tiles(d)), 256, 0, st>>>(Xp, d, DP1p, HP, R, d, HP, gU1, HP);
+            wide_colsum_rows_kernel<<<dim3((unsigned)((d + 255) / 256), P), 256, 0, st>>>(VOp, d, (int)N, d, gc3, d);      // rows t0 + j_lo = 0 ...
+            wide_colsum_rows_kernel<<<dim3((unsigned)((HP + 255) / 256), P), 256, 0, st>>>(DPp, HP, (int)N, HP, gc2, HP);
+            wide_colsum_rows_kernel<<<dim3((unsigned)((HP + 255) / 256), P), 256, 0, st>>>(DP1p, HP, (int)N, HP, gc1, HP);
+            CMCD_CUDA_OK(cudaGetLastError());
+        } else {
+            CMCD_CUDA_OK(cudaMemsetAsync(gU1, 0, (size_t)d * HP * sizeof(float), st));
+            CMCD_CUDA_OK(cudaMemsetAsync(gW2, 0, (size_t)HP * HP * sizeof(float), st));
+            CMCD_CUDA_OK(cudaMemsetAsync(gW3, 0, (size_t)HP * d * sizeof(float), st));
+        }
+    }
+    adj = abar; zp = row(0);   // after node 0: carried cotangent = dL/dz_0, row(0) = z_0
     wide_vd_final_kernel<<<ew(d), 256, 0, st>>>(gmu, gls, adj, zp, c, a.vd_mean, (int)N, d, pathwise ? 1 : 0, g_vd_mean, g_vd_logdiag);
     CMCD_CUDA_OK(cudaGetLastError());
     return 0;
