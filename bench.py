@@ -51,9 +51,9 @@ FLOP_TRAIN = 105.0e3
 FLOP_FWD_EXECUTED = 17.5e3
 FLOP_BWD_EXECUTED = 52.0e3
 
-# ncu --set full capture of bridge_bwd_tc_kernel at N=131072, K=256 (profiles/r1_ncu_summary.md, fifth capture r1g):
-# dram__bytes_read.sum 332.3 MB + dram__bytes_write.sum 55.1 MB per launch
-NCU_BWD_DRAM_BYTES_PER_PARTICLE = (332.265984e6 + 55.141632e6) / 131072
+# ncu --set full capture of bridge_bwd_tc_kernel at N=131072, K=256 (profiles/r2_ncu_summary.md, capture r2; refreshed after the
+# round-2 kernel changes): dram__bytes_read.sum 304.9 MB + dram__bytes_write.sum 30.0 MB per launch
+NCU_BWD_DRAM_BYTES_PER_PARTICLE = (304.876288e6 + 30.016512e6) / 131072
 
 
 def _tensor_peak():

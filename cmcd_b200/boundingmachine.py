@@ -16,25 +16,26 @@ from .pytree import ravel_pytree, tree_map
 
 def initialize(dim, vdparams=None, nbridges=0, lfsteps=1, eps=0.0, eta=0.5, mdparams=None, ngridb=32,
                mgridref_y=None, trainable=("eps", "eta"), init_sigma=1.0, device="cuda"):
-    """boundingmachine.py:9-70.  (nbridges = 0 keeps the pytree of the MFVI path: vd, eps, eta only.)"""
+    """boundingmachine.py:9-70: the same pytree for every nbridges, including the MFVI machine (nbridges = 0: ngridb = 0, so
+    mgridref_y = ones(1), gridref_x = linspace(0, 1, 2), target_x = empty, md = zeros(dim)) -- flat vectors and checkpoints are
+    interchangeable with the reference's."""
     dev = torch.device(device)
     pt, pn = {}, {}
     vdp = vdparams if vdparams is not None else vd.initialize(dim, init_sigma=init_sigma, device=dev)
     (pt if "vd" in trainable else pn)["vd"] = tree_map(lambda t: t.to(dev), vdp)
     for name, val in (("eps", eps), ("eta", eta)):
         (pt if name in trainable else pn)[name] = torch.tensor(float(val), device=dev)
-    if nbridges >= 1:
-        md = mdparams.to(dev) if mdparams is not None else torch.zeros(dim, device=dev)   # momdist.py:9-11
-        (pt if "md" in trainable else pn)["md"] = md
-        if mgridref_y is not None:
-            ngridb = mgridref_y.shape[0] - 1
-            mgridref_y = mgridref_y.to(dev)
-        else:
-            ngridb = min(ngridb, nbridges)
-            mgridref_y = torch.ones(ngridb + 1, device=dev)
-        pn["gridref_x"] = torch.linspace(0, 1, ngridb + 2, device=dev)
-        pn["target_x"] = torch.linspace(0, 1, nbridges + 2, device=dev)[1:-1]
-        (pt if "mgridref_y" in trainable else pn)["mgridref_y"] = mgridref_y
+    md = mdparams.to(dev) if mdparams is not None else torch.zeros(dim, device=dev)   # momdist.py:9-11
+    (pt if "md" in trainable else pn)["md"] = md
+    if mgridref_y is not None:
+        ngridb = mgridref_y.shape[0] - 1
+        mgridref_y = mgridref_y.to(dev)
+    else:
+        ngridb = min(ngridb, nbridges)
+        mgridref_y = torch.ones(ngridb + 1, device=dev)
+    pn["gridref_x"] = torch.linspace(0, 1, ngridb + 2, device=dev)
+    pn["target_x"] = torch.linspace(0, 1, nbridges + 2, device=dev)[1:-1]
+    (pt if "mgridref_y" in trainable else pn)["mgridref_y"] = mgridref_y
     params_flat, unflatten = ravel_pytree((pt, pn), device=dev)
     return params_flat, unflatten, (dim, nbridges, lfsteps)
 

@@ -200,10 +200,14 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
     float* sf = reinterpret_cast<float*>(smem + BT_OFF_SMALL);
     float* sU1 = sf;                        // [D][64]
     float* sW3 = sU1 + D * BT_H;            // [D][64]: W3 TRANSPOSED (row m = output dim), so that pairs of hidden units are packed operands
-    float* sAccU1 = sW3 + BT_H * D;         // [D][64]  gradient accumulators shared by both tiles
-    float* sAccW3 = sAccU1 + D * BT_H;      // [64][D]
-    float* sAccC2 = sAccW3 + BT_H * D;      // [64]  (dds: c2 = st2.b and c3 = out.b are the same row for every step, so their cotangents
-    float* sAccC3 = sAccC2 + BT_H;          // [D]    are accumulated over the steps here and reported in table row 0; [D + 1] = out_scale)
+    // step-independent skinny gradients (U1, W3, and -- dds: c2 = st2.b, c3 = out.b are the same row for every step -- c2, c3):
+    // one PRIVATE accumulator block per warp, [c2 64 | W3 64 x D | U1 D x 64]: after a reduction the 16 lanes with bit 2 clear hold
+    // 16 distinct hidden units, so plain load-add-store suffices (ATOMS on CTA-shared accumulators showed up as 10 % of the
+    // kernel's stall samples, profiles/r2_bwd_tc_hot_lines.txt).  Summed over the warps at the end; c2 / c3 go to table row 0.
+    constexpr int BT_WACC = BT_H + 2 * BT_H * D;
+    float* sAccAll = sW3 + BT_H * D;                          // [8 warps][BT_WACC]
+    float* wAcc = sAccAll + warp * BT_WACC;
+    float* sAccC3 = sAccAll + (BT_THREADS / 32) * BT_WACC;    // [D] c3, [D] = out_scale  (rare: one atomic per warp and tile)
     float* sTp = sAccC3 + 8;                // mixture parameters (generic layout, MIX_STRIDE floats per component)
     float2* sMu = reinterpret_cast<float2*>(sTp + MIX_MAX * MIX_STRIDE);   // many_gmm: dense component means
     // per-warp double buffer for the per-step table rows c1[t] | c2[t] (cp.async one half-step ahead)
@@ -224,9 +228,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
         *reinterpret_cast<float*>(smem + BT_OFF_BD_HI + od) = hi;
         *reinterpret_cast<float*>(smem + BT_OFF_BD_LO + od) = lo;
     }
-    for (int i = tid; i < D * BT_H; i += BT_THREADS) { sU1[i] = nv.U1[i]; sAccU1[i] = 0.f; }
-    for (int i = tid; i < BT_H * D; i += BT_THREADS) { sW3[(i % D) * BT_H + i / D] = nv.W3[i]; sAccW3[i] = 0.f; }
-    for (int i = tid; i < BT_H + 8; i += BT_THREADS) sAccC2[i] = 0.f;
+    for (int i = tid; i < D * BT_H; i += BT_THREADS) sU1[i] = nv.U1[i];
+    for (int i = tid; i < BT_H * D; i += BT_THREADS) sW3[(i % D) * BT_H + i / D] = nv.W3[i];
+    for (int i = tid; i < (BT_THREADS / 32) * BT_WACC + 8; i += BT_THREADS) sAccAll[i] = 0.f;
     const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
     for (int i = tid; i < ntp; i += BT_THREADS) sTp[i] = a.tgt.mix[i];
     const bool fast_gmm = (a.tgt.kind == TGT_MANY_GMM);
@@ -599,9 +603,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 #endif   // D is free between GEMM1's epilogue and GEMM2
                         if (!(lane & 4)) {
                             const int jc = cc * 16 + bt_red_col(lane);
-                            atomicAdd(sAccC2 + jc, s2);
-                            atomicAdd(sAccW3 + jc * D + 0, s30);
-                            atomicAdd(sAccW3 + jc * D + 1, s31);
+                            wAcc[jc] += s2;
+                            wAcc[BT_H + jc * D + 0] += s30;
+                            wAcc[BT_H + jc * D + 1] += s31;
                         }
                     }
                 }
@@ -707,8 +711,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                         if (!(lane & 4)) {
                             const int jc = cc * 16 + bt_red_col(lane);
                             atomicAdd(part + L.c1 + (size_t)t * BT_H + jc, s1);
-                            atomicAdd(sAccU1 + 0 * BT_H + jc, s40);
-                            atomicAdd(sAccU1 + 1 * BT_H + jc, s41);
+                            wAcc[BT_H + BT_H * D + 0 * BT_H + jc] += s40;
+                            wAcc[BT_H + BT_H * D + 1 * BT_H + jc] += s41;
                         }
                     }
                 }
@@ -750,9 +754,14 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
     }
     flush_d3();
     __syncthreads();
-    for (int i = tid; i < D * BT_H; i += BT_THREADS) part[L.U1 + i] = sAccU1[i];
-    for (int i = tid; i < BT_H * D; i += BT_THREADS) part[L.W3 + i] = sAccW3[i];
-    for (int i = tid; i < BT_H; i += BT_THREADS) part[L.c2 + i] = sAccC2[i];        // row 0 of the c2 table carries the sum over the steps
+    for (int i = tid; i < BT_WACC; i += BT_THREADS) {
+        float v = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < BT_THREADS / 32; ++w8) v += sAccAll[w8 * BT_WACC + i];
+        if (i < BT_H) part[L.c2 + i] = v;                                            // row 0 of the c2 table carries the sum over the steps
+        else if (i < BT_H + BT_H * D) part[L.W3 + (i - BT_H)] = v;                   // [64][D]
+        else part[L.U1 + (i - BT_H - BT_H * D)] = v;                                 // [D][64]
+    }
     if (tid < D) part[L.c3 + tid] = sAccC3[tid];                                     // likewise c3
     if (tid == D) part[L.os] = sAccC3[D];
     umma::fence_before();
@@ -788,7 +797,7 @@ __global__ void bwd_tc_reduce_kernel(const float* __restrict__ partials, int nbl
 }
 
 static size_t bt_smem_bytes(int D) {
-    return (size_t)BT_OFF_SMALL + (size_t)(4 * D * BT_H + BT_H + 8 + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 8 * 4 * BT_H + 8) * sizeof(float);
+    return (size_t)BT_OFF_SMALL + (size_t)(2 * D * BT_H + 8 * (BT_H + 2 * BT_H * D) + 8 + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 8 * 4 * BT_H + 8) * sizeof(float);
 }
 
 bool bwd_tc_supported(const BridgeArgs& a, int D) {

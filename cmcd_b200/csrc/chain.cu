@@ -146,16 +146,17 @@ __global__ void __launch_bounds__(128) chain_fwd_kernel(const ChainView v, float
     }
     // zero-padded copies of the geffner weights: U1p [d][HP] = W1[:d], U2p = W2[:d], W2p [HP][HP] = W2, W3p [HP][dout] = W3
     if (c.arch == CMCD_ARCH_GEFFNER && U1p) {
-        const long long nb = gridDim.x - (T + 1), me = b - (T + 1);
-        const long long nU = (long long)d * HP, nW2 = (long long)HP * HP, nW3 = (long long)HP * dout, tot = 2 * nU + nW2 + nW3;
+        // one row per block iteration: rows [0, d) of U1p, [d, 2d) of U2p, then HP rows of W2p, then HP rows of W3p
+        const int nb = gridDim.x - (T + 1), me = b - (T + 1);
         const float* w1 = p + c.off[CMCD_LEAF_GEF_W1];
         const float* w2 = p + c.off[CMCD_LEAF_GEF_W2];
         const float* w3 = p + c.off[CMCD_LEAF_GEF_W3];
-        for (long long i = me * blockDim.x + tid; i < tot; i += nb * blockDim.x) {
-            if (i < nU) { const int r = (int)(i / HP), j = (int)(i % HP); U1p[i] = j < H ? w1[(size_t)r * H + j] : 0.f; }
-            else if (i < 2 * nU) { const long long k = i - nU; const int r = (int)(k / HP), j = (int)(k % HP); U2p[k] = j < H ? w2[(size_t)r * H + j] : 0.f; }
-            else if (i < 2 * nU + nW2) { const long long k = i - 2 * nU; const int r = (int)(k / HP), j = (int)(k % HP); W2p[k] = (r < H && j < H) ? w2[(size_t)r * H + j] : 0.f; }
-            else { const long long k = i - 2 * nU - nW2; const int r = (int)(k / dout), j = (int)(k % dout); W3p[k] = r < H ? w3[(size_t)r * dout + j] : 0.f; }
+        const int nrows = 2 * d + 2 * HP;
+        for (int rr = me; rr < nrows; rr += nb) {
+            if (rr < d) { for (int j = tid; j < HP; j += blockDim.x) U1p[(size_t)rr * HP + j] = j < H ? w1[(size_t)rr * H + j] : 0.f; }
+            else if (rr < 2 * d) { const int r = rr - d; for (int j = tid; j < HP; j += blockDim.x) U2p[(size_t)r * HP + j] = j < H ? w2[(size_t)r * H + j] : 0.f; }
+            else if (rr < 2 * d + HP) { const int r = rr - 2 * d; for (int j = tid; j < HP; j += blockDim.x) W2p[(size_t)r * HP + j] = (r < H && j < H) ? w2[(size_t)r * H + j] : 0.f; }
+            else { const int r = rr - 2 * d - HP; for (int j = tid; j < dout; j += blockDim.x) W3p[(size_t)r * dout + j] = r < H ? w3[(size_t)r * dout + j] : 0.f; }
         }
     }
 }
@@ -165,6 +166,19 @@ struct ChainGrads {
     const float *g_betas, *g_eps, *g_mean, *g_logdiag, *c1, *c2, *c3, *U1, *U2, *U3, *W2, *W3, *os;
 };
 __device__ __forceinline__ bool ch_train(const cmcd_chain& c, int leaf) { return c.off[leaf] >= 0 && ((c.train_mask >> leaf) & 1u); }
+
+// y[i] = sum_j v[j] W[i][j] for a row-major [rows][64] matrix: one warp per row (lanes over j, coalesced), shuffle reduction in a
+// fixed order.  v in shared memory; result to y (shared).  blockDim.x == 128 (4 warps).
+__device__ __forceinline__ void ch_rowdot64(const float* __restrict__ W, int rows, const float* v, float* y) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float v0 = v[lane], v1 = v[lane + 32];
+    for (int i = warp; i < rows; i += 4) {
+        float s = fmaf(v0, W[(size_t)i * CH_C + lane], v1 * W[(size_t)i * CH_C + lane + 32]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) y[i] = s;
+    }
+}
 
 // scratch layout (dds): per row t: code[128] | h[64] | tnet[64] | g_tnet[64] | g_pre[64] | g_phase[64]
 constexpr int CH_ROW = 2 * CH_C + 5 * CH_C;
@@ -180,28 +194,19 @@ __global__ void __launch_bounds__(128) chain_bwd_rows_kernel(const ChainView v, 
         ch_dds_row_forward(c, p, b, code, pre, h, tnet);
         if (tid < CH_C) gc1[tid] = g.c1[(size_t)b * HP + tid];
         __syncthreads();
-        if (tid < CH_C) {      // g_tnet[i] = sum_j g_c1[j] W1[d + i][j]
-            const float* w = p + c.off[CMCD_LEAF_DDS_ST1_W] + (size_t)(d + tid) * CH_C;
-            float s = 0.f;
-            for (int j = 0; j < CH_C; ++j) s = fmaf(gc1[j], w[j], s);
-            gt[tid] = s;
-        }
+        // g_tnet[i] = sum_j g_c1[j] W1[d + i][j]
+        ch_rowdot64(p + c.off[CMCD_LEAF_DDS_ST1_W] + (size_t)d * CH_C, CH_C, gc1, gt);
         __syncthreads();
-        if (tid < CH_C) {      // g_h[i] = sum_j g_tnet[j] tc2.w[i][j]; g_pre = g_h gelu'(pre)
-            const float* w = p + c.off[CMCD_LEAF_DDS_TC2_W] + (size_t)tid * CH_C;
-            float s = 0.f;
-            for (int j = 0; j < CH_C; ++j) s = fmaf(gt[j], w[j], s);
-            gp[tid] = s * ch_gelu_grad(pre[tid]);
-        }
+        // g_h[i] = sum_j g_tnet[j] tc2.w[i][j]; g_pre = g_h gelu'(pre)
+        ch_rowdot64(p + c.off[CMCD_LEAF_DDS_TC2_W], CH_C, gt, gp);
+        __syncthreads();
+        if (tid < CH_C) gp[tid] *= ch_gelu_grad(pre[tid]);
         __syncthreads();
         float* row = scratch + (size_t)b * CH_ROW;
-        {                      // g_code[cidx] = sum_j g_pre[j] tc1.w[cidx][j]  (all 128 threads)
-            const float* w = p + c.off[CMCD_LEAF_DDS_TC1_W] + (size_t)tid * CH_C;
-            float s = 0.f;
-            for (int j = 0; j < CH_C; ++j) s = fmaf(gp[j], w[j], s);
-            row[tid] = code[tid];
-            code[tid] = s;     // g_code overwrites code in shared memory after the copy (same thread reads and writes its element)
-        }
+        row[tid] = code[tid];
+        __syncthreads();
+        // g_code[cidx] = sum_j g_pre[j] tc1.w[cidx][j]  (128 rows); overwrites code in shared memory (its copy is in `row`)
+        ch_rowdot64(p + c.off[CMCD_LEAF_DDS_TC1_W], 2 * CH_C, gp, code);
         __syncthreads();
         if (tid < CH_C) {
             // d sin(arg)/d phase = cos(arg) = (saved) code[64 + ch]; d cos(arg)/d phase = -sin(arg)
@@ -222,17 +227,20 @@ __global__ void __launch_bounds__(128) chain_bwd_rows_kernel(const ChainView v, 
         const float* w2 = p + c.off[CMCD_LEAF_GEF_W2] + (size_t)d * H;
         const float* w3 = p + c.off[CMCD_LEAF_GEF_W3] + (size_t)d * dout;
         const int nrow = (b == K - 1) ? 2 : 1;
-        for (int i = tid; i < E; i += blockDim.x) {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int i = warp; i < E; i += 4) {          // one warp per embedding index: lanes stride over the hidden units (coalesced)
             float s = 0.f;
             for (int rr = 0; rr < nrow; ++rr) {
                 const int t = b + rr;
                 const float* g1 = g.c1 + (size_t)t * HP;
                 const float* g2 = g.c2 + (size_t)t * HP;
                 const float* g3 = g.c3 + (size_t)t * dout;
-                for (int j = 0; j < H; ++j) s = fmaf(g1[j], w1[(size_t)i * H + j], fmaf(g2[j], w2[(size_t)i * H + j], s));
-                for (int j = 0; j < dout; ++j) s = fmaf(g3[j], w3[(size_t)i * dout + j], s);
+                for (int j = lane; j < H; j += 32) s = fmaf(g1[j], w1[(size_t)i * H + j], fmaf(g2[j], w2[(size_t)i * H + j], s));
+                for (int j = lane; j < dout; j += 32) s = fmaf(g3[j], w3[(size_t)i * dout + j], s);
             }
-            out[c.off[CMCD_LEAF_GEF_EMB] + (size_t)b * E + i] = s;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) out[c.off[CMCD_LEAF_GEF_EMB] + (size_t)b * E + i] = s;
         }
         return;
     }
@@ -253,24 +261,44 @@ __global__ void __launch_bounds__(128) chain_bwd_rows_kernel(const ChainView v, 
             for (int k = 0; k <= G1; ++k) ggy[k] = 0.f;
         }
         __syncthreads();
-        if (tid == 0 && K >= 1) {    // K <= a few hundred: one thread, ascending order (deterministic)
-            const float* xp = p + c.off[CMCD_LEAF_GRID_X];
-            const float* tx = p + c.off[CMCD_LEAF_TARGET_X];
-            float ge = 0.f;
-            const float eps0 = p[c.off[CMCD_LEAF_EPS]];
-            (void)eps0;
-            for (int i = 0; i < K; ++i) {
-                const float x = tx[i];
-                int s = 0;
-                while (s < G1 + 1 && xp[s] <= x) ++s;
-                s = min(max(s, 1), G1);
-                const float dx = xp[s] - xp[s - 1], delta = x - xp[s - 1];
-                const float gb = g.g_betas[i];
-                if (dx == 0.f) ggy[s] += gb;
-                else { const float w = delta / dx; ggy[s] += w * gb; ggy[s - 1] += (1.0f - w) * gb; }
+        // per step (in parallel, 128 at a time): segment, interpolation weight, eps-schedule factor; then one thread accumulates
+        // the chunk in ascending step order (deterministic)
+        __shared__ int seg_s[128];
+        __shared__ float w_s[128], gb_s[128], ge_s[128];
+        __shared__ float ge_tot;
+        if (tid == 0) ge_tot = 0.f;
+        for (int i0 = 0; i0 < K; i0 += 128) {
+            const int i = i0 + tid;
+            if (i < K) {
+                const float* xp = p + c.off[CMCD_LEAF_GRID_X];
+                const float x = p[c.off[CMCD_LEAF_TARGET_X] + i];
+                int sidx = 0;
+                while (sidx < G1 + 1 && xp[sidx] <= x) ++sidx;
+                sidx = min(max(sidx, 1), G1);
+                const float dx = xp[sidx] - xp[sidx - 1], delta = x - xp[sidx - 1];
+                seg_s[tid] = sidx;
+                w_s[tid] = (dx == 0.f) ? 2.0f : delta / dx;          // 2 = marker for the degenerate segment (whole weight on the right node)
+                gb_s[tid] = g.g_betas[i];
                 const float dec = (c.eps_schedule == CMCD_EPS_LINEAR) ? 1.0f - (float)i / (float)(K - 1) : ch_eps_decay(c.eps_schedule, i, K);
-                ge = fmaf(g.g_eps[i], dec, ge);
+                ge_s[tid] = g.g_eps[i] * dec;
             }
+            __syncthreads();
+            if (tid == 0) {
+                float ge = ge_tot;
+                const int n = min(128, K - i0);
+                for (int q = 0; q < n; ++q) {
+                    const int sidx = seg_s[q];
+                    const float w = w_s[q], gb = gb_s[q];
+                    if (w == 2.0f) ggy[sidx] += gb;
+                    else { ggy[sidx] += w * gb; ggy[sidx - 1] += (1.0f - w) * gb; }
+                    ge += ge_s[q];
+                }
+                ge_tot = ge;
+            }
+            __syncthreads();
+        }
+        if (tid == 0 && K >= 1) {
+            const float ge = ge_tot;
             if (ch_train(c, CMCD_LEAF_EPS)) out[c.off[CMCD_LEAF_EPS]] = ge;
             if (ch_train(c, CMCD_LEAF_MGRID_Y)) {
                 // gy[k] = C[k] / tot (k >= 1): g_C[k] = ggy[k] / tot, g_tot = -sum_k ggy[k] gy[k] / tot; m[l] feeds C[k] for k > l and tot
@@ -301,7 +329,7 @@ __global__ void __launch_bounds__(256) chain_bwd_weights_kernel(const ChainView 
     const float* __restrict__ p = v.p;
     const int K = c.nbridges, T = K + 1, d = c.in_dim, dout = c.dim, H = c.hidden, HP = c.hidden_pad;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        long long k = idx;
+        int k = (int)idx;   // total < 2^31 (checked by the launcher): 32-bit divisions
         if (c.arch == CMCD_ARCH_DDS) {
             const int C = CH_C;
             // segments: tc1.w [128][64] | tc1.b | tc2.w [64][64] | tc2.b | st1.w [(d+64)][64] | st1.b | st2.w | st2.b | out.w [64][dout] | out.b | phase
@@ -325,7 +353,7 @@ __global__ void __launch_bounds__(256) chain_bwd_weights_kernel(const ChainView 
             k -= C * C;
             if (k < C) { float s = 0.f; for (int t = 0; t < T; ++t) s += scratch[(size_t)t * CH_ROW + 4 * C + k]; CH_PUT(CMCD_LEAF_DDS_TC2_B, k, s); continue; }
             k -= C;
-            if (k < (long long)(d + C) * C) {   // st1.w: rows < d = U1 cotangent; rows >= d: sum_t tnet[t][i] g_c1[t][j]
+            if (k < (d + C) * C) {   // st1.w: rows < d = U1 cotangent; rows >= d: sum_t tnet[t][i] g_c1[t][j]
                 const int r = (int)(k / C), j = (int)(k % C);
                 float s;
                 if (r < d) s = g.U1[(size_t)r * HP + j];
@@ -336,15 +364,15 @@ __global__ void __launch_bounds__(256) chain_bwd_weights_kernel(const ChainView 
                 CH_PUT(CMCD_LEAF_DDS_ST1_W, k, s);
                 continue;
             }
-            k -= (long long)(d + C) * C;
+            k -= (d + C) * C;
             if (k < C) { float s = 0.f; for (int t = 0; t < T; ++t) s += g.c1[(size_t)t * HP + k]; CH_PUT(CMCD_LEAF_DDS_ST1_B, k, s); continue; }
             k -= C;
             if (k < C * C) { CH_PUT(CMCD_LEAF_DDS_ST2_W, k, g.W2[k]); continue; }
             k -= C * C;
             if (k < C) { float s = 0.f; for (int t = 0; t < T; ++t) s += g.c2[(size_t)t * HP + k]; CH_PUT(CMCD_LEAF_DDS_ST2_B, k, s); continue; }
             k -= C;
-            if (k < (long long)C * dout) { CH_PUT(CMCD_LEAF_DDS_OUT_W, k, g.W3[k]); continue; }
-            k -= (long long)C * dout;
+            if (k < C * dout) { CH_PUT(CMCD_LEAF_DDS_OUT_W, k, g.W3[k]); continue; }
+            k -= C * dout;
             if (k < dout) { float s = 0.f; for (int t = 0; t < T; ++t) s += g.c3[(size_t)t * dout + k]; CH_PUT(CMCD_LEAF_DDS_OUT_B, k, s); continue; }
             k -= dout;
             if (k < C) { float s = 0.f; for (int t = 0; t < T; ++t) s += scratch[(size_t)t * CH_ROW + 6 * C + k]; CH_PUT(CMCD_LEAF_DDS_PHASE, k, s); continue; }
@@ -352,7 +380,7 @@ __global__ void __launch_bounds__(256) chain_bwd_weights_kernel(const ChainView 
             const int E = c.emb_dim, in = d + E;   // = H
             // segments: W1 [in][H] | b1 [H] | W2 [in][H] | b2 | W3 [in][dout] | b3
             auto emb_row = [&](int t) { return p + c.off[CMCD_LEAF_GEF_EMB] + (size_t)(t < K ? t : K - 1) * E; };
-            if (k < (long long)in * H) {     // W1: rows < d = U1 cotangent; rows >= d: sum_t e[t][i] g_c1[t][j]
+            if (k < in * H) {     // W1: rows < d = U1 cotangent; rows >= d: sum_t e[t][i] g_c1[t][j]
                 const int r = (int)(k / H), j = (int)(k % H);
                 float s;
                 if (r < d) s = g.U1[(size_t)r * HP + j];
@@ -360,10 +388,10 @@ __global__ void __launch_bounds__(256) chain_bwd_weights_kernel(const ChainView 
                 CH_PUT(CMCD_LEAF_GEF_W1, k, s);
                 continue;
             }
-            k -= (long long)in * H;
+            k -= in * H;
             if (k < H) { float s = 0.f; for (int t = 0; t < T; ++t) s += g.c1[(size_t)t * HP + k]; CH_PUT(CMCD_LEAF_GEF_B1, k, s); continue; }
             k -= H;
-            if (k < (long long)in * H) {     // W2: acts on a1 (all rows: W2 cotangent) + on x through U2 (rows < d) + on emb through c2 (rows >= d)
+            if (k < in * H) {     // W2: acts on a1 (all rows: W2 cotangent) + on x through U2 (rows < d) + on emb through c2 (rows >= d)
                 const int r = (int)(k / H), j = (int)(k % H);
                 float s = g.W2[(size_t)r * HP + j];
                 if (r < d) s += g.U2 ? g.U2[(size_t)r * HP + j] : 0.f;
@@ -371,10 +399,10 @@ __global__ void __launch_bounds__(256) chain_bwd_weights_kernel(const ChainView 
                 CH_PUT(CMCD_LEAF_GEF_W2, k, s);
                 continue;
             }
-            k -= (long long)in * H;
+            k -= in * H;
             if (k < H) { float s = 0.f; for (int t = 0; t < T; ++t) s += g.c2[(size_t)t * HP + k]; CH_PUT(CMCD_LEAF_GEF_B2, k, s); continue; }
             k -= H;
-            if (k < (long long)in * dout) {
+            if (k < in * dout) {
                 const int r = (int)(k / dout), j = (int)(k % dout);
                 float s = g.W3[(size_t)r * dout + j];
                 if (r < d) s += g.U3 ? g.U3[(size_t)r * dout + j] : 0.f;
@@ -382,7 +410,7 @@ __global__ void __launch_bounds__(256) chain_bwd_weights_kernel(const ChainView 
                 CH_PUT(CMCD_LEAF_GEF_W3, k, s);
                 continue;
             }
-            k -= (long long)in * dout;
+            k -= in * dout;
             if (k < dout) { float s = 0.f; for (int t = 0; t < T; ++t) s += g.c3[(size_t)t * dout + k]; CH_PUT(CMCD_LEAF_GEF_B3, k, s); continue; }
         }
     }
@@ -415,10 +443,9 @@ int launch_chain_fwd(const cmcd_chain* c, cudaStream_t st, const float* params_f
     const int T = c->nbridges + 1;
     int grid = (c->arch == CMCD_ARCH_NONE ? 0 : 0) + T + 1;
     if (c->arch == CMCD_ARCH_GEFFNER && U1p) {
-        const long long tot = 2LL * c->in_dim * c->hidden_pad + (long long)c->hidden_pad * c->hidden_pad + (long long)c->hidden_pad * c->dim;
-        long long nb = (tot + 128 * 8 - 1) / (128 * 8);
-        if (nb > 2048) nb = 2048;
-        grid += (int)nb;
+        int nb = 2 * c->in_dim + 2 * c->hidden_pad;   // one padded row per block (capped: the blocks stride over the rows)
+        if (nb > 4096) nb = 4096;
+        grid += nb;
     }
     chain_fwd_kernel<<<grid, 128, 0, st>>>(v, betas, eps, c1, c2, c3, U1p, U2p, W2p, W3p);
     CMCD_CUDA_OK(cudaGetLastError());
@@ -446,6 +473,7 @@ int launch_chain_bwd(const cmcd_chain* c, cudaStream_t st, const float* params_f
     chain_bwd_rows_kernel<<<T + 1, 128, 0, st>>>(v, g, scratch, grad_flat);
     CMCD_CUDA_OK(cudaGetLastError());
     const long long total = chain_weight_elements(*c);
+    if (total >= (1LL << 31)) { set_error("chain_bwd: network too large (%lld weight elements)", total); return 2; }
     if (total > 0) {
         long long nb = (total + 255) / 256;
         if (nb > 4096) nb = 4096;

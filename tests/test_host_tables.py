@@ -49,3 +49,20 @@ def test_clip_settings_follow_the_operator():
     assert mcd_utils._clips("MCD_CAIS_UHA_sn", False) == (1e2, inf)      # stable=True is hard-coded, mcd_under_lp_a_cais.py:48
     assert mcd_utils._clips("MCD_U_a-lp-sn", True) == (inf, inf)        # the lp_a / lp_e / lp_ea operators never clip
     assert mcd_utils._clips("MCD_CAIS_sn", True) == (1e3, inf) and mcd_utils._clips("MCD_CAIS_var_sn", True) == (1e2, 1e2)
+
+
+def test_mfvi_machine_pytree_matches_reference_layout():
+    """boundingmachine.initialize(nbridges=0) (main.py:83-85) builds the same pytree as the reference: vd | then the frozen leaves in
+    sorted key order eps, eta, gridref_x (2), md (dim), mgridref_y (1), target_x (0) -- boundingmachine.py:9-70."""
+    import torch
+    from cmcd_b200 import boundingmachine as PB
+    from oracle import mcdboundingmachine as OM
+    dim = 3
+    pf, unf, fixed = PB.initialize(dim, trainable=("vd",), init_sigma=1.5, device="cpu")
+    po, unfo, fixedo = OM.bm_initialize(dim, init_sigma=1.5)
+    assert fixed == fixedo == (dim, 0, 1)
+    assert pf.numel() == po.numel() == 2 * dim + 1 + 1 + 2 + dim + 1 + 0
+    assert torch.equal(pf, po)
+    pt, pn = unf(pf)
+    assert sorted(pt) == ["vd"] and sorted(pn) == ["eps", "eta", "gridref_x", "md", "mgridref_y", "target_x"]
+    assert pn["target_x"].numel() == 0 and pn["mgridref_y"].tolist() == [1.0] and pn["gridref_x"].tolist() == [0.0, 1.0]
