@@ -36,7 +36,7 @@ constexpr int TC_CTAS_PER_SM = 3;
 
 template <int D>
 struct TcCtx {
-    const float *sU1, *sU2, *sW3, *sU3;   // shared memory
+    const float *sU1, *sU2, *sW3, *sU3, *sW3T;   // shared memory (sW3T: W3 transposed, [D][64])
     const float *c1, *c2, *c3;            // global per-step tables [T][64], [T][64], [T][D]
     const float* tab;                     // this warp's staged rows c1[t] | c2[t] of the current half-step (shared memory)
     float out_scale, out_clip;
@@ -70,6 +70,9 @@ template <int D, int ACT>
 __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, int next_t, const float (&x)[D], float (&skipacc)[D]) {
     constexpr bool skip = (ACT == ACT_SOFTPLUS);
     const float4* __restrict__ c1v = reinterpret_cast<const float4*>(cx.tab);
+    f32x2_t xb[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) xb[a] = pk2(x[a], x[a]);
 #pragma unroll
     for (int m = 0; m < D; ++m) skipacc[m] = 0.f;
 #pragma unroll 1
@@ -78,13 +81,15 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, int next_t, co
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 cc = c1v[c * 4 + q];
-            float p[4] = {cc.x, cc.y, cc.z, cc.w};
+            f32x2_t p01 = pk2(cc.x, cc.y), p23 = pk2(cc.z, cc.w);   // two hidden units per FFMA2 (x broadcast pairs built once per node)
 #pragma unroll
             for (int a = 0; a < D; ++a) {
                 const float4 u = *reinterpret_cast<const float4*>(cx.sU1 + a * TC_H + c * 16 + q * 4);
-                p[0] = fmaf(x[a], u.x, p[0]); p[1] = fmaf(x[a], u.y, p[1]);
-                p[2] = fmaf(x[a], u.z, p[2]); p[3] = fmaf(x[a], u.w, p[3]);
+                p01 = fma2(xb[a], pk2(u.x, u.y), p01);
+                p23 = fma2(xb[a], pk2(u.z, u.w), p23);
             }
+            float p[4];
+            upk2(p01, p[0], p[1]); upk2(p23, p[2], p[3]);
             float av[4];
             if constexpr (ACT == ACT_GELU) {   // two activations per instruction slot (FFMA2)
                 upk2(gelu_fast2(p[0], p[1]), av[0], av[1]);
@@ -161,6 +166,9 @@ __device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (
         o[m] = p;
     }
     const float4* __restrict__ c2v = reinterpret_cast<const float4*>(cx.tab + TC_H);
+    f32x2_t O2[D];                        // dds: output-layer partial sums over (even, odd) hidden units
+#pragma unroll
+    for (int m = 0; m < D; ++m) O2[m] = pk2(0.f, 0.f);
     umma::mbar_wait(cx.mbar, cx.parity);
     cx.parity ^= 1u;
     umma::fence_after();
@@ -172,30 +180,45 @@ __device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 cc = c2v[c * 4 + q];
-            float p[4] = {__uint_as_float(v[q * 4 + 0]) + cc.x, __uint_as_float(v[q * 4 + 1]) + cc.y,
-                          __uint_as_float(v[q * 4 + 2]) + cc.z, __uint_as_float(v[q * 4 + 3]) + cc.w};
-            if (has_u) {
+            if constexpr (ACT == ACT_GELU) {
+                // dds: no U2 term; bias add, two exact-erf GELUs and the output-layer products all on packed pairs of hidden units
+                float p0, p1, p2, p3;
+                upk2(add2(pk2(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1])), pk2(cc.x, cc.y)), p0, p1);
+                upk2(add2(pk2(__uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3])), pk2(cc.z, cc.w)), p2, p3);
+                const f32x2_t A01 = gelu_fast2(p0, p1), A23 = gelu_fast2(p2, p3);
 #pragma unroll
-                for (int a = 0; a < D; ++a) {
-                    const float4 u = *reinterpret_cast<const float4*>(cx.sU2 + a * TC_H + c * 16 + q * 4);
-                    p[0] = fmaf(x[a], u.x, p[0]); p[1] = fmaf(x[a], u.y, p[1]);
-                    p[2] = fmaf(x[a], u.z, p[2]); p[3] = fmaf(x[a], u.w, p[3]);
+                for (int m = 0; m < D; ++m) {
+                    const float4 w = *reinterpret_cast<const float4*>(cx.sW3T + m * TC_H + c * 16 + q * 4);
+                    O2[m] = fma2(A01, pk2(w.x, w.y), O2[m]);
+                    O2[m] = fma2(A23, pk2(w.z, w.w), O2[m]);
+                }
+            } else {
+                float p[4] = {__uint_as_float(v[q * 4 + 0]) + cc.x, __uint_as_float(v[q * 4 + 1]) + cc.y,
+                              __uint_as_float(v[q * 4 + 2]) + cc.z, __uint_as_float(v[q * 4 + 3]) + cc.w};
+                if (has_u) {
+#pragma unroll
+                    for (int a = 0; a < D; ++a) {
+                        const float4 u = *reinterpret_cast<const float4*>(cx.sU2 + a * TC_H + c * 16 + q * 4);
+                        p[0] = fmaf(x[a], u.x, p[0]); p[1] = fmaf(x[a], u.y, p[1]);
+                        p[2] = fmaf(x[a], u.z, p[2]); p[3] = fmaf(x[a], u.w, p[3]);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float av = act_tc<ACT>(p[e]);
+                    const int j = c * 16 + q * 4 + e;
+#pragma unroll
+                    for (int m = 0; m < D; ++m) o[m] = fmaf(av, cx.sW3[j * D + m], o[m]);
                 }
             }
-            float av[4];
-            if constexpr (ACT == ACT_GELU) {
-                upk2(gelu_fast2(p[0], p[1]), av[0], av[1]);
-                upk2(gelu_fast2(p[2], p[3]), av[2], av[3]);
-            } else {
+        }
+    }
+    if constexpr (ACT == ACT_GELU) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) av[e] = act_tc<ACT>(p[e]);
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = c * 16 + q * 4 + e;
-#pragma unroll
-                for (int m = 0; m < D; ++m) o[m] = fmaf(av[e], cx.sW3[j * D + m], o[m]);
-            }
+        for (int m = 0; m < D; ++m) {
+            float e0, e1;
+            upk2(O2[m], e0, e1);
+            o[m] += e0 + e1;
         }
     }
     umma::fence_before();   // orders these tcgen05.ld before the next batch's writes to D (via the next mbarrier arrive / wait)
@@ -219,7 +242,8 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
     float* sU2 = sU1 + D * TC_H;
     float* sW3 = sU2 + D * TC_H;
     float* sU3 = sW3 + TC_H * D;
-    float* sTp = sU3 + ((D * D + 3) & ~3);
+    float* sW3T = sU3 + ((D * D + 3) & ~3);
+    float* sTp = sW3T + D * TC_H;
     // B[n = j][k = i] = W2[i][j], split into tf32 hi / lo
     for (int idx = tid; idx < TC_H * TC_H; idx += TC_PB) {
         const int i = idx / TC_H, j = idx % TC_H;
@@ -231,7 +255,7 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
         *reinterpret_cast<__nv_bfloat16*>(sBhi16 + umma::core_off16(j, i, TC_H)) = __float2bfloat16(hi);
     }
     for (int i = tid; i < D * TC_H; i += TC_PB) { sU1[i] = nv.U1[i]; sU2[i] = nv.U2 ? nv.U2[i] : 0.f; }
-    for (int i = tid; i < TC_H * D; i += TC_PB) sW3[i] = nv.W3[i];
+    for (int i = tid; i < TC_H * D; i += TC_PB) { sW3[i] = nv.W3[i]; sW3T[(i % D) * TC_H + i / D] = nv.W3[i]; }
     for (int i = tid; i < D * D; i += TC_PB) sU3[i] = nv.U3 ? nv.U3[i] : 0.f;
     const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
     for (int i = tid; i < ntp; i += TC_PB) sTp[i] = a.tgt.mix[i];
@@ -256,7 +280,7 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
     umma::fence_after();
 
     TcCtx<D> cx;
-    cx.sU1 = sU1; cx.sU2 = sU2; cx.sW3 = sW3; cx.sU3 = sU3;
+    cx.sU1 = sU1; cx.sU2 = sU2; cx.sW3 = sW3; cx.sU3 = sU3; cx.sW3T = sW3T;
     cx.c1 = nv.c1; cx.c2 = nv.c2; cx.c3 = nv.c3;
     cx.out_scale = net_out_scale(nv); cx.out_clip = nv.out_clip;
     cx.tmem_base = tmem_slot;
@@ -407,7 +431,7 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
 template <int D, int ACT>
 static int launch_fwd_tc_t(const BridgeArgs& a_in, cudaStream_t st, int num_sms) {
     // request > 227/4 KB so that at most three CTAs (3 x 160 TMEM columns) share an SM
-    size_t smem = 2 * TC_B_BYTES + TC_B16_BYTES + (2 * D * TC_H + TC_H * D + D * D + 4 + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 4 * 4 * TC_H + 8) * sizeof(float);
+    size_t smem = 2 * TC_B_BYTES + TC_B16_BYTES + (2 * D * TC_H + 2 * TC_H * D + D * D + 4 + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 4 * 4 * TC_H + 8) * sizeof(float);
     if (smem < 58 * 1024) smem = 58 * 1024;
     auto kern = bridge_fwd_tc_kernel<D, ACT>;
     CMCD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
