@@ -25,7 +25,7 @@ def get_config(**overrides):
     c = dict(boundmode="UHA", model="lorenz", N=5, nbridges=8, lfsteps=1, emb_dim=20, nlayers=3, init_eta=0.0, init_eps=1e-5,
              init_sigma=1.0, pretrain_mfvi=True, train_vi=True, train_eps=True, train_betas=True, nn_arch="geffner",
              eps_schedule="", grad_clipping=False, mfvi_iters=150000, mfvi_lr=0.01, iters=150000, lr=0.0001, seed=1,
-             n_samples=500, n_input_dist_seeds=30, use_ema=False)
+             n_samples=500, n_input_dist_seeds=30, use_ema=False, use_whitened=False)
     c.update(overrides)
     return SimpleNamespace(**c)
 
@@ -42,7 +42,7 @@ def setup_config(config):
 def main(config, device="cuda", graph=True, sync_every=500, log=print):
     """main.py:60-262 -> dict(elbo_final, final_ln_Z, elbo_final_std, final_ln_Z_std, losses, params_flat, diverged)."""
     config = setup_config(config)
-    out = load_model(config.model, device=device)
+    out = load_model(config.model, config, device=device)
     log_prob_model, dim = out[0], out[1]
     rng_key_gen = opt.prng_key(config.seed)
     train_rng_key_gen, eval_rng_key_gen = opt.split_key(rng_key_gen)

@@ -111,14 +111,28 @@ class CallbackTarget:
 
     kind = "callback"
 
-    def __init__(self, log_prob, dim, device="cuda"):
+    def __init__(self, log_prob, dim, device="cuda", closed_form=None):
+        """``closed_form(x, v) -> (log p [N], score [N,d], H v [N,d] or None)``: optional analytic evaluation used instead of
+        autograd / double backward (same contract, fewer launches)."""
         self.log_prob, self.dim, self.device = log_prob, int(dim), torch.device(device)
+        self.closed_form = closed_form
         self.calls = 0
 
         def _eval(user, stream, x, n, dim_, v, out_logp, out_score, out_hvp):
             try:
                 with torch.cuda.stream(torch.cuda.ExternalStream(int(stream or 0), device=self.device)), torch.enable_grad():
                     self.calls += 1
+                    if self.closed_form is not None:
+                        with torch.no_grad():
+                            vt = _view(v, (n, dim_), self.device) if (v and out_hvp) else None
+                            lp, sc, hv = self.closed_form(_view(x, (n, dim_), self.device), vt)
+                            if out_logp:
+                                _view(out_logp, (n,), self.device).copy_(lp)
+                            if out_score:
+                                _view(out_score, (n, dim_), self.device).copy_(sc)
+                            if vt is not None:
+                                _view(out_hvp, (n, dim_), self.device).copy_(hv)
+                        return 0
                     xt = _view(x, (n, dim_), self.device).detach().clone().requires_grad_(True)
                     lp = self.log_prob(xt)
                     want_hvp = bool(v) and bool(out_hvp)
@@ -146,6 +160,10 @@ class CallbackTarget:
         return t
 
     def evaluate(self, x, v=None):
+        if self.closed_form is not None:
+            with torch.no_grad():
+                lp, sc, hv = self.closed_form(x.detach().to(torch.float32), v)
+            return (lp, sc) if v is None else (lp, sc, hv)
         x = x.detach().to(torch.float32).clone().requires_grad_(True)
         with torch.enable_grad():
             lp = self.log_prob(x)
@@ -197,7 +215,7 @@ def lgcp_constants(file_path, num_dim=1600):
     gram = 1.91 * np.exp(-np.linalg.norm(bv[:, None] - bv[None], axis=-1) / (m * (1.0 / 33)))
     chol = np.linalg.cholesky(gram)
     linv = np.linalg.inv(chol)
-    return dict(counts=counts.reshape(-1), kinv=linv.T @ linv, linv=np.tril(linv),
+    return dict(counts=counts.reshape(-1), kinv=linv.T @ linv, linv=np.tril(linv), chol=chol,
                 mu0=math.log(126.0) - 0.5 * 1.91,
                 log_norm=-0.5 * num_dim * math.log(2 * math.pi) - float(np.sum(np.log(np.abs(np.diag(chol))))),
                 bin_area=1.0 / num_dim)
@@ -209,10 +227,30 @@ def load_model(model="many_gmm", config=None, device="cuda"):
     if "funnel" in model:
         return Target("funnel", int(g("funnel_d", 10)), device), int(g("funnel_d", 10)), None
     if "lgcp" in model:
-        if g("use_whitened", False):
-            raise NotImplementedError("use_whitened=True is outside the hot-path scope")
         c = lgcp_constants(g("file_path", os.path.join(_DATA, "pines.csv")))
         dev = torch.device(device)
+        if g("use_whitened", False):
+            # config.use_whitened (model_handler.py:348-351,373-384; configs/base.py:134 default False): the density of the whitened
+            # variable e with latent = L e + mu0 (cp_utils.py:107-128).  Not in the fused registry: served through the batched
+            # score callback of the step-wise path with CLOSED-FORM score and Hessian-vector product (two dense products each),
+            #   score = -e + L^T (counts - a exp(latent)),   H v = -v - L^T (a exp(latent) * (L v)).
+            chol = torch.tensor(c["chol"], dtype=torch.float32, device=dev)
+            counts = torch.tensor(c["counts"], dtype=torch.float32, device=dev)
+            mu0, area, wn = float(c["mu0"]), float(c["bin_area"]), -0.5 * 1600 * math.log(2.0 * math.pi)
+
+            def log_prob_white(white):
+                latent = white @ chol.T + mu0
+                return wn - 0.5 * (white * white).sum(-1) + (latent * counts - area * torch.exp(latent)).sum(-1)
+
+            def closed_form(white, v):
+                latent = white @ chol.T + mu0
+                e = area * torch.exp(latent)
+                lp = wn - 0.5 * (white * white).sum(-1) + (latent * counts).sum(-1) - e.sum(-1)
+                sc = -white + (counts - e) @ chol
+                hv = None if v is None else -v - (e * (v @ chol.T)) @ chol
+                return lp, sc, hv
+
+            return CallbackTarget(log_prob_white, 1600, device, closed_form=closed_form), 1600
         lg = {k: torch.tensor(c[k], dtype=torch.float32).contiguous().to(dev) for k in ("kinv", "linv", "counts")}
         lg.update(mu0=c["mu0"], log_norm=c["log_norm"], bin_area=c["bin_area"])
         return Target("lgcp", 1600, device, lgcp=lg), 1600

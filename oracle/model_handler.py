@@ -143,7 +143,14 @@ def load_model_lgcp(config, dtype=torch.float32):
     log_norm = -0.5 * d * math.log(2.0 * math.pi) - c["half_log_det"]
     a = c["poisson_a"]
     if config.use_whitened:
-        raise NotImplementedError("use_whitened=True is outside the hot-path scope (configs/base.py:134 default False)")
+        # model_handler.py:373-384: density of the WHITENED variable e, latent = L e + mu0 (cp_utils.py:107-128)
+        white_norm = -0.5 * d * math.log(2.0 * math.pi)
+
+        def log_prob_white(white):
+            latent = white @ chol.T + mu0
+            return white_norm - 0.5 * (white * white).sum(-1) + (latent * counts - a * torch.exp(latent)).sum(-1)
+
+        return log_prob_white, d
 
     def log_prob(x):
         white = torch.linalg.solve_triangular(chol, (x - mu0).T, upper=False).T  # cp_utils.py:153

@@ -31,6 +31,9 @@ CONFIGS = {
                    vd_mean=3.5, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
     "D_lgcp_ula": dict(model="lgcp", mode="MCD_ULA", N=11, K=4, nn_arch="geffner", emb_dim=20, eps=5e-4, sigma=0.3,
                        vd_mean=3.5, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+    # config.use_whitened = True (model_handler.py:348-351,373-384): density of the whitened variable, served by the callback path
+    "D_lgcp_white": dict(model="lgcp", model_cfg=dict(use_whitened=True), mode="MCD_CAIS_sn", N=11, K=4, nn_arch="geffner", emb_dim=20,
+                         eps=1e-3, sigma=0.3, eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
     "lin_funnel": dict(model="funnel", mode="MCD_CAIS_sn", N=200, K=12, nn_arch="dds", emb_dim=20, eps=0.05, sigma=1.0,
                        eps_schedule="linear", clip=True, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
     # underdamped "LDVI" family (mcd_under_lp_a.py): network on (z, rho), on z only, and none
@@ -70,7 +73,7 @@ def oracle_problem(name, dtype=torch.float32, N=None, K=None):
         c["N"] = N
     if K:
         c["K"] = K
-    log_prob, dim = OH.load_model(c["model"], dtype=dtype)
+    log_prob, dim = OH.load_model(c["model"], OH.default_config(**c.get("model_cfg", {})), dtype=dtype)
     # parameters are always drawn in float32 (identical values for every dtype), then cast
     vdp = OM.vd_initialize(dim, c["sigma"])
     g = torch.Generator().manual_seed(7)
@@ -92,7 +95,8 @@ def product_problem(name, pf_oracle, device="cuda", N=None, K=None):
         c["N"] = N
     if K:
         c["K"] = K
-    out = PH.load_model(c["model"], device=device)
+    from types import SimpleNamespace
+    out = PH.load_model(c["model"], config=SimpleNamespace(**c["model_cfg"]) if "model_cfg" in c else None, device=device)
     target, dim = out[0], out[1]
     mgrid = torch.ones(min(32, c["K"]) + 1)
     pf, unf, fixed = PM.initialize(dim, vdparams=PV.initialize(dim, device=device), nbridges=c["K"], eps=c["eps"], gamma=c.get("gamma", 10.0), eta=c.get("eta", 0.5),

@@ -83,7 +83,7 @@ def test_short_bridges_every_path(name, K):
     assert (e_kernel <= np.maximum(GRAD_TOL, 2 * e_oracle32)).all(), (name, K, e_kernel, e_oracle32)
 
 
-@pytest.mark.parametrize("name", ["D_lgcp", "D_lgcp_ula"])
+@pytest.mark.parametrize("name", ["D_lgcp", "D_lgcp_ula", "D_lgcp_white"])
 def test_gradient_parity_lgcp(name):
     """README.md:63 target (d=1600, geffner in=1620, eps / vd / betas trained) through the wide reverse path."""
     c, unf, g32, g64, gp, l64, lp_ = _grads(name)

@@ -75,7 +75,7 @@ def test_forward_parity_readme_40gmm_k256():
     assert abs(l_p[fin].mean().item() - l_o[fin].mean().item()) < EST_TOL * max(1.0, abs(l_o[fin].mean().item()))
 
 
-@pytest.mark.parametrize("name", ["D_lgcp", "D_lgcp_ula"])
+@pytest.mark.parametrize("name", ["D_lgcp", "D_lgcp_ula", "D_lgcp_white"])
 def test_forward_parity_lgcp(name):
     """README.md:63 target (d=1600 dense prior, N=20, K=8, geffner in=1620) through the wide path."""
     c, (loss_o, l_o, z_o), (loss_p, l_p, z_p) = _run_both(name)

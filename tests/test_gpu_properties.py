@@ -83,3 +83,22 @@ def test_empty_batch_and_bad_arguments():
     assert lv.numel() == 0 and z.shape == (0, 2)
     with pytest.raises(NotImplementedError):
         PM.compute_bound(torch.arange(1, 5), pf, unf, (fixed[0], fixed[1], "MCD_DNF", fixed[3]), target, **kw)
+
+
+@pytest.mark.parametrize("name", ["C_manygmm_dds_small", "A_gmm", "B_funnel"])
+def test_empty_and_single_particle_batches(name):
+    """N = 0 (an empty shard of a sharded step) returns empty outputs without a launch; N = 1 runs a one-particle tile / CTA and
+    equals the first particle of a larger batch bit for bit (per-particle results do not depend on the batch)."""
+    from cmcd_b200 import mcdboundingmachine as PM
+    c, lp, dim, pf, unf, fixed = oracle_problem(name)
+    _, target, _, pf_p, unf_p, fixed_p = product_problem(name, pf)
+    kw = dict(eps_schedule=c["eps_schedule"], grad_clipping=c["clip"])
+    seeds = torch.from_numpy(seeds_for(64))
+    with torch.no_grad():
+        l0, (z0, _) = PM.compute_log_elbo(seeds[:0], pf_p, unf_p, fixed_p, target, **kw)
+        assert l0.shape == (0,) and z0.shape == (0, dim)
+        l1, (z1, _) = PM.compute_log_elbo(seeds[:1], pf_p, unf_p, fixed_p, target, **kw)
+        lf, (zf, _) = PM.compute_log_elbo(seeds, pf_p, unf_p, fixed_p, target, **kw)
+    assert torch.equal(l1, lf[:1]) and torch.equal(z1, zf[:1])
+    g1, _ = PM.grad_and_loss(lambda *a: PM.compute_bound(*a, **kw))(seeds[:1], pf_p, unf_p, fixed_p, target)
+    assert torch.isfinite(g1).all()

@@ -66,3 +66,31 @@ def test_mfvi_machine_pytree_matches_reference_layout():
     pt, pn = unf(pf)
     assert sorted(pt) == ["vd"] and sorted(pn) == ["eps", "eta", "gridref_x", "md", "mgridref_y", "target_x"]
     assert pn["target_x"].numel() == 0 and pn["mgridref_y"].tolist() == [1.0] and pn["gridref_x"].tolist() == [0.0, 1.0]
+
+
+def test_whitened_lgcp_closed_form_matches_autograd():
+    """config.use_whitened = True (model_handler.py:348-351,373-384): the product serves the whitened LGCP density through the callback
+    path with a closed-form score / Hessian-vector product; both must equal autograd over the oracle's restatement of
+    whitened_posterior_log_density (fp64)."""
+    import torch
+    from cmcd_b200 import model_handler as PH
+    from oracle import model_handler as OH
+    cfg = OH.default_config(use_whitened=True)
+    lp, d = OH.load_model("lgcp", cfg, dtype=torch.float64)
+    target, dim = PH.load_model("lgcp", cfg, device="cpu")
+    assert dim == d == 1600 and target.kind == "callback"
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, d, generator=g, dtype=torch.float64) * 0.3
+    v = torch.randn(4, d, generator=g, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    l = lp(xr)
+    (s,) = torch.autograd.grad(l.sum(), xr, create_graph=True)
+    (h,) = torch.autograd.grad((s * v).sum(), xr)
+    l2, s2, h2 = target.closed_form(x.float(), v.float())
+    rel = lambda a, b: ((a.double() - b).abs().max() / b.abs().max()).item()
+    assert rel(l2, l.detach()) < 1e-6 and rel(s2, s.detach()) < 1e-5 and rel(h2, h) < 1e-5
+    # the unwhitened density at latent = L e + mu0 differs from the whitened one at e by the log-determinant only
+    lp_u, _ = OH.load_model("lgcp", OH.default_config(), dtype=torch.float64)
+    c = OH.lgcp_constants(cfg.file_path)
+    latent = x @ torch.tensor(c["chol"]).T + c["mu_zero"]
+    assert torch.allclose(lp_u(latent) + c["half_log_det"], l.detach(), rtol=1e-10, atol=1e-8)
