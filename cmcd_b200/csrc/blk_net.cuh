@@ -99,18 +99,25 @@ __device__ __forceinline__ void bk_net_fwd(const NetView& nv, const NetSmem& s, 
             }
             acc[jj][0] = b0; acc[jj][1] = b1;
         }
+        // packed fp32x2: one FFMA2 updates two hidden units of one particle (same per-element rounding as the scalar FMAs)
+        f32x2_t acc2[4][2];
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) { acc2[jp][0] = pk2(acc[2 * jp][0], acc[2 * jp + 1][0]); acc2[jp][1] = pk2(acc[2 * jp][1], acc[2 * jp + 1][1]); }
 #pragma unroll 8
         for (int i = 0; i < HP; ++i) {
             const float4 w0 = *reinterpret_cast<const float4*>(s.W2 + (size_t)i * HP + j0);
             const float4 w1 = *reinterpret_cast<const float4*>(s.W2 + (size_t)i * HP + j0 + 4);
             const float2 h = *reinterpret_cast<const float2*>(S1 + i * BK_RS + p0);
-            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const f32x2_t hx = pk2(h.x, h.x), hy = pk2(h.y, h.y);
+            const f32x2_t w[4] = {pk2(w0.x, w0.y), pk2(w0.z, w0.w), pk2(w1.x, w1.y), pk2(w1.z, w1.w)};
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                acc[jj][0] = fmaf(h.x, w[jj], acc[jj][0]);
-                acc[jj][1] = fmaf(h.y, w[jj], acc[jj][1]);
+            for (int jp = 0; jp < 4; ++jp) {
+                acc2[jp][0] = fma2(hx, w[jp], acc2[jp][0]);
+                acc2[jp][1] = fma2(hy, w[jp], acc2[jp][1]);
             }
         }
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) { upk2(acc2[jp][0], acc[2 * jp][0], acc[2 * jp + 1][0]); upk2(acc2[jp][1], acc[2 * jp][1], acc[2 * jp + 1][1]); }
         // activation, and this tile's share of layer 3 (8 of the HP terms of every output of its 2 particles)
         float o3[D][2];
 #pragma unroll
@@ -250,18 +257,24 @@ __device__ __forceinline__ void bk_net_bwd(const NetView& nv, const NetSmem& ns,
             float acc[8][2];
 #pragma unroll
             for (int ii = 0; ii < 8; ++ii) { acc[ii][0] = 0.f; acc[ii][1] = 0.f; }
+            f32x2_t acc2[4][2];   // packed fp32x2 over pairs of hidden units, as in the layer-2 product
+#pragma unroll
+            for (int ip = 0; ip < 4; ++ip) { acc2[ip][0] = pk2(0.f, 0.f); acc2[ip][1] = pk2(0.f, 0.f); }
 #pragma unroll 8
             for (int jj = 0; jj < HP; ++jj) {
                 const float4 w0 = *reinterpret_cast<const float4*>(sW2T + (size_t)jj * HP + i0);
                 const float4 w1 = *reinterpret_cast<const float4*>(sW2T + (size_t)jj * HP + i0 + 4);
                 const float2 h = *reinterpret_cast<const float2*>(S3 + jj * BK_RS + p0);
-                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                const f32x2_t hx = pk2(h.x, h.x), hy = pk2(h.y, h.y);
+                const f32x2_t wv[4] = {pk2(w0.x, w0.y), pk2(w0.z, w0.w), pk2(w1.x, w1.y), pk2(w1.z, w1.w)};
 #pragma unroll
-                for (int ii = 0; ii < 8; ++ii) {
-                    acc[ii][0] = fmaf(h.x, wv[ii], acc[ii][0]);
-                    acc[ii][1] = fmaf(h.y, wv[ii], acc[ii][1]);
+                for (int ip = 0; ip < 4; ++ip) {
+                    acc2[ip][0] = fma2(hx, wv[ip], acc2[ip][0]);
+                    acc2[ip][1] = fma2(hy, wv[ip], acc2[ip][1]);
                 }
             }
+#pragma unroll
+            for (int ip = 0; ip < 4; ++ip) { upk2(acc2[ip][0], acc[2 * ip][0], acc[2 * ip + 1][0]); upk2(acc2[ip][1], acc[2 * ip][1], acc[2 * ip + 1][1]); }
             float dxp[DI][2];
 #pragma unroll
             for (int m = 0; m < DI; ++m) { dxp[m][0] = 0.f; dxp[m][1] = 0.f; }
