@@ -137,8 +137,8 @@ __device__ __forceinline__ void bt_tmem_reduce16x3(uint32_t sc0, uint32_t sc1, u
 }
 
 // 16 values of row q (hidden units 16c..16c+15) -> bf16 hi + bf16 lo parts in two MN-major SW128 tiles
-__device__ __forceinline__ void bt_stage_bf16x2(uint8_t* t1, uint8_t* t2, int q, int c, const float (&v)[16]) {
-    uint32_t h1[8], h2[8];
+// (h1 / h2: the packed (even, odd) bf16 pairs, also the TMEM A operand of the kind::f16 recompute / input-gradient products)
+__device__ __forceinline__ void bt_stage_bf16x2(uint8_t* t1, uint8_t* t2, int q, int c, const float (&v)[16], uint32_t (&h1)[8], uint32_t (&h2)[8]) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const __nv_bfloat162 hi = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
@@ -154,9 +154,33 @@ __device__ __forceinline__ void bt_stage_bf16x2(uint8_t* t1, uint8_t* t2, int q,
     *reinterpret_cast<uint4*>(t2 + o0) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
     *reinterpret_cast<uint4*>(t2 + o1) = make_uint4(h2[4], h2[5], h2[6], h2[7]);
 }
+__device__ __forceinline__ void bt_stage_bf16x2(uint8_t* t1, uint8_t* t2, int q, int c, const float (&v)[16]) {
+    uint32_t h1[8], h2[8];
+    bt_stage_bf16x2(t1, t2, q, c, v, h1, h2);
+}
 
 // 24 x tcgen05.mma kind::tf32: D = A_hi B_lo + A_lo B_hi + A_hi B_hi (small terms first: the accumulator truncates)
 // (dhi / dlo: shared-memory descriptors of the B tile's first K block; one K block further = +256 B = +16 in the address field)
+#ifndef BT_GEMM_TF32
+// Default since round 2: GEMM1 / GEMM2 as 12 x tcgen05.mma kind::f16 on the bf16 (hi, lo) pairs the weight-gradient staging
+// computes anyway -- A from TMEM as packed pairs (column c = elements 2c, 2c+1; 32 + 32 columns), B = W2 as bf16 (hi, lo) K-major
+// core-matrix tiles -- D = A_hi B_lo + A_lo B_hi + A_hi B_hi (small terms first).  Operand precision 2^-17 (hi + lo carry 16
+// mantissa bits) instead of 2^-22: used only for the adjoint's recompute / cotangent products, whose errors average over
+// particles and steps (parity tolerances unchanged, tests/test_gpu_parity_bwd.py); the forward kernel keeps tf32 x 3.
+// Saves the tf32 splits (384 instructions per node), half of the operand STTM traffic and 3/4 of the MMA time per product.
+// -DBT_GEMM_TF32 restores the tf32 3-pass form.
+__device__ __forceinline__ void bt_issue_gemm(uint32_t tmem_base, uint32_t d_col, uint64_t dhi, uint64_t dlo) {
+    const uint32_t idesc = umma::make_idesc_bf16_k(128, BT_H);
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t acol = tmem_base + (pass == 1 ? BT_A_LO : BT_A_HI);
+        const uint64_t bd = (pass == 0) ? dlo : dhi;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // K = 16 per MMA = 8 packed TMEM columns, two 8 x 16 B core matrices of B (+256 B)
+            umma::mma_f16_ts(tmem_base + d_col, acol + k * 8, bd + (uint64_t)(k * 16), idesc, (pass | k) > 0);
+    }
+}
+#else
 __device__ __forceinline__ void bt_issue_gemm(uint32_t tmem_base, uint32_t d_col, uint64_t dhi, uint64_t dlo) {
     const uint32_t idesc = umma::make_idesc_tf32(128, BT_H);
 #pragma unroll
@@ -168,6 +192,7 @@ __device__ __forceinline__ void bt_issue_gemm(uint32_t tmem_base, uint32_t d_col
             umma::mma_tf32_ts(tmem_base + d_col, acol + k * 8, bd + (uint64_t)(k * 16), idesc, (pass | k) > 0);
     }
 }
+#endif
 // 16 x tcgen05.mma kind::f16: D3[128 x 64] (+)= [X_H1 ; X_H2]^T (Z_G1 + Z_G2) over K = 128 particles
 // (dx / dz: descriptors of the first 16-particle K block of the a1 / dp2 staging tiles; +2048 B per K block, +16 KB for the low part)
 __device__ __forceinline__ void bt_issue_wgrad(uint32_t tmem_base, uint64_t dx, uint64_t dz, bool fresh) {
@@ -219,6 +244,16 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
     };
     for (int idx = tid; idx < BT_H * BT_H; idx += BT_THREADS) {
         const int i = idx / BT_H, j = idx % BT_H;
+#ifndef BT_GEMM_TF32
+        const float w = nv.W2[idx];
+        const __nv_bfloat16 hi = __float2bfloat16(w), lo = __float2bfloat16(w - __bfloat162float(hi));
+        const int of = umma::core_off16(j, i, BT_H);   // GEMM1: B[n = j][k = i] = W2[i][j]
+        const int od = umma::core_off16(i, j, BT_H);   // GEMM2: B[n = i][k = j] = W2[i][j]
+        *reinterpret_cast<__nv_bfloat16*>(smem + BT_OFF_BF_HI + of) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(smem + BT_OFF_BF_LO + of) = lo;
+        *reinterpret_cast<__nv_bfloat16*>(smem + BT_OFF_BD_HI + od) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(smem + BT_OFF_BD_LO + od) = lo;
+#else
         float hi, lo;
         umma::split_tf32(nv.W2[idx], hi, lo);
         const int of = umma::core_off(j, i, BT_H);   // GEMM1: B[n = j][k = i] = W2[i][j]
@@ -227,6 +262,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
         *reinterpret_cast<float*>(smem + BT_OFF_BF_LO + of) = lo;
         *reinterpret_cast<float*>(smem + BT_OFF_BD_HI + od) = hi;
         *reinterpret_cast<float*>(smem + BT_OFF_BD_LO + od) = lo;
+#endif
     }
     for (int i = tid; i < D * BT_H; i += BT_THREADS) sU1[i] = nv.U1[i];
     for (int i = tid; i < BT_H * D; i += BT_THREADS) sW3[(i % D) * BT_H + i / D] = nv.W3[i];
@@ -249,10 +285,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
 
     const uint32_t tmem_base = tmem_slot + (uint32_t)wg * BT_TILE_COLS;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint64_t bf_hi = umma::make_desc(umma::smem_u32(smem + BT_OFF_BF_HI), 128, 32 * BT_H);
-    const uint64_t bf_lo = umma::make_desc(umma::smem_u32(smem + BT_OFF_BF_LO), 128, 32 * BT_H);
-    const uint64_t bd_hi = umma::make_desc(umma::smem_u32(smem + BT_OFF_BD_HI), 128, 32 * BT_H);
-    const uint64_t bd_lo = umma::make_desc(umma::smem_u32(smem + BT_OFF_BD_LO), 128, 32 * BT_H);
+#ifndef BT_GEMM_TF32
+    constexpr uint32_t BT_B_SBO = 16 * BT_H;   // bf16 K-major core matrices: 8 rows x 16 B, next 8-row group 16 * K bytes further
+#else
+    constexpr uint32_t BT_B_SBO = 32 * BT_H;
+#endif
+    const uint64_t bf_hi = umma::make_desc(umma::smem_u32(smem + BT_OFF_BF_HI), 128, BT_B_SBO);
+    const uint64_t bf_lo = umma::make_desc(umma::smem_u32(smem + BT_OFF_BF_LO), 128, BT_B_SBO);
+    const uint64_t bd_hi = umma::make_desc(umma::smem_u32(smem + BT_OFF_BD_HI), 128, BT_B_SBO);
+    const uint64_t bd_lo = umma::make_desc(umma::smem_u32(smem + BT_OFF_BD_LO), 128, BT_B_SBO);
     uint8_t* tX1 = smem + BT_OFF_TILE + wg * 4 * BT_T16K;
     uint8_t* tX2 = tX1 + BT_T16K;
     uint8_t* tZ1 = tX1 + 2 * BT_T16K;
@@ -412,6 +453,14 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                         for (int e = 0; e < 8; ++e) g1s[k4][e] = (k4 == cc) ? g1[e] : g1s[k4][e];
                     }
 #endif
+#ifndef BT_GEMM_TF32
+                    {
+                        uint32_t h1[8], h2[8];
+                        bt_stage_bf16x2(tX1, tX2, q, cc, a1, h1, h2);
+                        umma::tmem_st8(tmem_lane + BT_A_HI + cc * 8, h1);
+                        umma::tmem_st8(tmem_lane + BT_A_LO + cc * 8, h2);
+                    }
+#else
 #ifndef BT_X_NOSPLIT
                     uint32_t hh[16], ll[16];
 #pragma unroll
@@ -427,6 +476,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                     bt_stage_bf16x2(tX1, tX2, q, cc, a1);
 #else
                     if (a1[3] == 12345.678f) bt_stage_bf16x2(tX1, tX2, q, cc, a1);
+#endif
 #endif
                 }
                 umma::tmem_st_wait();
@@ -570,6 +620,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                         const f32x2_t DP = mul2(S, pk2(__uint_as_float(g2u[2 * k]), __uint_as_float(g2u[2 * k + 1])));
                         upk2(DP, dp2[2 * k], dp2[2 * k + 1]);
                     }
+#ifndef BT_GEMM_TF32
+                    {   // packed pairs of chunk cc go to columns [8 cc, 8 cc + 8) of the two A regions: inside parking chunks <= cc / 2,
+                        // which this loop has already consumed
+                        uint32_t h1[8], h2[8];
+                        bt_stage_bf16x2(tZ1, tZ2, q, cc, dp2, h1, h2);
+                        umma::tmem_st8(tmem_lane + BT_A_HI + cc * 8, h1);
+                        umma::tmem_st8(tmem_lane + BT_A_LO + cc * 8, h2);
+                    }
+#else
 #ifndef BT_X_NOSPLIT
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
@@ -584,6 +643,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bridge_bwd_tc_kernel(const Brid
                     bt_stage_bf16x2(tZ1, tZ2, q, cc, dp2);
 #else
                     if (dp2[3] == 12345.678f) bt_stage_bf16x2(tZ1, tZ2, q, cc, dp2);
+#endif
 #endif
                     // gc2[t][j] += sum_p dp2 ; gW3[j][m] += sum_p a2 vo[m]   (three butterflies in lock step; D == 2)
                     {

@@ -441,7 +441,7 @@ int launch_chain_fwd(const cmcd_chain* c, cudaStream_t st, const float* params_f
     if (c->arch != CMCD_ARCH_NONE && (!c1 || !c2 || !c3)) { set_error("chain_fwd: table buffers missing"); return 2; }
     ChainView v; v.c = *c; v.p = params_flat;
     const int T = c->nbridges + 1;
-    int grid = (c->arch == CMCD_ARCH_NONE ? 0 : 0) + T + 1;
+    int grid = T + 1;
     if (c->arch == CMCD_ARCH_GEFFNER && U1p) {
         int nb = 2 * c->in_dim + 2 * c->hidden_pad;   // one padded row per block (capped: the blocks stride over the rows)
         if (nb > 4096) nb = 4096;

@@ -746,33 +746,6 @@ static int run_gemm_t(cudaStream_t st, int num_sms, const float* X, int ldx, con
     return 0;
 }
 
-// G[i][j] += sum_n A[n][i] B[n][j]
-__global__ void __launch_bounds__(128) wide_outer_acc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                                             int N, int I, int J, float* __restrict__ G, int ldg) {
-    const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int i = blockIdx.y;
-    if (j >= J || i >= I) return;
-    if (((J | ldb | ldg) & 3) || ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(G)) & 15)) {   // rows not 16-byte aligned (dim % 4 != 0, or views at odd offsets)
-        for (int q = 0; q < 4 && j + q < J; ++q) {
-            float acc1 = 0.f;
-            for (int n = 0; n < N; ++n) acc1 = fmaf(__ldg(A + (size_t)n * lda + i), __ldg(B + (size_t)n * ldb + j + q), acc1);
-            G[(size_t)i * ldg + j + q] += acc1;
-        }
-        return;
-    }
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int n = 0; n < N; ++n) {
-        const float a = __ldg(A + (size_t)n * lda + i);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(B + (size_t)n * ldb + j));
-        acc.x = fmaf(a, b.x, acc.x); acc.y = fmaf(a, b.y, acc.y); acc.z = fmaf(a, b.z, acc.z); acc.w = fmaf(a, b.w, acc.w);
-    }
-    float4* g = reinterpret_cast<float4*>(G + (size_t)i * ldg + j);
-    float4 o = *g;
-    o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
-    *g = o;
-}
-
-// g[j] += sum_n V[n][j]
 // G[i][j] = sum_r A[r][i] B[r][j] over R stacked rows (all particles of all trajectory points): the weight cotangents of one
 // whole reverse pass as ONE product per layer instead of a rank-N read-modify-write of the 10 MB gradient per point.
 // 64 x 64 output tile per CTA, 4 x 4 per thread, 16-row slabs of A and B staged in shared memory.  Overwrites G.
@@ -821,14 +794,6 @@ __global__ void wide_colsum_rows_kernel(const float* __restrict__ V, int ldv, in
     for (int n = 0; n < N; ++n) s += V[((size_t)t * N + n) * ldv + j];
     g[(size_t)t * ldg + j] = s;
 }
-__global__ void wide_colsum_acc_kernel(const float* __restrict__ V, int ldv, int N, int J, float* __restrict__ g) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= J) return;
-    float s = 0.f;
-    for (int n = 0; n < N; ++n) s += V[(size_t)n * ldv + j];
-    g[j] += s;
-}
-
 __global__ void wide_neg_kernel(const float* __restrict__ cot, int N, float* __restrict__ c) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < N) c[n] = -cot[n];

@@ -97,7 +97,10 @@ typedef struct cmcd_net {
                                    trainable factor_sn, nn.py:63, on the device: no host read-back per iteration, CUDA-graph safe) */
 } cmcd_net;
 
-/* Cotangents of every differentiable cmcd_net field (same shapes); NULL members are skipped. */
+/* Cotangents of every differentiable cmcd_net field (same shapes); NULL members are skipped.
+ * arch = CMCD_ARCH_DDS: PISNet's c2 / c3 tables repeat one bias row for every step (nn_dds.py:159-164: st2.b, LinearZero bias),
+ * so only the SUM over the rows of their cotangents is meaningful; the tensor-core adjoint reports that sum in row 0 and zeros
+ * elsewhere (the other kernels report per-row values whose sum is the same). */
 typedef struct cmcd_net_grad {
     float* U1; float* U2; float* U3; float* W2; float* W3; float* c1; float* c2; float* c3;
     float* out_scale;    /* [1] */
