@@ -36,27 +36,39 @@ def _worker(rank, world, port, loss, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from cmcd_b200.distributed import global_ln_z, shard_bounds, sharded_grad_and_loss
+    from cmcd_b200.distributed import ShardedStep, global_ln_z, shard_bounds, sharded_grad_and_loss
     c, lp, pf, unf, fixed, seeds = _problem()
     lo, hi = shard_bounds(len(seeds), world, rank)
-    g, value, (l, z) = sharded_grad_and_loss(_local_forward(c, lp, unf, fixed), seeds[lo:hi], pf, loss=loss)
+    if loss == "kl_step":     # the step object bench.py uses (eager form: CUDA graphs need a GPU), one fused all-reduce
+        class _Fwd:           # seeds arrive as the step's static int32 tensor
+            def __call__(self, s, p):
+                return _local_forward(c, lp, unf, fixed)(s.numpy(), p)
+        step = ShardedStep(_Fwd(), pf.float(), hi - lo, graph=False)
+        g, value, (l, z) = step(torch.from_numpy(seeds[lo:hi]))
+        assert step.n_global == len(seeds)
+    else:
+        g, value, (l, z) = sharded_grad_and_loss(_local_forward(c, lp, unf, fixed), seeds[lo:hi], pf, loss=loss)
     lnz = global_ln_z(l)
     if rank == 0:
         torch.save({"g": g, "value": value, "lnz": lnz}, out)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("loss", ["kl", "var"])
+@pytest.mark.parametrize("loss", ["kl", "var", "kl_step"])
 def test_two_rank_step_matches_single_process(tmp_path, loss):
     from oracle import mcdboundingmachine as OM
     c, lp, pf, unf, fixed, seeds = _problem()
-    fn = OM.compute_bound if loss == "kl" else OM.compute_bound_var
+    fn = OM.compute_bound_var if loss == "var" else OM.compute_bound
     g_ref, (l_ref, _) = OM.grad_and_loss(fn, seeds, pf, unf, fixed, lp, eps_schedule=c["eps_schedule"], grad_clipping=c["clip"])
-    v_ref = l_ref.mean().item() if loss == "kl" else l_ref.var(unbiased=False).item()
+    v_ref = l_ref.var(unbiased=False).item() if loss == "var" else l_ref.mean().item()
     out = str(tmp_path / "r0.pt")
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, loss, out), nprocs=2, join=True)
     r = torch.load(out)
+    if loss == "kl_step":    # the step works in float32 (the product's dtype)
+        assert abs(float(r["value"]) - v_ref) < 1e-5 * max(1, abs(v_ref))
+        torch.testing.assert_close(r["g"].double(), g_ref, rtol=1e-4, atol=1e-6)
+        return
     assert abs(r["value"] - v_ref) < 1e-9 * max(1, abs(v_ref))
     torch.testing.assert_close(r["g"], g_ref, rtol=1e-9, atol=1e-12)
     lnz_ref = (torch.logsumexp(-l_ref, 0) - np.log(len(seeds))).item()
