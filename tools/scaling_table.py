@@ -49,8 +49,8 @@ for e in range(16, 21):
     out.append("| " + " | ".join(row) + " |")
 out += ["", "Reading: the collective is 0.02-0.03 ms at every size (84 KB over NVLink) and the host chain 0.1-0.5 ms, so scaling is set by the two",
         "bridge kernels alone.  They process whole 128-particle tiles -- forward 3 CTAs per SM, adjoint 2 tiles per SM -- and one trajectory",
-        "point of one tile is a ~5 us (forward) / ~11 us (adjoint) dependency chain, so a pass cannot take less than ~257 x that: ~1.3 ms +",
-        "~2.8 ms.  At N_global = 2^20 on 8 GPUs a rank still has 1024 tiles (7 per SM) and the loss is tile quantisation (the adjoint's 3.46",
+        "point of one tile is a ~5 us (forward) / ~10 us (adjoint) dependency chain, so a pass cannot take less than ~257 x that: ~1.3 ms +",
+        "~2.5 ms.  At N_global = 2^20 on 8 GPUs a rank still has 1024 tiles (7 per SM) and the loss is tile quantisation (the adjoint's 3.46",
         "rounds cost 4); from 2^17 per 8 GPUs downwards (<= 128 tiles per rank, fewer tiles than SMs) the time is the latency floor and adding GPUs",
         "no longer helps -- the regime where more particles per GPU are free."]
 open(os.path.join(ROOT, "profiles", f"{tag}_scaling.md"), "w").write("\n".join(out) + "\n")
