@@ -2,7 +2,6 @@
 epilogue kernels) against the framework chain it replaces (make_betas / eps_table / nn.build_tables under torch autograd,
 CMCD_DISABLE_CHAIN=1) on identical inputs: same losses and the same flat gradient up to the summation order of the small
 products.  (Every oracle parity test runs through the fused chain as well -- it is the default path.)"""
-import numpy as np
 import pytest
 import torch
 

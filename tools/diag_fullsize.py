@@ -7,7 +7,6 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-import numpy as np
 import torch
 
 from cmcd_b200 import mcdboundingmachine as PM
