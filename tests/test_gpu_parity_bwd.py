@@ -211,7 +211,9 @@ def test_one_thread_path_several_tiles_per_cta(name, N, K):
 
 
 # ---------------------------------------------------------------- round 2: BASELINE.json configs at their full sizes
-FULL_SIZE = {"C_manygmm_dds": (2000, 256), "Cvar_manygmm": (2000, 256), "Ckl_manygmm_geffner": (2000, 256)}
+FULL_SIZE = {"C_manygmm_dds": (2000, 256), "Cvar_manygmm": (2000, 256), "Ckl_manygmm_geffner": (2000, 256),
+             # the paper's baselines at the same particle count (block-cooperative underdamped kernels, 2000 particles x 64 steps)
+             "LDVI_manygmm_dds": (2000, 64), "CAISUHA_manygmm_dds": (2000, 64)}
 
 
 @pytest.mark.parametrize("name", list(FULL_SIZE))
@@ -284,7 +286,7 @@ def test_gradient_parity_readme_full_size(name):
 
 
 @pytest.mark.parametrize("name,N,K", [("C_manygmm_dds_small", 60000, 2), ("C_manygmm_dds_small", 60037, 3),
-                                      ("ULAsn_gmm_dds", 60000, 2), ("lin_funnel", 60000, 2)])
+                                      ("ULAsn_gmm_dds", 60000, 2), ("lin_funnel", 60000, 2), ("B_funnel", 60000, 2)])
 def test_tensor_core_path_several_tiles_per_cta(name, N, K):
     """More particles than one tile per CTA of the tcgen05 kernels (forward: 3 x 148 CTAs x 128 particles = 56 832; adjoint:
     148 CTAs x 256 = 37 888): the persistent tile loop, the mbarrier phase carried from tile to tile and the TMEM weight-gradient
