@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcmcd_b200.so")
-SOURCES = ["capi.cu", "bridge_fwd.cu", "bridge_fwd_tc.cu", "bridge_bwd.cu", "bridge_bwd_tc.cu", "bridge_ud.cu", "bridge_blk.cu", "bridge_blk_ud.cu", "bridge_uha.cu", "reduce.cu", "wide.cu", "opt.cu", "chain.cu", "xla_ffi.cc"]
+SOURCES = ["capi.cu", "bridge_fwd.cu", "bridge_fwd_tc.cu", "bridge_fwd_tcw.cu", "bridge_bwd.cu", "bridge_bwd_tc.cu", "bridge_ud.cu", "bridge_blk.cu", "bridge_blk_ud.cu", "bridge_uha.cu", "reduce.cu", "wide.cu", "opt.cu", "chain.cu", "xla_ffi.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--threads", "0"]
 

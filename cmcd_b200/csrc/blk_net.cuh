@@ -21,12 +21,10 @@ constexpr int BK_HP_MAX = 156;
 //   softplus(x) = max(x, 0) + ln2 lg2(1 + e),  e = 2^(-|x| log2 e);  softplus'(x) = 1/(1+e) (x >= 0) | e/(1+e) (x < 0)
 // absolute error <= 1.5e-7 on the value (lg2.approx: 2^-22.6 absolute on [1, 2]) and 1.2e-7 on the derivative; the dds GELU uses
 // the Abramowitz-Stegun form of the tensor-core kernels (common.cuh, |error| <= 4.7e-7).
-__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 template <int ACT>
 __device__ __forceinline__ float bk_act(float x) {
     if constexpr (ACT == ACT_SOFTPLUS) {
-        const float e = ex2_ftz(-fabsf(x) * 1.4426950408889634f);
-        return fmaf(0.6931471805599453f, lg2_ftz(1.0f + e), fmaxf(x, 0.f));
+        return softplus_fast(x);   // common.cuh
     } else {
         return gelu_fast(x);
     }

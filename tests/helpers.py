@@ -21,6 +21,9 @@ CONFIGS = {
                          sigma=15.0, eps_schedule=None, clip=True, trainable=("eta", "gamma", "mgridref_y")),
     "Ckl_manygmm_geffner": dict(model="many_gmm", mode="MCD_CAIS_sn", N=300, K=16, nn_arch="geffner", emb_dim=130, eps=0.1,
                                 sigma=15.0, eps_schedule=None, clip=True, trainable=("eta", "gamma", "mgridref_y")),
+    # hidden_pad 144 (emb_dim 142 + d = 2): the 144-wide tensor-core tiles without padding columns; MCD_ULA_sn node form
+    "ULAsn_manygmm_e142": dict(model="many_gmm", mode="MCD_ULA_sn", N=300, K=12, nn_arch="geffner", emb_dim=142, eps=0.1,
+                               sigma=15.0, eps_schedule="cos_sq", clip=True, trainable=("eta", "gamma", "eps", "mgridref_y")),
     "ULA_gmm": dict(model="gmm", mode="MCD_ULA", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.01, sigma=1.0,
                     eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
     "ULAsn_funnel": dict(model="funnel", mode="MCD_ULA_sn", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.05, sigma=1.0,

@@ -286,7 +286,9 @@ def test_gradient_parity_readme_full_size(name):
 
 
 @pytest.mark.parametrize("name,N,K", [("C_manygmm_dds_small", 60000, 2), ("C_manygmm_dds_small", 60037, 3),
-                                      ("ULAsn_gmm_dds", 60000, 2), ("lin_funnel", 60000, 2), ("B_funnel", 60000, 2)])
+                                      ("ULAsn_gmm_dds", 60000, 2), ("lin_funnel", 60000, 2), ("B_funnel", 60000, 2),
+                                      # hidden_pad 136 on 144-wide tiles, one CTA per SM: 148 x 128 = 18 944 particles per wave
+                                      ("Ckl_manygmm_geffner", 40037, 2)])
 def test_tensor_core_path_several_tiles_per_cta(name, N, K):
     """More particles than one tile per CTA of the tcgen05 kernels (forward: 3 x 148 CTAs x 128 particles = 56 832; adjoint:
     148 CTAs x 256 = 37 888): the persistent tile loop, the mbarrier phase carried from tile to tile and the TMEM weight-gradient
