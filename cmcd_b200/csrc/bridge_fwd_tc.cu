@@ -27,19 +27,12 @@
 namespace cmcd {
 
 constexpr int TC_PB = 128;   // particles per CTA (TMEM lanes)
-// Two tile widths HT (the MMA's N and K): 64 (hidden_pad 64: dds, narrow geffner nets) and 144 (hidden_pad 129..144: the geffner
-// net of README.md:30,34, emb_dim 130 + d = 2 -> hidden_pad 136, zero-padded to the next multiple of 16).
-//   HT = 64 : TMEM 128 columns (accumulator D, A_hi as tf32) + 32 columns (A_lo as packed bf16 pairs) = 160 per CTA -> three CTAs per SM
-//   HT = 144: one 512-column allocation (D 144 | A_hi 144 | A_lo 72) and 203 KB of operand tiles -> one CTA per SM
-template <int HT>
-struct TcGeo {
-    static constexpr uint32_t COL_D = 0, COL_AH = HT, COL_LO = 2 * HT;
-    static constexpr uint32_t COLS_MAIN = HT == 64 ? 128 : 512, COLS_LO = 32;
-    static constexpr bool SPLIT_ALLOC = HT == 64;   // A_lo in its own 32-column allocation
-    static constexpr int B_BYTES = HT * HT * 4;     // one HT x HT fp32 operand tile
-    static constexpr int B16_BYTES = HT * HT * 2;   // the bf16 copy of B_hi for the A_lo pass
-    static constexpr int CTAS_PER_SM = HT == 64 ? 3 : 1;
-};
+constexpr int TC_H = 64;     // hidden width of this path
+// TMEM: 128 columns (accumulator D, A_hi as tf32) + 32 columns (A_lo as packed bf16 pairs) = 160 per CTA -> three CTAs per SM
+constexpr uint32_t TC_COL_D = 0, TC_COL_AH = 64, TC_COLS_MAIN = 128, TC_COLS_LO = 32;
+constexpr int TC_B_BYTES = TC_H * TC_H * 4;   // one 64x64 fp32 operand tile
+constexpr int TC_B16_BYTES = TC_H * TC_H * 2; // the bf16 copy of B_hi for the A_lo pass
+constexpr int TC_CTAS_PER_SM = 3;
 
 template <int D>
 struct TcCtx {
@@ -47,7 +40,6 @@ struct TcCtx {
     const float *c1, *c2, *c3;            // global per-step tables [T][64], [T][64], [T][D]
     const float* tab;                     // this warp's staged rows c1[t] | c2[t] of the current half-step (shared memory)
     float out_scale, out_clip;
-    int HP;                               // real row length of the tables (hidden_pad <= HT)
     uint32_t tmem_base, tmem_lane;        // main allocation (D | A_hi): base; base + this warp's lane quarter
     uint32_t tmem_lo_base, tmem_lo_lane;  // second allocation: A_lo as packed bf16 pairs
     uint64_t bhi, blo, bhi16;             // shared-memory descriptors of the B tiles (first K block)
@@ -55,7 +47,7 @@ struct TcCtx {
     uint64_t* mbar_ready;                 // A operand staged by all 128 threads
     uint32_t parity, parity_ready;
     // TMA staging of the table rows (a.tab_tma): CTA-shared double buffer, one mbarrier per buffer, phase bit per buffer
-    float* tab_shared;                    // [2][2 * HT]
+    float* tab_shared;                    // [2][2 * 64]
     uint64_t* tab_bar;                    // [2]
     uint32_t tab_parity;                  // bit b = phase of buffer b
     int tma;
@@ -74,10 +66,9 @@ __device__ __forceinline__ float gauss_logprob_tc(const float (&x)[D], const flo
 }
 
 // layer 1 -> TMEM A operand -> issue the MMA batch.  skipacc += a1 W3 (geffner residual), 0 otherwise.
-template <int D, int ACT, int HT>
+template <int D, int ACT>
 __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, int next_t, const float (&x)[D], float (&skipacc)[D]) {
     constexpr bool skip = (ACT == ACT_SOFTPLUS);
-    using G = TcGeo<HT>;
     const float4* __restrict__ c1v = reinterpret_cast<const float4*>(cx.tab);
     f32x2_t xb[D];
 #pragma unroll
@@ -85,7 +76,7 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, int next_t, co
 #pragma unroll
     for (int m = 0; m < D; ++m) skipacc[m] = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < HT / 16; ++c) {
+    for (int c = 0; c < 4; ++c) {
         uint32_t h[16], l[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -93,7 +84,7 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, int next_t, co
             f32x2_t p01 = pk2(cc.x, cc.y), p23 = pk2(cc.z, cc.w);   // two hidden units per FFMA2 (x broadcast pairs built once per node)
 #pragma unroll
             for (int a = 0; a < D; ++a) {
-                const float4 u = *reinterpret_cast<const float4*>(cx.sU1 + a * HT + c * 16 + q * 4);
+                const float4 u = *reinterpret_cast<const float4*>(cx.sU1 + a * TC_H + c * 16 + q * 4);
                 p01 = fma2(xb[a], pk2(u.x, u.y), p01);
                 p23 = fma2(xb[a], pk2(u.z, u.w), p23);
             }
@@ -125,7 +116,7 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, int next_t, co
             l[q * 2 + 0] = *reinterpret_cast<const uint32_t*>(&l01);
             l[q * 2 + 1] = *reinterpret_cast<const uint32_t*>(&l23);
         }
-        umma::tmem_st16(cx.tmem_lane + G::COL_AH + c * 16, h);
+        umma::tmem_st16(cx.tmem_lane + TC_COL_AH + c * 16, h);
         umma::tmem_st8(cx.tmem_lo_lane + c * 8, l);
     }
     umma::tmem_st_wait();
@@ -140,21 +131,20 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, int next_t, co
                 // every thread of the CTA has arrived for node t, i.e. is done with the rows of node t - 1: their buffer is free.
                 // One thread requests both rows of node t + 1 through the TMA engine (two 256-byte bulk copies, one mbarrier).
                 const int b = next_t & 1;
-                const uint32_t row = (uint32_t)(HT == 64 ? 64 : cx.HP) * sizeof(float);
-                umma::mbar_arrive_expect_tx(cx.tab_bar + b, 2 * row);
-                umma::bulk_copy_g2s(cx.tab_shared + b * (2 * HT), cx.c1 + (size_t)next_t * (HT == 64 ? 64 : cx.HP), row, cx.tab_bar + b);
-                umma::bulk_copy_g2s(cx.tab_shared + b * (2 * HT) + HT, cx.c2 + (size_t)next_t * (HT == 64 ? 64 : cx.HP), row, cx.tab_bar + b);
+                umma::mbar_arrive_expect_tx(cx.tab_bar + b, 2 * TC_H * sizeof(float));
+                umma::bulk_copy_g2s(cx.tab_shared + b * (2 * TC_H), cx.c1 + (size_t)next_t * TC_H, TC_H * sizeof(float), cx.tab_bar + b);
+                umma::bulk_copy_g2s(cx.tab_shared + b * (2 * TC_H) + TC_H, cx.c2 + (size_t)next_t * TC_H, TC_H * sizeof(float), cx.tab_bar + b);
             }
-            const uint32_t idesc = umma::make_idesc_tf32(128, HT), idesc16 = umma::make_idesc_bf16_k(128, HT);
-            const uint32_t dcol = cx.tmem_base + G::COL_D, ahi = cx.tmem_base + G::COL_AH;
+            const uint32_t idesc = umma::make_idesc_tf32(128, TC_H), idesc16 = umma::make_idesc_bf16_k(128, TC_H);
+            const uint32_t dcol = cx.tmem_base + TC_COL_D, ahi = cx.tmem_base + TC_COL_AH;
             // D = A_hi B_lo + A_lo B_hi + A_hi B_hi, small terms first: the fp32 accumulator truncates on every accumulate
             // (tools/umma_probe2.cu, test 3).  Next K block of a B tile: +256 B = +16 in the descriptor's address field.
 #pragma unroll
-            for (int k = 0; k < HT / 8; ++k) umma::mma_tf32_ts(dcol, ahi + k * 8, cx.blo + (uint64_t)(k * 16), idesc, k > 0);
+            for (int k = 0; k < 8; ++k) umma::mma_tf32_ts(dcol, ahi + k * 8, cx.blo + (uint64_t)(k * 16), idesc, k > 0);
 #pragma unroll
-            for (int k = 0; k < HT / 16; ++k) umma::mma_f16_ts(dcol, cx.tmem_lo_base + k * 8, cx.bhi16 + (uint64_t)(k * 16), idesc16, 1);
+            for (int k = 0; k < 4; ++k) umma::mma_f16_ts(dcol, cx.tmem_lo_base + k * 8, cx.bhi16 + (uint64_t)(k * 16), idesc16, 1);
 #pragma unroll
-            for (int k = 0; k < HT / 8; ++k) umma::mma_tf32_ts(dcol, ahi + k * 8, cx.bhi + (uint64_t)(k * 16), idesc, 1);
+            for (int k = 0; k < 8; ++k) umma::mma_tf32_ts(dcol, ahi + k * 8, cx.bhi + (uint64_t)(k * 16), idesc, 1);
             umma::commit(cx.mbar);
         }
         __syncwarp();
@@ -162,7 +152,7 @@ __device__ __forceinline__ void tc_net_issue(TcCtx<D>& cx, int t, int next_t, co
 }
 
 // wait for the MMA batch, epilogue: out = out_scale * clamp(W3^T (act(D + c2[t] + U2^T x) [+ a1]) + U3^T x + c3[t])
-template <int D, int ACT, int HT>
+template <int D, int ACT>
 __device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (&x)[D], const float (&skipacc)[D], float (&out)[D]) {
     constexpr bool has_u = (ACT == ACT_SOFTPLUS);   // geffner: U2, U3 present
     float o[D];
@@ -175,8 +165,7 @@ __device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (
         }
         o[m] = p;
     }
-    using G = TcGeo<HT>;
-    const float4* __restrict__ c2v = reinterpret_cast<const float4*>(cx.tab + HT);
+    const float4* __restrict__ c2v = reinterpret_cast<const float4*>(cx.tab + TC_H);
     f32x2_t O2[D];                        // dds: output-layer partial sums over (even, odd) hidden units
 #pragma unroll
     for (int m = 0; m < D; ++m) O2[m] = pk2(0.f, 0.f);
@@ -184,9 +173,9 @@ __device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (
     cx.parity ^= 1u;
     umma::fence_after();
 #pragma unroll 1
-    for (int c = 0; c < HT / 16; ++c) {
+    for (int c = 0; c < 4; ++c) {
         uint32_t v[16];
-        umma::tmem_ld16(cx.tmem_lane + G::COL_D + c * 16, v);
+        umma::tmem_ld16(cx.tmem_lane + TC_COL_D + c * 16, v);
         umma::tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -199,7 +188,7 @@ __device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (
                 const f32x2_t A01 = gelu_fast2(p0, p1), A23 = gelu_fast2(p2, p3);
 #pragma unroll
                 for (int m = 0; m < D; ++m) {
-                    const float4 w = *reinterpret_cast<const float4*>(cx.sW3T + m * HT + c * 16 + q * 4);
+                    const float4 w = *reinterpret_cast<const float4*>(cx.sW3T + m * TC_H + c * 16 + q * 4);
                     O2[m] = fma2(A01, pk2(w.x, w.y), O2[m]);
                     O2[m] = fma2(A23, pk2(w.z, w.w), O2[m]);
                 }
@@ -209,7 +198,7 @@ __device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (
                 if (has_u) {
 #pragma unroll
                     for (int a = 0; a < D; ++a) {
-                        const float4 u = *reinterpret_cast<const float4*>(cx.sU2 + a * HT + c * 16 + q * 4);
+                        const float4 u = *reinterpret_cast<const float4*>(cx.sU2 + a * TC_H + c * 16 + q * 4);
                         p[0] = fmaf(x[a], u.x, p[0]); p[1] = fmaf(x[a], u.y, p[1]);
                         p[2] = fmaf(x[a], u.z, p[2]); p[3] = fmaf(x[a], u.w, p[3]);
                     }
@@ -237,75 +226,55 @@ __device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (
     for (int m = 0; m < D; ++m) out[m] = cx.out_scale * fminf(fmaxf(o[m], -cx.out_clip), cx.out_clip);
 }
 
-template <int D, int ACT, int HT>
-__global__ void __launch_bounds__(TC_PB, TcGeo<HT>::CTAS_PER_SM) bridge_fwd_tc_kernel(const BridgeArgs a) {
-    using G = TcGeo<HT>;
+template <int D, int ACT>
+__global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(const BridgeArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t tmem_slot, tmem_slot_lo;
     __shared__ __align__(8) uint64_t mbar, mbar_ready, tab_bar[2];
-    __shared__ __align__(128) float tab_shared[2][2 * HT];
+    __shared__ __align__(128) float tab_shared[2][2 * TC_H];
     const int tid = threadIdx.x, warp = tid >> 5;
     const NetView& nv = a.net;
-    // rows of the network arrays are HP long (HT = 64: HP = 64, a compile-time constant); columns HP..HT-1 of every staged copy are zero
-    const int HP = HT == 64 ? 64 : nv.HP;
     uint8_t* sBhi = smem_raw;
-    uint8_t* sBlo = smem_raw + G::B_BYTES;
-    uint8_t* sBhi16 = smem_raw + 2 * G::B_BYTES;
-    float* sf = reinterpret_cast<float*>(smem_raw + 2 * G::B_BYTES + G::B16_BYTES);
+    uint8_t* sBlo = smem_raw + TC_B_BYTES;
+    uint8_t* sBhi16 = smem_raw + 2 * TC_B_BYTES;
+    float* sf = reinterpret_cast<float*>(smem_raw + 2 * TC_B_BYTES + TC_B16_BYTES);
     float* sU1 = sf;
-    float* sU2 = sU1 + D * HT;
-    float* sW3 = sU2 + D * HT;
-    float* sU3 = sW3 + HT * D;
+    float* sU2 = sU1 + D * TC_H;
+    float* sW3 = sU2 + D * TC_H;
+    float* sU3 = sW3 + TC_H * D;
     float* sW3T = sU3 + ((D * D + 3) & ~3);
-    float* sTp = sW3T + D * HT;
+    float* sTp = sW3T + D * TC_H;
     // B[n = j][k = i] = W2[i][j], split into tf32 hi / lo
-    for (int idx = tid; idx < HT * HT; idx += TC_PB) {
-        const int i = idx / HT, j = idx % HT;
+    for (int idx = tid; idx < TC_H * TC_H; idx += TC_PB) {
+        const int i = idx / TC_H, j = idx % TC_H;
         float hi, lo;
-        umma::split_tf32((i < HP && j < HP) ? nv.W2[i * HP + j] : 0.f, hi, lo);
-        const int off = umma::core_off(j, i, HT);
+        umma::split_tf32(nv.W2[idx], hi, lo);
+        const int off = umma::core_off(j, i, TC_H);
         *reinterpret_cast<float*>(sBhi + off) = hi;
         *reinterpret_cast<float*>(sBlo + off) = lo;
-        *reinterpret_cast<__nv_bfloat16*>(sBhi16 + umma::core_off16(j, i, HT)) = __float2bfloat16(hi);
+        *reinterpret_cast<__nv_bfloat16*>(sBhi16 + umma::core_off16(j, i, TC_H)) = __float2bfloat16(hi);
     }
-    for (int idx = tid; idx < D * HT; idx += TC_PB) {
-        const int r = idx / HT, j = idx % HT;
-        sU1[idx] = j < HP ? nv.U1[r * HP + j] : 0.f;
-        sU2[idx] = (nv.U2 && j < HP) ? nv.U2[r * HP + j] : 0.f;
-    }
-    for (int idx = tid; idx < HT * D; idx += TC_PB) {
-        const int j = idx / D, m = idx % D;
-        const float w3 = j < HP ? nv.W3[idx] : 0.f;   // padded hidden units: act(0) != 0 for softplus, their output weights are 0
-        sW3[idx] = w3;
-        sW3T[m * HT + j] = w3;
-    }
+    for (int i = tid; i < D * TC_H; i += TC_PB) { sU1[i] = nv.U1[i]; sU2[i] = nv.U2 ? nv.U2[i] : 0.f; }
+    for (int i = tid; i < TC_H * D; i += TC_PB) { sW3[i] = nv.W3[i]; sW3T[(i % D) * TC_H + i / D] = nv.W3[i]; }
     for (int i = tid; i < D * D; i += TC_PB) sU3[i] = nv.U3 ? nv.U3[i] : 0.f;
     const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
     for (int i = tid; i < ntp; i += TC_PB) sTp[i] = a.tgt.mix[i];
     float2* sMu = reinterpret_cast<float2*>(sTp + MIX_MAX * MIX_STRIDE);   // many_gmm: dense component means
-    // per-warp double buffer for the per-step table rows c1[t] | c2[t] (cp.async one half-step ahead); rows padded to HT
-    float* sTab = reinterpret_cast<float*>(sMu + MIX_MAX) + warp * (2 * 2 * HT);
+    // per-warp double buffer for the per-step table rows c1[t] | c2[t] (cp.async one half-step ahead)
+    float* sTab = reinterpret_cast<float*>(sMu + MIX_MAX) + warp * (2 * 2 * TC_H);
     const int lane_ = tid & 31;
-    for (int i = lane_; i < 2 * 2 * HT; i += 32) sTab[i] = 0.f;
-    for (int i = tid; i < 2 * 2 * HT; i += TC_PB) (&tab_shared[0][0])[i] = 0.f;
-    auto stage_tab = [&](int t, int buf) {   // 16-byte chunks of the c1 row then the c2 row (HT = 64: one per lane)
-        const int rc = HP >> 2;              // chunks per row
-        for (int ch = lane_; ch < 2 * rc; ch += 32) {
-            const int second = ch >= rc, o = (second ? ch - rc : ch) * 4;
-            umma::cp_async16(sTab + buf * (2 * HT) + second * HT + o, (second ? nv.c2 : nv.c1) + (size_t)t * HP + o);
-        }
+    auto stage_tab = [&](int t, int buf) {   // 32 lanes x 16 B = c1 row (256 B) + c2 row (256 B)
+        const float* src = (lane_ < 16 ? nv.c1 : nv.c2) + (size_t)t * TC_H + (lane_ & 15) * 4;
+        umma::cp_async16(sTab + buf * (2 * TC_H) + lane_ * 4, src);
         umma::cp_async_commit();
     };
     const bool fast_gmm = (D == 2) && (a.tgt.kind == TGT_MANY_GMM);
     if (fast_gmm)
         many_gmm_stage_means(a.tgt, sMu, tid, TC_PB);
     const ManyGmmConst gc = many_gmm_const(a.tgt);
-    if (warp == 0) {
-        umma::tmem_alloc(&tmem_slot, G::COLS_MAIN, !G::SPLIT_ALLOC);
-        if (G::SPLIT_ALLOC) umma::tmem_alloc(&tmem_slot_lo, G::COLS_LO, true);
-    }
+    if (warp == 0) { umma::tmem_alloc(&tmem_slot, TC_COLS_MAIN, false); umma::tmem_alloc(&tmem_slot_lo, TC_COLS_LO, true); }
     if (tid == 0) { umma::mbar_init(&mbar, 1); umma::mbar_init(&mbar_ready, TC_PB); umma::mbar_init(&tab_bar[0], 1); umma::mbar_init(&tab_bar[1], 1); }
-    umma::fence_async_smem();   // generic-proxy writes of the B tiles (and the zeroed table buffers) -> visible to the async proxy
+    umma::fence_async_smem();   // generic-proxy writes of the B tiles -> visible to the tensor core (async proxy)
     umma::fence_before();
     __syncthreads();
     umma::fence_after();
@@ -314,14 +283,13 @@ __global__ void __launch_bounds__(TC_PB, TcGeo<HT>::CTAS_PER_SM) bridge_fwd_tc_k
     cx.sU1 = sU1; cx.sU2 = sU2; cx.sW3 = sW3; cx.sU3 = sU3; cx.sW3T = sW3T;
     cx.c1 = nv.c1; cx.c2 = nv.c2; cx.c3 = nv.c3;
     cx.out_scale = net_out_scale(nv); cx.out_clip = nv.out_clip;
-    cx.HP = HP;
     cx.tmem_base = tmem_slot;
     cx.tmem_lane = tmem_slot + ((uint32_t)(warp * 32) << 16);
-    cx.tmem_lo_base = G::SPLIT_ALLOC ? tmem_slot_lo : tmem_slot + G::COL_LO;
-    cx.tmem_lo_lane = cx.tmem_lo_base + ((uint32_t)(warp * 32) << 16);
-    cx.bhi16 = umma::make_desc(umma::smem_u32(sBhi16), 128, 16 * HT);
-    cx.bhi = umma::make_desc(umma::smem_u32(sBhi), 128, 32 * HT);
-    cx.blo = umma::make_desc(umma::smem_u32(sBlo), 128, 32 * HT);
+    cx.tmem_lo_base = tmem_slot_lo;
+    cx.tmem_lo_lane = tmem_slot_lo + ((uint32_t)(warp * 32) << 16);
+    cx.bhi16 = umma::make_desc(umma::smem_u32(sBhi16), 128, 16 * TC_H);
+    cx.bhi = umma::make_desc(umma::smem_u32(sBhi), 128, 32 * TC_H);
+    cx.blo = umma::make_desc(umma::smem_u32(sBlo), 128, 32 * TC_H);
     cx.mbar = &mbar; cx.parity = 0u;
     cx.mbar_ready = &mbar_ready; cx.parity_ready = 0u;
     cx.tab_shared = &tab_shared[0][0]; cx.tab_bar = tab_bar; cx.tab_parity = 0u; cx.tma = a.tab_tma;
@@ -374,10 +342,9 @@ __global__ void __launch_bounds__(TC_PB, TcGeo<HT>::CTAS_PER_SM) bridge_fwd_tc_k
             if (cx.tma) {
                 __syncthreads();              // the previous tile's last node may still be reading buffer 0 in a lagging warp
                 if (tid == 0) {
-                    const uint32_t row = (uint32_t)HP * sizeof(float);
-                    umma::mbar_arrive_expect_tx(&tab_bar[0], 2 * row);
-                    umma::bulk_copy_g2s(&tab_shared[0][0], nv.c1, row, &tab_bar[0]);
-                    umma::bulk_copy_g2s(&tab_shared[0][HT], nv.c2, row, &tab_bar[0]);
+                    umma::mbar_arrive_expect_tx(&tab_bar[0], 2 * TC_H * sizeof(float));
+                    umma::bulk_copy_g2s(&tab_shared[0][0], nv.c1, TC_H * sizeof(float), &tab_bar[0]);
+                    umma::bulk_copy_g2s(&tab_shared[0][TC_H], nv.c2, TC_H * sizeof(float), &tab_bar[0]);
                 }
             } else stage_tab(0, 0);
         }
@@ -398,10 +365,10 @@ __global__ void __launch_bounds__(TC_PB, TcGeo<HT>::CTAS_PER_SM) bridge_fwd_tc_k
                 } else {
                     umma::cp_async_wait_all();
                     __syncwarp();
-                    cx.tab = sTab + (t & 1) * (2 * HT);
+                    cx.tab = sTab + (t & 1) * (2 * TC_H);
                     if (nd < K) stage_tab(t + 1, (t + 1) & 1);
                 }
-                tc_net_issue<D, ACT, HT>(cx, t, nd < K ? t + 1 : -1, x, skipacc);
+                tc_net_issue<D, ACT>(cx, t, nd < K ? t + 1 : -1, x, skipacc);
             }
             // ---- work that does not depend on the network output overlaps the MMA batch ----
             if (fast_gmm) { float d0, d1; lp = many_gmm_eval<false>(gc, sMu, x[0], x[1], sp[0], sp[1], 0.f, 0.f, d0, d1); }
@@ -416,7 +383,7 @@ __global__ void __launch_bounds__(TC_PB, TcGeo<HT>::CTAS_PER_SM) bridge_fwd_tc_k
             if (nd < K) step_keys_and_normal<D>(k, xi);   // split + Gaussian + key advance of step nd (two interleaved threefry batches)
 #pragma unroll
             for (int j = 0; j < D; ++j) nnv[j] = 0.f;
-            if (use_nn) tc_net_finish<D, ACT, HT>(cx, t, x, skipacc, nnv);
+            if (use_nn) tc_net_finish<D, ACT>(cx, t, x, skipacc, nnv);
             if (nd > 0) {   // backward kernel of step nd - 1 (beta, eps, scale, mf still hold that step's values), weight update
                 float mb[D];
 #pragma unroll
@@ -458,26 +425,22 @@ __global__ void __launch_bounds__(TC_PB, TcGeo<HT>::CTAS_PER_SM) bridge_fwd_tc_k
     }
     umma::fence_before();
     __syncthreads();
-    if (warp == 0) {
-        umma::tmem_dealloc(cx.tmem_base, G::COLS_MAIN);
-        if (G::SPLIT_ALLOC) umma::tmem_dealloc(cx.tmem_lo_base, G::COLS_LO);
-    }
+    if (warp == 0) { umma::tmem_dealloc(cx.tmem_base, TC_COLS_MAIN); umma::tmem_dealloc(cx.tmem_lo_base, TC_COLS_LO); }
 }
 
-template <int D, int ACT, int HT>
+template <int D, int ACT>
 static int launch_fwd_tc_t(const BridgeArgs& a_in, cudaStream_t st, int num_sms) {
-    using G = TcGeo<HT>;
-    size_t smem = 2 * G::B_BYTES + G::B16_BYTES + (2 * D * HT + 2 * HT * D + D * D + 4 + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 4 * 4 * HT + 8) * sizeof(float);
-    // HT = 64: request > 227/4 KB so that at most three CTAs (3 x 160 TMEM columns) share an SM
+    // request > 227/4 KB so that at most three CTAs (3 x 160 TMEM columns) share an SM
+    size_t smem = 2 * TC_B_BYTES + TC_B16_BYTES + (2 * D * TC_H + 2 * TC_H * D + D * D + 4 + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 4 * 4 * TC_H + 8) * sizeof(float);
     if (smem < 58 * 1024) smem = 58 * 1024;
-    auto kern = bridge_fwd_tc_kernel<D, ACT, HT>;
+    auto kern = bridge_fwd_tc_kernel<D, ACT>;
     CMCD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // TMA bulk copies need 16-byte aligned rows; CMCD_TAB_TMA=0 keeps the per-warp cp.async staging (A/B runs)
     BridgeArgs a = a_in;
     const char* env = std::getenv("CMCD_TAB_TMA");
     a.tab_tma = (!env || env[0] != '0') && !((reinterpret_cast<uintptr_t>(a.net.c1) | reinterpret_cast<uintptr_t>(a.net.c2)) & 15);
     const long long ntiles = (a.N + TC_PB - 1) / TC_PB;
-    long long grid = (long long)G::CTAS_PER_SM * num_sms;
+    long long grid = (long long)TC_CTAS_PER_SM * num_sms;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, TC_PB, smem, st>>>(a);
@@ -485,22 +448,15 @@ static int launch_fwd_tc_t(const BridgeArgs& a_in, cudaStream_t st, int num_sms)
     return 0;
 }
 
-// hidden_pad == 64 networks (dds; geffner with x_dim + emb_dim in 57..64) at d = 2 / 10, and the geffner net of README.md:30,34
-// (hidden_pad 129..144, d = 2) on 144-wide tiles; K >= 1 and a network in use.  CMCD_TC_WIDE=0 keeps the wide net on the FP32 paths.
-static bool fwd_tc_wide(const BridgeArgs& a, int D) {
-    const char* env = std::getenv("CMCD_TC_WIDE");
-    return D == 2 && a.net.arch == CMCD_ARCH_GEFFNER && a.net.HP > 128 && a.net.HP <= 144 && !(a.net.HP & 3) && env && env[0] == '1';
-}
+// hidden_pad == 64 networks (dds; geffner with x_dim + emb_dim in 57..64); K >= 1 and a network in use
 bool fwd_tc_supported(const BridgeArgs& a, int D) {
-    if (a.net.arch == CMCD_ARCH_NONE || a.K < 1 || a.mode == CMCD_MODE_ULA) return false;
-    return (a.net.HP == 64 && (D == 2 || D == 10)) || fwd_tc_wide(a, D);
+    return a.net.arch != CMCD_ARCH_NONE && a.net.HP == TC_H && a.K >= 1 && a.mode != CMCD_MODE_ULA && (D == 2 || D == 10);
 }
 
 int launch_bridge_fwd_tc(const BridgeArgs& a, int D, cudaStream_t st, int num_sms) {
     const bool dds = a.net.arch == CMCD_ARCH_DDS;
-    if (fwd_tc_wide(a, D)) return launch_fwd_tc_t<2, ACT_SOFTPLUS, 144>(a, st, num_sms);
-    if (D == 2) return dds ? launch_fwd_tc_t<2, ACT_GELU, 64>(a, st, num_sms) : launch_fwd_tc_t<2, ACT_SOFTPLUS, 64>(a, st, num_sms);
-    if (D == 10) return dds ? launch_fwd_tc_t<10, ACT_GELU, 64>(a, st, num_sms) : launch_fwd_tc_t<10, ACT_SOFTPLUS, 64>(a, st, num_sms);
+    if (D == 2) return dds ? launch_fwd_tc_t<2, ACT_GELU>(a, st, num_sms) : launch_fwd_tc_t<2, ACT_SOFTPLUS>(a, st, num_sms);
+    if (D == 10) return dds ? launch_fwd_tc_t<10, ACT_GELU>(a, st, num_sms) : launch_fwd_tc_t<10, ACT_SOFTPLUS>(a, st, num_sms);
     set_error("bridge_fwd_tc: dim=%d has no instantiation", D);
     return 2;
 }

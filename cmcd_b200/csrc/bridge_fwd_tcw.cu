@@ -41,7 +41,7 @@ __device__ __forceinline__ int tw_chunk_end(int g) { return g == 3 ? 9 : 2 * g +
 
 template <int D>
 struct TwCtx {
-    const float *sU1, *sU2, *sW3, *sU3;   // shared memory, rows padded to TW_H with zeros
+    const float *sU1, *sU2, *sW3T, *sU3;  // shared memory, rows padded to TW_H with zeros; sW3T = W3 transposed, [D][TW_H]
     const float *c1, *c2, *c3;            // global per-step tables [T][HP], [T][HP], [T][D]
     const float* tab;                     // staged rows c1[t] | c2[t] of the current node (shared memory)
     float out_scale, out_clip;
@@ -73,7 +73,7 @@ __device__ __forceinline__ void tw_quad_sync(int warp) {   // warps w, w + 4, w 
 // one 16-unit chunk of layer 1: a1 = softplus(U1^T x + c1[t]) -> tf32 hi (16 columns) + bf16 lo (8 packed columns) of the thread's
 // TMEM lane; acc += a1 W3 (residual skip, nn.py:70)
 template <int D>
-__device__ __forceinline__ void tw_layer1_chunk(const TwCtx<D>& cx, int c, const f32x2_t (&xb)[D], float (&acc)[D]) {
+__device__ __forceinline__ void tw_layer1_chunk(const TwCtx<D>& cx, int c, const f32x2_t (&xb)[D], f32x2_t (&acc)[D]) {
     const float4* __restrict__ c1v = reinterpret_cast<const float4*>(cx.tab);
     uint32_t h[16], l[8];
 #pragma unroll
@@ -86,17 +86,20 @@ __device__ __forceinline__ void tw_layer1_chunk(const TwCtx<D>& cx, int c, const
             p01 = fma2(xb[a], pk2(u.x, u.y), p01);
             p23 = fma2(xb[a], pk2(u.z, u.w), p23);
         }
-        float p[4], lov[4];
+        float p[4], av[4], lov[4];
         upk2(p01, p[0], p[1]); upk2(p23, p[2], p[3]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float a1 = softplus_fast(p[e]);
-            const int j = c * 16 + q * 4 + e;
-#pragma unroll
-            for (int m = 0; m < D; ++m) acc[m] = fmaf(a1, cx.sW3[j * D + m], acc[m]);
+            av[e] = softplus_fast(p[e]);
             float hi;
-            umma::split_tf32(a1, hi, lov[e]);
+            umma::split_tf32(av[e], hi, lov[e]);
             h[q * 4 + e] = __float_as_uint(hi);
+        }
+#pragma unroll
+        for (int m = 0; m < D; ++m) {   // acc[m] = (sum over even units, sum over odd units) of a1 W3[., m]
+            const float4 w = *reinterpret_cast<const float4*>(cx.sW3T + m * TW_H + c * 16 + q * 4);
+            acc[m] = fma2(pk2(av[0], av[1]), pk2(w.x, w.y), acc[m]);
+            acc[m] = fma2(pk2(av[2], av[3]), pk2(w.z, w.w), acc[m]);
         }
         const __nv_bfloat162 l01 = __floats2bfloat162_rn(lov[0], lov[1]), l23 = __floats2bfloat162_rn(lov[2], lov[3]);
         l[q * 2 + 0] = *reinterpret_cast<const uint32_t*>(&l01);
@@ -140,7 +143,7 @@ __device__ __forceinline__ void tw_issue_half(uint32_t tmem_base, uint64_t bhi, 
 
 // one stage of layer 1; warp 0 issues the stage's MMAs once all 512 threads have stored theirs
 template <int D, int STAGE>
-__device__ __forceinline__ void tw_stage(TwCtx<D>& cx, int next_t, const f32x2_t (&xb)[D], float (&acc)[D]) {
+__device__ __forceinline__ void tw_stage(TwCtx<D>& cx, int next_t, const f32x2_t (&xb)[D], f32x2_t (&acc)[D]) {
     const int cb = STAGE ? tw_chunk_split(cx.grp) : tw_chunk_begin(cx.grp);
     const int ce = STAGE ? tw_chunk_end(cx.grp) : tw_chunk_split(cx.grp);
 #pragma unroll 1
@@ -170,21 +173,21 @@ __device__ __forceinline__ void tw_stage(TwCtx<D>& cx, int next_t, const f32x2_t
     }
 }
 
-// layer 1 of this thread's units in two stages.  acc receives this group's share of a1 W3.
+// layer 1 of this thread's units in two stages.  acc receives this group's share of a1 W3 (as even / odd unit partial sums).
 template <int D>
-__device__ __forceinline__ void tw_net_issue(TwCtx<D>& cx, int next_t, const float (&x)[D], float (&acc)[D]) {
+__device__ __forceinline__ void tw_net_issue(TwCtx<D>& cx, int next_t, const float (&x)[D], f32x2_t (&acc)[D]) {
     f32x2_t xb[D];
 #pragma unroll
     for (int a = 0; a < D; ++a) xb[a] = pk2(x[a], x[a]);
 #pragma unroll
-    for (int m = 0; m < D; ++m) acc[m] = 0.f;
+    for (int m = 0; m < D; ++m) acc[m] = pk2(0.f, 0.f);
     tw_stage<D, 0>(cx, next_t, xb, acc);
     tw_stage<D, 1>(cx, next_t, xb, acc);
 }
 
 // wait for this group's half of the MMA, epilogue over its units: acc += W3^T softplus(D + c2[t] + U2^T x)
 template <int D>
-__device__ __forceinline__ void tw_net_finish(TwCtx<D>& cx, const float (&x)[D], float (&acc)[D]) {
+__device__ __forceinline__ void tw_net_finish(TwCtx<D>& cx, const float (&x)[D], f32x2_t (&acc)[D]) {
     const float4* __restrict__ c2v = reinterpret_cast<const float4*>(cx.tab + TW_H);
     const int cb = tw_chunk_begin(cx.grp), ce = tw_chunk_end(cx.grp);
     umma::mbar_wait(cx.mbar_done + (cx.grp >> 1), cx.parity);
@@ -207,14 +210,15 @@ __device__ __forceinline__ void tw_net_finish(TwCtx<D>& cx, const float (&x)[D],
                 p01 = fma2(xa, pk2(u.x, u.y), p01);
                 p23 = fma2(xa, pk2(u.z, u.w), p23);
             }
-            float p[4];
+            float p[4], av[4];
             upk2(p01, p[0], p[1]); upk2(p23, p[2], p[3]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float av = softplus_fast(p[e]);
-                const int j = c * 16 + q * 4 + e;
+            for (int e = 0; e < 4; ++e) av[e] = softplus_fast(p[e]);
 #pragma unroll
-                for (int m = 0; m < D; ++m) acc[m] = fmaf(av, cx.sW3[j * D + m], acc[m]);
+            for (int m = 0; m < D; ++m) {
+                const float4 w = *reinterpret_cast<const float4*>(cx.sW3T + m * TW_H + c * 16 + q * 4);
+                acc[m] = fma2(pk2(av[0], av[1]), pk2(w.x, w.y), acc[m]);
+                acc[m] = fma2(pk2(av[2], av[3]), pk2(w.z, w.w), acc[m]);
             }
         }
     }
@@ -239,8 +243,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) bridge_fwd_tcw_kernel(const Bri
     float* sf = reinterpret_cast<float*>(smem_raw + 2 * TW_B_BYTES + TW_B16_BYTES);
     float* sU1 = sf;
     float* sU2 = sU1 + D * TW_H;
-    float* sW3 = sU2 + D * TW_H;
-    float* sU3 = sW3 + TW_H * D;
+    float* sW3T = sU2 + D * TW_H;
+    float* sU3 = sW3T + TW_H * D;
     float* sTp = sU3 + ((D * D + 3) & ~3);
     // B[n = j][k = i] = W2[i][j], split into tf32 hi / lo
     for (int base = 0; base < TW_H * TW_H; base += 8 * TW_THREADS) {   // eight loads in flight per thread
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) bridge_fwd_tcw_kernel(const Bri
         sU2[idx] = (nv.U2 && j < HP) ? nv.U2[r * HP + j] : 0.f;
     }
     // padded hidden units: softplus(0) != 0, their output weights are 0
-    for (int idx = tid; idx < TW_H * D; idx += TW_THREADS) sW3[idx] = idx < HP * D ? nv.W3[idx] : 0.f;
+    for (int idx = tid; idx < TW_H * D; idx += TW_THREADS) sW3T[(idx % D) * TW_H + idx / D] = idx < HP * D ? nv.W3[idx] : 0.f;
     for (int i = tid; i < D * D; i += TW_THREADS) sU3[i] = nv.U3 ? nv.U3[i] : 0.f;
     const int ntp = (a.tgt.kind == TGT_GMM || a.tgt.kind == TGT_MANY_GMM) ? a.tgt.ncomp * MIX_STRIDE : 0;
     for (int i = tid; i < ntp; i += TW_THREADS) sTp[i] = a.tgt.mix[i];
@@ -288,7 +292,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) bridge_fwd_tcw_kernel(const Bri
     umma::fence_after();
 
     TwCtx<D> cx;
-    cx.sU1 = sU1; cx.sU2 = sU2; cx.sW3 = sW3; cx.sU3 = sU3;
+    cx.sU1 = sU1; cx.sU2 = sU2; cx.sW3T = sW3T; cx.sU3 = sU3;
     cx.c1 = nv.c1; cx.c2 = nv.c2; cx.c3 = nv.c3;
     cx.out_scale = net_out_scale(nv); cx.out_clip = nv.out_clip;
     cx.HP = HP; cx.grp = grp;
@@ -358,7 +362,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) bridge_fwd_tcw_kernel(const Bri
         for (int nd = 0; nd <= K; ++nd) {
             const int t = t0 + nd;
             const bool use_nn = cais || nd > 0;
-            float acc[D], c3v[D];
+            f32x2_t acc[D];
+            float c3v[D];
             if (grp == 0) {
 #pragma unroll
                 for (int j = 0; j < D; ++j) sX[pl * D + j] = x[j];
@@ -391,7 +396,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) bridge_fwd_tcw_kernel(const Bri
                         float p = c3v[m];
 #pragma unroll
                         for (int q = 0; q < D; ++q) p = fmaf(x[q], sU3[q * D + m], p);
-                        acc[m] += p;
+                        acc[m] = add2(acc[m], pk2(p, 0.f));
                     }
                 }
             } else if (grp == 1) {
@@ -413,7 +418,11 @@ __global__ void __launch_bounds__(TW_THREADS, 1) bridge_fwd_tcw_kernel(const Bri
                 tw_net_finish<D>(cx, x, acc);
                 if (grp != 0) {
 #pragma unroll
-                    for (int j = 0; j < D; ++j) sO[((grp - 1) * TW_PB + pl) * D + j] = acc[j];
+                    for (int j = 0; j < D; ++j) {
+                        float e0, e1;
+                        upk2(acc[j], e0, e1);
+                        sO[((grp - 1) * TW_PB + pl) * D + j] = e0 + e1;
+                    }
                 }
             }
             tw_quad_sync(warp);                      // partial outputs, Gaussians and target score handed to group 0
@@ -423,7 +432,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) bridge_fwd_tcw_kernel(const Bri
             for (int m = 0; m < D; ++m) {
                 nnv[m] = 0.f;
                 if (use_nn) {
-                    float o = acc[m];
+                    float o, o1;
+                    upk2(acc[m], o, o1);
+                    o += o1;
 #pragma unroll
                     for (int g = 0; g < TW_G - 1; ++g) o += sO[(g * TW_PB + pl) * D + m];
                     nnv[m] = cx.out_scale * fminf(fmaxf(o, -cx.out_clip), cx.out_clip);
@@ -484,7 +495,7 @@ static size_t tw_smem_bytes(int D) {
 // MCD_ULA_sn), 16-byte aligned table rows for the bulk copies.  CMCD_TC_WIDE=0 keeps the FP32 mappings (A/B runs, tests).
 bool fwd_tcw_supported(const BridgeArgs& a, int D) {
     const char* env = std::getenv("CMCD_TC_WIDE");
-    if (env && (env[0] == '0' || env[0] == '1')) return false;   // 0: FP32 mappings; 1: one thread per particle on 144-wide tiles
+    if (env && env[0] == '0') return false;
     if (D != 2 || a.net.arch != CMCD_ARCH_GEFFNER || a.K < 1 || a.mode == CMCD_MODE_ULA) return false;
     if (a.net.HP <= 128 || a.net.HP > TW_H || (a.net.HP & 3)) return false;
     return !((reinterpret_cast<uintptr_t>(a.net.c1) | reinterpret_cast<uintptr_t>(a.net.c2)) & 15);

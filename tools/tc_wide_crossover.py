@@ -32,7 +32,7 @@ for name, N, K in RUNS:
     gl = PM.grad_and_loss(lambda *a: bound(*a, **kw))
     seeds = torch.from_numpy(seeds_for(N)).cuda()
     row = dict(config=name, N=N, K=K, hidden_pad=fixed[3].hidden_pad)
-    for tag, env in (("tc144_4thr", None), ("tc144_1thr", "1"), ("fp32", "0")):
+    for tag, env in (("tc144", None), ("fp32", "0")):
         os.environ.pop("CMCD_TC_WIDE", None)
         if env is not None:
             os.environ["CMCD_TC_WIDE"] = env
