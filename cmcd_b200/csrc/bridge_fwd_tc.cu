@@ -226,7 +226,7 @@ __device__ __forceinline__ void tc_net_finish(TcCtx<D>& cx, int t, const float (
     for (int m = 0; m < D; ++m) out[m] = cx.out_scale * fminf(fmaxf(o[m], -cx.out_clip), cx.out_clip);
 }
 
-template <int D, int ACT>
+template <int D, int ACT, bool EV>
 __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(const BridgeArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t tmem_slot, tmem_slot_lo;
@@ -308,13 +308,18 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
         const long long n_raw = tile * TC_PB + tid;
         const bool active = n_raw < a.N;
         const long long n = active ? n_raw : a.N - 1;   // tail lanes shadow the last particle (all 128 lanes take part in the MMA)
-        Key k = prng_key(a.seeds[n]);
-        Key ka;
-        split(k, ka, k);
+        constexpr bool ev = EV;   // mcd_utils.evolve entry: (z, rng_key_gen) given by the caller (mcd_utils.py:24-33), own instantiation
+        Key k, ka;
         float z[D], xi[D];
-        normal_vec<D>(ka, xi);
         float w = 0.f;
-        {   // z0 = sigma*xi + mu ; w = -log q(z0)   (vardist/diag_gauss.py:26-33,44-62)
+        if constexpr (ev) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) z[j] = a.z0[n * D + j];
+            ka.k0 = a.keys[2 * n]; ka.k1 = a.keys[2 * n + 1];
+        } else {   // z0 = sigma*xi + mu ; w = -log q(z0)   (vardist/diag_gauss.py:26-33,44-62)
+            k = prng_key(a.seeds[n]);
+            split(k, ka, k);
+            normal_vec<D>(ka, xi);
             float lq = 0.f;
 #pragma unroll
             for (int j = 0; j < D; ++j) {
@@ -330,8 +335,8 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
         }
         float sp[D], dummy[D];
         float lp = 0.f;
-        ka = split_first(k);    // mcdboundingmachine.py:162
-        k = split_second(ka);   // mcd_cais.py:94
+        if (!ev) ka = split_first(k);   // mcdboundingmachine.py:162 (evolve entry: ka is the caller's rng_key_gen)
+        k = split_second(ka);           // mcd_cais.py:94
         float wm = 0.f;
         // K + 1 nodes z_0 .. z_K, ONE network evaluation per node: in the CAIS modes NN(z_j, j) serves both the
         // backward-kernel mean of step j-1 (mcd_cais.py:78, called there as NN(z', i + 1)) and the forward-kernel mean of
@@ -418,7 +423,8 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
         w += wm;
         w += lp;
         if (active) {
-            a.out_negw[n] = -w;
+            // evolve returns the steps' log-ratio sum (mcd_cais.py:98-99); compute_log_elbo adds -log q(z_0) and log p(z_K)
+            a.out_negw[n] = ev ? wm : -w;
 #pragma unroll
             for (int j = 0; j < D; ++j) a.out_z[n * D + j] = z[j];
         }
@@ -430,10 +436,11 @@ __global__ void __launch_bounds__(TC_PB, TC_CTAS_PER_SM) bridge_fwd_tc_kernel(co
 
 template <int D, int ACT>
 static int launch_fwd_tc_t(const BridgeArgs& a_in, cudaStream_t st, int num_sms) {
+    const bool ev = a_in.z0 != nullptr;
     // request > 227/4 KB so that at most three CTAs (3 x 160 TMEM columns) share an SM
     size_t smem = 2 * TC_B_BYTES + TC_B16_BYTES + (2 * D * TC_H + 2 * TC_H * D + D * D + 4 + MIX_MAX * MIX_STRIDE + 2 * MIX_MAX + 4 * 4 * TC_H + 8) * sizeof(float);
     if (smem < 58 * 1024) smem = 58 * 1024;
-    auto kern = bridge_fwd_tc_kernel<D, ACT>;
+    auto kern = ev ? bridge_fwd_tc_kernel<D, ACT, true> : bridge_fwd_tc_kernel<D, ACT, false>;
     CMCD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // TMA bulk copies need 16-byte aligned rows; CMCD_TAB_TMA=0 keeps the per-warp cp.async staging (A/B runs)
     BridgeArgs a = a_in;

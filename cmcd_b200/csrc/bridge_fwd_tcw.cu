@@ -333,30 +333,36 @@ __global__ void __launch_bounds__(TW_THREADS, 1) bridge_fwd_tcw_kernel(const Bri
         const long long n = active ? n_raw : a.N - 1;   // tail lanes shadow the last particle (all 128 lanes take part in the MMA)
         // Roles besides the hidden units: group 0 = state of the particle (z, log-weight, kernel means); group 1 = its key chain and
         // Gaussians (independent of the trajectory); group 2 = target score at every node; group 3 = a third chunk of hidden units.
-        Key k = prng_key(a.seeds[n]);
-        Key ka;
-        split(k, ka, k);
+        const bool ev = a.z0 != nullptr;   // mcd_utils.evolve entry: (z, rng_key_gen) given by the caller (mcd_utils.py:24-33)
+        Key k, ka;
+        if (ev) { ka.k0 = a.keys[2 * n]; ka.k1 = a.keys[2 * n + 1]; }
+        else { k = prng_key(a.seeds[n]); split(k, ka, k); }
         float z[D], xi[D], x[D], mf[D];
         float w = 0.f, wm = 0.f, lp = 0.f;
         if (grp == 0) {
-            normal_vec<D>(ka, xi);
-            // z0 = sigma*xi + mu ; w = -log q(z0)   (vardist/diag_gauss.py:26-33,44-62)
-            float lq = 0.f;
+            if (ev) {
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
-                z[j] = sig[j] * xi[j] + mu[j];
-                const float v = (z[j] - mu[j]) / sig[j];
-                lq += -0.5f * v * v - logf(2.5066282746310002f * sig[j]);
-                x[j] = z[j]; mf[j] = 0.f;
+                for (int j = 0; j < D; ++j) z[j] = a.z0[n * D + j];
+            } else {   // z0 = sigma*xi + mu ; w = -log q(z0)   (vardist/diag_gauss.py:26-33,44-62)
+                normal_vec<D>(ka, xi);
+                float lq = 0.f;
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    z[j] = sig[j] * xi[j] + mu[j];
+                    const float v = (z[j] - mu[j]) / sig[j];
+                    lq += -0.5f * v * v - logf(2.5066282746310002f * sig[j]);
+                }
+                w = -lq;
             }
-            w = -lq;
+#pragma unroll
+            for (int j = 0; j < D; ++j) { x[j] = z[j]; mf[j] = 0.f; }
             if (a.traj && active) {
 #pragma unroll
                 for (int j = 0; j < D; ++j) a.traj[((size_t)0 * D + j) * a.N + n] = z[j];
             }
         }
-        ka = split_first(k);    // mcdboundingmachine.py:162
-        k = split_second(ka);   // mcd_cais.py:94      (advanced by group 1 only)
+        if (!ev) ka = split_first(k);   // mcdboundingmachine.py:162 (evolve entry: ka is the caller's rng_key_gen)
+        k = split_second(ka);           // mcd_cais.py:94      (advanced by group 1 only)
         float beta = 0.f, eps = 0.f, scale = 1.f;
         // K + 1 nodes z_0 .. z_K, ONE network evaluation per node (node form, see bridge_fwd_tc.cu)
         for (int nd = 0; nd <= K; ++nd) {
@@ -477,7 +483,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) bridge_fwd_tcw_kernel(const Bri
         if (grp == 0 && active) {
             w += wm;
             w += lp;
-            a.out_negw[n] = -w;
+            // evolve returns the steps' log-ratio sum (mcd_cais.py:98-99); compute_log_elbo adds -log q(z_0) and log p(z_K)
+            a.out_negw[n] = ev ? wm : -w;
 #pragma unroll
             for (int j = 0; j < D; ++j) a.out_z[n * D + j] = z[j];
         }

@@ -282,6 +282,11 @@ int cmcd_bridge_evolve(const cmcd_bridge_desc* desc, void* stream, const float* 
     if (a.N == 0) return 0;
     const int sms = num_sms();
     if (sms <= 0) { set_error("no CUDA device"); return 1; }
+    // same kernels as cmcd_bridge_fwd (the block-cooperative mapping has no evolve entry: one thread per particle instead)
+    if (fwd_tcw_supported(a, desc->dim) && !std::getenv("CMCD_DISABLE_TC"))
+        return launch_bridge_fwd_tcw(a, desc->dim, (cudaStream_t)stream, sms);
+    if (fwd_tc_supported(a, desc->dim) && !std::getenv("CMCD_DISABLE_TC"))
+        return launch_bridge_fwd_tc(a, desc->dim, (cudaStream_t)stream, sms);
     return launch_bridge_fwd(a, desc->dim, (cudaStream_t)stream, sms);
 }
 
