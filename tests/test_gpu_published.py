@@ -1,12 +1,14 @@
 """The one external pin the reference tree offers: train the README commands through the CUDA path (opt.run / opt.sample /
 log_final_losses) and compare the final ELBO / ln Z with the numbers printed in the reference's notebook
-(/root/reference/src/notebooks/plotting_rebuttal.ipynb:413-418 funnel, :554-559 and :1007-1012 gmm).
+(/root/reference/src/notebooks/plotting_rebuttal.ipynb:413-418 funnel, :554-559 and :1007-1012 gmm, :3500-3508 / :6392 lgcp).
 
 These are trained-model results from the authors' wandb sweeps (11 000 Adam iterations, 30 x n_samples evaluation), so they
 pin the whole chain -- seeds, bridge, adjoint, optimizer, estimators -- statistically, not per call: network initial values
 are drawn from the reference's distributions but not from its bit stream, and the ELBO of a trained model varies from run
 to run.  Tolerance: |ELBO - published| <= max(0.1, 4 x published std) and |ln Z - published| <= max(0.15, 3 x published
-std); additionally ln Z must sit within 0.3 of the true value 0 of these normalised targets.
+std); additionally ln Z must sit within 0.3 of the true value 0 of the normalised targets (funnel, gmm).  The lgcp run
+(README.md:63: MFVI pretraining 20 000 iterations + 37 500 bridge iterations at d = 1600, ~100 s on a B200) is the unnormalised Cox
+process posterior: ELBO 469.48 +- 0.25 and ln Z 491.06 +- 3.5 in the notebook.
 """
 import os
 import sys
@@ -19,7 +21,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["funnel", "gmm_readme"])
+@pytest.mark.parametrize("name", ["funnel", "gmm_readme", "lgcp"])
 def test_trained_elbo_lnz_match_reference_notebook(name):
     from train_published import RUNS
     from cmcd_b200 import experiment as E
@@ -31,5 +33,6 @@ def test_trained_elbo_lnz_match_reference_notebook(name):
           f"ln Z {res['final_ln_Z']:.4f} (published {pub['ln_Z']:.4f} +- {pub['ln_Z_std']:.3f})")
     assert abs(res["elbo_final"] - pub["elbo"]) <= max(0.1, 4 * pub["elbo_std"])
     assert abs(res["final_ln_Z"] - pub["ln_Z"]) <= max(0.15, 3 * pub["ln_Z_std"])
-    assert abs(res["final_ln_Z"]) < 0.3     # true ln Z = 0
+    if name != "lgcp":
+        assert abs(res["final_ln_Z"]) < 0.3     # true ln Z = 0
     assert res["losses"][-1] < res["losses"][0]
