@@ -301,6 +301,12 @@ static int run_gemm(cudaStream_t st, const float* X, int ldx, float shift, const
     return 0;
 }
 
+// One-block-per-particle kernels (N ~ 20 blocks on 148 SMs): their run time is one thread's serial walk over d / blockDim elements with
+// ~12 dependent-latency loads each, so the block is as wide as the register budget allows (d = 1600: 6.25 -> 1.6 elements per thread;
+// node kernel 33 -> 14 us, kernel means 19 -> 9-10 us, target finalize 10.5 -> 5.5 us).
+constexpr int WIDE_PB_MAX = 1024;
+static int wide_pb(int d) { return d >= 1024 ? 1024 : d >= 512 ? 512 : 256; }
+
 __device__ __forceinline__ float block_sum(float v, float* sh) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -321,7 +327,7 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 __device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
 
 // ---- init: keys, z0 = mu + sigma xi0, w0 = -log q(z0).  One block per particle. ---------------------------
-__global__ void __launch_bounds__(256) wide_init_kernel(const int32_t* seeds, int d, const float* mu, const float* logdiag,
+__global__ void __launch_bounds__(WIDE_PB_MAX) wide_init_kernel(const int32_t* seeds, int d, const float* mu, const float* logdiag,
                                                         float* z, float* w, uint32_t* keys, float* traj, long long N) {
     __shared__ float sh[32];
     const int n = blockIdx.x;
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(256) wide_init_kernel(const int32_t* seeds, in
 }
 
 // ---- target finalize: sp = -(K^-1 dv) + counts - a exp(x); lp = -0.5 dv.(K^-1 dv) + log_norm + sum(x c - a e^x) ----
-__global__ void __launch_bounds__(256) wide_target_fin_kernel(const float* __restrict__ part, int S, int N, int d,
+__global__ void __launch_bounds__(WIDE_PB_MAX) wide_target_fin_kernel(const float* __restrict__ part, int S, int N, int d,
                                                               const float* __restrict__ x, const float* __restrict__ counts,
                                                               float mu0, float log_norm, float area, float* sp, float* lp) {
     __shared__ float sh[32];
@@ -398,7 +404,7 @@ __global__ void wide_l2_fin_kernel(const float* __restrict__ part, int S, int N,
 
 // ---- forward-kernel mean + sample:  mf = z - eps uf - eps NN ; zn = mf + s xi ; fkterm kept per element ----
 // One block per particle.  NN output = out_scale * clamp(sum part3 + c3[t]).  Advances the key chain.
-__global__ void __launch_bounds__(256) wide_fwd_mean_kernel(const float* __restrict__ part3, int S, int N, int d,
+__global__ void __launch_bounds__(WIDE_PB_MAX) wide_fwd_mean_kernel(const float* __restrict__ part3, int S, int N, int d,
                                                             const float* __restrict__ c3t, float out_scale_v, const float* __restrict__ out_scale_dev, float out_clip,
                                                             int use_nn, const float* __restrict__ z, const float* __restrict__ sp,
                                                             const float* __restrict__ mu, const float* __restrict__ logdiag,
@@ -439,7 +445,7 @@ __global__ void __launch_bounds__(256) wide_fwd_mean_kernel(const float* __restr
 }
 
 // ---- backward-kernel mean + weight update:  mb = zn - eps ub + eps NN ; w += logN(z; mb, s) - logN(zn; mf, s) ----
-__global__ void __launch_bounds__(256) wide_bwd_mean_kernel(const float* __restrict__ part3, int S, int N, int d,
+__global__ void __launch_bounds__(WIDE_PB_MAX) wide_bwd_mean_kernel(const float* __restrict__ part3, int S, int N, int d,
                                                             const float* __restrict__ c3t, float out_scale_v, const float* __restrict__ out_scale_dev, float out_clip,
                                                             int use_nn, const float* __restrict__ z, const float* __restrict__ zn,
                                                             const float* __restrict__ mf, const float* __restrict__ spn,
@@ -542,7 +548,7 @@ int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
     const float skip = 1.f;
     int S = 1;
 
-    wide_init_kernel<<<(unsigned)N, 256, 0, st>>>(a.seeds, d, a.vd_mean, a.vd_logdiag, z, w, keys, a.traj, N);
+    wide_init_kernel<<<(unsigned)N, wide_pb(d), 0, st>>>(a.seeds, d, a.vd_mean, a.vd_logdiag, z, w, keys, a.traj, N);
     CMCD_CUDA_OK(cudaGetLastError());
     auto target_at = [&](const float* x) -> int {
         if (tg->kind == CMCD_TARGET_CALLBACK) {   // generic target: the caller's batched score, enqueued on the same stream
@@ -551,7 +557,7 @@ int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
         }
         if (as) { CMCD_CUDA_OK(cudaEventRecord(as->fork, st)); CMCD_CUDA_OK(cudaStreamWaitEvent(as->side, as->fork, 0)); }
         if (int rc = run_gemm(st_t, x, d, tg->lgcp_mu0, tg->lgcp_kinv, d, (int)N, d, d, num_sms, partT, &ST)) return rc;
-        wide_target_fin_kernel<<<(unsigned)N, 256, 0, st_t>>>(partT, ST, (int)N, d, x, tg->lgcp_counts, tg->lgcp_mu0,
+        wide_target_fin_kernel<<<(unsigned)N, wide_pb(d), 0, st_t>>>(partT, ST, (int)N, d, x, tg->lgcp_counts, tg->lgcp_mu0,
                                                               tg->lgcp_log_norm, tg->lgcp_bin_area, sp, lp);
         CMCD_CUDA_OK(cudaGetLastError());
         if (as) CMCD_CUDA_OK(cudaEventRecord(as->join, as->side));
@@ -581,7 +587,7 @@ int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
     if (nn_f && K > 0) { if (int rc = net_at(z, 0, &S3)) return rc; }   // ... while the network runs on the caller's stream
     if (int rc = target_join()) return rc;
     for (int i = 0; i < K; ++i) {
-        wide_fwd_mean_kernel<<<(unsigned)N, 256, 0, st>>>(part, S3, (int)N, d, has_net ? nv.c3 + (size_t)i * d : nullptr,
+        wide_fwd_mean_kernel<<<(unsigned)N, wide_pb(d), 0, st>>>(part, S3, (int)N, d, has_net ? nv.c3 + (size_t)i * d : nullptr,
                                                           nv.out_scale, nv.out_scale_dev, nv.out_clip, nn_f ? 1 : 0, z, sp, a.vd_mean, a.vd_logdiag,
                                                           a.betas, a.eps, i, a.clip_t, a.clip_q, keys, zn, mf,
                                                           a.traj ? a.traj + (size_t)(i + 1) * d * N : nullptr);
@@ -590,7 +596,7 @@ int launch_wide_fwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
         const int tb = cais ? i + 1 : i;
         if (nn_b) { if (int rc = net_at(zn, tb, &S3)) return rc; }
         if (int rc = target_join()) return rc;
-        wide_bwd_mean_kernel<<<(unsigned)N, 256, 0, st>>>(part, S3, (int)N, d, has_net ? nv.c3 + (size_t)tb * d : nullptr,
+        wide_bwd_mean_kernel<<<(unsigned)N, wide_pb(d), 0, st>>>(part, S3, (int)N, d, has_net ? nv.c3 + (size_t)tb * d : nullptr,
                                                           nv.out_scale, nv.out_scale_dev, nv.out_clip, nn_b ? 1 : 0, z, zn, mf, sp, a.vd_mean,
                                                           a.vd_logdiag, a.betas, a.eps, i, a.clip_t, a.clip_q, w);
         CMCD_CUDA_OK(cudaGetLastError());
@@ -820,7 +826,7 @@ struct WideNodeArgs {
     float out_scale, out_clip, clip_t, clip_q;
     const float* out_scale_dev;
 };
-__global__ void __launch_bounds__(256) wide_node_kernel(const WideNodeArgs a) {
+__global__ void __launch_bounds__(WIDE_PB_MAX) wide_node_kernel(const WideNodeArgs a) {
     __shared__ float sh[32];
     const int n = blockIdx.x;
     const bool hasB = a.j > 0, hasF = a.j < a.K;
@@ -1023,7 +1029,7 @@ int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
             return 0;
         }
         if (int rc = run_gemm(st_t, x, d, tg->lgcp_mu0, tg->lgcp_kinv, d, (int)N, d, d, num_sms, partT, &ST)) return rc;
-        wide_target_fin_kernel<<<(unsigned)N, 256, 0, st_t>>>(partT, ST, (int)N, d, x, tg->lgcp_counts, tg->lgcp_mu0,
+        wide_target_fin_kernel<<<(unsigned)N, wide_pb(d), 0, st_t>>>(partT, ST, (int)N, d, x, tg->lgcp_counts, tg->lgcp_mu0,
                                                               tg->lgcp_log_norm, tg->lgcp_bin_area, score, lp);
         CMCD_CUDA_OK(cudaGetLastError());
         return 0;
@@ -1086,7 +1092,7 @@ int launch_wide_bwd(const BridgeArgs& a, const cmcd_target* tg, int D, cudaStrea
         h.base = G; h.vo = voj; h.vm = vm; h.r = r; h.gmu_acc = gmu; h.gls_acc = gls; h.g_beta = gbeta_buf; h.g_eps = geps_buf; h.g_os = gos;
         h.S3 = S3; h.N = (int)N; h.d = d; h.j = j; h.K = K; h.pathwise = pathwise; h.use_nn = use_nn; h.nn_f = nn_f;
         h.out_scale = nv.out_scale; h.out_scale_dev = nv.out_scale_dev; h.out_clip = nv.out_clip; h.clip_t = a.clip_t; h.clip_q = a.clip_q;
-        wide_node_kernel<<<(unsigned)N, 256, 0, st>>>(h);
+        wide_node_kernel<<<(unsigned)N, wide_pb(d), 0, st>>>(h);
         CMCD_CUDA_OK(cudaGetLastError());
         // the Hessian-vector product K^-1 vm (side stream) overlaps the network pull-back (caller's stream)
         if (pathwise && !generic) {
