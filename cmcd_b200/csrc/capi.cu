@@ -21,7 +21,7 @@ void set_error(const char* fmt, ...) {
 int launch_bridge_fwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sms);
 bool fwd_tc_supported(const BridgeArgs& a, int D);
 int launch_bridge_fwd_tc(const BridgeArgs& a, int D, cudaStream_t st, int num_sms);
-bool fwd_tcw_supported(const BridgeArgs& a, int D);
+bool fwd_tcw_supported(const BridgeArgs& a, int D, int num_sms);
 int launch_bridge_fwd_tcw(const BridgeArgs& a, int D, cudaStream_t st, int num_sms);
 int launch_bridge_bwd(const BridgeArgs& a, int D, cudaStream_t st, int num_sms, const float* cot_negw,
                       float* g_vd_mean, float* g_vd_logdiag, float* g_betas, float* g_eps,
@@ -181,7 +181,7 @@ int cmcd_bridge_fwd(const cmcd_bridge_desc* desc, void* stream, const int32_t* s
     if (desc->mode == CMCD_MODE_UHA)
         return launch_bridge_uha_fwd(a, desc->dim, desc->lfsteps > 0 ? desc->lfsteps : 1, (cudaStream_t)stream, sms);
     // hidden width 64 and 129..144: tcgen05 tiles; other widths: FP32 FMA kernels.  CMCD_DISABLE_TC=1 forces the FP32 kernels (A/B runs).
-    if (fwd_tcw_supported(a, desc->dim) && !std::getenv("CMCD_DISABLE_TC"))
+    if (fwd_tcw_supported(a, desc->dim, sms) && !std::getenv("CMCD_DISABLE_TC"))
         return launch_bridge_fwd_tcw(a, desc->dim, (cudaStream_t)stream, sms);
     if (fwd_tc_supported(a, desc->dim) && !std::getenv("CMCD_DISABLE_TC"))
         return launch_bridge_fwd_tc(a, desc->dim, (cudaStream_t)stream, sms);
@@ -283,7 +283,7 @@ int cmcd_bridge_evolve(const cmcd_bridge_desc* desc, void* stream, const float* 
     const int sms = num_sms();
     if (sms <= 0) { set_error("no CUDA device"); return 1; }
     // same kernels as cmcd_bridge_fwd (the block-cooperative mapping has no evolve entry: one thread per particle instead)
-    if (fwd_tcw_supported(a, desc->dim) && !std::getenv("CMCD_DISABLE_TC"))
+    if (fwd_tcw_supported(a, desc->dim, sms) && !std::getenv("CMCD_DISABLE_TC"))
         return launch_bridge_fwd_tcw(a, desc->dim, (cudaStream_t)stream, sms);
     if (fwd_tc_supported(a, desc->dim) && !std::getenv("CMCD_DISABLE_TC"))
         return launch_bridge_fwd_tc(a, desc->dim, (cudaStream_t)stream, sms);

@@ -188,3 +188,26 @@ def test_wide_tensor_core_forward_matches_fp32_mapping(name, N, K, monkeypatch):
         assert not torch.equal(l_tc, l_fp), "CMCD_TC_WIDE=0 did not change the path"
     ok = (e_l < REL_TOL) & (e_z.reshape(len(e_l), -1).max(-1) < REL_TOL)
     assert ok.mean() >= (0.99 if N >= 100 else 1.0), (name, N, K, ok.mean(), e_l.max(), e_z.max())
+
+
+@pytest.mark.parametrize("name,N,K", [("C_manygmm_dds_small", 500, 16), ("C_manygmm_dds", 2000, 64), ("ULAsn_gmm_dds", 300, 8), ("rand_12", 310, 11),
+                                      ("C_manygmm_dds_small", 1, 3), ("C_manygmm_dds_small", 18944, 2)])
+def test_quad_tensor_core_forward_matches_one_thread_mapping(name, N, K, monkeypatch):
+    """hidden_pad 64 at d = 2 with at most one 128-particle tile per SM: the four-threads-per-particle tensor-core forward
+    (csrc/bridge_fwd_tcw.cu, HT = 64) against the one-thread-per-particle tensor-core kernel (CMCD_TC_QUAD=0,
+    csrc/bridge_fwd_tc.cu) -- same 3-pass product, same per-particle algebra, different summation order of the output layer."""
+    import test_gpu_random_configs  # noqa: F401  (registers the rand_* configurations)
+    _, _, _, pf_o, _, _ = oracle_problem(name, torch.float32, N=N, K=K)
+    c, target, dim, pf, unf, fixed = product_problem(name, pf_o, N=N, K=K)
+    seeds = torch.from_numpy(seeds_for(N))
+    kw = dict(eps_schedule=c["eps_schedule"], grad_clipping=c["clip"])
+    with torch.no_grad():
+        l_q, (z_q, _) = PM.compute_log_elbo(seeds, pf, unf, fixed, target, **kw)
+        monkeypatch.setenv("CMCD_TC_QUAD", "0")
+        l_1, (z_1, _) = PM.compute_log_elbo(seeds, pf, unf, fixed, target, **kw)
+    fin = torch.isfinite(l_1)
+    assert l_q.numel() == N and (torch.isfinite(l_q) == fin).all()
+    e_l = rel_err(l_q[fin].cpu(), l_1[fin].cpu())
+    e_z = rel_err(z_q[fin].cpu(), z_1[fin].cpu())
+    ok = (e_l < REL_TOL) & (e_z.reshape(len(e_l), -1).max(-1) < REL_TOL)
+    assert ok.mean() >= (0.99 if N >= 100 else 1.0), (name, N, K, ok.mean(), e_l.max(), e_z.max())
