@@ -1,23 +1,30 @@
-// Forward bridge kernel, tensor-core variant for the WIDE geffner net of README.md:30,34 (emb_dim 130 + d = 2 -> hidden_pad 136;
-// any hidden_pad in 129..144): layer 2 of the drift network as tcgen05 tiles of 128 particles x 144 x 144.
+// Forward bridge kernel, tensor-core variant with FOUR threads per particle, for the two cases in which one 128-particle tile has an
+// SM to itself:
+//   HT = 144  the WIDE geffner net of README.md:30,34 (emb_dim 130 + d = 2 -> hidden_pad 136; any hidden_pad in 129..144): layer 2 as
+//             tcgen05 tiles of 128 particles x 144 x 144 -- 203 KB of operand tiles (W2^T as tf32 hi, tf32 lo and bf16 hi) and 360 of the
+//             512 TMEM columns, so no second tile fits;
+//   HT = 64   hidden_pad 64 (dds, narrow geffner nets) with at most one tile per SM (README sizes, small shards of a sharded batch):
+//             the three-CTAs-per-SM kernel of bridge_fwd_tc.cu then has nothing to overlap.
 //
 // Same contract as bridge_fwd_kernel (bridge_fwd.cu) / bridge_fwd_tc_kernel (bridge_fwd_tc.cu): replaces
 // vmap(compute_log_elbo) (src/mcdboundingmachine.py:126-205) over src/mcd_cais.py:46-89 / src/mcd_cais_var.py:56-101 /
-// src/mcd_over_orig.py:18-55 with apply_fun_sn = the geffner net (src/nn.py:42-72) in table form (include/cmcd_b200.h, cmcd_net).
+// src/mcd_over_orig.py:18-55 with apply_fun_sn = the geffner net (src/nn.py:42-72) or PISNet (src/nn_dds.py:145-164) in table form
+// (include/cmcd_b200.h, cmcd_net); also serves cmcd_bridge_evolve (a.z0 / a.keys given).
 //
-// What differs from the 64-wide kernel, and why:
-//   * one CTA per SM (203 KB of operand tiles: W2^T as tf32 hi, tf32 lo and bf16 hi; 360 of the 512 TMEM columns), so no second tile
-//     is resident to hide latency, and a lone warp per scheduler issues at ~0.25 IPC through the activation chains.  The CTA
-//     therefore has 512 threads = FOUR threads per particle: group g (warps 4g .. 4g+3) owns the 16-unit chunks {0,1} / {2,3} /
-//     {4,5} / {6,7,8} of the 144 hidden units; group 0 also owns the per-particle algebra (keys, Gaussians, target score, kernel
-//     means, log-weights), which runs in the shadow of the MMA batch.  Warps w, w+4, w+8, w+12 address the same TMEM lane quarter;
-//     the four threads of a particle exchange the network input (group 0 -> others) and the partial output sums (others -> group 0,
-//     added in a fixed order) through shared memory with 128-thread named barriers.
-//   * the MMA batch (45 instructions per half of N, ~3.4k cycles of tensor pipe) would be exposed between layer 1 and the epilogue,
-//     so it is issued in two K stages (stage 0 as soon as every group has stored its first chunk(s): {0,2,4,6,7}; stage 1: {1,3,5,8})
-//     and committed per half of N (columns 0..63 for groups 0-1 first, 64..143 for groups 2-3).
-//   * the per-step table rows (544 B each) arrive by TMA bulk copy into a CTA-wide double buffer.
-// Precision scheme as in the 64-wide kernel: D = A_hi B_lo + A_lo B_hi + A_hi B_hi with A_hi / B_hi / B_lo tf32 and A_lo bf16.
+// What differs from bridge_fwd_tc.cu, and why:
+//   * with one tile per SM a lone warp per scheduler walks the activation chains at ~0.25 IPC.  The CTA therefore has 512 threads:
+//     group g (warps 4g .. 4g+3) owns the 16-unit chunks {0,1} / {2,3} / {4,5} / {6,7,8} of the 144 hidden units (HT = 64: chunk g).
+//     Warps w, w+4, w+8, w+12 address the same TMEM lane quarter, so all four threads of a particle store into / read from its lane.
+//     The per-particle algebra is spread too -- on one thread it was the critical path once the network was split: group 0 keeps the
+//     particle's state (z, kernel means, log-weight), group 1 runs the key chain and the Gaussians (independent of the trajectory),
+//     group 2 evaluates the target score at every node.  The four exchange the network input (group 0 -> others), the partial
+//     output sums (others -> group 0, added in a fixed order), xi and (score, log p) through shared memory with two 128-thread
+//     named barriers per node.
+//   * HT = 144: the MMA batch (45 instructions per half of N, ~3.4k cycles of tensor pipe) would be exposed between layer 1 and the
+//     epilogue, so it is issued in two K stages (stage 0 as soon as every group has stored its first chunk(s): {0,2,4,6,7}; stage 1:
+//     {1,3,5,8}) and committed per half of N (columns 0..63 for groups 0-1 first, 64..143 for groups 2-3).  HT = 64: one stage of 20.
+//   * the per-step table rows arrive by TMA bulk copy into a CTA-wide double buffer.
+// Precision scheme as in bridge_fwd_tc.cu: D = A_hi B_lo + A_lo B_hi + A_hi B_hi with A_hi / B_hi / B_lo tf32 and A_lo bf16.
 #include <cuda_bf16.h>
 
 #include <cstdlib>
