@@ -403,15 +403,42 @@ __global__ void __launch_bounds__(TW_THREADS, 1) bridge_fwd_tcw_kernel(const Bri
         if (!ev) ka = split_first(k);   // mcdboundingmachine.py:162 (evolve entry: ka is the caller's rng_key_gen)
         k = split_second(ka);           // mcd_cais.py:94      (advanced by group 1 only)
         float beta = 0.f, eps = 0.f, scale = 1.f;
+        // Group 0's serial section between the two barriers of consecutive nodes is on every thread's critical path, so only what
+        // the next node's input needs stays there (combine, kernel mean, sample); the log-weight update of the step just closed
+        // (two Gaussian log-densities, a logf, the trajectory store) is parked in these registers and done in the next node's
+        // MMA shadow (or after the last node).
+        bool pend = false;
+        int pend_nd = 0;
+        float pw_x[D], pw_z[D], pw_mf[D], pw_nn[D], pw_gu[D], pw_gq[D], pw_beta = 0.f, pw_eps = 0.f, pw_scale = 1.f;
+        auto weight_update = [&]() {   // backward kernel of step pend_nd - 1, weight update (statement order of bridge_fwd_tc_kernel)
+            float mb[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const float ub = -(pw_beta * pw_gu[j] + (1.0f - pw_beta) * pw_gq[j]);
+                mb[j] = pw_x[j] - pw_eps * ub;
+                mb[j] = mb[j] + pw_eps * pw_nn[j];
+            }
+            const float lognorm = logf(2.5066282746310002f * pw_scale);
+            const float fk = tw_gauss_logprob<D>(pw_x, pw_mf, pw_scale, lognorm);
+            const float bk = tw_gauss_logprob<D>(pw_z, mb, pw_scale, lognorm);
+            wm += bk - fk;
+            if (a.traj && active) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) a.traj[((size_t)pend_nd * D + j) * a.N + n] = pw_x[j];
+            }
+            pend = false;
+        };
         // K + 1 nodes z_0 .. z_K, ONE network evaluation per node (node form, see bridge_fwd_tc.cu)
         for (int nd = 0; nd <= K; ++nd) {
             const int t = t0 + nd;
             const bool use_nn = cais || nd > 0;
             f32x2_t acc[D];
             float c3v[D];
+            float bnx = 0.f, enx = 0.f;   // step constants of this node's forward kernel, requested before layer 1
             if (grp == 0) {
 #pragma unroll
                 for (int j = 0; j < D; ++j) sX[pl * D + j] = x[j];
+                if (nd < K) { bnx = __ldg(a.betas + nd); enx = __ldg(a.eps + nd); }
                 if (use_nn) {
 #pragma unroll
                     for (int m = 0; m < D; ++m) c3v[m] = __ldg(cx.c3 + (size_t)t * D + m);   // requested before layer 1, used after it
@@ -434,6 +461,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) bridge_fwd_tcw_kernel(const Bri
                     const float sq = -((x[j] - mu[j]) / sig[j]) / sig[j];
                     gq[j] = fminf(fmaxf(sq, -a.clip_q), a.clip_q);
                 }
+                if (pend) weight_update();
                 if (use_nn) {
                     // out = out_scale * clamp(W3^T (a2 + a1) + U3^T x + c3[t]): the terms outside the hidden units
 #pragma unroll
@@ -488,27 +516,18 @@ __global__ void __launch_bounds__(TW_THREADS, 1) bridge_fwd_tcw_kernel(const Bri
                 if (nd < K) xi[m] = sXi[pl * D + m];
             }
             lp = sSp[pl * (D + 1) + D];
-            if (nd > 0) {   // backward kernel of step nd - 1 (beta, eps, scale, mf still hold that step's values), weight update
-                float mb[D];
+            if (nd > 0) {   // the step nd - 1 just closed: park its log-weight update (beta, eps, scale, mf still hold that step's values)
+                pend = true; pend_nd = nd; pw_beta = beta; pw_eps = eps; pw_scale = scale;
 #pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    const float ub = -(beta * gu[j] + (1.0f - beta) * gq[j]);
-                    mb[j] = x[j] - eps * ub;
-                    mb[j] = mb[j] + eps * nnv[j];
-                }
-                const float lognorm = logf(2.5066282746310002f * scale);
-                const float fk = tw_gauss_logprob<D>(x, mf, scale, lognorm);
-                const float bk = tw_gauss_logprob<D>(z, mb, scale, lognorm);
-                wm += bk - fk;
+                for (int j = 0; j < D; ++j) { pw_x[j] = x[j]; pw_z[j] = z[j]; pw_mf[j] = mf[j]; pw_nn[j] = nnv[j]; pw_gu[j] = gu[j]; pw_gq[j] = gq[j]; }
 #pragma unroll
                 for (int j = 0; j < D; ++j) z[j] = x[j];
-                if (a.traj && active) {
-#pragma unroll
-                    for (int j = 0; j < D; ++j) a.traj[((size_t)nd * D + j) * a.N + n] = z[j];
-                }
+                // (144-wide tiles: group 3's three chunks are the critical path, not this section -- measured 1.62 vs 1.65 ms --
+                //  and the parked state costs the registers the epilogue needs: update in place)
+                if constexpr (HT == 144) weight_update();
             }
             if (nd < K) {   // forward kernel of step nd: mean, sample z_{nd+1}
-                beta = __ldg(a.betas + nd); eps = __ldg(a.eps + nd);
+                beta = bnx; eps = enx;
                 scale = sqrtf(2.0f * eps);
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
@@ -519,6 +538,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) bridge_fwd_tcw_kernel(const Bri
                 }
             }
         }
+        if (grp == 0 && pend) weight_update();
         if (grp == 0 && active) {
             w += wm;
             w += lp;
