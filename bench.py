@@ -193,6 +193,53 @@ def cpu_baseline_sample():
             "variants_particle_steps_per_s": variants, "note": CPU_VARIANT_NOTE}
 
 
+# The other BASELINE.json configurations at the sizes the README commands use: secondary numbers of the
+# default single-GPU run, measured through the same public API (grad_and_loss / compute_bound) with CUDA events, median of 7.
+README_CONFIGS = {
+    "gmm (README.md:73)": dict(model="gmm", mode="MCD_CAIS_sn", N=300, K=8, nn_arch="geffner", emb_dim=20, eps=0.01, sigma=1.0,
+                                eps_schedule=None, clip=False, trainable=("eta", "gamma", "vd", "mgridref_y")),
+    "funnel (README.md:53)": dict(model="funnel", mode="MCD_CAIS_sn", N=300, K=8, nn_arch="geffner", emb_dim=48, eps=0.1, sigma=1.0,
+                                   eps_schedule="cos_sq", clip=False, trainable=("eta", "gamma", "vd", "mgridref_y")),
+    "40-GMM dds (README.md:26)": dict(model="many_gmm", mode="MCD_CAIS_sn", N=2000, K=256, nn_arch="dds", emb_dim=20, eps=1.0, sigma=60.0,
+                                       eps_schedule="cos_sq", clip=True, trainable=("eta", "gamma", "mgridref_y")),
+    "40-GMM geffner log-variance (README.md:30)": dict(model="many_gmm", mode="MCD_CAIS_var_sn", N=2000, K=256, nn_arch="geffner", emb_dim=130,
+                                                        eps=0.65, sigma=15.0, eps_schedule=None, clip=True, trainable=("eta", "gamma", "mgridref_y")),
+    "40-GMM geffner KL (README.md:34)": dict(model="many_gmm", mode="MCD_CAIS_sn", N=2000, K=256, nn_arch="geffner", emb_dim=130, eps=0.1,
+                                              sigma=15.0, eps_schedule=None, clip=True, trainable=("eta", "gamma", "mgridref_y")),
+    "lgcp (README.md:63)": dict(model="lgcp", mode="MCD_CAIS_sn", N=20, K=8, nn_arch="geffner", emb_dim=20, eps=1e-3, sigma=0.3,
+                                 eps_schedule=None, clip=False, trainable=("eta", "gamma", "eps", "vd", "mgridref_y")),
+}
+
+
+def readme_config_times(dev, reps=7):
+    from cmcd_b200 import mcdboundingmachine as PM
+    from cmcd_b200 import model_handler as PH
+    from cmcd_b200 import variationaldist as PV
+
+    def med(fn):
+        for _ in range(3):
+            fn()
+        ts = sorted(_event_ms(fn, dev) for _ in range(reps))
+        return ts[len(ts) // 2]
+
+    rows = {}
+    for name, c in README_CONFIGS.items():
+        target, dim = PH.load_model(c["model"], device=dev)[:2]
+        pf, unf, fixed = PM.initialize(dim, vdparams=PV.initialize(dim, c["sigma"], device=dev), nbridges=c["K"], eps=c["eps"],
+                                       trainable=c["trainable"], emb_dim=c["emb_dim"], mode=c["mode"], nn_arch=c["nn_arch"], device=dev)
+        kw = dict(eps_schedule=c["eps_schedule"], grad_clipping=c["clip"])
+        bound = PM.compute_bound_var if c["mode"] == "MCD_CAIS_var_sn" else PM.compute_bound
+        gl = PM.grad_and_loss(lambda *a: bound(*a, **kw))
+        seeds = torch.from_numpy(np.random.default_rng(7).integers(1, 10**6, c["N"]).astype(np.int32)).to(dev)
+        t_train = med(lambda: gl(seeds, pf, unf, fixed, target))
+        with torch.no_grad():
+            t_fwd = med(lambda: bound(seeds, pf, unf, fixed, target, **kw))
+        rows[name] = {"N": c["N"], "nbridges": c["K"], "dim": dim, "nn_arch": c["nn_arch"], "boundmode": c["mode"],
+                      "train_iter_ms": round(t_train, 3), "sampling_pass_ms": round(t_fwd, 3),
+                      "train_particle_steps_per_s": round(c["N"] * c["K"] / t_train * 1e3, 1)}
+    return rows
+
+
 def _event_ms(fn, dev):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -213,6 +260,7 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="also time N_global = 2^16 .. 2^20 (strong scaling table)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured per-rank step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-readme-configs", action="store_true", help="skip the secondary README-size timings of the single-GPU run")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -455,6 +503,10 @@ def main():
             out["weak_scaling"] = weak
         if sweep is not None:
             out["sweep"] = sweep
+        if world == 1 and not args.no_readme_configs:
+            out["readme_configs"] = {"what": "device time of one eager train iteration / one sampling pass of the other BASELINE.json "
+                                             "configurations at their README sizes (synthetic, random-init network)",
+                                     "rows": readme_config_times(dev)}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample()
         emit(out)
