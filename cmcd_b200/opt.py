@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .model_handler import _threefry2x32
+from .model_handler import Target, _threefry2x32
 
 _PROJECT_BOUNDS = {"eps": (0.0000001, 0.5), "eta": (0.0, 0.99), "gamma": (0.001, float("inf")),
                    "mgridref_y": (0.001, float("inf"))}   # relu(x - 0.001) + 0.001 == max(x, 0.001)  (opt.py:22-23)
@@ -161,6 +161,13 @@ def sample(info, n_samples, n_input_dist_seeds, params_flat, unflatten, params_f
     dev = params_flat.device
     eval_seeds = randint_seeds(rng_key_gen, n_samples * n_input_dist_seeds, 1, 10**6, device=dev)
     elbos, zs = [], []
+    # Every particle's result depends on its own seed only, so the small-d targets take all seed batches in ONE pass (one table
+    # chain, one bridge launch with n_input_dist_seeds x n_samples particles instead of 30 latency-bound launches); the wide path
+    # (lgcp, callback targets: workspace proportional to the batch) keeps the reference's loop.
+    if isinstance(log_prob_model, Target) and log_prob_model.kind != "lgcp":
+        with torch.no_grad():
+            _, (loss_list, z) = loss_fn(eval_seeds, params_flat, unflatten, params_fixed, log_prob_model)
+        return loss_list.reshape(n_input_dist_seeds, n_samples), z
     with torch.no_grad():
         for i in range(n_input_dist_seeds):
             seeds = eval_seeds[i * n_samples:(i + 1) * n_samples]
