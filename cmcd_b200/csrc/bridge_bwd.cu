@@ -236,6 +236,10 @@ static int launch_bwd_d(const BridgeArgs& a, cudaStream_t st, int num_sms, const
     // (17 broadcast LDS.128 per 68 FMAs instead of 2 per 8 with the generic JC = 8 chunks)
     if (HP == 136) return launch_bwd_t<D, ACT_SOFTPLUS, 136, 68, 64>(a, st, num_sms, cot, out, ws, ws_bytes);
     if (HP < 64) return launch_bwd_t<D, ACT_SOFTPLUS, 0, 8, BIG>(a, st, num_sms, cot, out, ws, ws_bytes);
+    // wide nets at d = 10 (e.g. funnel with emb_dim ~140: hidden_pad 152): W2 plus three [HP][64 + 4] activation arrays pass 227 KB;
+    // 32 particles per block fit up to hidden_pad ~190
+    if (bwd_smem_bytes<D, ACT_SOFTPLUS, 0, 8, 64>(HP, true) > 227 * 1024)
+        return launch_bwd_t<D, ACT_SOFTPLUS, 0, 8, 32>(a, st, num_sms, cot, out, ws, ws_bytes);
     return launch_bwd_t<D, ACT_SOFTPLUS, 0, 8, 64>(a, st, num_sms, cot, out, ws, ws_bytes);
 }
 

@@ -41,6 +41,10 @@ RANDOM["rand_16"] = dict(model="gmm", mode="MCD_CAIS_sn", nn_arch="geffner", emb
                          eps_schedule="cos_sq", clip=True, trainable=TRAINABLE[1])
 RANDOM["rand_17"] = dict(model="gmm", mode="MCD_ULA_sn", nn_arch="geffner", emb_dim=142, N=300, K=5, eps=0.03, sigma=0.9,
                          eps_schedule="linear", clip=False, trainable=TRAINABLE[2])
+# funnel (d = 10) with a wide time embedding: hidden_pad 152 -- the FP32 adjoint then takes 32 particles per block (found by a larger
+# throw-away sweep: the 64-particle blocks need 242 KB of shared memory there)
+RANDOM["rand_18"] = dict(model="funnel", mode="MCD_CAIS_sn", nn_arch="geffner", emb_dim=138, N=201, K=2, eps=0.01, sigma=0.95,
+                         eps_schedule="linear", clip=False, trainable=TRAINABLE[1])
 helpers.CONFIGS.update(RANDOM)
 
 
