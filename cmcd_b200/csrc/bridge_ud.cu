@@ -58,8 +58,8 @@ __device__ __forceinline__ float ud_gauss_logprob(const float (&x)[D], const flo
 }
 
 // DI: 0 = no network, D = network on z, 2D = network on (z, rho')
-template <int D, int ACT, int HPT, int JC, int DI>
-__global__ void __launch_bounds__(UD_FWD_PB, (HPT > 64 ? 1 : 2)) bridge_ud_fwd_kernel(const BridgeArgs a) {
+template <int D, int ACT, int HPT, int JC, int DI, int PB = UD_FWD_PB>
+__global__ void __launch_bounds__(PB, (HPT > 64 ? 1 : 2)) bridge_ud_fwd_kernel(const BridgeArgs a) {
     constexpr int DIN = DI ? DI : D;
     extern __shared__ float4 smem4[];
     float* sm = reinterpret_cast<float*>(smem4);
@@ -81,9 +81,9 @@ __global__ void __launch_bounds__(UD_FWD_PB, (HPT > 64 ? 1 : 2)) bridge_ud_fwd_k
 #pragma unroll
     for (int j = 0; j < D; ++j) { mu[j] = a.vd_mean[j]; sig[j] = expf(a.vd_logdiag[j]); }
 
-    const long long ntiles = (a.N + UD_FWD_PB - 1) / UD_FWD_PB;
+    const long long ntiles = (a.N + PB - 1) / PB;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long n = tile * UD_FWD_PB + tid;
+        const long long n = tile * PB + tid;
         if (n >= a.N) continue;
         Key k = prng_key(a.seeds[n]);
         Key ka;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(UD_FWD_PB, (HPT > 64 ? 1 : 2)) bridge_ud_fwd_k
                         float x[DIN];
 #pragma unroll
                         for (int j = 0; j < D; ++j) { x[j] = z[j]; x[D + j] = rho[j]; }
-                        net_fwd<D, ACT, HPT, JC, UD_FWD_PB, DIN>(nv, ns, i, x, nnf, a1col);
+                        net_fwd<D, ACT, HPT, JC, PB, DIN>(nv, ns, i, x, nnf, a1col);
                     }
                 }
                 step_keys_and_normal<D>(g, xi);   // :31-32 and :59
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(UD_FWD_PB, (HPT > 64 ? 1 : 2)) bridge_ud_fwd_k
                             x[j] = z[j];
                             if constexpr (DIN > D) x[D + j] = rp[j];
                         }
-                        net_fwd<D, ACT, HPT, JC, UD_FWD_PB, DIN>(nv, ns, i, x, nnv, a1col);
+                        net_fwd<D, ACT, HPT, JC, PB, DIN>(nv, ns, i, x, nnv, a1col);
 #pragma unroll
                         for (int j = 0; j < D; ++j) mb[j] = mb[j] + cn * nnv[j];
                     }
@@ -412,24 +412,27 @@ __global__ void __launch_bounds__(BPB, 1) bridge_ud_bwd_kernel(const BridgeArgs 
 
 // ---------------------------------------------------------------------------------------------------------------- launchers
 
-template <int D, int ACT, int HPT, int JC, int DI>
+template <int D, int ACT, int HPT, int JC, int DI, int PB = UD_FWD_PB>
 static int launch_ud_fwd_t(const BridgeArgs& a, cudaStream_t st, int num_sms) {
     constexpr int DIN = DI ? DI : D;
     const int HP = a.net.HP;
     const bool has_net = DI != 0;
-    size_t fl = (has_net ? net_smem_floats(D, HP, DIN) + (size_t)HP * UD_FWD_PB : 0) + MIX_MAX * MIX_STRIDE + 8;
+    size_t fl = (has_net ? net_smem_floats(D, HP, DIN) + (size_t)HP * PB : 0) + MIX_MAX * MIX_STRIDE + 8;
     const size_t smem = fl * sizeof(float);
-    auto kern = bridge_ud_fwd_kernel<D, ACT, HPT, JC, DI>;
+    if constexpr (PB > 32 && HPT == 0 && ACT == ACT_SOFTPLUS) {   // wide (z, rho) nets (funnel, emb_dim ~140: hidden_pad 168): 32 particles per block
+        if (smem > 227 * 1024) return launch_ud_fwd_t<D, ACT, HPT, JC, DI, 32>(a, st, num_sms);
+    }
+    auto kern = bridge_ud_fwd_kernel<D, ACT, HPT, JC, DI, PB>;
     if (smem > 227 * 1024) { set_error("bridge_ud_fwd: hidden_pad=%d needs %zu B shared memory (> 227 KB)", HP, smem); return 2; }
     CMCD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CMCD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, UD_FWD_PB, smem));
+    CMCD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PB, smem));
     if (occ < 1) { set_error("bridge_ud_fwd: kernel does not fit on an SM"); return 2; }
-    const long long ntiles = (a.N + UD_FWD_PB - 1) / UD_FWD_PB;
+    const long long ntiles = (a.N + PB - 1) / PB;
     long long grid = (long long)num_sms * occ;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, UD_FWD_PB, smem, st>>>(a);
+    kern<<<(unsigned)grid, PB, smem, st>>>(a);
     CMCD_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -500,6 +503,12 @@ static int launch_ud_bwd_n(const BridgeArgs& a, cudaStream_t st, int num_sms, co
             if (a.net.HP == 64) return launch_ud_bwd_t<D, ACT_GELU, 64, 64, 128, DI>(a, st, num_sms, cot, out, ws, ws_bytes);
             return launch_ud_bwd_t<D, ACT_GELU, 0, 8, 64, DI>(a, st, num_sms, cot, out, ws, ws_bytes);
         }
+        // wide nets (funnel with emb_dim ~130: the (z, rho) network has hidden_pad 152): W2 plus three [HP][64 + 4] activation arrays pass
+        // 227 KB; 32 particles per block fit
+        constexpr int DIN = DI ? DI : D;
+        const size_t fl64 = net_smem_floats(D, a.net.HP, DIN) + 3 * (size_t)a.net.HP * 68 + MIX_MAX * MIX_STRIDE + (size_t)(DIN + D) * 68 + 8;
+        if (fl64 * sizeof(float) > 227 * 1024)
+            return launch_ud_bwd_t<D, ACT_SOFTPLUS, 0, 8, 32, DI>(a, st, num_sms, cot, out, ws, ws_bytes);
         return launch_ud_bwd_t<D, ACT_SOFTPLUS, 0, 8, 64, DI>(a, st, num_sms, cot, out, ws, ws_bytes);
     }
 }

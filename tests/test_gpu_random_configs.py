@@ -45,6 +45,11 @@ RANDOM["rand_17"] = dict(model="gmm", mode="MCD_ULA_sn", nn_arch="geffner", emb_
 # throw-away sweep: the 64-particle blocks need 242 KB of shared memory there)
 RANDOM["rand_18"] = dict(model="funnel", mode="MCD_CAIS_sn", nn_arch="geffner", emb_dim=138, N=201, K=2, eps=0.01, sigma=0.95,
                          eps_schedule="linear", clip=False, trainable=TRAINABLE[1])
+# the same for the underdamped operators, whose network sees (z, rho): hidden_pad 152 (adjoint) and 168 (forward too) at d = 10
+RANDOM["rand_19"] = dict(model="funnel", mode="MCD_U_a-lp-sn", nn_arch="geffner", emb_dim=130, N=150, K=3, eps=0.02, sigma=1.0, gamma=5.0,
+                         eps_schedule=None, clip=False, trainable=TRAINABLE[2])
+RANDOM["rand_20"] = dict(model="funnel", mode="MCD_CAIS_UHA_sn", nn_arch="geffner", emb_dim=142, N=97, K=3, eps=0.02, sigma=1.0, gamma=5.0,
+                         eps_schedule=None, clip=False, trainable=TRAINABLE[2])
 helpers.CONFIGS.update(RANDOM)
 
 
