@@ -37,6 +37,13 @@ RUNS = {
                                 pretrain_mfvi=False, train_vi=True, train_eps=False, lr=0.001, n_samples=500),
                        published=dict(elbo=-1.185452, elbo_std=0.041783, ln_Z=0.001775, ln_Z_std=0.101838,
                                       src="plotting_rebuttal.ipynb:1007 (second sweep cais/24wsukx8, K=8, init_eps 0.1)")),
+    # README.md:26 (the headline configuration of BASELINE.json at its own size).  No trained-model numbers in the tree (wandb links only);
+    # the 40-GMM is a normalised mixture, so the TRUE ln Z is 0 -- an analytic pin of the whole chain at K = 256 with the dds net.
+    "many_gmm_dds": dict(cfg=dict(boundmode="MCD_CAIS_sn", model="many_gmm", N=2000, nbridges=256, nn_arch="dds", init_eps=1.0, init_sigma=60.0,
+                                  iters=150000, pretrain_mfvi=False, train_vi=False, train_eps=False, lr=0.001, n_samples=500,
+                                  eps_schedule="cos_sq", grad_clipping=True),
+                         published=dict(elbo=None, elbo_std=None, ln_Z=0.0, ln_Z_std=None,
+                                        src="README.md:26 command; analytic ln Z = 0 of the normalised mixture (no published ELBO in the tree)")),
     "lgcp": dict(cfg=dict(boundmode="MCD_CAIS_sn", model="lgcp", N=20, emb_dim=20, init_eps=0.00001, init_sigma=1.0, iters=37500,
                           pretrain_mfvi=True, train_vi=True, train_eps=True, lr=0.0001, n_samples=500, mfvi_iters=20000),
                  published=dict(elbo=469.48, elbo_std=0.25, ln_Z=491.06, ln_Z_std=3.5,
