@@ -44,6 +44,15 @@ RUNS = {
                                   eps_schedule="cos_sq", grad_clipping=True),
                          published=dict(elbo=None, elbo_std=None, ln_Z=0.0, ln_Z_std=None,
                                         src="README.md:26 command; analytic ln Z = 0 of the normalised mixture (no published ELBO in the tree)")),
+    # README.md:30 / :34: the geffner (emb_dim 130) log-variance and KL commands; same analytic pin
+    "many_gmm_logvar": dict(cfg=dict(boundmode="MCD_CAIS_var_sn", model="many_gmm", N=2000, nbridges=256, nn_arch="geffner", emb_dim=130, init_eps=0.65,
+                                     init_sigma=15.0, iters=150000, pretrain_mfvi=False, train_vi=False, train_eps=False, lr=0.005, n_samples=500,
+                                     grad_clipping=True),
+                            published=dict(elbo=None, elbo_std=None, ln_Z=0.0, ln_Z_std=None, src="README.md:30 command; analytic ln Z = 0")),
+    "many_gmm_kl": dict(cfg=dict(boundmode="MCD_CAIS_sn", model="many_gmm", N=2000, nbridges=256, nn_arch="geffner", emb_dim=130, init_eps=0.1,
+                                 init_sigma=15.0, iters=150000, pretrain_mfvi=False, train_vi=False, train_eps=False, lr=0.005, n_samples=500,
+                                 grad_clipping=True),
+                        published=dict(elbo=None, elbo_std=None, ln_Z=0.0, ln_Z_std=None, src="README.md:34 command; analytic ln Z = 0")),
     "lgcp": dict(cfg=dict(boundmode="MCD_CAIS_sn", model="lgcp", N=20, emb_dim=20, init_eps=0.00001, init_sigma=1.0, iters=37500,
                           pretrain_mfvi=True, train_vi=True, train_eps=True, lr=0.0001, n_samples=500, mfvi_iters=20000),
                  published=dict(elbo=469.48, elbo_std=0.25, ln_Z=491.06, ln_Z_std=3.5,
