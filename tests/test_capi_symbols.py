@@ -61,6 +61,13 @@ def test_product_does_not_import_oracle():
                 assert "import oracle" not in s and "from oracle" not in s, f
 
 
+def test_every_kernel_source_is_built():
+    """Every .cu / .cc under csrc/ is in the build list (a source left out would silently drop its entry points' kernels)."""
+    from cmcd_b200 import build as B
+    on_disk = {f for f in os.listdir(B.CSRC) if f.endswith((".cu", ".cc"))}
+    assert on_disk == set(B.SOURCES), (sorted(on_disk - set(B.SOURCES)), sorted(set(B.SOURCES) - on_disk))
+
+
 def test_xla_ffi_shim_compiles_against_stub():
     """cmcd_b200/csrc/xla_ffi.cc (the jax.ffi custom-call handlers) cannot be built against jaxlib here; a header-only stub of
     the public xla/ffi/api/ffi.h surface it uses (tests/xla_ffi_stub) makes the compiler check that every handler's Ctx / Arg /
